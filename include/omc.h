@@ -1,0 +1,126 @@
+/* libomc — C ABI of the B200-native openMCMC hot path.
+ *
+ * The reference (sede-open/openMCMC, pure Python) has no FFI boundary; its seam is the duck-typed sampler / model
+ * interface that mcmc.MCMC calls.  This header is the boundary a maintainer would bind from
+ * Python (ctypes stub in INTEGRATION.md): every entry point below names the reference code it replaces as
+ * `ref: <file>:<lines>` relative to /root/reference/src/openmcmc/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all reals are float64 (the reference is fp64)
+ *   - `void* stream` is a cudaStream_t (0 = legacy default stream); every call is asynchronous on that stream
+ *   - omc_vec_t = per-chain operand: element c lives at ptr + c*chain_stride; chain_stride 0 = shared by all chains;
+ *     ptr NULL = the documented default
+ *   - return 0 = ok, <0 = argument / plan error, >0 = cudaError_t; text via omc_last_error() (thread local)
+ *   - numerical failures never abort a batch: they set bits in the per-chain `status` word (OMC_STATUS_*)
+ *   - ownership: the caller owns every buffer; the library owns only what omc_*_create returns
+ */
+#ifndef OMC_H
+#define OMC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMC_ABI_VERSION 1
+#define OMC_STATUS_NOT_PD 1          /* Cholesky pivot <= 0 (reference: LinAlgError from np.linalg.cholesky) */
+#define OMC_STATUS_NAN 2             /* NaN/inf in log-density or gradient (reference F6: crash)               */
+#define OMC_STATUS_OUT_OF_SUPPORT 4  /* proposal outside the support                                          */
+
+typedef struct {
+  const double* ptr;
+  long long chain_stride;
+} omc_vec_t;
+
+/* Counter-based RNG site (Philox4x32-10).  Replaces the reference's global numpy RandomState reached through
+ * scipy.stats.*.rvs.  Draw = f(seed, sweep counter, global chain id, site, position). */
+typedef struct {
+  unsigned long long seed;
+  const unsigned long long* sweep; /* device counter, bumped once per sweep (omc_counter_add); NULL = 0 */
+  unsigned int chain_offset;       /* global id of local chain 0 (multi-GPU sharding)                  */
+  unsigned int site;               /* one id per sampler in the plan                                    */
+} omc_rng_t;
+
+/* ------------------------------------------------------------------ library / device */
+int omc_abi_version(void);
+const char* omc_last_error(void);
+int omc_device_init(int device);          /* cudaSetDevice + attribute cache; must precede everything else */
+int omc_device_sm_count(void);
+int omc_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
+
+/* ------------------------------------------------------------------ sweep execution (ref: mcmc.py:87-111)
+ * A sweep is recorded once as a CUDA graph (capture between begin/end on `stream`, calling the op entry points
+ * below) and replayed by omc_run_schedule with the reference's iteration numbering: (n_burn+n_iter) outer
+ * iterations of n_thin sweeps; after each non-burn iteration the `store` graph runs once. */
+typedef struct omc_graph omc_graph_t;
+int omc_graph_capture_begin(void* stream);
+int omc_graph_capture_end(void* stream, omc_graph_t** out);
+int omc_graph_launch(omc_graph_t* g, void* stream, long long times);
+int omc_graph_destroy(omc_graph_t* g);
+int omc_graph_num_kernel_nodes(omc_graph_t* g, long long* out);
+int omc_run_schedule(omc_graph_t* sweep, omc_graph_t* store, void* stream, long long n_burn, long long n_iter,
+                     long long n_thin);
+/* store[iter] <- src : `count` doubles into dst + (*iter_counter)*count   (ref: sampler.py:89-118) */
+int omc_store_copy(const double* src, double* dst, long long count, const unsigned long long* iter_counter,
+                   long long max_iter, void* stream);
+
+/* ------------------------------------------------------------------ conjugate regression (C1 / C2)
+ * omc_reg_pass: one fused pass over (X, y[, w]) per chain -> record  G = X'WX | g = X'Wy | rss | cnt
+ *   ref: location_scale.py:234-242 (Hessian X'QX), sampler.py:190-192 (X'Q(y-d)), sampler.py:275-284 (r'Pr, #diag>0)
+ *   X: [n x p] row-major per chain; y,w: [n]; beta: [p] (NULL => rss = y'Wy); stats: [n_chains][p*p+p+2]
+ *   workspace: omc_reg_pass_workspace() doubles when n_split > 1 (few chains, long n), else may be NULL. */
+int omc_reg_pass_workspace(int n_chains, int n, int p, int* n_split_out, long long* workspace_doubles);
+int omc_reg_pass(const double* X, long long strideX, const double* y, long long strideY, const double* w,
+                 long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
+                 double* stats, double* workspace, void* stream);
+
+/* omc_nn_dense_draw: NormalNormal conditional draw for a dense p x p posterior precision (p <= 64)
+ *   Q = lambda*P0 + tau*G ; b = lambda*P0*mu0 + tau*g ; L = chol(Q) ; mu = L^-T L^-1 b ; beta = mu + L^-T z
+ *   ref: sampler.py:154-207 (NormalNormal.sample), gmrf.py:167-198 (sample_normal_canonical), gmrf.py:29-61 */
+typedef struct {
+  int n_chains, p;
+  omc_vec_t stats;      /* records from omc_reg_pass (chain_stride = p*p+p+2)                */
+  omc_vec_t tau;        /* scalar multiplying G and g; NULL => 1                             */
+  int prior_kind;       /* 0 scaled identity, 1 diagonal, 2 dense row-major                  */
+  omc_vec_t prior_P;    /* un-scaled prior precision (kind 0: 1 value or NULL => 1)          */
+  omc_vec_t lambda;     /* scalar multiplying prior_P; NULL => 1                             */
+  omc_vec_t mu0;        /* prior mean [p]; NULL => 0                                         */
+  double* beta;         /* out [n_chains][p]                                                 */
+  omc_rng_t rng;
+  const double* debug_z; /* injected standard normals [n_chains][p] (ref tests patch norm.rvs); NULL => Philox */
+  double* probe_Q;      /* optional [n_chains][p*p] posterior precision                      */
+  double* probe_b;      /* optional [n_chains][p]                                            */
+  double* probe_L;      /* optional [n_chains][p*p] lower Cholesky factor                    */
+  double* probe_mu;     /* optional [n_chains][p] posterior mean                             */
+  int* status;          /* optional [n_chains], OR-ed with OMC_STATUS_*                      */
+} omc_nn_dense_t;
+int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream);
+
+/* omc_quadform: ss = (x-mu)' P (x-mu), cnt = #(diag P > 0) per chain  (ref: sampler.py:276-284 for a prior precision) */
+typedef struct {
+  int n_chains, p;
+  omc_vec_t x, mu;      /* mu NULL => 0 */
+  int kind;
+  omc_vec_t P;
+  double* ss;           /* out [n_chains] */
+  double* cnt;          /* out [n_chains] */
+} omc_quadform_t;
+int omc_quadform(const omc_quadform_t* args, void* stream);
+
+/* omc_ng_draw: NormalGamma conditional draw  x ~ Gamma(a0 + cnt/2, rate = b0 + ss/2)
+ *   ref: sampler.py:252-288 (b == 0 => scale = inf => sample = inf guard at :285-286) */
+typedef struct {
+  int n_chains;
+  omc_vec_t a0, b0;     /* Gamma prior shape / rate */
+  omc_vec_t ss, cnt;    /* quadratic form and count (e.g. into an omc_reg_pass record) */
+  double* out;          /* [n_chains] */
+  omc_rng_t rng;
+  const double* debug_g; /* injected standard-gamma variates Gamma(a*,1) [n_chains]; NULL => Marsaglia-Tsang */
+  double* probe_a;      /* optional [n_chains] posterior shape */
+  double* probe_b;      /* optional [n_chains] posterior rate  */
+} omc_ng_draw_t;
+int omc_ng_draw(const omc_ng_draw_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMC_H */

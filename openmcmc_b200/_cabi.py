@@ -1,0 +1,143 @@
+"""ctypes binding of libomc.so (include/omc.h) — the only way the Python host code reaches the CUDA kernels.
+
+There is no CPU fallback: if the shared library is missing `load()` raises, and every numeric entry point of the
+package goes through it.
+"""
+
+import ctypes as C
+import os
+
+_LIB_NAME = "libomc.so"
+_lib = None
+
+
+class OmcError(RuntimeError):
+    """Raised when a libomc call returns non-zero; carries omc_last_error()."""
+
+
+class Vec(C.Structure):
+    """omc_vec_t: per-chain operand (device pointer + element stride between chains, 0 = shared)."""
+
+    _fields_ = [("ptr", C.c_void_p), ("chain_stride", C.c_longlong)]
+
+
+class Rng(C.Structure):
+    """omc_rng_t"""
+
+    _fields_ = [
+        ("seed", C.c_ulonglong),
+        ("sweep", C.c_void_p),
+        ("chain_offset", C.c_uint),
+        ("site", C.c_uint),
+    ]
+
+
+class NNDense(C.Structure):
+    """omc_nn_dense_t"""
+
+    _fields_ = [
+        ("n_chains", C.c_int),
+        ("p", C.c_int),
+        ("stats", Vec),
+        ("tau", Vec),
+        ("prior_kind", C.c_int),
+        ("prior_P", Vec),
+        ("lam", Vec),
+        ("mu0", Vec),
+        ("beta", C.c_void_p),
+        ("rng", Rng),
+        ("debug_z", C.c_void_p),
+        ("probe_Q", C.c_void_p),
+        ("probe_b", C.c_void_p),
+        ("probe_L", C.c_void_p),
+        ("probe_mu", C.c_void_p),
+        ("status", C.c_void_p),
+    ]
+
+
+class Quadform(C.Structure):
+    """omc_quadform_t"""
+
+    _fields_ = [
+        ("n_chains", C.c_int),
+        ("p", C.c_int),
+        ("x", Vec),
+        ("mu", Vec),
+        ("kind", C.c_int),
+        ("P", Vec),
+        ("ss", C.c_void_p),
+        ("cnt", C.c_void_p),
+    ]
+
+
+class NGDraw(C.Structure):
+    """omc_ng_draw_t"""
+
+    _fields_ = [
+        ("n_chains", C.c_int),
+        ("a0", Vec),
+        ("b0", Vec),
+        ("ss", Vec),
+        ("cnt", Vec),
+        ("out", C.c_void_p),
+        ("rng", Rng),
+        ("debug_g", C.c_void_p),
+        ("probe_a", C.c_void_p),
+        ("probe_b", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
+PROTOTYPES = {
+    "omc_abi_version": (C.c_int, []),
+    "omc_last_error": (C.c_char_p, []),
+    "omc_device_init": (C.c_int, [C.c_int]),
+    "omc_device_sm_count": (C.c_int, []),
+    "omc_counter_add": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    "omc_graph_capture_begin": (C.c_int, [C.c_void_p]),
+    "omc_graph_capture_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "omc_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),
+    "omc_graph_destroy": (C.c_int, [C.c_void_p]),
+    "omc_graph_num_kernel_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "omc_run_schedule": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong]),
+    "omc_store_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "omc_reg_pass_workspace": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "omc_reg_pass": (
+        C.c_int,
+        [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "omc_nn_dense_draw": (C.c_int, [C.POINTER(NNDense), C.c_void_p]),
+    "omc_quadform": (C.c_int, [C.POINTER(Quadform), C.c_void_p]),
+    "omc_ng_draw": (C.c_int, [C.POINTER(NGDraw), C.c_void_p]),
+}
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load():
+    """Load libomc.so and attach prototypes.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise OmcError(
+            f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C openmcmc_b200/csrc). openmcmc_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().omc_last_error()
+        raise OmcError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,341 @@
+// reg_pass: the fused likelihood pass of the conjugate-regression hot path.
+//
+// For every chain c, ONE streaming pass over (X_c, y_c [, w_c]) produces the sufficient statistics the
+// NormalNormal / NormalGamma Gibbs updates need:
+//     G   = X' W X          (p x p)   -- the reference's  (grad_param @ Q) @ grad_param.T,  location_scale.py:238-241
+//     g   = X' W y          (p)       -- the reference's  A.T @ Q_rsp @ (y - d),            sampler.py:190-192
+//     rss = (y-Xb)' W (y-Xb)          -- the reference's  residual.T @ P @ residual,        sampler.py:276,284
+//     cnt = #(w > 0)                  -- the reference's  sum(P.diagonal() > 0),            sampler.py:283
+// W = diag(w) (or I when w == nullptr); tau is NOT folded in here (ScaledMatrix scalar is applied by the consumers).
+//
+// Kernel: one CTA per (chain, row-split).  X rows are streamed global->shared with a 3-stage cp.async pipeline into
+// a padded layout (row stride 8*PB+4 doubles => the DMMA fragment reads below are bank-conflict free).  The SYRK runs
+// on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native FP64 MMA shape on sm_100a).  Because
+// A = X' and B = X come from the same tile, one 8-register fragment set per 4 rows feeds all PB(PB+1)/2 lower-triangle
+// 8x8 output tiles (36 DMMA per 8 LDS.64 at p=64).  g and rss ride along on the FP64 FMA pipe (+~5%).
+// Roofline: 46.1 MFLOP of DMMA per chain at n=10^4,p=64 vs 5.2 MB of HBM traffic => FP64-bound.
+#include "../../include/omc.h"
+#include "omc_common.cuh"
+#include "omc_internal.h"
+
+namespace {
+
+constexpr int KC = 64;      // rows per pipeline stage
+constexpr int NSTAGE = 3;   // cp.async stages
+constexpr int NWARP = 4;
+constexpr int NTHREADS = NWARP * 32;
+
+struct RegPassArgs {
+  const double* X;
+  const double* y;
+  const double* w;
+  const double* beta;
+  long long strideX, strideY, strideW, strideB;  // elements between consecutive chains (0 => shared by all chains)
+  int n, p, n_chains, n_split, rows_per_split;
+  double* out;  // records [chain][split][rec] ; rec = p*p + p + 2 : G | g | rss | cnt
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int PB>
+struct Smem {
+  static constexpr int LD = 8 * PB + 4;  // padded row stride (doubles): (2g + 8k) mod 32 banks are distinct per phase
+  static constexpr int STAGE_DOUBLES = KC * LD + 2 * KC;  // X tile | y | w
+  static constexpr int BYTES = NSTAGE * STAGE_DOUBLES * 8;
+};
+
+template <int PB, bool WEIGHTED>
+__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(RegPassArgs a) {
+  using S = Smem<PB>;
+  constexpr int LD = S::LD;
+  constexpr int NT = PB * (PB + 1) / 2;
+  extern __shared__ __align__(16) double smem[];
+
+  const int chain = blockIdx.y, split = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, kq = lane & 3;
+  const int p = a.p, n = a.n;
+  const int row0 = split * a.rows_per_split;
+  const int row1 = min(n, row0 + a.rows_per_split);
+  const int nrows = max(0, row1 - row0);
+  const int nstage_total = (nrows + KC - 1) / KC;
+
+  const double* Xc = a.X + (long long)chain * a.strideX + (long long)row0 * p;
+  const double* yc = a.y + (long long)chain * a.strideY + row0;
+  const double* wc = WEIGHTED ? a.w + (long long)chain * a.strideW + row0 : nullptr;
+
+  // zero the whole staging area once: columns >= p of every row are never written by the loader and must read as 0
+  for (int i = tid; i < NSTAGE * S::STAGE_DOUBLES; i += NTHREADS) smem[i] = 0.0;
+  __syncthreads();
+
+  const bool vec16 = ((p & 1) == 0) && ((((unsigned long long)Xc) & 15ull) == 0);
+
+  auto issue_stage = [&](int st) {
+    if (st < nstage_total) {
+      double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
+      double* ys = Xs + KC * LD;
+      double* ws = ys + KC;
+      const int r_base = st * KC;
+      const int valid = min(KC, nrows - r_base);
+      const double* src = Xc + (long long)r_base * p;
+      if (vec16) {
+        const int cpr = p >> 1;  // 16-byte chunks per row
+        const int total = KC * cpr;
+        for (int id = tid; id < total; id += NTHREADS) {
+          int r = id / cpr, c = id - r * cpr;
+          bool ok = r < valid;
+          cp_async16(Xs + r * LD + 2 * c, ok ? (const void*)(src + (long long)r * p + 2 * c) : (const void*)Xc,
+                     ok ? 16 : 0);
+        }
+      } else {
+        const int total = KC * p;
+        for (int id = tid; id < total; id += NTHREADS) {
+          int r = id / p, c = id - r * p;
+          bool ok = r < valid;
+          cp_async8(Xs + r * LD + c, ok ? (const void*)(src + (long long)r * p + c) : (const void*)Xc, ok ? 8 : 0);
+        }
+      }
+      for (int r = tid; r < KC; r += NTHREADS) {
+        bool ok = r < valid;
+        cp_async8(ys + r, ok ? (const void*)(yc + r_base + r) : (const void*)yc, ok ? 8 : 0);
+        if (WEIGHTED) cp_async8(ws + r, ok ? (const void*)(wc + r_base + r) : (const void*)wc, ok ? 8 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // per-lane slice of beta in fragment layout: column 8*jb + g
+  double bfrag[PB];
+#pragma unroll
+  for (int jb = 0; jb < PB; ++jb) {
+    int col = 8 * jb + g;
+    bfrag[jb] = (a.beta != nullptr && col < p) ? a.beta[(long long)chain * a.strideB + col] : 0.0;
+  }
+
+  double acc[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+  double gacc[PB];
+#pragma unroll
+  for (int jb = 0; jb < PB; ++jb) gacc[jb] = 0.0;
+  double rss = 0.0, cnt = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
+
+  for (int st = 0; st < nstage_total; ++st) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    issue_stage(st + NSTAGE - 1);
+    const double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
+    const double* ys = Xs + KC * LD;
+    const double* ws = ys + KC;
+#pragma unroll 2
+    for (int ks = warp; ks < KC / 4; ks += NWARP) {
+      const int r = 4 * ks + kq;
+      const double* xr = Xs + r * LD + g;
+      double af[PB], bf[PB];
+#pragma unroll
+      for (int jb = 0; jb < PB; ++jb) af[jb] = xr[8 * jb];
+      const double yv = ys[r];
+      double wv = 1.0;
+      if (WEIGHTED) {
+        wv = ws[r];
+#pragma unroll
+        for (int jb = 0; jb < PB; ++jb) bf[jb] = af[jb] * wv;
+      } else {
+#pragma unroll
+        for (int jb = 0; jb < PB; ++jb) bf[jb] = af[jb];
+      }
+      // SYRK tiles (lower triangle of the 8x8-block grid)
+#pragma unroll
+      for (int i = 0; i < PB; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) dmma884(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], af[i], bf[j]);
+      // X' W y and the residual of this row
+      double dot = 0.0;
+#pragma unroll
+      for (int jb = 0; jb < PB; ++jb) {
+        gacc[jb] = fma(bf[jb], yv, gacc[jb]);
+        dot = fma(af[jb], bfrag[jb], dot);
+      }
+      dot += omc_shfl_xor(dot, 4);
+      dot += omc_shfl_xor(dot, 8);
+      dot += omc_shfl_xor(dot, 16);
+      const double res = yv - dot;
+      rss = fma(WEIGHTED ? wv * res : res, res, rss);
+      if (WEIGHTED) cnt += (wv > 0.0) ? 1.0 : 0.0;
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- combine the 4 warps (rows were split across warps) through shared memory
+  double* red = smem;  // NT*64 + 8*PB + 2*4 doubles, fits in one stage
+  // g: sum over the 4 k-lanes; rss/cnt: lanes sharing kq hold identical copies -> keep g==0 lanes only
+#pragma unroll
+  for (int jb = 0; jb < PB; ++jb) {
+    gacc[jb] += omc_shfl_xor(gacc[jb], 1);
+    gacc[jb] += omc_shfl_xor(gacc[jb], 2);
+  }
+  if (g != 0) { rss = 0.0; cnt = 0.0; }
+  rss = omc_warp_sum(rss);
+  cnt = omc_warp_sum(cnt);
+  for (int wsrc = 1; wsrc < NWARP; ++wsrc) {
+    if (warp == wsrc) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        red[t * 64 + 2 * lane] = acc[t][0];
+        red[t * 64 + 2 * lane + 1] = acc[t][1];
+      }
+      if (kq == 0) {
+#pragma unroll
+        for (int jb = 0; jb < PB; ++jb) red[NT * 64 + 8 * jb + g] = gacc[jb];
+      }
+      if (lane == 0) { red[NT * 64 + 8 * PB] = rss; red[NT * 64 + 8 * PB + 1] = cnt; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        acc[t][0] += red[t * 64 + 2 * lane];
+        acc[t][1] += red[t * 64 + 2 * lane + 1];
+      }
+#pragma unroll
+      for (int jb = 0; jb < PB; ++jb) gacc[jb] += red[NT * 64 + 8 * jb + g];
+      rss += red[NT * 64 + 8 * PB];
+      cnt += red[NT * 64 + 8 * PB + 1];
+    }
+    __syncthreads();
+  }
+
+  if (warp == 0) {
+    const int rec = p * p + p + 2;
+    double* o = a.out + ((long long)chain * a.n_split + split) * rec;
+#pragma unroll
+    for (int i = 0; i < PB; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const int t = i * (i + 1) / 2 + j;
+        const int rr = 8 * i + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cc = 8 * j + 2 * kq + e;
+          if (rr < p && cc < p) {
+            o[rr * p + cc] = acc[t][e];
+            if (i != j) o[cc * p + rr] = acc[t][e];
+          }
+        }
+      }
+    if (kq == 0) {
+#pragma unroll
+      for (int jb = 0; jb < PB; ++jb)
+        if (8 * jb + g < p) o[p * p + 8 * jb + g] = gacc[jb];
+    }
+    if (lane == 0) {
+      o[p * p + p] = rss;
+      o[p * p + p + 1] = WEIGHTED ? cnt : (double)nrows;
+    }
+  }
+}
+
+// sum the per-split records: out[c][:] = sum_s part[c][s][:]
+__global__ void reg_reduce_kernel(const double* part, double* out, int n_split, int rec, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long c = i / rec;
+  int e = (int)(i - c * rec);
+  const double* src = part + (c * n_split) * rec + e;
+  double s = 0.0;
+  for (int k = 0; k < n_split; ++k) s += src[(long long)k * rec];
+  out[i] = s;
+}
+
+template <int PB>
+int launch_pb(const RegPassArgs& a, bool weighted, cudaStream_t st) {
+  dim3 grid(a.n_split, a.n_chains);
+  const int smem = Smem<PB>::BYTES;
+  if (weighted) {
+    OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    reg_pass_kernel<PB, true><<<grid, NTHREADS, smem, st>>>(a);
+  } else {
+    OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    reg_pass_kernel<PB, false><<<grid, NTHREADS, smem, st>>>(a);
+  }
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int omc_reg_pass_workspace(int n_chains, int n, int p, int* n_split_out, long long* workspace_doubles) {
+  OMC_REQUIRE(n_chains > 0 && n >= 0 && p > 0, "omc_reg_pass_workspace: bad shape C=%d n=%d p=%d", n_chains, n, p);
+  OMC_REQUIRE(p <= 64, "omc_reg_pass: p=%d > 64 is not supported yet (column panels are a round-2 item)", p);
+  int sms = omc_sm_count();
+  int max_split = (n + KC - 1) / KC;
+  if (max_split < 1) max_split = 1;
+  int want = (4 * sms + n_chains - 1) / n_chains;  // aim for >= 4 CTAs per SM when chains are few
+  int s = want < 1 ? 1 : (want > max_split ? max_split : want);
+  *n_split_out = s;
+  *workspace_doubles = (s > 1) ? (long long)n_chains * s * ((long long)p * p + p + 2) : 0;
+  return 0;
+}
+
+extern "C" int omc_reg_pass(const double* X, long long strideX, const double* y, long long strideY, const double* w,
+                            long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
+                            double* stats, double* workspace, void* stream) {
+  int n_split = 1;
+  long long ws = 0;
+  int rc = omc_reg_pass_workspace(n_chains, n, p, &n_split, &ws);
+  if (rc) return rc;
+  OMC_REQUIRE(X && y && stats, "omc_reg_pass: null pointer");
+  OMC_REQUIRE(n_split == 1 || workspace != nullptr, "omc_reg_pass: workspace required (n_split=%d)", n_split);
+  OMC_REQUIRE(n_chains <= 65535, "omc_reg_pass: n_chains=%d exceeds grid.y; shard the chains", n_chains);
+  cudaStream_t st = (cudaStream_t)stream;
+  RegPassArgs a;
+  a.X = X; a.y = y; a.w = w; a.beta = beta;
+  a.strideX = strideX; a.strideY = strideY; a.strideW = strideW; a.strideB = strideB;
+  a.n = n; a.p = p; a.n_chains = n_chains; a.n_split = n_split;
+  int rps = (n + n_split - 1) / n_split;
+  rps = ((rps + KC - 1) / KC) * KC;
+  if (rps < KC) rps = KC;
+  a.rows_per_split = rps;
+  a.out = (n_split > 1) ? workspace : stats;
+  const int pb = (p + 7) / 8;
+  const bool weighted = (w != nullptr);
+  switch (pb) {
+    case 1: rc = launch_pb<1>(a, weighted, st); break;
+    case 2: rc = launch_pb<2>(a, weighted, st); break;
+    case 3: rc = launch_pb<3>(a, weighted, st); break;
+    case 4: rc = launch_pb<4>(a, weighted, st); break;
+    case 5: rc = launch_pb<5>(a, weighted, st); break;
+    case 6: rc = launch_pb<6>(a, weighted, st); break;
+    case 7: rc = launch_pb<7>(a, weighted, st); break;
+    default: rc = launch_pb<8>(a, weighted, st); break;
+  }
+  if (rc) return rc;
+  if (n_split > 1) {
+    const int rec = p * p + p + 2;
+    long long total = (long long)n_chains * rec;
+    reg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, stats, n_split, rec, total);
+    OMC_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,166 @@
+"""Typed Python wrappers over the C-ABI op entry points (include/omc.h).
+
+Device memory and streams come from torch (plumbing only); every numeric result is produced by libomc's CUDA
+kernels.  Tensors are float64 CUDA tensors; per-chain operands have a leading chain dimension.
+"""
+
+import ctypes as C
+
+import torch
+
+from openmcmc_b200 import _cabi
+from openmcmc_b200._cabi import Vec, Rng, check
+
+MAT_EYE, MAT_DIAG, MAT_DENSE = 0, 1, 2
+_initialised = set()
+
+
+def lib():
+    return _cabi.load()
+
+
+def init_device(device=None) -> int:
+    """Select the CUDA device for libomc (must be sm_100a).  Raises if CUDA is unavailable — no CPU path exists."""
+    if not torch.cuda.is_available():
+        raise _cabi.OmcError("openmcmc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    torch.cuda.set_device(dev)
+    if dev not in _initialised:
+        check(lib().omc_device_init(dev), "omc_device_init")
+        _initialised.add(dev)
+    return dev
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float64, torch.int32, torch.int64, torch.uint8), (t.dtype, t.device)
+    assert t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def vec(t, per_chain_elems=None) -> Vec:
+    """Build an omc_vec_t.  `t` is None (default), a shared tensor (stride 0) or a per-chain tensor [C, ...]."""
+    if t is None:
+        return Vec(None, 0)
+    if isinstance(t, tuple):  # (tensor, explicit stride in elements)
+        return Vec(t[0].data_ptr(), int(t[1]))
+    if per_chain_elems is None:
+        return Vec(t.data_ptr(), 0)
+    return Vec(t.data_ptr(), int(per_chain_elems))
+
+
+def rng(seed=0, sweep=None, chain_offset=0, site=0) -> Rng:
+    return Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, sweep.data_ptr() if sweep is not None else None, int(chain_offset),
+               int(site))
+
+
+def counter_add(counter, inc=1):
+    check(lib().omc_counter_add(_ptr(counter), int(inc), stream_ptr()), "omc_counter_add")
+
+
+# ----------------------------------------------------------------------------- conjugate regression
+def reg_pass_workspace(n_chains, n, p):
+    ns = C.c_int(0)
+    ws = C.c_longlong(0)
+    check(lib().omc_reg_pass_workspace(n_chains, n, p, C.byref(ns), C.byref(ws)), "omc_reg_pass_workspace")
+    return ns.value, ws.value
+
+
+def reg_pass(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_shared=False, w_shared=False):
+    """stats[c] = [X'WX | X'Wy | rss | cnt] for every chain (one fused pass over X)."""
+    check(
+        lib().omc_reg_pass(
+            _ptr(X), 0 if x_shared else n * p, _ptr(y), 0 if y_shared else n, _ptr(w), 0 if w_shared else n,
+            _ptr(beta), p, n_chains, n, p, _ptr(stats), _ptr(workspace), stream_ptr()),
+        "omc_reg_pass",
+    )
+
+
+def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, rng_, debug_z=None, probe_Q=None,
+                  probe_b=None, probe_L=None, probe_mu=None, status=None):
+    a = _cabi.NNDense()
+    a.n_chains, a.p = n_chains, p
+    a.stats = Vec(stats.data_ptr(), p * p + p + 2)
+    a.tau, a.prior_kind, a.prior_P, a.lam, a.mu0 = tau, prior_kind, prior_P, lam, mu0
+    a.beta = beta.data_ptr()
+    a.rng = rng_
+    a.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    a.probe_Q = probe_Q.data_ptr() if probe_Q is not None else None
+    a.probe_b = probe_b.data_ptr() if probe_b is not None else None
+    a.probe_L = probe_L.data_ptr() if probe_L is not None else None
+    a.probe_mu = probe_mu.data_ptr() if probe_mu is not None else None
+    a.status = status.data_ptr() if status is not None else None
+    check(lib().omc_nn_dense_draw(C.byref(a), stream_ptr()), "omc_nn_dense_draw")
+
+
+def quadform(n_chains, p, x, mu, kind, P, ss, cnt):
+    a = _cabi.Quadform()
+    a.n_chains, a.p, a.x, a.mu, a.kind, a.P = n_chains, p, x, mu, kind, P
+    a.ss, a.cnt = ss.data_ptr(), cnt.data_ptr()
+    check(lib().omc_quadform(C.byref(a), stream_ptr()), "omc_quadform")
+
+
+def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None):
+    a = _cabi.NGDraw()
+    a.n_chains, a.a0, a.b0, a.ss, a.cnt = n_chains, a0, b0, ss, cnt
+    a.out = out.data_ptr()
+    a.rng = rng_
+    a.debug_g = debug_g.data_ptr() if debug_g is not None else None
+    a.probe_a = probe_a.data_ptr() if probe_a is not None else None
+    a.probe_b = probe_b.data_ptr() if probe_b is not None else None
+    check(lib().omc_ng_draw(C.byref(a), stream_ptr()), "omc_ng_draw")
+
+
+# ----------------------------------------------------------------------------- graphs / schedule
+class Graph:
+    """A captured CUDA graph of op launches (omc_graph_t)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @staticmethod
+    def capture(fn):
+        """Record every libomc launch `fn()` makes on the current stream into a replayable graph."""
+        st = stream_ptr()
+        check(lib().omc_graph_capture_begin(st), "omc_graph_capture_begin")
+        try:
+            fn()
+        finally:
+            h = C.c_void_p()
+            rc = lib().omc_graph_capture_end(st, C.byref(h))
+        check(rc, "omc_graph_capture_end")
+        return Graph(h)
+
+    def launch(self, times=1):
+        check(lib().omc_graph_launch(self.handle, stream_ptr(), int(times)), "omc_graph_launch")
+
+    def num_kernels(self) -> int:
+        n = C.c_longlong(0)
+        check(lib().omc_graph_num_kernel_nodes(self.handle, C.byref(n)), "omc_graph_num_kernel_nodes")
+        return n.value
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().omc_graph_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def run_schedule(sweep: Graph, store, n_burn, n_iter, n_thin):
+    check(
+        lib().omc_run_schedule(sweep.handle, store.handle if store is not None else None, stream_ptr(), int(n_burn),
+                               int(n_iter), int(n_thin)),
+        "omc_run_schedule",
+    )
+
+
+def store_copy(src, dst, count, iter_counter, max_iter):
+    check(lib().omc_store_copy(_ptr(src), _ptr(dst), int(count), _ptr(iter_counter), int(max_iter), stream_ptr()),
+          "omc_store_copy")
