@@ -87,6 +87,7 @@ typedef struct {
   double* beta;         /* out [n_chains][p]                                                 */
   omc_rng_t rng;
   const double* debug_z; /* injected standard normals [n_chains][p] (ref tests patch norm.rvs); NULL => Philox */
+  long long debug_sweep_stride; /* elements between consecutive sweeps' injected draws (0 = same every sweep) */
   double* probe_Q;      /* optional [n_chains][p*p] posterior precision                      */
   double* probe_b;      /* optional [n_chains][p]                                            */
   double* probe_L;      /* optional [n_chains][p*p] lower Cholesky factor                    */
@@ -115,10 +116,69 @@ typedef struct {
   double* out;          /* [n_chains] */
   omc_rng_t rng;
   const double* debug_g; /* injected standard-gamma variates Gamma(a*,1) [n_chains]; NULL => Marsaglia-Tsang */
+  long long debug_sweep_stride;
   double* probe_a;      /* optional [n_chains] posterior shape */
   double* probe_b;      /* optional [n_chains] posterior rate  */
 } omc_ng_draw_t;
 int omc_ng_draw(const omc_ng_draw_t* args, void* stream);
+
+/* ------------------------------------------------------------------ log-densities (ref: Model.log_p, model.py:57-70)
+ * Every kernel writes out[c] (accumulate = 0) or adds to it (accumulate = 1), one value per chain. */
+
+/* Normal log-pdf from a pre-computed quadratic form with the UN-scaled precision matrix P:
+ *   0.5 * (dim*log(scalar) + logdet(P) - dim*log(2 pi) - scalar*ss)
+ * ref: location_scale.py:145-167 -> gmrf.py:321-348 (the reference re-factorises scalar*P on every call; log|scalar*P|
+ * = dim*log(scalar) + log|P| with log|P| computed once for a constant P). */
+typedef struct {
+  int n_chains;
+  double dim;
+  omc_vec_t ss;       /* r' P r                                  */
+  omc_vec_t scalar;   /* NULL => 1                               */
+  omc_vec_t logdet;   /* log|P|, NULL => 0 (identity)            */
+  double* out;
+  int accumulate;
+} omc_logp_normal_ss_t;
+int omc_logp_normal_ss(const omc_logp_normal_ss_t* args, void* stream);
+
+/* Gamma(shape, rate) log-pdf summed over n_elem responses per chain, scipy.stats.gamma.logpdf semantics:
+ *   xlogy(a-1, x/scale) - x/scale - gammaln(a) - log(scale), scale = 1/rate; -inf for x < 0
+ * ref: distribution.py:241-261.  shape / rate hold shape_len / rate_len (1 or n_elem) values per chain. */
+typedef struct {
+  int n_chains, n_elem, shape_len, rate_len;
+  omc_vec_t x, shape, rate;
+  double* out;
+  int accumulate;
+} omc_logp_gamma_t;
+int omc_logp_gamma(const omc_logp_gamma_t* args, void* stream);
+
+/* Poisson(rate) log-pmf summed over n_elem responses: xlogy(k, mu) - gammaln(k+1) - mu; -inf for k<0 or non-integer k
+ * ref: distribution.py:490-508 */
+typedef struct {
+  int n_chains, n_elem, rate_len;
+  omc_vec_t k, rate;
+  double* out;
+  int accumulate;
+} omc_logp_poisson_t;
+int omc_logp_poisson(const omc_logp_poisson_t* args, void* stream);
+
+/* out[c] (+)= value  — constant log-densities such as Uniform (ref: distribution.py:422-442) */
+int omc_logp_const(double value, int n_chains, double* out, int accumulate, void* stream);
+
+/* yhat[c] = sum_t X_t[c] @ theta_t[c] for up to 4 terms (ref: parameter.py:162-197 LinearCombination.predictor) */
+typedef struct {
+  int n_chains, n, n_terms;
+  int p[4];
+  omc_vec_t X[4];      /* [n x p_t] row-major */
+  omc_vec_t theta[4];  /* [p_t]               */
+  double* out;         /* [n_chains][n]       */
+} omc_linear_predictor_t;
+int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
+
+/* One-off helpers for CONSTANT precision matrices (data, not sampled): log-determinants used by the Normal log-pdf.
+ * n_mats matrices, each `n` diagonal entries (sum_log) or an n x n dense SPD matrix, n <= 64 (logdet_dense: 2*sum log diag chol).
+ * ref: gmrf.py:339-342 */
+int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream);
+int omc_logdet_dense(const double* P, int n_mats, int n, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,7 @@ class NNDense(C.Structure):
         ("beta", C.c_void_p),
         ("rng", Rng),
         ("debug_z", C.c_void_p),
+        ("debug_sweep_stride", C.c_longlong),
         ("probe_Q", C.c_void_p),
         ("probe_b", C.c_void_p),
         ("probe_L", C.c_void_p),
@@ -82,9 +83,38 @@ class NGDraw(C.Structure):
         ("out", C.c_void_p),
         ("rng", Rng),
         ("debug_g", C.c_void_p),
+        ("debug_sweep_stride", C.c_longlong),
         ("probe_a", C.c_void_p),
         ("probe_b", C.c_void_p),
     ]
+
+
+class LogpNormalSS(C.Structure):
+    """omc_logp_normal_ss_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("dim", C.c_double), ("ss", Vec), ("scalar", Vec), ("logdet", Vec),
+                ("out", C.c_void_p), ("accumulate", C.c_int)]
+
+
+class LogpGamma(C.Structure):
+    """omc_logp_gamma_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n_elem", C.c_int), ("shape_len", C.c_int), ("rate_len", C.c_int),
+                ("x", Vec), ("shape", Vec), ("rate", Vec), ("out", C.c_void_p), ("accumulate", C.c_int)]
+
+
+class LogpPoisson(C.Structure):
+    """omc_logp_poisson_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n_elem", C.c_int), ("rate_len", C.c_int), ("k", Vec), ("rate", Vec),
+                ("out", C.c_void_p), ("accumulate", C.c_int)]
+
+
+class LinearPredictor(C.Structure):
+    """omc_linear_predictor_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n", C.c_int), ("n_terms", C.c_int), ("p", C.c_int * 4), ("X", Vec * 4),
+                ("theta", Vec * 4), ("out", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
@@ -110,6 +140,13 @@ PROTOTYPES = {
     "omc_nn_dense_draw": (C.c_int, [C.POINTER(NNDense), C.c_void_p]),
     "omc_quadform": (C.c_int, [C.POINTER(Quadform), C.c_void_p]),
     "omc_ng_draw": (C.c_int, [C.POINTER(NGDraw), C.c_void_p]),
+    "omc_logp_normal_ss": (C.c_int, [C.POINTER(LogpNormalSS), C.c_void_p]),
+    "omc_logp_gamma": (C.c_int, [C.POINTER(LogpGamma), C.c_void_p]),
+    "omc_logp_poisson": (C.c_int, [C.POINTER(LogpPoisson), C.c_void_p]),
+    "omc_logp_const": (C.c_int, [C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
+    "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(DD_THREADS) nn_dense_draw_kernel(omc_nn_dense_
   }
   // z: injected or Philox/Box-Muller
   if (a.debug_z) {
-    for (int i = tid; i < p; i += DD_THREADS) z[i] = a.debug_z[(long long)chain * p + i];
+    const double* dz = a.debug_z + (a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride;
+    for (int i = tid; i < p; i += DD_THREADS) z[i] = dz[(long long)chain * p + i];
   } else {
     OmcRng rng = to_rng(a.rng);
     for (int t = tid; 2 * t < p; t += DD_THREADS) {
@@ -191,7 +192,7 @@ __global__ void ng_draw_kernel(omc_ng_draw_t a) {
   if (a.probe_a) a.probe_a[chain] = shape;
   if (a.probe_b) a.probe_b[chain] = rate;
   double gvar;
-  if (a.debug_g) gvar = a.debug_g[chain];
+  if (a.debug_g) gvar = a.debug_g[(a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride + chain];
   else gvar = omc_std_gamma(to_rng(a.rng), chain, 0, shape);
   // reference: scale = inf when rate == 0 (sampler.py:285-286)
   a.out[chain] = (rate == 0.0) ? INFINITY : gvar * (1.0 / rate);

@@ -1,0 +1,163 @@
+// Log-density kernels and the LinearCombination predictor (a13).
+// Element-wise HBM sweeps with warp-shuffle reductions: one CTA per chain, grid-stride over the elements.
+#include "../../include/omc.h"
+#include "omc_common.cuh"
+#include "omc_internal.h"
+
+namespace {
+constexpr int LP_THREADS = 256;
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+
+__device__ __forceinline__ double vat(const omc_vec_t& v, int chain, long long i, double dflt) {
+  return v.ptr ? v.ptr[(long long)chain * v.chain_stride + i] : dflt;
+}
+
+__global__ void logp_normal_ss_kernel(omc_logp_normal_ss_t a) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.n_chains) return;
+  const double s = vat(a.scalar, c, 0, 1.0);
+  const double v = 0.5 * (a.dim * log(s) + vat(a.logdet, c, 0, 0.0) - a.dim * LOG_2PI - s * vat(a.ss, c, 0, 0.0));
+  a.out[c] = a.accumulate ? a.out[c] + v : v;
+}
+
+__global__ void __launch_bounds__(LP_THREADS) logp_gamma_kernel(omc_logp_gamma_t a) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < a.n_elem; i += LP_THREADS) {
+    const double x = vat(a.x, c, i, 0.0);
+    const double sh = vat(a.shape, c, a.shape_len > 1 ? i : 0, 1.0);
+    const double rt = vat(a.rate, c, a.rate_len > 1 ? i : 0, 1.0);
+    const double scale = 1.0 / rt;
+    const double y = x / scale;
+    double lp = omc_xlogy(sh - 1.0, y) - y - lgamma(sh) - log(scale);
+    if (!(y >= 0.0)) lp = isnan(y) ? y : -INFINITY;
+    acc += lp;
+  }
+  acc = omc_block_sum(acc, scratch);
+  if (threadIdx.x == 0) a.out[c] = a.accumulate ? a.out[c] + acc : acc;
+}
+
+__global__ void __launch_bounds__(LP_THREADS) logp_poisson_kernel(omc_logp_poisson_t a) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < a.n_elem; i += LP_THREADS) {
+    const double k = vat(a.k, c, i, 0.0);
+    const double mu = vat(a.rate, c, a.rate_len > 1 ? i : 0, 1.0);
+    double lp = omc_xlogy(k, mu) - lgamma(k + 1.0) - mu;
+    if (!(k >= 0.0) || floor(k) != k) lp = isnan(k) ? k : -INFINITY;
+    acc += lp;
+  }
+  acc = omc_block_sum(acc, scratch);
+  if (threadIdx.x == 0) a.out[c] = a.accumulate ? a.out[c] + acc : acc;
+}
+
+__global__ void logp_const_kernel(double v, int n, double* out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) out[c] = accumulate ? out[c] + v : v;
+}
+
+// one warp per output row; rows of X_t are contiguous (p_t doubles)
+__global__ void __launch_bounds__(LP_THREADS) linear_predictor_kernel(omc_linear_predictor_t a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)a.n_chains * a.n;
+  for (long long row = warp_global; row < total; row += nwarps) {
+    const int c = (int)(row / a.n);
+    const int r = (int)(row - (long long)c * a.n);
+    double acc = 0.0;
+    for (int t = 0; t < a.n_terms; ++t) {
+      const int p = a.p[t];
+      const double* x = a.X[t].ptr + (long long)c * a.X[t].chain_stride + (long long)r * p;
+      const double* th = a.theta[t].ptr + (long long)c * a.theta[t].chain_stride;
+      for (int j = lane; j < p; j += 32) acc = fma(x[j], th[j], acc);
+    }
+    acc = omc_warp_sum(acc);
+    if (lane == 0) a.out[row] = acc;
+  }
+}
+__global__ void __launch_bounds__(LP_THREADS) sum_log_kernel(const double* x, long long n, double* out) {
+  __shared__ double scratch[32];
+  const double* xm = x + (long long)blockIdx.x * n;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += LP_THREADS) acc += log(xm[i]);
+  acc = omc_block_sum(acc, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+// unblocked Cholesky of one small matrix per CTA (setup-time only)
+__global__ void __launch_bounds__(64) logdet_dense_kernel(const double* P, int n, double* out) {
+  extern __shared__ double A[];
+  const double* Pm = P + (long long)blockIdx.x * n * n;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n * n; e += 64) A[e] = Pm[e];
+  __syncthreads();
+  double ld = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double d = A[j * n + j];
+    if (!(d > 0.0)) { ld = nan(""); break; }
+    const double s = sqrt(d);
+    ld += 2.0 * log(s);
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += 64) A[i * n + j] /= s;
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += 64)
+      for (int c = j + 1; c <= i; ++c) A[i * n + c] -= A[i * n + j] * A[c * n + j];
+    __syncthreads();
+  }
+  if (tid == 0) out[blockIdx.x] = ld;
+}
+}  // namespace
+
+extern "C" {
+int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream) {
+  OMC_REQUIRE(x && out && n_mats >= 1 && n >= 0, "omc_sum_log: bad argument");
+  sum_log_kernel<<<n_mats, LP_THREADS, 0, (cudaStream_t)stream>>>(x, n, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logdet_dense(const double* P, int n_mats, int n, double* out, void* stream) {
+  OMC_REQUIRE(P && out && n_mats >= 1 && n >= 1 && n <= 64, "omc_logdet_dense: bad argument (n=%d)", n);
+  logdet_dense_kernel<<<n_mats, 64, (size_t)n * n * sizeof(double), (cudaStream_t)stream>>>(P, n, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logp_normal_ss(const omc_logp_normal_ss_t* a, void* stream) {
+  OMC_REQUIRE(a && a->out && a->ss.ptr, "omc_logp_normal_ss: null argument");
+  logp_normal_ss_kernel<<<(a->n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logp_gamma(const omc_logp_gamma_t* a, void* stream) {
+  OMC_REQUIRE(a && a->out && a->x.ptr, "omc_logp_gamma: null argument");
+  OMC_REQUIRE(a->n_chains >= 1 && a->n_elem >= 0, "omc_logp_gamma: bad shape");
+  logp_gamma_kernel<<<a->n_chains, LP_THREADS, 0, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logp_poisson(const omc_logp_poisson_t* a, void* stream) {
+  OMC_REQUIRE(a && a->out && a->k.ptr, "omc_logp_poisson: null argument");
+  logp_poisson_kernel<<<a->n_chains, LP_THREADS, 0, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logp_const(double value, int n_chains, double* out, int accumulate, void* stream) {
+  OMC_REQUIRE(out && n_chains >= 1, "omc_logp_const: bad argument");
+  logp_const_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(value, n_chains, out, accumulate);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_linear_predictor(const omc_linear_predictor_t* a, void* stream) {
+  OMC_REQUIRE(a && a->out && a->n_terms >= 1 && a->n_terms <= 4, "omc_linear_predictor: bad argument");
+  const long long total = (long long)a->n_chains * a->n;
+  long long blocks = (total * 32 + LP_THREADS - 1) / LP_THREADS;
+  const long long cap = (long long)omc_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  linear_predictor_kernel<<<(unsigned)blocks, LP_THREADS, 0, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+}

@@ -1,0 +1,542 @@
+"""Sweep-plan compiler and resident device state.
+
+The reference runs `for sampler in samplers: state = sampler.sample(state)` over a dict of numpy arrays
+(mcmc.py:97-111).  Here the same (model, samplers, state) triple is compiled ONCE into a list of CUDA kernel launches
+over buffers resident in HBM, batched over `n_chains` independent chains; the launch list of one sweep is captured in a
+CUDA graph and replayed (kernels.Graph / omc_run_schedule).
+
+Host logic only: shapes, pattern matching of the declarative model onto kernels, and a small dataflow pass that
+decides which derived quantities (sufficient statistics, quadratic forms) are still valid at each point of the sweep so
+that e.g. the Gibbs regression needs exactly ONE pass over X per sweep.  No arithmetic on chain state happens here.
+"""
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from openmcmc_b200 import kernels as K
+from openmcmc_b200.parameter import Identity, LinearCombination, ScaledMatrix
+
+F64 = torch.float64
+
+
+# ============================================================================================== device state
+@dataclass
+class DevArray:
+    """One state entry on the device.
+
+    data : float64 tensor, [C, rows, cols] when per_chain else [rows, cols]
+    kind : 'dense' | 'eye' | 'diag' | 'tridiag'   (structure of a square matrix; 'dense' for everything else)
+           eye -> data None ; diag -> data [.., n] ; tridiag -> data [.., n] main diagonal and off [.., n-1]
+    """
+
+    data: torch.Tensor
+    per_chain: bool
+    rows: int
+    cols: int
+    kind: str = "dense"
+    off: torch.Tensor = None
+
+    @property
+    def size(self):
+        return self.rows * self.cols
+
+    def vec(self, elems=None):
+        if self.data is None:
+            return K.vec(None)
+        per = self.data[0].numel() if self.per_chain else None
+        return K.vec(self.data, per)
+
+    def off_vec(self):
+        per = self.off[0].numel() if self.per_chain else None
+        return K.vec(self.off, per)
+
+
+def classify_matrix(m):
+    """Structure of a (host) square matrix: returns (kind, main, off).  Host-side inspection of constant data."""
+    if sparse.issparse(m):
+        m = m.tocoo()
+        n = m.shape[0]
+        offs = np.abs(m.row - m.col)
+        nz = m.data != 0
+        if np.all(offs[nz] == 0):
+            d = np.zeros(n)
+            np.add.at(d, m.row[nz], m.data[nz])
+            return ("eye", None, None) if np.all(d == 1.0) else ("diag", d, None)
+        if np.all(offs[nz] <= 1):
+            d = np.zeros(n)
+            e_lo = np.zeros(n - 1)
+            e_up = np.zeros(n - 1)
+            for r, c, v in zip(m.row[nz], m.col[nz], m.data[nz]):
+                if r == c:
+                    d[r] += v
+                elif r == c + 1:
+                    e_lo[c] += v
+                else:
+                    e_up[r] += v
+            if not np.array_equal(e_lo, e_up):
+                raise NotImplementedError("non-symmetric tridiagonal precision matrix")
+            return "tridiag", d, e_lo
+        if n <= 64:
+            return "dense", np.asarray(m.todense(), dtype=np.float64), None
+        raise NotImplementedError(f"sparse {n}x{n} precision with bandwidth > 1 is not supported by the device path")
+    m = np.asarray(m, dtype=np.float64)
+    n = m.shape[0]
+    if m.ndim == 2 and m.shape[0] == m.shape[1]:
+        offd = m - np.diag(np.diag(m))
+        if not np.any(offd):
+            d = np.diag(m).copy()
+            return ("eye", None, None) if np.all(d == 1.0) else ("diag", d, None)
+        if n > 2 and not np.any(np.triu(m, 2)) and not np.any(np.tril(m, -2)) and n > 64:
+            return "tridiag", np.diag(m).copy(), np.diag(m, -1).copy()
+    return "dense", m, None
+
+
+class DeviceState:
+    """Chain-batched MCMC state resident in HBM (replaces the reference's dict of numpy arrays, mcmc.py:63-76).
+
+    Entries are uploaded lazily from the bound host dict the first time a plan fragment asks for them.
+    """
+
+    def __init__(self, n_chains: int, device: int, host_state: dict = None, per_chain_names=()):
+        self.n_chains = n_chains
+        self.device = torch.device("cuda", device)
+        self.arrays = {}
+        self.host_state = host_state if host_state is not None else {}
+        self.per_chain_names = set(per_chain_names)
+        self.h2d_bytes = 0
+
+    def _t(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.h2d_bytes += a.nbytes
+        return torch.as_tensor(a).to(self.device, non_blocking=False)
+
+    def put(self, name, value, per_chain=None, as_matrix=False):
+        """Upload one entry.  2-D host arrays are shared by all chains unless per_chain=True (then replicated);
+        3-D arrays [C, rows, cols] are per-chain.  torch tensors are moved/bound as they are."""
+        C = self.n_chains
+        if per_chain is None:
+            per_chain = name in self.per_chain_names
+        if isinstance(value, torch.Tensor):
+            if not value.is_cuda:
+                self.h2d_bytes += value.numel() * value.element_size()
+            t = value.to(self.device, F64, non_blocking=True)
+            if t.dim() == 3:
+                if t.shape[0] != C:
+                    raise ValueError(f"state['{name}'] has leading dimension {t.shape[0]} but n_chains={C}")
+                arr = DevArray(t.contiguous(), True, t.shape[1], t.shape[2])
+            else:
+                t = t.reshape(t.shape[0], -1) if t.dim() == 2 else t.reshape(-1, 1)
+                if t.shape[0] == 1 and t.shape[1] > 1:
+                    t = t.t()
+                arr = DevArray(t.contiguous(), False, t.shape[0], t.shape[1])
+                if per_chain:
+                    arr = DevArray(t.unsqueeze(0).repeat(C, 1, 1).contiguous(), True, t.shape[0], t.shape[1])
+            self.arrays[name] = arr
+            return arr
+        if as_matrix or sparse.issparse(value):
+            kind, main, off = classify_matrix(value)
+            n = value.shape[0]
+            if kind == "eye":
+                arr = DevArray(None, False, n, n, "eye")
+            elif kind == "diag":
+                arr = DevArray(self._t(main), False, n, n, "diag")
+            elif kind == "tridiag":
+                arr = DevArray(self._t(main), False, n, n, "tridiag", self._t(off))
+            else:
+                arr = DevArray(self._t(main), False, n, n, "dense")
+            self.arrays[name] = arr
+            return arr
+        a = np.asarray(value, dtype=np.float64)
+        if a.ndim == 3:
+            if a.shape[0] != C:
+                raise ValueError(f"state['{name}'] has leading dimension {a.shape[0]} but n_chains={C}")
+            arr = DevArray(self._t(a), True, a.shape[1], a.shape[2])
+        else:
+            # reference coercion (mcmc.py:65-76): scalars / 1-D -> column vectors, (1,k) lists -> (k,1)
+            if a.ndim < 2:
+                a = np.atleast_2d(a).T
+            elif a.shape[0] == 1 and a.shape[1] > 1 and not isinstance(value, np.ndarray):
+                a = a.T
+            if per_chain:
+                arr = DevArray(self._t(np.broadcast_to(a, (C,) + a.shape)), True, a.shape[0], a.shape[1])
+            else:
+                arr = DevArray(self._t(a), False, a.shape[0], a.shape[1])
+        self.arrays[name] = arr
+        return arr
+
+    def __getitem__(self, name):
+        if name not in self.arrays:
+            if name not in self.host_state:
+                raise KeyError(f"state entry '{name}' is required by the model but missing from the state")
+            self.put(name, self.host_state[name])
+        return self.arrays[name]
+
+    def __contains__(self, name):
+        return name in self.arrays or name in self.host_state
+
+    def get_host(self, name):
+        """Download: per-chain entries come back as [C, rows, cols] (squeezed to [rows, cols] when C == 1)."""
+        a = self.arrays[name]
+        if a.data is None:
+            return sparse.identity(a.rows, format="csc")
+        h = a.data.cpu().numpy()
+        if a.per_chain and self.n_chains == 1:
+            h = h[0]
+        return h
+
+
+# ============================================================================================== plan
+class PlanError(NotImplementedError):
+    """The (model, sampler) combination is outside what the device path implements; raised at compile time."""
+
+
+@dataclass
+class Quantity:
+    """A derived per-chain quantity (e.g. sufficient statistics) with the state entries it depends on."""
+
+    name: str
+    deps: frozenset
+    compute: callable  # emits the kernels that refresh it (may refresh sibling quantities as well)
+    siblings: tuple = ()
+
+
+@dataclass
+class Plan:
+    """Launch list of one sweep plus the store epilogue, built for a fixed (model, samplers, state layout)."""
+
+    state: DeviceState
+    seed: int = 0
+    chain_offset: int = 0
+    quantities: dict = field(default_factory=dict)
+    valid: dict = field(default_factory=dict)
+    ops: list = field(default_factory=list)          # current emission target
+    n_sites: int = 0
+    sweep_counter: torch.Tensor = None
+    iter_counter: torch.Tensor = None
+    status: torch.Tensor = None
+    debug: dict = field(default_factory=dict)         # site name -> injected draw tensors
+    probes: dict = field(default_factory=dict)        # name -> tensor with intermediates (parity tests)
+    keep: list = field(default_factory=list)          # tensors that must outlive the captured graph
+
+    def __post_init__(self):
+        dev = self.state.device
+        self.sweep_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.iter_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(self.state.n_chains, dtype=torch.int32, device=dev)
+
+    # ---- helpers
+    def new(self, *shape, fill=None):
+        t = torch.empty(*shape, dtype=F64, device=self.state.device)
+        if fill is not None:
+            t.fill_(fill)
+        self.keep.append(t)
+        return t
+
+    def rng_site(self):
+        self.n_sites += 1
+        return K.rng(seed=self.seed, sweep=self.sweep_counter, chain_offset=self.chain_offset, site=self.n_sites)
+
+    def ctx(self, sampler):
+        """Per-sampler persistent context (RNG site, injected draws, probes) — compile() may run more than once."""
+        c = self.__dict__.setdefault("_ctx", {})
+        return c.setdefault(id(sampler), {})
+
+    def debug_tensor(self, value, size):
+        """Injected draws -> (device tensor [n_sweeps, C, size], sweep stride).  Accepts [size], [C,size],
+        [n_sweeps,C,size] (trailing singleton dims ignored)."""
+        C = self.state.n_chains
+        a = np.asarray(value, dtype=np.float64)
+        if a.size == size:
+            a = np.broadcast_to(a.reshape(1, 1, size), (1, C, size))
+        elif a.size == C * size:
+            a = a.reshape(1, C, size)
+        else:
+            if a.size % (C * size) != 0:
+                raise ValueError(f"injected draws of size {a.size} do not match n_chains={C} x size={size}")
+            a = a.reshape(-1, C, size)
+        t = torch.as_tensor(np.ascontiguousarray(a)).to(self.state.device)
+        self.keep.append(t)
+        return t, (C * size if a.shape[0] > 1 else 0)
+
+    def emit(self, fn, label):
+        self.ops.append((label, fn))
+
+    def add_quantity(self, q: Quantity):
+        self.quantities[q.name] = q
+        self.valid[q.name] = False
+
+    def require(self, qname):
+        if not self.valid[qname]:
+            q = self.quantities[qname]
+            q.compute()
+            self.valid[qname] = True
+            for s in q.siblings:
+                self.valid[s] = True
+
+    def wrote(self, param):
+        for q in self.quantities.values():
+            if param in q.deps:
+                self.valid[q.name] = False
+
+
+# ---------------------------------------------------------------------------------------------- matching helpers
+def _scalar_and_matrix(precision):
+    """(matrix_name, scalar_name|None) of a precision Parameter."""
+    if isinstance(precision, ScaledMatrix):
+        return precision.matrix, precision.scalar
+    if isinstance(precision, Identity):
+        return precision.form, None
+    raise PlanError(f"precision parameter {type(precision).__name__} is not supported by the device path")
+
+
+def _mat_kind(arr: DevArray):
+    return {"eye": K.MAT_EYE, "diag": K.MAT_DIAG, "dense": K.MAT_DENSE}[arr.kind]
+
+
+def ensure_matrix(state: DeviceState, host_state: dict, name: str) -> DevArray:
+    """(Re-)upload `name` as a structured square matrix (eye/diag/tridiag/dense)."""
+    arr = state.arrays.get(name)
+    if arr is not None and (arr.kind != "dense" or arr.rows != arr.cols or arr.per_chain):
+        return arr
+    return state.put(name, host_state[name], as_matrix=True)
+
+
+class RegressionLikelihood:
+    """y ~ N(X beta (+ nothing else), (tau * W)^-1) with W = I or diag: owner of the fused pass (omc_reg_pass)."""
+
+    def __init__(self, plan: Plan, host_state, dist, param):
+        st = plan.state
+        self.plan = plan
+        self.dist = dist
+        self.param = param
+        form = dist.mean.form
+        if list(form.keys()) != [param]:
+            raise PlanError("LinearCombination means with more than one term are not supported by the device path yet")
+        self.X = st[form[param]]
+        self.y = st[dist.response]
+        self.beta = st[param]
+        if self.y.cols != 1 or self.beta.cols != 1:
+            raise PlanError("replicated responses (n_rep > 1) are not supported by the regression device path yet")
+        self.n, self.p = self.X.rows, self.X.cols
+        if self.p > 64:
+            raise PlanError(f"p={self.p} > 64 regression coefficients are not supported yet")
+        mname, self.scalar = _scalar_and_matrix(dist.precision)
+        W = ensure_matrix(st, host_state, mname)
+        if W.kind not in ("eye", "diag"):
+            raise PlanError("the regression likelihood precision must be (a scalar times) the identity or a diagonal")
+        self.W = W
+        C = st.n_chains
+        self.rec = self.p * self.p + self.p + 2
+        self.stats = plan.new(C, self.rec, fill=0.0)
+        ns, ws = K.reg_pass_workspace(C, self.n, self.p)
+        self.work = plan.new(max(ws, 1))
+        deps_data = frozenset({form[param], dist.response, mname})
+        self.q_gg = f"gram[{dist.response}]"
+        self.q_rss = f"rss[{dist.response}]"
+        plan.add_quantity(Quantity(self.q_gg, deps_data, self._emit_pass, (self.q_rss,)))
+        plan.add_quantity(Quantity(self.q_rss, deps_data | {param}, self._emit_pass, (self.q_gg,)))
+
+    def _emit_pass(self):
+        C, n, p = self.plan.state.n_chains, self.n, self.p
+        X, y, W, beta, stats, work = self.X, self.y, self.W, self.beta, self.stats, self.work
+        w = W.data if W.kind == "diag" else None
+
+        def launch():
+            K.reg_pass(X.data, y.data, w, beta.data, stats, work, C, n, p, x_shared=not X.per_chain,
+                       y_shared=not y.per_chain, w_shared=True)
+
+        self.plan.emit(launch, "reg_pass")
+
+    # views into the record
+    def rss_vec(self):
+        return K.vec((self.stats[:, self.p * self.p + self.p:], self.rec))
+
+    def cnt_vec(self):
+        return K.vec((self.stats[:, self.p * self.p + self.p + 1:], self.rec))
+
+
+def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
+    """Fitted values store[response][:, it] = dist.<predictor>.predictor(state).  ref: mcmc.py:109-111."""
+    st = plan.state
+    C = st.n_chains
+    par = getattr(dist, predictor)
+    n = st[dist.response].rows
+    buf = plan.new(n_iter, C, n, fill=float("nan"))
+    if isinstance(par, LinearCombination):
+        now = plan.new(C, n)
+        terms = []
+        for prm, pref in par.form.items():
+            X, th = st[pref], st[prm]
+            if X.kind != "dense" or th.cols != 1:
+                raise PlanError("fitted values: unsupported LinearCombination term")
+            terms.append((X, th))
+        if len(terms) > 4:
+            raise PlanError("fitted values: more than 4 LinearCombination terms")
+
+        def launch():
+            K.linear_predictor(C, n, [(X.vec(), th.vec(), X.cols) for X, th in terms], now)
+            K.store_copy(now, buf, C * n, plan.iter_counter, n_iter)
+
+        plan.emit(launch, f"fitted[{dist.response}]")
+    elif isinstance(par, Identity):
+        src = st[par.form]
+        if not src.per_chain:
+            src = st.put(par.form, src.data, per_chain=True)
+
+        def launch():
+            K.store_copy(src.data, buf, C * n, plan.iter_counter, n_iter)
+
+        plan.emit(launch, f"fitted[{dist.response}]")
+    else:
+        raise PlanError(f"fitted values for {type(par).__name__} are not supported on the device")
+    return buf
+
+
+def as_chain_tensor(value, n_chains, size, device):
+    """Injected draws: accept [size], [size,1], [C,size] or [C,size,1]; broadcast over chains."""
+    a = np.asarray(value, dtype=np.float64)
+    if a.size == size:
+        a = np.broadcast_to(a.reshape(1, size), (n_chains, size))
+    else:
+        a = a.reshape(n_chains, size)
+    return torch.as_tensor(np.ascontiguousarray(a)).to(device)
+
+
+def get_regression(plan: Plan, host_state, lik, param) -> RegressionLikelihood:
+    cache = plan.__dict__.setdefault("_regressions", {})
+    key = lik.response
+    if key not in cache:
+        cache[key] = RegressionLikelihood(plan, host_state, lik, param)
+    return cache[key]
+
+
+def get_quadratic_form(plan: Plan, host_state, nrm):
+    """Quadratic form r' P r (P un-scaled) and #(diag P > 0) of a Normal distribution's residual.
+
+    Returns (ss_vec_fn, cnt_vec_fn, quantity_name).  ref: sampler.py:275-284.
+    """
+    st = plan.state
+    if isinstance(nrm.mean, LinearCombination):
+        params = list(nrm.mean.form.keys())
+        rl = get_regression(plan, host_state, nrm, params[0])
+        return rl.rss_vec, rl.cnt_vec, rl.q_rss
+    if not isinstance(nrm.mean, Identity):
+        raise PlanError(f"unsupported Normal mean {type(nrm.mean).__name__}")
+    cache = plan.__dict__.setdefault("_quadforms", {})
+    key = nrm.response
+    if key in cache:
+        return cache[key]
+    mname, _ = _scalar_and_matrix(nrm.precision)
+    P = ensure_matrix(st, host_state, mname)
+    x, mu = st[nrm.response], st[nrm.mean.form]
+    C = st.n_chains
+    if x.cols != 1:
+        raise PlanError("replicated responses (n_rep > 1) are not supported by the device quadratic form yet")
+    if P.kind == "tridiag" or x.rows > 4096:
+        from openmcmc_b200 import gmrf_plan
+
+        out = gmrf_plan.long_quadratic_form(plan, nrm, P, x, mu)
+        cache[key] = out
+        return out
+    ss, cnt = plan.new(C), plan.new(C)
+    qname = f"quad[{nrm.response}]"
+    p = x.rows
+
+    def compute():
+        def launch():
+            K.quadform(C, p, x.vec(), mu.vec(), _mat_kind(P), P.vec(), ss, cnt)
+
+        plan.emit(launch, f"quadform[{nrm.response}]")
+
+    plan.add_quantity(Quantity(qname, frozenset({nrm.response, nrm.mean.form, mname}), compute))
+    out = (lambda: K.vec(ss, 1), lambda: K.vec(cnt, 1), qname)
+    cache[key] = out
+    return out
+
+
+def logdet_of(plan: Plan, P: DevArray):
+    """log|P| of a constant structured matrix, computed once on the device at plan time (None => 0)."""
+    if P.kind == "eye":
+        return None
+    C = plan.state.n_chains
+    out = plan.new(1 if not P.per_chain else C)
+    if P.kind == "diag":
+        K.sum_log(P.data, P.rows, out)
+    elif P.kind == "dense":
+        K.logdet_dense(P.data, P.rows, out)
+    else:
+        from openmcmc_b200 import gmrf_plan
+
+        gmrf_plan.tridiag_logdet(plan, P, out)
+    return out
+
+
+def compile_log_post(plan: Plan, host_state, model, out):
+    """Emit kernels accumulating model.log_p(state) per chain into `out` [C].  ref: mcmc.py:108, model.py:57-70."""
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal, NullDistribution
+
+    st = plan.state
+    C = st.n_chains
+    first = True
+    for dist in model.values():
+        acc = 0 if first else 1
+        if isinstance(dist, NullDistribution):
+            continue
+        if isinstance(dist, Normal):
+            if dist.domain_response_lower is not None or dist.domain_response_upper is not None:
+                raise PlanError("log_post with truncated Normal members is not supported on the device yet")
+            mname, sname = _scalar_and_matrix(dist.precision)
+            ss_vec, _, qname = get_quadratic_form(plan, host_state, dist)
+            P = ensure_matrix(st, host_state, mname)
+            logdet = logdet_of(plan, P)
+            scal = st[sname] if sname else None
+            dim = st[dist.response].rows
+            plan.require(qname)
+
+            def launch(dim=dim, ss_vec=ss_vec, scal=scal, logdet=logdet, acc=acc):
+                K.logp_normal_ss(C, dim, ss_vec(), scal.vec() if scal else K.vec(None),
+                                 K.vec(logdet) if logdet is not None else K.vec(None), out, acc)
+
+            plan.emit(launch, f"logp_normal[{dist.response}]")
+        elif isinstance(dist, Gamma):
+            x = st[dist.response]
+            if not isinstance(dist.shape, Identity) or not isinstance(dist.rate, Identity):
+                raise PlanError("log_post: Gamma with non-Identity shape/rate is not supported on the device yet")
+            sh, rt = st[dist.shape.form], st[dist.rate.form]
+
+            def launch(x=x, sh=sh, rt=rt, acc=acc):
+                K.logp_gamma(C, x.size, x.vec(), sh.vec(), sh.size, rt.vec(), rt.size, out, acc)
+
+            plan.emit(launch, f"logp_gamma[{dist.response}]")
+        elif isinstance(dist, Poisson):
+            k = st[dist.response]
+            if not isinstance(dist.rate, Identity):
+                raise PlanError("log_post: Poisson with non-Identity rate is not supported on the device yet")
+            rt = st[dist.rate.form]
+
+            def launch(k=k, rt=rt, acc=acc):
+                K.logp_poisson(C, k.size, k.vec(), rt.vec(), rt.size, out, acc)
+
+            plan.emit(launch, f"logp_poisson[{dist.response}]")
+        elif isinstance(dist, Uniform):
+            x = st[dist.response]
+            rng_ = np.broadcast_to(dist.domain_response_upper - dist.domain_response_lower, (x.rows, 1))
+            value = -float(np.sum(np.log(rng_))) * x.cols
+
+            def launch(value=value, acc=acc):
+                K.logp_const(value, C, out, acc)
+
+            plan.emit(launch, f"logp_uniform[{dist.response}]")
+        else:
+            raise PlanError(f"log_post: distribution {type(dist).__name__} is not supported on the device")
+        first = False
+    if first:
+
+        def launch():
+            K.logp_const(0.0, C, out, 0)
+
+        plan.emit(launch, "logp_zero")

@@ -1,0 +1,101 @@
+"""Host-array entry points: run ONE device operation on a reference-style dict state (numpy in, numpy out).
+
+This is what `sampler.sample(state)`, `dist.log_p(state)`, `model.grad_log_p(...)` and `param.predictor(state)` call
+when used exactly like the reference objects (n_chains = 1, host arrays).  Each call uploads what it needs, launches
+the same CUDA kernels the resident sweep plan uses, and downloads the result — host<->device copies included, which is
+what bench.py's `e2e` leg measures.  There is no CPU arithmetic here.
+"""
+
+import itertools
+
+import numpy as np
+import torch
+
+from openmcmc_b200 import engine
+from openmcmc_b200 import kernels as K
+
+_call_counter = itertools.count(1)
+_default_seed = 0
+
+
+def set_seed(seed: int):
+    """Seed for the single-call (`.sample(state)`) RNG stream; the reference uses numpy's global RandomState."""
+    global _default_seed, _call_counter
+    _default_seed = int(seed)
+    _call_counter = itertools.count(1)
+
+
+def _run_ops(ops):
+    for _, fn in ops:
+        fn()
+
+
+def sample_once(sampler, state: dict, debug_draws: dict = None) -> dict:
+    """ref: MCMCSampler.sample contract (sampler.py:57-67): returns the state with state[param] replaced."""
+    dev = K.init_device()
+    st = engine.DeviceState(1, dev, state, per_chain_names={sampler.param})
+    plan = engine.Plan(st, seed=_default_seed)
+    plan.sweep_counter.fill_(next(_call_counter))
+    sampler.compile(plan, state, debug_draws)
+    _run_ops(plan.ops)
+    torch.cuda.synchronize()
+    status = int(plan.status.max().item())
+    if status & 1:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")  # reference: np.linalg.cholesky raises
+    new = st.get_host(sampler.param)
+    old = state[sampler.param]
+    state[sampler.param] = new.reshape(np.shape(old)) if np.ndim(old) == 2 else new
+    if hasattr(sampler, "_after_sample"):
+        sampler._after_sample(plan)
+    return state
+
+
+def linear_predictor(state: dict, terms):
+    """sum_t state[X_t] @ state[theta_t]  (ref: parameter.py:174-197) on the device."""
+    if not terms:
+        return 0
+    dev = K.init_device()
+    st = engine.DeviceState(1, dev, state)
+    n = None
+    vt = []
+    n_rep = 1
+    for xname, tname in terms:
+        X, th = st[xname], st[tname]
+        if X.kind != "dense":
+            raise engine.PlanError("LinearCombination.predictor with structured prefactors is not supported yet")
+        if th.cols != 1:
+            raise engine.PlanError("LinearCombination.predictor with replicated parameters is not supported yet")
+        n = X.rows
+        vt.append((X.vec(), th.vec(), X.cols))
+    out = torch.empty(1, n, dtype=torch.float64, device=st.device)
+    for i in range(0, len(vt), 4):
+        part = out if i == 0 else torch.empty_like(out)
+        K.linear_predictor(1, n, vt[i:i + 4], part)
+        if i:
+            raise engine.PlanError("LinearCombination with more than 4 terms is not supported yet")
+    torch.cuda.synchronize()
+    return out.cpu().numpy().reshape(n, n_rep)
+
+
+def scaled_matrix(state: dict, matrix: str, scalar: str):
+    raise engine.PlanError(
+        "ScaledMatrix.predictor materialises scalar*matrix on the host in the reference (parameter.py:329); the device "
+        "path never forms it (kernels take the scalar and the un-scaled matrix separately)")
+
+
+def log_p(dist, state: dict, by_observation: bool = False):
+    from openmcmc_b200 import devdist
+
+    return devdist.log_p_host(dist, state, by_observation)
+
+
+def grad_log_p(dist, state: dict, param: str, hessian_required: bool, method: str):
+    from openmcmc_b200 import devdist
+
+    return devdist.grad_log_p_host(dist, state, param, hessian_required, method)
+
+
+def rvs(dist, state: dict, n: int = 1):
+    from openmcmc_b200 import devdist
+
+    return devdist.rvs_host(dist, state, n)

@@ -82,7 +82,7 @@ def reg_pass(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_
 
 
 def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, rng_, debug_z=None, probe_Q=None,
-                  probe_b=None, probe_L=None, probe_mu=None, status=None):
+                  probe_b=None, probe_L=None, probe_mu=None, status=None, debug_sweep_stride=0):
     a = _cabi.NNDense()
     a.n_chains, a.p = n_chains, p
     a.stats = Vec(stats.data_ptr(), p * p + p + 2)
@@ -90,6 +90,7 @@ def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, 
     a.beta = beta.data_ptr()
     a.rng = rng_
     a.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    a.debug_sweep_stride = int(debug_sweep_stride)
     a.probe_Q = probe_Q.data_ptr() if probe_Q is not None else None
     a.probe_b = probe_b.data_ptr() if probe_b is not None else None
     a.probe_L = probe_L.data_ptr() if probe_L is not None else None
@@ -105,15 +106,56 @@ def quadform(n_chains, p, x, mu, kind, P, ss, cnt):
     check(lib().omc_quadform(C.byref(a), stream_ptr()), "omc_quadform")
 
 
-def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None):
+def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None, debug_sweep_stride=0):
     a = _cabi.NGDraw()
     a.n_chains, a.a0, a.b0, a.ss, a.cnt = n_chains, a0, b0, ss, cnt
     a.out = out.data_ptr()
     a.rng = rng_
     a.debug_g = debug_g.data_ptr() if debug_g is not None else None
+    a.debug_sweep_stride = int(debug_sweep_stride)
     a.probe_a = probe_a.data_ptr() if probe_a is not None else None
     a.probe_b = probe_b.data_ptr() if probe_b is not None else None
     check(lib().omc_ng_draw(C.byref(a), stream_ptr()), "omc_ng_draw")
+
+
+# ----------------------------------------------------------------------------- log densities / predictors
+def logp_normal_ss(n_chains, dim, ss, scalar, logdet, out, accumulate):
+    a = _cabi.LogpNormalSS(n_chains, float(dim), ss, scalar, logdet, out.data_ptr(), int(accumulate))
+    check(lib().omc_logp_normal_ss(C.byref(a), stream_ptr()), "omc_logp_normal_ss")
+
+
+def logp_gamma(n_chains, n_elem, x, shape, shape_len, rate, rate_len, out, accumulate):
+    a = _cabi.LogpGamma(n_chains, n_elem, shape_len, rate_len, x, shape, rate, out.data_ptr(), int(accumulate))
+    check(lib().omc_logp_gamma(C.byref(a), stream_ptr()), "omc_logp_gamma")
+
+
+def logp_poisson(n_chains, n_elem, k, rate, rate_len, out, accumulate):
+    a = _cabi.LogpPoisson(n_chains, n_elem, rate_len, k, rate, out.data_ptr(), int(accumulate))
+    check(lib().omc_logp_poisson(C.byref(a), stream_ptr()), "omc_logp_poisson")
+
+
+def logp_const(value, n_chains, out, accumulate):
+    check(lib().omc_logp_const(float(value), n_chains, _ptr(out), int(accumulate), stream_ptr()), "omc_logp_const")
+
+
+def linear_predictor(n_chains, n, terms, out):
+    """terms: list of (X_vec, theta_vec, p)."""
+    a = _cabi.LinearPredictor()
+    a.n_chains, a.n, a.n_terms = n_chains, n, len(terms)
+    for i, (xv, tv, p) in enumerate(terms):
+        a.p[i] = p
+        a.X[i] = xv
+        a.theta[i] = tv
+    a.out = out.data_ptr()
+    check(lib().omc_linear_predictor(C.byref(a), stream_ptr()), "omc_linear_predictor")
+
+
+def sum_log(x, n, out):
+    check(lib().omc_sum_log(_ptr(x), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_sum_log")
+
+
+def logdet_dense(P, n, out):
+    check(lib().omc_logdet_dense(_ptr(P), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_logdet_dense")
 
 
 # ----------------------------------------------------------------------------- graphs / schedule

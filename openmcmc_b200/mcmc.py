@@ -1,0 +1,192 @@
+"""MCMC driver (host-side mirror of `openmcmc.mcmc.MCMC`).  ref: mcmc.py:18-115
+
+Same constructor and `run_mcmc()` / `.store` / `.state` surface as the reference, plus keyword extras for the batched
+device engine: `n_chains`, `seed`, `device`, `chain_offset`, `debug_draws`.  `run_mcmc()` uploads the state once,
+compiles the (model, samplers) pair into a sweep plan, captures one sweep as a CUDA graph, replays it
+(n_burn + n_iter) * n_thin times with the chain state resident in HBM, and brings the stored samples back.
+"""
+
+from copy import copy
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from openmcmc_b200 import engine
+from openmcmc_b200 import kernels as K
+from openmcmc_b200.model import Model
+
+
+@dataclass
+class MCMC:
+    """ref: mcmc.py:18-85.  For n_chains == 1 `store[param]` has the reference shape (size, n_iter); for n_chains > 1
+    it is (n_chains, size, n_iter) and `store["log_post"]` is (n_iter, n_chains)."""
+
+    state: dict
+    samplers: list
+    model: Model
+    n_burn: int = 5000
+    n_iter: int = 5000
+    n_thin: int = 1
+    n_chains: int = 1
+    seed: int = 0
+    device: int = None
+    chain_offset: int = 0
+    debug_draws: dict = None   # {param: {"z"|"g"|"u": array [n_sweeps, (C,) size]}} injected random streams
+    probes: bool = False       # keep per-sampler intermediates (Q, b, L, mu, a*, b*) of the LAST sweep
+    store: dict = field(default_factory=dict, init=False)
+
+    def __post_init__(self):
+        """State coercion as mcmc.py:63-76 (host side: shapes only).  Missing sampled parameters are drawn from their
+        prior on the device (mcmc.py:78-80)."""
+        self.state = copy(self.state)
+        for key, term in self.state.items():
+            if sparse.issparse(term) or isinstance(term, torch.Tensor):
+                continue
+            if not isinstance(term, np.ndarray):
+                term = np.array(term, ndmin=2, dtype=np.float64)
+                if np.shape(term)[0] == 1:
+                    term = term.T
+            elif term.ndim < 2:
+                term = np.atleast_2d(term).T
+            self.state[key] = term
+        for sampler in self.samplers:
+            if sampler.param not in self.state:
+                self.state[sampler.param] = sampler.model[sampler.param].rvs(self.state)
+        self._prepared = None
+        self.status = None
+        self.timing = {}
+
+    # ------------------------------------------------------------------ device pipeline
+    def prepare(self):
+        """Upload + compile + capture.  Returns self (idempotent)."""
+        if self._prepared is not None:
+            return self
+        dev = K.init_device(self.device)
+        C = self.n_chains
+        sampled = {s.param for s in self.samplers}
+        st = engine.DeviceState(C, dev, self.state, per_chain_names=sampled)
+        self.stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self.stream):
+            plan = engine.Plan(st, seed=self.seed, chain_offset=self.chain_offset)
+            plan.probes = {"enable": True} if self.probes else {}
+            dd = self.debug_draws or {}
+            # pass A (dry): learn which derived quantities are valid at the end of a sweep
+            plan.ops = []
+            for s in self.samplers:
+                s.compile(plan, self.state, dd.get(s.param))
+            valid_end = dict(plan.valid)
+            # pass B: steady-state sweep, assuming the end-of-sweep validity at its start
+            plan.ops = sweep_ops = []
+            for s in self.samplers:
+                s.compile(plan, self.state, dd.get(s.param))
+            if plan.valid != valid_end:  # no fixed point (should not happen): fall back to the cold sweep
+                plan.valid = {k: False for k in plan.valid}
+                plan.ops = sweep_ops = []
+                for s in self.samplers:
+                    s.compile(plan, self.state, dd.get(s.param))
+                valid_end = {k: False for k in plan.valid}
+            sweep_ops.append(("sweep_counter", lambda: K.counter_add(plan.sweep_counter, 1)))
+            # store epilogue (ref: mcmc.py:105-111)
+            plan.ops = store_ops = []
+            n_iter = max(self.n_iter, 1)
+            self._dev_store = {}
+            for s in self.samplers:
+                arr = st[s.param]
+                buf = plan.new(n_iter, C, arr.size, fill=float("nan"))
+                self._dev_store[s.param] = buf
+                store_ops.append((f"store[{s.param}]", (lambda arr=arr, buf=buf: K.store_copy(
+                    arr.data, buf, C * arr.size, plan.iter_counter, n_iter))))
+            self._dev_logpost = plan.new(n_iter, C, fill=float("nan"))
+            self._logpost_now = plan.new(C)
+            saved_valid = dict(plan.valid)
+            engine.compile_log_post(plan, self.state, self.model, self._logpost_now)
+            store_ops.append(("store[log_post]", lambda: K.store_copy(self._logpost_now, self._dev_logpost, C,
+                                                                        plan.iter_counter, n_iter)))
+            self._dev_fitted = {}
+            if self.model.response is not None:
+                for response, predictor in self.model.response.items():
+                    self._dev_fitted[response] = engine.compile_fitted(plan, self.state, self.model[response],
+                                                                       predictor, n_iter)
+            store_ops.append(("iter_counter", lambda: K.counter_add(plan.iter_counter, 1)))
+            plan.valid = saved_valid
+            # prologue: quantities the steady-state sweep assumes valid, computed from the initial state
+            plan.ops = prologue_ops = []
+            done = set()
+            for qname, ok in valid_end.items():
+                if ok and qname not in done:
+                    q = plan.quantities[qname]
+                    q.compute()
+                    done.add(qname)
+                    done.update(q.siblings)
+            self.plan = plan
+            self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
+            self._sweep_graph = K.Graph.capture(lambda: [fn() for _, fn in sweep_ops])
+            self._store_graph = K.Graph.capture(lambda: [fn() for _, fn in store_ops])
+            for _, fn in prologue_ops:
+                fn()
+        self.stream.synchronize()
+        self._prepared = st
+        return self
+
+    def launches_per_sweep(self) -> int:
+        self.prepare()
+        return self._sweep_graph.num_kernels()
+
+    def run_device(self, n_burn=None, n_iter=None, n_thin=None):
+        """Replay the captured sweep graph on the engine's stream (asynchronous)."""
+        self.prepare()
+        n_burn = self.n_burn if n_burn is None else n_burn
+        n_iter = self.n_iter if n_iter is None else n_iter
+        n_thin = self.n_thin if n_thin is None else n_thin
+        with torch.cuda.stream(self.stream):
+            K.run_schedule(self._sweep_graph, self._store_graph, n_burn, n_iter, n_thin)
+
+    def collect(self):
+        """Download the stored samples and the final state (ref shapes; see class docstring)."""
+        st = self._prepared
+        self.stream.synchronize()
+        C = self.n_chains
+        n_done = int(self.plan.iter_counter.item())
+        self.store = {}
+        d2h = 0
+        for s in self.samplers:
+            buf = self._dev_store[s.param][: self.n_iter].cpu().numpy()      # [n_iter, C, size]
+            d2h += buf.nbytes
+            arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
+            self.store[s.param] = arr[0] if C == 1 else arr
+        lp = self._dev_logpost[: self.n_iter].cpu().numpy()
+        d2h += lp.nbytes
+        self.store["log_post"] = lp.reshape(self.n_iter, 1) if C == 1 else lp
+        for response, buf in self._dev_fitted.items():
+            h = buf[: self.n_iter].cpu().numpy()
+            d2h += h.nbytes
+            arr = np.transpose(h, (1, 2, 0))
+            self.store[response] = arr[0] if C == 1 else arr
+        for s in self.samplers:
+            new = st.get_host(s.param)
+            self.state[s.param] = new
+            d2h += new.nbytes
+        self.status = self.plan.status.cpu().numpy()
+        self.timing["d2h_bytes"] = d2h
+        self.timing["h2d_bytes"] = st.h2d_bytes
+        self.timing["stored_iterations"] = n_done
+        return self.store
+
+    def run_mcmc(self):
+        """ref: mcmc.py:87-115"""
+        self.prepare()
+        self.run_device()
+        self.collect()
+        if np.any(self.status & 1):
+            bad = int(np.sum((self.status & 1) != 0))
+            if self.n_chains == 1:
+                raise np.linalg.LinAlgError("Matrix is not positive definite")
+            print(f"warning: {bad} chain(s) hit a non-positive-definite precision (status bit 1)")
+        from openmcmc_b200.sampler.metropolis_hastings import MetropolisHastings
+
+        for sampler in self.samplers:
+            if isinstance(sampler, MetropolisHastings):
+                sampler._collect_accept(self.plan)
+                print(f"{sampler.param}: {sampler.accept_rate.get_acceptance_rate()}")

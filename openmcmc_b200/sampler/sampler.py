@@ -1,0 +1,198 @@
+"""MCMCSampler base class and the conjugate samplers NormalNormal / NormalGamma.  ref: sampler/sampler.py:37-288
+
+The classes keep the reference's constructor signatures and `.sample(state) -> state` contract.  Numerically they are
+*plan fragments*: `compile(plan, host_state)` appends the CUDA kernel launches of one update to the sweep plan
+(engine.Plan); `.sample()` on a host dict compiles and runs a one-sampler plan on the device (n_chains = 1).
+MixtureAllocation is SURVEY §8 f2 ("next") and not provided in round 1.
+"""
+
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from typing import Union
+
+import numpy as np
+
+from openmcmc_b200 import engine
+from openmcmc_b200 import kernels as K
+from openmcmc_b200.distribution.location_scale import Normal
+from openmcmc_b200.model import Model
+from openmcmc_b200.parameter import Identity, LinearCombination, MixtureParameterMatrix, ScaledMatrix
+
+
+@dataclass
+class MCMCSampler(ABC):
+    """ref: sampler.py:37-118"""
+
+    param: str
+    model: Model
+    max_variable_size: Union[int, tuple, None] = None
+
+    def __post_init__(self):
+        self.model = self.model.conditional(self.param)
+
+    def sample(self, current_state: dict, debug_draws: dict = None) -> dict:
+        """Generate the next sample of self.param on the device and return the updated state dict.
+
+        `debug_draws` (extension) injects the reference's random streams, e.g. {"z": ...} for NormalNormal,
+        {"g": ...} for NormalGamma (standard-gamma variates), mirroring the reference tests' rvs patches.
+        """
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.sample_once(self, current_state, debug_draws)
+
+    @abstractmethod
+    def compile(self, plan: "engine.Plan", host_state: dict, debug_draws: dict = None):
+        """Append this sampler's kernel launches to the sweep plan."""
+
+    def init_store(self, current_state: dict, store: dict, n_iterations: int) -> dict:
+        """ref: sampler.py:69-87"""
+        if self.max_variable_size is None:
+            store[self.param] = np.full(shape=(np.size(current_state[self.param]), n_iterations), fill_value=np.nan)
+        elif isinstance(self.max_variable_size, tuple):
+            store[self.param] = np.full(shape=self.max_variable_size + (n_iterations,), fill_value=np.nan)
+        else:
+            store[self.param] = np.full(shape=(self.max_variable_size, n_iterations), fill_value=np.nan)
+        return store
+
+    def store(self, current_state: dict, store: dict, iteration: int) -> dict:
+        """ref: sampler.py:89-118 (host copy of one column; the device path stores with omc_store_copy instead)"""
+        current_param = np.asarray(current_state[self.param])
+        if self.max_variable_size is None:
+            store[self.param][:, [iteration]] = current_param.reshape(-1, 1)
+        elif isinstance(self.max_variable_size, tuple):
+            index_list = [np.arange(current_param.shape[dim], dtype=int) for dim in range(current_param.ndim)]
+            index_list.append(np.array([iteration]))
+            store[self.param][np.ix_(*index_list)] = current_param.reshape(current_param.shape + (1,))
+        else:
+            store[self.param][range(current_param.size), [iteration]] = current_param.flatten()
+        return store
+
+
+@dataclass
+class NormalNormal(MCMCSampler):
+    """Normal-Normal conjugate update.  ref: sampler.py:121-207
+
+    Device paths (chosen from the model structure at compile time):
+      * dense   : one Normal likelihood with mean X @ param (LinearCombination), diagonal/identity response precision,
+                  any small (p <= 64) prior precision          -> omc_reg_pass + omc_nn_dense_draw
+      * banded  : one Normal likelihood with mean = param (Identity), diagonal/identity response precision, tridiagonal
+                  prior precision (temporal GMRF)              -> omc_tridiag_nn_draw
+    Truncated priors (gibbs_canonical_truncated_normal) are SURVEY §8 f3 ("next").
+    """
+
+    def __post_init__(self):
+        super().__post_init__()
+        self._is_response = {key: key == self.param for key in self.model.keys()}
+
+    def compile(self, plan, host_state, debug_draws=None):
+        prior = self.model[self.param]
+        if not isinstance(prior, Normal):
+            raise engine.PlanError("NormalNormal needs a Normal prior on the sampled parameter")
+        if prior.domain_response_lower is not None or prior.domain_response_upper is not None:
+            raise engine.PlanError("truncated NormalNormal is outside the round-1 hot path (SURVEY.md §8 f3)")
+        liks = [d for k, d in self.model.items() if not self._is_response[k]]
+        if len(liks) != 1 or not isinstance(liks[0], Normal):
+            raise engine.PlanError("the device NormalNormal supports exactly one Normal likelihood term")
+        lik = liks[0]
+        if isinstance(lik.mean, LinearCombination):
+            return self._compile_dense(plan, host_state, prior, lik, debug_draws)
+        if isinstance(lik.mean, Identity) and lik.mean.form == self.param:
+            from openmcmc_b200 import gmrf_plan
+
+            return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, lik, debug_draws)
+        raise engine.PlanError(f"NormalNormal: unsupported likelihood mean {type(lik.mean).__name__}")
+
+    def _compile_dense(self, plan, host_state, prior, lik, debug_draws):
+        st = plan.state
+        C = st.n_chains
+        rl = engine.get_regression(plan, host_state, lik, self.param)
+        p = rl.p
+        if not isinstance(prior.mean, Identity):
+            raise engine.PlanError("NormalNormal: prior mean must be an Identity parameter")
+        mu0 = st[prior.mean.form]
+        pm_name, lam_name = engine._scalar_and_matrix(prior.precision)
+        P0 = engine.ensure_matrix(st, host_state, pm_name)
+        if P0.kind == "tridiag":
+            raise engine.PlanError("tridiagonal prior with a regression likelihood is not supported")
+        lam = st[lam_name] if lam_name else None
+        tau = st[rl.scalar] if rl.scalar else None
+        beta = st[self.param]
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["dz"], ctx["dz_stride"] = (None, 0)
+            if debug_draws and "z" in debug_draws:
+                ctx["dz"], ctx["dz_stride"] = plan.debug_tensor(debug_draws["z"], p)
+            ctx["probes"] = None
+            if plan.probes is not None and plan.probes.get("enable"):
+                probes = {k: plan.new(C, p, p) for k in ("Q", "L")}
+                probes.update({k: plan.new(C, p) for k in ("b", "mu")})
+                plan.probes[self.param] = ctx["probes"] = probes
+        rng, dz, dz_stride, probes = ctx["rng"], ctx["dz"], ctx["dz_stride"], ctx["probes"]
+        plan.require(rl.q_gg)
+
+        def launch():
+            K.nn_dense_draw(
+                C, p, rl.stats, tau.vec() if tau else K.vec(None), engine._mat_kind(P0), P0.vec(),
+                lam.vec() if lam else K.vec(None), mu0.vec(), beta.data, rng, debug_z=dz,
+                probe_Q=probes["Q"] if probes else None, probe_b=probes["b"] if probes else None,
+                probe_L=probes["L"] if probes else None, probe_mu=probes["mu"] if probes else None, status=plan.status,
+                debug_sweep_stride=dz_stride)
+
+        plan.emit(launch, f"nn_dense_draw[{self.param}]")
+        plan.wrote(self.param)
+
+
+@dataclass
+class NormalGamma(MCMCSampler):
+    """Normal-Gamma conjugate update of a scalar precision.  ref: sampler.py:210-288
+
+    The quadratic form r' P r comes from whichever kernel owns the Normal distribution's residual: the regression pass
+    (likelihood precision), omc_quadform (small prior precision) or the tridiagonal kernels (GMRF).
+    MixtureParameterMatrix precisions (the K-loop at sampler.py:281-284) are SURVEY §8 f2 ("next").
+    """
+
+    def __post_init__(self):
+        super().__post_init__()
+        nrm_prm = list(self.model.keys())
+        nrm_prm.remove(self.param)
+        self.normal_param = nrm_prm[0]
+        precision = self.model[self.normal_param].precision
+        if not isinstance(precision, (Identity, ScaledMatrix, MixtureParameterMatrix)):
+            raise TypeError("precision must be either Identity, ScaledMatrix or MixtureParameterMatrix")
+
+    def compile(self, plan, host_state, debug_draws=None):
+        from openmcmc_b200.distribution.distribution import Gamma
+
+        st = plan.state
+        C = st.n_chains
+        gam = self.model[self.param]
+        nrm = self.model[self.normal_param]
+        if not isinstance(gam, Gamma) or not isinstance(gam.shape, Identity) or not isinstance(gam.rate, Identity):
+            raise engine.PlanError("NormalGamma needs a Gamma prior with Identity shape and rate")
+        if not isinstance(nrm.precision, ScaledMatrix) or nrm.precision.scalar != self.param:
+            raise engine.PlanError("NormalGamma: the Normal precision must be ScaledMatrix(matrix, scalar=param)")
+        out = st[self.param]
+        if out.size != 1:
+            raise engine.PlanError("vector-valued NormalGamma (mixture precisions) is SURVEY §8 f2 (next)")
+        ss_vec, cnt_vec, qname = engine.get_quadratic_form(plan, host_state, nrm)
+        a0, b0 = st[gam.shape.form], st[gam.rate.form]
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["dg"], ctx["dg_stride"] = (None, 0)
+            if debug_draws and "g" in debug_draws:
+                ctx["dg"], ctx["dg_stride"] = plan.debug_tensor(debug_draws["g"], 1)
+            ctx["probes"] = None
+            if plan.probes is not None and plan.probes.get("enable"):
+                plan.probes[self.param] = ctx["probes"] = {"a": plan.new(C), "b": plan.new(C)}
+        rng, dg, dg_stride, probes = ctx["rng"], ctx["dg"], ctx["dg_stride"], ctx["probes"]
+        plan.require(qname)
+
+        def launch():
+            K.ng_draw(C, a0.vec(), b0.vec(), ss_vec(), cnt_vec(), out.data, rng, debug_g=dg,
+                      probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
+                      debug_sweep_stride=dg_stride)
+
+        plan.emit(launch, f"ng_draw[{self.param}]")
+        plan.wrote(self.param)

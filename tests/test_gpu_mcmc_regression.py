@@ -1,0 +1,176 @@
+"""GPU parity: the full MCMC driver on the Gibbs regression model (BASELINE configs[0] shape and friends) replays the
+reference's golden chains when the reference's random streams are injected (debug_draws).  Tolerance 1e-9 on draws,
+1e-10 on deterministic quantities (BASELINE.json north_star)."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "regression_*.npz")))
+
+
+def build(g, n_chains=1, response=True):
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    X, y, mu = g["X"], g["y"], g["mu"]
+    n, p = X.shape
+    P_tau = sparse.diags(g["w"], format="csc") if g["w"].size else sparse.csc_matrix(np.eye(n))
+    P_lambda = g["P_lambda"]
+    if str(g["prior"]) != "dense":
+        P_lambda = sparse.csc_matrix(P_lambda)
+    mdl = Model(
+        [Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
+         Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+         Gamma("tau", shape="a_tau", rate="b_tau"),
+         Gamma("lambda", shape="a_lambda", rate="b_lambda")],
+        response={"y": "mean"} if response else None,
+    )
+    smap = {"beta": NormalNormal("beta", mdl), "tau": NormalGamma("tau", mdl), "lambda": NormalGamma("lambda", mdl)}
+    samplers = [smap[str(k)] for k in g["order"]]
+    state = {"y": y, "X": X, "beta": np.zeros((p, 1)), "P_tau": P_tau, "tau": 1.0, "P_lambda": P_lambda, "mu": mu,
+             "lambda": 0.01, "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3, "b_lambda": 1e-3}
+    return mdl, samplers, state
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_mcmc_replays_reference_chain(name):
+    from openmcmc_b200.mcmc import MCMC
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    mdl, samplers, state = build(g)
+    n_iter = g["store_beta"].shape[1]
+    dd = {"beta": {"z": g["z"]}, "tau": {"g": g["g_tau"]}, "lambda": {"g": g["g_lambda"]}}
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, debug_draws=dd)
+    M.run_mcmc()
+    assert M.store["beta"].shape == g["store_beta"].shape
+    assert M.store["tau"].shape == g["store_tau"].shape
+    assert M.store["log_post"].shape == g["store_log_post"].shape
+    np.testing.assert_allclose(M.store["beta"], g["store_beta"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(M.store["tau"], g["store_tau"], rtol=1e-9)
+    np.testing.assert_allclose(M.store["lambda"], g["store_lambda"], rtol=1e-9)
+    np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
+    np.testing.assert_allclose(M.store["y"], g["store_y"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(M.state["beta"], g["store_beta"][:, [-1]], rtol=1e-9, atol=1e-12)
+
+
+def test_mcmc_burn_thin_schedule_and_chains():
+    """Iteration numbering (mcmc.py:97-103): (n_burn+n_iter)*n_thin sweeps; identical injected draws on every chain
+    give identical chains; batched shapes (C, size, n_iter)."""
+    from openmcmc_b200.mcmc import MCMC
+
+    g = dict(np.load(os.path.join(GOLD, "regression_n50_p3.npz")))
+    mdl, samplers, state = build(g, response=False)
+    C = 5
+    # 6 recorded sweeps = n_burn 2 + n_iter 2 with n_thin... use n_thin=1: burn 2, iter 4
+    dd = {"beta": {"z": np.repeat(g["z"][:, None, :], C, axis=1)},
+          "tau": {"g": np.repeat(g["g_tau"][:, None], C, axis=1)},
+          "lambda": {"g": np.repeat(g["g_lambda"][:, None], C, axis=1)}}
+    M = MCMC(state, samplers, model=mdl, n_burn=2, n_iter=4, n_chains=C, debug_draws=dd)
+    M.run_mcmc()
+    assert M.store["beta"].shape == (C, 3, 4)
+    assert M.store["log_post"].shape == (4, C)
+    for c in range(C):
+        np.testing.assert_allclose(M.store["beta"][c], g["store_beta"][:, 2:], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(M.store["tau"][c], g["store_tau"][:, 2:], rtol=1e-9)
+    # thinning: n_thin=2, n_iter=3 stores sweeps 1,3,5
+    M2 = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=3, n_thin=2, n_chains=C, debug_draws=dd)
+    M2.run_mcmc()
+    np.testing.assert_allclose(M2.store["beta"][0], g["store_beta"][:, 1::2], rtol=1e-9, atol=1e-12)
+    assert M2.launches_per_sweep() >= 5
+
+
+def test_mcmc_free_running_posterior_matches_truth():
+    """Free-running chains (Philox): posterior mean of beta close to the least-squares solution; many chains agree
+    within Monte-Carlo error; different chains differ; results independent of chain_offset sharding."""
+    from openmcmc_b200.mcmc import MCMC
+
+    g = dict(np.load(os.path.join(GOLD, "regression_n50_p3.npz")))
+    mdl, samplers, state = build(g, response=False)
+    C = 64
+    M = MCMC(state, samplers, model=mdl, n_burn=200, n_iter=300, n_chains=C, seed=123)
+    M.run_mcmc()
+    b = M.store["beta"]                      # (C, 3, 300)
+    ls = np.linalg.lstsq(g["X"], g["y"], rcond=None)[0].ravel()
+    np.testing.assert_allclose(b.mean(axis=(0, 2)), ls, atol=0.02)
+    assert np.std(b[:, 0, -1]) > 0
+    tau_mean = M.store["tau"].mean()
+    resid = g["y"] - g["X"] @ ls.reshape(-1, 1)
+    assert abs(tau_mean - 1.0 / np.var(resid)) / tau_mean < 0.15
+    # sharding invariance: chains 32..63 computed alone with chain_offset=32 reproduce the same draws
+    M2 = MCMC(state, samplers, model=mdl, n_burn=200, n_iter=300, n_chains=32, seed=123, chain_offset=32)
+    M2.run_mcmc()
+    np.testing.assert_array_equal(M2.store["beta"], b[32:])
+
+
+def test_sampler_single_call_reference_kats():
+    """The reference's own known-answer tests for NormalNormal / NormalGamma (tests/test_sampler.py:262-341) through
+    the same `.sample(state)` call, with its rvs patches expressed as debug_draws."""
+    from openmcmc_b200 import parameter
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    for n, p in [(1, 1), (1, 10), (10, 1), (10, 10)]:
+        rng = np.random.default_rng(0)
+        state = {}
+        state["prefactor_matrix"] = rng.random((n, p))
+        state["parameter"] = rng.random((p, 1))
+        state["response"] = state["prefactor_matrix"] @ state["parameter"]
+        state["prior_mean"] = rng.random((1, 1)) * np.ones((p, 1))
+        state["precision_matrix"] = np.diag(rng.random(n) + 0.1)
+        state["prior_precision_vector"] = 0.1 + rng.random(1)
+        state["prior_precision_matrix"] = np.eye(p)
+        state["gamma_shape"] = 1e-3 * np.ones(1)
+        state["gamma_rate"] = 1e-3 * np.ones(1)
+        model = Model([
+            Normal("response", mean=parameter.LinearCombination(form={"parameter": "prefactor_matrix"}),
+                   precision=parameter.Identity("precision_matrix")),
+            Normal("parameter", mean=parameter.Identity("prior_mean"),
+                   precision=parameter.ScaledMatrix(matrix="prior_precision_matrix", scalar="prior_precision_vector")),
+            Gamma("prior_precision_vector", shape=parameter.Identity("gamma_shape"), rate=parameter.Identity("gamma_rate")),
+        ])
+        nn = NormalNormal("parameter", model)
+        # 1) X = 0 and z = 0 -> prior mean (test_sampler.py:274-277)
+        ts = dict(state)
+        ts["prefactor_matrix"] = np.zeros((n, p))
+        out = nn.sample(dict(ts), debug_draws={"z": np.zeros(p)})
+        np.testing.assert_allclose(out["parameter"], state["prior_mean"])
+        # 2) prior precision 0, z = 0 -> weighted least squares (test_sampler.py:279-288); needs n >= p for full rank
+        W = state["precision_matrix"]
+        Xm = state["prefactor_matrix"]
+        if n >= p and n > 1:
+            ts = dict(state)
+            ts["prior_precision_vector"] = np.zeros(1)
+            out = nn.sample(dict(ts), debug_draws={"z": np.zeros(p)})
+            np.testing.assert_allclose(out["parameter"], np.linalg.solve(Xm.T @ W @ Xm, Xm.T @ W @ state["response"]))
+        # 3) zero means, z = 1 -> solve(chol(X'WX + Q0).T, 1) (test_sampler.py:290-308)
+        ts = dict(state)
+        ts["response"] = np.zeros((n, 1))
+        ts["prior_mean"] = np.zeros((p, 1))
+        out = nn.sample(dict(ts), debug_draws={"z": np.ones(p)})
+        comp = np.linalg.solve(np.linalg.cholesky(Xm.T @ W @ Xm + state["prior_precision_vector"] * np.eye(p)).T,
+                               np.ones((p, 1)))
+        np.testing.assert_allclose(out["parameter"], comp)
+        assert out["parameter"].shape == (p, 1)
+        # NormalGamma: gamma.rvs -> a*scale, zero prior => 1/tau = mean(resid^2) (test_sampler.py:311-341)
+        ng = NormalGamma("prior_precision_vector", model)
+        ts = dict(state)
+        ts["gamma_shape"] = np.zeros(1)
+        ts["gamma_rate"] = np.zeros(1)
+        out = ng.sample(dict(ts), debug_draws={"g": np.array([p / 2.0])})   # E[Gamma(a*,1)] = a* = p/2
+        resid = ts["parameter"] - ts["prior_mean"]
+        np.testing.assert_allclose(1 / out["prior_precision_vector"], np.mean(resid ** 2))
+        # untouched keys (test_sampler.py:181-198)
+        for k in ts:
+            if k != "prior_precision_vector":
+                np.testing.assert_allclose(out[k], ts[k])

@@ -1,0 +1,89 @@
+"""CPU: the numpy oracle reproduces the reference's golden vectors (tests/golden/*.npz, made by make_golden.py from
+the live reference with injected random streams).  This is what pins the oracle."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import conjugate, dist, gmrf
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False))
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "regression_*.npz"))))
+def test_regression_chain_replay(name):
+    g = _load(name)
+    X, y, mu = g["X"], g["y"], g["mu"]
+    n, p = X.shape
+    w = g["w"] if g["w"].size else None
+    P0 = g["P_lambda"]
+    order = tuple(str(s) for s in g["order"])
+    state = {"beta": np.zeros((p, 1)), "tau": 1.0, "lambda": 0.01, "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3,
+             "b_lambda": 1e-3}
+    n_iter = g["store_beta"].shape[1]
+    logdet_P0 = 2 * np.sum(np.log(np.diag(np.linalg.cholesky(P0))))
+    logdet_W = 0.0 if w is None else float(np.sum(np.log(w)))
+    for it in range(n_iter):
+        state = conjugate.gibbs_regression_sweep(X, y, state, g["z"][it], g["g_tau"][it], g["g_lambda"][it], P0=P0,
+                                                 mu0=mu, w=w, order=order)
+        np.testing.assert_allclose(state["beta"].ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(state["tau"], g["store_tau"][0, it], rtol=1e-10)
+        np.testing.assert_allclose(state["lambda"], g["store_lambda"][0, it], rtol=1e-10)
+        np.testing.assert_allclose((X @ state["beta"]).ravel(), g["store_y"][:, it], rtol=1e-9, atol=1e-11)
+        _, _, rss, _ = conjugate.regression_suffstats(X, y, w, state["beta"])
+        ssb, _ = conjugate.quadform(P0, state["beta"], mu)
+        lp = (dist.normal_log_p_from_ss(n, state["tau"], logdet_W, rss)
+              + dist.normal_log_p_from_ss(p, state["lambda"], logdet_P0, ssb)
+              + dist.gamma_log_p(state["tau"], 1e-3, 1e-3) + dist.gamma_log_p(state["lambda"], 1e-3, 1e-3))
+        np.testing.assert_allclose(lp, g["store_log_post"][it, 0], rtol=1e-10)
+
+
+def test_truncnorm_restatement_matches_scipy():
+    """oracle.gmrf truncated-normal helpers == scipy.stats.truncnorm (what gmrf.py:269-318 calls)."""
+    from scipy import stats
+
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        mean, scale = rng.normal() * 3, rng.random() * 2 + 0.05
+        lo = mean + scale * rng.normal() * 3
+        hi = lo + rng.random() * 5 * scale + 1e-3
+        if rng.random() < 0.3:
+            hi = np.inf
+        if rng.random() < 0.2:
+            lo = -np.inf
+        u = rng.random()
+        a, b = (lo - mean) / scale, (hi - mean) / scale
+        x_ref = stats.truncnorm.ppf(u, a, b, loc=mean, scale=scale)
+        x = gmrf.truncated_normal_rv(mean, scale, lo, hi, u)
+        np.testing.assert_allclose(x, x_ref, rtol=1e-12, atol=1e-12)
+        lp_ref = stats.truncnorm.logpdf(x_ref, a, b, loc=mean, scale=scale)
+        lp = gmrf.truncated_normal_log_pdf(x_ref, mean, scale, lo, hi)
+        np.testing.assert_allclose(lp, lp_ref, rtol=1e-11, atol=1e-11)
+    assert gmrf.truncated_normal_log_pdf(-1.0, 0.0, 1.0, 0.0, np.inf) == -np.inf
+
+
+def test_tridiag_restatement_matches_dense():
+    """Thomas-order tridiagonal Cholesky == dense Cholesky of the same matrix (gmrf.py:489-520 contract)."""
+    rng = np.random.default_rng(1)
+    s = np.cumsum(rng.exponential(size=40))
+    d, e = gmrf.precision_irregular_diagonals(s)
+    d = 3.0 * d + 0.7
+    e = 3.0 * e
+    Q = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    L = np.linalg.cholesky(Q)
+    l, c = gmrf.tridiag_cholesky(d, e)
+    np.testing.assert_allclose(l, np.diag(L), rtol=1e-13)
+    np.testing.assert_allclose(c, np.diag(L, -1), rtol=1e-12)
+    b, z = rng.normal(size=40), rng.normal(size=40)
+    x, mu, _, _ = gmrf.tridiag_sample_canonical(d, e, b, z)
+    x_ref, mu_ref, _ = gmrf.sample_normal_canonical(b.reshape(-1, 1), Q, z.reshape(-1, 1))
+    np.testing.assert_allclose(mu, mu_ref.ravel(), rtol=1e-11)
+    np.testing.assert_allclose(x, x_ref.ravel(), rtol=1e-11)
+    np.testing.assert_allclose(gmrf.tridiag_quadform(d, e, z), z @ Q @ z, rtol=1e-12)
+    np.testing.assert_allclose(gmrf.tridiag_logdet(d, e), np.linalg.slogdet(Q)[1], rtol=1e-12)
