@@ -1,0 +1,90 @@
+"""Oracle (test infrastructure): CPU timing leg used by bench.py (`cpu_baseline` and `--impl reference`).
+
+Times the numpy restatement of the reference's Gibbs sweep on the host cores: one worker process per core, one BLAS
+thread each (the reference is single-threaded; SURVEY B.3 measured that 8 BLAS threads are slower than 1 at p=64),
+chains looped inside each worker exactly as a user of the reference would loop `MCMC.run_mcmc()` over chains.
+
+    python -m oracle.cpu_bench --workload c2 --chains-per-worker 2 --sweeps 3 --workers 16
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+
+def _worker(workload, chains, sweeps, seed, n, p):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+
+    from oracle import conjugate, dist
+
+    rng = np.random.default_rng(seed)
+    data = []
+    for _ in range(chains):
+        X = rng.standard_normal((n, p))
+        X[:, 0] = 1.0
+        y = X @ rng.standard_normal((p, 1)) + 0.1 * rng.standard_normal((n, 1))
+        st = {"beta": np.zeros((p, 1)), "tau": 1.0, "lambda": 0.01, "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3,
+              "b_lambda": 1e-3}
+        data.append((X, y, st))
+    t0 = time.perf_counter()
+    for X, y, st in data:
+        for _ in range(sweeps):
+            st = conjugate.gibbs_regression_sweep(X, y, st, rng.standard_normal(p), rng.standard_gamma(n / 2),
+                                                  rng.standard_gamma(p / 2))
+            # per-iteration log-posterior as mcmc.py:108 (rss with the new beta, both Normal terms, both Gamma terms)
+            _, _, rss, _ = conjugate.regression_suffstats(X, y, None, st["beta"])
+            ssb, _ = conjugate.quadform(1.0, st["beta"], None)
+            _ = (dist.normal_log_p_from_ss(n, st["tau"], 0.0, rss) + dist.normal_log_p_from_ss(p, st["lambda"], 0.0, ssb)
+                 + dist.gamma_log_p(st["tau"], 1e-3, 1e-3) + dist.gamma_log_p(st["lambda"], 1e-3, 1e-3))
+    return time.perf_counter() - t0
+
+
+def run_parallel(workload="c2", workers=None, chains_per_worker=2, sweeps=3, n=10000, p=64, seed=0):
+    """Launch `workers` single-threaded processes; returns dict(value=chain-iterations/s, seconds, cores, sample)."""
+    workers = workers or os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "oracle.cpu_bench", "--worker", "--workload", workload, "--chains-per-worker",
+           str(chains_per_worker), "--sweeps", str(sweeps), "--n", str(n), "--p", str(p)]
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd + ["--seed", str(seed + i)], env=env, stdout=subprocess.PIPE, cwd=root)
+             for i in range(workers)]
+    inner = []
+    for pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("cpu_bench worker failed")
+        inner.append(float(out.decode().strip().splitlines()[-1]))
+    wall = time.perf_counter() - t0
+    total = workers * chains_per_worker * sweeps
+    # throughput of the timed loops themselves (process start-up and data generation excluded)
+    value = total / max(inner)
+    return {"value": value, "unit": "chain-iterations/s", "cores": workers, "seconds": max(inner), "wall": wall,
+            "sample": f"{workers} workers x {chains_per_worker} chains x {sweeps} sweeps of n={n}, p={p} "
+                      f"(numpy port of the reference sweep incl. per-iteration log_post), 1 BLAS thread per worker"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--worker", action="store_true")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workers", type=int, default=None)
+    ap.add_argument("--chains-per-worker", type=int, default=2)
+    ap.add_argument("--sweeps", type=int, default=3)
+    ap.add_argument("--n", type=int, default=10000)
+    ap.add_argument("--p", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    if a.worker:
+        print(_worker(a.workload, a.chains_per_worker, a.sweeps, a.seed, a.n, a.p))
+    else:
+        print(json.dumps(run_parallel(a.workload, a.workers, a.chains_per_worker, a.sweeps, a.n, a.p, a.seed)))
+
+
+if __name__ == "__main__":
+    main()
