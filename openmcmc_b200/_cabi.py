@@ -151,7 +151,8 @@ PROTOTYPES = {
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    """In-tree libomc.so; OMC_LIB overrides it (used only by tools/tune_reg_pass.sh to time kernel variants)."""
+    return os.environ.get("OMC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load():

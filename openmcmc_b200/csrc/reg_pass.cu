@@ -20,9 +20,31 @@
 
 namespace {
 
-constexpr int KC = 64;      // rows per pipeline stage
-constexpr int NSTAGE = 3;   // cp.async stages
-constexpr int NWARP = 4;
+// tuning knobs (overridable with -D for tools/tune_reg_pass.sh; defaults = measured best, see profiles/)
+#ifndef OMC_RP_KC
+#define OMC_RP_KC 48
+#endif
+#ifndef OMC_RP_NSTAGE
+#define OMC_RP_NSTAGE 4
+#endif
+#ifndef OMC_RP_NWARP
+#define OMC_RP_NWARP 4
+#endif
+#ifndef OMC_RP_MINBLOCKS
+#define OMC_RP_MINBLOCKS 2
+#endif
+#ifndef OMC_RP_BULK_BALANCED
+#define OMC_RP_BULK_BALANCED 0
+#endif
+#ifndef OMC_RP_USE_BULK
+#define OMC_RP_USE_BULK 0
+#endif
+#ifndef OMC_RP_SIDE
+#define OMC_RP_SIDE 1  // 0 = skip X'y / rss (experiments only: isolates the DMMA rate)
+#endif
+constexpr int KC = OMC_RP_KC;          // rows per pipeline stage
+constexpr int NSTAGE = OMC_RP_NSTAGE;  // pipeline stages
+constexpr int NWARP = OMC_RP_NWARP;
 constexpr int NTHREADS = NWARP * 32;
 
 struct RegPassArgs {
@@ -54,15 +76,47 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP): one 16B-aligned contiguous row per copy
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 template <int PB>
 struct Smem {
   static constexpr int LD = 8 * PB + 4;  // padded row stride (doubles): (2g + 8k) mod 32 banks are distinct per phase
   static constexpr int STAGE_DOUBLES = KC * LD + 2 * KC;  // X tile | y | w
-  static constexpr int BYTES = NSTAGE * STAGE_DOUBLES * 8;
+  static constexpr int BYTES = NSTAGE * STAGE_DOUBLES * 8 + 64;  // + mbarriers
 };
 
-template <int PB, bool WEIGHTED>
-__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(RegPassArgs a) {
+// BULK = true : rows arrive through cp.async.bulk (one elected warp issues 64 row copies per stage, completion on an
+//               mbarrier) -- needs p even and 16-byte aligned rows; the <64-row tail is staged synchronously.
+// BULK = false: generic cp.async (LDGSTS) path with zero-fill, any p / alignment.
+template <int PB, bool WEIGHTED, bool BULK>
+__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 3) reg_pass_kernel(RegPassArgs a) {
   using S = Smem<PB>;
   constexpr int LD = S::LD;
   constexpr int NT = PB * (PB + 1) / 2;
@@ -83,11 +137,48 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(Re
 
   // zero the whole staging area once: columns >= p of every row are never written by the loader and must read as 0
   for (int i = tid; i < NSTAGE * S::STAGE_DOUBLES; i += NTHREADS) smem[i] = 0.0;
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem + NSTAGE * S::STAGE_DOUBLES);
+  if (BULK && tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(full_bar + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (BULK) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero-fill before async-proxy writes
   __syncthreads();
 
+  // number of stages that go through the async pipeline; BULK handles the ragged tail synchronously afterwards
+  const int npipe = BULK ? nrows / KC : nstage_total;
   const bool vec16 = ((p & 1) == 0) && ((((unsigned long long)Xc) & 15ull) == 0);
+  const int fcpr = max(p >> 1, 1);
+  const bool fastrow = vec16 && (NTHREADS % fcpr == 0);
+  const int fr0 = tid / fcpr, fc0 = tid % fcpr, frstep = NTHREADS / fcpr;
 
   auto issue_stage = [&](int st) {
+    if (BULK) {
+      if (st < npipe) {
+        double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
+        double* ys = Xs + KC * LD;
+        double* ws = ys + KC;
+        unsigned long long* bar = full_bar + (st % NSTAGE);
+        const int r_base = st * KC;
+        const double* src = Xc + (long long)r_base * p;
+        const unsigned row_bytes = (unsigned)p * 8u;
+        if (tid == 0) mbar_expect_tx(bar, KC * row_bytes + KC * 8u * (WEIGHTED ? 2u : 1u));
+#if OMC_RP_BULK_BALANCED
+        // spread the row copies over all warps so no single warp serialises the issue
+        for (int r = tid; r < KC; r += NTHREADS) bulk_g2s(Xs + r * LD, src + (long long)r * p, row_bytes, bar);
+        if (tid == NTHREADS - 1) bulk_g2s(ys, yc + r_base, KC * 8u, bar);
+        if (WEIGHTED && tid == NTHREADS - 2) bulk_g2s(ws, wc + r_base, KC * 8u, bar);
+#else
+        if (warp == 0) {
+          for (int r = lane; r < KC; r += 32) bulk_g2s(Xs + r * LD, src + (long long)r * p, row_bytes, bar);
+          if (lane == 0) bulk_g2s(ys, yc + r_base, KC * 8u, bar);
+          if (WEIGHTED && lane == 1) bulk_g2s(ws, wc + r_base, KC * 8u, bar);
+        }
+#endif
+      }
+      return;
+    }
     if (st < nstage_total) {
       double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
       double* ys = Xs + KC * LD;
@@ -95,7 +186,14 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(Re
       const int r_base = st * KC;
       const int valid = min(KC, nrows - r_base);
       const double* src = Xc + (long long)r_base * p;
-      if (vec16) {
+      if (fastrow) {
+        // p/2 divides the CTA size: thread -> (row fr0 + i*frstep, chunk fc0), no per-chunk integer division
+        for (int r = fr0; r < KC; r += frstep) {
+          bool ok = r < valid;
+          cp_async16(Xs + r * LD + 2 * fc0, ok ? (const void*)(src + (long long)r * p + 2 * fc0) : (const void*)Xc,
+                     ok ? 16 : 0);
+        }
+      } else if (vec16) {
         const int cpr = p >> 1;  // 16-byte chunks per row
         const int total = KC * cpr;
         for (int id = tid; id < total; id += NTHREADS) {
@@ -137,14 +235,8 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(Re
   for (int jb = 0; jb < PB; ++jb) gacc[jb] = 0.0;
   double rss = 0.0, cnt = 0.0;
 
-#pragma unroll
-  for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
-
-  for (int st = 0; st < nstage_total; ++st) {
-    cp_async_wait<NSTAGE - 2>();
-    __syncthreads();
-    issue_stage(st + NSTAGE - 1);
-    const double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
+  // one stage = KC rows; the 4 warps take k-steps (4 rows each) round-robin
+  auto compute_stage = [&](const double* Xs) {
     const double* ys = Xs + KC * LD;
     const double* ws = ys + KC;
 #pragma unroll 2
@@ -169,6 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(Re
       for (int i = 0; i < PB; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) dmma884(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], af[i], bf[j]);
+#if OMC_RP_SIDE
       // X' W y and the residual of this row
       double dot = 0.0;
 #pragma unroll
@@ -182,10 +275,47 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? 2 : 3) reg_pass_kernel(Re
       const double res = yv - dot;
       rss = fma(WEIGHTED ? wv * res : res, res, rss);
       if (WEIGHTED) cnt += (wv > 0.0) ? 1.0 : 0.0;
+#else
+      rss += yv;
+#endif
     }
+  };
+
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
+
+  for (int st = 0; st < npipe; ++st) {
+    if (BULK) {
+      __syncthreads();                 // everyone is done with the buffer stage st+NSTAGE-1 will overwrite
+      issue_stage(st + NSTAGE - 1);
+      mbar_wait(full_bar + (st % NSTAGE), (unsigned)((st / NSTAGE) & 1));
+    } else {
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();
+      issue_stage(st + NSTAGE - 1);
+    }
+    compute_stage(smem + (st % NSTAGE) * S::STAGE_DOUBLES);
   }
-  cp_async_wait<0>();
+  if (!BULK) cp_async_wait<0>();
   __syncthreads();
+  if (BULK && nrows - npipe * KC > 0) {
+    // ragged tail (< KC rows): synchronous staging into buffer 0 with zero rows behind it
+    const int r_base = npipe * KC, valid = nrows - r_base;
+    double* Xs = smem;
+    double* ys = Xs + KC * LD;
+    double* ws = ys + KC;
+    for (int id = tid; id < KC * p; id += NTHREADS) {
+      int r = id / p, c = id - r * p;
+      Xs[r * LD + c] = (r < valid) ? Xc[(long long)(r_base + r) * p + c] : 0.0;
+    }
+    for (int r = tid; r < KC; r += NTHREADS) {
+      ys[r] = (r < valid) ? yc[r_base + r] : 0.0;
+      if (WEIGHTED) ws[r] = (r < valid) ? wc[r_base + r] : 0.0;
+    }
+    __syncthreads();
+    compute_stage(Xs);
+    __syncthreads();
+  }
 
   // ---- combine the 4 warps (rows were split across warps) through shared memory
   double* red = smem;  // NT*64 + 8*PB + 2*4 doubles, fits in one stage
@@ -268,19 +398,24 @@ __global__ void reg_reduce_kernel(const double* part, double* out, int n_split, 
   out[i] = s;
 }
 
-template <int PB>
-int launch_pb(const RegPassArgs& a, bool weighted, cudaStream_t st) {
+template <int PB, bool W, bool B>
+int launch_one(const RegPassArgs& a, cudaStream_t st) {
   dim3 grid(a.n_split, a.n_chains);
   const int smem = Smem<PB>::BYTES;
-  if (weighted) {
-    OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    reg_pass_kernel<PB, true><<<grid, NTHREADS, smem, st>>>(a);
-  } else {
-    OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    reg_pass_kernel<PB, false><<<grid, NTHREADS, smem, st>>>(a);
-  }
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, W, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  reg_pass_kernel<PB, W, B><<<grid, NTHREADS, smem, st>>>(a);
   OMC_LAUNCH_CHECK();
   return 0;
+}
+
+template <int PB>
+int launch_pb(const RegPassArgs& a, bool weighted, cudaStream_t st) {
+  // bulk (TMA-engine) row copies need 16-byte aligned rows of a multiple of 16 bytes, for X, y and w alike
+  auto al16 = [](const void* q) { return (((unsigned long long)q) & 15ull) == 0; };
+  const bool bulk = OMC_RP_USE_BULK && (a.p % 2 == 0) && al16(a.X) && (a.strideX % 2 == 0) && al16(a.y) && (a.strideY % 2 == 0) &&
+                    (!weighted || (al16(a.w) && (a.strideW % 2 == 0)));
+  if (weighted) return bulk ? launch_one<PB, true, true>(a, st) : launch_one<PB, true, false>(a, st);
+  return bulk ? launch_one<PB, false, true>(a, st) : launch_one<PB, false, false>(a, st);
 }
 
 }  // namespace
