@@ -8,12 +8,15 @@
 //     cnt = #(w > 0)                  -- the reference's  sum(P.diagonal() > 0),            sampler.py:283
 // W = diag(w) (or I when w == nullptr); tau is NOT folded in here (ScaledMatrix scalar is applied by the consumers).
 //
-// Kernel: one CTA per (chain, row-split).  X rows are streamed global->shared with a 3-stage cp.async pipeline into
-// a padded layout (row stride 8*PB+4 doubles => the DMMA fragment reads below are bank-conflict free).  The SYRK runs
-// on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native FP64 MMA shape on sm_100a).  Because
-// A = X' and B = X come from the same tile, one 8-register fragment set per 4 rows feeds all PB(PB+1)/2 lower-triangle
-// 8x8 output tiles (36 DMMA per 8 LDS.64 at p=64).  g and rss ride along on the FP64 FMA pipe (+~5%).
-// Roofline: 46.1 MFLOP of DMMA per chain at n=10^4,p=64 vs 5.2 MB of HBM traffic => FP64-bound.
+// Kernel: one CTA (4 warps) per (chain, row-split).  X rows are streamed global->shared with a 4-stage cp.async
+// (LDGSTS.128) pipeline into a padded layout (row stride 8*PB+4 doubles => the fragment reads are bank-conflict free).
+// The SYRK runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native FP64 MMA shape on
+// sm_100a).  A = X' and B = X come from the same tile, so one PB-register fragment set per 4 rows feeds all
+// PB(PB+1)/2 lower-triangle 8x8 output tiles.  For PB >= 5 the tiles are split over two "tile-group" warps
+// (18 tiles = 72 accumulator registers each at p=64) so that 3 CTAs = 12 warps fit per SM and the LDS->DMMA latency
+// of one warp is hidden by the others (ncu: profiles/r01_*); rows (k-steps) are split over the remaining warps.
+// g rides on tile-group 0 and rss on tile-group 1 (FP64 FMA pipe, ~5% of the DMMA work).
+// Roofline: 46.1 MFLOP of DMMA per chain at n=10^4,p=64 vs 5.2 MB of HBM traffic => FP64-pipe bound.
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"
@@ -22,29 +25,23 @@ namespace {
 
 // tuning knobs (overridable with -D for tools/tune_reg_pass.sh; defaults = measured best, see profiles/)
 #ifndef OMC_RP_KC
-#define OMC_RP_KC 48
+#define OMC_RP_KC 64
 #endif
 #ifndef OMC_RP_NSTAGE
-#define OMC_RP_NSTAGE 4
+#define OMC_RP_NSTAGE 3
 #endif
-#ifndef OMC_RP_NWARP
-#define OMC_RP_NWARP 4
+#ifndef OMC_RP_TG
+#define OMC_RP_TG 1        // tile groups for PB >= 5 (1: every warp owns all tiles, 254 regs; 2: 18 tiles per warp)
 #endif
 #ifndef OMC_RP_MINBLOCKS
-#define OMC_RP_MINBLOCKS 2
-#endif
-#ifndef OMC_RP_BULK_BALANCED
-#define OMC_RP_BULK_BALANCED 0
+#define OMC_RP_MINBLOCKS ((OMC_RP_TG == 1) ? 2 : 3)
 #endif
 #ifndef OMC_RP_USE_BULK
-#define OMC_RP_USE_BULK 0
-#endif
-#ifndef OMC_RP_SIDE
-#define OMC_RP_SIDE 1  // 0 = skip X'y / rss (experiments only: isolates the DMMA rate)
+#define OMC_RP_USE_BULK 1  // stage rows with cp.async.bulk (TMA engine) when shape/alignment allow
 #endif
 constexpr int KC = OMC_RP_KC;          // rows per pipeline stage
 constexpr int NSTAGE = OMC_RP_NSTAGE;  // pipeline stages
-constexpr int NWARP = OMC_RP_NWARP;
+constexpr int NWARP = 4;
 constexpr int NTHREADS = NWARP * 32;
 
 struct RegPassArgs {
@@ -76,7 +73,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP): one 16B-aligned contiguous row per copy
+// ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP)
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
 }
@@ -106,143 +103,60 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 }
 
 template <int PB>
-struct Smem {
+struct Cfg {
   static constexpr int LD = 8 * PB + 4;  // padded row stride (doubles): (2g + 8k) mod 32 banks are distinct per phase
   static constexpr int STAGE_DOUBLES = KC * LD + 2 * KC;  // X tile | y | w
-  static constexpr int BYTES = NSTAGE * STAGE_DOUBLES * 8 + 64;  // + mbarriers
+  static constexpr int NT = PB * (PB + 1) / 2;             // lower-triangle 8x8 tiles
+  static constexpr int TG = (PB >= 5) ? OMC_RP_TG : 1;     // tile groups (warps sharing the same rows)
+  // chunked layout of the bulk path: a stage = 4 contiguous chunks of RC rows (one bulk copy each, rows packed at
+  // stride 8*PB), chunk q shifted by 4 doubles so that the 4 k-lanes (one row from each chunk) hit distinct banks
+  static constexpr int RC = KC / 4;
+  static constexpr int CH = RC * 8 * PB + 4;
+  static constexpr int RG = NWARP / TG;                    // row groups
+  static constexpr int NTG = (NT + TG - 1) / TG;           // tiles per group
+  static constexpr int RED_DOUBLES = NWARP * (NTG * 64 + 8 * PB + 2);
+  static constexpr int SMEM_DOUBLES = (NSTAGE * STAGE_DOUBLES > RED_DOUBLES) ? NSTAGE * STAGE_DOUBLES : RED_DOUBLES;
+  static constexpr int BYTES = SMEM_DOUBLES * 8 + 64;  // + mbarriers
 };
 
-// BULK = true : rows arrive through cp.async.bulk (one elected warp issues 64 row copies per stage, completion on an
-//               mbarrier) -- needs p even and 16-byte aligned rows; the <64-row tail is staged synchronously.
-// BULK = false: generic cp.async (LDGSTS) path with zero-fill, any p / alignment.
-template <int PB, bool WEIGHTED, bool BULK>
-__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 3) reg_pass_kernel(RegPassArgs a) {
-  using S = Smem<PB>;
-  constexpr int LD = S::LD;
-  constexpr int NT = PB * (PB + 1) / 2;
-  extern __shared__ __align__(16) double smem[];
-
-  const int chain = blockIdx.y, split = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, kq = lane & 3;
-  const int p = a.p, n = a.n;
-  const int row0 = split * a.rows_per_split;
-  const int row1 = min(n, row0 + a.rows_per_split);
-  const int nrows = max(0, row1 - row0);
-  const int nstage_total = (nrows + KC - 1) / KC;
-
-  const double* Xc = a.X + (long long)chain * a.strideX + (long long)row0 * p;
-  const double* yc = a.y + (long long)chain * a.strideY + row0;
-  const double* wc = WEIGHTED ? a.w + (long long)chain * a.strideW + row0 : nullptr;
-
-  // zero the whole staging area once: columns >= p of every row are never written by the loader and must read as 0
-  for (int i = tid; i < NSTAGE * S::STAGE_DOUBLES; i += NTHREADS) smem[i] = 0.0;
-  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem + NSTAGE * S::STAGE_DOUBLES);
-  if (BULK && tid == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(full_bar + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  if (BULK) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero-fill before async-proxy writes
-  __syncthreads();
-
-  // number of stages that go through the async pipeline; BULK handles the ragged tail synchronously afterwards
-  const int npipe = BULK ? nrows / KC : nstage_total;
-  const bool vec16 = ((p & 1) == 0) && ((((unsigned long long)Xc) & 15ull) == 0);
-  const int fcpr = max(p >> 1, 1);
-  const bool fastrow = vec16 && (NTHREADS % fcpr == 0);
-  const int fr0 = tid / fcpr, fc0 = tid % fcpr, frstep = NTHREADS / fcpr;
-
-  auto issue_stage = [&](int st) {
-    if (BULK) {
-      if (st < npipe) {
-        double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
-        double* ys = Xs + KC * LD;
-        double* ws = ys + KC;
-        unsigned long long* bar = full_bar + (st % NSTAGE);
-        const int r_base = st * KC;
-        const double* src = Xc + (long long)r_base * p;
-        const unsigned row_bytes = (unsigned)p * 8u;
-        if (tid == 0) mbar_expect_tx(bar, KC * row_bytes + KC * 8u * (WEIGHTED ? 2u : 1u));
-#if OMC_RP_BULK_BALANCED
-        // spread the row copies over all warps so no single warp serialises the issue
-        for (int r = tid; r < KC; r += NTHREADS) bulk_g2s(Xs + r * LD, src + (long long)r * p, row_bytes, bar);
-        if (tid == NTHREADS - 1) bulk_g2s(ys, yc + r_base, KC * 8u, bar);
-        if (WEIGHTED && tid == NTHREADS - 2) bulk_g2s(ws, wc + r_base, KC * 8u, bar);
-#else
-        if (warp == 0) {
-          for (int r = lane; r < KC; r += 32) bulk_g2s(Xs + r * LD, src + (long long)r * p, row_bytes, bar);
-          if (lane == 0) bulk_g2s(ys, yc + r_base, KC * 8u, bar);
-          if (WEIGHTED && lane == 1) bulk_g2s(ws, wc + r_base, KC * 8u, bar);
-        }
-#endif
-      }
-      return;
-    }
-    if (st < nstage_total) {
-      double* Xs = smem + (st % NSTAGE) * S::STAGE_DOUBLES;
-      double* ys = Xs + KC * LD;
-      double* ws = ys + KC;
-      const int r_base = st * KC;
-      const int valid = min(KC, nrows - r_base);
-      const double* src = Xc + (long long)r_base * p;
-      if (fastrow) {
-        // p/2 divides the CTA size: thread -> (row fr0 + i*frstep, chunk fc0), no per-chunk integer division
-        for (int r = fr0; r < KC; r += frstep) {
-          bool ok = r < valid;
-          cp_async16(Xs + r * LD + 2 * fc0, ok ? (const void*)(src + (long long)r * p + 2 * fc0) : (const void*)Xc,
-                     ok ? 16 : 0);
-        }
-      } else if (vec16) {
-        const int cpr = p >> 1;  // 16-byte chunks per row
-        const int total = KC * cpr;
-        for (int id = tid; id < total; id += NTHREADS) {
-          int r = id / cpr, c = id - r * cpr;
-          bool ok = r < valid;
-          cp_async16(Xs + r * LD + 2 * c, ok ? (const void*)(src + (long long)r * p + 2 * c) : (const void*)Xc,
-                     ok ? 16 : 0);
-        }
-      } else {
-        const int total = KC * p;
-        for (int id = tid; id < total; id += NTHREADS) {
-          int r = id / p, c = id - r * p;
-          bool ok = r < valid;
-          cp_async8(Xs + r * LD + c, ok ? (const void*)(src + (long long)r * p + c) : (const void*)Xc, ok ? 8 : 0);
-        }
-      }
-      for (int r = tid; r < KC; r += NTHREADS) {
-        bool ok = r < valid;
-        cp_async8(ys + r, ok ? (const void*)(yc + r_base + r) : (const void*)yc, ok ? 8 : 0);
-        if (WEIGHTED) cp_async8(ws + r, ok ? (const void*)(wc + r_base + r) : (const void*)wc, ok ? 8 : 0);
-      }
-    }
-    cp_async_commit();
-  };
-
-  // per-lane slice of beta in fragment layout: column 8*jb + g
-  double bfrag[PB];
-#pragma unroll
-  for (int jb = 0; jb < PB; ++jb) {
-    int col = 8 * jb + g;
-    bfrag[jb] = (a.beta != nullptr && col < p) ? a.beta[(long long)chain * a.strideB + col] : 0.0;
-  }
-
-  double acc[NT][2];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+template <int PB, bool WEIGHTED>
+struct Worker {
+  using C = Cfg<PB>;
+  double acc[C::NTG][2];
   double gacc[PB];
-#pragma unroll
-  for (int jb = 0; jb < PB; ++jb) gacc[jb] = 0.0;
-  double rss = 0.0, cnt = 0.0;
+  double bfrag[PB];
+  double rss, cnt;
+  int lane, g, kq;
 
-  // one stage = KC rows; the 4 warps take k-steps (4 rows each) round-robin
-  auto compute_stage = [&](const double* Xs) {
+  __device__ __forceinline__ void init(const RegPassArgs& a, int chain, int lane_) {
+    lane = lane_;
+    g = lane >> 2;
+    kq = lane & 3;
+#pragma unroll
+    for (int t = 0; t < C::NTG; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+    for (int jb = 0; jb < PB; ++jb) {
+      gacc[jb] = 0.0;
+      const int col = 8 * jb + g;  // per-lane slice of beta in fragment layout
+      bfrag[jb] = (a.beta != nullptr && col < a.p) ? a.beta[(long long)chain * a.strideB + col] : 0.0;
+    }
+    rss = 0.0;
+    cnt = 0.0;
+  }
+
+  // one stage = KC rows; row group `rg` takes k-steps (4 rows each) rg, rg+RG, ...; tile group G its share of tiles
+  template <int G, bool CHUNKED>
+  __device__ __forceinline__ void stage(const double* Xs, int rg) {
+    constexpr int LD = C::LD;
+    constexpr bool DO_G = (G == 0);
+    constexpr bool DO_RSS = (G == C::TG - 1);
     const double* ys = Xs + KC * LD;
     const double* ws = ys + KC;
 #pragma unroll 2
-    for (int ks = warp; ks < KC / 4; ks += NWARP) {
-      const int r = 4 * ks + kq;
-      const double* xr = Xs + r * LD + g;
+    for (int ks = rg; ks < KC / 4; ks += C::RG) {
+      // padded layout: row 4ks+kq at stride LD ; chunked layout: row ks of chunk kq
+      const int r = CHUNKED ? kq * C::RC + ks : 4 * ks + kq;
+      const double* xr = CHUNKED ? Xs + kq * C::CH + ks * (8 * PB) + g : Xs + r * LD + g;
       double af[PB], bf[PB];
 #pragma unroll
       for (int jb = 0; jb < PB; ++jb) af[jb] = xr[8 * jb];
@@ -256,132 +170,236 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 3) reg
 #pragma unroll
         for (int jb = 0; jb < PB; ++jb) bf[jb] = af[jb];
       }
-      // SYRK tiles (lower triangle of the 8x8-block grid)
+      // SYRK tiles of this group (lower triangle of the 8x8-block grid, row-major enumeration)
 #pragma unroll
       for (int i = 0; i < PB; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) dmma884(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], af[i], bf[j]);
-#if OMC_RP_SIDE
-      // X' W y and the residual of this row
-      double dot = 0.0;
+        for (int j = 0; j <= i; ++j) {
+          const int t = i * (i + 1) / 2 + j;
+          if (t / C::NTG == G) dmma884(acc[t - G * C::NTG][0], acc[t - G * C::NTG][1], af[i], bf[j]);
+        }
+      if (DO_G) {  // X' W y
 #pragma unroll
-      for (int jb = 0; jb < PB; ++jb) {
-        gacc[jb] = fma(bf[jb], yv, gacc[jb]);
-        dot = fma(af[jb], bfrag[jb], dot);
+        for (int jb = 0; jb < PB; ++jb) gacc[jb] = fma(bf[jb], yv, gacc[jb]);
       }
-      dot += omc_shfl_xor(dot, 4);
-      dot += omc_shfl_xor(dot, 8);
-      dot += omc_shfl_xor(dot, 16);
-      const double res = yv - dot;
-      rss = fma(WEIGHTED ? wv * res : res, res, rss);
-      if (WEIGHTED) cnt += (wv > 0.0) ? 1.0 : 0.0;
-#else
-      rss += yv;
-#endif
+      if (DO_RSS) {  // residual of the 4 rows of this k-step
+        double dot = 0.0;
+#pragma unroll
+        for (int jb = 0; jb < PB; ++jb) dot = fma(af[jb], bfrag[jb], dot);
+        dot += omc_shfl_xor(dot, 4);
+        dot += omc_shfl_xor(dot, 8);
+        dot += omc_shfl_xor(dot, 16);
+        const double res = yv - dot;
+        rss = fma(WEIGHTED ? wv * res : res, res, rss);
+        if (WEIGHTED) cnt += (wv > 0.0) ? 1.0 : 0.0;
+      }
     }
+  }
+};
+
+// BULK = true : p == 8*PB and 16-byte aligned rows: 4 chunk copies + 1 y copy (+1 w) per stage through the TMA engine
+//               (cp.async.bulk, completion on an mbarrier) -- no LSU traffic for staging, so the DMMA fragment LDS never
+//               queue behind LDGSTS; the < KC-row tail is staged synchronously.
+// BULK = false: generic cp.async (LDGSTS) path with zero-fill into the padded layout, any p / alignment.
+template <int PB, bool WEIGHTED, bool BULK>
+__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg_pass_kernel(RegPassArgs a) {
+  using C = Cfg<PB>;
+  constexpr int LD = C::LD;
+  extern __shared__ __align__(16) double smem[];
+
+  const int chain = blockIdx.y, split = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tg = warp % C::TG, rg = warp / C::TG;
+  const int p = a.p, n = a.n;
+  const int row0 = split * a.rows_per_split;
+  const int row1 = min(n, row0 + a.rows_per_split);
+  const int nrows = max(0, row1 - row0);
+  const int nstage_total = (nrows + KC - 1) / KC;
+
+  const double* Xc = a.X + (long long)chain * a.strideX + (long long)row0 * p;
+  const double* yc = a.y + (long long)chain * a.strideY + row0;
+  const double* wc = WEIGHTED ? a.w + (long long)chain * a.strideW + row0 : nullptr;
+
+  // zero the staging area once: columns >= p of every row are never written by the loader and must read as 0
+  for (int i = tid; i < NSTAGE * C::STAGE_DOUBLES; i += NTHREADS) smem[i] = 0.0;
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem + C::SMEM_DOUBLES);
+  if (BULK) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) mbar_init(full_bar + s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero-fill before async-proxy writes
+  }
+  __syncthreads();
+  const int npipe = BULK ? nrows / KC : nstage_total;  // stages that go through the async pipeline
+
+  const bool vec16 = ((p & 1) == 0) && ((((unsigned long long)Xc) & 15ull) == 0);
+  const int fcpr = max(p >> 1, 1);                        // 16-byte chunks per row
+  const bool fastrow = vec16 && (NTHREADS % fcpr == 0);   // thread -> fixed (row offset, chunk): no per-chunk division
+  const int fr0 = tid / fcpr, fc0 = tid % fcpr, frstep = NTHREADS / fcpr;
+
+  auto issue_stage = [&](int st) {
+    if (BULK) {
+      if (st < npipe && tid == 0) {
+        double* Xs = smem + (st % NSTAGE) * C::STAGE_DOUBLES;
+        double* ys = Xs + KC * LD;
+        unsigned long long* bar = full_bar + (st % NSTAGE);
+        const int r_base = st * KC;
+        constexpr unsigned chunk_bytes = C::RC * 8 * PB * 8;
+        mbar_expect_tx(bar, 4 * chunk_bytes + KC * 8u * (WEIGHTED ? 2u : 1u));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          bulk_g2s(Xs + q * C::CH, Xc + (long long)(r_base + q * C::RC) * (8 * PB), chunk_bytes, bar);
+        bulk_g2s(ys, yc + r_base, KC * 8u, bar);
+        if (WEIGHTED) bulk_g2s(ys + KC, wc + r_base, KC * 8u, bar);
+      }
+      return;
+    }
+    if (st < nstage_total) {
+      double* Xs = smem + (st % NSTAGE) * C::STAGE_DOUBLES;
+      double* ys = Xs + KC * LD;
+      double* ws = ys + KC;
+      const int r_base = st * KC;
+      const int valid = min(KC, nrows - r_base);
+      const double* src = Xc + (long long)r_base * p;
+      if (fastrow) {
+        for (int r = fr0; r < KC; r += frstep) {
+          const bool ok = r < valid;
+          cp_async16(Xs + r * LD + 2 * fc0, ok ? (const void*)(src + (long long)r * p + 2 * fc0) : (const void*)Xc,
+                     ok ? 16 : 0);
+        }
+      } else if (vec16) {
+        const int total = KC * fcpr;
+        for (int id = tid; id < total; id += NTHREADS) {
+          const int r = id / fcpr, c = id - r * fcpr;
+          const bool ok = r < valid;
+          cp_async16(Xs + r * LD + 2 * c, ok ? (const void*)(src + (long long)r * p + 2 * c) : (const void*)Xc,
+                     ok ? 16 : 0);
+        }
+      } else {
+        const int total = KC * p;
+        for (int id = tid; id < total; id += NTHREADS) {
+          const int r = id / p, c = id - r * p;
+          const bool ok = r < valid;
+          cp_async8(Xs + r * LD + c, ok ? (const void*)(src + (long long)r * p + c) : (const void*)Xc, ok ? 8 : 0);
+        }
+      }
+      for (int r = tid; r < KC; r += NTHREADS) {
+        const bool ok = r < valid;
+        cp_async8(ys + r, ok ? (const void*)(yc + r_base + r) : (const void*)yc, ok ? 8 : 0);
+        if (WEIGHTED) cp_async8(ws + r, ok ? (const void*)(wc + r_base + r) : (const void*)wc, ok ? 8 : 0);
+      }
+    }
+    cp_async_commit();
   };
+
+  Worker<PB, WEIGHTED> wk;
+  wk.init(a, chain, lane);
 
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
 
   for (int st = 0; st < npipe; ++st) {
     if (BULK) {
-      __syncthreads();                 // everyone is done with the buffer stage st+NSTAGE-1 will overwrite
+      __syncthreads();  // buffer (st-1)%NSTAGE is free again
       issue_stage(st + NSTAGE - 1);
       mbar_wait(full_bar + (st % NSTAGE), (unsigned)((st / NSTAGE) & 1));
     } else {
       cp_async_wait<NSTAGE - 2>();
-      __syncthreads();
+      __syncthreads();  // stage st has landed for everyone; buffer (st-1)%NSTAGE is free again
       issue_stage(st + NSTAGE - 1);
     }
-    compute_stage(smem + (st % NSTAGE) * S::STAGE_DOUBLES);
+    const double* Xs = smem + (st % NSTAGE) * C::STAGE_DOUBLES;
+    if (C::TG == 1 || tg == 0) wk.template stage<0, BULK>(Xs, rg);
+    else wk.template stage<C::TG - 1, BULK>(Xs, rg);
   }
   if (!BULK) cp_async_wait<0>();
   __syncthreads();
   if (BULK && nrows - npipe * KC > 0) {
-    // ragged tail (< KC rows): synchronous staging into buffer 0 with zero rows behind it
+    // ragged tail (< KC rows): synchronous staging into buffer 0 (chunked layout), zero rows behind the data
     const int r_base = npipe * KC, valid = nrows - r_base;
     double* Xs = smem;
     double* ys = Xs + KC * LD;
-    double* ws = ys + KC;
-    for (int id = tid; id < KC * p; id += NTHREADS) {
-      int r = id / p, c = id - r * p;
-      Xs[r * LD + c] = (r < valid) ? Xc[(long long)(r_base + r) * p + c] : 0.0;
+    for (int id = tid; id < KC * 8 * PB; id += NTHREADS) {
+      const int r = id / (8 * PB), c = id - r * (8 * PB);
+      Xs[(r / C::RC) * C::CH + (r % C::RC) * (8 * PB) + c] = (r < valid) ? Xc[(long long)(r_base + r) * p + c] : 0.0;
     }
     for (int r = tid; r < KC; r += NTHREADS) {
       ys[r] = (r < valid) ? yc[r_base + r] : 0.0;
-      if (WEIGHTED) ws[r] = (r < valid) ? wc[r_base + r] : 0.0;
+      if (WEIGHTED) ys[KC + r] = (r < valid) ? wc[r_base + r] : 0.0;
     }
     __syncthreads();
-    compute_stage(Xs);
+    if (C::TG == 1 || tg == 0) wk.template stage<0, true>(Xs, rg);
+    else wk.template stage<C::TG - 1, true>(Xs, rg);
     __syncthreads();
   }
 
-  // ---- combine the 4 warps (rows were split across warps) through shared memory
-  double* red = smem;  // NT*64 + 8*PB + 2*4 doubles, fits in one stage
-  // g: sum over the 4 k-lanes; rss/cnt: lanes sharing kq hold identical copies -> keep g==0 lanes only
+  // ---- combine the row groups through shared memory (per warp: tiles | g | rss, cnt)
+  constexpr int WREC = C::NTG * 64 + 8 * PB + 2;
+  double* red = smem + warp * WREC;
+  const int g = lane >> 2, kq = lane & 3;
 #pragma unroll
-  for (int jb = 0; jb < PB; ++jb) {
-    gacc[jb] += omc_shfl_xor(gacc[jb], 1);
-    gacc[jb] += omc_shfl_xor(gacc[jb], 2);
+  for (int t = 0; t < C::NTG; ++t) {
+    red[t * 64 + 2 * lane] = wk.acc[t][0];
+    red[t * 64 + 2 * lane + 1] = wk.acc[t][1];
   }
-  if (g != 0) { rss = 0.0; cnt = 0.0; }
-  rss = omc_warp_sum(rss);
-  cnt = omc_warp_sum(cnt);
-  for (int wsrc = 1; wsrc < NWARP; ++wsrc) {
-    if (warp == wsrc) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        red[t * 64 + 2 * lane] = acc[t][0];
-        red[t * 64 + 2 * lane + 1] = acc[t][1];
-      }
-      if (kq == 0) {
-#pragma unroll
-        for (int jb = 0; jb < PB; ++jb) red[NT * 64 + 8 * jb + g] = gacc[jb];
-      }
-      if (lane == 0) { red[NT * 64 + 8 * PB] = rss; red[NT * 64 + 8 * PB + 1] = cnt; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        acc[t][0] += red[t * 64 + 2 * lane];
-        acc[t][1] += red[t * 64 + 2 * lane + 1];
-      }
-#pragma unroll
-      for (int jb = 0; jb < PB; ++jb) gacc[jb] += red[NT * 64 + 8 * jb + g];
-      rss += red[NT * 64 + 8 * PB];
-      cnt += red[NT * 64 + 8 * PB + 1];
-    }
-    __syncthreads();
+  for (int jb = 0; jb < PB; ++jb) {  // sum the 4 k-lanes
+    double v = wk.gacc[jb];
+    v += omc_shfl_xor(v, 1);
+    v += omc_shfl_xor(v, 2);
+    if (kq == 0) red[C::NTG * 64 + 8 * jb + g] = v;
   }
+  {
+    // lanes sharing kq hold identical copies of each row's residual -> keep the g == 0 lanes only
+    double r = (g == 0) ? wk.rss : 0.0, c = (g == 0) ? wk.cnt : 0.0;
+    r = omc_warp_sum(r);
+    c = omc_warp_sum(c);
+    if (lane == 0) {
+      red[C::NTG * 64 + 8 * PB] = r;
+      red[C::NTG * 64 + 8 * PB + 1] = c;
+    }
+  }
+  __syncthreads();
 
-  if (warp == 0) {
+  if (rg == 0) {  // one writer warp per tile group
     const int rec = p * p + p + 2;
     double* o = a.out + ((long long)chain * a.n_split + split) * rec;
+    const double* base = smem + tg * WREC;  // warp index of (tg, rg) is rg*TG + tg
 #pragma unroll
     for (int i = 0; i < PB; ++i)
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
         const int t = i * (i + 1) / 2 + j;
-        const int rr = 8 * i + g;
+        if (t / C::NTG != tg) continue;
+        const int tl = t - tg * C::NTG;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int cc = 8 * j + 2 * kq + e;
+          double v = 0.0;
+          for (int q = 0; q < C::RG; ++q) v += base[q * C::TG * WREC + tl * 64 + 2 * lane + e];
+          const int rr = 8 * i + g, cc = 8 * j + 2 * kq + e;
           if (rr < p && cc < p) {
-            o[rr * p + cc] = acc[t][e];
-            if (i != j) o[cc * p + rr] = acc[t][e];
+            o[rr * p + cc] = v;
+            if (i != j) o[cc * p + rr] = v;
           }
         }
       }
-    if (kq == 0) {
-#pragma unroll
-      for (int jb = 0; jb < PB; ++jb)
-        if (8 * jb + g < p) o[p * p + 8 * jb + g] = gacc[jb];
+    if (tg == 0) {
+      for (int c = lane; c < 8 * PB; c += 32) {
+        double v = 0.0;
+        for (int q = 0; q < C::RG; ++q) v += base[q * C::TG * WREC + C::NTG * 64 + c];
+        if (c < p) o[p * p + c] = v;
+      }
     }
-    if (lane == 0) {
-      o[p * p + p] = rss;
-      o[p * p + p + 1] = WEIGHTED ? cnt : (double)nrows;
+    if (tg == C::TG - 1 && lane == 0) {
+      double r = 0.0, c = 0.0;
+      for (int q = 0; q < C::RG; ++q) {
+        r += base[q * C::TG * WREC + C::NTG * 64 + 8 * PB];
+        c += base[q * C::TG * WREC + C::NTG * 64 + 8 * PB + 1];
+      }
+      o[p * p + p] = r;
+      o[p * p + p + 1] = WEIGHTED ? c : (double)nrows;
     }
   }
 }
@@ -401,7 +419,7 @@ __global__ void reg_reduce_kernel(const double* part, double* out, int n_split, 
 template <int PB, bool W, bool B>
 int launch_one(const RegPassArgs& a, cudaStream_t st) {
   dim3 grid(a.n_split, a.n_chains);
-  const int smem = Smem<PB>::BYTES;
+  const int smem = Cfg<PB>::BYTES;
   OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, W, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   reg_pass_kernel<PB, W, B><<<grid, NTHREADS, smem, st>>>(a);
   OMC_LAUNCH_CHECK();
@@ -410,10 +428,10 @@ int launch_one(const RegPassArgs& a, cudaStream_t st) {
 
 template <int PB>
 int launch_pb(const RegPassArgs& a, bool weighted, cudaStream_t st) {
-  // bulk (TMA-engine) row copies need 16-byte aligned rows of a multiple of 16 bytes, for X, y and w alike
+  // bulk (TMA-engine) copies need fully packed rows (p == 8*PB) and 16-byte aligned chunk starts for X, y and w
   auto al16 = [](const void* q) { return (((unsigned long long)q) & 15ull) == 0; };
-  const bool bulk = OMC_RP_USE_BULK && (a.p % 2 == 0) && al16(a.X) && (a.strideX % 2 == 0) && al16(a.y) && (a.strideY % 2 == 0) &&
-                    (!weighted || (al16(a.w) && (a.strideW % 2 == 0)));
+  const bool bulk = OMC_RP_USE_BULK && (a.p == 8 * PB) && al16(a.X) && (a.strideX % 2 == 0) && al16(a.y) &&
+                    (a.strideY % 2 == 0) && (!weighted || (al16(a.w) && (a.strideW % 2 == 0)));
   if (weighted) return bulk ? launch_one<PB, true, true>(a, st) : launch_one<PB, true, false>(a, st);
   return bulk ? launch_one<PB, false, true>(a, st) : launch_one<PB, false, false>(a, st);
 }

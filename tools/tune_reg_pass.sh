@@ -10,10 +10,13 @@ build() { # name flags...
      $SRC/reg_pass.cu $SRC/omc_api.cu $SRC/dense_draw.cu $SRC/logp.cu -o $OUT/libomc_$name.so 2> $OUT/$name.log || { tail -5 $OUT/$name.log; return 1; }
 }
 if [ "$1" == "build" ]; then
-  build bulk_w0 &
-  build bulk_bal -DOMC_RP_BULK_BALANCED=1 &
-  build ldgsts_fast -DOMC_RP_USE_BULK=0 &
-  build ldgsts_fast_s4 -DOMC_RP_USE_BULK=0 -DOMC_RP_NSTAGE=4 -DOMC_RP_KC=48 &
+  build tg2_bulk &
+  build tg1_bulk -DOMC_RP_TG=1 &
+  build tg2_ldgsts -DOMC_RP_USE_BULK=0 &
+  build tg1_bulk_kc64 -DOMC_RP_TG=1 -DOMC_RP_KC=64 -DOMC_RP_NSTAGE=3 &
+  wait
+  build tg2_bulk_kc64s2 -DOMC_RP_KC=64 -DOMC_RP_NSTAGE=2 &
+  build tg2_bulk_kc16s8 -DOMC_RP_KC=16 -DOMC_RP_NSTAGE=8 &
   wait
   ls -la $OUT
 else
