@@ -180,6 +180,86 @@ int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
 int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream);
 int omc_logdet_dense(const double* P, int n_mats, int n, double* out, void* stream);
 
+/* ------------------------------------------------------------------ Metropolis-Hastings family (C4)
+ * The conditional model of the sampled parameter theta (n_elem values per chain) is a sum of up to 4 terms.
+ * ref: Model.log_p / grad_log_p (model.py:57-112) over the conditional model (sampler.py:53-55). */
+#define OMC_TERM_POISSON_RATE 1     /* data k ~ Poisson(rate = theta)                ref: distribution.py:490-508          */
+#define OMC_TERM_GAMMA_RESPONSE 2   /* theta ~ Gamma(shape p1, rate p2)              ref: distribution.py:241-261          */
+#define OMC_TERM_NORMAL_RESPONSE 3  /* theta ~ N(p1, (scalar*P)^-1), optional domain ref: location_scale.py:145-188,222-232 */
+#define OMC_TERM_UNIFORM_RESPONSE 4 /* theta ~ U(p1, p2): constant log-density       ref: distribution.py:422-442          */
+typedef struct {
+  int kind;
+  int mat_kind;        /* NORMAL: 0 eye / 1 diag / 2 dense storage of P                         */
+  int p1_len, p2_len;  /* 1 or n_elem                                                            */
+  omc_vec_t data;      /* POISSON: the counts k [n_elem]                                         */
+  omc_vec_t p1, p2;    /* GAMMA: shape, rate; NORMAL: p1 = mean; UNIFORM: lower, upper           */
+  omc_vec_t P;         /* NORMAL: un-scaled precision                                            */
+  omc_vec_t scalar;    /* NORMAL: scalar multiplying P (NULL => 1)                               */
+  omc_vec_t logdet;    /* NORMAL: log|P| (NULL => 0)                                             */
+  double dom_lo, dom_hi; /* NORMAL: log_p = -inf outside [dom_lo, dom_hi] (+-inf = unbounded)    */
+} omc_term_t;
+typedef struct {
+  int n_chains, n_elem, n_terms;
+  omc_term_t terms[4];
+} omc_mh_model_t;
+
+/* out[c] = sum of the terms' log-densities at theta[c]  (theta: [n_chains][n_elem]) */
+int omc_mh_logp(const omc_mh_model_t* model, const double* theta, double* out, void* stream);
+/* grad [n_chains][n_elem] of the POSITIVE log-density, hess [n_chains][n_elem^2] of the NEGATIVE log-density (may be NULL).
+ * method 0: analytic derivatives (what the samplers use)
+ * method 1: the reference's central finite differences, step 1e-4, Hessian = FD of the FD gradient, applied per term as
+ *           the reference does (Normal terms stay analytic)   ref: distribution.py:124-198 */
+int omc_mh_grad_hess(const omc_mh_model_t* model, const double* theta, int method, double* grad, double* hess,
+                     void* stream);
+
+/* RandomWalk (loop = 0: all elements at once) and RandomWalkLoop (loop = 1: one column of the (p_dim, n_rep) parameter
+ * at a time, each with its own accept/reject).  limits != NULL => truncated-normal proposals with the asymmetric
+ * proposal densities.  Accept iff log(u) < log_accept (strict; NaN rejects).
+ * ref: metropolis_hastings.py:127-173 (accept), :212-269 (proposal), :276-289 (loop); gmrf.py:269-318 (truncnorm) */
+typedef struct {
+  omc_mh_model_t model;
+  double* theta;             /* [n_chains][p_dim*n_rep] in/out, row-major (p_dim, n_rep)                 */
+  int p_dim, n_rep, loop;
+  omc_vec_t step;            /* step sizes; step_rows in {1,p_dim}, step_cols in {1,n_rep}              */
+  int step_rows, step_cols;
+  const double* limits;      /* [p_dim][2] lower, upper (shared by all chains) or NULL                  */
+  omc_rng_t rng;
+  const double* debug_z;     /* injected proposal variates: N(0,1) (untruncated) or the uniforms behind
+                                truncnorm.rvs (truncated); [n_chains][n_steps][p_prop]                  */
+  const double* debug_u;     /* injected accept uniforms [n_chains][n_steps]                            */
+  long long debug_sweep_stride_z, debug_sweep_stride_u;
+  long long* counters;       /* optional [n_chains][2]: accepted, proposed (ref AcceptRate)             */
+  double* probe;             /* optional [n_chains][n_steps][5]: logp_cur, logp_prop, logq_fwd, logq_rev, accepted */
+} omc_random_walk_t;
+int omc_random_walk(const omc_random_walk_t* args, void* stream);
+
+/* ManifoldMALA: proposal N(theta + 1/2 s^2 H^-1 g, s^2 H^-1) forward and reverse, dense H (n_elem <= 64).
+ * ref: metropolis_hastings.py:292-373.  A non-PD Hessian or a NaN (proposal outside the support) REJECTS the move and
+ * sets the chain's status bits; the reference raises instead. */
+typedef struct {
+  omc_mh_model_t model;
+  double* theta;             /* [n_chains][n_elem] in/out                                               */
+  double step;
+  int method;                /* derivatives: 0 analytic, 1 reference finite differences                 */
+  omc_rng_t rng;
+  const double* debug_z;     /* injected N(0,1) [n_chains][n_elem]                                      */
+  const double* debug_u;     /* injected accept uniform [n_chains]                                      */
+  long long debug_sweep_stride_z, debug_sweep_stride_u;
+  long long* counters;       /* optional [n_chains][2]                                                  */
+  int* status;               /* optional [n_chains]                                                     */
+  double* probe_mu;          /* optional [n_chains][n_elem]   forward proposal mean                     */
+  double* probe_L;           /* optional [n_chains][n_elem^2] forward proposal Cholesky factor          */
+  double* probe_prop;        /* optional [n_chains][n_elem]   proposed point                            */
+  double* probe_scalars;     /* optional [n_chains][6]: logp_cur, logp_prop, logq_fwd, logq_rev, log_accept, accepted */
+} omc_mmala_t;
+int omc_mmala(const omc_mmala_t* args, void* stream);
+
+/* element-wise truncated-normal helpers exposed for parity tests (ref: gmrf.py:269-318 / scipy.stats.truncnorm) */
+int omc_truncnorm_rv(const double* mean, const double* scale, const double* lower, const double* upper,
+                     const double* u, long long n, double* out, void* stream);
+int omc_truncnorm_logpdf(const double* x, const double* mean, const double* scale, const double* lower,
+                         const double* upper, long long n, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,559 @@
+// Metropolis-Hastings kernels: model log-density / gradient / Hessian over a term list,
+// RandomWalk / RandomWalkLoop (Gaussian and truncated-Gaussian proposals) and ManifoldMALA, batched over chains.
+//
+// Mapping: one WARP per chain for log_p / gradients / random-walk steps (lanes stride over the n_elem parameters, warp
+// shuffles reduce the sums); one CTA per chain for ManifoldMALA (dense Hessian + Cholesky in shared memory).  Chain
+// state stays in HBM between sweeps; within a kernel it lives in shared memory.  These kernels are latency / FP64-ALU
+// bound (lgamma, log, erfc): bytes per chain-iteration are ~1 KB.
+#include "../../include/omc.h"
+#include "omc_common.cuh"
+#include "omc_internal.h"
+#include "omc_smallmat.cuh"
+#include "omc_special.cuh"
+
+namespace {
+
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+constexpr int MH_WARPS = 4;  // warps (= chains) per CTA in the warp-per-chain kernels
+
+__device__ __forceinline__ double vat(const omc_vec_t& v, int chain, long long i, double dflt) {
+  return v.ptr ? v.ptr[(long long)chain * v.chain_stride + i] : dflt;
+}
+__device__ __forceinline__ OmcRng to_rng(const omc_rng_t& r) {
+  OmcRng o;
+  o.seed = r.seed; o.sweep = r.sweep; o.chain_offset = r.chain_offset; o.site = r.site;
+  return o;
+}
+__device__ __forceinline__ double mat_at(int kind, const omc_vec_t& P, int chain, int n, int i, int j) {
+  if (kind == OMC_MAT_DENSE) return P.ptr[(long long)chain * P.chain_stride + (long long)i * n + j];
+  if (i != j) return 0.0;
+  if (kind == OMC_MAT_DIAG) return P.ptr[(long long)chain * P.chain_stride + i];
+  return P.ptr ? P.ptr[(long long)chain * P.chain_stride] : 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------- term log-densities
+// Warp-cooperative: every lane of the warp calls with the same arguments; result valid in all lanes.
+__device__ double term_logp_warp(const omc_term_t& t, int n, int chain, const double* th) {
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  switch (t.kind) {
+    case OMC_TERM_POISSON_RATE:
+      for (int i = lane; i < n; i += 32) {
+        const double k = vat(t.data, chain, i, 0.0), mu = th[i];
+        double lp = omc_xlogy(k, mu) - lgamma(k + 1.0) - mu;
+        if (!(mu >= 0.0)) lp = nan("");                       // scipy: invalid rate -> nan
+        else if (!(k >= 0.0) || floor(k) != k) lp = -INFINITY;  // off the support
+        acc += lp;
+      }
+      break;
+    case OMC_TERM_GAMMA_RESPONSE:
+      for (int i = lane; i < n; i += 32) {
+        const double x = th[i];
+        const double sh = vat(t.p1, chain, t.p1_len > 1 ? i : 0, 1.0), rt = vat(t.p2, chain, t.p2_len > 1 ? i : 0, 1.0);
+        const double scale = 1.0 / rt, y = x / scale;
+        double lp = omc_xlogy(sh - 1.0, y) - y - lgamma(sh) - log(scale);
+        if (!(y >= 0.0)) lp = isnan(y) ? y : -INFINITY;
+        acc += lp;
+      }
+      break;
+    case OMC_TERM_NORMAL_RESPONSE: {
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      bool outside = false;
+      for (int i = lane; i < n; i += 32) {
+        const double ri = th[i] - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0);
+        if (th[i] < t.dom_lo || th[i] > t.dom_hi) outside = true;
+        double q;
+        if (t.mat_kind == OMC_MAT_DENSE) {
+          q = 0.0;
+          for (int j = 0; j < n; ++j)
+            q += mat_at(OMC_MAT_DENSE, t.P, chain, n, i, j) * (th[j] - vat(t.p1, chain, t.p1_len > 1 ? j : 0, 0.0));
+        } else {
+          q = mat_at(t.mat_kind, t.P, chain, n, i, i) * ri;
+        }
+        acc += ri * q;
+      }
+      acc = omc_warp_sum(acc);
+      outside = __any_sync(0xffffffffu, outside);
+      if (outside) return -INFINITY;
+      return 0.5 * (n * log(s) + vat(t.logdet, chain, 0, 0.0) - n * LOG_2PI - s * acc);
+    }
+    case OMC_TERM_UNIFORM_RESPONSE:
+      for (int i = lane; i < n; i += 32)
+        acc -= log(vat(t.p2, chain, t.p2_len > 1 ? i : 0, 1.0) - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0));
+      break;
+    default:
+      break;
+  }
+  return omc_warp_sum(acc);
+}
+
+__device__ double model_logp_warp(const omc_mh_model_t& m, int chain, const double* th) {
+  double s = 0.0;
+  for (int k = 0; k < m.n_terms; ++k) s += term_logp_warp(m.terms[k], m.n_elem, chain, th);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------- derivatives
+// Analytic gradient (positive log-pdf) and Hessian (negative log-pdf) of one term, accumulated into g[n], H[n x ldh].
+// Thread-parallel over `nthr` cooperating threads with index `tid`.
+__device__ void term_grad_hess_analytic(const omc_term_t& t, int n, int chain, const double* th, double* g, double* H,
+                                        int ldh, int tid, int nthr) {
+  switch (t.kind) {
+    case OMC_TERM_POISSON_RATE:
+      for (int i = tid; i < n; i += nthr) {
+        const double k = vat(t.data, chain, i, 0.0), x = th[i];
+        g[i] += k / x - 1.0;
+        if (H) H[i * ldh + i] += k / (x * x);
+      }
+      break;
+    case OMC_TERM_GAMMA_RESPONSE:
+      for (int i = tid; i < n; i += nthr) {
+        const double x = th[i];
+        const double sh = vat(t.p1, chain, t.p1_len > 1 ? i : 0, 1.0), rt = vat(t.p2, chain, t.p2_len > 1 ? i : 0, 1.0);
+        g[i] += (sh - 1.0) / x - rt;
+        if (H) H[i * ldh + i] += (sh - 1.0) / (x * x);
+      }
+      break;
+    case OMC_TERM_NORMAL_RESPONSE: {
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      for (int i = tid; i < n; i += nthr) {
+        double q = 0.0;
+        if (t.mat_kind == OMC_MAT_DENSE) {
+          for (int j = 0; j < n; ++j) {
+            const double pij = mat_at(OMC_MAT_DENSE, t.P, chain, n, i, j);
+            q += pij * (th[j] - vat(t.p1, chain, t.p1_len > 1 ? j : 0, 0.0));
+            if (H) H[i * ldh + j] += s * pij;
+          }
+        } else {
+          const double pii = mat_at(t.mat_kind, t.P, chain, n, i, i);
+          q = pii * (th[i] - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0));
+          if (H) H[i * ldh + i] += s * pii;
+        }
+        g[i] += -s * q;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// The reference's finite differences for one term (warp-cooperative; th is a scratch copy the warp may perturb).
+//   grad_k = [l(th + h/2 e_k) - l(th - h/2 e_k)] / h                       distribution.py:124-158
+//   H[:,k] = [grad(th - h/2 e_k) - grad(th + h/2 e_k)] / h                 distribution.py:160-198
+__device__ void term_grad_fd_warp(const omc_term_t& t, int n, int chain, double* th, double* gout /*n, lane-strided*/) {
+  const int lane = threadIdx.x & 31;
+  const double h = 1e-4;
+  for (int k = 0; k < n; ++k) {
+    const double x0 = th[k];
+    __syncwarp();
+    if (lane == 0) th[k] = x0 + h / 2;
+    __syncwarp();
+    const double lp = term_logp_warp(t, n, chain, th);
+    __syncwarp();
+    if (lane == 0) th[k] = x0 + (-h / 2);
+    __syncwarp();
+    const double lm = term_logp_warp(t, n, chain, th);
+    __syncwarp();
+    if (lane == 0) { th[k] = x0; gout[k] = (lp - lm) / h; }
+    __syncwarp();
+  }
+}
+
+// warp-cooperative gradient (+ optional Hessian) of the whole model at th (shared memory, n doubles).
+// scratch: >= 3n doubles of shared memory private to the warp.
+__device__ void model_grad_hess_warp(const omc_mh_model_t& m, int chain, const double* th, int method, double* g,
+                                     double* H, int ldh, double* scratch) {
+  const int lane = threadIdx.x & 31, n = m.n_elem;
+  for (int i = lane; i < n; i += 32) g[i] = 0.0;
+  if (H)
+    for (int e = lane; e < n * n; e += 32) H[(e / n) * ldh + (e % n)] = 0.0;
+  __syncwarp();
+  for (int k = 0; k < m.n_terms; ++k) {
+    const omc_term_t& t = m.terms[k];
+    if (method == 0 || t.kind == OMC_TERM_NORMAL_RESPONSE) {
+      term_grad_hess_analytic(t, n, chain, th, g, H, ldh, lane, 32);
+      __syncwarp();
+      continue;
+    }
+    double* thw = scratch;          // perturbed copy
+    double* gt = scratch + n;       // term gradient
+    double* gp = scratch + 2 * n;   // gradient at a perturbed point
+    for (int i = lane; i < n; i += 32) thw[i] = th[i];
+    __syncwarp();
+    term_grad_fd_warp(t, n, chain, thw, gt);
+    for (int i = lane; i < n; i += 32) g[i] += gt[i];
+    __syncwarp();
+    if (H) {
+      const double h = 1e-4;
+      for (int c = 0; c < n; ++c) {
+        const double x0 = thw[c];
+        __syncwarp();
+        if (lane == 0) thw[c] = x0 + h / 2;
+        __syncwarp();
+        term_grad_fd_warp(t, n, chain, thw, gp);
+        for (int i = lane; i < n; i += 32) gt[i] = gp[i];  // gt <- grad_plus (term gradient already added to g)
+        __syncwarp();
+        if (lane == 0) thw[c] = x0 + (-h / 2);
+        __syncwarp();
+        term_grad_fd_warp(t, n, chain, thw, gp);             // gp = grad_minus
+        for (int i = lane; i < n; i += 32) H[i * ldh + c] += (gp[i] - gt[i]) / h;
+        __syncwarp();
+        if (lane == 0) thw[c] = x0;
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- probes
+__global__ void __launch_bounds__(MH_WARPS * 32) mh_logp_kernel(omc_mh_model_t m, const double* theta, double* out) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * MH_WARPS + warp;
+  if (chain >= m.n_chains) return;
+  double* th = sm + warp * m.n_elem;
+  for (int i = lane; i < m.n_elem; i += 32) th[i] = theta[(long long)chain * m.n_elem + i];
+  __syncwarp();
+  const double lp = model_logp_warp(m, chain, th);
+  if (lane == 0) out[chain] = lp;
+}
+
+__global__ void __launch_bounds__(MH_WARPS * 32) mh_grad_hess_kernel(omc_mh_model_t m, const double* theta, int method,
+                                                                    double* grad, double* hess) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = m.n_elem;
+  const int chain = blockIdx.x * MH_WARPS + warp;
+  if (chain >= m.n_chains) return;
+  double* base = sm + warp * (5 * n);
+  double* th = base;
+  double* g = base + n;
+  double* scratch = base + 2 * n;
+  for (int i = lane; i < n; i += 32) th[i] = theta[(long long)chain * n + i];
+  __syncwarp();
+  double* H = hess ? hess + (long long)chain * n * n : nullptr;  // accumulate straight into global memory
+  model_grad_hess_warp(m, chain, th, method, g, H, n, scratch);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) grad[(long long)chain * n + i] = g[i];
+}
+
+// ---------------------------------------------------------------------------------------------- random walk
+__global__ void __launch_bounds__(MH_WARPS * 32) random_walk_kernel(omc_random_walk_t a) {
+  extern __shared__ double sm[];
+  const omc_mh_model_t& m = a.model;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = m.n_elem;
+  const int chain = blockIdx.x * MH_WARPS + warp;
+  if (chain >= m.n_chains) return;
+  double* cur = sm + warp * (2 * n);
+  double* prop = cur + n;
+  double* gth = a.theta + (long long)chain * n;
+  for (int i = lane; i < n; i += 32) cur[i] = prop[i] = gth[i];
+  __syncwarp();
+  const OmcRng rng = to_rng(a.rng);
+  const long long sw = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+  const int n_steps = a.loop ? a.n_rep : 1;
+  const int p_prop = a.loop ? a.p_dim : n;                 // elements proposed per step
+  const unsigned blocks_per_step = (unsigned)((p_prop + 1) / 2 + 1);
+  const double* dz = a.debug_z ? a.debug_z + sw * a.debug_sweep_stride_z + (long long)chain * n_steps * p_prop : nullptr;
+  const double* du = a.debug_u ? a.debug_u + sw * a.debug_sweep_stride_u + (long long)chain * n_steps : nullptr;
+  double logp_cur = model_logp_warp(m, chain, cur);
+  long long n_acc = 0;
+  for (int stp = 0; stp < n_steps; ++stp) {
+    // ---- proposal for the elements of this step: element e = i*n_rep + col (loop) or e = q (joint)
+    double lq_fwd = 0.0, lq_rev = 0.0;
+    for (int q = lane; q < p_prop; q += 32) {
+      const int row = a.loop ? q : q / a.n_rep, col = a.loop ? stp : q % a.n_rep;
+      const int e = row * a.n_rep + col;
+      const double stepv = vat(a.step, chain, (a.step_rows > 1 ? row : 0) * (a.step_cols > 1 ? a.n_rep : 1) +
+                                                  (a.step_cols > 1 ? col : 0), 0.2);
+      double var;  // N(0,1) or U(0,1) driving this element's proposal
+      if (dz) var = dz[(long long)stp * p_prop + q];
+      else {
+        uint4 b = omc_rng_block(rng, chain, stp * blocks_per_step + (unsigned)(q >> 1));
+        if (a.limits) var = (q & 1) ? omc_u01(b.z, b.w) : omc_u01(b.x, b.y);
+        else {
+          double z0, z1;
+          omc_normal2(rng, chain, stp * blocks_per_step + (unsigned)(q >> 1), z0, z1);
+          var = (q & 1) ? z1 : z0;
+        }
+      }
+      const double mu = cur[e];
+      if (a.limits) {
+        const double lb = a.limits[2 * row], ub = a.limits[2 * row + 1];
+        const double z = omc_truncated_normal_rv(mu, stepv, lb, ub, var);
+        prop[e] = z;
+        lq_fwd += omc_truncated_normal_log_pdf(z, mu, stepv, lb, ub);
+        lq_rev += omc_truncated_normal_log_pdf(mu, z, stepv, lb, ub);
+      } else {
+        prop[e] = mu + stepv * var;
+      }
+    }
+    lq_fwd = omc_warp_sum(lq_fwd);
+    lq_rev = omc_warp_sum(lq_rev);
+    __syncwarp();
+    const double logp_prop = model_logp_warp(m, chain, prop);
+    // ---- accept / reject (metropolis_hastings.py:155-173)
+    double u;
+    if (du) u = du[stp];
+    else {
+      uint4 b = omc_rng_block(rng, chain, stp * blocks_per_step + blocks_per_step - 1);
+      u = omc_u01(b.x, b.y);
+    }
+    const double log_accept = logp_prop + lq_rev - (logp_cur + lq_fwd);
+    const bool accept = log(u) < log_accept;
+    if (a.probe && lane == 0) {
+      double* pr = a.probe + ((long long)chain * n_steps + stp) * 5;
+      pr[0] = logp_cur; pr[1] = logp_prop; pr[2] = lq_fwd; pr[3] = lq_rev; pr[4] = accept ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int q = lane; q < p_prop; q += 32) {
+      const int row = a.loop ? q : q / a.n_rep, col = a.loop ? stp : q % a.n_rep;
+      const int e = row * a.n_rep + col;
+      if (accept) cur[e] = prop[e];
+      else prop[e] = cur[e];
+    }
+    if (accept) { logp_cur = logp_prop; ++n_acc; }
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) gth[i] = cur[i];
+  if (a.counters && lane == 0) {
+    a.counters[2 * (long long)chain] += n_acc;
+    a.counters[2 * (long long)chain + 1] += n_steps;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- manifold MALA
+constexpr int MM_THREADS = 128;
+
+// proposal parameters at `th`: L = chol(H / step^2) (in Hm), mu = th + 1/2 (L L')^-1 g.  Returns false if not PD / NaN.
+// ref: metropolis_hastings.py:325-348
+__device__ bool mmala_params(const omc_mmala_t& a, int chain, const double* th, double* Hm, int ld, double* g, double* mu,
+                             double* scratch) {
+  const int n = a.model.n_elem, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) model_grad_hess_warp(a.model, chain, th, a.method, g, Hm, ld, scratch);
+  __syncthreads();
+  const double inv_s2 = 1.0 / (a.step * a.step);
+  bool bad = false;
+  for (int e = tid; e < n * n; e += MM_THREADS) {
+    const double v = Hm[(e / n) * ld + (e % n)] * inv_s2;  // precision_cr = hessian_cr / step**2
+    Hm[(e / n) * ld + (e % n)] = v;
+    if (isnan(v) || isinf(v)) bad = true;
+  }
+  for (int i = tid; i < n; i += MM_THREADS)
+    if (isnan(g[i]) || isinf(g[i])) bad = true;
+  if (__syncthreads_or(bad)) return false;
+  if (!omc_chol_block(Hm, n, ld)) return false;
+  __syncthreads();
+  if (warp == 0) {
+    double x0 = (lane < n) ? g[lane] : 0.0, x1 = (lane + 32 < n) ? g[lane + 32] : 0.0;
+    omc_warp_solve_lower(Hm, n, ld, x0, x1);
+    omc_warp_solve_lower_T(Hm, n, ld, x0, x1);
+    if (lane < n) mu[lane] = th[lane] + 0.5 * x0;
+    if (lane + 32 < n) mu[lane + 32] = th[lane + 32] + 0.5 * x1;
+  }
+  __syncthreads();
+  return true;
+}
+
+// log N(x | mu, (L L')^-1) up to the constant the reference drops: sum log diag L - 1/2 |L'(x - mu)|^2
+// ref: metropolis_hastings.py:350-373.  Called by warp 0 only.
+__device__ double mmala_log_density_warp(const double* L, int n, int ld, const double* x, const double* mu) {
+  const int lane = threadIdx.x & 31;
+  const double r0 = (lane < n) ? x[lane] - mu[lane] : 0.0, r1 = (lane + 32 < n) ? x[lane + 32] - mu[lane + 32] : 0.0;
+  double w0, w1;
+  omc_warp_mul_lower_T(L, n, ld, r0, r1, w0, w1);
+  double ld_sum = 0.0;
+  if (lane < n) ld_sum += log(L[lane * ld + lane]);
+  if (lane + 32 < n) ld_sum += log(L[(lane + 32) * ld + lane + 32]);
+  ld_sum = omc_warp_sum(ld_sum);
+  const double ww = omc_warp_sum(w0 * w0 + w1 * w1);
+  return ld_sum - 0.5 * ww;
+}
+
+__global__ void __launch_bounds__(MM_THREADS) mmala_kernel(omc_mmala_t a) {
+  extern __shared__ double sm[];
+  const int n = a.model.n_elem, ld = n + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chain = blockIdx.x;
+  double* Hm = sm;              // n x ld
+  double* cur = Hm + n * ld;    // n
+  double* prop = cur + n;       // n
+  double* g = prop + n;         // n
+  double* mu = g + n;           // n
+  double* zv = mu + n;          // n
+  double* scratch = zv + n;     // 3n
+  __shared__ double sc[8];
+  double* gth = a.theta + (long long)chain * n;
+  for (int i = tid; i < n; i += MM_THREADS) cur[i] = gth[i];
+  __syncthreads();
+  const long long sw = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+  const OmcRng rng = to_rng(a.rng);
+  int status = 0;
+  bool ok = mmala_params(a, chain, cur, Hm, ld, g, mu, scratch);
+  if (!ok) status |= OMC_STATUS_NOT_PD;
+  if (ok) {
+    // z, then prop = mu + L^-T z  (gmrf.sample_normal, gmrf.py:29-61)
+    if (a.debug_z) {
+      const double* dz = a.debug_z + sw * a.debug_sweep_stride_z + (long long)chain * n;
+      for (int i = tid; i < n; i += MM_THREADS) zv[i] = dz[i];
+    } else {
+      for (int t = tid; 2 * t < n; t += MM_THREADS) {
+        double z0, z1;
+        omc_normal2(rng, chain, t, z0, z1);
+        zv[2 * t] = z0;
+        if (2 * t + 1 < n) zv[2 * t + 1] = z1;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = (lane < n) ? zv[lane] : 0.0, x1 = (lane + 32 < n) ? zv[lane + 32] : 0.0;
+      omc_warp_solve_lower_T(Hm, n, ld, x0, x1);
+      if (lane < n) prop[lane] = x0 + mu[lane];
+      if (lane + 32 < n) prop[lane + 32] = x1 + mu[lane + 32];
+      __syncwarp();
+      const double lq = mmala_log_density_warp(Hm, n, ld, prop, mu);
+      const double lpc = model_logp_warp(a.model, chain, cur);
+      const double lpp = model_logp_warp(a.model, chain, prop);
+      if (lane == 0) { sc[0] = lpc; sc[1] = lpp; sc[2] = lq; }
+    }
+    __syncthreads();
+    if (a.probe_mu) for (int i = tid; i < n; i += MM_THREADS) a.probe_mu[(long long)chain * n + i] = mu[i];
+    if (a.probe_prop) for (int i = tid; i < n; i += MM_THREADS) a.probe_prop[(long long)chain * n + i] = prop[i];
+    if (a.probe_L)
+      for (int e = tid; e < n * n; e += MM_THREADS)
+        a.probe_L[(long long)chain * n * n + e] = ((e % n) <= (e / n)) ? Hm[(e / n) * ld + (e % n)] : 0.0;
+    __syncthreads();
+    // reverse proposal parameters at the proposed point
+    const bool ok2 = mmala_params(a, chain, prop, Hm, ld, g, mu, scratch);
+    if (!ok2) { status |= OMC_STATUS_NAN; ok = false; }
+    else if (warp == 0) {
+      const double lqr = mmala_log_density_warp(Hm, n, ld, cur, mu);
+      if (lane == 0) sc[3] = lqr;
+    }
+    __syncthreads();
+  }
+  bool accept = false;
+  double log_accept = nan("");
+  if (ok) {
+    double u;
+    if (a.debug_u) u = a.debug_u[sw * a.debug_sweep_stride_u + chain];
+    else {
+      uint4 b = omc_rng_block(rng, chain, 0xFFFFu);
+      u = omc_u01(b.x, b.y);
+    }
+    log_accept = sc[1] + sc[3] - (sc[0] + sc[2]);
+    accept = log(u) < log_accept;
+    if (isnan(log_accept)) status |= OMC_STATUS_NAN;
+  }
+  if (accept)
+    for (int i = tid; i < n; i += MM_THREADS) gth[i] = prop[i];
+  if (tid == 0) {
+    if (a.counters) {
+      a.counters[2 * (long long)chain] += accept ? 1 : 0;
+      a.counters[2 * (long long)chain + 1] += 1;
+    }
+    if (a.status && status) atomicOr(&a.status[chain], status);
+    if (a.probe_scalars) {
+      double* ps = a.probe_scalars + (long long)chain * 6;
+      ps[0] = sc[0]; ps[1] = sc[1]; ps[2] = sc[2]; ps[3] = sc[3]; ps[4] = log_accept; ps[5] = accept ? 1.0 : 0.0;
+    }
+  }
+}
+
+__global__ void truncnorm_rv_kernel(const double* mean, const double* scale, const double* lower, const double* upper,
+                                    const double* u, long long n, double* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = omc_truncated_normal_rv(mean[i], scale[i], lower[i], upper[i], u[i]);
+}
+__global__ void truncnorm_logpdf_kernel(const double* x, const double* mean, const double* scale, const double* lower,
+                                        const double* upper, long long n, double* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = omc_truncated_normal_log_pdf(x[i], mean[i], scale[i], lower[i], upper[i]);
+}
+
+int check_model(const omc_mh_model_t* m, const char* who) {
+  OMC_REQUIRE(m->n_chains >= 1 && m->n_elem >= 1 && m->n_terms >= 0 && m->n_terms <= 4, "%s: bad model shape", who);
+  for (int k = 0; k < m->n_terms; ++k) {
+    const omc_term_t& t = m->terms[k];
+    OMC_REQUIRE(t.kind >= 1 && t.kind <= 4, "%s: unknown term kind %d", who, t.kind);
+    if (t.kind == OMC_TERM_POISSON_RATE) OMC_REQUIRE(t.data.ptr, "%s: Poisson term without counts", who);
+    if (t.kind == OMC_TERM_NORMAL_RESPONSE)
+      OMC_REQUIRE(t.mat_kind == OMC_MAT_EYE || t.P.ptr, "%s: Normal term without precision", who);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int omc_mh_logp(const omc_mh_model_t* model, const double* theta, double* out, void* stream) {
+  OMC_REQUIRE(model && theta && out, "omc_mh_logp: null argument");
+  if (int rc = check_model(model, "omc_mh_logp")) return rc;
+  const int blocks = (model->n_chains + MH_WARPS - 1) / MH_WARPS;
+  const size_t smem = (size_t)MH_WARPS * model->n_elem * sizeof(double);
+  mh_logp_kernel<<<blocks, MH_WARPS * 32, smem, (cudaStream_t)stream>>>(*model, theta, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_mh_grad_hess(const omc_mh_model_t* model, const double* theta, int method, double* grad, double* hess,
+                     void* stream) {
+  OMC_REQUIRE(model && theta && grad, "omc_mh_grad_hess: null argument");
+  OMC_REQUIRE(method == 0 || method == 1, "omc_mh_grad_hess: method=%d", method);
+  if (int rc = check_model(model, "omc_mh_grad_hess")) return rc;
+  const int blocks = (model->n_chains + MH_WARPS - 1) / MH_WARPS;
+  const size_t smem = (size_t)MH_WARPS * 5 * model->n_elem * sizeof(double);
+  OMC_REQUIRE(smem <= 200 * 1024, "omc_mh_grad_hess: n_elem=%d too large", model->n_elem);
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(mh_grad_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mh_grad_hess_kernel<<<blocks, MH_WARPS * 32, smem, (cudaStream_t)stream>>>(*model, theta, method, grad, hess);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_random_walk(const omc_random_walk_t* a, void* stream) {
+  OMC_REQUIRE(a && a->theta, "omc_random_walk: null argument");
+  if (int rc = check_model(&a->model, "omc_random_walk")) return rc;
+  OMC_REQUIRE(a->p_dim >= 1 && a->n_rep >= 1 && a->p_dim * a->n_rep == a->model.n_elem,
+              "omc_random_walk: (p_dim=%d, n_rep=%d) does not match n_elem=%d", a->p_dim, a->n_rep, a->model.n_elem);
+  OMC_REQUIRE((a->step_rows == 1 || a->step_rows == a->p_dim) && (a->step_cols == 1 || a->step_cols == a->n_rep),
+              "omc_random_walk: step shape (%d,%d)", a->step_rows, a->step_cols);
+  const int blocks = (a->model.n_chains + MH_WARPS - 1) / MH_WARPS;
+  const size_t smem = (size_t)MH_WARPS * 2 * a->model.n_elem * sizeof(double);
+  OMC_REQUIRE(smem <= 200 * 1024, "omc_random_walk: n_elem=%d too large", a->model.n_elem);
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(random_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  random_walk_kernel<<<blocks, MH_WARPS * 32, smem, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_mmala(const omc_mmala_t* a, void* stream) {
+  OMC_REQUIRE(a && a->theta, "omc_mmala: null argument");
+  if (int rc = check_model(&a->model, "omc_mmala")) return rc;
+  const int n = a->model.n_elem;
+  OMC_REQUIRE(n <= 64, "omc_mmala: n_elem=%d > 64 is not supported", n);
+  OMC_REQUIRE(a->step > 0.0, "omc_mmala: step=%g", a->step);
+  const size_t smem = (size_t)(n * (n + 1) + 8 * n) * sizeof(double);
+  mmala_kernel<<<a->model.n_chains, MM_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_truncnorm_rv(const double* mean, const double* scale, const double* lower, const double* upper,
+                     const double* u, long long n, double* out, void* stream) {
+  OMC_REQUIRE(mean && scale && lower && upper && u && out && n >= 0, "omc_truncnorm_rv: bad argument");
+  if (n == 0) return 0;
+  truncnorm_rv_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(mean, scale, lower, upper, u, n, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_truncnorm_logpdf(const double* x, const double* mean, const double* scale, const double* lower,
+                         const double* upper, long long n, double* out, void* stream) {
+  OMC_REQUIRE(x && mean && scale && lower && upper && out && n >= 0, "omc_truncnorm_logpdf: bad argument");
+  if (n == 0) return 0;
+  truncnorm_logpdf_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, mean, scale, lower, upper, n,
+                                                                                          out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
