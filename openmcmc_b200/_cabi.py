@@ -117,6 +117,39 @@ class LinearPredictor(C.Structure):
                 ("theta", Vec * 4), ("out", C.c_void_p)]
 
 
+class Term(C.Structure):
+    """omc_term_t"""
+
+    _fields_ = [("kind", C.c_int), ("mat_kind", C.c_int), ("p1_len", C.c_int), ("p2_len", C.c_int), ("data", Vec),
+                ("p1", Vec), ("p2", Vec), ("P", Vec), ("scalar", Vec), ("logdet", Vec), ("dom_lo", C.c_double),
+                ("dom_hi", C.c_double)]
+
+
+class MHModel(C.Structure):
+    """omc_mh_model_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n_elem", C.c_int), ("n_terms", C.c_int), ("terms", Term * 4)]
+
+
+class RandomWalkArgs(C.Structure):
+    """omc_random_walk_t"""
+
+    _fields_ = [("model", MHModel), ("theta", C.c_void_p), ("p_dim", C.c_int), ("n_rep", C.c_int), ("loop", C.c_int),
+                ("step", Vec), ("step_rows", C.c_int), ("step_cols", C.c_int), ("limits", C.c_void_p), ("rng", Rng),
+                ("debug_z", C.c_void_p), ("debug_u", C.c_void_p), ("debug_sweep_stride_z", C.c_longlong),
+                ("debug_sweep_stride_u", C.c_longlong), ("counters", C.c_void_p), ("probe", C.c_void_p)]
+
+
+class MMalaArgs(C.Structure):
+    """omc_mmala_t"""
+
+    _fields_ = [("model", MHModel), ("theta", C.c_void_p), ("step", C.c_double), ("method", C.c_int), ("rng", Rng),
+                ("debug_z", C.c_void_p), ("debug_u", C.c_void_p), ("debug_sweep_stride_z", C.c_longlong),
+                ("debug_sweep_stride_u", C.c_longlong), ("counters", C.c_void_p), ("status", C.c_void_p),
+                ("probe_mu", C.c_void_p), ("probe_L", C.c_void_p), ("probe_prop", C.c_void_p),
+                ("probe_scalars", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
 PROTOTYPES = {
     "omc_abi_version": (C.c_int, []),
@@ -147,6 +180,12 @@ PROTOTYPES = {
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "omc_mh_logp": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "omc_mh_grad_hess": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "omc_random_walk": (C.c_int, [C.POINTER(RandomWalkArgs), C.c_void_p]),
+    "omc_mmala": (C.c_int, [C.POINTER(MMalaArgs), C.c_void_p]),
+    "omc_truncnorm_rv": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]),
+    "omc_truncnorm_logpdf": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]),
 }
 
 

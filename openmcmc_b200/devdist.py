@@ -1,0 +1,172 @@
+"""Distributions on the device: pattern-matching of a conditional Model onto the term list of the MH kernels
+(include/omc.h: omc_mh_model_t) and the host-array entry points behind `dist.log_p`, `dist.grad_log_p`, `dist.rvs`.
+
+ref: model.py:57-112 (Model.log_p / grad_log_p fan-out), distribution.py:241-261, 490-508, 422-442,
+location_scale.py:145-250.  Host logic only (shapes and matching); every value is computed by libomc kernels.
+"""
+
+import numpy as np
+import torch
+
+from openmcmc_b200 import engine
+from openmcmc_b200 import kernels as K
+from openmcmc_b200.parameter import Identity
+
+F64 = torch.float64
+
+
+def _expand(plan, arr: "engine.DevArray", p_dim: int, n_rep: int):
+    """Operand of a term: returns (vec, len) with len in {1, n_elem}; (p_dim,1) operands of a replicated parameter are
+    broadcast along the replicate axis once at plan time (constant data)."""
+    n_elem = p_dim * n_rep
+    if arr.size in (1, n_elem):
+        return arr.vec(), arr.size
+    if arr.size == p_dim and arr.cols == 1:
+        t = arr.data.reshape(-1, p_dim, 1).expand(-1, p_dim, n_rep).contiguous()
+        plan.keep.append(t)
+        return (K.vec(t, n_elem) if arr.per_chain else K.vec(t)), n_elem
+    raise engine.PlanError(f"operand of shape ({arr.rows},{arr.cols}) cannot be broadcast to ({p_dim},{n_rep})")
+
+
+def build_terms(plan: "engine.Plan", host_state: dict, model, param: str):
+    """Term list of the conditional model of `param` (every member distribution of `model` that depends on it).
+
+    Returns (omc_mh_model_t, labels).  Raises PlanError for combinations the device path does not implement.
+    """
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal, NullDistribution
+
+    st = plan.state
+    theta = st[param]
+    p_dim, n_rep = theta.rows, theta.cols
+    n_elem = p_dim * n_rep
+    terms, labels = [], []
+    for dist in model.values():
+        if param not in dist.param_list or isinstance(dist, NullDistribution):
+            continue
+        if isinstance(dist, Poisson) and isinstance(dist.rate, Identity) and dist.rate.form == param:
+            k = st[dist.response]
+            if k.size != n_elem:
+                raise engine.PlanError(f"Poisson response '{dist.response}' does not match the shape of '{param}'")
+            terms.append(K.term(K.TERM_POISSON_RATE, data=k.vec()))
+        elif isinstance(dist, Gamma) and dist.response == param:
+            if not isinstance(dist.shape, Identity) or not isinstance(dist.rate, Identity):
+                raise engine.PlanError("MH on a Gamma response needs Identity shape and rate parameters")
+            (v1, l1), (v2, l2) = _expand(plan, st[dist.shape.form], p_dim, n_rep), _expand(plan, st[dist.rate.form],
+                                                                                         p_dim, n_rep)
+            terms.append(K.term(K.TERM_GAMMA_RESPONSE, p1=v1, p1_len=l1, p2=v2, p2_len=l2))
+        elif isinstance(dist, Normal) and dist.response == param:
+            if not isinstance(dist.mean, Identity):
+                raise engine.PlanError("MH on a Normal response needs an Identity mean parameter")
+            mname, sname = engine._scalar_and_matrix(dist.precision)
+            P = engine.ensure_matrix(st, host_state, mname)
+            if P.kind == "tridiag":
+                raise engine.PlanError("MH with a tridiagonal Normal prior is not supported by the device path")
+            if n_rep != 1 and P.kind != "eye":
+                raise engine.PlanError("MH on a replicated Normal response supports identity precision matrices only")
+            v1, l1 = _expand(plan, st[dist.mean.form], p_dim, n_rep)
+            logdet = engine.logdet_of(plan, P)
+            lo = -np.inf if dist.domain_response_lower is None else float(np.max(dist.domain_response_lower))
+            hi = np.inf if dist.domain_response_upper is None else float(np.min(dist.domain_response_upper))
+            for lim in (dist.domain_response_lower, dist.domain_response_upper):
+                if lim is not None and np.ptp(np.asarray(lim, dtype=float)) != 0:
+                    raise engine.PlanError("element-wise different Normal domain limits are not supported yet")
+            terms.append(K.term(K.TERM_NORMAL_RESPONSE, mat_kind=engine._mat_kind(P), p1=v1, p1_len=l1, P=P.vec(),
+                                scalar=st[sname].vec() if sname else None,
+                                logdet=K.vec(logdet, 1 if P.per_chain else None) if logdet is not None else None,
+                                dom_lo=lo, dom_hi=hi))
+        elif (isinstance(dist, Normal) and isinstance(dist.mean, Identity) and dist.mean.form == param
+              and dist.response != param):
+            # theta is the (Identity) mean of another Normal response y: (y-theta)'Q(y-theta) is the response form with
+            # the roles of y and theta swapped; grad = Q(y-theta), H = Q  (location_scale.py:234-242 with grad = eye)
+            mname, sname = engine._scalar_and_matrix(dist.precision)
+            P = engine.ensure_matrix(st, host_state, mname)
+            if P.kind == "tridiag" or (n_rep != 1 and P.kind != "eye"):
+                raise engine.PlanError("MH through a Normal mean supports eye / diagonal / dense precisions, n_rep = 1")
+            yv, yl = _expand(plan, st[dist.response], p_dim, n_rep)
+            logdet = engine.logdet_of(plan, P)
+            terms.append(K.term(K.TERM_NORMAL_RESPONSE, mat_kind=engine._mat_kind(P), p1=yv, p1_len=yl, P=P.vec(),
+                                scalar=st[sname].vec() if sname else None,
+                                logdet=K.vec(logdet, 1 if P.per_chain else None) if logdet is not None else None))
+        elif isinstance(dist, Uniform) and dist.response == param:
+            lo = st.put(f"__uniform_lo[{param}]", np.broadcast_to(dist.domain_response_lower, (p_dim, 1)).copy())
+            hi = st.put(f"__uniform_hi[{param}]", np.broadcast_to(dist.domain_response_upper, (p_dim, 1)).copy())
+            (v1, l1), (v2, l2) = _expand(plan, lo, p_dim, n_rep), _expand(plan, hi, p_dim, n_rep)
+            terms.append(K.term(K.TERM_UNIFORM_RESPONSE, p1=v1, p1_len=l1, p2=v2, p2_len=l2))
+        else:
+            raise engine.PlanError(
+                f"the device MH path has no term for {type(dist).__name__}('{dist.response}') as a function of '{param}'")
+        labels.append(f"{type(dist).__name__}[{dist.response}]")
+    return K.mh_model(st.n_chains, n_elem, terms), labels
+
+
+# ============================================================================================== host-array calls
+def _one_chain_plan(state: dict, per_chain=()):
+    dev = K.init_device()
+    st = engine.DeviceState(1, dev, state, per_chain_names=set(per_chain))
+    return engine.Plan(st), st
+
+
+def log_p_host(dist, state: dict, by_observation: bool = False):
+    """dist.log_p(state) for a host dict state (n_chains = 1).  ref: distribution.py:40-54"""
+    from openmcmc_b200.model import Model
+
+    if by_observation:
+        raise engine.PlanError("log_p(by_observation=True) is only used by MixtureAllocation (SURVEY.md §8 f2: next)")
+    plan, st = _one_chain_plan(state)
+    out = plan.new(1)
+    plan.ops = []
+    engine.compile_log_post(plan, state, Model([dist]), out)
+    for _, fn in plan.ops:
+        fn()
+    torch.cuda.synchronize()
+    return float(out.item())
+
+
+def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, method: str):
+    """dist.grad_log_p(state, param): gradient of +log p with the shape of state[param] and Hessian of -log p (d x d).
+
+    ref: distribution.py:90-198 (finite differences), location_scale.py:190-250 (analytic Normal).
+    """
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination
+
+    if method not in ("fd", "analytic"):
+        raise ValueError("method must be 'fd' (the reference's finite differences) or 'analytic'")
+    plan, st = _one_chain_plan(state, per_chain=(param,))
+    shape = np.shape(state[param])
+    if isinstance(dist, Normal) and isinstance(dist.mean, LinearCombination) and param in dist.mean.form:
+        # linear-mean branch (location_scale.py:234-242): H = scalar * X'WX, g = scalar * X'W(y - X beta) from the fused
+        # regression pass
+        rl = engine.get_regression(plan, state, dist, param)
+        plan.ops = []
+        rl._emit_pass()
+        for _, fn in plan.ops:
+            fn()
+        p = rl.p
+        torch.cuda.synchronize()
+        rec = rl.stats[0].cpu().numpy()
+        tau = float(np.asarray(state[rl.scalar]).item()) if rl.scalar else 1.0
+        G = rec[: p * p].reshape(p, p)
+        beta = np.asarray(state[param], dtype=np.float64).reshape(p, 1)
+        grad = tau * (rec[p * p: p * p + p].reshape(p, 1) - G @ beta)
+        return (grad.reshape(shape), tau * G) if hessian_required else grad.reshape(shape)
+    model, _ = build_terms(plan, state, Model([dist]), param)
+    theta = st[param].data
+    n = model.n_elem
+    grad = plan.new(1, n)
+    hess = plan.new(1, n, n, fill=0.0) if hessian_required else None
+    K.mh_grad_hess(model, theta, 1 if method == "fd" else 0, grad, hess)
+    torch.cuda.synchronize()
+    g = grad.cpu().numpy().reshape(shape)
+    if hessian_required:
+        return g, hess.cpu().numpy().reshape(n, n)
+    return g
+
+
+def rvs_host(dist, state: dict, n: int = 1):
+    """Prior draws for parameters missing from the initial state (mcmc.py:78-80)."""
+    raise engine.PlanError(
+        f"{type(dist).__name__}.rvs on the device is not provided: give an initial value for '{dist.response}' in the "
+        "state (prior draws at start-up are outside the per-sweep hot path)")

@@ -206,3 +206,78 @@ def run_schedule(sweep: Graph, store, n_burn, n_iter, n_thin):
 def store_copy(src, dst, count, iter_counter, max_iter):
     check(lib().omc_store_copy(_ptr(src), _ptr(dst), int(count), _ptr(iter_counter), int(max_iter), stream_ptr()),
           "omc_store_copy")
+
+
+# ----------------------------------------------------------------------------- Metropolis-Hastings family
+TERM_POISSON_RATE, TERM_GAMMA_RESPONSE, TERM_NORMAL_RESPONSE, TERM_UNIFORM_RESPONSE = 1, 2, 3, 4
+
+
+def term(kind, mat_kind=0, p1_len=1, p2_len=1, data=None, p1=None, p2=None, P=None, scalar=None, logdet=None,
+         dom_lo=float("-inf"), dom_hi=float("inf")) -> "_cabi.Term":
+    """Build an omc_term_t; operands are omc_vec_t (see `vec`) or None."""
+    none = Vec(None, 0)
+    return _cabi.Term(int(kind), int(mat_kind), int(p1_len), int(p2_len), data or none, p1 or none, p2 or none,
+                      P or none, scalar or none, logdet or none, float(dom_lo), float(dom_hi))
+
+
+def mh_model(n_chains, n_elem, terms) -> "_cabi.MHModel":
+    if len(terms) > 4:
+        raise _cabi.OmcError("the device MH model supports at most 4 terms in the conditional model")
+    m = _cabi.MHModel()
+    m.n_chains, m.n_elem, m.n_terms = int(n_chains), int(n_elem), len(terms)
+    for i, t in enumerate(terms):
+        m.terms[i] = t
+    return m
+
+
+def mh_logp(model, theta, out):
+    check(lib().omc_mh_logp(C.byref(model), _ptr(theta), _ptr(out), stream_ptr()), "omc_mh_logp")
+
+
+def mh_grad_hess(model, theta, method, grad, hess=None):
+    """method: 0 analytic, 1 the reference's finite-difference stencil.  hess must be zero-initialised by the kernel."""
+    check(lib().omc_mh_grad_hess(C.byref(model), _ptr(theta), int(method), _ptr(grad), _ptr(hess), stream_ptr()),
+          "omc_mh_grad_hess")
+
+
+def random_walk(model, theta, p_dim, n_rep, loop, step, step_rows, step_cols, limits, rng_, debug_z=None, debug_u=None,
+                stride_z=0, stride_u=0, counters=None, probe=None):
+    a = _cabi.RandomWalkArgs()
+    a.model = model
+    a.theta = theta.data_ptr()
+    a.p_dim, a.n_rep, a.loop = int(p_dim), int(n_rep), int(loop)
+    a.step, a.step_rows, a.step_cols = step, int(step_rows), int(step_cols)
+    a.limits = limits.data_ptr() if limits is not None else None
+    a.rng = rng_
+    a.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    a.debug_u = debug_u.data_ptr() if debug_u is not None else None
+    a.debug_sweep_stride_z, a.debug_sweep_stride_u = int(stride_z), int(stride_u)
+    a.counters = counters.data_ptr() if counters is not None else None
+    a.probe = probe.data_ptr() if probe is not None else None
+    check(lib().omc_random_walk(C.byref(a), stream_ptr()), "omc_random_walk")
+
+
+def mmala(model, theta, step, method, rng_, debug_z=None, debug_u=None, stride_z=0, stride_u=0, counters=None,
+          status=None, probe_mu=None, probe_L=None, probe_prop=None, probe_scalars=None):
+    a = _cabi.MMalaArgs()
+    a.model = model
+    a.theta = theta.data_ptr()
+    a.step, a.method = float(step), int(method)
+    a.rng = rng_
+    a.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    a.debug_u = debug_u.data_ptr() if debug_u is not None else None
+    a.debug_sweep_stride_z, a.debug_sweep_stride_u = int(stride_z), int(stride_u)
+    for name, t in (("counters", counters), ("status", status), ("probe_mu", probe_mu), ("probe_L", probe_L),
+                    ("probe_prop", probe_prop), ("probe_scalars", probe_scalars)):
+        setattr(a, name, t.data_ptr() if t is not None else None)
+    check(lib().omc_mmala(C.byref(a), stream_ptr()), "omc_mmala")
+
+
+def truncnorm_rv(mean, scale, lower, upper, u, out):
+    check(lib().omc_truncnorm_rv(_ptr(mean), _ptr(scale), _ptr(lower), _ptr(upper), _ptr(u), out.numel(), _ptr(out),
+                                 stream_ptr()), "omc_truncnorm_rv")
+
+
+def truncnorm_logpdf(x, mean, scale, lower, upper, out):
+    check(lib().omc_truncnorm_logpdf(_ptr(x), _ptr(mean), _ptr(scale), _ptr(lower), _ptr(upper), out.numel(),
+                                     _ptr(out), stream_ptr()), "omc_truncnorm_logpdf")

@@ -155,6 +155,7 @@ class MCMC:
             buf = self._dev_store[s.param][: self.n_iter].cpu().numpy()      # [n_iter, C, size]
             d2h += buf.nbytes
             arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
+            arr = self._shape_store(s, arr, st[s.param])
             self.store[s.param] = arr[0] if C == 1 else arr
         lp = self._dev_logpost[: self.n_iter].cpu().numpy()
         d2h += lp.nbytes
@@ -173,6 +174,22 @@ class MCMC:
         self.timing["h2d_bytes"] = st.h2d_bytes
         self.timing["stored_iterations"] = n_done
         return self.store
+
+    @staticmethod
+    def _shape_store(sampler, arr, dev_arr):
+        """max_variable_size layouts of the reference's sample store (sampler.py:69-118): tuple -> the parameter's own
+        (rows, cols) shape padded with NaN; int -> flat, padded with NaN.  arr: [C, size, n_iter]."""
+        mvs = sampler.max_variable_size
+        if mvs is None:
+            return arr
+        C, size, n_iter = arr.shape
+        if isinstance(mvs, tuple):
+            out = np.full((C,) + tuple(mvs) + (n_iter,), np.nan)
+            out[:, : dev_arr.rows, : dev_arr.cols, :] = arr.reshape(C, dev_arr.rows, dev_arr.cols, n_iter)
+            return out
+        out = np.full((C, int(mvs), n_iter), np.nan)
+        out[:, :size, :] = arr
+        return out
 
     def run_mcmc(self):
         """ref: mcmc.py:87-115"""

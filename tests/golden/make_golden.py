@@ -124,6 +124,136 @@ def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "l
     return out
 
 
+# ----------------------------------------------------------------------------------------------- Metropolis-Hastings (C4 shape)
+def _run_ref(state, samplers, mdl, n_iter):
+    import openmcmc.mcmc as m
+
+    m.tqdm = lambda it: it
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter)
+    M.run_mcmc()
+    return M
+
+
+def poisson_gamma_state(p, seed, layout="col", vector_prior=False):
+    rng = np.random.default_rng(seed)
+    lam_true = rng.gamma(5.0, 1.0, size=p)
+    y = rng.poisson(lam_true).astype(float)
+    shape = (p, 1) if layout == "col" else (1, p)
+    a = np.full((p, 1), 2.0) + (rng.random((p, 1)) if vector_prior else 0.0)
+    b = np.full((p, 1), 0.5) + (rng.random((p, 1)) * 0.2 if vector_prior else 0.0)
+    if not vector_prior or layout != "col":
+        a, b = np.array([[2.0]]), np.array([[0.5]])
+    state = {"y": y.reshape(shape), "lam": (y + 1.0).reshape(shape) * 0.9, "a": a, "b": b}
+    mdl = Model([Poisson("y", rate="lam"), Gamma("lam", shape="a", rate="b")])
+    return state, mdl
+
+
+def mmala_poisson_gamma_case(p, seed, n_iter, step, vector_prior=False):
+    """mMALA on Poisson counts with a Gamma prior: the reference differentiates by finite differences."""
+    state, mdl = poisson_gamma_state(p, seed, vector_prior=vector_prior)
+    state0 = {k: np.array(v, copy=True) for k, v in state.items()}
+    g0, H0 = mdl.grad_log_p(state0, "lam", hessian_required=True)
+    lp0 = mdl.log_p(state0)
+    with Streams(seed + 10) as s:
+        smp = ManifoldMALA("lam", mdl, step=np.array([[step]]))
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"y": state0["y"], "lam0": state0["lam"], "a": state0["a"], "b": state0["b"], "step": step,
+            "grad0": g0, "hess0": H0, "logp0": lp0, "z": s.stack("z"), "u": s.stack("u").ravel(),
+            "store_lam": M.store["lam"], "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
+def mmala_normal_case(p, seed, n_iter, step):
+    """mMALA on a Normal prior + Normal 'observation' of theta: analytic derivatives in the reference, so the chain
+    must replay to 1e-9."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((p, p))
+    P = A @ A.T + p * np.eye(p)
+    state = {"theta": rng.standard_normal((p, 1)), "mu": rng.standard_normal((p, 1)), "P": P, "lam": 0.7,
+             "yobs": rng.standard_normal((p, 1)), "W": sparse.diags(rng.random(p) + 0.5, format="csc"), "tau": 2.5}
+    mdl = Model([Normal("theta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam")),
+                 Normal("yobs", mean="theta", precision=ScaledMatrix(matrix="W", scalar="tau"))])
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    g0, H0 = mdl.grad_log_p({**state0, "lam": np.array([[0.7]]), "tau": np.array([[2.5]])}, "theta", hessian_required=True)
+    with Streams(seed + 10) as s:
+        smp = ManifoldMALA("theta", mdl, step=np.array([[step]]))
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"theta0": state0["theta"], "mu": state0["mu"], "P": P, "lam": 0.7, "yobs": state0["yobs"],
+            "w": np.asarray(state0["W"].diagonal()), "tau": 2.5, "step": step, "grad0": g0, "hess0": np.asarray(H0),
+            "z": s.stack("z"), "u": s.stack("u").ravel(), "store_theta": M.store["theta"],
+            "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
+def rwl_case(p, seed, n_iter, step):
+    """RandomWalkLoop over a (1, p) parameter with truncated proposals on [0, inf) (the only working form)."""
+    state, mdl = poisson_gamma_state(p, seed, layout="row")
+    state0 = {k: np.array(v, copy=True) for k, v in state.items()}
+    with Streams(seed + 10) as s:
+        smp = RandomWalkLoop("lam", mdl, step=np.array([[step]]), domain_limits=np.array([[0.0, np.inf]]),
+                             max_variable_size=(1, p))   # a (1, p) parameter cannot be stored otherwise (sampler.py:107)
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"y": state0["y"], "lam0": state0["lam"], "a": state0["a"], "b": state0["b"], "step": step,
+            "limits": np.array([[0.0, np.inf]]), "tn_u": s.stack("tn_u").reshape(n_iter, p),
+            "u": s.stack("u").reshape(n_iter, p), "store_lam": M.store["lam"], "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
+def rw_case(p, seed, n_iter, truncated):
+    """RandomWalk (all elements at once): untruncated vector step, or truncated scalar."""
+    state, mdl = poisson_gamma_state(p, seed, vector_prior=not truncated)
+    state0 = {k: np.array(v, copy=True) for k, v in state.items()}
+    rng = np.random.default_rng(seed + 5)
+    step = np.array([[0.4]]) if truncated else 0.15 + 0.2 * rng.random((p, 1))
+    lim = np.array([[0.5, 12.0]]) if truncated else None
+    with Streams(seed + 10) as s:
+        smp = RandomWalk("lam", mdl, step=step, domain_limits=lim)
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"y": state0["y"], "lam0": state0["lam"], "a": state0["a"], "b": state0["b"], "step": step,
+            "limits": lim if truncated else np.zeros((0, 2)),
+            "z": (s.stack("tn_u") if truncated else s.stack("z")).reshape(n_iter, p), "u": s.stack("u").ravel(),
+            "store_lam": M.store["lam"], "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
+def truncnorm_grid(seed=0, n=400):
+    """scipy.stats.truncnorm ppf / logpdf on random and tail cases (what gmrf.py:269-318 calls)."""
+    rng = np.random.default_rng(seed)
+    mean = rng.normal(size=n) * 3
+    scale = rng.random(n) * 2 + 0.05
+    lower = mean + scale * rng.normal(size=n) * 3
+    upper = lower + rng.random(n) * 5 * scale + 1e-3
+    upper[rng.random(n) < 0.3] = np.inf
+    lower[rng.random(n) < 0.2] = -np.inf
+    # far tails on both sides
+    k = n // 8
+    lower[:k] = mean[:k] + scale[:k] * (4 + 10 * rng.random(k))
+    upper[:k] = np.inf
+    upper[k:2 * k] = mean[k:2 * k] - scale[k:2 * k] * (4 + 10 * rng.random(k))
+    lower[k:2 * k] = -np.inf
+    u = rng.random(n)
+    a, b = (lower - mean) / scale, (upper - mean) / scale
+    x = stats.truncnorm.ppf(u, a, b, loc=mean, scale=scale)
+    lp = gmrf.truncated_normal_log_pdf(x, mean, scale, lower, upper)
+    x_other = np.clip(x + scale * rng.normal(size=n), np.where(np.isfinite(lower), lower, x - 1), np.where(np.isfinite(upper), upper, x + 1))
+    lp_other = gmrf.truncated_normal_log_pdf(x_other, mean, scale, lower, upper)
+    return {"mean": mean, "scale": scale, "lower": lower, "upper": upper, "u": u, "x": x, "logpdf": lp,
+            "x_other": x_other, "logpdf_other": lp_other}
+
+
+def mh_cases():
+    return {
+        "mmala_poisson_gamma_p6": mmala_poisson_gamma_case(6, 11, 8, 0.5),
+        "mmala_poisson_gamma_p32_vec": mmala_poisson_gamma_case(32, 12, 3, 0.4, vector_prior=True),
+        "mmala_normal_p7": mmala_normal_case(7, 13, 8, 0.8),
+        "mmala_normal_p40": mmala_normal_case(40, 14, 4, 0.9),
+        "rwl_poisson_gamma_1x8": rwl_case(8, 15, 6, 0.5),
+        "rw_poisson_gamma_p6": rw_case(6, 16, 10, truncated=False),
+        "rw_trunc_scalar": rw_case(1, 17, 12, truncated=True),
+        "truncnorm_grid": truncnorm_grid(),
+    }
+
+
 def main():
     cases = {
         "regression_n50_p3": regression_case(50, 3, 0, 6),
@@ -132,6 +262,11 @@ def main():
                                                                prior="dense"),
         "regression_n1000_p64": regression_case(1000, 64, 3, 3),
     }
+    which = sys.argv[1:] or ["regression", "mh"]
+    if "regression" not in which:
+        cases = {}
+    if "mh" in which:
+        cases.update(mh_cases())
     for name, d in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, {k: np.shape(v) for k, v in d.items() if k.startswith("store")})

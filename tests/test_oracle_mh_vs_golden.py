@@ -1,0 +1,99 @@
+"""CPU: the numpy oracle of the Metropolis-Hastings family (oracle/mh.py) reproduces golden chains recorded from the
+live reference with its random streams replayed (tests/golden/make_golden.py)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gmrf, mh
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False))
+
+
+def poisson_gamma_terms(g):
+    return [mh.Term("poisson_rate", data=g["y"]), mh.Term("gamma_response", p1=g["a"], p2=g["b"])]
+
+
+def normal_terms(g):
+    p = g["theta0"].shape[0]
+    return [mh.Term("normal_response", p1=g["mu"], Q=g["lam"] * g["P"]),
+            mh.Term("normal_response", p1=g["yobs"], Q=g["tau"] * np.diag(g["w"]))], p
+
+
+@pytest.mark.parametrize("name", ["mmala_poisson_gamma_p6", "mmala_poisson_gamma_p32_vec"])
+def test_mmala_fd_chain(name):
+    """Finite-difference derivatives: the reference cannot reproduce its own FD Hessian beyond ~1e-6, so
+    the chain replay is held to 1e-5 and the deterministic probes to the measured FD self-noise."""
+    g = _load(name)
+    terms = poisson_gamma_terms(g)
+    g0, H0 = mh.grad_hess(terms, g["lam0"], "reference")
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-4, atol=1e-4)
+    ga, Ha = mh.grad_hess(terms, g["lam0"], "analytic")
+    np.testing.assert_allclose(ga, g["grad0"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(Ha, g["hess0"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(mh.log_p(terms, g["lam0"]), g["logp0"], rtol=1e-13)
+    theta = g["lam0"]
+    n_acc = 0
+    for it in range(g["store_lam"].shape[1]):
+        theta, info = mh.mmala_step(terms, theta, float(g["step"]), g["z"][it], g["u"][it], "reference")
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_lam"][:, it], rtol=1e-5)
+        np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-6)
+    assert n_acc == g["accept"][0]
+
+
+@pytest.mark.parametrize("name", ["mmala_normal_p7", "mmala_normal_p40"])
+def test_mmala_analytic_chain(name):
+    g = _load(name)
+    terms, p = normal_terms(g)
+    g0, H0 = mh.grad_hess(terms, g["theta0"], "reference")
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-12, atol=1e-13)
+    theta = g["theta0"]
+    for it in range(g["store_theta"].shape[1]):
+        theta, info = mh.mmala_step(terms, theta, float(g["step"]), g["z"][it], g["u"][it], "analytic")
+        np.testing.assert_allclose(theta.ravel(), g["store_theta"][:, it], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-11)
+
+
+def test_random_walk_loop_chain():
+    g = _load("rwl_poisson_gamma_1x8")
+    terms = poisson_gamma_terms(g)
+    theta = g["lam0"]
+    n_acc = 0
+    for it in range(g["store_lam"].shape[2]):
+        theta, infos = mh.random_walk_loop_sweep(terms, theta, g["step"], g["tn_u"][it], g["u"][it], g["limits"])
+        n_acc += sum(i["accepted"] for i in infos)
+        np.testing.assert_allclose(theta, g["store_lam"][:, :, it], rtol=1e-11)
+        np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-12)
+    assert n_acc == g["accept"][0] and g["accept"][1] == g["store_lam"].shape[2] * 8
+
+
+@pytest.mark.parametrize("name", ["rw_poisson_gamma_p6", "rw_trunc_scalar"])
+def test_random_walk_chain(name):
+    g = _load(name)
+    terms = poisson_gamma_terms(g)
+    theta = g["lam0"]
+    limits = g["limits"] if g["limits"].size else None
+    n_acc = 0
+    for it in range(g["store_lam"].shape[1]):
+        theta, info = mh.random_walk_step(terms, theta, g["step"], g["z"][it].reshape(theta.shape), g["u"][it], limits)
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_lam"][:, it], rtol=1e-11)
+    assert n_acc == g["accept"][0]
+
+
+def test_truncnorm_grid():
+    g = _load("truncnorm_grid")
+    x = gmrf.truncated_normal_rv(g["mean"], g["scale"], g["lower"], g["upper"], g["u"])
+    np.testing.assert_allclose(x, g["x"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(gmrf.truncated_normal_log_pdf(g["x"], g["mean"], g["scale"], g["lower"], g["upper"]),
+                               g["logpdf"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(gmrf.truncated_normal_log_pdf(g["x_other"], g["mean"], g["scale"], g["lower"],
+                                                             g["upper"]), g["logpdf_other"], rtol=1e-11, atol=1e-11)
