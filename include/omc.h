@@ -180,6 +180,47 @@ int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
 int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream);
 int omc_logdet_dense(const double* P, int n_mats, int n, double* out, void* stream);
 
+/* ------------------------------------------------------------------ temporal GMRF: tridiagonal NormalNormal (C3)
+ * Posterior precision Q = lambda*P + tau*W with P tridiagonal (main pd[n], off pe[n-1], shared by all chains; the RW1
+ * precision of gmrf.py:351-411) and W diagonal (w) or identity;  b = lambda*h + tau*W*y with h = P*mu0.
+ * omc_tridiag_nn_draw: x = L^-T (L^-1 b + z), L = natural-order Cholesky factor of Q, plus the quadratic forms of the
+ * new state  ss_prior = (x-mu0)'P(x-mu0),  ss_lik = (y-x)'W(y-x)  that the NormalGamma updates of lambda / tau need.
+ *   ref: sampler.py:154-207, gmrf.py:167-198 (sample_normal_canonical), :489-520 (sparse_cholesky, natural order, no
+ *        pivoting), :437-462 (cho_solve), :29-61 (sample_normal), sampler.py:275-284 (quadratic forms)
+ * Parallel exact scans (pivots: Moebius maps; solves: affine maps) with decoupled look-back replace the sequential
+ * recurrences; x == NULL runs the factorisation only (logdet / probes).  A pivot <= 0 sets OMC_STATUS_NOT_PD.
+ * workspace: omc_tridiag_workspace() bytes, zero-filled once (omc_tridiag_workspace_init or a zeroed allocation). */
+typedef struct {
+  int n_chains;
+  long long n;
+  const double* pd;      /* [n]   main diagonal of P (shared)                                  */
+  const double* pe;      /* [n-1] off diagonal of P (shared)                                   */
+  omc_vec_t lambda, tau; /* scalars (NULL => 1)                                                */
+  omc_vec_t w;           /* [n] diagonal of W (NULL => identity)                               */
+  omc_vec_t y;           /* [n] response                                                       */
+  omc_vec_t h;           /* [n] P*mu0 (NULL => 0)                                              */
+  omc_vec_t mu0;         /* [n] prior mean (NULL => 0), used by the prior quadratic form       */
+  double* x;             /* [n_chains][n] out (quadforms: in)                                  */
+  omc_rng_t rng;
+  const double* debug_z; /* injected N(0,1) [n_chains][n]; NULL => Philox                      */
+  long long debug_sweep_stride;
+  double* ss_prior;      /* optional out [n_chains]                                            */
+  double* ss_lik;        /* optional out [n_chains]                                            */
+  double* logdet;        /* optional out [n_chains]: log|Q| = sum log pivots                   */
+  double* probe_l;       /* optional out [n_chains][n]   diagonal of L                         */
+  double* probe_c;       /* optional out [n_chains][n-1] sub-diagonal of L                     */
+  int* status;           /* optional [n_chains]                                                */
+  void* workspace;
+} omc_tridiag_nn_t;
+int omc_tridiag_workspace(int n_chains, long long n, long long* bytes);
+int omc_tridiag_workspace_init(void* workspace, int n_chains, long long n, void* stream);
+int omc_tridiag_nn_draw(const omc_tridiag_nn_t* args, void* stream);
+/* quadratic forms of the CURRENT x only (no draw): ss_prior / ss_lik as above (ref: sampler.py:275-284) */
+int omc_tridiag_quadforms(const omc_tridiag_nn_t* args, void* stream);
+/* out = P v for the shared tridiagonal P and per-chain / shared v [n]  (prior-mean term P*mu0, sampler.py:181-183) */
+int omc_tridiag_matvec(const double* pd, const double* pe, omc_vec_t v, int n_chains, long long n, double* out,
+                       void* stream);
+
 /* ------------------------------------------------------------------ Metropolis-Hastings family (C4)
  * The conditional model of the sampled parameter theta (n_elem values per chain) is a sum of up to 4 terms.
  * ref: Model.log_p / grad_log_p (model.py:57-112) over the conditional model (sampler.py:53-55). */

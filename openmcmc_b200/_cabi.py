@@ -150,6 +150,18 @@ class MMalaArgs(C.Structure):
                 ("probe_scalars", C.c_void_p)]
 
 
+class TridiagNN(C.Structure):
+    """omc_tridiag_nn_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n", C.c_longlong), ("pd", C.c_void_p), ("pe", C.c_void_p), ("lam", Vec),
+                ("tau", Vec), ("w", Vec), ("y", Vec), ("h", Vec), ("mu0", Vec), ("x", C.c_void_p), ("rng", Rng),
+                ("debug_z", C.c_void_p), ("debug_sweep_stride", C.c_longlong), ("ss_prior", C.c_void_p),
+                ("ss_lik", C.c_void_p), ("logdet", C.c_void_p), ("probe_l", C.c_void_p), ("probe_c", C.c_void_p),
+                ("status", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"omc_tridiag_nn_t": TridiagNN}
+
 # name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
 PROTOTYPES = {
     "omc_abi_version": (C.c_int, []),
@@ -180,6 +192,11 @@ PROTOTYPES = {
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "omc_tridiag_workspace": (C.c_int, [C.c_int, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "omc_tridiag_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "omc_tridiag_nn_draw": (C.c_int, [C.POINTER(TridiagNN), C.c_void_p]),
+    "omc_tridiag_quadforms": (C.c_int, [C.POINTER(TridiagNN), C.c_void_p]),
+    "omc_tridiag_matvec": (C.c_int, [C.c_void_p, C.c_void_p, Vec, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_mh_logp": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_mh_grad_hess": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_random_walk": (C.c_int, [C.POINTER(RandomWalkArgs), C.c_void_p]),

@@ -38,6 +38,8 @@ class DevArray:
     cols: int
     kind: str = "dense"
     off: torch.Tensor = None
+    npos: int = None          # structured matrices: number of positive diagonal entries (sampler.py:283), host count
+    is_matrix: bool = False   # classified by put(as_matrix=True): structure is final, never re-uploaded
 
     @property
     def size(self):
@@ -66,16 +68,13 @@ def classify_matrix(m):
             np.add.at(d, m.row[nz], m.data[nz])
             return ("eye", None, None) if np.all(d == 1.0) else ("diag", d, None)
         if np.all(offs[nz] <= 1):
+            r, c, v = m.row[nz], m.col[nz], m.data[nz]
             d = np.zeros(n)
-            e_lo = np.zeros(n - 1)
-            e_up = np.zeros(n - 1)
-            for r, c, v in zip(m.row[nz], m.col[nz], m.data[nz]):
-                if r == c:
-                    d[r] += v
-                elif r == c + 1:
-                    e_lo[c] += v
-                else:
-                    e_up[r] += v
+            e_lo = np.zeros(max(n - 1, 0))
+            e_up = np.zeros(max(n - 1, 0))
+            np.add.at(d, r[r == c], v[r == c])
+            np.add.at(e_lo, c[r == c + 1], v[r == c + 1])
+            np.add.at(e_up, r[c == r + 1], v[c == r + 1])
             if not np.array_equal(e_lo, e_up):
                 raise NotImplementedError("non-symmetric tridiagonal precision matrix")
             return "tridiag", d, e_lo
@@ -107,16 +106,21 @@ class DeviceState:
         self.host_state = host_state if host_state is not None else {}
         self.per_chain_names = set(per_chain_names)
         self.h2d_bytes = 0
+        self._retired = []   # replaced entries stay alive: kernels hold raw device pointers (omc_vec_t) into them
 
     def _t(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
+        if not a.flags.writeable:
+            a = a.copy()
         self.h2d_bytes += a.nbytes
-        return torch.as_tensor(a).to(self.device, non_blocking=False)
+        return torch.from_numpy(a).to(self.device, non_blocking=False)
 
     def put(self, name, value, per_chain=None, as_matrix=False):
         """Upload one entry.  2-D host arrays are shared by all chains unless per_chain=True (then replicated);
         3-D arrays [C, rows, cols] are per-chain.  torch tensors are moved/bound as they are."""
         C = self.n_chains
+        if name in self.arrays:
+            self._retired.append(self.arrays[name])
         if per_chain is None:
             per_chain = name in self.per_chain_names
         if isinstance(value, torch.Tensor):
@@ -139,6 +143,7 @@ class DeviceState:
         if as_matrix or sparse.issparse(value):
             kind, main, off = classify_matrix(value)
             n = value.shape[0]
+            npos = n if kind == "eye" else int(np.sum((np.diag(main) if kind == "dense" else main) > 0))
             if kind == "eye":
                 arr = DevArray(None, False, n, n, "eye")
             elif kind == "diag":
@@ -147,6 +152,8 @@ class DeviceState:
                 arr = DevArray(self._t(main), False, n, n, "tridiag", self._t(off))
             else:
                 arr = DevArray(self._t(main), False, n, n, "dense")
+            arr.is_matrix = True
+            arr.npos = npos
             self.arrays[name] = arr
             return arr
         a = np.asarray(value, dtype=np.float64)
@@ -299,7 +306,7 @@ def _mat_kind(arr: DevArray):
 def ensure_matrix(state: DeviceState, host_state: dict, name: str) -> DevArray:
     """(Re-)upload `name` as a structured square matrix (eye/diag/tridiag/dense)."""
     arr = state.arrays.get(name)
-    if arr is not None and (arr.kind != "dense" or arr.rows != arr.cols or arr.per_chain):
+    if arr is not None and (arr.is_matrix or arr.kind != "dense" or arr.rows != arr.cols or arr.per_chain):
         return arr
     return state.put(name, host_state[name], as_matrix=True)
 
@@ -419,6 +426,18 @@ def get_quadratic_form(plan: Plan, host_state, nrm):
     Returns (ss_vec_fn, cnt_vec_fn, quantity_name).  ref: sampler.py:275-284.
     """
     st = plan.state
+    from openmcmc_b200 import gmrf_plan
+
+    fields = gmrf_plan._fields(plan)
+    if fields and (nrm.response in fields or gmrf_plan._quick_mean_name(nrm) in fields):
+        mname, _ = _scalar_and_matrix(nrm.precision)
+        P = ensure_matrix(st, host_state, mname)
+        if nrm.response in fields or gmrf_plan._identity_mean_of(plan, host_state, nrm) in fields:
+            key = nrm.response
+            cache = plan.__dict__.setdefault("_quadforms", {})
+            if key not in cache:
+                cache[key] = gmrf_plan.long_quadratic_form(plan, host_state, nrm, P, None, None)
+            return cache[key]
     if isinstance(nrm.mean, LinearCombination):
         params = list(nrm.mean.form.keys())
         rl = get_regression(plan, host_state, nrm, params[0])
@@ -436,9 +455,7 @@ def get_quadratic_form(plan: Plan, host_state, nrm):
     if x.cols != 1:
         raise PlanError("replicated responses (n_rep > 1) are not supported by the device quadratic form yet")
     if P.kind == "tridiag" or x.rows > 4096:
-        from openmcmc_b200 import gmrf_plan
-
-        out = gmrf_plan.long_quadratic_form(plan, nrm, P, x, mu)
+        out = gmrf_plan.long_quadratic_form(plan, host_state, nrm, P, x, mu)
         cache[key] = out
         return out
     ss, cnt = plan.new(C), plan.new(C)

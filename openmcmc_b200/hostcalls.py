@@ -36,6 +36,9 @@ def sample_once(sampler, state: dict, debug_draws: dict = None) -> dict:
     st = engine.DeviceState(1, dev, state, per_chain_names={sampler.param})
     plan = engine.Plan(st, seed=_default_seed)
     plan.sweep_counter.fill_(next(_call_counter))
+    from openmcmc_b200 import gmrf_plan
+
+    gmrf_plan.discover(plan, state, list(sampler.model.values()))
     sampler.compile(plan, state, debug_draws)
     _run_ops(plan.ops)
     torch.cuda.synchronize()

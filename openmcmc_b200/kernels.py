@@ -281,3 +281,43 @@ def truncnorm_rv(mean, scale, lower, upper, u, out):
 def truncnorm_logpdf(x, mean, scale, lower, upper, out):
     check(lib().omc_truncnorm_logpdf(_ptr(x), _ptr(mean), _ptr(scale), _ptr(lower), _ptr(upper), out.numel(),
                                      _ptr(out), stream_ptr()), "omc_truncnorm_logpdf")
+
+
+# ----------------------------------------------------------------------------- temporal GMRF (tridiagonal precision)
+def tridiag_workspace(n_chains, n) -> int:
+    b = C.c_longlong(0)
+    check(lib().omc_tridiag_workspace(int(n_chains), int(n), C.byref(b)), "omc_tridiag_workspace")
+    return b.value
+
+
+def tridiag_args(n_chains, n, pd, pe, workspace, lam=None, tau=None, w=None, y=None, h=None, mu0=None, x=None,
+                 rng_=None, debug_z=None, debug_sweep_stride=0, ss_prior=None, ss_lik=None, logdet=None, probe_l=None,
+                 probe_c=None, status=None) -> "_cabi.TridiagNN":
+    """Build an omc_tridiag_nn_t.  lam/tau/w/y/h/mu0 are omc_vec_t (see `vec`) or None; the rest tensors or None."""
+    none = Vec(None, 0)
+    a = _cabi.TridiagNN()
+    a.n_chains, a.n = int(n_chains), int(n)
+    a.pd, a.pe = pd.data_ptr(), (pe.data_ptr() if pe is not None and pe.numel() else None)
+    a.lam, a.tau, a.w, a.y, a.h, a.mu0 = lam or none, tau or none, w or none, y or none, h or none, mu0 or none
+    a.x = x.data_ptr() if x is not None else None
+    a.rng = rng_ if rng_ is not None else Rng(0, None, 0, 0)
+    a.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    a.debug_sweep_stride = int(debug_sweep_stride)
+    for name, t in (("ss_prior", ss_prior), ("ss_lik", ss_lik), ("logdet", logdet), ("probe_l", probe_l),
+                    ("probe_c", probe_c), ("status", status)):
+        setattr(a, name, t.data_ptr() if t is not None else None)
+    a.workspace = workspace.data_ptr()
+    return a
+
+
+def tridiag_nn_draw(args):
+    check(lib().omc_tridiag_nn_draw(C.byref(args), stream_ptr()), "omc_tridiag_nn_draw")
+
+
+def tridiag_quadforms(args):
+    check(lib().omc_tridiag_quadforms(C.byref(args), stream_ptr()), "omc_tridiag_quadforms")
+
+
+def tridiag_matvec(pd, pe, v, n_chains, n, out):
+    check(lib().omc_tridiag_matvec(_ptr(pd), _ptr(pe) if pe is not None and pe.numel() else None, v, int(n_chains),
+                                   int(n), _ptr(out), stream_ptr()), "omc_tridiag_matvec")

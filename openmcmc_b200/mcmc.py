@@ -72,6 +72,9 @@ class MCMC:
             plan = engine.Plan(st, seed=self.seed, chain_offset=self.chain_offset)
             plan.probes = {"enable": True} if self.probes else {}
             dd = self.debug_draws or {}
+            from openmcmc_b200 import gmrf_plan
+
+            gmrf_plan.discover(plan, self.state, list(self.model.values()))
             # pass A (dry): learn which derived quantities are valid at the end of a sweep
             plan.ops = []
             for s in self.samplers:

@@ -94,13 +94,15 @@ class NormalNormal(MCMCSampler):
         if len(liks) != 1 or not isinstance(liks[0], Normal):
             raise engine.PlanError("the device NormalNormal supports exactly one Normal likelihood term")
         lik = liks[0]
+        from openmcmc_b200 import gmrf_plan
+
+        if gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, lik):
+            return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, lik, debug_draws)
         if isinstance(lik.mean, LinearCombination):
             return self._compile_dense(plan, host_state, prior, lik, debug_draws)
-        if isinstance(lik.mean, Identity) and lik.mean.form == self.param:
-            from openmcmc_b200 import gmrf_plan
-
-            return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, lik, debug_draws)
-        raise engine.PlanError(f"NormalNormal: unsupported likelihood mean {type(lik.mean).__name__}")
+        raise engine.PlanError(
+            f"NormalNormal: a likelihood mean of type {type(lik.mean).__name__} with a small dense prior is not "
+            "supported by the device path (write it as LinearCombination({param: X}))")
 
     def _compile_dense(self, plan, host_state, prior, lik, debug_draws):
         st = plan.state

@@ -100,3 +100,53 @@ def gibbs_regression_sweep(X, y, state, z, g_tau, g_lam, P0=1.0, mu0=None, w=Non
             ss, cnt = quadform(P0, s["beta"], mu0)
             s["lambda"], _, _ = normal_gamma(s["a_lambda"], s["b_lambda"], ss, cnt, g_lam)
     return s
+
+
+def gmrf_normal_normal(pd, pe, w, y, mu0, lam, tau, z):
+    """NormalNormal.sample for a field with prior N(mu0, (lam P)^-1), P tridiagonal (main pd, off pe), and likelihood
+    y ~ N(b, (tau W)^-1), W = diag(w).
+
+    ref: sampler.py:154-207: Q = lam P + tau W (Identity-mean likelihood Hessian = Q_rsp, location_scale.py:234-242
+    with grad = I), b = lam P mu0 + tau W y; gmrf.sample_normal_canonical on the sparse branch (gmrf.py:167-198,
+    489-520).  Returns dict(x, mu, l, c, d, e, b).
+    """
+    pd, pe, w, y, mu0 = (np.asarray(v, dtype=np.float64).ravel() for v in (pd, pe, w, y, mu0))
+    d = lam * pd + tau * w
+    e = lam * pe
+    Pmu = pd * mu0
+    Pmu[:-1] += pe * mu0[1:]
+    Pmu[1:] += pe * mu0[:-1]
+    b = lam * Pmu + tau * w * y
+    x, mu, l, c = gmrf.tridiag_sample_canonical(d, e, b, np.asarray(z, dtype=np.float64).ravel())
+    return {"x": x, "mu": mu, "l": l, "c": c, "d": d, "e": e, "b": b}
+
+
+def gibbs_gmrf_sweep(pd, pe, w, y, mu0, state, z, g_lam, g_tau, order=("b", "lambda", "tau")):
+    """One sweep of the example-4 Gibbs sampler.  ref: examples/4_GMRF_smoother.ipynb; mcmc.py:98-100.
+    state: b (n,), lambda, tau, a_lam, b_lam, a_tau, b_tau.  cnt = number of positive diagonal entries (sampler.py:283)."""
+    s = dict(state)
+    pd, pe, w, y, mu0 = (np.asarray(v, dtype=np.float64).ravel() for v in (pd, pe, w, y, mu0))
+    for name in order:
+        if name == "b":
+            s["b"] = gmrf_normal_normal(pd, pe, w, y, mu0, s["lambda"], s["tau"], z)["x"]
+        elif name == "lambda":
+            ss = gmrf.tridiag_quadform(pd, pe, s["b"] - mu0)
+            s["lambda"], _, _ = normal_gamma(s["a_lam"], s["b_lam"], ss, float(np.sum(pd > 0)), g_lam)
+        elif name == "tau":
+            r = y - s["b"]
+            s["tau"], _, _ = normal_gamma(s["a_tau"], s["b_tau"], float(np.sum(w * r * r)), float(np.sum(w > 0)), g_tau)
+    return s
+
+
+def gmrf_log_post(pd, pe, w, y, mu0, s):
+    """Model.log_p of the example-4 model.  ref: model.py:57-70, location_scale.py:145-167 -> gmrf.py:321-348,
+    distribution.py:241-261.  log|lam P| = n log lam + log|P|."""
+    from oracle import dist
+
+    pd, pe, w, y, mu0 = (np.asarray(v, dtype=np.float64).ravel() for v in (pd, pe, w, y, mu0))
+    n = pd.size
+    r = y - s["b"]
+    lp = dist.normal_log_p_from_ss(n, s["tau"], float(np.sum(np.log(w))), float(np.sum(w * r * r)))
+    lp += dist.normal_log_p_from_ss(n, s["lambda"], gmrf.tridiag_logdet(pd, pe), gmrf.tridiag_quadform(pd, pe, s["b"] - mu0))
+    lp += dist.gamma_log_p(s["lambda"], s["a_lam"], s["b_lam"]) + dist.gamma_log_p(s["tau"], s["a_tau"], s["b_tau"])
+    return lp

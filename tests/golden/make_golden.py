@@ -254,6 +254,55 @@ def mh_cases():
     }
 
 
+# ----------------------------------------------------------------------------------------------- temporal GMRF (C3 shape)
+def gmrf_case(n, seed, n_iter, form="notebook", irregular=False, weighted=False, nonzero_mu=False,
+              order=("b", "lambda", "tau")):
+    """examples/4_GMRF_smoother: b ~ N(mu, (lambda P)^-1), y ~ N(b, (tau W)^-1), Gamma priors on lambda and tau.
+    form="notebook": mean="b" (the reference then runs DENSE linear algebra, SURVEY F4);
+    form="sparse"  : mean=LinearCombination({"b": "I"}) with sparse I (SuperLU path, gmrf.py:489-520)."""
+    rng = np.random.default_rng(seed)
+    s = np.arange(n) * (60.0 / 99.0)
+    if irregular:
+        s = np.cumsum(0.2 + rng.random(n))
+    P = gmrf.precision_irregular(s)
+    P[0, 0] = P[0, 0] + 0.001
+    P = sparse.csc_matrix(P)
+    truth = np.sin(s / 20) + 2 * np.cos(s / 12) + 2
+    y = truth + rng.standard_normal(n)
+    W = sparse.diags(rng.random(n) + 0.5, format="csc") if weighted else sparse.csc_matrix(np.eye(n))
+    mu = (0.5 * rng.standard_normal(n) + 2.0) if nonzero_mu else np.zeros(n)
+    mean = "b" if form == "notebook" else LinearCombination(form={"b": "I"})
+    mdl = Model([Normal("y", mean=mean, precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
+                 Normal("b", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+                 Gamma("lambda", shape="a_lam", rate="b_lam"),
+                 Gamma("tau", shape="a_tau", rate="b_tau")])
+    state = {"y": y.copy(), "b": y.copy(), "mu": mu, "lambda": 100, "P_lambda": P, "a_lam": 10, "b_lam": 1, "tau": 1,
+             "P_tau": W, "a_tau": 1, "b_tau": 1}
+    if form != "notebook":
+        state["I"] = sparse.identity(n, format="csc")
+    smap = {"b": NormalNormal("b", mdl), "lambda": NormalGamma("lambda", mdl), "tau": NormalGamma("tau", mdl)}
+    with Streams(seed + 1) as st:
+        M = _run_ref(state, [smap[k] for k in order], mdl, n_iter)
+    g = st.stack("g")
+    gorder = [k for k in order if k != "b"]
+    Pc = P.tocsc()
+    return {"s": s, "y": y, "mu": mu, "pd": Pc.diagonal(), "pe": Pc.diagonal(1), "w": np.asarray(W.diagonal()),
+            "form": form, "order": np.array(order), "z": st.stack("z"),
+            "g_" + gorder[0]: g[0::2, 0], "g_" + gorder[1]: g[1::2, 0],
+            "store_b": M.store["b"], "store_lambda": M.store["lambda"], "store_tau": M.store["tau"],
+            "store_log_post": M.store["log_post"]}
+
+
+def gmrf_cases():
+    return {
+        "gmrf_n100_notebook": gmrf_case(100, 21, 5),
+        "gmrf_n100_sparse": gmrf_case(100, 21, 5, form="sparse"),
+        "gmrf_n2500_sparse_weighted_mu": gmrf_case(2500, 22, 3, form="sparse", weighted=True, nonzero_mu=True,
+                                                   order=("tau", "b", "lambda")),
+        "gmrf_n5000_sparse_irregular": gmrf_case(5000, 23, 3, form="sparse", irregular=True),
+    }
+
+
 def main():
     cases = {
         "regression_n50_p3": regression_case(50, 3, 0, 6),
@@ -262,11 +311,13 @@ def main():
                                                                prior="dense"),
         "regression_n1000_p64": regression_case(1000, 64, 3, 3),
     }
-    which = sys.argv[1:] or ["regression", "mh"]
+    which = sys.argv[1:] or ["regression", "mh", "gmrf"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
         cases.update(mh_cases())
+    if "gmrf" in which:
+        cases.update(gmrf_cases())
     for name, d in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, {k: np.shape(v) for k, v in d.items() if k.startswith("store")})

@@ -87,3 +87,20 @@ def test_tridiag_restatement_matches_dense():
     np.testing.assert_allclose(x, x_ref.ravel(), rtol=1e-11)
     np.testing.assert_allclose(gmrf.tridiag_quadform(d, e, z), z @ Q @ z, rtol=1e-12)
     np.testing.assert_allclose(gmrf.tridiag_logdet(d, e), np.linalg.slogdet(Q)[1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "gmrf_*.npz"))))
+def test_gmrf_chain_replay(name):
+    """The tridiagonal restatement replays the reference's example-4 chains: the notebook form (dense LAPACK in the
+    reference) and the sparse form (SuperLU, natural order).  Tolerance = kappa * eps scale."""
+    g = _load(name)
+    order = tuple(str(s) for s in g["order"])
+    s = {"b": g["y"].copy(), "lambda": 100.0, "tau": 1.0, "a_lam": 10.0, "b_lam": 1.0, "a_tau": 1.0, "b_tau": 1.0}
+    for it in range(g["store_b"].shape[1]):
+        s = conjugate.gibbs_gmrf_sweep(g["pd"], g["pe"], g["w"], g["y"], g["mu"], s, g["z"][it], g["g_lambda"][it],
+                                       g["g_tau"][it], order)
+        np.testing.assert_allclose(s["b"], g["store_b"][:, it], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(s["lambda"], g["store_lambda"][0, it], rtol=1e-9)
+        np.testing.assert_allclose(s["tau"], g["store_tau"][0, it], rtol=1e-9)
+        np.testing.assert_allclose(conjugate.gmrf_log_post(g["pd"], g["pe"], g["w"], g["y"], g["mu"], s),
+                                   g["store_log_post"][it, 0], rtol=1e-10)
