@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py — chain-iterations/s of the openMCMC hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4a|c4b]
 
 A "step" is one sweep (every sampler once) over all chains of the workload; `value` = chain-iterations/s with the
 inputs resident in HBM; `e2e` = the same metric through the public API (`MCMC(...).run_mcmc()`) with HOST inputs, the
 host->device upload and the device->host sample download inside the timed region.  N > 1: one process per GPU
 (torchrun), chains sharded by rank (weak scaling, no data-path collective), time = max over ranks.
-`--impl reference` times the CPU path (numpy port of the reference sweep, oracle/cpu_bench.py) on the host cores.
+`--impl reference` times the CPU path (numpy/scipy port of the reference sweep, oracle/cpu_bench.py) on the host cores.
+
+Default workload = BASELINE.json configs[1] (batched Bayesian linear regression), the configuration the metric is
+quoted on that fits one GPU; the other configs are selectable for the per-config numbers in DESIGN.md / profiles/.
 """
 
 import argparse
@@ -27,9 +30,23 @@ UNIT = "chain-iterations/s"
 WORKLOADS = {
     # BASELINE.json configs[1]: batched Bayesian linear regression (the config the metric is quoted on; fits 1 GPU)
     "c2": dict(name="batched Bayesian linear regression: 4096 chains/GPU, n=10000, p=64, NormalNormal+NormalGamma Gibbs",
-               chains=4096, n=10000, p=64),
+               kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="reg_pass",
+               cpu=dict(chains_per_worker=8, sweeps=100), ref=dict(chains_per_worker=2, sweeps=5)),
     # BASELINE.json configs[0]: example-3 regression, single chain (latency bound)
-    "c1": dict(name="examples/3_linear_regression: 1 chain, n=1000, p=3", chains=1, n=1000, p=3),
+    "c1": dict(name="examples/3_linear_regression: 1 chain, n=1000, p=3", kind="regression", chains=1, n=1000, p=3,
+               thin=1, dominant="reg_pass", cpu=dict(chains_per_worker=1, sweeps=4000),
+               ref=dict(chains_per_worker=1, sweeps=500)),
+    # BASELINE.json configs[2]: example-4 GMRF smoother scaled up (sparse-enabled form)
+    "c3": dict(name="temporal GMRF smoother: 64 chains/GPU, n=1e6 grid points, tridiagonal NormalNormal + 2x NormalGamma",
+               kind="gmrf", chains=64, n=1_000_000, p=0, thin=10, dominant="tridiag_nn_draw",
+               cpu=dict(chains_per_worker=1, sweeps=3), ref=dict(chains_per_worker=1, sweeps=1)),
+    # BASELINE.json configs[3]: 65,536 chains x 32 params over 8 GPUs = 8192 chains per GPU
+    "c4a": dict(name="ManifoldMALA, Poisson counts + Gamma prior: 8192 chains/GPU x 32 params", kind="mh", chains=8192,
+                n=0, p=32, thin=1, dominant="mmala", cpu=dict(chains_per_worker=1, sweeps=30),
+                ref=dict(chains_per_worker=1, sweeps=4)),
+    "c4b": dict(name="RandomWalkLoop (truncated proposals), Poisson counts + Gamma prior: 8192 chains/GPU x (1,32) params",
+                kind="mh", chains=8192, n=0, p=32, thin=1, dominant="random_walk_loop",
+                cpu=dict(chains_per_worker=4, sweeps=300), ref=dict(chains_per_worker=2, sweeps=50)),
 }
 
 
@@ -41,39 +58,43 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=None, help="override chains per GPU (debug only)")
+    ap.add_argument("--n", type=int, default=None, help="override n (debug only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
 
+def config_of(args, wl):
+    return {"workload": wl["name"], "chains_per_gpu": args.chains or wl["chains"], "n_obs": args.n or wl["n"],
+            "p": wl["p"], "n_thin": wl["thin"]}
+
+
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
-def run_reference(args, wl):
+def run_reference(args, wl, key):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cpu_bench
 
     cores = os.cpu_count() or 1
-    # each step = a bounded sample of the workload: every core runs 2 chains for 5 sweeps
-    per_step = dict(chains_per_worker=2, sweeps=5)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_bench.run_parallel(workers=cores, n=wl["n"], p=wl["p"], **per_step)
-    vals, secs = [], 0.0
-    for k in range(args.steps if args.steps <= 8 else 8):
-        r = cpu_bench.run_parallel(workers=cores, n=wl["n"], p=wl["p"], seed=100 + k, **per_step)
-        vals.append(r["value"])
+    per_step = wl["ref"]   # each step = a bounded sample of the workload on every core
+    n, p = args.n or wl["n"], wl["p"]
+    for _ in range(1 if args.warmup > 0 else 0):
+        cpu_bench.run_parallel(workload=key, workers=cores, n=n, p=p, **per_step)
+    secs, steps_done = 0.0, 0
+    for k in range(min(args.steps, 8)):
+        r = cpu_bench.run_parallel(workload=key, workers=cores, n=n, p=p, seed=100 + k, **per_step)
         secs += r["seconds"]
-    steps_done = len(vals)
+        steps_done += 1
     total_its = cores * per_step["chains_per_worker"] * per_step["sweeps"] * steps_done
     value = total_its / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
-        "warmup": 1, "ms_per_step": secs / steps_done * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "chains_per_gpu": wl["chains"], "n_obs": wl["n"], "p": wl["p"]},
+        "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": secs / steps_done * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, wl),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps_done} steps x ({cores} workers x {per_step['chains_per_worker']} chains x "
-                                   f"{per_step['sweeps']} sweeps), numpy port of the reference sweep (oracle/), "
+                                   f"{per_step['sweeps']} sweeps), numpy/scipy port of the reference sweep (oracle/), "
                                    "1 BLAS thread per worker"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -93,7 +114,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -126,54 +147,158 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        # median over the samples taken under load (upper half of the observed clocks)
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------------------------- B200 arm
-def build_model():
+# --------------------------------------------------------------------------------------------- workloads (B200 arm)
+def build_regression(C, n, p, dev, rank, host):
+    import numpy as np
+    import torch
+    from scipy import sparse
+
     from openmcmc_b200.distribution.distribution import Gamma
     from openmcmc_b200.distribution.location_scale import Normal
     from openmcmc_b200.model import Model
     from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
     from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
 
+    # synthetic data generated on the device (X = [1, N(0,1)...], y = X beta* + 0.1 eps), seed = rank
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    X = torch.randn(C, n, p, dtype=torch.float64, device=dev, generator=gen)
+    X[:, :, 0] = 1.0
+    beta_true = torch.randn(C, p, 1, dtype=torch.float64, device=dev, generator=gen)
+    y = torch.bmm(X, beta_true) + 0.1 * torch.randn(C, n, 1, dtype=torch.float64, device=dev, generator=gen)
+    if host:
+        X, y = _pinned(X), _pinned(y)
     mdl = Model([
         Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
         Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
         Gamma("tau", shape="a_tau", rate="b_tau"),
         Gamma("lambda", shape="a_lambda", rate="b_lambda")])
     samplers = [NormalNormal("beta", mdl), NormalGamma("tau", mdl), NormalGamma("lambda", mdl)]
-    return mdl, samplers
+    state = {"y": y, "X": X, "beta": np.zeros((p, 1)), "P_tau": sparse.identity(n, format="csc"), "tau": 1.0,
+             "P_lambda": sparse.identity(p, format="csc"), "mu": np.zeros((p, 1)), "lambda": 0.01,
+             "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3, "b_lambda": 1e-3}
+    return mdl, samplers, state
 
 
-def make_state(X, y, n, p):
+def build_gmrf(C, n, p, dev, rank, host):
+    """regular grid s_i = i*(60/99), P = precision_irregular(s), P[0,0] += 1e-3,
+    y = sin(s/20) + 2 cos(s/12) + 2 + eps; lambda0 = 100, a_lam = 10, b_lam = 1, tau0 = 1, a_tau = b_tau = 1."""
+    import numpy as np
+    import torch
     from scipy import sparse
+
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    s = np.arange(n) * (60.0 / 99.0)
+    dr = 1.0 / np.diff(s)
+    pd = np.append(np.append(dr[0], dr[:-1] + dr[1:]), dr[-1])
+    pd[0] += 1e-3
+    P = sparse.diags([-dr, pd, -dr], offsets=[-1, 0, 1], format="csc")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    truth = torch.as_tensor(np.sin(s / 20) + 2 * np.cos(s / 12) + 2).to(dev)
+    y = truth.reshape(1, n, 1) + torch.randn(C, n, 1, dtype=torch.float64, device=dev, generator=gen)
+    if host:
+        y = _pinned(y)
+    mdl = Model([Normal("y", mean=LinearCombination(form={"b": "I"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
+                 Normal("b", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+                 Gamma("lambda", shape="a_lam", rate="b_lam"),
+                 Gamma("tau", shape="a_tau", rate="b_tau")])
+    samplers = [NormalNormal("b", mdl), NormalGamma("lambda", mdl), NormalGamma("tau", mdl)]
+    state = {"y": y, "b": y, "mu": np.zeros(n), "lambda": 100, "P_lambda": P, "a_lam": 10, "b_lam": 1, "tau": 1,
+             "P_tau": sparse.identity(n, format="csc"), "I": sparse.identity(n, format="csc"), "a_tau": 1, "b_tau": 1}
+    return mdl, samplers, state
+
+
+def build_mh(C, n, p, dev, rank, host, loop):
+    """y_j ~ Poisson(lambda*_j), lambda* ~ Gamma(5,1), prior Gamma(2, 0.5); step 0.5."""
     import numpy as np
+    import torch
 
-    return {"y": y, "X": X, "beta": np.zeros((p, 1)), "P_tau": sparse.identity(n, format="csc"), "tau": 1.0,
-            "P_lambda": sparse.identity(p, format="csc"), "mu": np.zeros((p, 1)), "lambda": 0.01,
-            "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3, "b_lambda": 1e-3}
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA, RandomWalkLoop
+
+    rng = np.random.default_rng(99 + rank)
+    shape = (C, 1, p) if loop else (C, p, 1)
+    y = rng.poisson(rng.gamma(5.0, 1.0, size=shape)).astype(np.float64)
+    yt = torch.as_tensor(y)
+    yt = yt.pin_memory() if host else yt.to(dev)
+    mdl = Model([Poisson("y", rate="lam"), Gamma("lam", shape="a", rate="b")])
+    if loop:
+        smp = RandomWalkLoop("lam", mdl, step=np.array([[0.5]]), domain_limits=np.array([[0.0, np.inf]]),
+                             max_variable_size=(1, p))
+    else:
+        smp = ManifoldMALA("lam", mdl, step=np.array([[0.5]]))
+    state = {"y": yt, "lam": torch.as_tensor(y + 1.0), "a": np.array([[2.0]]), "b": np.array([[0.5]])}
+    return mdl, [smp], state
 
 
-def run_b200(args, wl):
-    import numpy as np
+def _pinned(t):
+    import torch
+
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t)
+    return h
+
+
+def build(wl, C, n, dev, rank, host=False):
+    if wl["kind"] == "regression":
+        return build_regression(C, n, wl["p"], dev, rank, host)
+    if wl["kind"] == "gmrf":
+        return build_gmrf(C, n, wl["p"], dev, rank, host)
+    return build_mh(C, n, wl["p"], dev, rank, host, loop=wl["dominant"] == "random_walk_loop")
+
+
+def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak):
+    """Algorithmic work of the dominant op per launch over its measured duration."""
+    hbm_peak, hbm_src = peaks
+    sec = op_ms * 1e-3
+    if wl["kind"] == "regression":
+        flops = C * (n * p * (p + 1) + 4 * n * p)       # SYRK + X'y + residual per chain (SURVEY §8d)
+        byts = C * 8 * n * (p + 1)
+        return {"bound": "tensor", "kernel": "reg_pass_kernel (FP64 DMMA SYRK + X'y + rss)",
+                "achieved": flops / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flops / sec / 1e12 / fp64_peak if fp64_peak else None,
+                "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
+                "hbm": {"achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
+                        "peak_source": hbm_src}}
+    if wl["kind"] == "gmrf":
+        byts = C * 32 * n                                 # read y, P diag + off, write b (SURVEY §8d)
+        return {"bound": "hbm", "kernel": "omc_tridiag_nn_draw (tridiag_forward_kernel + tridiag_backward_kernel)",
+                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
+                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+    byts = C * 32 * p                                     # read theta, y; write theta, sample (SURVEY §8d)
+    return {"bound": "hbm", "kernel": f"{wl['dominant']}_kernel (latency / FP64-ALU bound: 1 KB per chain-iteration)",
+            "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
+            "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+
+
+def run_b200(args, wl, key):
     import torch
     import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    C, n, p, thin = args.chains or wl["chains"], args.n or wl["n"], wl["p"], wl["thin"]
+    thin = max(1, min(thin, args.steps))
     # CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import cpu_bench
 
-        cpu_baseline = cpu_bench.run_parallel(workers=os.cpu_count() or 1, chains_per_worker=8, sweeps=100,
-                                              n=wl["n"], p=wl["p"])
-        cpu_baseline = {"value": cpu_baseline["value"], "unit": UNIT, "cores": cpu_baseline["cores"], "kind": "port",
-                        "sample": cpu_baseline["sample"]}
+        r = cpu_bench.run_parallel(workload=key, workers=os.cpu_count() or 1, n=n, p=p, **wl["cpu"])
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -181,18 +306,11 @@ def run_b200(args, wl):
     from openmcmc_b200.mcmc import MCMC
 
     K.init_device(local)
-    C, n, p = args.chains or wl["chains"], wl["n"], wl["p"]
     dev = torch.device("cuda", local)
-    # synthetic data generated on the device (X = [1, N(0,1)...], y = X beta* + 0.1 eps), seed = chain id
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    X = torch.randn(C, n, p, dtype=torch.float64, device=dev, generator=gen)
-    X[:, :, 0] = 1.0
-    beta_true = torch.randn(C, p, 1, dtype=torch.float64, device=dev, generator=gen)
-    y = torch.bmm(X, beta_true) + 0.1 * torch.randn(C, n, 1, dtype=torch.float64, device=dev, generator=gen)
-    mdl, samplers = build_model()
-    M = MCMC(make_state(X, y, n, p), samplers, model=mdl, n_burn=0, n_iter=args.steps, n_chains=C, seed=7,
-             device=local, chain_offset=rank * C)
+    mdl, samplers, state = build(wl, C, n, dev, rank)
+    n_iter = max(args.steps // thin, 1)
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7, device=local,
+             chain_offset=rank * C)
     M.prepare()
     launches_per_sweep = M.launches_per_sweep()
     store_launches = M._store_graph.num_kernels()
@@ -203,7 +321,7 @@ def run_b200(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # warm-up (untimed), then exactly K timed sweeps: every timed step = sweep graph + store graph (samples + log_post)
+    # warm-up (untimed), then exactly K timed sweeps; every n_thin-th sweep is followed by the store graph
     M.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
     barrier()
     clocks = ClockSampler(local)
@@ -212,43 +330,42 @@ def run_b200(args, wl):
     e1 = torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(M.stream):
         e0.record()
-    M.run_device(n_burn=0, n_iter=args.steps, n_thin=1)
+    M.run_device(n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter, n_thin=thin)
     with torch.cuda.stream(M.stream):
         e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # dominant kernel alone, same buffers, on the engine's stream (events on that stream)
-    rl = M.plan._regressions["y"]
+    # dominant op alone: the very launch closure of the sweep plan, on the engine's stream, events on that stream
+    op = next(fn for label, fn in M._ops["sweep"] if label.startswith(wl["dominant"]))
     reps = 10
     with torch.cuda.stream(M.stream):
         k0 = torch.cuda.Event(enable_timing=True)
         k1 = torch.cuda.Event(enable_timing=True)
-        K.reg_pass(rl.X.data, rl.y.data, None, rl.beta.data, rl.stats, rl.work, C, n, p)
+        op()
         k0.record()
         for _ in range(reps):
-            K.reg_pass(rl.X.data, rl.y.data, None, rl.beta.data, rl.stats, rl.work, C, n, p)
+            op()
         k1.record()
     barrier()
-    pass_ms = k0.elapsed_time(k1) / reps
+    op_ms = k0.elapsed_time(k1) / reps
     clk = clocks.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     M.collect()
-    status_bad = int((M.status != 0).sum())
+    status_bad = int(((M.status & 3) != 0).sum())
+    accept = {s.param: s.accept_rate.get_acceptance_rate() for s in samplers if hasattr(s, "accept_rate")}
     value = C * world * args.steps / (ms_max * 1e-3)
 
-    # FP64 peak (cuBLAS DGEMM) measured live: the roofline denominator for the DMMA SYRK pass
-    fp64_peak = None
-    hbm_peak = None
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        hbm_peak = float(peaks["hbm_gbs"])
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        peaks = (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]),
+                 "MEASURED_PEAKS.json hbm_gbs (of measured)")
     except Exception:
-        hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
-    if rank == 0:
+        peaks = (6650.0, "fallback 6.65 TB/s (of fallback)")
+    fp64_peak = None
+    if rank == 0 and wl["kind"] == "regression":
+        # FP64 peak (cuBLAS DGEMM) measured live: the roofline denominator for the DMMA SYRK pass
         a = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
         b = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
         best = 0.0
@@ -266,18 +383,19 @@ def run_b200(args, wl):
     # ---- e2e: public API with HOST (pinned) inputs, upload + K sweeps + sample download inside the timed region
     e2e = None
     if not args.no_e2e:
-        del M
-        Xh = torch.empty(X.shape, dtype=torch.float64, pin_memory=True)
-        yh = torch.empty(y.shape, dtype=torch.float64, pin_memory=True)
-        Xh.copy_(X)
-        yh.copy_(y)
-        del X, y, rl
+        del M, op, state
+        torch.cuda.empty_cache()
+        mdl, samplers2, hstate = build(wl, C, n, dev, rank, host=True)
         torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
-        M2 = MCMC(make_state(Xh, yh, n, p), samplers, model=mdl, n_burn=0, n_iter=args.steps, n_chains=C, seed=7,
-                  device=local, chain_offset=rank * C)
-        M2.run_mcmc()
+        M2 = MCMC(hstate, samplers2, model=mdl, n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter,
+                  n_thin=thin, n_chains=C, seed=7, device=local, chain_offset=rank * C)
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            M2.run_mcmc()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -286,33 +404,26 @@ def run_b200(args, wl):
         dt = float(tt.item())
         e2e = {"value": C * world * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": M2.timing["h2d_bytes"] / args.steps,
-               "d2h_bytes_per_step": M2.timing["d2h_bytes"] / args.steps,
-               "seconds": dt, "note": "MCMC(...).run_mcmc() with pinned host X,y: upload + compile + graph capture + "
-                                      f"{args.steps} sweeps + download of all stored samples"}
+               "d2h_bytes_per_step": M2.timing["d2h_bytes"] / args.steps, "seconds": dt,
+               "note": "MCMC(...).run_mcmc() with pinned host inputs: upload + plan compile + graph capture + "
+                       f"{args.steps} sweeps + download of all stored samples"}
 
     if rank == 0:
-        flops_alg = n * p * (p + 1) + 4 * n * p            # SYRK + X'y + residual per chain-iteration
-        bytes_alg = 8 * n * (p + 1)
-        roof = {"bound": "tensor", "kernel": "reg_pass_kernel (FP64 DMMA SYRK + X'y + rss)",
-                "achieved": C * flops_alg / (pass_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (C * flops_alg / (pass_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
-                "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                "traffic": None, "kernel_ms": pass_ms, "share_of_step": pass_ms / (ms_max / args.steps),
-                "hbm": {"achieved": C * bytes_alg / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": C * bytes_alg / (pass_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+        roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak)
         try:
-            roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "reg_pass_traffic.json")))["dram_bytes_per_launch"]
+            roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", f"{key}_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
+        cfg = config_of(args, wl)
+        cfg.update({"l2": "per-GPU inputs are far larger than the 126 MB L2 (c2: 21 GB of X, c3: 512 MB of y + 1 GB of "
+                          "scratch); c1/c4 working sets are L2-resident by nature of the workload",
+                    "per_step": "1 sweep = every sampler once over all chains; every n_thin-th sweep also stores the "
+                                "samples and log_post", "chains_failed": status_bad, "accept": accept})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "chains_per_gpu": C, "n_obs": n, "p": p,
-                       "l2": "inputs (21.3 GB of X per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "per_step": "1 sweep = NormalNormal(beta) + fused X pass + NormalGamma(tau) + NormalGamma(lambda)"
-                                   " + store of beta/tau/lambda/log_post", "chains_failed": status_bad},
-            "clocks": clk, "e2e": e2e, "gpu_launches": (launches_per_sweep + store_launches) * args.steps,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches_per_sweep * args.steps + store_launches * n_iter,
             "roofline": roof, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -324,9 +435,9 @@ def main():
     args = parse()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, wl, args.workload)
     else:
-        run_b200(args, wl)
+        run_b200(args, wl, args.workload)
 
 
 if __name__ == "__main__":

@@ -23,8 +23,9 @@ extern "C" {
 
 #define OMC_ABI_VERSION 1
 #define OMC_STATUS_NOT_PD 1          /* Cholesky pivot <= 0 (reference: LinAlgError from np.linalg.cholesky) */
-#define OMC_STATUS_NAN 2             /* NaN/inf in log-density or gradient (reference F6: crash)               */
-#define OMC_STATUS_OUT_OF_SUPPORT 4  /* proposal outside the support                                          */
+#define OMC_STATUS_NAN 2             /* NaN/inf in the log-density or gradient of the CURRENT state            */
+#define OMC_STATUS_OUT_OF_SUPPORT 4  /* a PROPOSAL was invalid (outside the support / non-PD Hessian) and was
+                                        rejected; informational (the reference crashes here)         */
 
 typedef struct {
   const double* ptr;

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(MM_THREADS) mmala_kernel(omc_mmala_t a) {
     __syncthreads();
     // reverse proposal parameters at the proposed point
     const bool ok2 = mmala_params(a, chain, prop, Hm, ld, g, mu, scratch);
-    if (!ok2) { status |= OMC_STATUS_NAN; ok = false; }
+    if (!ok2) { status |= OMC_STATUS_OUT_OF_SUPPORT; ok = false; }  // invalid PROPOSAL: reject, chain stays healthy
     else if (warp == 0) {
       const double lqr = mmala_log_density_warp(Hm, n, ld, cur, mu);
       if (lane == 0) sc[3] = lqr;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(MM_THREADS) mmala_kernel(omc_mmala_t a) {
     }
     log_accept = sc[1] + sc[3] - (sc[0] + sc[2]);
     accept = log(u) < log_accept;
-    if (isnan(log_accept)) status |= OMC_STATUS_NAN;
+    if (isnan(log_accept)) status |= isnan(sc[0]) ? OMC_STATUS_NAN : OMC_STATUS_OUT_OF_SUPPORT;
   }
   if (accept)
     for (int i = tid; i < n; i += MM_THREADS) gth[i] = prop[i];

@@ -127,6 +127,8 @@ class DeviceState:
             if not value.is_cuda:
                 self.h2d_bytes += value.numel() * value.element_size()
             t = value.to(self.device, F64, non_blocking=True)
+            if per_chain and t.data_ptr() == value.data_ptr():
+                t = t.clone()   # sampled entries are written by the kernels: never alias the caller's tensor
             if t.dim() == 3:
                 if t.shape[0] != C:
                     raise ValueError(f"state['{name}'] has leading dimension {t.shape[0]} but n_chains={C}")

@@ -19,9 +19,21 @@ def _worker(workload, chains, sweeps, seed, n, p):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     import numpy as np
 
+    rng = np.random.default_rng(seed)
+    if workload in ("c1", "c2"):
+        return _worker_regression(rng, chains, sweeps, n, p)
+    if workload == "c3":
+        return _worker_gmrf(rng, chains, sweeps, n)
+    if workload in ("c4a", "c4b"):
+        return _worker_mh(rng, chains, sweeps, p, workload)
+    raise ValueError(workload)
+
+
+def _worker_regression(rng, chains, sweeps, n, p):
+    import numpy as np
+
     from oracle import conjugate, dist
 
-    rng = np.random.default_rng(seed)
     data = []
     for _ in range(chains):
         X = rng.standard_normal((n, p))
@@ -40,6 +52,64 @@ def _worker(workload, chains, sweeps, seed, n, p):
             ssb, _ = conjugate.quadform(1.0, st["beta"], None)
             _ = (dist.normal_log_p_from_ss(n, st["tau"], 0.0, rss) + dist.normal_log_p_from_ss(p, st["lambda"], 0.0, ssb)
                  + dist.gamma_log_p(st["tau"], 1e-3, 1e-3) + dist.gamma_log_p(st["lambda"], 1e-3, 1e-3))
+    return time.perf_counter() - t0
+
+
+def _worker_gmrf(rng, chains, sweeps, n):
+    """Example-4 sweep with the reference's own sparse call stack (gmrf.py:167-198 sparse branch: one splu with natural
+    ordering and no pivoting + three spsolve), the NormalGamma updates and the per-iteration log_post, which
+    re-factorises both Normal precisions (gmrf.py:339)."""
+    import numpy as np
+
+    from oracle import conjugate, dist, gmrf
+
+    s = np.arange(n) * (60.0 / 99.0)
+    pd, pe = gmrf.precision_irregular_diagonals(s)
+    pd = pd.copy()
+    pd[0] += 1e-3
+    truth = np.sin(s / 20) + 2 * np.cos(s / 12) + 2
+    data = [(truth + rng.standard_normal(n), {"lambda": 100.0, "tau": 1.0}) for _ in range(chains)]
+    t0 = time.perf_counter()
+    for y, st in data:
+        for _ in range(sweeps):
+            x, L = gmrf.sparse_sample_normal_canonical(st["lambda"] * pd + st["tau"], st["lambda"] * pe, st["tau"] * y,
+                                                       rng.standard_normal(n))
+            ssp = gmrf.tridiag_quadform(pd, pe, x)
+            st["lambda"], _, _ = conjugate.normal_gamma(10.0, 1.0, ssp, float(n), rng.standard_gamma(10.0 + n / 2))
+            r = y - x
+            ssl = float(r @ r)
+            st["tau"], _, _ = conjugate.normal_gamma(1.0, 1.0, ssl, float(n), rng.standard_gamma(1.0 + n / 2))
+            # log_post: Normal.log_p factorises lambda*P and tau*I again (location_scale.py:145-167 -> gmrf.py:321-348)
+            ld_p = gmrf.sparse_logdet(st["lambda"] * pd, st["lambda"] * pe)
+            ld_w = gmrf.sparse_logdet(np.full(n, st["tau"]), np.zeros(n - 1))
+            _ = (0.5 * (ld_p - n * np.log(2 * np.pi) - st["lambda"] * ssp) + 0.5 * (ld_w - n * np.log(2 * np.pi) - st["tau"] * ssl)
+                 + dist.gamma_log_p(st["lambda"], 10.0, 1.0) + dist.gamma_log_p(st["tau"], 1.0, 1.0))
+    return time.perf_counter() - t0
+
+
+def _worker_mh(rng, chains, sweeps, p, workload):
+    """C4: Poisson counts with a Gamma(2, 0.5) prior; c4a ManifoldMALA with the reference's finite-difference
+    derivatives (distribution.py:124-198), c4b RandomWalkLoop over a (1, p) parameter with truncated proposals."""
+    import numpy as np
+
+    from oracle import mh
+
+    data = []
+    for _ in range(chains):
+        y = rng.poisson(rng.gamma(5.0, 1.0, size=p)).astype(float)
+        shape = (p, 1) if workload == "c4a" else (1, p)
+        terms = [mh.Term("poisson_rate", data=y.reshape(shape)), mh.Term("gamma_response", p1=np.array([[2.0]]),
+                                                                        p2=np.array([[0.5]]))]
+        data.append((terms, (y + 1.0).reshape(shape)))
+    t0 = time.perf_counter()
+    for terms, theta in data:
+        for _ in range(sweeps):
+            if workload == "c4a":
+                theta, _ = mh.mmala_step(terms, theta, 0.5, rng.standard_normal(p), rng.random(), "reference")
+            else:
+                theta, _ = mh.random_walk_loop_sweep(terms, theta, np.array([[0.5]]), rng.random((p, 1)), rng.random(p),
+                                                     np.array([[0.0, np.inf]]))
+            _ = mh.log_p(terms, theta)   # per-iteration log_post (mcmc.py:108)
     return time.perf_counter() - t0
 
 
@@ -65,8 +135,8 @@ def run_parallel(workload="c2", workers=None, chains_per_worker=2, sweeps=3, n=1
     # throughput of the timed loops themselves (process start-up and data generation excluded)
     value = total / max(inner)
     return {"value": value, "unit": "chain-iterations/s", "cores": workers, "seconds": max(inner), "wall": wall,
-            "sample": f"{workers} workers x {chains_per_worker} chains x {sweeps} sweeps of n={n}, p={p} "
-                      f"(numpy port of the reference sweep incl. per-iteration log_post), 1 BLAS thread per worker"}
+            "sample": f"{workers} workers x {chains_per_worker} chains x {sweeps} sweeps of {workload} (n={n}, p={p}; "
+                      f"numpy/scipy port of the reference sweep incl. per-iteration log_post), 1 BLAS thread per worker"}
 
 
 def main():

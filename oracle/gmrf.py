@@ -146,6 +146,41 @@ def tridiag_logdet(d, e):
     return float(2.0 * np.sum(np.log(fac[0])))
 
 
+# ----------------------------------------------------------------------------- the reference's sparse call stack
+def _tridiag_csc(d, e):
+    from scipy import sparse
+
+    return sparse.diags([e, d, e], offsets=[-1, 0, 1], format="csc")
+
+
+def sparse_cholesky_scipy(Q):
+    """ref: gmrf.py:489-520 — splu(diag_pivot_thresh=0, natural ordering, no row permutation) -> L * sqrt(diag U)."""
+    from scipy import sparse
+    from scipy.sparse import linalg as sla
+
+    lu = sla.splu(Q, diag_pivot_thresh=0, options={"RowPerm": False, "ColPerm": False})
+    return lu.L.dot(sparse.diags(lu.U.diagonal() ** 0.5)).tocsc()
+
+
+def sparse_sample_normal_canonical(d, e, b, z):
+    """Rue & Held Alg 2.5 on the sparse branch exactly as the reference runs it: one splu + two spsolve for the mean
+    (gmrf.py:459-460) + one spsolve for the draw (gmrf.py:432).  Used by the CPU timing leg (bench.py); the tridiagonal
+    restatement above is what the parity tests use.  Returns (x, L)."""
+    from scipy.sparse import linalg as sla
+
+    Q = _tridiag_csc(d, e)
+    L = sparse_cholesky_scipy(Q)
+    w = sla.spsolve(L, b)
+    mu = sla.spsolve(L.T.tocsc(), w)
+    return mu + sla.spsolve(L.T.tocsc(), z), L
+
+
+def sparse_logdet(d, e):
+    """log|Q| the way Normal.log_p gets it: a fresh sparse Cholesky per call (gmrf.py:339-342)."""
+    L = sparse_cholesky_scipy(_tridiag_csc(d, e))
+    return float(2.0 * np.sum(np.log(L.diagonal())))
+
+
 # ----------------------------------------------------------------------------- truncated normal (scipy.stats.truncnorm)
 # ref: gmrf.py:269-318 standardise (a, b) = ((lower-mean)/scale, (upper-mean)/scale) and call
 # scipy.stats.truncnorm.rvs / logpdf.  scipy (_continuous_distns.py, truncnorm_gen) draws by inverse CDF of ONE
