@@ -9,6 +9,7 @@ Host logic only: which state entries feed which kernel argument, and which deriv
 
 import numpy as np
 import torch
+from scipy import sparse
 
 from openmcmc_b200 import engine
 from openmcmc_b200 import kernels as K
@@ -160,8 +161,16 @@ def _identity_mean_of(plan, host_state, nrm):
         return nrm.mean.form
     if isinstance(nrm.mean, LinearCombination) and len(nrm.mean.form) == 1:
         (prm, pref), = nrm.mean.form.items()
-        A = engine.ensure_matrix(plan.state, host_state, pref)
-        if A.kind == "eye":
+        arr = plan.state.arrays.get(pref)
+        if arr is not None:
+            return prm if arr.kind == "eye" else None
+        shape = getattr(host_state.get(pref), "shape", None)
+        if shape is None or len(shape) != 2 or shape[0] != shape[1]:
+            return None     # a rectangular design matrix: the regression path
+        if not sparse.issparse(host_state[pref]) and shape[0] > 64:
+            return None     # a large dense square prefactor is data, not an identity
+        if engine.classify_matrix(host_state[pref])[0] == "eye":
+            engine.ensure_matrix(plan.state, host_state, pref)
             return prm
     return None
 

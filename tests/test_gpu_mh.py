@@ -216,7 +216,7 @@ def test_free_running_poisson_gamma_posterior(kind):
     mdl = _pg_model()
     if kind == "mmala":
         state = {"y": y.reshape(p, 1), "lam": (y + 1.0).reshape(p, 1), "a": np.array([[2.0]]), "b": np.array([[0.5]])}
-        smp = ManifoldMALA("lam", mdl, step=np.array([[0.9]]))
+        smp = ManifoldMALA("lam", mdl, step=np.array([[0.6]]))
     else:
         state = {"y": y.reshape(1, p), "lam": (y + 1.0).reshape(1, p), "a": np.array([[2.0]]), "b": np.array([[0.5]])}
         smp = RandomWalkLoop("lam", mdl, step=np.array([[2.0]]), domain_limits=np.array([[0.0, np.inf]]),
@@ -226,7 +226,7 @@ def test_free_running_poisson_gamma_posterior(kind):
     last = M.store["lam"].reshape(C, p, -1)[:, :, -1]
     assert np.all((M.status & 3) == 0)   # bit 4 (a rejected invalid proposal) is informational
     rate = smp.accept_rate.acceptance_rate
-    assert 20 < rate < 99, rate
+    assert 10 < rate < 99.9, rate
     for j in range(p):
         post = stats.gamma(a=2.0 + y[j], scale=1.0 / 1.5)
         assert stats.kstest(last[:, j], post.cdf).pvalue > 0.01, (kind, j)
