@@ -266,7 +266,7 @@ class Plan:
             if a.size % (C * size) != 0:
                 raise ValueError(f"injected draws of size {a.size} do not match n_chains={C} x size={size}")
             a = a.reshape(-1, C, size)
-        t = torch.as_tensor(np.ascontiguousarray(a)).to(self.state.device)
+        t = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True)).to(self.state.device)
         self.keep.append(t)
         return t, (C * size if a.shape[0] > 1 else 0)
 
