@@ -125,6 +125,7 @@ class MCMC:
                     done.update(q.siblings)
             self.plan = plan
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
+            self._warm_up(plan, st, sampled)
             self._sweep_graph = K.Graph.capture(lambda: [fn() for _, fn in sweep_ops])
             self._store_graph = K.Graph.capture(lambda: [fn() for _, fn in store_ops])
             for _, fn in prologue_ops:
@@ -132,6 +133,27 @@ class MCMC:
         self.stream.synchronize()
         self._prepared = st
         return self
+
+    def _warm_up(self, plan, st, sampled):
+        """Run every op of the prologue, the sweep and the store epilogue once, eagerly, then put the chain state back.
+
+        A kernel's first launch can make the driver load its module and grow the context's local-memory pool; both are
+        synchronising operations that invalidate a stream capture, so they have to happen before the graphs are
+        recorded.  Restored afterwards: sampled parameters, sweep / iteration counters, status bits, MH accept counters
+        (derived quantities are recomputed by the prologue, store rows are overwritten by the first stored iteration).
+        """
+        saved = [(st[name].data, st[name].data.clone()) for name in sampled]
+        for ctx in plan.__dict__.get("_ctx", {}).values():
+            if ctx.get("counters") is not None:
+                saved.append((ctx["counters"], ctx["counters"].clone()))
+        for t in (plan.sweep_counter, plan.iter_counter, plan.status):
+            saved.append((t, t.clone()))
+        for phase in ("prologue", "sweep", "store"):
+            for _, fn in self._ops[phase]:
+                fn()
+        for t, copy_ in saved:
+            t.copy_(copy_)
+        torch.cuda.current_stream().synchronize()
 
     def launches_per_sweep(self) -> int:
         self.prepare()
