@@ -5,83 +5,129 @@
 //   ref: sampler.py:154-207 (NormalNormal.sample), gmrf.py:167-198 (sample_normal_canonical), gmrf.py:489-520
 //        (sparse_cholesky: SuperLU, natural ordering, no pivoting == the Thomas-order recurrence), gmrf.py:437-462, 29-61
 //
-// The reference factorises sequentially (1e6 dependent steps per chain).  Here every recurrence is an exact parallel
-// scan over tiles of TILE = 256 threads x 8 elements, single pass with decoupled look-back between tiles:
-//   pivots   u_i = d_i - e_{i-1}^2 / u_{i-1}          Moebius maps compose as 2x2 matrix products (normalised)
-//   forward  f_i = b_i - m_{i-1} f_{i-1}, m = e/u     affine maps (A, B)
-//   backward x_i = g_i - m_i x_{i+1}, g = f/u + z/sqrt(u)   affine maps, tile aggregates published by the forward
-//            kernel so that the backward kernel's tiles are independent
-// (LDL' form: L = L~ D^1/2, so x = L~^-T (D^-1 L~^-1 b + D^-1/2 z) is the reference's mu + L^-T z exactly.)
-// After the scan fixes the value entering a thread's 8 elements, the thread re-runs the *sequential* recurrence on
-// them, so every stored number comes from the same operations as the sequential algorithm; the scan only supplies the
-// boundary values (relative error ~1e-15, damped by the contraction of the pivot recurrence).
+// LDL' form (L = L~ D^1/2, so x = L~^-T (D^-1 L~^-1 b + D^-1/2 z) is the reference's mu + L^-T z exactly):
+//   pivots    u_i = d_i - e_{i-1}^2 / u_{i-1}
+//   forward   f_i = b_i - m_{i-1} f_{i-1},          m_i = e_i / u_i
+//   draw      g_i = f_i / u_i + z_i / sqrt(u_i)
+//   backward  x_i = g_i - m_i x_{i+1}
+// The reference runs these sequentially (1e6 dependent steps per chain).  Here a tile is 128 threads x 18 consecutive
+// elements, and two kernels do the work with ONE read of y each and no per-element scratch in HBM:
 //
-// HBM traffic per chain-iteration (n doubles each): forward reads y, writes g and m; backward reads g, m, y, writes x;
-// P (pd, pe) is shared by all chains and read tile-major, so it stays in L2.  DESIGN.md gives the byte accounting.
+//  tg_forward_kernel   pivots and forward solve as ONE projective linear recurrence on s_i = (p_i, p_{i-1}, h_i),
+//                      u_i = p_i/p_{i-1}, f_i = h_i/p_{i-1}:   p_i = d_i p_{i-1} - e_{i-1}^2 p_{i-2},
+//                      h_i = b_i p_{i-1} - e_{i-1} h_{i-1}.  Element maps compose as 3x3 block-triangular matrices (7
+//                      entries, no divisions); thread aggregates -> CTA scan -> decoupled look-back over tiles (warp-wide
+//                      window).  Output: the exact (1/u, f) entering every thread's 18 elements (16 B per thread).
+//  tg_solve_kernel     re-runs the *sequential* recurrences on each thread's 18 elements from that boundary (so every
+//                      pivot / f / g comes from the reference's operation sequence), keeps g and m in registers, builds
+//                      the backward affine aggregate on the way, scans it (CTA + reverse look-back over tiles), then
+//                      walks back down producing x and both quadratic forms (x-mu0)'P(x-mu0), (y-x)'W(y-x) in the same
+//                      pass.  x leaves through shared memory with one bulk (TMA-engine) store per tile.
+//
+// Tiles are staged global -> shared with cp.async.bulk (1-D, completion on an mbarrier); a thread's 18 elements sit at a
+// 144-byte stride, so 16-byte LDS/STS are bank-conflict free.  Work is handed out tile-major by an atomic ticket (tile t
+// of all chains, then t+1): predecessors are always running or done (deadlock-free look-back) and the chains read the
+// same tile of the shared P together (L2).  HBM traffic per chain-iteration: y twice (16n) + x once (8n) + boundaries
+// (1.8n) against the algorithmic 32n of SURVEY §8d.  DESIGN.md gives the op and byte accounting.
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"
 
 namespace {
 
-constexpr int TG_THREADS = 256;
-constexpr int TG_E = 8;
-constexpr int TG_TILE = TG_THREADS * TG_E;
+constexpr int TG_K = 18;                   // consecutive elements per thread
+constexpr int TG_NT = 128;                 // threads per CTA
+constexpr int TG_NW = TG_NT / 32;
+constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per staged array
+constexpr int TG_PAIRS = TG_K / 2;
+constexpr unsigned FULL = 0xffffffffu;
 
-struct __align__(16) TileRec {
-  unsigned long long flag0, flag1;  // epoch*4 + {1: aggregate ready, 2: inclusive prefix ready}
-  double m[4];                      // Moebius aggregate of the tile
-  double u_end;                     // pivot of the last element of the tile
-  double fa, fb, f_end;             // forward affine aggregate, f of the last element
-  double ba, bb;                    // backward affine aggregate: x_first = ba * x_in + bb
-  double x_in;                      // x of the first element of the NEXT tile (boundary value for the backward kernel)
-  double part[3];                   // per-tile partial sums: log-det, prior quadratic form, likelihood quadratic form
+struct __align__(128) RecF {
+  unsigned long long flag;   // epoch*4 + {1: tile transfer matrix ready, 2: inclusive end state ready}
+  double t[7];               // tile transfer matrix (a b c d e f g), normalised
+  double u_end, f_end;       // pivot / forward-solve value of the tile's last element
+  double pad[6];
+};
+struct __align__(64) RecB {
+  unsigned long long flag;   // epoch*4 + {1: affine aggregate ready, 2: x_first ready}
+  double a, b;               // x_first = a * x_in + b   (x_in = first x of the next tile)
+  double x_first;
+  double part[3];            // per-tile partial sums: prior quadratic form, likelihood quadratic form, log-det
+  double pad;
 };
 
 struct Workspace {
   unsigned long long epoch;
-  unsigned int ticket, done;
-  unsigned int pad[12];
-  // followed by: unsigned int chain_done[n_chains] (padded), TileRec rec[n_tiles][n_chains], scratch g/m
+  unsigned int ticket_f, ticket_b, done_b, pad0;
+  unsigned int pad[10];
+  // followed by: unsigned int chain_done[n_chains] (padded), RecF[n_tiles][n_chains], RecB[n_tiles][n_chains],
+  //              double2 bound[n_chains][n_tiles * TG_NT]
 };
 
 __host__ __device__ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  long long off_chain_done, off_rec, off_g, off_m, total;
+  long long off_chain_done, off_recf, off_recb, off_bound, off_flags_end, total;
   long long n_tiles;
 };
 __host__ __device__ inline Layout make_layout(int n_chains, long long n) {
   Layout L;
   L.n_tiles = (n + TG_TILE - 1) / TG_TILE;
   L.off_chain_done = sizeof(Workspace);
-  L.off_rec = align_up(L.off_chain_done + 2ll * n_chains * sizeof(unsigned int), 128);
-  L.off_g = align_up(L.off_rec + L.n_tiles * n_chains * (long long)sizeof(TileRec), 128);
-  L.off_m = L.off_g + align_up((long long)n_chains * n * 8, 128);
-  L.total = L.off_m + align_up((long long)n_chains * n * 8, 128);
+  L.off_recf = align_up(L.off_chain_done + (long long)n_chains * sizeof(unsigned int), 128);
+  L.off_recb = L.off_recf + L.n_tiles * n_chains * (long long)sizeof(RecF);
+  L.off_flags_end = L.off_recb + L.n_tiles * n_chains * (long long)sizeof(RecB);
+  L.off_bound = align_up(L.off_flags_end, 128);
+  L.total = L.off_bound + align_up((long long)n_chains * L.n_tiles * TG_NT * 16, 128);
   return L;
 }
 
 // ---------------------------------------------------------------------------------------------- small operators
-struct Mob { double a, b, c, d; };   // u -> (a u + b) / (c u + d)
-struct Aff { double a, b; };         // v -> a v + b
+// Transfer matrix of the projective recurrence on (p, q, h):  p' = a p + b q,  q' = c p + d q,  h' = e p + f q + g h.
+struct TM { double a, b, c, d, e, f, g; };
+struct Aff { double a, b; };  // v -> a v + b
 
-__device__ __forceinline__ Mob mob_identity() { return Mob{1.0, 0.0, 0.0, 1.0}; }
-__device__ __forceinline__ Mob mob_mul(const Mob& x, const Mob& y) {  // x after y
-  return Mob{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+__device__ __forceinline__ TM tm_identity() { return TM{1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0}; }
+// left-multiply by the map of one element: p' = dd p - e2 q, q' = p, h' = bb p - ee h
+__device__ __forceinline__ void tm_step(TM& t, double dd, double e2, double bb, double ee) {
+  const double na = fma(dd, t.a, -(e2 * t.c));
+  const double nb = fma(dd, t.b, -(e2 * t.d));
+  const double ne = fma(bb, t.a, -(ee * t.e));
+  const double nf = fma(bb, t.b, -(ee * t.f));
+  t.c = t.a; t.d = t.b; t.a = na; t.b = nb; t.e = ne; t.f = nf; t.g = -(ee * t.g);
 }
-__device__ __forceinline__ void mob_normalize(Mob& m) {
-  const double mx = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
-  int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
-  e = max(-1000, min(1000, e));
-  const double s = __hiloint2double((1023 - e) << 20, 0);
-  m.a *= s; m.b *= s; m.c *= s; m.d *= s;
+__device__ __forceinline__ TM tm_mul(const TM& x, const TM& y) {  // x after y
+  TM r;
+  r.a = fma(x.a, y.a, x.b * y.c);
+  r.b = fma(x.a, y.b, x.b * y.d);
+  r.c = fma(x.c, y.a, x.d * y.c);
+  r.d = fma(x.c, y.b, x.d * y.d);
+  r.e = fma(x.e, y.a, fma(x.f, y.c, x.g * y.e));
+  r.f = fma(x.e, y.b, fma(x.f, y.d, x.g * y.f));
+  r.g = x.g * y.g;
+  return r;
 }
-__device__ __forceinline__ double mob_apply(const Mob& m, double u) { return (m.a * u + m.b) / (m.c * u + m.d); }
-__device__ __forceinline__ Aff aff_mul(const Aff& x, const Aff& y) { return Aff{x.a * y.a, x.a * y.b + x.b}; }  // x after y
+// scale by a power of two so that the projective block (a b c d) has magnitude ~1 (exact; entries grow like u^k)
+__device__ __forceinline__ void tm_normalize(TM& t) {
+  const double mx = fmax(fmax(fabs(t.a), fabs(t.b)), fmax(fabs(t.c), fabs(t.d)));
+  int ex = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+  ex = max(-1000, min(1000, ex));
+  const double s = __hiloint2double((1023 - ex) << 20, 0);
+  t.a *= s; t.b *= s; t.c *= s; t.d *= s; t.e *= s; t.f *= s; t.g *= s;
+}
+__device__ __forceinline__ Aff aff_mul(const Aff& x, const Aff& y) { return Aff{x.a * y.a, fma(x.a, y.b, x.b)}; }  // x after y
 
-__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
+__device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(FULL, v, d); }
+__device__ __forceinline__ TM tm_shfl(const TM& t, int src) {
+  return TM{shfl_d(t.a, src), shfl_d(t.b, src), shfl_d(t.c, src), shfl_d(t.d, src), shfl_d(t.e, src), shfl_d(t.f, src),
+            shfl_d(t.g, src)};
+}
+__device__ __forceinline__ TM tm_shfl_up(const TM& t, int d) {
+  return TM{shfl_up_d(t.a, d), shfl_up_d(t.b, d), shfl_up_d(t.c, d), shfl_up_d(t.d, d), shfl_up_d(t.e, d),
+            shfl_up_d(t.f, d), shfl_up_d(t.g, d)};
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
   unsigned long long v;
@@ -97,473 +143,550 @@ __device__ __forceinline__ double ld_cg(const double* p) {
   return v;
 }
 
-__device__ __forceinline__ double vget(const omc_vec_t& v, int chain, long long i, double dflt) {
-  return v.ptr ? v.ptr[(long long)chain * v.chain_stride + i] : dflt;
+// 1/sqrt(u): MUFU.RSQ64H seed (~2^-22) + two Newton steps (relative error ~1e-16; not correctly rounded, which the
+// 1e-10 parity bar does not need).  u <= 0 or NaN gives NaN/inf and is reported through the status word.
+__device__ __forceinline__ double fast_rsqrt(double u) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  const double hu = 0.5 * u;
+  double e = fma(-hu, y * y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hu, y * y, 0.5);
+  y = fma(y, e, y);
+  return y;
 }
 
-// 8 consecutive doubles of a per-chain / shared vector starting at element i0 (16-byte vector loads when aligned and
-// fully inside the array, scalar loads at the ragged end); out-of-range entries get `fill`.
-__device__ __forceinline__ void load8(const double* base, long long i0, long long n, double fill, double (&v)[TG_E]) {
-  if (base == nullptr) {
+// ---- mbarrier + bulk async copies (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "TG_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra TG_WAIT_DONE;\n"
+      "bra TG_WAIT_LOOP;\n"
+      "TG_WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------- tile staging
+// Shared-memory map (doubles): [0] mbarrier, [2..3] slot in front of pe (pe[-1]), then TG_TILE doubles per array.
+struct Stage {
+  const double* src;   // element 0 of this chain's array (nullptr => constant fill)
+  long long limit;     // number of valid elements in the array
+  double fill;
+  double* dst;
+};
+
+// Stage `cnt` arrays for the tile starting at element i_t.  Full interior tiles with 16-byte aligned sources go through
+// cp.async.bulk; everything else (last tile, odd alignments, absent arrays) through plain loads.  Ends with the data
+// visible to every thread.
+template <int CNT>
+__device__ __forceinline__ void stage_tile(const Stage (&st)[CNT], long long i_t, long long n, unsigned long long* bar,
+                                           int tid) {
+  bool bulk = (i_t + TG_TILE < n);
 #pragma unroll
-    for (int k = 0; k < TG_E; ++k) v[k] = fill;
-    return;
-  }
-  if (i0 + TG_E <= n && ((reinterpret_cast<uintptr_t>(base + i0) & 15) == 0)) {
-    const double2* p = reinterpret_cast<const double2*>(base + i0);
+  for (int q = 0; q < CNT; ++q)
+    if (st[q].src) bulk = bulk && al16(st[q].src + i_t) && (i_t + TG_TILE <= st[q].limit);
+  if (bulk) {
+    if (tid == 0) {
+      unsigned bytes = 0;
 #pragma unroll
-    for (int k = 0; k < TG_E / 2; ++k) {
-      const double2 t = __ldg(p + k);
-      v[2 * k] = t.x;
-      v[2 * k + 1] = t.y;
+      for (int q = 0; q < CNT; ++q)
+        if (st[q].src) bytes += TG_TILE * 8;
+      mbar_expect_tx(bar, bytes);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (st[q].src) bulk_g2s(st[q].dst, st[q].src + i_t, TG_TILE * 8, bar);
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) v[k] = (i0 + k < n) ? __ldg(base + i0 + k) : fill;
   }
-}
-__device__ __forceinline__ void store8(double* base, long long i0, long long n, const double (&v)[TG_E]) {
-  if (i0 + TG_E <= n && ((reinterpret_cast<uintptr_t>(base + i0) & 15) == 0)) {
-    double2* p = reinterpret_cast<double2*>(base + i0);
 #pragma unroll
-    for (int k = 0; k < TG_E / 2; ++k) p[k] = make_double2(v[2 * k], v[2 * k + 1]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k)
-      if (i0 + k < n) base[i0 + k] = v[k];
-  }
-}
-
-// CTA-wide inclusive scan of Moebius maps in thread order; returns the thread's EXCLUSIVE prefix (maps of all lower
-// threads composed) and writes the tile aggregate to `total` (valid in all threads).  smem: 8 warps x 4 doubles + 4.
-__device__ __forceinline__ Mob block_scan_mob(Mob mine, double* sm, Mob& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Mob inc = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Mob o{shfl_up_d(inc.a, d), shfl_up_d(inc.b, d), shfl_up_d(inc.c, d), shfl_up_d(inc.d, d)};
-    if (lane >= d) {
-      inc = mob_mul(inc, o);
-      mob_normalize(inc);
+  for (int q = 0; q < CNT; ++q) {
+    if (st[q].src && bulk) continue;
+    for (int j = tid; j < TG_TILE; j += TG_NT) {
+      const long long i = i_t + j;
+      st[q].dst[j] = (st[q].src && i < st[q].limit) ? __ldg(st[q].src + i) : st[q].fill;
     }
   }
+  if (bulk) mbar_wait(bar, 0);
   __syncthreads();
-  if (lane == 31) { sm[warp * 4 + 0] = inc.a; sm[warp * 4 + 1] = inc.b; sm[warp * 4 + 2] = inc.c; sm[warp * 4 + 3] = inc.d; }
-  __syncthreads();
-  Mob wex = mob_identity();
-  Mob tot = mob_identity();
-  for (int w = 0; w < TG_THREADS / 32; ++w) {
-    Mob ww{sm[w * 4 + 0], sm[w * 4 + 1], sm[w * 4 + 2], sm[w * 4 + 3]};
-    if (w == warp) wex = tot;
-    tot = mob_mul(ww, tot);
-    mob_normalize(tot);
-  }
-  total = tot;
-  Mob lex{shfl_up_d(inc.a, 1), shfl_up_d(inc.b, 1), shfl_up_d(inc.c, 1), shfl_up_d(inc.d, 1)};
-  if (lane == 0) lex = mob_identity();
-  Mob ex = mob_mul(lex, wex);
-  mob_normalize(ex);
-  return ex;
 }
 
-// Same for affine maps.  forward = true: thread order ascending (exclusive prefix = all LOWER threads);
-// forward = false: descending (exclusive prefix = all HIGHER threads, composed from the top down).
-template <bool FORWARD>
-__device__ __forceinline__ Aff block_scan_aff(Aff mine, double* sm, Aff& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = TG_THREADS / 32;
-  Aff inc = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Aff o;
-    if (FORWARD) { o.a = shfl_up_d(inc.a, d); o.b = shfl_up_d(inc.b, d); }
-    else { o.a = shfl_dn_d(inc.a, d); o.b = shfl_dn_d(inc.b, d); }
-    const bool ok = FORWARD ? (lane >= d) : (lane + d < 32);
-    if (ok) inc = aff_mul(inc, o);
-  }
-  __syncthreads();
-  if (lane == (FORWARD ? 31 : 0)) { sm[warp * 2] = inc.a; sm[warp * 2 + 1] = inc.b; }
-  __syncthreads();
-  Aff wex{1.0, 0.0}, tot{1.0, 0.0};
-  for (int k = 0; k < NW; ++k) {
-    const int w = FORWARD ? k : NW - 1 - k;
-    Aff ww{sm[w * 2], sm[w * 2 + 1]};
-    if (w == warp) wex = tot;
-    tot = aff_mul(ww, tot);
-  }
-  total = tot;
-  Aff lex;
-  if (FORWARD) { lex.a = shfl_up_d(inc.a, 1); lex.b = shfl_up_d(inc.b, 1); if (lane == 0) lex = Aff{1.0, 0.0}; }
-  else { lex.a = shfl_dn_d(inc.a, 1); lex.b = shfl_dn_d(inc.b, 1); if (lane == 31) lex = Aff{1.0, 0.0}; }
-  return aff_mul(lex, wex);
-}
-
-__device__ __forceinline__ OmcRng to_rng(const omc_rng_t& r) {
-  OmcRng o;
-  o.seed = r.seed; o.sweep = r.sweep; o.chain_offset = r.chain_offset; o.site = r.site;
-  return o;
-}
-
-// standard normals for elements [i0, i0+8) of a chain: Philox block index = element pair index (position based, so
-// the draw does not depend on the tiling); blocks beyond 2^20 spill into the second counter word.
-__device__ __forceinline__ void normals8(const OmcRng& r, unsigned int chain, long long i0, double (&z)[TG_E]) {
-  const unsigned long long sw = r.sweep ? *r.sweep : 0ull;
-  const uint2 key = make_uint2((unsigned int)r.seed, (unsigned int)(r.seed >> 32));
-#pragma unroll
-  for (int k = 0; k < TG_E / 2; ++k) {
-    const unsigned long long blk = (unsigned long long)(i0 >> 1) + k;
-    uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(blk >> 20) * 0x9E3779B9u,
-                           r.chain_offset + chain, (r.site << 20) | (unsigned int)(blk & 0xFFFFFu));
-    const uint4 b = philox4x32_10(ctr, key);
-    const double u1 = omc_u01(b.x, b.y), u2 = omc_u01(b.z, b.w);
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    z[2 * k] = rad * c;
-    z[2 * k + 1] = rad * s;
-  }
+// two standard normals for elements (2*pair, 2*pair+1) of a chain: Philox block index = element pair index (position
+// based, so the draw does not depend on tiling or sharding); pairs beyond 2^20 spill into the second counter word.
+__device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
+                                            unsigned long long pair, double& z0, double& z1) {
+  uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
+                         (site << 20) | (unsigned int)(pair & 0xFFFFFu));
+  const uint4 b = philox4x32_10(ctr, key);
+  const double u1 = omc_u01(b.x, b.y), u2 = omc_u01(b.z, b.w);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
 }
 
 // ---------------------------------------------------------------------------------------------- forward kernel
-__global__ void __launch_bounds__(TG_THREADS) tridiag_forward_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
-  __shared__ double sm[40];
+template <bool GENERAL>
+__global__ void __launch_bounds__(TG_NT) tg_forward_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+  extern __shared__ __align__(128) double sm[];
   __shared__ unsigned int s_ticket;
-  __shared__ double s_bcast[2];
-  __shared__ int s_bad;
-  const int tid = threadIdx.x;
+  __shared__ double s_tot[TG_NW][7];
+  __shared__ double s_in[2];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
+  double* spe = sm + 4;
+  double* spd = spe + TG_TILE;
+  double* sy = spd + TG_TILE;
+  double* sw = sy + TG_TILE;       // GENERAL only
+  double* sh = sw + TG_TILE;       // GENERAL only
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
   if (tid == 0) {
-    s_ticket = atomicAdd(&ws->ticket, 1u);
-    s_bad = 0;
+    s_ticket = atomicAdd(&ws->ticket_f, 1u);
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
   const long long work = s_ticket;
   const int C = a.n_chains;
-  const long long tile = work / C;     // tile-major order: the 64 chains read the same tile of the shared P together
+  const long long tile = work / C;     // tile-major: the chains read the same tile of the shared P together
   const int chain = (int)(work % C);
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
-  TileRec* recs = reinterpret_cast<TileRec*>(wsb + L.off_rec);
-  TileRec* rec = recs + tile * C + chain;
-  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
+  RecF* recs = reinterpret_cast<RecF*>(wsb + L.off_recf);
+  RecF* rec = recs + tile * C + chain;
   const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
+  const long long i_t = tile * TG_TILE;
+  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
+  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
 
-  const long long i0 = tile * TG_TILE + (long long)tid * TG_E;
-  const double lam = vget(a.lambda, chain, 0, 1.0), tau = vget(a.tau, chain, 0, 1.0);
-  double d[TG_E], e[TG_E], ep;  // d_i, e_i (couples i, i+1), ep = e_{i0-1}
-  {
-    double pd[TG_E], wv[TG_E];
-    load8(a.pd, i0, n, 1.0, pd);
-    load8(a.pe, i0, n - 1, 0.0, e);
-    load8(a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, i0, n, 1.0, wv);
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) {
-      d[k] = lam * pd[k] + tau * wv[k];
-      e[k] *= lam;
-    }
-    ep = (a.pe && i0 > 0 && i0 - 1 < n - 1) ? lam * __ldg(a.pe + i0 - 1) : 0.0;
+  const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
+  if (GENERAL) {
+    const Stage st[5] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
+                         {a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, n, 1.0, sw},
+                         {a.h.ptr ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr, n, 0.0, sh}};
+    if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+    stage_tile<5>(st, i_t, n, bar, tid);
+  } else {
+    const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
+    if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+    stage_tile<3>(st, i_t, n, bar, tid);
   }
-  // ---- stage 0: pivots.  thread aggregate of the Moebius maps of its elements
-  Mob agg = mob_identity();
+
+  // ---- thread aggregate over its 18 elements (no divisions)
+  const int j0 = tid * TG_K;
+  TM t = tm_identity();
   {
-    double eprev = ep;
+    double eprev = lam * spe[j0 - 1];
 #pragma unroll
-    for (int k = 0; k < TG_E; ++k) {
-      if (i0 + k < n) {
-        const double e2 = eprev * eprev;
-        const Mob nm{d[k] * agg.a - e2 * agg.c, d[k] * agg.b - e2 * agg.d, agg.a, agg.b};
-        agg = nm;
+    for (int c = 0; c < TG_PAIRS; ++c) {
+      const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
+      const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
+      const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
+      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0);
+      if (GENERAL) {
+        w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
+        h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
       }
-      eprev = e[k];
+      {
+        const double tw = GENERAL ? tau * w2.x : tau;
+        const double dd = fma(lam, pd2.x, tw);
+        const double bb = GENERAL ? fma(lam, h2.x, tw * y2.x) : tw * y2.x;
+        tm_step(t, dd, eprev * eprev, bb, eprev);
+        eprev = lam * pe2.x;
+      }
+      {
+        const double tw = GENERAL ? tau * w2.y : tau;
+        const double dd = fma(lam, pd2.y, tw);
+        const double bb = GENERAL ? fma(lam, h2.y, tw * y2.y) : tw * y2.y;
+        tm_step(t, dd, eprev * eprev, bb, eprev);
+        eprev = lam * pe2.y;
+      }
+      if (c == 2 || c == 5) tm_normalize(t);
     }
-    mob_normalize(agg);
+    tm_normalize(t);
   }
-  Mob tile_tot;
-  const Mob ex = block_scan_mob(agg, sm, tile_tot);
-  if (tid == 0) {
-    double u_in = 1.0;
+  // ---- CTA scan of the transfer matrices (thread order): inclusive within the warp, then across the 4 warps
+  TM inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const TM o = tm_shfl_up(inc, d);
+    if (lane >= d) inc = tm_mul(inc, o);
+    if (d == 4) tm_normalize(inc);
+  }
+  tm_normalize(inc);
+  if (lane == 31) {
+    s_tot[warp][0] = inc.a; s_tot[warp][1] = inc.b; s_tot[warp][2] = inc.c; s_tot[warp][3] = inc.d;
+    s_tot[warp][4] = inc.e; s_tot[warp][5] = inc.f; s_tot[warp][6] = inc.g;
+  }
+  __syncthreads();
+  TM wex = tm_identity();   // composition of the warps below this one
+  for (int w = 0; w < warp; ++w) {
+    const TM ww{s_tot[w][0], s_tot[w][1], s_tot[w][2], s_tot[w][3], s_tot[w][4], s_tot[w][5], s_tot[w][6]};
+    wex = tm_mul(ww, wex);
+  }
+  TM ex = tm_shfl_up(inc, 1);
+  if (lane == 0) ex = tm_identity();
+  ex = tm_mul(ex, wex);       // exclusive prefix of this thread inside the tile
+  tm_normalize(ex);
+
+  // ---- decoupled look-back over the tiles of this chain (warp 0, 32 predecessors per round)
+  if (warp == 0) {
+    TM tot = tm_identity();
+#pragma unroll
+    for (int w = 0; w < TG_NW; ++w) {
+      const TM ww{s_tot[w][0], s_tot[w][1], s_tot[w][2], s_tot[w][3], s_tot[w][4], s_tot[w][5], s_tot[w][6]};
+      tot = tm_mul(ww, tot);
+    }
+    tm_normalize(tot);
+    double su = 1.0, sf = 0.0;   // state (u, f) with q = 1 at the far end of the walk (virtual tile -1: u = 1, f = 0)
+    TM R = tm_identity();        // composition of the aggregates between that state and this tile
     if (tile > 0) {
-      rec->m[0] = tile_tot.a; rec->m[1] = tile_tot.b; rec->m[2] = tile_tot.c; rec->m[3] = tile_tot.d;
-      st_release(&rec->flag0, FLAG_A);
-      Mob R = mob_identity();
-      long long j = tile - 1;
+      if (lane == 0) {
+        rec->t[0] = tot.a; rec->t[1] = tot.b; rec->t[2] = tot.c; rec->t[3] = tot.d;
+        rec->t[4] = tot.e; rec->t[5] = tot.f; rec->t[6] = tot.g;
+        st_release(&rec->flag, FLAG_A);
+      }
+      long long base = tile - 1;
       while (true) {
-        TileRec* pr = recs + j * C + chain;
-        unsigned long long f;
-        do { f = ld_acquire(&pr->flag0); } while (f != FLAG_A && f != FLAG_P);
-        if (f == FLAG_P) { u_in = mob_apply(R, ld_cg(&pr->u_end)); break; }
-        Mob mj{ld_cg(&pr->m[0]), ld_cg(&pr->m[1]), ld_cg(&pr->m[2]), ld_cg(&pr->m[3])};
-        R = mob_mul(R, mj);
-        mob_normalize(R);
-        --j;   // tile 0 always publishes FLAG_P, so the walk terminates
-      }
-    }
-    s_bcast[0] = u_in;
-  }
-  __syncthreads();
-  const double u_tile_in = s_bcast[0];
-  double u_prev = mob_apply(ex, u_tile_in);   // pivot of element i0-1 (dummy 1.0 for the very first element)
-  if (i0 == 0) u_prev = 1.0;
-  double iu[TG_E];                            // 1 / u_i
-  bool bad = false;
-  double logdet = 0.0;
-  const double iu_prev = 1.0 / u_prev;
-  {
-    double eprev = ep, iup = iu_prev;
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) {
-      if (i0 + k < n) {
-        const double u = d[k] - (eprev * eprev) * iup;
-        if (!(u > 0.0)) bad = true;
-        iup = 1.0 / u;
-        iu[k] = iup;
-        if (a.logdet) logdet += log(u);
-        if (i0 + k == n - 1 || (tid == TG_THREADS - 1 && k == TG_E - 1)) {   // last element of the tile
-          rec->u_end = u;
-          st_release(&rec->flag0, FLAG_P);
+        const long long j = base - lane;
+        unsigned long long fl = FLAG_P;   // tiles before the first: inclusive state (1, 0)
+        const RecF* pr = nullptr;
+        if (j >= 0) {
+          pr = recs + j * C + chain;
+          do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
         }
-      } else {
-        iu[k] = 1.0;
-      }
-      eprev = e[k];
-    }
-  }
-  if (bad) s_bad = 1;
-  // ---- stage 1: forward substitution  f_i = b_i - m_{i-1} f_{i-1},  b_i = tau w_i y_i + lambda h_i
-  double f[TG_E];
-  {
-    double yv[TG_E], wv[TG_E], hv[TG_E];
-    load8(a.y.ptr + (long long)chain * a.y.chain_stride, i0, n, 0.0, yv);
-    load8(a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, i0, n, 1.0, wv);
-    load8(a.h.ptr ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr, i0, n, 0.0, hv);
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) f[k] = tau * wv[k] * yv[k] + lam * hv[k];   // holds b_i for now
-  }
-  double mprev[TG_E];  // m_{i-1} = e_{i-1} / u_{i-1}
-  Aff fagg{1.0, 0.0};
-  {
-    double eprev = ep, iup = iu_prev;
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) {
-      mprev[k] = eprev * iup;
-      if (i0 + k < n) {
-        fagg.a = -mprev[k] * fagg.a;
-        fagg.b = f[k] - mprev[k] * fagg.b;
-      }
-      eprev = e[k];
-      iup = iu[k];
-    }
-  }
-  Aff ftot;
-  const Aff fex = block_scan_aff<true>(fagg, sm, ftot);
-  if (tid == 0) {
-    double f_in = 0.0;
-    if (tile > 0) {
-      rec->fa = ftot.a; rec->fb = ftot.b;
-      st_release(&rec->flag1, FLAG_A);
-      Aff R{1.0, 0.0};
-      long long j = tile - 1;
-      while (true) {
-        TileRec* pr = recs + j * C + chain;
-        unsigned long long fl;
-        do { fl = ld_acquire(&pr->flag1); } while (fl != FLAG_A && fl != FLAG_P);
-        if (fl == FLAG_P) { f_in = R.a * ld_cg(&pr->f_end) + R.b; break; }
-        R = aff_mul(R, Aff{ld_cg(&pr->fa), ld_cg(&pr->fb)});
-        --j;
-      }
-    }
-    s_bcast[1] = f_in;
-  }
-  __syncthreads();
-  {
-    double fp = fex.a * s_bcast[1] + fex.b;   // f of element i0-1
-#pragma unroll
-    for (int k = 0; k < TG_E; ++k) {
-      if (i0 + k < n) {
-        fp = f[k] - mprev[k] * fp;
-        f[k] = fp;
-        if (i0 + k == n - 1 || (tid == TG_THREADS - 1 && k == TG_E - 1)) {
-          rec->f_end = fp;
-          st_release(&rec->flag1, FLAG_P);
+        const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
+        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
+        TM mine = tm_identity();
+        double pu = 1.0, pf = 0.0;
+        if (pr) {
+          if (lane == lp) {
+            pu = ld_cg(&pr->u_end);
+            pf = ld_cg(&pr->f_end);
+          } else if (lane < lp) {
+            mine = TM{ld_cg(&pr->t[0]), ld_cg(&pr->t[1]), ld_cg(&pr->t[2]), ld_cg(&pr->t[3]), ld_cg(&pr->t[4]),
+                      ld_cg(&pr->t[5]), ld_cg(&pr->t[6])};
+          }
         }
+        for (int l = 0; l < lp; ++l) {
+          R = tm_mul(R, tm_shfl(mine, l));
+          if ((l & 3) == 3) tm_normalize(R);
+        }
+        tm_normalize(R);
+        if (lp < 32) {
+          su = shfl_d(pu, lp);
+          sf = shfl_d(pf, lp);
+          break;
+        }
+        base -= 32;
       }
     }
-  }
-  // ---- g_i = f_i / u_i + z_i / sqrt(u_i),  m_i = e_i / u_i ; backward tile aggregate
-  double z[TG_E];
-  if (a.debug_z) {
-    const long long sw = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
-    load8(a.debug_z + sw * a.debug_sweep_stride + (long long)chain * n, i0, n, 0.0, z);
-  } else if (i0 < n) {
-    normals8(to_rng(a.rng), chain, i0, z);
-  }
-  double g[TG_E], m[TG_E];
-  Aff bagg{1.0, 0.0};  // x_{i0} = bagg.a * x_{i0+8} + bagg.b, built from the top element down
-#pragma unroll
-  for (int k = TG_E - 1; k >= 0; --k) {
-    if (i0 + k < n) {
-      const double su = sqrt(iu[k]);
-      g[k] = f[k] * iu[k] + z[k] * su;
-      m[k] = e[k] * iu[k];
-      bagg.a = -m[k] * bagg.a;
-      bagg.b = g[k] - m[k] * bagg.b;
-      if (a.probe_l) a.probe_l[(long long)chain * n + i0 + k] = 1.0 / su;
-      if (a.probe_c && i0 + k < n - 1) a.probe_c[(long long)chain * (n - 1) + i0 + k] = e[k] * su;
-    } else {
-      g[k] = 0.0;
-      m[k] = 0.0;
+    const double p1 = fma(R.a, su, R.b), q1 = fma(R.c, su, R.d), h1 = fma(R.e, su, fma(R.g, sf, R.f));
+    const double u_in = p1 / q1, f_in = h1 / q1;
+    const double p2 = fma(tot.a, u_in, tot.b), q2 = fma(tot.c, u_in, tot.d), h2 = fma(tot.e, u_in, fma(tot.g, f_in, tot.f));
+    if (lane == 0) {
+      rec->u_end = p2 / q2;
+      rec->f_end = h2 / q2;
+      st_release(&rec->flag, FLAG_P);
+      s_in[0] = u_in;
+      s_in[1] = f_in;
     }
-  }
-  double* gs = reinterpret_cast<double*>(wsb + L.off_g) + (long long)chain * n;
-  double* ms = reinterpret_cast<double*>(wsb + L.off_m) + (long long)chain * n;
-  if (i0 < n) {
-    store8(gs, i0, n, g);
-    store8(ms, i0, n, m);
-  }
-  Aff btot;
-  (void)block_scan_aff<false>(bagg, sm, btot);
-  const double ld_tile = a.logdet ? omc_block_sum(logdet, sm) : 0.0;
-  __syncthreads();
-  if (tid == 0) {
-    rec->ba = btot.a;
-    rec->bb = btot.b;
-    rec->part[0] = ld_tile;
-    if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
-    __threadfence();
-    const unsigned int dn = atomicAdd(&chain_done[chain], 1u);
-    s_ticket = (dn == (unsigned int)(L.n_tiles - 1)) ? 1u : 0u;
   }
   __syncthreads();
-  // ---- chain finisher: boundary values x_in for every tile of this chain (backward scan over the tile aggregates)
-  if (s_ticket && tid < 32) {
-    __threadfence();
-    const int lane = tid;
-    const long long T = L.n_tiles;
-    const long long per = (T + 31) / 32;
-    // lane l owns tiles [hi - per, hi) counted from the top: tile index t = T-1 - (l*per + q)
-    Aff la{1.0, 0.0};
-    for (long long q = 0; q < per; ++q) {
-      const long long t = T - 1 - (lane * per + q);
-      if (t >= 0) {
-        TileRec* r = recs + t * C + chain;
-        la = aff_mul(Aff{ld_cg(&r->ba), ld_cg(&r->bb)}, la);
-      }
-    }
-    Aff inc = la;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) {
-      Aff o{shfl_up_d(inc.a, dd), shfl_up_d(inc.b, dd)};
-      if (lane >= dd) inc = aff_mul(inc, o);
-    }
-    Aff exl{shfl_up_d(inc.a, 1), shfl_up_d(inc.b, 1)};
-    if (lane == 0) exl = Aff{1.0, 0.0};
-    double xin = exl.b;  // x entering the lane's top tile (x beyond the last element is 0 and its multiplier m is 0)
-    double ldsum = 0.0;
-    for (long long q = 0; q < per; ++q) {
-      const long long t = T - 1 - (lane * per + q);
-      if (t >= 0) {
-        TileRec* r = recs + t * C + chain;
-        r->x_in = xin;
-        xin = ld_cg(&r->ba) * xin + ld_cg(&r->bb);
-        ldsum += ld_cg(&r->part[0]);
-      }
-    }
-    if (a.logdet) {
-      // fixed summation order (lane partials, then a shuffle tree): deterministic
-      ldsum = omc_warp_sum(ldsum);
-      if (lane == 0) a.logdet[chain] = ldsum;
-    }
-    if (lane == 0) chain_done[chain] = 0;
-  }
-  // ---- last CTA of the launch re-arms the ticket counter and advances the epoch
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int dn = atomicAdd(&ws->done, 1u);
-    if (dn == (unsigned int)(L.n_tiles * C - 1)) {
-      ws->ticket = 0;
-      ws->done = 0;
-      ws->epoch = epoch + 1;
-      __threadfence();
-    }
+  // ---- boundary values entering this thread's elements: 1/u_{i0-1} and f_{i0-1}
+  {
+    const double u_in = s_in[0], f_in = s_in[1];
+    const double p = fma(ex.a, u_in, ex.b), q = fma(ex.c, u_in, ex.d), h = fma(ex.e, u_in, fma(ex.g, f_in, ex.f));
+    double2* bound = reinterpret_cast<double2*>(wsb + L.off_bound) + ((long long)chain * L.n_tiles + tile) * TG_NT;
+    bound[tid] = make_double2(q / p, h / q);
   }
 }
 
-// ---------------------------------------------------------------------------------------------- backward kernel
-// SOLVE = true : x_i = g_i - m_i x_{i+1} from the scratch written by the forward kernel, then the quadratic forms.
-// SOLVE = false: x is given (quadratic forms of the current state only).
-template <bool SOLVE>
-__global__ void __launch_bounds__(TG_THREADS) tridiag_backward_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
-  __shared__ double sm[40];
-  __shared__ unsigned int s_last;
-  const int tid = threadIdx.x;
+// ---------------------------------------------------------------------------------------------- solve kernel
+// GENERAL: diagonal weights w, prior-mean terms h = P mu0 and mu0 are staged too (absent ones are filled with 1 / 0).
+// DEBUG  : injected normals (debug_z), log-det / factor probes, and the factorisation-only mode (x == NULL).
+template <bool GENERAL, bool DEBUG>
+__global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned int s_ticket, s_last;
+  __shared__ double s_red[2 * TG_NW + 4];
+  __shared__ double s_xin;
+  __shared__ int s_bad;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
+  double* spe = sm + 4;
+  double* spd = spe + TG_TILE;
+  double* sy = spd + TG_TILE;
+  double* sw = sy + TG_TILE;                 // GENERAL
+  double* sh = sw + TG_TILE;                 // GENERAL
+  double* smu = sh + TG_TILE;                // GENERAL (TG_TILE + 2: mu0 of the next tile's first element)
+  double* sz = GENERAL ? smu + TG_TILE + 2 : sy + TG_TILE;   // DEBUG
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
+  if (tid == 0) {
+    s_ticket = atomicAdd(&ws->ticket_b, 1u);
+    s_bad = 0;
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const long long work = s_ticket;
   const int C = a.n_chains;
   const long long T = L.n_tiles;
-  const long long work = blockIdx.x;
-  const long long tile = T - 1 - work / C;   // top tiles first: they were written last by the forward kernel (L2)
+  const long long tile = T - 1 - work / C;   // top tiles first (reverse look-back); tile-major over the chains
   const int chain = (int)(work % C);
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
-  TileRec* recs = reinterpret_cast<TileRec*>(wsb + L.off_rec);
-  TileRec* rec = recs + tile * C + chain;
-  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done) + C;
-  const long long i0 = tile * TG_TILE + (long long)tid * TG_E;
-  double* xg = a.x + (long long)chain * n;
-  double x[TG_E];
-  double x_next;   // x_{i0+8}
-  if (SOLVE) {
-    const double* gs = reinterpret_cast<const double*>(wsb + L.off_g) + (long long)chain * n;
-    const double* ms = reinterpret_cast<const double*>(wsb + L.off_m) + (long long)chain * n;
-    double g[TG_E], m[TG_E];
-    load8(gs, i0, n, 0.0, g);
-    load8(ms, i0, n, 0.0, m);
-    Aff bagg{1.0, 0.0};
-#pragma unroll
-    for (int k = TG_E - 1; k >= 0; --k) {
-      bagg.a = -m[k] * bagg.a;
-      bagg.b = g[k] - m[k] * bagg.b;
-    }
-    Aff btot;
-    const Aff bex = block_scan_aff<false>(bagg, sm, btot);
-    x_next = bex.a * rec->x_in + bex.b;
-    double xn = x_next;
-#pragma unroll
-    for (int k = TG_E - 1; k >= 0; --k) {
-      xn = g[k] - m[k] * xn;
-      x[k] = xn;
-    }
-    if (i0 < n) store8(xg, i0, n, x);
-  } else {
-    load8(xg, i0, n, 0.0, x);
-    x_next = (i0 + TG_E < n) ? xg[i0 + TG_E] : 0.0;
-  }
-  // ---- quadratic forms: (x-mu0)' P (x-mu0) and (y-x)' W (y-x)
-  double ssp = 0.0, ssl = 0.0;
+  RecB* recs = reinterpret_cast<RecB*>(wsb + L.off_recb);
+  RecB* rec = recs + tile * C + chain;
+  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
+  const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
+  const long long i_t = tile * TG_TILE;
+  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
+  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
+  const bool solve = !DEBUG || a.x != nullptr;
+
+  const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
   {
-    double pd[TG_E], pe[TG_E], mu[TG_E], yv[TG_E], wv[TG_E];
-    load8(a.pd, i0, n, 0.0, pd);
-    load8(a.pe, i0, n - 1, 0.0, pe);
-    const double* mup = a.mu0.ptr ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
-    load8(mup, i0, n, 0.0, mu);
-    load8(a.y.ptr ? a.y.ptr + (long long)chain * a.y.chain_stride : nullptr, i0, n, 0.0, yv);
-    load8(a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, i0, n, 1.0, wv);
-    const double mu_next = (mup && i0 + TG_E < n) ? __ldg(mup + i0 + TG_E) : 0.0;
-    double r_next = x_next - mu_next;
+    const double* wp = (GENERAL && a.w.ptr) ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr;
+    const double* hp = (GENERAL && a.h.ptr) ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr;
+    const double* mp = (GENERAL && a.mu0.ptr) ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
+    const double* zp = nullptr;
+    if (DEBUG && a.debug_z) {
+      const long long sw_ = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+      zp = a.debug_z + sw_ * a.debug_sweep_stride + (long long)chain * n;
+    }
+    if (tid == 0) {
+      spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+      if (GENERAL) smu[TG_TILE] = (mp && i_t + TG_TILE < n) ? __ldg(mp + i_t + TG_TILE) : 0.0;
+    }
+    if (GENERAL && DEBUG) {
+      const Stage st[7] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
+                           {hp, n, 0.0, sh}, {mp, n, 0.0, smu}, {zp, n, 0.0, sz}};
+      stage_tile<7>(st, i_t, n, bar, tid);
+    } else if (GENERAL) {
+      const Stage st[6] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
+                           {hp, n, 0.0, sh}, {mp, n, 0.0, smu}};
+      stage_tile<6>(st, i_t, n, bar, tid);
+    } else if (DEBUG) {
+      const Stage st[4] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {zp, n, 0.0, sz}};
+      stage_tile<4>(st, i_t, n, bar, tid);
+    } else {
+      const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
+      stage_tile<3>(st, i_t, n, bar, tid);
+    }
+  }
+
+  // ---- ascending pass: the sequential recurrences on this thread's 18 elements from the exact boundary values
+  const int j0 = tid * TG_K;
+  const long long i0 = i_t + j0;
+  double g[TG_K], m[TG_K];
+  Aff bagg{1.0, 0.0};          // x_{i0} = bagg.a * x_{i0+18} + bagg.b
+  bool bad = false;
+  double logdet = 0.0;
+  {
+    const double2 bnd = reinterpret_cast<const double2*>(wsb + L.off_bound)[((long long)chain * T + tile) * TG_NT + tid];
+    double iu_prev = bnd.x, f_prev = bnd.y;
+    double eprev = lam * spe[j0 - 1];
+    const unsigned long long sweep = (!DEBUG || !a.debug_z) ? (a.rng.sweep ? *a.rng.sweep : 0ull) : 0ull;
+    const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
+    const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
+    const bool use_rng = solve && !(DEBUG && a.debug_z) && (i0 < n);
 #pragma unroll
-    for (int k = TG_E - 1; k >= 0; --k) {
-      if (i0 + k < n) {
-        const double r = x[k] - mu[k];
-        ssp += pd[k] * r * r + 2.0 * pe[k] * r * r_next;
-        const double q = yv[k] - x[k];
-        ssl += wv[k] * q * q;
-        r_next = r;
+    for (int c = 0; c < TG_PAIRS; ++c) {
+      const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
+      const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
+      const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
+      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0), z2 = make_double2(0.0, 0.0);
+      if (GENERAL) {
+        w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
+        h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
+      }
+      if (DEBUG && a.debug_z) {
+        z2 = *reinterpret_cast<const double2*>(sz + j0 + 2 * c);
+      } else if (use_rng) {
+        normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), z2.x, z2.y);
+      }
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int k = 2 * c + hlf;
+        const double pdk = hlf ? pd2.y : pd2.x, pek = hlf ? pe2.y : pe2.x, yk = hlf ? y2.y : y2.x;
+        const double wk = hlf ? w2.y : w2.x, hk = hlf ? h2.y : h2.x, zk = hlf ? z2.y : z2.x;
+        const double tw = GENERAL ? tau * wk : tau;
+        const double dd = fma(lam, pdk, tw);
+        const double bb = GENERAL ? fma(lam, hk, tw * yk) : tw * yk;
+        const double u = fma(-(eprev * eprev), iu_prev, dd);
+        if (!(u > 0.0) && i0 + k < n) bad = true;
+        const double su = fast_rsqrt(u);
+        const double iu = su * su;
+        const double mp_ = eprev * iu_prev;
+        const double f = fma(-mp_, f_prev, bb);
+        const double e = lam * pek;
+        const double mk = e * iu;
+        const double gk = fma(f, iu, zk * su);
+        g[k] = gk;
+        m[k] = mk;
+        bagg.b = fma(bagg.a, gk, bagg.b);
+        bagg.a = -(bagg.a * mk);
+        if (DEBUG && i0 + k < n) {
+          if (a.logdet) logdet += log(u);
+          if (a.probe_l) a.probe_l[(long long)chain * n + i0 + k] = sqrt(u);
+          if (a.probe_c && i0 + k < n - 1) a.probe_c[(long long)chain * (n - 1) + i0 + k] = e * su;
+        }
+        iu_prev = iu;
+        f_prev = f;
+        eprev = e;
       }
     }
   }
-  ssp = omc_block_sum(ssp, sm);
-  ssl = omc_block_sum(ssl, sm);
+  if (bad) s_bad = 1;
+
+  double ssp = 0.0, ssl = 0.0;
+  if (solve) {
+    // ---- CTA scan of the backward affine maps, from the top thread down; exclusive prefix = all HIGHER threads
+    Aff inc = bagg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const Aff o{shfl_dn_d(inc.a, d), shfl_dn_d(inc.b, d)};
+      if (lane + d < 32) inc = aff_mul(inc, o);
+    }
+    if (lane == 0) { s_red[2 * warp] = inc.a; s_red[2 * warp + 1] = inc.b; }
+    __syncthreads();
+    Aff wex{1.0, 0.0};    // composition of the warps above this one
+    for (int w = TG_NW - 1; w > warp; --w) wex = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, wex);
+    Aff lex{shfl_dn_d(inc.a, 1), shfl_dn_d(inc.b, 1)};
+    if (lane == 31) lex = Aff{1.0, 0.0};
+    const Aff bex = aff_mul(lex, wex);   // x_{i0+18} = bex.a * x_in + bex.b
+    // ---- reverse look-back over the tiles of this chain (warp 0)
+    if (warp == 0) {
+      Aff tot{1.0, 0.0};
+#pragma unroll
+      for (int w = TG_NW - 1; w >= 0; --w) tot = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, tot);
+      double xfar = 0.0;     // x beyond the last element is 0 (and its multiplier m_{n-1} is 0)
+      Aff R{1.0, 0.0};
+      if (tile < T - 1) {
+        if (lane == 0) {
+          rec->a = tot.a;
+          rec->b = tot.b;
+          st_release(&rec->flag, FLAG_A);
+        }
+        long long base = tile + 1;
+        while (true) {
+          const long long j = base + lane;
+          unsigned long long fl = FLAG_P;
+          const RecB* pr = nullptr;
+          if (j < T) {
+            pr = recs + j * C + chain;
+            do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
+          }
+          const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
+          const int lp = pmask ? (__ffs(pmask) - 1) : 32;
+          Aff mine{1.0, 0.0};
+          double px = 0.0;
+          if (pr) {
+            if (lane == lp) px = ld_cg(&pr->x_first);
+            else if (lane < lp) mine = Aff{ld_cg(&pr->a), ld_cg(&pr->b)};
+          }
+          for (int l = 0; l < lp; ++l) R = aff_mul(R, Aff{shfl_d(mine.a, l), shfl_d(mine.b, l)});
+          if (lp < 32) {
+            xfar = shfl_d(px, lp);
+            break;
+          }
+          base += 32;
+        }
+      }
+      const double x_in = fma(R.a, xfar, R.b);
+      if (lane == 0) {
+        rec->x_first = fma(tot.a, x_in, tot.b);
+        st_release(&rec->flag, FLAG_P);
+        s_xin = x_in;
+      }
+    }
+    __syncthreads();
+    // ---- descending pass: x and both quadratic forms; x overwrites y in shared memory
+    double xn = fma(bex.a, s_xin, bex.b);
+    double rn = GENERAL ? xn - smu[j0 + TG_K] : xn;
+#pragma unroll
+    for (int c = TG_PAIRS - 1; c >= 0; --c) {
+      const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
+      const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
+      const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
+      double2 w2 = make_double2(1.0, 1.0), mu2 = make_double2(0.0, 0.0);
+      if (GENERAL) {
+        w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
+        mu2 = *reinterpret_cast<const double2*>(smu + j0 + 2 * c);
+      }
+      double2 x2;
+#pragma unroll
+      for (int hlf = 1; hlf >= 0; --hlf) {
+        const int k = 2 * c + hlf;
+        const double pdk = hlf ? pd2.y : pd2.x, pek = hlf ? pe2.y : pe2.x, yk = hlf ? y2.y : y2.x;
+        const double wk = hlf ? w2.y : w2.x, muk = hlf ? mu2.y : mu2.x;
+        const double x = fma(-m[k], xn, g[k]);
+        const double r = GENERAL ? x - muk : x;
+        if (i0 + k < n) {
+          ssp = fma(pdk * r, r, fma(2.0 * pek * r, rn, ssp));
+          const double q = yk - x;
+          ssl = GENERAL ? fma(wk * q, q, ssl) : fma(q, q, ssl);
+        }
+        if (hlf) x2.y = x; else x2.x = x;
+        xn = x;
+        rn = r;
+      }
+      *reinterpret_cast<double2*>(sy + j0 + 2 * c) = x2;
+    }
+    // ---- x tile: shared -> global (bulk store for full aligned tiles)
+    double* xg = a.x + (long long)chain * n + i_t;
+    const bool bulk_out = (i_t + TG_TILE <= n) && al16(xg);
+    if (bulk_out) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (bulk_out) {
+      if (tid == 0) bulk_s2g(xg, sy, TG_TILE * 8);
+    } else {
+      for (int j = tid; j < TG_TILE; j += TG_NT)
+        if (i_t + j < n) xg[j] = sy[j];
+    }
+  }
+  // ---- per-tile partial sums (fixed order: shuffle tree, then the 4 warps in order)
+  ssp = omc_warp_sum(ssp);
+  ssl = omc_warp_sum(ssl);
+  if (DEBUG) logdet = omc_warp_sum(logdet);
+  __syncthreads();
+  if (lane == 0) { s_red[warp] = ssp; s_red[TG_NW + warp] = ssl; }
+  __shared__ double s_ld[TG_NW];
+  if (DEBUG && lane == 0) s_ld[warp] = logdet;
+  __syncthreads();
   if (tid == 0) {
-    rec->part[1] = ssp;
-    rec->part[2] = ssl;
+    double sp = 0.0, sl = 0.0, ld = 0.0;
+    for (int w = 0; w < TG_NW; ++w) { sp += s_red[w]; sl += s_red[TG_NW + w]; if (DEBUG) ld += s_ld[w]; }
+    rec->part[0] = sp;
+    rec->part[1] = sl;
+    rec->part[2] = ld;
+    if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
     __threadfence();
     const unsigned int dn = atomicAdd(&chain_done[chain], 1u);
     s_last = (dn == (unsigned int)(T - 1)) ? 1u : 0u;
@@ -571,11 +694,97 @@ __global__ void __launch_bounds__(TG_THREADS) tridiag_backward_kernel(omc_tridia
   __syncthreads();
   if (s_last && tid < 32) {   // deterministic per-chain reduction of the tile partials
     __threadfence();
+    double sp = 0.0, sl = 0.0, ld = 0.0;
+    for (long long t = tid; t < T; t += 32) {
+      const RecB* r = recs + t * C + chain;
+      sp += ld_cg(&r->part[0]);
+      sl += ld_cg(&r->part[1]);
+      ld += ld_cg(&r->part[2]);
+    }
+    sp = omc_warp_sum(sp);
+    sl = omc_warp_sum(sl);
+    ld = omc_warp_sum(ld);
+    if (tid == 0) {
+      if (solve && a.ss_prior) a.ss_prior[chain] = sp;
+      if (solve && a.ss_lik) a.ss_lik[chain] = sl;
+      if (DEBUG && a.logdet) a.logdet[chain] = ld;
+      chain_done[chain] = 0;
+    }
+  }
+  // ---- last CTA of the launch re-arms the ticket counters and advances the epoch
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int dn = atomicAdd(&ws->done_b, 1u);
+    if (dn == (unsigned int)(T * C - 1)) {
+      ws->ticket_f = 0;
+      ws->ticket_b = 0;
+      ws->done_b = 0;
+      ws->epoch = epoch + 1;
+      __threadfence();
+    }
+    if (solve) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- quadratic forms only
+// ss_prior = (x-mu0)' P (x-mu0), ss_lik = (y-x)' W (y-x) of the CURRENT x (ref: sampler.py:275-284); coalesced sweep,
+// per-tile partials reduced per chain in a fixed order (deterministic).
+__global__ void __launch_bounds__(TG_NT) tg_quadforms_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+  __shared__ double s_red[2 * TG_NW];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = a.n_chains;
+  const long long T = L.n_tiles;
+  const long long tile = blockIdx.x / C;
+  const int chain = (int)(blockIdx.x % C);
+  const long long n = a.n;
+  char* wsb = reinterpret_cast<char*>(ws);
+  RecB* recs = reinterpret_cast<RecB*>(wsb + L.off_recb);
+  RecB* rec = recs + tile * C + chain;
+  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
+  const double* xg = a.x + (long long)chain * n;
+  const double* mup = a.mu0.ptr ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
+  const double* yp = a.y.ptr ? a.y.ptr + (long long)chain * a.y.chain_stride : nullptr;
+  const double* wp = a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr;
+  double ssp = 0.0, ssl = 0.0;
+  for (int r = 0; r < TG_K; ++r) {
+    const long long i = tile * TG_TILE + r * TG_NT + tid;
+    if (i < n) {
+      const double x = xg[i];
+      const double ri = x - (mup ? __ldg(mup + i) : 0.0);
+      double rn = 0.0, pe = 0.0;
+      if (i + 1 < n) {
+        rn = xg[i + 1] - (mup ? __ldg(mup + i + 1) : 0.0);
+        pe = a.pe ? __ldg(a.pe + i) : 0.0;
+      }
+      ssp = fma(__ldg(a.pd + i) * ri, ri, fma(2.0 * pe * ri, rn, ssp));
+      if (yp) {
+        const double q = __ldg(yp + i) - x;
+        ssl = fma((wp ? __ldg(wp + i) : 1.0) * q, q, ssl);
+      }
+    }
+  }
+  ssp = omc_warp_sum(ssp);
+  ssl = omc_warp_sum(ssl);
+  if (lane == 0) { s_red[warp] = ssp; s_red[TG_NW + warp] = ssl; }
+  __syncthreads();
+  if (tid == 0) {
+    double sp = 0.0, sl = 0.0;
+    for (int w = 0; w < TG_NW; ++w) { sp += s_red[w]; sl += s_red[TG_NW + w]; }
+    rec->part[0] = sp;
+    rec->part[1] = sl;
+    __threadfence();
+    const unsigned int dn = atomicAdd(&chain_done[chain], 1u);
+    s_last = (dn == (unsigned int)(T - 1)) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && tid < 32) {
+    __threadfence();
     double sp = 0.0, sl = 0.0;
     for (long long t = tid; t < T; t += 32) {
-      TileRec* r = recs + t * C + chain;
-      sp += ld_cg(&r->part[1]);
-      sl += ld_cg(&r->part[2]);
+      const RecB* r = recs + t * C + chain;
+      sp += ld_cg(&r->part[0]);
+      sl += ld_cg(&r->part[1]);
     }
     sp = omc_warp_sum(sp);
     sl = omc_warp_sum(sl);
@@ -587,9 +796,9 @@ __global__ void __launch_bounds__(TG_THREADS) tridiag_backward_kernel(omc_tridia
   }
 }
 
-__global__ void tridiag_ws_init_kernel(Workspace* ws, Layout L, int n_chains) {
-  // zero the header, the per-chain counters and every tile flag
-  const long long words = L.off_g / 8;
+__global__ void tridiag_ws_init_kernel(Workspace* ws, Layout L) {
+  // zero the header, the per-chain counters and every tile record (flags)
+  const long long words = L.off_flags_end / 8;
   unsigned long long* p = reinterpret_cast<unsigned long long*>(ws);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (long long)gridDim.x * blockDim.x)
     p[i] = 0ull;
@@ -616,6 +825,30 @@ int check_args(const omc_tridiag_nn_t* a, const char* who) {
   return 0;
 }
 
+constexpr int smem_doubles(bool general, bool debug, bool solve_kernel) {
+  int arrays = 3;
+  if (general) arrays += solve_kernel ? 3 : 2;
+  if (debug) arrays += 1;
+  return 4 + arrays * TG_TILE + 4;
+}
+
+template <bool GENERAL>
+int launch_forward(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
+  const int smem = smem_doubles(GENERAL, false, false) * 8;
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_forward_kernel<GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tg_forward_kernel<GENERAL><<<grid, TG_NT, smem, st>>>(a, ws, L);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+template <bool GENERAL, bool DEBUG>
+int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
+  const int smem = smem_doubles(GENERAL, DEBUG, true) * 8;
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_solve_kernel<GENERAL, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tg_solve_kernel<GENERAL, DEBUG><<<grid, TG_NT, smem, st>>>(a, ws, L);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -629,7 +862,7 @@ int omc_tridiag_workspace(int n_chains, long long n, long long* bytes) {
 int omc_tridiag_workspace_init(void* workspace, int n_chains, long long n, void* stream) {
   OMC_REQUIRE(workspace, "omc_tridiag_workspace_init: null workspace");
   const Layout L = make_layout(n_chains, n);
-  tridiag_ws_init_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Workspace*>(workspace), L, n_chains);
+  tridiag_ws_init_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Workspace*>(workspace), L);
   OMC_LAUNCH_CHECK();
   return 0;
 }
@@ -640,13 +873,12 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   const Layout L = make_layout(a->n_chains, a->n);
   const unsigned int grid = (unsigned int)(L.n_tiles * a->n_chains);
   Workspace* ws = reinterpret_cast<Workspace*>(a->workspace);
-  tridiag_forward_kernel<<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*a, ws, L);
-  OMC_LAUNCH_CHECK();
-  if (a->x) {
-    tridiag_backward_kernel<true><<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*a, ws, L);
-    OMC_LAUNCH_CHECK();
-  }
-  return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
+  const bool debug = a->debug_z || a->logdet || a->probe_l || a->probe_c || !a->x;
+  if (int rc = general ? launch_forward<true>(*a, ws, L, grid, st) : launch_forward<false>(*a, ws, L, grid, st)) return rc;
+  if (general) return debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
+  return debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
 }
 
 int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
@@ -654,7 +886,7 @@ int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
   OMC_REQUIRE(a->x, "omc_tridiag_quadforms: x missing");
   const Layout L = make_layout(a->n_chains, a->n);
   const unsigned int grid = (unsigned int)(L.n_tiles * a->n_chains);
-  tridiag_backward_kernel<false><<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*a, reinterpret_cast<Workspace*>(a->workspace), L);
+  tg_quadforms_kernel<<<grid, TG_NT, 0, (cudaStream_t)stream>>>(*a, reinterpret_cast<Workspace*>(a->workspace), L);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -91,8 +91,8 @@ def test_tridiag_draw_matches_oracle(n, C, irregular, weighted, with_mu):
         ssp = gmrf.tridiag_quadform(pd, pe, o["x"] - mu0) if n > 1 else pd[0] * (o["x"][0] - mu0[0]) ** 2
         np.testing.assert_allclose(out["ss_prior"][c].item(), ssp, rtol=1e-9)
         np.testing.assert_allclose(out["ss_lik"][c].item(), np.sum(w[c] * (y[c] - o["x"]) ** 2), rtol=1e-10)
-        np.testing.assert_allclose(ss2["ss_prior"][c].item(), out["ss_prior"][c].item(), rtol=1e-13)
-        np.testing.assert_allclose(ss2["ss_lik"][c].item(), out["ss_lik"][c].item(), rtol=1e-13)
+        np.testing.assert_allclose(ss2["ss_prior"][c].item(), out["ss_prior"][c].item(), rtol=1e-11)
+        np.testing.assert_allclose(ss2["ss_lik"][c].item(), out["ss_lik"][c].item(), rtol=1e-11)
 
 
 def test_tridiag_not_positive_definite_sets_status():
