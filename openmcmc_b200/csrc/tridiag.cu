@@ -11,27 +11,30 @@
 //   draw      g_i = f_i / u_i + z_i / sqrt(u_i)
 //   backward  x_i = g_i - m_i x_{i+1}
 // The reference runs these sequentially (1e6 dependent steps per chain).  Here a tile is 128 threads x 18 consecutive
-// elements, and two kernels do the work with ONE read of y each and no per-element scratch in HBM:
+// elements, and three kernels do the work with ONE read of y each and no per-element scratch in HBM:
 //
-//  tg_forward_kernel   pivots and forward solve as ONE projective linear recurrence on s_i = (p_i, p_{i-1}, h_i),
+//  tg_aggregate_kernel pivots and forward solve as ONE projective linear recurrence on s_i = (p_i, p_{i-1}, h_i),
 //                      u_i = p_i/p_{i-1}, f_i = h_i/p_{i-1}:   p_i = d_i p_{i-1} - e_{i-1}^2 p_{i-2},
 //                      h_i = b_i p_{i-1} - e_{i-1} h_{i-1}.  Element maps compose as 3x3 block-triangular matrices (7
-//                      entries, no divisions); thread aggregates -> CTA scan -> decoupled look-back over tiles (warp-wide
-//                      window).  Output: the exact (1/u, f) entering every thread's 18 elements (16 B per thread).
-//  tg_solve_kernel     re-runs the *sequential* recurrences on each thread's 18 elements from that boundary (so every
-//                      pivot / f / g comes from the reference's operation sequence), keeps g and m in registers, builds
-//                      the backward affine aggregate on the way, scans it (CTA + reverse look-back over tiles), then
-//                      walks back down producing x and both quadratic forms (x-mu0)'P(x-mu0), (y-x)'W(y-x) in the same
-//                      pass.  x leaves through shared memory with one bulk (TMA-engine) store per tile.
+//                      entries, no divisions); thread aggregates -> CTA scan.  Pure streaming: writes every thread's
+//                      exclusive prefix inside its tile (56 B per 18 elements) and the tile total.
+//  tg_tilescan_kernel  one warp per chain scans the tile totals -> the exact (u, f) entering every tile.
+//  tg_solve_kernel     draws the tile's normals while its TMA loads are in flight, forms the exact (1/u, f) entering each
+//                      thread's 18 elements, re-runs the *sequential* recurrences on them (so every pivot / f / g comes
+//                      from the reference's operation sequence), keeps g and m in registers, builds the backward affine
+//                      aggregate on the way, scans it (CTA + reverse decoupled look-back over tiles), then walks back
+//                      down producing x and both quadratic forms (x-mu0)'P(x-mu0), (y-x)'W(y-x) in the same pass.
+//                      x leaves through shared memory with one bulk (TMA-engine) store per tile.
 //
 // Tiles are staged global -> shared with cp.async.bulk (1-D, completion on an mbarrier); a thread's 18 elements sit at a
-// 144-byte stride, so 16-byte LDS/STS are bank-conflict free.  Work is handed out tile-major by an atomic ticket (tile t
-// of all chains, then t+1): predecessors are always running or done (deadlock-free look-back) and the chains read the
-// same tile of the shared P together (L2).  HBM traffic per chain-iteration: y twice (16n) + x once (8n) + boundaries
-// (1.8n) against the algorithmic 32n of SURVEY §8d.  DESIGN.md gives the op and byte accounting.
+// 144-byte stride, so 16-byte LDS/STS are bank-conflict free.  Work is tile-major (tile t of all chains, then t+1): the
+// chains read the same tile of the shared P together (L2), and in the solve kernel an atomic ticket guarantees that the
+// tiles a look-back waits on are running or done.  HBM traffic per chain-iteration: y twice (16n) + x once (8n) +
+// thread prefixes (6.2n) against the algorithmic 32n of SURVEY §8d.  DESIGN.md gives the op and byte accounting.
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"
+#include "omc_logtab.cuh"
 
 namespace {
 
@@ -42,12 +45,6 @@ constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per st
 constexpr int TG_PAIRS = TG_K / 2;
 constexpr unsigned FULL = 0xffffffffu;
 
-struct __align__(128) RecF {
-  unsigned long long flag;   // epoch*4 + {1: tile transfer matrix ready, 2: inclusive end state ready}
-  double t[7];               // tile transfer matrix (a b c d e f g), normalised
-  double u_end, f_end;       // pivot / forward-solve value of the tile's last element
-  double pad[6];
-};
 struct __align__(64) RecB {
   unsigned long long flag;   // epoch*4 + {1: affine aggregate ready, 2: x_first ready}
   double a, b;               // x_first = a * x_in + b   (x_in = first x of the next tile)
@@ -58,27 +55,30 @@ struct __align__(64) RecB {
 
 struct Workspace {
   unsigned long long epoch;
-  unsigned int ticket_f, ticket_b, done_b, pad0;
-  unsigned int pad[10];
-  // followed by: unsigned int chain_done[n_chains] (padded), RecF[n_tiles][n_chains], RecB[n_tiles][n_chains],
-  //              double2 bound[n_chains][n_tiles * TG_NT]
+  unsigned int ticket_b, done_b;
+  unsigned int pad[12];
+  // followed by: unsigned int chain_done[n_chains] (padded), RecB[n_tiles][n_chains],
+  //              tile totals double[n_tiles][n_chains][8], tile inputs double2[n_tiles][n_chains],
+  //              thread prefixes double[n_chains][n_tiles][7][TG_NT]
 };
 
 __host__ __device__ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  long long off_chain_done, off_recf, off_recb, off_bound, off_flags_end, total;
+  long long off_chain_done, off_recb, off_flags_end, off_tt, off_sin, off_ex, total;
   long long n_tiles;
 };
 __host__ __device__ inline Layout make_layout(int n_chains, long long n) {
   Layout L;
   L.n_tiles = (n + TG_TILE - 1) / TG_TILE;
+  const long long tc = L.n_tiles * n_chains;
   L.off_chain_done = sizeof(Workspace);
-  L.off_recf = align_up(L.off_chain_done + (long long)n_chains * sizeof(unsigned int), 128);
-  L.off_recb = L.off_recf + L.n_tiles * n_chains * (long long)sizeof(RecF);
-  L.off_flags_end = L.off_recb + L.n_tiles * n_chains * (long long)sizeof(RecB);
-  L.off_bound = align_up(L.off_flags_end, 128);
-  L.total = L.off_bound + align_up((long long)n_chains * L.n_tiles * TG_NT * 16, 128);
+  L.off_recb = align_up(L.off_chain_done + (long long)n_chains * sizeof(unsigned int), 128);
+  L.off_flags_end = L.off_recb + tc * (long long)sizeof(RecB);
+  L.off_tt = align_up(L.off_flags_end, 128);
+  L.off_sin = L.off_tt + tc * 64;
+  L.off_ex = align_up(L.off_sin + tc * 16, 128);
+  L.total = L.off_ex + tc * 7 * TG_NT * 8;
   return L;
 }
 
@@ -201,12 +201,12 @@ struct Stage {
   double* dst;
 };
 
-// Stage `cnt` arrays for the tile starting at element i_t.  Full interior tiles with 16-byte aligned sources go through
-// cp.async.bulk; everything else (last tile, odd alignments, absent arrays) through plain loads.  Ends with the data
-// visible to every thread.
+// Stage CNT arrays for the tile starting at element i_t.  Full interior tiles with 16-byte aligned sources go through
+// cp.async.bulk (issued here, completion on `bar`); everything else (last tile, odd alignments, absent arrays) through
+// plain loads.  Returns whether the bulk path was taken; stage_wait() makes the data visible to every thread.
 template <int CNT>
-__device__ __forceinline__ void stage_tile(const Stage (&st)[CNT], long long i_t, long long n, unsigned long long* bar,
-                                           int tid) {
+__device__ __forceinline__ bool stage_issue(const Stage (&st)[CNT], long long i_t, long long n, unsigned long long* bar,
+                                            int tid) {
   bool bulk = (i_t + TG_TILE < n);
 #pragma unroll
   for (int q = 0; q < CNT; ++q)
@@ -231,32 +231,83 @@ __device__ __forceinline__ void stage_tile(const Stage (&st)[CNT], long long i_t
       st[q].dst[j] = (st[q].src && i < st[q].limit) ? __ldg(st[q].src + i) : st[q].fill;
     }
   }
+  return bulk;
+}
+__device__ __forceinline__ void stage_wait(bool bulk, unsigned long long* bar) {
   if (bulk) mbar_wait(bar, 0);
   __syncthreads();
 }
 
-// two standard normals for elements (2*pair, 2*pair+1) of a chain: Philox block index = element pair index (position
-// based, so the draw does not depend on tiling or sharding); pairs beyond 2^20 spill into the second counter word.
+// ---------------------------------------------------------------------------------------------- normals
+// Two standard normals for elements (2*pair, 2*pair+1) of a chain from one Philox4x32-10 block; block index = element
+// pair index (position based, so the draw does not depend on tiling or sharding); pairs beyond 2^20 spill into the
+// second counter word.  Box-Muller in fp64 with purpose-built pieces (tools/rng_model.py is the numpy model):
+//   -ln U   : U = m 2^-(j+1) straight from the bits (j = leading zeros, m in [1,2) from the next 52 bits, no int->fp
+//             conversion); ln m = lc[i] + ln1p(m rc[i] - 1) with a 128-entry table on the top 7 mantissa bits and a
+//             degree-7 series (|m rc - 1| <= 2^-8); absolute error 2e-15
+//   radius  : sqrt(2E) = 2E * rsqrt(2E)
+//   angle   : uniform in the first octant from 52 bits (Taylor sin / cos to 1 ulp on [0, pi/4]), three more bits swap
+//             sin <-> cos and pick the two signs
 __device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
-                                            unsigned long long pair, double& z0, double& z1) {
+                                            unsigned long long pair, const double2* __restrict__ slog, double& z0,
+                                            double& z1) {
   uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
                          (site << 20) | (unsigned int)(pair & 0xFFFFFu));
   const uint4 b = philox4x32_10(ctr, key);
-  const double u1 = omc_u01(b.x, b.y), u2 = omc_u01(b.z, b.w);
-  const double rad = sqrt(-2.0 * log(u1));
-  double s, c;
-  sincospi(2.0 * u2, &s, &c);
-  z0 = rad * c;
-  z1 = rad * s;
+  // ---- radius
+  const unsigned long long r = ((unsigned long long)b.y << 32) | b.x;
+  const int j = __clzll((long long)r);
+  const unsigned long long sh = (j >= 63) ? 0ull : (r << (j + 1));
+  const unsigned long long mb = sh >> 12;
+  const double2 tab = slog[(int)(mb >> 45)];
+  const double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mb));
+  const double rr = fma(mm, tab.x, -1.0);
+  double p = fma(rr, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(p, rr, 1.0 / 5.0);
+  p = fma(p, rr, -1.0 / 4.0);
+  p = fma(p, rr, 1.0 / 3.0);
+  p = fma(p, rr, -1.0 / 2.0);
+  p = fma(p, rr, 1.0);
+  const double lnm = fma(p, rr, tab.y);
+  double e2 = 2.0 * fma((double)(j + 1), 0.6931471805599453094, -lnm);   // 2E = -2 ln U
+  e2 = fmax(e2, 1e-300);
+  const double rad = e2 * fast_rsqrt(e2);
+  // ---- angle
+  const unsigned long long ab = ((unsigned long long)b.w << 32) | b.z;
+  const double fr = __longlong_as_double((long long)(0x3FF0000000000000ull | (ab >> 12))) - 1.0;
+  const double phi = fr * 0.78539816339744830962;
+  const double x2 = phi * phi;
+  double ps = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+  ps = fma(ps, x2, -1.0 / 39916800.0);
+  ps = fma(ps, x2, 1.0 / 362880.0);
+  ps = fma(ps, x2, -1.0 / 5040.0);
+  ps = fma(ps, x2, 1.0 / 120.0);
+  ps = fma(ps, x2, -1.0 / 6.0);
+  ps = fma(ps, x2, 1.0);
+  double pc = fma(x2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
+  pc = fma(pc, x2, 1.0 / 479001600.0);
+  pc = fma(pc, x2, -1.0 / 3628800.0);
+  pc = fma(pc, x2, 1.0 / 40320.0);
+  pc = fma(pc, x2, -1.0 / 720.0);
+  pc = fma(pc, x2, 1.0 / 24.0);
+  pc = fma(pc, x2, -0.5);
+  pc = fma(pc, x2, 1.0);
+  ps *= phi;
+  const bool swp = b.z & 1u;
+  const double cs = swp ? ps : pc, sn = swp ? pc : ps;
+  double a0 = rad * cs, a1 = rad * sn;
+  // signs: XOR the sign bit
+  a0 = __hiloint2double(__double2hiint(a0) ^ (int)((b.z & 2u) << 30), __double2loint(a0));
+  a1 = __hiloint2double(__double2hiint(a1) ^ (int)((b.z & 4u) << 29), __double2loint(a1));
+  z0 = a0;
+  z1 = a1;
 }
 
-// ---------------------------------------------------------------------------------------------- forward kernel
+// ---------------------------------------------------------------------------------------------- aggregate kernel
 template <bool GENERAL>
-__global__ void __launch_bounds__(TG_NT) tg_forward_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+__global__ void __launch_bounds__(TG_NT) tg_aggregate_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   extern __shared__ __align__(128) double sm[];
-  __shared__ unsigned int s_ticket;
   __shared__ double s_tot[TG_NW][7];
-  __shared__ double s_in[2];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
   double* spd = spe + TG_TILE;
@@ -264,38 +315,33 @@ __global__ void __launch_bounds__(TG_NT) tg_forward_kernel(omc_tridiag_nn_t a, W
   double* sw = sy + TG_TILE;       // GENERAL only
   double* sh = sw + TG_TILE;       // GENERAL only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
   if (tid == 0) {
-    s_ticket = atomicAdd(&ws->ticket_f, 1u);
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const long long work = s_ticket;
   const int C = a.n_chains;
-  const long long tile = work / C;     // tile-major: the chains read the same tile of the shared P together
-  const int chain = (int)(work % C);
+  const long long tile = blockIdx.x / C;     // tile-major: the chains read the same tile of the shared P together
+  const int chain = (int)(blockIdx.x % C);
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
-  RecF* recs = reinterpret_cast<RecF*>(wsb + L.off_recf);
-  RecF* rec = recs + tile * C + chain;
-  const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
   const long long i_t = tile * TG_TILE;
   const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
   const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
 
   const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
+  if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+  bool bulk;
   if (GENERAL) {
     const Stage st[5] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
                          {a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, n, 1.0, sw},
                          {a.h.ptr ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr, n, 0.0, sh}};
-    if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
-    stage_tile<5>(st, i_t, n, bar, tid);
+    bulk = stage_issue<5>(st, i_t, n, bar, tid);
   } else {
     const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
-    if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
-    stage_tile<3>(st, i_t, n, bar, tid);
+    bulk = stage_issue<3>(st, i_t, n, bar, tid);
   }
+  stage_wait(bulk, bar);
 
   // ---- thread aggregate over its 18 elements (no divisions)
   const int j0 = tid * TG_K;
@@ -353,77 +399,66 @@ __global__ void __launch_bounds__(TG_NT) tg_forward_kernel(omc_tridiag_nn_t a, W
   if (lane == 0) ex = tm_identity();
   ex = tm_mul(ex, wex);       // exclusive prefix of this thread inside the tile
   tm_normalize(ex);
-
-  // ---- decoupled look-back over the tiles of this chain (warp 0, 32 predecessors per round)
-  if (warp == 0) {
-    TM tot = tm_identity();
-#pragma unroll
-    for (int w = 0; w < TG_NW; ++w) {
-      const TM ww{s_tot[w][0], s_tot[w][1], s_tot[w][2], s_tot[w][3], s_tot[w][4], s_tot[w][5], s_tot[w][6]};
-      tot = tm_mul(ww, tot);
-    }
+  {
+    double* exg = reinterpret_cast<double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + tile) * 7 * TG_NT + tid;
+    exg[0 * TG_NT] = ex.a; exg[1 * TG_NT] = ex.b; exg[2 * TG_NT] = ex.c; exg[3 * TG_NT] = ex.d;
+    exg[4 * TG_NT] = ex.e; exg[5 * TG_NT] = ex.f; exg[6 * TG_NT] = ex.g;
+  }
+  if (tid == TG_NT - 1) {     // tile total = the last thread's inclusive prefix
+    TM tot = tm_mul(inc, wex);
     tm_normalize(tot);
-    double su = 1.0, sf = 0.0;   // state (u, f) with q = 1 at the far end of the walk (virtual tile -1: u = 1, f = 0)
-    TM R = tm_identity();        // composition of the aggregates between that state and this tile
-    if (tile > 0) {
-      if (lane == 0) {
-        rec->t[0] = tot.a; rec->t[1] = tot.b; rec->t[2] = tot.c; rec->t[3] = tot.d;
-        rec->t[4] = tot.e; rec->t[5] = tot.f; rec->t[6] = tot.g;
-        st_release(&rec->flag, FLAG_A);
-      }
-      long long base = tile - 1;
-      while (true) {
-        const long long j = base - lane;
-        unsigned long long fl = FLAG_P;   // tiles before the first: inclusive state (1, 0)
-        const RecF* pr = nullptr;
-        if (j >= 0) {
-          pr = recs + j * C + chain;
-          do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
-        }
-        const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
-        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
-        TM mine = tm_identity();
-        double pu = 1.0, pf = 0.0;
-        if (pr) {
-          if (lane == lp) {
-            pu = ld_cg(&pr->u_end);
-            pf = ld_cg(&pr->f_end);
-          } else if (lane < lp) {
-            mine = TM{ld_cg(&pr->t[0]), ld_cg(&pr->t[1]), ld_cg(&pr->t[2]), ld_cg(&pr->t[3]), ld_cg(&pr->t[4]),
-                      ld_cg(&pr->t[5]), ld_cg(&pr->t[6])};
-          }
-        }
-        for (int l = 0; l < lp; ++l) {
-          R = tm_mul(R, tm_shfl(mine, l));
-          if ((l & 3) == 3) tm_normalize(R);
-        }
-        tm_normalize(R);
-        if (lp < 32) {
-          su = shfl_d(pu, lp);
-          sf = shfl_d(pf, lp);
-          break;
-        }
-        base -= 32;
-      }
-    }
-    const double p1 = fma(R.a, su, R.b), q1 = fma(R.c, su, R.d), h1 = fma(R.e, su, fma(R.g, sf, R.f));
-    const double u_in = p1 / q1, f_in = h1 / q1;
-    const double p2 = fma(tot.a, u_in, tot.b), q2 = fma(tot.c, u_in, tot.d), h2 = fma(tot.e, u_in, fma(tot.g, f_in, tot.f));
-    if (lane == 0) {
-      rec->u_end = p2 / q2;
-      rec->f_end = h2 / q2;
-      st_release(&rec->flag, FLAG_P);
-      s_in[0] = u_in;
-      s_in[1] = f_in;
+    double* tt = reinterpret_cast<double*>(wsb + L.off_tt) + (tile * C + chain) * 8;
+    tt[0] = tot.a; tt[1] = tot.b; tt[2] = tot.c; tt[3] = tot.d; tt[4] = tot.e; tt[5] = tot.f; tt[6] = tot.g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- tile scan kernel
+// One warp per chain: exclusive scan of the tile totals -> (u, f) entering every tile.
+__global__ void __launch_bounds__(128) tg_tilescan_kernel(Workspace* ws, Layout L, int C) {
+  const int lane = threadIdx.x & 31;
+  const int chain = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (chain >= C) return;
+  char* wsb = reinterpret_cast<char*>(ws);
+  const double* tt = reinterpret_cast<const double*>(wsb + L.off_tt);
+  double2* sin_ = reinterpret_cast<double2*>(wsb + L.off_sin);
+  const long long T = L.n_tiles;
+  const long long per = (T + 31) / 32;
+  TM agg = tm_identity();
+  for (long long q = 0; q < per; ++q) {
+    const long long t = lane * per + q;
+    if (t < T) {
+      const double* p = tt + (t * C + chain) * 8;
+      agg = tm_mul(TM{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}, agg);
+      tm_normalize(agg);
     }
   }
-  __syncthreads();
-  // ---- boundary values entering this thread's elements: 1/u_{i0-1} and f_{i0-1}
+  TM inc = agg;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const TM o = tm_shfl_up(inc, d);
+    if (lane >= d) {
+      inc = tm_mul(inc, o);
+      tm_normalize(inc);
+    }
+  }
+  TM ex = tm_shfl_up(inc, 1);
+  if (lane == 0) ex = tm_identity();
+  // state entering the lane's first tile, from the initial state (u, q, f) = (1, 1, 0)
+  double u, f;
   {
-    const double u_in = s_in[0], f_in = s_in[1];
-    const double p = fma(ex.a, u_in, ex.b), q = fma(ex.c, u_in, ex.d), h = fma(ex.e, u_in, fma(ex.g, f_in, ex.f));
-    double2* bound = reinterpret_cast<double2*>(wsb + L.off_bound) + ((long long)chain * L.n_tiles + tile) * TG_NT;
-    bound[tid] = make_double2(q / p, h / q);
+    const double p0 = ex.a + ex.b, q0 = ex.c + ex.d, h0 = ex.e + ex.f;
+    u = p0 / q0;
+    f = h0 / q0;
+  }
+  for (long long q = 0; q < per; ++q) {
+    const long long t = lane * per + q;
+    if (t < T) {
+      sin_[t * C + chain] = make_double2(u, f);
+      const double* p = tt + (t * C + chain) * 8;
+      const double pp = fma(p[0], u, p[1]), qq = fma(p[2], u, p[3]), hh = fma(p[4], u, fma(p[6], f, p[5]));
+      u = pp / qq;
+      f = hh / qq;
+    }
   }
 }
 
@@ -435,16 +470,18 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
   extern __shared__ __align__(128) double sm[];
   __shared__ unsigned int s_ticket, s_last;
   __shared__ double s_red[2 * TG_NW + 4];
+  __shared__ double s_ld[TG_NW];
   __shared__ double s_xin;
   __shared__ int s_bad;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
   double* spd = spe + TG_TILE;
   double* sy = spd + TG_TILE;
-  double* sw = sy + TG_TILE;                 // GENERAL
+  double* sz = sy + TG_TILE;                 // normals (generated here, or the injected debug_z tile)
+  double2* slog = reinterpret_cast<double2*>(sz + TG_TILE);   // 128 x (rc, lc)
+  double* sw = sz + TG_TILE + 256;           // GENERAL
   double* sh = sw + TG_TILE;                 // GENERAL
   double* smu = sh + TG_TILE;                // GENERAL (TG_TILE + 2: mu0 of the next tile's first element)
-  double* sz = GENERAL ? smu + TG_TILE + 2 : sy + TG_TILE;   // DEBUG
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
   if (tid == 0) {
@@ -453,6 +490,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  slog[tid] = reinterpret_cast<const double2*>(omc_logtab)[tid];
   __syncthreads();
   const long long work = s_ticket;
   const int C = a.n_chains;
@@ -469,67 +507,93 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
   const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
   const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
   const bool solve = !DEBUG || a.x != nullptr;
+  const bool inject = DEBUG && a.debug_z != nullptr;
+  const int j0 = tid * TG_K;
+  const long long i0 = i_t + j0;
+  const int nvalid = (int)max(0ll, min((long long)TG_K, n - i0));   // this thread's elements inside the chain
 
   const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
+  bool bulk;
   {
     const double* wp = (GENERAL && a.w.ptr) ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr;
     const double* hp = (GENERAL && a.h.ptr) ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr;
     const double* mp = (GENERAL && a.mu0.ptr) ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
-    const double* zp = nullptr;
-    if (DEBUG && a.debug_z) {
-      const long long sw_ = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
-      zp = a.debug_z + sw_ * a.debug_sweep_stride + (long long)chain * n;
-    }
     if (tid == 0) {
       spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
       if (GENERAL) smu[TG_TILE] = (mp && i_t + TG_TILE < n) ? __ldg(mp + i_t + TG_TILE) : 0.0;
     }
-    if (GENERAL && DEBUG) {
-      const Stage st[7] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
-                           {hp, n, 0.0, sh}, {mp, n, 0.0, smu}, {zp, n, 0.0, sz}};
-      stage_tile<7>(st, i_t, n, bar, tid);
+    if (DEBUG) {
+      const double* zp = nullptr;
+      if (inject) {
+        const long long sw_ = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+        zp = a.debug_z + sw_ * a.debug_sweep_stride + (long long)chain * n;
+      }
+      if (GENERAL) {
+        const Stage st[7] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
+                             {hp, n, 0.0, sh}, {mp, n, 0.0, smu}, {zp, inject ? n : 0, 0.0, sz}};
+        bulk = stage_issue<7>(st, i_t, n, bar, tid);
+      } else {
+        const Stage st[4] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
+                             {zp, inject ? n : 0, 0.0, sz}};
+        bulk = stage_issue<4>(st, i_t, n, bar, tid);
+      }
     } else if (GENERAL) {
       const Stage st[6] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
                            {hp, n, 0.0, sh}, {mp, n, 0.0, smu}};
-      stage_tile<6>(st, i_t, n, bar, tid);
-    } else if (DEBUG) {
-      const Stage st[4] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {zp, n, 0.0, sz}};
-      stage_tile<4>(st, i_t, n, bar, tid);
+      bulk = stage_issue<6>(st, i_t, n, bar, tid);
     } else {
       const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
-      stage_tile<3>(st, i_t, n, bar, tid);
+      bulk = stage_issue<3>(st, i_t, n, bar, tid);
     }
   }
+  // ---- this thread's 18 normals, drawn while the tile loads are in flight (each thread reads back only its own)
+  if (!inject) {
+    if (DEBUG) __syncthreads();   // the generic fill of sz above (other threads' stores) must not land after ours
+    if (solve && nvalid > 0) {
+      const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
+      const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
+      const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
+#pragma unroll 3
+      for (int c = 0; c < TG_PAIRS; ++c) {
+        double2 z2;
+        normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), slog, z2.x, z2.y);
+        *reinterpret_cast<double2*>(sz + j0 + 2 * c) = z2;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < TG_PAIRS; ++c) *reinterpret_cast<double2*>(sz + j0 + 2 * c) = make_double2(0.0, 0.0);
+    }
+  }
+  // ---- exact boundary values entering this thread's elements: 1/u_{i0-1} and f_{i0-1}
+  double iu_prev, f_prev;
+  {
+    const double2 sin_ = reinterpret_cast<const double2*>(wsb + L.off_sin)[tile * C + chain];
+    const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * T + tile) * 7 * TG_NT + tid;
+    const double ea = exg[0], eb = exg[TG_NT], ec = exg[2 * TG_NT], ed = exg[3 * TG_NT], ee = exg[4 * TG_NT],
+                 ef = exg[5 * TG_NT], eg = exg[6 * TG_NT];
+    const double p = fma(ea, sin_.x, eb), q = fma(ec, sin_.x, ed), h = fma(ee, sin_.x, fma(eg, sin_.y, ef));
+    iu_prev = q / p;
+    f_prev = h / q;
+  }
+  stage_wait(bulk, bar);
 
-  // ---- ascending pass: the sequential recurrences on this thread's 18 elements from the exact boundary values
-  const int j0 = tid * TG_K;
-  const long long i0 = i_t + j0;
+  // ---- ascending pass: the sequential recurrences on this thread's 18 elements
   double g[TG_K], m[TG_K];
   Aff bagg{1.0, 0.0};          // x_{i0} = bagg.a * x_{i0+18} + bagg.b
   bool bad = false;
   double logdet = 0.0;
   {
-    const double2 bnd = reinterpret_cast<const double2*>(wsb + L.off_bound)[((long long)chain * T + tile) * TG_NT + tid];
-    double iu_prev = bnd.x, f_prev = bnd.y;
     double eprev = lam * spe[j0 - 1];
-    const unsigned long long sweep = (!DEBUG || !a.debug_z) ? (a.rng.sweep ? *a.rng.sweep : 0ull) : 0ull;
-    const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
-    const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
-    const bool use_rng = solve && !(DEBUG && a.debug_z) && (i0 < n);
 #pragma unroll
     for (int c = 0; c < TG_PAIRS; ++c) {
       const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
       const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
       const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
-      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0), z2 = make_double2(0.0, 0.0);
+      const double2 z2 = *reinterpret_cast<const double2*>(sz + j0 + 2 * c);
+      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0);
       if (GENERAL) {
         w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
         h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
-      }
-      if (DEBUG && a.debug_z) {
-        z2 = *reinterpret_cast<const double2*>(sz + j0 + 2 * c);
-      } else if (use_rng) {
-        normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), z2.x, z2.y);
       }
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
@@ -540,7 +604,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
         const double dd = fma(lam, pdk, tw);
         const double bb = GENERAL ? fma(lam, hk, tw * yk) : tw * yk;
         const double u = fma(-(eprev * eprev), iu_prev, dd);
-        if (!(u > 0.0) && i0 + k < n) bad = true;
+        if (!(u > 0.0) && k < nvalid) bad = true;
         const double su = fast_rsqrt(u);
         const double iu = su * su;
         const double mp_ = eprev * iu_prev;
@@ -552,7 +616,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
         m[k] = mk;
         bagg.b = fma(bagg.a, gk, bagg.b);
         bagg.a = -(bagg.a * mk);
-        if (DEBUG && i0 + k < n) {
+        if (DEBUG && k < nvalid) {
           if (a.logdet) logdet += log(u);
           if (a.probe_l) a.probe_l[(long long)chain * n + i0 + k] = sqrt(u);
           if (a.probe_c && i0 + k < n - 1) a.probe_c[(long long)chain * (n - 1) + i0 + k] = e * su;
@@ -581,7 +645,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
     Aff lex{shfl_dn_d(inc.a, 1), shfl_dn_d(inc.b, 1)};
     if (lane == 31) lex = Aff{1.0, 0.0};
     const Aff bex = aff_mul(lex, wex);   // x_{i0+18} = bex.a * x_in + bex.b
-    // ---- reverse look-back over the tiles of this chain (warp 0)
+    // ---- reverse look-back over the tiles of this chain (warp 0, 32 successors per round)
     if (warp == 0) {
       Aff tot{1.0, 0.0};
 #pragma unroll
@@ -648,7 +712,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
         const double wk = hlf ? w2.y : w2.x, muk = hlf ? mu2.y : mu2.x;
         const double x = fma(-m[k], xn, g[k]);
         const double r = GENERAL ? x - muk : x;
-        if (i0 + k < n) {
+        if (k < nvalid) {
           ssp = fma(pdk * r, r, fma(2.0 * pek * r, rn, ssp));
           const double q = yk - x;
           ssl = GENERAL ? fma(wk * q, q, ssl) : fma(q, q, ssl);
@@ -677,7 +741,6 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
   if (DEBUG) logdet = omc_warp_sum(logdet);
   __syncthreads();
   if (lane == 0) { s_red[warp] = ssp; s_red[TG_NW + warp] = ssl; }
-  __shared__ double s_ld[TG_NW];
   if (DEBUG && lane == 0) s_ld[warp] = logdet;
   __syncthreads();
   if (tid == 0) {
@@ -711,12 +774,11 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
       chain_done[chain] = 0;
     }
   }
-  // ---- last CTA of the launch re-arms the ticket counters and advances the epoch
+  // ---- last CTA of the launch re-arms the ticket counter and advances the epoch
   if (tid == 0) {
     __threadfence();
     const unsigned int dn = atomicAdd(&ws->done_b, 1u);
     if (dn == (unsigned int)(T * C - 1)) {
-      ws->ticket_f = 0;
       ws->ticket_b = 0;
       ws->done_b = 0;
       ws->epoch = epoch + 1;
@@ -825,24 +887,20 @@ int check_args(const omc_tridiag_nn_t* a, const char* who) {
   return 0;
 }
 
-constexpr int smem_doubles(bool general, bool debug, bool solve_kernel) {
-  int arrays = 3;
-  if (general) arrays += solve_kernel ? 3 : 2;
-  if (debug) arrays += 1;
-  return 4 + arrays * TG_TILE + 4;
-}
+constexpr int aggregate_smem_doubles(bool general) { return 4 + (general ? 5 : 3) * TG_TILE + 4; }
+constexpr int solve_smem_doubles(bool general) { return 4 + 4 * TG_TILE + 256 + (general ? 3 * TG_TILE + 2 : 0) + 2; }
 
 template <bool GENERAL>
-int launch_forward(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
-  const int smem = smem_doubles(GENERAL, false, false) * 8;
-  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_forward_kernel<GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tg_forward_kernel<GENERAL><<<grid, TG_NT, smem, st>>>(a, ws, L);
+int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
+  const int smem = aggregate_smem_doubles(GENERAL) * 8;
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_aggregate_kernel<GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tg_aggregate_kernel<GENERAL><<<grid, TG_NT, smem, st>>>(a, ws, L);
   OMC_LAUNCH_CHECK();
   return 0;
 }
 template <bool GENERAL, bool DEBUG>
 int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
-  const int smem = smem_doubles(GENERAL, DEBUG, true) * 8;
+  const int smem = solve_smem_doubles(GENERAL) * 8;
   OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_solve_kernel<GENERAL, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tg_solve_kernel<GENERAL, DEBUG><<<grid, TG_NT, smem, st>>>(a, ws, L);
   OMC_LAUNCH_CHECK();
@@ -876,7 +934,9 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
   const bool debug = a->debug_z || a->logdet || a->probe_l || a->probe_c || !a->x;
-  if (int rc = general ? launch_forward<true>(*a, ws, L, grid, st) : launch_forward<false>(*a, ws, L, grid, st)) return rc;
+  if (int rc = general ? launch_aggregate<true>(*a, ws, L, grid, st) : launch_aggregate<false>(*a, ws, L, grid, st)) return rc;
+  tg_tilescan_kernel<<<(a->n_chains * 32 + 127) / 128, 128, 0, st>>>(ws, L, a->n_chains);
+  OMC_LAUNCH_CHECK();
   if (general) return debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
   return debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
 }
