@@ -55,7 +55,7 @@ struct __align__(64) RecB {
 
 struct Workspace {
   unsigned long long epoch;
-  unsigned int ticket_b, done_b;
+  unsigned int done_b, pad0;
   unsigned int pad[12];
   // followed by: unsigned int chain_done[n_chains] (padded), RecB[n_tiles][n_chains],
   //              tile totals double[n_tiles][n_chains][8], tile inputs double2[n_tiles][n_chains],
@@ -210,22 +210,22 @@ __device__ __forceinline__ bool stage_issue(const Stage (&st)[CNT], long long i_
   bool bulk = (i_t + TG_TILE < n);
 #pragma unroll
   for (int q = 0; q < CNT; ++q)
-    if (st[q].src) bulk = bulk && al16(st[q].src + i_t) && (i_t + TG_TILE <= st[q].limit);
+    if (st[q].dst && st[q].src) bulk = bulk && al16(st[q].src + i_t) && (i_t + TG_TILE <= st[q].limit);
   if (bulk) {
     if (tid == 0) {
       unsigned bytes = 0;
 #pragma unroll
       for (int q = 0; q < CNT; ++q)
-        if (st[q].src) bytes += TG_TILE * 8;
+        if (st[q].dst && st[q].src) bytes += TG_TILE * 8;
       mbar_expect_tx(bar, bytes);
 #pragma unroll
       for (int q = 0; q < CNT; ++q)
-        if (st[q].src) bulk_g2s(st[q].dst, st[q].src + i_t, TG_TILE * 8, bar);
+        if (st[q].dst && st[q].src) bulk_g2s(st[q].dst, st[q].src + i_t, TG_TILE * 8, bar);
     }
   }
 #pragma unroll
   for (int q = 0; q < CNT; ++q) {
-    if (st[q].src && bulk) continue;
+    if (!st[q].dst || (st[q].src && bulk)) continue;
     for (int j = tid; j < TG_TILE; j += TG_NT) {
       const long long i = i_t + j;
       st[q].dst[j] = (st[q].src && i < st[q].limit) ? __ldg(st[q].src + i) : st[q].fill;
@@ -249,8 +249,7 @@ __device__ __forceinline__ void stage_wait(bool bulk, unsigned long long* bar) {
 //   angle   : uniform in the first octant from 52 bits (Taylor sin / cos to 1 ulp on [0, pi/4]), three more bits swap
 //             sin <-> cos and pick the two signs
 __device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
-                                            unsigned long long pair, const double2* __restrict__ slog, double& z0,
-                                            double& z1) {
+                                            unsigned long long pair, double& z0, double& z1) {
   uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
                          (site << 20) | (unsigned int)(pair & 0xFFFFFu));
   const uint4 b = philox4x32_10(ctr, key);
@@ -259,7 +258,7 @@ __device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, un
   const int j = __clzll((long long)r);
   const unsigned long long sh = (j >= 63) ? 0ull : (r << (j + 1));
   const unsigned long long mb = sh >> 12;
-  const double2 tab = slog[(int)(mb >> 45)];
+  const double2 tab = __ldg(reinterpret_cast<const double2*>(omc_logtab) + (int)(mb >> 45));
   const double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mb));
   const double rr = fma(mm, tab.x, -1.0);
   double p = fma(rr, 1.0 / 7.0, -1.0 / 6.0);
@@ -413,19 +412,20 @@ __global__ void __launch_bounds__(TG_NT) tg_aggregate_kernel(omc_tridiag_nn_t a,
 }
 
 // ---------------------------------------------------------------------------------------------- tile scan kernel
-// One warp per chain: exclusive scan of the tile totals -> (u, f) entering every tile.
-__global__ void __launch_bounds__(128) tg_tilescan_kernel(Workspace* ws, Layout L, int C) {
-  const int lane = threadIdx.x & 31;
-  const int chain = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (chain >= C) return;
+// One CTA per chain: exclusive scan of the tile totals -> (u, f) entering every tile.
+constexpr int TS_NT = 256;
+__global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layout L, int C) {
+  __shared__ double s_tot[TS_NT / 32][7];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chain = blockIdx.x;
   char* wsb = reinterpret_cast<char*>(ws);
   const double* tt = reinterpret_cast<const double*>(wsb + L.off_tt);
   double2* sin_ = reinterpret_cast<double2*>(wsb + L.off_sin);
   const long long T = L.n_tiles;
-  const long long per = (T + 31) / 32;
+  const long long per = (T + TS_NT - 1) / TS_NT;
   TM agg = tm_identity();
   for (long long q = 0; q < per; ++q) {
-    const long long t = lane * per + q;
+    const long long t = tid * per + q;
     if (t < T) {
       const double* p = tt + (t * C + chain) * 8;
       agg = tm_mul(TM{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}, agg);
@@ -441,9 +441,21 @@ __global__ void __launch_bounds__(128) tg_tilescan_kernel(Workspace* ws, Layout 
       tm_normalize(inc);
     }
   }
+  if (lane == 31) {
+    s_tot[warp][0] = inc.a; s_tot[warp][1] = inc.b; s_tot[warp][2] = inc.c; s_tot[warp][3] = inc.d;
+    s_tot[warp][4] = inc.e; s_tot[warp][5] = inc.f; s_tot[warp][6] = inc.g;
+  }
+  __syncthreads();
+  TM wex = tm_identity();
+  for (int w = 0; w < warp; ++w) {
+    const TM ww{s_tot[w][0], s_tot[w][1], s_tot[w][2], s_tot[w][3], s_tot[w][4], s_tot[w][5], s_tot[w][6]};
+    wex = tm_mul(ww, wex);
+    tm_normalize(wex);
+  }
   TM ex = tm_shfl_up(inc, 1);
   if (lane == 0) ex = tm_identity();
-  // state entering the lane's first tile, from the initial state (u, q, f) = (1, 1, 0)
+  ex = tm_mul(ex, wex);
+  // state entering the thread's first tile, from the initial state (u, q, f) = (1, 1, 0)
   double u, f;
   {
     const double p0 = ex.a + ex.b, q0 = ex.c + ex.d, h0 = ex.e + ex.f;
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(128) tg_tilescan_kernel(Workspace* ws, Layout 
     f = h0 / q0;
   }
   for (long long q = 0; q < per; ++q) {
-    const long long t = lane * per + q;
+    const long long t = tid * per + q;
     if (t < T) {
       sin_[t * C + chain] = make_double2(u, f);
       const double* p = tt + (t * C + chain) * 8;
@@ -465,37 +477,29 @@ __global__ void __launch_bounds__(128) tg_tilescan_kernel(Workspace* ws, Layout 
 // ---------------------------------------------------------------------------------------------- solve kernel
 // GENERAL: diagonal weights w, prior-mean terms h = P mu0 and mu0 are staged too (absent ones are filled with 1 / 0).
 // DEBUG  : injected normals (debug_z), log-det / factor probes, and the factorisation-only mode (x == NULL).
+// Tiles are taken in blockIdx order, top tile first: the reverse look-back of a tile waits only on tiles with a LOWER
+// block index, which the hardware dispatches earlier (the usual assumption of single-pass scans).
 template <bool GENERAL, bool DEBUG>
-__global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+__global__ void __launch_bounds__(TG_NT, DEBUG ? 1 : (GENERAL ? 2 : 4))
+tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   extern __shared__ __align__(128) double sm[];
-  __shared__ unsigned int s_ticket, s_last;
-  __shared__ double s_red[2 * TG_NW + 4];
-  __shared__ double s_ld[TG_NW];
-  __shared__ double s_xin;
+  __shared__ double s_red[2 * TG_NW];
+  __shared__ double s_part[3 * TG_NW];
   __shared__ int s_bad;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
   double* spd = spe + TG_TILE;
   double* sy = spd + TG_TILE;
-  double* sz = sy + TG_TILE;                 // normals (generated here, or the injected debug_z tile)
-  double2* slog = reinterpret_cast<double2*>(sz + TG_TILE);   // 128 x (rc, lc)
-  double* sw = sz + TG_TILE + 256;           // GENERAL
-  double* sh = sw + TG_TILE;                 // GENERAL
-  double* smu = sh + TG_TILE;                // GENERAL (TG_TILE + 2: mu0 of the next tile's first element)
+  double* sz = sy + TG_TILE;                          // DEBUG: the injected debug_z tile
+  double* sw = DEBUG ? sz + TG_TILE : sz;             // GENERAL
+  double* sh = sw + TG_TILE;                          // GENERAL
+  double* smu = sh + TG_TILE;                         // GENERAL (TG_TILE + 2: mu0 of the next tile's first element)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
-  if (tid == 0) {
-    s_ticket = atomicAdd(&ws->ticket_b, 1u);
-    s_bad = 0;
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  slog[tid] = reinterpret_cast<const double2*>(omc_logtab)[tid];
-  __syncthreads();
-  const long long work = s_ticket;
   const int C = a.n_chains;
   const long long T = L.n_tiles;
-  const long long tile = T - 1 - work / C;   // top tiles first (reverse look-back); tile-major over the chains
+  const long long work = blockIdx.x;
+  const long long tile = T - 1 - work / C;   // top tiles first; tile-major over the chains
   const int chain = (int)(work % C);
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
@@ -504,67 +508,56 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
   unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
   const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
   const long long i_t = tile * TG_TILE;
-  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
-  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
   const bool solve = !DEBUG || a.x != nullptr;
   const bool inject = DEBUG && a.debug_z != nullptr;
   const int j0 = tid * TG_K;
   const long long i0 = i_t + j0;
   const int nvalid = (int)max(0ll, min((long long)TG_K, n - i0));   // this thread's elements inside the chain
 
-  const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
+  // ---- stage the tile (thread 0 issues the bulk copies; nobody waits yet)
   bool bulk;
   {
+    const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
     const double* wp = (GENERAL && a.w.ptr) ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr;
     const double* hp = (GENERAL && a.h.ptr) ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr;
     const double* mp = (GENERAL && a.mu0.ptr) ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
+    const double* zp = nullptr;
+    if (inject) {
+      const long long sw_ = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+      zp = a.debug_z + sw_ * a.debug_sweep_stride + (long long)chain * n;
+    }
     if (tid == 0) {
+      s_bad = 0;
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
       spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
       if (GENERAL) smu[TG_TILE] = (mp && i_t + TG_TILE < n) ? __ldg(mp + i_t + TG_TILE) : 0.0;
     }
-    if (DEBUG) {
-      const double* zp = nullptr;
-      if (inject) {
-        const long long sw_ = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
-        zp = a.debug_z + sw_ * a.debug_sweep_stride + (long long)chain * n;
-      }
-      if (GENERAL) {
-        const Stage st[7] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
-                             {hp, n, 0.0, sh}, {mp, n, 0.0, smu}, {zp, inject ? n : 0, 0.0, sz}};
-        bulk = stage_issue<7>(st, i_t, n, bar, tid);
-      } else {
-        const Stage st[4] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
-                             {zp, inject ? n : 0, 0.0, sz}};
-        bulk = stage_issue<4>(st, i_t, n, bar, tid);
-      }
-    } else if (GENERAL) {
-      const Stage st[6] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}, {wp, n, 1.0, sw},
-                           {hp, n, 0.0, sh}, {mp, n, 0.0, smu}};
-      bulk = stage_issue<6>(st, i_t, n, bar, tid);
-    } else {
-      const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
-      bulk = stage_issue<3>(st, i_t, n, bar, tid);
-    }
+    const Stage st[7] = {{a.pe, n - 1, 0.0, spe},
+                         {a.pd, n, 1.0, spd},
+                         {yp, n, 0.0, sy},
+                         {wp, n, 1.0, GENERAL ? sw : nullptr},
+                         {hp, n, 0.0, GENERAL ? sh : nullptr},
+                         {mp, n, 0.0, GENERAL ? smu : nullptr},
+                         {zp, n, 0.0, inject ? sz : nullptr}};
+    bulk = stage_issue<7>(st, i_t, n, bar, tid);
   }
-  // ---- this thread's 18 normals, drawn while the tile loads are in flight (each thread reads back only its own)
-  if (!inject) {
-    if (DEBUG) __syncthreads();   // the generic fill of sz above (other threads' stores) must not land after ours
-    if (solve && nvalid > 0) {
-      const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
-      const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
-      const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
-#pragma unroll 3
-      for (int c = 0; c < TG_PAIRS; ++c) {
-        double2 z2;
-        normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), slog, z2.x, z2.y);
-        *reinterpret_cast<double2*>(sz + j0 + 2 * c) = z2;
-      }
-    } else {
+  // ---- this thread's 18 normals, drawn into registers while the tile loads are in flight
+  double g[TG_K], m[TG_K];
+  if (!inject && solve && nvalid > 0) {
+    const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
+    const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
+    const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
 #pragma unroll
-      for (int c = 0; c < TG_PAIRS; ++c) *reinterpret_cast<double2*>(sz + j0 + 2 * c) = make_double2(0.0, 0.0);
-    }
+    for (int c = 0; c < TG_PAIRS; ++c)
+      normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), g[2 * c], g[2 * c + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < TG_K; ++k) g[k] = 0.0;
   }
   // ---- exact boundary values entering this thread's elements: 1/u_{i0-1} and f_{i0-1}
+  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
+  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
   double iu_prev, f_prev;
   {
     const double2 sin_ = reinterpret_cast<const double2*>(wsb + L.off_sin)[tile * C + chain];
@@ -575,10 +568,18 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
     iu_prev = q / p;
     f_prev = h / q;
   }
-  stage_wait(bulk, bar);
+  __syncthreads();               // mbarrier initialised, plain-load fills visible
+  if (bulk) mbar_wait(bar, 0);
+  if (inject) {
+#pragma unroll
+    for (int c = 0; c < TG_PAIRS; ++c) {
+      const double2 z2 = *reinterpret_cast<const double2*>(sz + j0 + 2 * c);
+      g[2 * c] = z2.x;
+      g[2 * c + 1] = z2.y;
+    }
+  }
 
   // ---- ascending pass: the sequential recurrences on this thread's 18 elements
-  double g[TG_K], m[TG_K];
   Aff bagg{1.0, 0.0};          // x_{i0} = bagg.a * x_{i0+18} + bagg.b
   bool bad = false;
   double logdet = 0.0;
@@ -589,7 +590,6 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
       const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
       const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
       const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
-      const double2 z2 = *reinterpret_cast<const double2*>(sz + j0 + 2 * c);
       double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0);
       if (GENERAL) {
         w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
       for (int hlf = 0; hlf < 2; ++hlf) {
         const int k = 2 * c + hlf;
         const double pdk = hlf ? pd2.y : pd2.x, pek = hlf ? pe2.y : pe2.x, yk = hlf ? y2.y : y2.x;
-        const double wk = hlf ? w2.y : w2.x, hk = hlf ? h2.y : h2.x, zk = hlf ? z2.y : z2.x;
+        const double wk = hlf ? w2.y : w2.x, hk = hlf ? h2.y : h2.x, zk = g[k];
         const double tw = GENERAL ? tau * wk : tau;
         const double dd = fma(lam, pdk, tw);
         const double bb = GENERAL ? fma(lam, hk, tw * yk) : tw * yk;
@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
   if (bad) s_bad = 1;
 
   double ssp = 0.0, ssl = 0.0;
+  bool bulk_out = false;
   if (solve) {
     // ---- CTA scan of the backward affine maps, from the top thread down; exclusive prefix = all HIGHER threads
     Aff inc = bagg;
@@ -641,58 +642,57 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
     if (lane == 0) { s_red[2 * warp] = inc.a; s_red[2 * warp + 1] = inc.b; }
     __syncthreads();
     Aff wex{1.0, 0.0};    // composition of the warps above this one
-    for (int w = TG_NW - 1; w > warp; --w) wex = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, wex);
+    Aff tot{1.0, 0.0};    // the whole tile
+#pragma unroll
+    for (int w = TG_NW - 1; w >= 0; --w) {
+      if (w == warp) wex = tot;
+      tot = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, tot);
+    }
     Aff lex{shfl_dn_d(inc.a, 1), shfl_dn_d(inc.b, 1)};
     if (lane == 31) lex = Aff{1.0, 0.0};
     const Aff bex = aff_mul(lex, wex);   // x_{i0+18} = bex.a * x_in + bex.b
-    // ---- reverse look-back over the tiles of this chain (warp 0, 32 successors per round)
-    if (warp == 0) {
-      Aff tot{1.0, 0.0};
-#pragma unroll
-      for (int w = TG_NW - 1; w >= 0; --w) tot = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, tot);
-      double xfar = 0.0;     // x beyond the last element is 0 (and its multiplier m_{n-1} is 0)
-      Aff R{1.0, 0.0};
-      if (tile < T - 1) {
-        if (lane == 0) {
-          rec->a = tot.a;
-          rec->b = tot.b;
-          st_release(&rec->flag, FLAG_A);
-        }
-        long long base = tile + 1;
-        while (true) {
-          const long long j = base + lane;
-          unsigned long long fl = FLAG_P;
-          const RecB* pr = nullptr;
-          if (j < T) {
-            pr = recs + j * C + chain;
-            do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
-          }
-          const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
-          const int lp = pmask ? (__ffs(pmask) - 1) : 32;
-          Aff mine{1.0, 0.0};
-          double px = 0.0;
-          if (pr) {
-            if (lane == lp) px = ld_cg(&pr->x_first);
-            else if (lane < lp) mine = Aff{ld_cg(&pr->a), ld_cg(&pr->b)};
-          }
-          for (int l = 0; l < lp; ++l) R = aff_mul(R, Aff{shfl_d(mine.a, l), shfl_d(mine.b, l)});
-          if (lp < 32) {
-            xfar = shfl_d(px, lp);
-            break;
-          }
-          base += 32;
-        }
+    // ---- reverse look-back over the tiles of this chain, 32 successors per round.  Every warp walks it for itself
+    //      (no CTA barrier, nobody idles); warp 0 publishes the tile's records.
+    double xfar = 0.0;     // x beyond the last element is 0 (and its multiplier m_{n-1} is 0)
+    Aff R{1.0, 0.0};
+    if (tile < T - 1) {
+      if (tid == 0) {
+        rec->a = tot.a;
+        rec->b = tot.b;
+        st_release(&rec->flag, FLAG_A);
       }
-      const double x_in = fma(R.a, xfar, R.b);
-      if (lane == 0) {
-        rec->x_first = fma(tot.a, x_in, tot.b);
-        st_release(&rec->flag, FLAG_P);
-        s_xin = x_in;
+      long long base = tile + 1;
+      while (true) {
+        const long long j = base + lane;
+        unsigned long long fl = FLAG_P;
+        const RecB* pr = nullptr;
+        if (j < T) {
+          pr = recs + j * C + chain;
+          do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
+        }
+        const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
+        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
+        Aff mine{1.0, 0.0};
+        double px = 0.0;
+        if (pr) {
+          if (lane == lp) px = ld_cg(&pr->x_first);
+          else if (lane < lp) mine = Aff{ld_cg(&pr->a), ld_cg(&pr->b)};
+        }
+        for (int l = 0; l < lp; ++l) R = aff_mul(R, Aff{shfl_d(mine.a, l), shfl_d(mine.b, l)});
+        if (lp < 32) {
+          xfar = shfl_d(px, lp);
+          break;
+        }
+        base += 32;
       }
     }
-    __syncthreads();
+    const double x_in = fma(R.a, xfar, R.b);
+    if (tid == 0) {
+      rec->x_first = fma(tot.a, x_in, tot.b);
+      st_release(&rec->flag, FLAG_P);
+    }
     // ---- descending pass: x and both quadratic forms; x overwrites y in shared memory
-    double xn = fma(bex.a, s_xin, bex.b);
+    double xn = fma(bex.a, x_in, bex.b);
     double rn = GENERAL ? xn - smu[j0 + TG_K] : xn;
 #pragma unroll
     for (int c = TG_PAIRS - 1; c >= 0; --c) {
@@ -723,11 +723,21 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
       }
       *reinterpret_cast<double2*>(sy + j0 + 2 * c) = x2;
     }
-    // ---- x tile: shared -> global (bulk store for full aligned tiles)
-    double* xg = a.x + (long long)chain * n + i_t;
-    const bool bulk_out = (i_t + TG_TILE <= n) && al16(xg);
+    bulk_out = (i_t + TG_TILE <= n) && al16(a.x + (long long)chain * n + i_t);
     if (bulk_out) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncthreads();
+  }
+  // ---- per-tile partial sums (fixed order: shuffle tree, then the 4 warps in order)
+  ssp = omc_warp_sum(ssp);
+  ssl = omc_warp_sum(ssl);
+  if (DEBUG) logdet = omc_warp_sum(logdet);
+  if (lane == 0) {
+    s_part[warp] = ssp;
+    s_part[TG_NW + warp] = ssl;
+    s_part[2 * TG_NW + warp] = logdet;
+  }
+  __syncthreads();
+  if (solve) {   // x tile: shared -> global (one bulk store for full aligned tiles)
+    double* xg = a.x + (long long)chain * n + i_t;
     if (bulk_out) {
       if (tid == 0) bulk_s2g(xg, sy, TG_TILE * 8);
     } else {
@@ -735,56 +745,48 @@ __global__ void __launch_bounds__(TG_NT) tg_solve_kernel(omc_tridiag_nn_t a, Wor
         if (i_t + j < n) xg[j] = sy[j];
     }
   }
-  // ---- per-tile partial sums (fixed order: shuffle tree, then the 4 warps in order)
-  ssp = omc_warp_sum(ssp);
-  ssl = omc_warp_sum(ssl);
-  if (DEBUG) logdet = omc_warp_sum(logdet);
-  __syncthreads();
-  if (lane == 0) { s_red[warp] = ssp; s_red[TG_NW + warp] = ssl; }
-  if (DEBUG && lane == 0) s_ld[warp] = logdet;
-  __syncthreads();
-  if (tid == 0) {
-    double sp = 0.0, sl = 0.0, ld = 0.0;
-    for (int w = 0; w < TG_NW; ++w) { sp += s_red[w]; sl += s_red[TG_NW + w]; if (DEBUG) ld += s_ld[w]; }
-    rec->part[0] = sp;
-    rec->part[1] = sl;
-    rec->part[2] = ld;
-    if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
-    __threadfence();
-    const unsigned int dn = atomicAdd(&chain_done[chain], 1u);
-    s_last = (dn == (unsigned int)(T - 1)) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last && tid < 32) {   // deterministic per-chain reduction of the tile partials
-    __threadfence();
-    double sp = 0.0, sl = 0.0, ld = 0.0;
-    for (long long t = tid; t < T; t += 32) {
-      const RecB* r = recs + t * C + chain;
-      sp += ld_cg(&r->part[0]);
-      sl += ld_cg(&r->part[1]);
-      ld += ld_cg(&r->part[2]);
-    }
-    sp = omc_warp_sum(sp);
-    sl = omc_warp_sum(sl);
-    ld = omc_warp_sum(ld);
-    if (tid == 0) {
-      if (solve && a.ss_prior) a.ss_prior[chain] = sp;
-      if (solve && a.ss_lik) a.ss_lik[chain] = sl;
-      if (DEBUG && a.logdet) a.logdet[chain] = ld;
-      chain_done[chain] = 0;
-    }
-  }
-  // ---- last CTA of the launch re-arms the ticket counter and advances the epoch
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int dn = atomicAdd(&ws->done_b, 1u);
-    if (dn == (unsigned int)(T * C - 1)) {
-      ws->ticket_b = 0;
-      ws->done_b = 0;
-      ws->epoch = epoch + 1;
+  if (warp == 0) {
+    unsigned int last = 0;
+    if (lane == 0) {
+      double sp = 0.0, sl = 0.0, ld = 0.0;
+      for (int w = 0; w < TG_NW; ++w) { sp += s_part[w]; sl += s_part[TG_NW + w]; ld += s_part[2 * TG_NW + w]; }
+      rec->part[0] = sp;
+      rec->part[1] = sl;
+      rec->part[2] = ld;
+      if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
       __threadfence();
+      last = (atomicAdd(&chain_done[chain], 1u) == (unsigned int)(T - 1)) ? 1u : 0u;
     }
-    if (solve) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
+    last = __shfl_sync(FULL, last, 0);
+    if (last) {   // deterministic per-chain reduction of the tile partials
+      __threadfence();
+      double sp = 0.0, sl = 0.0, ld = 0.0;
+      for (long long t = lane; t < T; t += 32) {
+        const RecB* r = recs + t * C + chain;
+        sp += ld_cg(&r->part[0]);
+        sl += ld_cg(&r->part[1]);
+        ld += ld_cg(&r->part[2]);
+      }
+      sp = omc_warp_sum(sp);
+      sl = omc_warp_sum(sl);
+      ld = omc_warp_sum(ld);
+      if (lane == 0) {
+        if (solve && a.ss_prior) a.ss_prior[chain] = sp;
+        if (solve && a.ss_lik) a.ss_lik[chain] = sl;
+        if (DEBUG && a.logdet) a.logdet[chain] = ld;
+        chain_done[chain] = 0;
+      }
+    }
+    // ---- last CTA of the launch advances the epoch
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(&ws->done_b, 1u) == (unsigned int)(T * C - 1)) {
+        ws->done_b = 0;
+        ws->epoch = epoch + 1;
+        __threadfence();
+      }
+      if (solve) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
+    }
   }
 }
 
@@ -888,7 +890,9 @@ int check_args(const omc_tridiag_nn_t* a, const char* who) {
 }
 
 constexpr int aggregate_smem_doubles(bool general) { return 4 + (general ? 5 : 3) * TG_TILE + 4; }
-constexpr int solve_smem_doubles(bool general) { return 4 + 4 * TG_TILE + 256 + (general ? 3 * TG_TILE + 2 : 0) + 2; }
+constexpr int solve_smem_doubles(bool general, bool debug) {
+  return 4 + (3 + (debug ? 1 : 0) + (general ? 3 : 0)) * TG_TILE + 4;
+}
 
 template <bool GENERAL>
 int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
@@ -900,7 +904,7 @@ int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, 
 }
 template <bool GENERAL, bool DEBUG>
 int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
-  const int smem = solve_smem_doubles(GENERAL) * 8;
+  const int smem = solve_smem_doubles(GENERAL, DEBUG) * 8;
   OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_solve_kernel<GENERAL, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tg_solve_kernel<GENERAL, DEBUG><<<grid, TG_NT, smem, st>>>(a, ws, L);
   OMC_LAUNCH_CHECK();
@@ -935,7 +939,7 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
   const bool debug = a->debug_z || a->logdet || a->probe_l || a->probe_c || !a->x;
   if (int rc = general ? launch_aggregate<true>(*a, ws, L, grid, st) : launch_aggregate<false>(*a, ws, L, grid, st)) return rc;
-  tg_tilescan_kernel<<<(a->n_chains * 32 + 127) / 128, 128, 0, st>>>(ws, L, a->n_chains);
+  tg_tilescan_kernel<<<a->n_chains, TS_NT, 0, st>>>(ws, L, a->n_chains);
   OMC_LAUNCH_CHECK();
   if (general) return debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
   return debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
