@@ -39,11 +39,17 @@
 namespace {
 
 constexpr int TG_K = 18;                   // consecutive elements per thread
-constexpr int TG_NT = 128;                 // threads per CTA
+#ifndef TG_NT_DEF
+#define TG_NT_DEF 128
+#endif
+constexpr int TG_NT = TG_NT_DEF;           // threads per CTA
 constexpr int TG_NW = TG_NT / 32;
 constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per staged array
 constexpr int TG_PAIRS = TG_K / 2;
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef TG_SOLVE_MINB
+#define TG_SOLVE_MINB (512 / TG_NT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
+#endif
 
 struct __align__(64) RecB {
   unsigned long long flag;   // epoch*4 + {1: affine aggregate ready, 2: x_first ready}
@@ -136,6 +142,12 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 }
 __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// issue-now read-only load: volatile asm keeps it where it is written (ahead of the RNG work that hides its latency)
+__device__ __forceinline__ double ld_nc_now(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ double ld_cg(const double* p) {
   double v;
@@ -242,24 +254,23 @@ __device__ __forceinline__ void stage_wait(bool bulk, unsigned long long* bar) {
 // Two standard normals for elements (2*pair, 2*pair+1) of a chain from one Philox4x32-10 block; block index = element
 // pair index (position based, so the draw does not depend on tiling or sharding); pairs beyond 2^20 spill into the
 // second counter word.  Box-Muller in fp64 with purpose-built pieces (tools/rng_model.py is the numpy model):
-//   -ln U   : U = m 2^-(j+1) straight from the bits (j = leading zeros, m in [1,2) from the next 52 bits, no int->fp
-//             conversion); ln m = lc[i] + ln1p(m rc[i] - 1) with a 128-entry table on the top 7 mantissa bits and a
-//             degree-7 series (|m rc - 1| <= 2^-8); absolute error 2e-15
+//   -ln U   : U = m 2^-(j+1) straight from the bits: j = leading zeros of word y (geometric), m in [1,2) from 52 further
+//             bits (no int->fp conversion); ln m = lc[i] + ln1p(m rc[i] - 1) with a 128-entry table on the top 7
+//             mantissa bits and a degree-7 series (|m rc - 1| <= 2^-8); absolute error 2e-15.  When y has 12 or more
+//             leading zeros (probability 2^-12) the bits below bit 20 are no longer free: the caller redoes the pair
+//             with normal_pair_slow (64-bit leading-zero count, mantissa = the bits right after the leading one).
 //   radius  : sqrt(2E) = 2E * rsqrt(2E)
 //   angle   : uniform in the first octant from 52 bits (Taylor sin / cos to 1 ulp on [0, pi/4]), three more bits swap
 //             sin <-> cos and pick the two signs
-__device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
-                                            unsigned long long pair, double& z0, double& z1) {
-  uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
-                         (site << 20) | (unsigned int)(pair & 0xFFFFFu));
-  const uint4 b = philox4x32_10(ctr, key);
+__device__ __forceinline__ uint4 normal_block(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
+                                              unsigned long long pair) {
+  const uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u,
+                               gchain, (site << 20) | (unsigned int)(pair & 0xFFFFFu));
+  return philox4x32_10(ctr, key);
+}
+__device__ __forceinline__ void normal_from(double jp1, double mm, int idx, uint4 b, double& z0, double& z1) {
   // ---- radius
-  const unsigned long long r = ((unsigned long long)b.y << 32) | b.x;
-  const int j = __clzll((long long)r);
-  const unsigned long long sh = (j >= 63) ? 0ull : (r << (j + 1));
-  const unsigned long long mb = sh >> 12;
-  const double2 tab = __ldg(reinterpret_cast<const double2*>(omc_logtab) + (int)(mb >> 45));
-  const double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mb));
+  const double2 tab = __ldg(reinterpret_cast<const double2*>(omc_logtab) + idx);
   const double rr = fma(mm, tab.x, -1.0);
   double p = fma(rr, 1.0 / 7.0, -1.0 / 6.0);
   p = fma(p, rr, 1.0 / 5.0);
@@ -268,12 +279,11 @@ __device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, un
   p = fma(p, rr, -1.0 / 2.0);
   p = fma(p, rr, 1.0);
   const double lnm = fma(p, rr, tab.y);
-  double e2 = 2.0 * fma((double)(j + 1), 0.6931471805599453094, -lnm);   // 2E = -2 ln U
-  e2 = fmax(e2, 1e-300);
+  const double en = fma(jp1, 0.6931471805599453094, -lnm);     // E = -ln U  (>= -2e-15)
+  const double e2 = fma(2.0, en, 0x1p-47);                     // 2E, kept strictly positive
   const double rad = e2 * fast_rsqrt(e2);
-  // ---- angle
-  const unsigned long long ab = ((unsigned long long)b.w << 32) | b.z;
-  const double fr = __longlong_as_double((long long)(0x3FF0000000000000ull | (ab >> 12))) - 1.0;
+  // ---- angle: 52 bits = low 20 of w : z
+  const double fr = __hiloint2double((int)((b.w & 0x000FFFFFu) | 0x3FF00000u), (int)b.z) - 1.0;
   const double phi = fr * 0.78539816339744830962;
   const double x2 = phi * phi;
   double ps = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
@@ -292,14 +302,30 @@ __device__ __forceinline__ void normal_pair(unsigned long long sw, uint2 key, un
   pc = fma(pc, x2, -0.5);
   pc = fma(pc, x2, 1.0);
   ps *= phi;
-  const bool swp = b.z & 1u;
+  const bool swp = (b.w >> 20) & 1u;
   const double cs = swp ? ps : pc, sn = swp ? pc : ps;
-  double a0 = rad * cs, a1 = rad * sn;
-  // signs: XOR the sign bit
-  a0 = __hiloint2double(__double2hiint(a0) ^ (int)((b.z & 2u) << 30), __double2loint(a0));
-  a1 = __hiloint2double(__double2hiint(a1) ^ (int)((b.z & 4u) << 29), __double2loint(a1));
-  z0 = a0;
-  z1 = a1;
+  const double a0 = rad * cs, a1 = rad * sn;
+  z0 = __hiloint2double(__double2hiint(a0) ^ (int)((b.w << 10) & 0x80000000u), __double2loint(a0));
+  z1 = __hiloint2double(__double2hiint(a1) ^ (int)((b.w << 9) & 0x80000000u), __double2loint(a1));
+}
+// fast path; returns false when the pair has to be redone by normal_pair_slow
+__device__ __forceinline__ bool normal_pair_fast(uint4 b, double& z0, double& z1) {
+  const int j = __clz((int)b.y);
+  const double mm = __hiloint2double((int)((b.y & 0x000FFFFFu) | 0x3FF00000u), (int)b.x);
+  normal_from((double)(j + 1), mm, (int)((b.y >> 13) & 127u), b, z0, z1);
+  return b.y >= (1u << 20);
+}
+__device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
+                                                 unsigned long long pair) {
+  const uint4 b = normal_block(sw, key, gchain, site, pair);
+  const unsigned long long r = ((unsigned long long)b.y << 32) | b.x;
+  const int j = __clzll((long long)r);
+  const unsigned long long sh = (j >= 63) ? 0ull : (r << (j + 1));
+  const unsigned long long mb = sh >> 12;
+  const double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mb));
+  double2 z;
+  normal_from((double)(j + 1), mm, (int)(mb >> 45), b, z.x, z.y);
+  return z;
 }
 
 // ---------------------------------------------------------------------------------------------- aggregate kernel
@@ -480,7 +506,7 @@ __global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layou
 // Tiles are taken in blockIdx order, top tile first: the reverse look-back of a tile waits only on tiles with a LOWER
 // block index, which the hardware dispatches earlier (the usual assumption of single-pass scans).
 template <bool GENERAL, bool DEBUG>
-__global__ void __launch_bounds__(TG_NT, DEBUG ? 1 : (GENERAL ? 2 : 4))
+__global__ void __launch_bounds__(TG_NT, DEBUG ? 1 : (GENERAL ? 2 : TG_SOLVE_MINB))
 tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   extern __shared__ __align__(128) double sm[];
   __shared__ double s_red[2 * TG_NW];
@@ -542,29 +568,44 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
                          {zp, n, 0.0, inject ? sz : nullptr}};
     bulk = stage_issue<7>(st, i_t, n, bar, tid);
   }
+  // ---- loads of the thread prefix / tile input / scalars go out now; their latency hides under the normals
+  const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * T + tile) * 7 * TG_NT + tid;
+  const double* sin_p = reinterpret_cast<const double*>(wsb + L.off_sin) + (tile * C + chain) * 2;
+  const double ea = ld_nc_now(exg), eb = ld_nc_now(exg + TG_NT), ec = ld_nc_now(exg + 2 * TG_NT),
+               ed = ld_nc_now(exg + 3 * TG_NT), ee = ld_nc_now(exg + 4 * TG_NT), ef = ld_nc_now(exg + 5 * TG_NT),
+               eg = ld_nc_now(exg + 6 * TG_NT);
+  const double sin_x = ld_nc_now(sin_p), sin_y = ld_nc_now(sin_p + 1);
+  const double lam = a.lambda.ptr ? ld_nc_now(a.lambda.ptr + (long long)chain * a.lambda.chain_stride) : 1.0;
+  const double tau = a.tau.ptr ? ld_nc_now(a.tau.ptr + (long long)chain * a.tau.chain_stride) : 1.0;
   // ---- this thread's 18 normals, drawn into registers while the tile loads are in flight
   double g[TG_K], m[TG_K];
   if (!inject && solve && nvalid > 0) {
     const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
     const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
     const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
+    const unsigned long long pair0 = (unsigned long long)(i0 >> 1);
+    unsigned int redo = 0;
 #pragma unroll
-    for (int c = 0; c < TG_PAIRS; ++c)
-      normal_pair(sweep, key, gchain, a.rng.site, (unsigned long long)((i0 >> 1) + c), g[2 * c], g[2 * c + 1]);
+    for (int c = 0; c < TG_PAIRS; ++c) {
+      const uint4 b = normal_block(sweep, key, gchain, a.rng.site, pair0 + c);
+      if (!normal_pair_fast(b, g[2 * c], g[2 * c + 1])) redo |= 1u << c;
+    }
+    while (redo) {   // probability 2^-12 per pair
+      const int c = __ffs(redo) - 1;
+      redo &= redo - 1;
+      const double2 z = normal_pair_slow(sweep, key, gchain, a.rng.site, pair0 + c);
+#pragma unroll
+      for (int cc = 0; cc < TG_PAIRS; ++cc)
+        if (cc == c) { g[2 * cc] = z.x; g[2 * cc + 1] = z.y; }
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < TG_K; ++k) g[k] = 0.0;
   }
   // ---- exact boundary values entering this thread's elements: 1/u_{i0-1} and f_{i0-1}
-  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
-  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
   double iu_prev, f_prev;
   {
-    const double2 sin_ = reinterpret_cast<const double2*>(wsb + L.off_sin)[tile * C + chain];
-    const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * T + tile) * 7 * TG_NT + tid;
-    const double ea = exg[0], eb = exg[TG_NT], ec = exg[2 * TG_NT], ed = exg[3 * TG_NT], ee = exg[4 * TG_NT],
-                 ef = exg[5 * TG_NT], eg = exg[6 * TG_NT];
-    const double p = fma(ea, sin_.x, eb), q = fma(ec, sin_.x, ed), h = fma(ee, sin_.x, fma(eg, sin_.y, ef));
+    const double p = fma(ea, sin_x, eb), q = fma(ec, sin_x, ed), h = fma(ee, sin_x, fma(eg, sin_y, ef));
     iu_prev = q / p;
     f_prev = h / q;
   }
@@ -579,12 +620,22 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     }
   }
 
-  // ---- ascending pass: the sequential recurrences on this thread's 18 elements
+  // ---- ascending pass over this thread's 18 elements.  The pivots run in scaled principal-minor form
+  //        P_k = (s d_k) P_{k-1} - (s e_{k-1})^2 P_{k-2},   u_k = P_k / (s P_{k-1}),   s = 4^r ~ 1/u  (exact scaling)
+  //      so that the only serial dependence is ONE fused multiply-add per element; 1/sqrt(u_k) = sqrt(s) P_{k-1} /
+  //      sqrt(P_k P_{k-1}) and everything built on it (1/u, m, g) is independent work across the 18 elements.
   Aff bagg{1.0, 0.0};          // x_{i0} = bagg.a * x_{i0+18} + bagg.b
   bool bad = false;
   double logdet = 0.0;
   {
+    int ex2 = (((__double2hiint(iu_prev) >> 20) & 0x7ff) - 1023) & ~1;
+    ex2 = max(-600, min(600, ex2));
+    const double s = __hiloint2double((1023 + ex2) << 20, 0);
+    const double rs = __hiloint2double((1023 + ex2 / 2) << 20, 0);
+    const double sl = s * lam, st = s * tau;
+    double pm1 = 1.0, pm2 = iu_prev * __hiloint2double((1023 - ex2) << 20, 0);
     double eprev = lam * spe[j0 - 1];
+    double mprev = eprev * iu_prev;
 #pragma unroll
     for (int c = 0; c < TG_PAIRS; ++c) {
       const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
@@ -595,20 +646,26 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
         w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
         h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
       }
+      if (c == 3 || c == 6) {   // keep the minors near 1 (exact power-of-two rescale)
+        const int exp_ = max(-900, min(900, ((__double2hiint(pm1) >> 20) & 0x7ff) - 1023));
+        const double sc = __hiloint2double((1023 - exp_) << 20, 0);
+        pm1 *= sc;
+        pm2 *= sc;
+      }
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
         const int k = 2 * c + hlf;
         const double pdk = hlf ? pd2.y : pd2.x, pek = hlf ? pe2.y : pe2.x, yk = hlf ? y2.y : y2.x;
         const double wk = hlf ? w2.y : w2.x, hk = hlf ? h2.y : h2.x, zk = g[k];
-        const double tw = GENERAL ? tau * wk : tau;
-        const double dd = fma(lam, pdk, tw);
-        const double bb = GENERAL ? fma(lam, hk, tw * yk) : tw * yk;
-        const double u = fma(-(eprev * eprev), iu_prev, dd);
-        if (!(u > 0.0) && k < nvalid) bad = true;
-        const double su = fast_rsqrt(u);
+        const double ds = GENERAL ? fma(sl, pdk, st * wk) : fma(sl, pdk, st);   // s d_k
+        const double bb = GENERAL ? fma(lam, hk, tau * wk * yk) : tau * yk;
+        const double es = s * eprev;                                            // s e_{k-1}
+        const double pk = fma(ds, pm1, -((es * es) * pm2));
+        const double tt = pk * pm1;
+        if (!(tt > 0.0)) bad = true;       // pivot u_k <= 0 (or NaN)
+        const double su = rs * (pm1 * fast_rsqrt(tt));
         const double iu = su * su;
-        const double mp_ = eprev * iu_prev;
-        const double f = fma(-mp_, f_prev, bb);
+        const double f = fma(-mprev, f_prev, bb);
         const double e = lam * pek;
         const double mk = e * iu;
         const double gk = fma(f, iu, zk * su);
@@ -617,19 +674,22 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
         bagg.b = fma(bagg.a, gk, bagg.b);
         bagg.a = -(bagg.a * mk);
         if (DEBUG && k < nvalid) {
+          const double u = 1.0 / iu;
           if (a.logdet) logdet += log(u);
           if (a.probe_l) a.probe_l[(long long)chain * n + i0 + k] = sqrt(u);
           if (a.probe_c && i0 + k < n - 1) a.probe_c[(long long)chain * (n - 1) + i0 + k] = e * su;
         }
-        iu_prev = iu;
+        pm2 = pm1;
+        pm1 = pk;
         f_prev = f;
         eprev = e;
+        mprev = mk;
       }
     }
   }
   if (bad) s_bad = 1;
 
-  double ssp = 0.0, ssl = 0.0;
+  double ssp = 0.0, ssp2 = 0.0, ssl = 0.0;
   bool bulk_out = false;
   if (solve) {
     // ---- CTA scan of the backward affine maps, from the top thread down; exclusive prefix = all HIGHER threads
@@ -713,7 +773,8 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
         const double x = fma(-m[k], xn, g[k]);
         const double r = GENERAL ? x - muk : x;
         if (k < nvalid) {
-          ssp = fma(pdk * r, r, fma(2.0 * pek * r, rn, ssp));
+          ssp = fma(pdk * r, r, ssp);
+          ssp2 = fma(pek * r, rn, ssp2);
           const double q = yk - x;
           ssl = GENERAL ? fma(wk * q, q, ssl) : fma(q, q, ssl);
         }
@@ -727,7 +788,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     if (bulk_out) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   // ---- per-tile partial sums (fixed order: shuffle tree, then the 4 warps in order)
-  ssp = omc_warp_sum(ssp);
+  ssp = omc_warp_sum(fma(2.0, ssp2, ssp));
   ssl = omc_warp_sum(ssl);
   if (DEBUG) logdet = omc_warp_sum(logdet);
   if (lane == 0) {

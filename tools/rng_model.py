@@ -41,20 +41,25 @@ def clz64(r):
     return np.where(r == 0, 64, n)
 
 
-def normal_pair(r, a):
+def normal_pair(r, a, fast=True):
+    """r = (y << 32) | x, a = (w << 32) | z of the Philox block.  fast=True models normal_pair_fast (valid when y has
+    fewer than 12 leading zeros; the device redoes the other pairs with the slow path), fast=False normal_pair_slow."""
     j = clz64(r)
     sh = np.where(j >= 63, np.uint64(0), r << np.minimum(j + 1, 63).astype(np.uint64))
     mb = sh >> np.uint64(12)
+    if fast:
+        slow = (r >> np.uint64(32)) < np.uint64(1 << 20)
+        mb_fast = r & np.uint64((1 << 52) - 1)          # low 20 bits of y : x
+        mb = np.where(slow, mb, mb_fast)
     idx = (mb >> np.uint64(45)).astype(np.int64)
     m = (np.uint64(0x3FF0000000000000) | mb).view(np.float64)
     rr = m * tab[idx, 0] - 1.0
     p = rr * horner(LC, rr)
     lnm = tab[idx, 1] + p
     E = (j + 1) * LN2 - lnm
-    E = np.maximum(E, 1e-300)
-    rad = np.sqrt(2 * E)
-    f = (np.uint64(0x3FF0000000000000) | (a >> np.uint64(12))).view(np.float64) - 1.0
-    bits = (a & np.uint64(7)).astype(np.int64)
+    rad = np.sqrt(2 * E + 2.0 ** -47)
+    f = (np.uint64(0x3FF0000000000000) | (a & np.uint64((1 << 52) - 1))).view(np.float64) - 1.0   # low 20 of w : z
+    bits = ((a >> np.uint64(52)) & np.uint64(7)).astype(np.int64)
     phi = f * (math.pi / 4)
     x2 = phi * phi
     s = phi * horner(SC, x2)
