@@ -353,6 +353,27 @@ def run_b200(args, wl, key):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    # ---- diagnostics of the timed draws: per-chain ESS on the device store, all-gather of the per-chain records over
+    #      the process group (NCCL over NVLink when N > 1), split-R-hat / ESS on every rank
+    from openmcmc_b200 import diagnostics as G
+
+    strides = {"b": max(1, n // 64)} if wl["kind"] == "gmrf" else None
+    d0 = torch.cuda.Event(enable_timing=True)
+    d1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(M.stream):
+        d0.record()
+    summ = G.summarize(M, elem_stride=strides)
+    with torch.cuda.stream(M.stream):
+        d1.record()
+    torch.cuda.synchronize()
+    ess_total = float(G.min_ess_per_chain(summ, all_ranks=True).sum().item())
+    rhat_max = max(float(torch.nan_to_num(v["rhat"], nan=1.0).max().item()) for v in summ.values())
+    ess = {"value": ess_total / (ms_max * 1e-3), "unit": "ESS/s", "n_stored": int(M.plan.iter_counter.item()),
+           "ess_total": ess_total, "rhat_max": rhat_max, "params": sorted(summ), "diag_ms": d0.elapsed_time(d1),
+           "gathered_chains": int(next(iter(summ.values()))["n_chains_total"]),
+           "note": "sum over all chains of the minimum-over-parameters autocorrelation ESS (Geyer) of the draws stored "
+                   "in the timed region, divided by the timed seconds; per-chain records all-gathered over the "
+                   "process group"}
     M.collect()
     status_bad = int(((M.status & 3) != 0).sum())
     accept = {s.param: s.accept_rate.get_acceptance_rate() for s in samplers if hasattr(s, "accept_rate")}
@@ -383,7 +404,7 @@ def run_b200(args, wl, key):
     # ---- e2e: public API with HOST (pinned) inputs, upload + K sweeps + sample download inside the timed region
     e2e = None
     if not args.no_e2e:
-        del M, op, state
+        del M, op, state, summ
         torch.cuda.empty_cache()
         mdl, samplers2, hstate = build(wl, C, n, dev, rank, host=True)
         torch.cuda.empty_cache()
@@ -424,7 +445,7 @@ def run_b200(args, wl, key):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
             "gpu_launches": launches_per_sweep * args.steps + store_launches * n_iter,
-            "roofline": roof, "cpu_baseline": cpu_baseline,
+            "roofline": roof, "cpu_baseline": cpu_baseline, "ess": ess,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

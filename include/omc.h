@@ -302,6 +302,25 @@ int omc_truncnorm_rv(const double* mean, const double* scale, const double* lowe
 int omc_truncnorm_logpdf(const double* x, const double* mean, const double* scale, const double* lower,
                          const double* upper, long long n, double* out, void* stream);
 
+/* ------------------------------------------------------------------ chain diagnostics (no reference
+ * counterpart: parity unpinned, numpy restatement in oracle/diagnostics.py)
+ * omc_chain_stats: per chain and selected element of a stored parameter, from the device sample store
+ *   samples [n_iter][n_chains][size] (written by omc_store_copy); selected elements j*elem_stride, j < n_sel.
+ *   out [n_chains][n_sel][8] = n, mean, variance (n-1), ESS (autocorrelation, Geyer initial monotone sequence, lags <=
+ *   min(max_lag,127)), first-half mean, first-half variance, second-half mean, second-half variance.
+ * omc_rhat_combine: split-R-hat and total ESS per selected element from the records of ALL chains (every rank's
+ *   records after the NCCL all-gather): out [n_sel][4] = R-hat, sum of chain ESS, grand mean, var+ . */
+typedef struct {
+  const double* samples;
+  long long n_iter;
+  int n_chains;
+  long long size, n_sel, elem_stride;
+  int max_lag;
+  double* out;
+} omc_chain_stats_t;
+int omc_chain_stats(const omc_chain_stats_t* args, void* stream);
+int omc_rhat_combine(const double* stats, int n_chains_total, int n_sel, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,6 +206,20 @@ PROTOTYPES = {
 }
 
 
+class ChainStats(C.Structure):
+    """omc_chain_stats_t"""
+
+    _fields_ = [("samples", C.c_void_p), ("n_iter", C.c_longlong), ("n_chains", C.c_int), ("size", C.c_longlong),
+                ("n_sel", C.c_longlong), ("elem_stride", C.c_longlong), ("max_lag", C.c_int), ("out", C.c_void_p)]
+
+
+PROTOTYPES.update({
+    "omc_chain_stats": (C.c_int, [C.POINTER(ChainStats), C.c_void_p]),
+    "omc_rhat_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+})
+EXTRA_STRUCTS = {"omc_chain_stats_t": ChainStats}
+
+
 def lib_path() -> str:
     """In-tree libomc.so; OMC_LIB overrides it (used only by tools/tune_reg_pass.sh to time kernel variants)."""
     return os.environ.get("OMC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
