@@ -373,7 +373,8 @@ def run_b200(args, wl, key):
            "gathered_chains": int(next(iter(summ.values()))["n_chains_total"]),
            "note": "sum over all chains of the minimum-over-parameters autocorrelation ESS (Geyer) of the draws stored "
                    "in the timed region, divided by the timed seconds; per-chain records all-gathered over the "
-                   "process group"}
+                   "process group; rhat_max is taken ACROSS chains and is only meaningful when chains share their data (the "
+                   "c2/c4 workloads give every chain its own synthetic data set, so it is large by construction)"}
     M.collect()
     status_bad = int(((M.status & 3) != 0).sum())
     accept = {s.param: s.accept_rate.get_acceptance_rate() for s in samplers if hasattr(s, "accept_rate")}

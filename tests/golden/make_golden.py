@@ -26,6 +26,9 @@ from openmcmc.model import Model  # noqa: E402
 from openmcmc.parameter import Identity, LinearCombination, ScaledMatrix  # noqa: E402
 from openmcmc.sampler.metropolis_hastings import ManifoldMALA, RandomWalk, RandomWalkLoop  # noqa: E402
 from openmcmc.sampler.sampler import NormalGamma, NormalNormal  # noqa: E402
+from openmcmc.sampler.reversible_jump import ReversibleJump  # noqa: E402
+from openmcmc.distribution.location_scale import NullDistribution  # noqa: E402
+from openmcmc.parameter import MixtureParameterMatrix, MixtureParameterVector  # noqa: E402
 
 
 class Streams:
@@ -58,9 +61,15 @@ class Streams:
         self.log["tn_u"].append(np.array(u, dtype=float).ravel())
         return stats.truncnorm.ppf(u, a, b, loc=loc, scale=scale)
 
+    def randint_rvs(self, low, high, size=None):
+        k = int(self.rng.integers(int(np.asarray(low).ravel()[0]), int(np.asarray(high).ravel()[0])))
+        self.log["randint"].append(np.array([k], dtype=float))
+        return k
+
     def __enter__(self):
         for dist, name, fn in ((stats.norm, "rvs", self.norm_rvs), (stats.gamma, "rvs", self.gamma_rvs),
-                               (stats.uniform, "rvs", self.uniform_rvs), (stats.truncnorm, "rvs", self.truncnorm_rvs)):
+                               (stats.uniform, "rvs", self.uniform_rvs), (stats.truncnorm, "rvs", self.truncnorm_rvs),
+                               (stats.randint, "rvs", self.randint_rvs)):
             self._saved[(dist, name)] = getattr(dist, name)
             setattr(dist, name, fn)
         return self
@@ -303,6 +312,137 @@ def gmrf_cases():
     }
 
 
+# ----------------------------------------------------------------------------------------------- reversible jump (C5)
+def _rj_basis(X, theta, omega):
+    """tests/test_reversible_jump.py:23-40 of the reference (make_basis), restated for the state update callbacks."""
+    B = np.full((X.shape[0], theta.shape[1]), np.nan)
+    for k in range(theta.shape[1]):
+        B[:, [k]] = stats.norm.pdf(X, loc=theta[:, k], scale=omega[:, k])
+    return B
+
+
+def rj_case(seed, n_data, n0, n_max, n_steps, response="normal", with_omega=True, limits=(-10.0, 10.0), rho=6.0,
+            birth_probability=0.5):
+    """The reference's own RJ test model (tests/test_reversible_jump.py:137-252) driven step by step: only the
+    ReversibleJump sampler runs; every step records the state before, the variates, the proposal and the outcome."""
+    import openmcmc.sampler.reversible_jump as rjmod
+
+    rng = np.random.default_rng(seed)
+    lo, hi = -10.0, 10.0
+    X = lo + (hi - lo) * np.sort(rng.random((n_data, 1)), axis=0)
+    theta = lo + (hi - lo) * rng.random((1, n0))
+    omega = 0.7 + 0.8 * rng.random((1, n0)) if with_omega else np.ones((1, n0))
+    B = _rj_basis(X, theta, omega)
+    tau_beta, tau_y = 0.25, 100.0
+    beta = 2.0 * rng.standard_normal((n0, 1))
+    y = B @ beta + 0.1 * rng.standard_normal((n_data, 1))
+    state = {"y": y, "beta": beta + 0.05 * rng.standard_normal((n0, 1)), "tau_y": np.array([[tau_y]]), "P": sparse.eye(n_data), "B": B,
+             "n_basis": np.array([[float(n0)]]), "X": X, "theta": theta, "omega": omega, "mu_beta": np.zeros((1, 1)),
+             "tau_beta": tau_beta * np.ones((1, 1)), "rho": np.array([[rho]]), "alloc_beta": np.zeros((n0, 1), dtype=int),
+             "a_omega": 3.0 * np.ones((1, 1)), "b_omega": 2.0 * np.ones((1, 1))}
+    mean = LinearCombination(form={"beta": "B"})
+    prec = ScaledMatrix(matrix="P", scalar="tau_y")
+    resp = (Normal if response == "normal" else NullDistribution)(response="y", mean=mean, precision=prec)
+    dists = [resp,
+             Normal(response="beta", mean=MixtureParameterVector(param="mu_beta", allocation="alloc_beta"),
+                    precision=MixtureParameterMatrix(param="tau_beta", allocation="alloc_beta")),
+             Poisson(response="n_basis", rate="rho"),
+             Uniform(response="theta", domain_response_lower=np.array([lo], ndmin=2),
+                     domain_response_upper=np.array([hi], ndmin=2))]
+    assoc = ["theta"]
+    if with_omega:
+        dists.append(Gamma("omega", shape="a_omega", rate="b_omega"))
+        assoc.append("omega")
+    mdl = Model(dists)
+
+    def birth_fn(current_state, prop_state):
+        if not with_omega:
+            prop_state["omega"] = np.concatenate((prop_state["omega"], prop_state["omega"][:, -1:]), axis=1)
+        prop_state["B"] = _rj_basis(prop_state["X"], prop_state["theta"], prop_state["omega"])
+        prop_state["alloc_beta"] = np.concatenate((prop_state["alloc_beta"], np.array([0], ndmin=2)), axis=0)
+        return prop_state, 0.0, 0.0
+
+    def death_fn(current_state, prop_state, deletion_index):
+        if not with_omega:
+            prop_state["omega"] = np.delete(prop_state["omega"], obj=deletion_index, axis=1)
+        prop_state["B"] = np.delete(prop_state["B"], obj=deletion_index, axis=1)
+        prop_state["alloc_beta"] = np.delete(prop_state["alloc_beta"], obj=deletion_index, axis=0)
+        return prop_state, 0.0, 0.0
+
+    matching = {"variable": "beta", "matrix": "B", "scale": 1.0, "limits": list(limits) if limits else None}
+    rj = ReversibleJump(param="n_basis", model=mdl, associated_params=assoc, n_max=n_max, state_birth_function=birth_fn,
+                        state_death_function=death_fn, matching_params=matching, birth_probability=birth_probability)
+    keys = ["n", "theta", "omega", "beta"]
+    rec = {k + "_before": [] for k in keys}
+    rec.update({k + "_after": [] for k in keys})
+    for k in ("birth", "del_index", "u_move", "theta_new", "omega_new", "beta_new", "u_accept", "lq_fwd", "lq_rev",
+              "log_accept", "accepted", "cond"):
+        rec[k] = []
+
+    def pad(a):
+        out = np.full(n_max, np.nan)
+        a = np.asarray(a, dtype=float).ravel()
+        out[: a.size] = a
+        return out
+
+    info = {}
+    orig_prop = rj.proposal
+    orig_acc = rj.accept_proposal
+
+    def prop(current_state, param_index=None):
+        out = orig_prop(current_state)
+        info.update(prop=out[0], lq_fwd=out[1], lq_rev=out[2])
+        return out
+
+    def acc(log_accept):
+        r = orig_acc(log_accept)
+        info.update(log_accept=log_accept, accepted=r)
+        return r
+
+    rj.proposal = prop
+    rj.accept_proposal = acc
+    with Streams(seed + 1000) as S:
+        for it in range(n_steps):
+            n = int(np.asarray(state["n_basis"]).ravel()[0])
+            for k, v in (("n", [n]), ("theta", state["theta"]), ("omega", state["omega"]), ("beta", state["beta"])):
+                rec[k + "_before"].append(pad(v) if k != "n" else float(n))
+            nu, nr = len(S.log["u"]), len(S.log["randint"])
+            sB = state["B"]
+            state = rj.sample(state)
+            us = [float(u.ravel()[0]) for u in S.log["u"][nu:]]
+            birth = int(np.asarray(info["prop"]["n_basis"]).ravel()[0]) == n + 1
+            edge = n in (1, n_max)
+            rec["birth"].append(float(birth))
+            rec["u_move"].append(np.nan if edge else us[0])
+            rec["u_accept"].append(us[-1])
+            rec["del_index"].append(-1.0 if birth else float(S.log["randint"][nr][0]))
+            rec["theta_new"].append(float(info["prop"]["theta"][0, -1]) if birth else np.nan)
+            rec["omega_new"].append(float(info["prop"]["omega"][0, -1]) if birth else np.nan)
+            rec["beta_new"].append(float(info["prop"]["beta"][-1, 0]) if birth else np.nan)
+            for k in ("lq_fwd", "lq_rev", "log_accept"):
+                rec[k].append(float(np.asarray(info[k]).ravel()[0]))
+            rec["accepted"].append(float(info["accepted"]))
+            Bc = info["prop"]["B"] if birth else sB
+            rec["cond"].append(float(np.linalg.cond(Bc.T @ Bc + 1e-10 * np.eye(Bc.shape[1]))))
+            for k, v in (("n", None), ("theta", state["theta"]), ("omega", state["omega"]), ("beta", state["beta"])):
+                rec[k + "_after"].append(pad(v) if k != "n" else float(np.asarray(state["n_basis"]).ravel()[0]))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(X=X.ravel(), y=y.ravel(), tau_y=tau_y, tau_beta=tau_beta, mu_beta=0.0, rho=rho, a_omega=3.0, b_omega=2.0,
+               theta_lo=lo, theta_hi=hi, n_max=n_max, birth_probability=birth_probability, match_scale=1.0,
+               match_limits=np.array(limits if limits else [np.nan, np.nan]), response=response,
+               with_omega=float(with_omega))
+    return out
+
+
+def rj_cases():
+    return {
+        "rj_normal_n50_k4": rj_case(0, 50, 4, 12, 60),
+        "rj_null_n50_k4": rj_case(1, 50, 4, 8, 80, response="null", rho=4.0),
+        "rj_normal_untruncated_fixed_width": rj_case(2, 40, 3, 10, 50, with_omega=False, limits=None),
+        "rj_edges_nmax3": rj_case(3, 30, 1, 3, 60, response="null", rho=2.0, birth_probability=0.4),
+    }
+
+
 def main():
     cases = {
         "regression_n50_p3": regression_case(50, 3, 0, 6),
@@ -311,13 +451,15 @@ def main():
                                                                prior="dense"),
         "regression_n1000_p64": regression_case(1000, 64, 3, 3),
     }
-    which = sys.argv[1:] or ["regression", "mh", "gmrf"]
+    which = sys.argv[1:] or ["regression", "mh", "gmrf", "rj"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
         cases.update(mh_cases())
     if "gmrf" in which:
         cases.update(gmrf_cases())
+    if "rj" in which:
+        cases.update(rj_cases())
     for name, d in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, {k: np.shape(v) for k, v in d.items() if k.startswith("store")})
