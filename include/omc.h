@@ -321,6 +321,51 @@ typedef struct {
 int omc_chain_stats(const omc_chain_stats_t* args, void* stream);
 int omc_rhat_combine(const double* stats, int n_chains_total, int n_sel, double* out, void* stream);
 
+/* ------------------------------------------------------------------ ReversibleJump (C5)
+ * One birth / death step per chain for the Gaussian-kernel basis model of the reference's RJ tests
+ * (tests/test_reversible_jump.py:23-252): state of fixed capacity n_max (first n entries live), basis column
+ * j = N(X; theta_j, omega_j) built in (replaces the Python state_birth/death callbacks), matched coefficient
+ * transitions, move probabilities with their edge cases, accept / reject on the whole model:
+ * response Normal(y | B beta, (tau_y I)^-1) or Null (y.ptr == NULL), beta ~ iid N(mu_beta, 1/tau_beta), n ~ Poisson(rho),
+ * theta ~ U(theta_lo, theta_hi), omega ~ Gamma(omega_shape, omega_rate) when sample_omega.
+ *   ref: sampler/reversible_jump.py:76-373; metropolis_hastings.py:127-173; gmrf.py:269-318
+ * debug: injected variates per chain [6] = move uniform, new knot, new width, new coefficient (NaN => the matched mean),
+ *   deletion index, accept uniform — the FINAL values of the reference's rvs calls (SURVEY B.4 order).
+ * probe: [n_chains][8] = birth, deletion index, logp current, logp proposed, logq forward, logq reverse, log accept,
+ *   accepted.  logp_only != 0: write the model log-density of the current state to logp_out and return. */
+typedef struct {
+  int n_chains, n_data, n_max;
+  double* n_basis;             /* [n_chains] in/out                         */
+  double* theta;               /* [n_chains][n_max] in/out                  */
+  double* omega;               /* [n_chains][n_max] in/out                  */
+  double* beta;                /* [n_chains][n_max] in/out                  */
+  double* B;                   /* [n_chains][n_data][n_max] in/out          */
+  const double* X;             /* [n_data] data locations (shared)          */
+  omc_vec_t y;                 /* [n_data] response, NULL => Null response  */
+  omc_vec_t tau_y;
+  double theta_lo, theta_hi;
+  int sample_omega;            /* 0: a new component copies the last width  */
+  omc_vec_t omega_shape, omega_rate;
+  omc_vec_t mu_beta, tau_beta;
+  omc_vec_t rho;
+  double birth_probability;
+  double match_scale;
+  int match_truncated;
+  double match_lo, match_hi;
+  omc_rng_t rng;
+  const double* debug;
+  long long debug_sweep_stride;
+  long long* counters;         /* optional [n_chains][2]: accepted, proposed */
+  int* status;                 /* optional [n_chains]                        */
+  double* probe;               /* optional [n_chains][8]                     */
+  int logp_only;
+  double* logp_out;            /* [n_chains] when logp_only                  */
+} omc_rj_t;
+int omc_rj_smem_bytes(int n_data, int n_max);
+int omc_reversible_jump(const omc_rj_t* args, void* stream);
+/* B[c][r][j] = N(X_r; theta_cj, omega_cj) for j < n_c, 0 beyond (ref: make_basis, tests/test_reversible_jump.py:23-40) */
+int omc_rj_basis(const omc_rj_t* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,6 +220,27 @@ PROTOTYPES.update({
 EXTRA_STRUCTS = {"omc_chain_stats_t": ChainStats}
 
 
+class RJArgs(C.Structure):
+    """omc_rj_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n_data", C.c_int), ("n_max", C.c_int), ("n_basis", C.c_void_p),
+                ("theta", C.c_void_p), ("omega", C.c_void_p), ("beta", C.c_void_p), ("B", C.c_void_p), ("X", C.c_void_p),
+                ("y", Vec), ("tau_y", Vec), ("theta_lo", C.c_double), ("theta_hi", C.c_double), ("sample_omega", C.c_int),
+                ("omega_shape", Vec), ("omega_rate", Vec), ("mu_beta", Vec), ("tau_beta", Vec), ("rho", Vec),
+                ("birth_probability", C.c_double), ("match_scale", C.c_double), ("match_truncated", C.c_int),
+                ("match_lo", C.c_double), ("match_hi", C.c_double), ("rng", Rng), ("debug", C.c_void_p),
+                ("debug_sweep_stride", C.c_longlong), ("counters", C.c_void_p), ("status", C.c_void_p),
+                ("probe", C.c_void_p), ("logp_only", C.c_int), ("logp_out", C.c_void_p)]
+
+
+PROTOTYPES.update({
+    "omc_rj_smem_bytes": (C.c_int, [C.c_int, C.c_int]),
+    "omc_reversible_jump": (C.c_int, [C.POINTER(RJArgs), C.c_void_p]),
+    "omc_rj_basis": (C.c_int, [C.POINTER(RJArgs), C.c_void_p]),
+})
+EXTRA_STRUCTS["omc_rj_t"] = RJArgs
+
+
 def lib_path() -> str:
     """In-tree libomc.so; OMC_LIB overrides it (used only by tools/tune_reg_pass.sh to time kernel variants)."""
     return os.environ.get("OMC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)

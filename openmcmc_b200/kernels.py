@@ -321,3 +321,40 @@ def tridiag_quadforms(args):
 def tridiag_matvec(pd, pe, v, n_chains, n, out):
     check(lib().omc_tridiag_matvec(_ptr(pd), _ptr(pe) if pe is not None and pe.numel() else None, v, int(n_chains),
                                    int(n), _ptr(out), stream_ptr()), "omc_tridiag_matvec")
+
+
+# ----------------------------------------------------------------------------- ReversibleJump (Gaussian-kernel basis)
+def rj_args(n_chains, n_data, n_max, n_basis, theta, omega, beta, B, X, theta_lo, theta_hi, birth_probability=0.5,
+            y=None, tau_y=None, sample_omega=True, omega_shape=None, omega_rate=None, mu_beta=None, tau_beta=None,
+            rho=None, match_scale=1.0, match_limits=None, rng_=None, debug=None, debug_sweep_stride=0, counters=None,
+            status=None, probe=None, logp_out=None) -> "_cabi.RJArgs":
+    """Build an omc_rj_t.  State tensors are padded to n_max; y/tau_y/... are omc_vec_t (see `vec`) or None."""
+    none = Vec(None, 0)
+    a = _cabi.RJArgs()
+    a.n_chains, a.n_data, a.n_max = int(n_chains), int(n_data), int(n_max)
+    a.n_basis, a.theta, a.omega, a.beta, a.B, a.X = (t.data_ptr() for t in (n_basis, theta, omega, beta, B, X))
+    a.y, a.tau_y = y or none, tau_y or none
+    a.theta_lo, a.theta_hi = float(theta_lo), float(theta_hi)
+    a.sample_omega = int(bool(sample_omega))
+    a.omega_shape, a.omega_rate = omega_shape or none, omega_rate or none
+    a.mu_beta, a.tau_beta, a.rho = mu_beta or none, tau_beta or none, rho or none
+    a.birth_probability, a.match_scale = float(birth_probability), float(match_scale)
+    a.match_truncated = int(match_limits is not None)
+    a.match_lo, a.match_hi = (float(match_limits[0]), float(match_limits[1])) if match_limits is not None else (0.0, 0.0)
+    a.rng = rng_ if rng_ is not None else Rng(0, None, 0, 0)
+    a.debug = debug.data_ptr() if debug is not None else None
+    a.debug_sweep_stride = int(debug_sweep_stride)
+    for name, t in (("counters", counters), ("status", status), ("probe", probe), ("logp_out", logp_out)):
+        setattr(a, name, t.data_ptr() if t is not None else None)
+    a.logp_only = 0
+    return a
+
+
+def reversible_jump(args, logp_only=False):
+    args.logp_only = int(logp_only)
+    check(lib().omc_reversible_jump(C.byref(args), stream_ptr()), "omc_reversible_jump")
+    args.logp_only = 0
+
+
+def rj_basis(args):
+    check(lib().omc_rj_basis(C.byref(args), stream_ptr()), "omc_rj_basis")
