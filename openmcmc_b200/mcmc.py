@@ -95,16 +95,26 @@ class MCMC:
             plan.ops = store_ops = []
             n_iter = max(self.n_iter, 1)
             self._dev_store = {}
+            self._store_names = []
             for s in self.samplers:
-                arr = st[s.param]
-                buf = plan.new(n_iter, C, arr.size, fill=float("nan"))
-                self._dev_store[s.param] = buf
-                store_ops.append((f"store[{s.param}]", (lambda arr=arr, buf=buf: K.store_copy(
-                    arr.data, buf, C * arr.size, plan.iter_counter, n_iter))))
+                names = [s.param] + list(getattr(s, "stored_state_names", lambda: [])())
+                for name in names:
+                    if name in self._dev_store:
+                        continue
+                    arr = st[name]
+                    buf = plan.new(n_iter, C, arr.size, fill=float("nan"))
+                    self._dev_store[name] = buf
+                    self._store_names.append(name)
+                    store_ops.append((f"store[{name}]", (lambda arr=arr, buf=buf: K.store_copy(
+                        arr.data, buf, C * arr.size, plan.iter_counter, n_iter))))
             self._dev_logpost = plan.new(n_iter, C, fill=float("nan"))
             self._logpost_now = plan.new(C)
             saved_valid = dict(plan.valid)
-            engine.compile_log_post(plan, self.state, self.model, self._logpost_now)
+            rj = plan.__dict__.get("_rj")
+            if rj is not None:
+                rj.compile_log_post(plan, self._logpost_now)
+            else:
+                engine.compile_log_post(plan, self.state, self.model, self._logpost_now)
             store_ops.append(("store[log_post]", lambda: K.store_copy(self._logpost_now, self._dev_logpost, C,
                                                                         plan.iter_counter, n_iter)))
             self._dev_fitted = {}
@@ -142,7 +152,10 @@ class MCMC:
         recorded.  Restored afterwards: sampled parameters, sweep / iteration counters, status bits, MH accept counters
         (derived quantities are recomputed by the prologue, store rows are overwritten by the first stored iteration).
         """
-        saved = [(st[name].data, st[name].data.clone()) for name in sampled]
+        names = set(sampled)
+        for s in self.samplers:
+            names.update(getattr(s, "extra_state_names", lambda: [])())
+        saved = [(st[name].data, st[name].data.clone()) for name in names]
         for ctx in plan.__dict__.get("_ctx", {}).values():
             if ctx.get("counters") is not None:
                 saved.append((ctx["counters"], ctx["counters"].clone()))
@@ -176,12 +189,19 @@ class MCMC:
         n_done = int(self.plan.iter_counter.item())
         self.store = {}
         d2h = 0
+        owner = {}
         for s in self.samplers:
-            buf = self._dev_store[s.param][: self.n_iter].cpu().numpy()      # [n_iter, C, size]
+            for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
+                owner.setdefault(name, s)
+        for name in self._store_names:
+            s = owner[name]
+            buf = self._dev_store[name][: self.n_iter].cpu().numpy()          # [n_iter, C, size]
             d2h += buf.nbytes
             arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
-            arr = self._shape_store(s, arr, st[s.param])
-            self.store[s.param] = arr[0] if C == 1 else arr
+            if name == s.param:
+                arr = self._shape_store(s, arr, st[name])
+            self.store[name] = arr[0] if C == 1 else arr
+        self._mask_padded_store()
         lp = self._dev_logpost[: self.n_iter].cpu().numpy()
         d2h += lp.nbytes
         self.store["log_post"] = lp.reshape(self.n_iter, 1) if C == 1 else lp
@@ -191,14 +211,47 @@ class MCMC:
             arr = np.transpose(h, (1, 2, 0))
             self.store[response] = arr[0] if C == 1 else arr
         for s in self.samplers:
-            new = st.get_host(s.param)
-            self.state[s.param] = new
-            d2h += new.nbytes
+            for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
+                new = st.get_host(name)
+                self.state[name] = new
+                d2h += new.nbytes
+        self._trim_padded_state()
         self.status = self.plan.status.cpu().numpy()
         self.timing["d2h_bytes"] = d2h
         self.timing["h2d_bytes"] = st.h2d_bytes
         self.timing["stored_iterations"] = n_done
         return self.store
+
+    def _rj_sampler(self):
+        from openmcmc_b200.sampler.reversible_jump import ReversibleJump
+
+        return next((s for s in self.samplers if isinstance(s, ReversibleJump)), None)
+
+    def _mask_padded_store(self):
+        """Variable-dimension parameters are stored at capacity n_max: entries beyond the stored count become NaN, the
+        layout `max_variable_size` gives the reference's store (sampler.py:69-118)."""
+        rj = self._rj_sampler()
+        if rj is None or rj.param not in self.store:
+            return
+        cnt = self.store[rj.param]                                  # [(C,) 1, n_iter]
+        for name in rj.extra_state_names():
+            if name in self.store:
+                a = self.store[name]
+                idx = np.arange(a.shape[-2]).reshape(-1, 1)
+                a[np.broadcast_to(idx >= cnt[..., :1, :], a.shape)] = np.nan
+
+    def _trim_padded_state(self):
+        """Final state of one chain in the reference's exact shapes (theta (1,n), beta (n,1), B (n_data,n))."""
+        rj = self._rj_sampler()
+        if rj is None or self.n_chains != 1:
+            return
+        n = int(np.ravel(self.state[rj.param])[0])
+        b = rj.basis
+        self.state[b.knots] = np.asarray(self.state[b.knots]).reshape(1, -1)[:, :n]
+        self.state[b.widths] = np.asarray(self.state[b.widths]).reshape(1, -1)[:, :n]
+        var = rj.matching_params["variable"]
+        self.state[var] = np.asarray(self.state[var]).reshape(-1, 1)[:n]
+        self.state[b.matrix] = np.asarray(self.state[b.matrix])[:, :n]
 
     @staticmethod
     def _shape_store(sampler, arr, dev_arr):

@@ -240,3 +240,88 @@ def test_rj_free_running_with_widths_matches_the_reference_semantics():
     se = bm.std(ddof=1) / np.sqrt(50)
     assert abs(ns.mean() - trace.mean()) < 5 * se + 0.1, (ns.mean(), trace.mean(), se)
     assert abs(ns.mean() - 8.0) > 0.5    # ... and it is NOT the prior mean: the F8 quirk is really there
+
+
+def _rj_model(g, response):
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal, NullDistribution
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, MixtureParameterMatrix, MixtureParameterVector, ScaledMatrix
+
+    mean = LinearCombination(form={"beta": "B"})
+    prec = ScaledMatrix(matrix="P", scalar="tau_y")
+    resp = (Normal if response == "normal" else NullDistribution)(response="y", mean=mean, precision=prec)
+    dists = [resp,
+             Normal(response="beta", mean=MixtureParameterVector(param="mu_beta", allocation="alloc_beta"),
+                    precision=MixtureParameterMatrix(param="tau_beta", allocation="alloc_beta")),
+             Poisson(response="n_basis", rate="rho"),
+             Uniform(response="theta", domain_response_lower=np.array([float(g["theta_lo"])], ndmin=2),
+                     domain_response_upper=np.array([float(g["theta_hi"])], ndmin=2))]
+    if g["with_omega"]:
+        dists.append(Gamma("omega", shape="a_omega", rate="b_omega"))
+    return Model(dists)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_mcmc_with_reversible_jump_replays_reference_chain(name):
+    """The host classes (same constructor as the reference + the declarative basis) drive the kernel through the sweep
+    plan / CUDA graph: the golden steps are consecutive states of ONE reference chain, so the whole run is replayed."""
+    from scipy import sparse
+
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.reversible_jump import GaussianKernelBasis, ReversibleJump
+    from oracle import rj
+    from test_oracle_rj_vs_golden import tol_of
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    n_steps, n_max, nd = g["birth"].size, int(g["n_max"]), g["X"].size
+    n0 = int(g["n_before"][0])
+    th0, om0, be0 = (g[k + "_before"][0][:n0] for k in ("theta", "omega", "beta"))
+    mdl = _rj_model(g, str(g["response"]))
+    lim = g["match_limits"]
+    rjs = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta", "omega"] if g["with_omega"] else ["theta"],
+                         n_max=n_max, birth_probability=float(g["birth_probability"]),
+                         matching_params={"variable": "beta", "matrix": "B", "scale": float(g["match_scale"]),
+                                          "limits": None if np.isnan(lim[0]) else [float(lim[0]), float(lim[1])]},
+                         basis=GaussianKernelBasis(matrix="B", locations="X", knots="theta", widths="omega"))
+    state = {"y": g["y"].reshape(-1, 1), "beta": be0.reshape(-1, 1), "tau_y": float(g["tau_y"]), "P": sparse.eye(nd),
+             "B": rj.make_basis(g["X"], th0, om0), "n_basis": n0, "X": g["X"].reshape(-1, 1), "theta": th0.reshape(1, -1),
+             "omega": om0.reshape(1, -1), "mu_beta": np.zeros((1, 1)), "tau_beta": float(g["tau_beta"]) * np.ones((1, 1)),
+             "rho": float(g["rho"]), "alloc_beta": np.zeros((n0, 1)), "a_omega": float(g["a_omega"]) * np.ones((1, 1)),
+             "b_omega": float(g["b_omega"]) * np.ones((1, 1))}
+    dbg = np.stack([g["u_move"], g["theta_new"], g["omega_new"], g["beta_new"], g["del_index"], g["u_accept"]], axis=1)
+    M = MCMC(state, [rjs], model=mdl, n_burn=0, n_iter=n_steps, debug_draws={"n_basis": {"rj": dbg.reshape(n_steps, 1, 6)}})
+    M.run_mcmc()
+    np.testing.assert_array_equal(M.store["n_basis"].ravel(), g["n_after"])
+    tol = max(tol_of(g, it) for it in range(n_steps)) * n_steps
+    for it in range(n_steps):
+        na = int(g["n_after"][it])
+        np.testing.assert_allclose(M.store["theta"][:na, it], g["theta_after"][it][:na], rtol=1e-12)
+        np.testing.assert_allclose(M.store["beta"][:na, it], g["beta_after"][it][:na], rtol=1e-8, atol=tol)
+        assert np.all(np.isnan(M.store["theta"][na:, it]))
+    nf = int(g["n_after"][-1])
+    assert M.state["theta"].shape == (1, nf) and M.state["beta"].shape == (nf, 1) and M.state["B"].shape == (nd, nf)
+    # log_post of every stored iteration = the oracle's model log-density of that state
+    from test_oracle_rj_vs_golden import model_of, state_of
+
+    m = model_of(g)
+    for it in (0, n_steps // 2, n_steps - 1):
+        st = state_of(g, it, "after")
+        np.testing.assert_allclose(M.store["log_post"][it, 0], rj.model_log_p(m, st["n"], st["theta"], st["omega"], st["beta"], st["B"]),
+                                   rtol=1e-8)
+    assert rjs.accept_rate.count["proposal"] == n_steps
+    assert rjs.accept_rate.count["accept"] == int(g["accepted"].sum())
+
+
+def test_reversible_jump_with_python_callbacks_is_refused():
+    from openmcmc_b200 import engine
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.reversible_jump import ReversibleJump
+
+    g = dict(np.load(os.path.join(GOLD, NAMES[0] + ".npz")))
+    mdl = _rj_model(g, "null")
+    rjs = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta"], n_max=5,
+                         state_birth_function=lambda c, p: (p, 0.0, 0.0), state_death_function=lambda c, p, d: (p, 0.0, 0.0),
+                         matching_params={"variable": "beta", "matrix": "B", "scale": 1.0, "limits": None})
+    with pytest.raises(engine.PlanError):
+        MCMC({"n_basis": 2, "theta": np.zeros((1, 2))}, [rjs], model=mdl, n_burn=0, n_iter=1).run_mcmc()
