@@ -47,6 +47,10 @@ WORKLOADS = {
     "c4b": dict(name="RandomWalkLoop (truncated proposals), Poisson counts + Gamma prior: 8192 chains/GPU x (1,32) params",
                 kind="mh", chains=8192, n=0, p=32, thin=1, dominant="random_walk_loop",
                 cpu=dict(chains_per_worker=4, sweeps=300), ref=dict(chains_per_worker=2, sweeps=50)),
+    # BASELINE.json configs[4]: ReversibleJump on the Gaussian-kernel basis model, 8192 chains, capacity 128 components
+    "c5": dict(name="ReversibleJump birth/death, Gaussian-kernel basis model: 8192 chains/GPU, n_data=512, n_max=128, "
+                    "rho=32, Normal response, matched transitions", kind="rj", chains=8192, n=512, p=128, thin=1,
+               dominant="reversible_jump", cpu=dict(chains_per_worker=2, sweeps=300), ref=dict(chains_per_worker=1, sweeps=100)),
 }
 
 
@@ -242,6 +246,47 @@ def build_mh(C, n, p, dev, rank, host, loop):
     return mdl, [smp], state
 
 
+def build_rj(C, n_data, n_max, dev, rank, host):
+    """the reference RJ test model scaled — n_data points on [-10, 10], capacity n_max, rho = n_max / 4,
+    Gaussian-kernel basis, truncated matching [-10, 10] with scale 1; every chain has its own response."""
+    import numpy as np
+    import torch
+    from scipy import sparse
+
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, MixtureParameterMatrix, MixtureParameterVector, ScaledMatrix
+    from openmcmc_b200.sampler.reversible_jump import GaussianKernelBasis, ReversibleJump
+
+    rng = np.random.default_rng(77 + rank)
+    rho = n_max / 4.0
+    k0 = int(rho)
+    X = np.sort(rng.uniform(-10, 10, n_data))
+    theta = rng.uniform(-10, 10, (C, 1, k0))
+    omega = rng.uniform(0.8, 1.6, (C, 1, k0))
+    beta = rng.standard_normal((C, k0, 1))
+    z = (X.reshape(1, -1, 1) - theta) / omega
+    Bt = np.exp(-0.5 * z * z) / (np.sqrt(2 * np.pi) * omega)                # [C, n_data, k0]
+    y = Bt @ beta + 0.1 * rng.standard_normal((C, n_data, 1))
+    yt = torch.as_tensor(y)
+    yt = yt.pin_memory() if host else yt.to(dev)
+    mdl = Model([Normal("y", mean=LinearCombination(form={"beta": "B"}), precision=ScaledMatrix(matrix="P", scalar="tau_y")),
+                 Normal("beta", mean=MixtureParameterVector(param="mu_beta", allocation="alloc_beta"),
+                        precision=MixtureParameterMatrix(param="tau_beta", allocation="alloc_beta")),
+                 Poisson("n_basis", rate="rho"),
+                 Uniform("theta", domain_response_lower=np.array([[-10.0]]), domain_response_upper=np.array([[10.0]])),
+                 Gamma("omega", shape="a_omega", rate="b_omega")])
+    smp = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta", "omega"], n_max=n_max,
+                         matching_params={"variable": "beta", "matrix": "B", "scale": 1.0, "limits": [-10.0, 10.0]},
+                         basis=GaussianKernelBasis(matrix="B", locations="X", knots="theta", widths="omega"))
+    state = {"y": yt, "beta": beta, "tau_y": 100.0, "P": sparse.eye(n_data), "B": np.zeros((n_data, k0)), "n_basis": k0,
+             "X": X.reshape(-1, 1), "theta": theta, "omega": omega, "mu_beta": np.zeros((1, 1)),
+             "tau_beta": 0.25 * np.ones((1, 1)), "rho": rho, "alloc_beta": np.zeros((k0, 1)),
+             "a_omega": 3.0 * np.ones((1, 1)), "b_omega": 2.0 * np.ones((1, 1))}
+    return mdl, [smp], state
+
+
 def _pinned(t):
     import torch
 
@@ -255,6 +300,8 @@ def build(wl, C, n, dev, rank, host=False):
         return build_regression(C, n, wl["p"], dev, rank, host)
     if wl["kind"] == "gmrf":
         return build_gmrf(C, n, wl["p"], dev, rank, host)
+    if wl["kind"] == "rj":
+        return build_rj(C, n, wl["p"], dev, rank, host)
     return build_mh(C, n, wl["p"], dev, rank, host, loop=wl["dominant"] == "random_walk_loop")
 
 
@@ -277,6 +324,14 @@ def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak):
         return {"bound": "hbm", "kernel": "omc_tridiag_nn_draw (tridiag_forward_kernel + tridiag_backward_kernel)",
                 "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
                 "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+    if wl["kind"] == "rj":
+        k = p / 4.0                                       # expected live components (rho = n_max / 4)
+        byts = C * 2 * 8 * n * k                          # two passes over the live basis columns (8 n_data k)
+        flops = C * (2 * n * k * k + 4.0 / 3.0 * k ** 3)
+        return {"bound": "hbm", "kernel": "rj_kernel (Gram + in-place inverse + LU per chain; latency / FP64-ALU bound)",
+                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
+                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
+                "fp64": {"achieved_tflops": flops / sec / 1e12, "flops_per_chain_step": flops / C}}
     byts = C * 32 * p                                     # read theta, y; write theta, sample
     return {"bound": "hbm", "kernel": f"{wl['dominant']}_kernel (latency / FP64-ALU bound: 1 KB per chain-iteration)",
             "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,

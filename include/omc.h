@@ -360,6 +360,8 @@ typedef struct {
   double* probe;               /* optional [n_chains][8]                     */
   int logp_only;
   double* logp_out;            /* [n_chains] when logp_only                  */
+  int* size_class;             /* optional scratch [n_chains]: the step is then launched per size class of live
+                                  components (small shared-memory footprint for small chains)                   */
 } omc_rj_t;
 int omc_rj_smem_bytes(int n_data, int n_max);
 int omc_reversible_jump(const omc_rj_t* args, void* stream);

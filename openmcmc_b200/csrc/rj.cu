@@ -131,23 +131,29 @@ struct Shared {
   double theta_new, omega_new, beta_new, u_trunc, u_accept, lq_f, lq_r;
 };
 
-__global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a) {
+// ld: leading dimension of the shared-memory matrices (>= largest basis handled + 1).  With a size_class scratch array
+// the step is launched once per size class (classes fixed by rj_class_kernel from the counts BEFORE the step) and a CTA
+// serves its chain only in its class, so that chains with few live components run from a small shared-memory
+// footprint (several CTAs per SM) and only the rare large ones pay for the full capacity.
+__global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) {
   extern __shared__ __align__(16) double sm[];
   __shared__ Shared sh;
   __shared__ double s_red[32];
   __shared__ int s_piv[2];
   const int tid = threadIdx.x;
   const int chain = blockIdx.x;
-  const int nd = a.n_data, cap = a.n_max, ld = cap + 1;
+  const int nd = a.n_data, cap = a.n_max;
   double* A = sm;                         // ld * ld
   double* chunk = A + ld * ld;            // RJ_ROWS * ld
   double* bnew = chunk + RJ_ROWS * ld;    // nd
-  double* th = bnew + nd;                 // ld each from here on
-  double* om = th + ld;
-  double* be = om + ld;                   // current coefficients
-  double* bp = be + ld;                   // proposed coefficients (laid out on the LARGER basis)
-  double* colv = bp + ld;
+  const int lv = cap + 1;                 // vectors are kept at full capacity whatever the matrix size class
+  double* th = bnew + nd;                 // lv each from here on
+  double* om = th + lv;
+  double* be = om + lv;                   // current coefficients
+  double* bp = be + lv;                   // proposed coefficients (laid out on the LARGER basis)
+  double* colv = bp + lv;
   const int k = (int)a.n_basis[chain];
+  if (cls >= 0 && a.size_class[chain] != cls) return;   // another launch of this step owns the chain
   double* thg = a.theta + (long long)chain * cap;
   double* omg = a.omega + (long long)chain * cap;
   double* beg = a.beta + (long long)chain * cap;
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a) {
     if (tid == 0 && a.status) atomicOr(&a.status[chain], OMC_STATUS_NAN);
     return;
   }
-  for (int j = tid; j < ld; j += RJ_NT) {
+  for (int j = tid; j < lv; j += RJ_NT) {
     th[j] = j < k ? thg[j] : 0.0;
     om[j] = j < k ? omg[j] : 1.0;
     be[j] = j < k ? beg[j] : 0.0;
@@ -421,6 +427,13 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a) {
   }
 }
 
+__global__ void rj_class_kernel(const double* n_basis, int n_chains, int* size_class) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const int k = (int)n_basis[c];
+  size_class[c] = (k <= 31) ? 0 : (k <= 63) ? 1 : 2;   // invalid counts fall into class 0, which reports them
+}
+
 // B[c][r][j] = N(X_r; theta_cj, omega_cj) for the live columns  (make_basis; also the state_update_function of the
 // RandomWalkLoop samplers on theta / omega in the reference's test model)
 __global__ void rj_basis_kernel(omc_rj_t a) {
@@ -445,10 +458,11 @@ int rj_check(const omc_rj_t* a, const char* who) {
 
 extern "C" {
 
-int omc_rj_smem_bytes(int n_data, int n_max) {
-  const int ld = n_max + 1;
-  return (ld * ld + RJ_ROWS * ld + n_data + 5 * ld) * 8;
+static int rj_smem_for_ld(int n_data, int n_max, int ld) {
+  return (ld * ld + RJ_ROWS * ld + n_data + 5 * (n_max + 1)) * 8;
 }
+
+int omc_rj_smem_bytes(int n_data, int n_max) { return rj_smem_for_ld(n_data, n_max, n_max + 1); }
 
 int omc_reversible_jump(const omc_rj_t* a, void* stream) {
   if (int rc = rj_check(a, "omc_reversible_jump")) return rc;
@@ -459,8 +473,28 @@ int omc_reversible_jump(const omc_rj_t* a, void* stream) {
   OMC_REQUIRE(smem <= 220 * 1024, "omc_reversible_jump: n_max=%d, n_data=%d need %d bytes of shared memory", a->n_max,
               a->n_data, smem);
   OMC_CHECK_CUDA(cudaFuncSetAttribute(rj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rj_kernel<<<a->n_chains, RJ_NT, smem, (cudaStream_t)stream>>>(*a);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->logp_only) {   // no matrices needed: vectors only
+    rj_kernel<<<a->n_chains, RJ_NT, rj_smem_for_ld(a->n_data, a->n_max, 1), st>>>(*a, 1, -1);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
+  if (!a->size_class || a->n_max <= 32) {
+    rj_kernel<<<a->n_chains, RJ_NT, smem, st>>>(*a, a->n_max + 1, -1);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
+  // size classes by live components BEFORE the step: n <= 31 (ld 33), n <= 63 (ld 65), the rest at full capacity
+  rj_class_kernel<<<(a->n_chains + 255) / 256, 256, 0, st>>>(a->n_basis, a->n_chains, a->size_class);
   OMC_LAUNCH_CHECK();
+  const int hi[3] = {31, 63, a->n_max};
+  for (int q = 0; q < 3; ++q) {
+    const int top = hi[q] < a->n_max ? hi[q] : a->n_max;
+    const int ld = (top + 1 < a->n_max ? top + 1 : a->n_max) + 1;   // a birth from n = top needs top + 1 columns
+    rj_kernel<<<a->n_chains, RJ_NT, rj_smem_for_ld(a->n_data, a->n_max, ld), st>>>(*a, ld, q);
+    OMC_LAUNCH_CHECK();
+    if (top >= a->n_max) break;
+  }
   return 0;
 }
 

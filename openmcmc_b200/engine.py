@@ -244,6 +244,11 @@ class Plan:
         self.keep.append(t)
         return t
 
+    def keep_tensor(self, t):
+        """Keep a tensor alive for the lifetime of the plan (kernels hold raw device pointers) and return it."""
+        self.keep.append(t)
+        return t
+
     def rng_site(self):
         self.n_sites += 1
         return K.rng(seed=self.seed, sweep=self.sweep_counter, chain_offset=self.chain_offset, site=self.n_sites)

@@ -165,7 +165,7 @@ class ReversibleJump(MetropolisHastings):
                 omega_shape=v("omega_shape"), omega_rate=v("omega_rate"), mu_beta=v("mu_beta"), tau_beta=v("tau_beta"),
                 rho=v("rho"), match_scale=float(self.matching_params["scale"]), match_limits=lim, rng_=ctx["rng"],
                 debug=dbg, debug_sweep_stride=dbg_stride, counters=ctx["counters"], status=plan.status,
-                probe=ctx["probe"])
+                probe=ctx["probe"], size_class=plan.keep_tensor(torch.zeros(C, dtype=torch.int32, device=dev)))
             plan.keep.extend([n_dev, theta, omega, beta, Bm])
             K.rj_basis(ctx["args"])     # basis of the initial knots (the host copy is not trusted to be padded)
             plan.__dict__["_rj"] = self

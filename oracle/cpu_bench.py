@@ -26,7 +26,38 @@ def _worker(workload, chains, sweeps, seed, n, p):
         return _worker_gmrf(rng, chains, sweeps, n)
     if workload in ("c4a", "c4b"):
         return _worker_mh(rng, chains, sweeps, p, workload)
+    if workload == "c5":
+        return _worker_rj(rng, chains, sweeps, n, p)
     raise ValueError(workload)
+
+
+def _worker_rj(rng, chains, sweeps, n_data, n_max):
+    """C5: ReversibleJump steps on the Gaussian-kernel basis model (n_data points, rho = n_max / 4 expected knots) with a
+    Normal response, plus the per-iteration log_post (mcmc.py:108)."""
+    import numpy as np
+
+    from oracle import rj
+
+    rho = n_max / 4.0
+    X = np.sort(rng.uniform(-10, 10, n_data))
+    data = []
+    for _ in range(chains):
+        k = int(rho)
+        th, om = rng.uniform(-10, 10, k), rng.uniform(0.8, 1.6, k)
+        B = rj.make_basis(X, th, om)
+        be = rng.standard_normal(k)
+        y = B @ be + 0.1 * rng.standard_normal(n_data)
+        m = dict(X=X, y=y, tau_y=100.0, tau_beta=0.25, mu_beta=0.0, rho=rho, a_omega=3.0, b_omega=2.0, theta_lo=-10.0,
+                 theta_hi=10.0, n_max=n_max, birth_probability=0.5, match_scale=1.0, match_limits=(-10.0, 10.0))
+        data.append((m, dict(n=k, theta=th, omega=om, beta=be, B=B)))
+    t0 = time.perf_counter()
+    for m, st in data:
+        for _ in range(sweeps):
+            d = dict(u_move=rng.random(), theta_new=rng.uniform(-10, 10), omega_new=rng.gamma(3.0) / 2.0, beta_new=None,
+                     u_trunc=rng.random(), del_index=float(rng.integers(0, st["n"])), u_accept=rng.random())
+            st, _ = rj.rj_step(m, st, d)
+            _ = rj.model_log_p(m, st["n"], st["theta"], st["omega"], st["beta"], st["B"])
+    return time.perf_counter() - t0
 
 
 def _worker_regression(rng, chains, sweeps, n, p):

@@ -98,6 +98,13 @@ def rj_step(m, st, draws):
         beta_p = mu_star.copy()
         if draws.get("beta_new") is not None:
             beta_p[-1] = draws["beta_new"]
+        elif draws.get("u_trunc") is not None:      # free-running: the uniform behind truncnorm.rvs (gmrf.py:269-292)
+            if m["match_limits"] is not None:
+                lo_, hi_ = m["match_limits"]
+                a_, b_ = (lo_ - mu_star[-1]) / m["match_scale"], (hi_ - mu_star[-1]) / m["match_scale"]
+                beta_p[-1] = float(stats.truncnorm.ppf(draws["u_trunc"], a_, b_, loc=mu_star[-1], scale=m["match_scale"]))
+            else:
+                beta_p[-1] = mu_star[-1] + m["match_scale"] * float(stats.norm.ppf(draws["u_trunc"]))
         if m["match_limits"] is not None:
             lq_f = truncnorm_logpdf(beta_p[-1], mu_star[-1], m["match_scale"], *m["match_limits"])
         else:
