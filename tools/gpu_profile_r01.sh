@@ -1,16 +1,23 @@
 #!/bin/bash
-# Round-1 measurement recipe (run under gpurun): plain bench first, then the ncu launch lists of the same commands,
-# then one --set full capture of the top kernels.  Outputs under gpurun_out/.
+# Round-1 measurement recipe (run under gpurun): plain bench of every workload first, then the ncu launch lists of the
+# same commands, then one --set full capture of the top kernels.  Outputs under gpurun_out/; summaries are written into
+# profiles/ afterwards with tools/ncu_summary.py.
 set -x
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err || exit 1
-tail -c 600 gpurun_out/bench_c2.json
-for w in c2 c3 c4a c4b; do
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_$w.csv \
+for w in c2 c1 c3 c4a c4b c5; do
+  timeout 600 python bench.py --workload $w > gpurun_out/r01_bench_$w.json 2> gpurun_out/r01_bench_$w.err || echo "bench $w failed"
+done
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01_bench_reference.json 2>> gpurun_out/r01_bench_c2.err
+for w in c2 c3 c4a c4b c5; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_$w.csv \
     python bench.py --workload $w --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_$w.log 2>&1
 done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tridiag_forward -c 1 -s 3 -o gpurun_out/r01_tridiag_forward -f \
-  python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_fwd.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tridiag_backward -c 1 -s 3 -o gpurun_out/r01_tridiag_backward -f \
-  python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_bwd.log 2>&1
-ls -la gpurun_out | tail -20
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tg_aggregate|tg_tilescan|tg_solve" -c 3 -s 9 -o gpurun_out/r01_tridiag -f \
+  python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c3.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:reg_pass -c 1 -s 3 -o gpurun_out/r01_reg_pass_full -f \
+  python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rj_kernel" -c 3 -s 6 -o gpurun_out/r01_rj -f \
+  python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c5.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mmala_kernel|random_walk_kernel" -c 1 -s 3 -o gpurun_out/r01_mmala -f \
+  python bench.py --workload c4a --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c4a.log 2>&1
+ls -la gpurun_out | tail -30
