@@ -38,7 +38,10 @@
 
 namespace {
 
-constexpr int TG_K = 18;                   // consecutive elements per thread
+#ifndef TG_K_DEF
+#define TG_K_DEF 18
+#endif
+constexpr int TG_K = TG_K_DEF;             // consecutive elements per thread (K/2 odd: 16-byte LDS stay conflict-free)
 #ifndef TG_NT_DEF
 #define TG_NT_DEF 128
 #endif
@@ -51,19 +54,21 @@ constexpr unsigned FULL = 0xffffffffu;
 #define TG_SOLVE_MINB (512 / TG_NT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
 #endif
 
+// Look-back record of one tile.  Every payload travels in ONE 16-byte word together with its flag (16-byte accesses
+// are single transactions), so neither the writer nor the readers need a fence:
+//   flag = epoch*4 + 1 on (a, b): affine aggregate ready, x_first = a * x_in + b  (x_in = first x of the next tile)
+//   flag = epoch*4 + 2 on x     : x_first itself ready
 struct __align__(64) RecB {
-  unsigned long long flag;   // epoch*4 + {1: affine aggregate ready, 2: x_first ready}
-  double a, b;               // x_first = a * x_in + b   (x_in = first x of the next tile)
-  double x_first;
-  double part[3];            // per-tile partial sums: prior quadratic form, likelihood quadratic form, log-det
-  double pad;
+  double a; unsigned long long fa;
+  double b; unsigned long long fb;
+  double x; unsigned long long fx;
+  double pad[2];
 };
 
 struct Workspace {
-  unsigned long long epoch;
-  unsigned int done_b, pad0;
-  unsigned int pad[12];
-  // followed by: unsigned int chain_done[n_chains] (padded), RecB[n_tiles][n_chains],
+  unsigned long long epoch;   // advanced by the tile-scan kernel of every draw
+  unsigned int pad[14];
+  // followed by: RecB[n_tiles][n_chains], per-tile partial sums double[n_tiles][n_chains][4],
   //              tile totals double[n_tiles][n_chains][8], tile inputs double2[n_tiles][n_chains],
   //              thread prefixes double[n_chains][n_tiles][7][TG_NT]
 };
@@ -71,17 +76,17 @@ struct Workspace {
 __host__ __device__ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  long long off_chain_done, off_recb, off_flags_end, off_tt, off_sin, off_ex, total;
+  long long off_recb, off_flags_end, off_parts, off_tt, off_sin, off_ex, total;
   long long n_tiles;
 };
 __host__ __device__ inline Layout make_layout(int n_chains, long long n) {
   Layout L;
   L.n_tiles = (n + TG_TILE - 1) / TG_TILE;
   const long long tc = L.n_tiles * n_chains;
-  L.off_chain_done = sizeof(Workspace);
-  L.off_recb = align_up(L.off_chain_done + (long long)n_chains * sizeof(unsigned int), 128);
+  L.off_recb = align_up(sizeof(Workspace), 128);
   L.off_flags_end = L.off_recb + tc * (long long)sizeof(RecB);
-  L.off_tt = align_up(L.off_flags_end, 128);
+  L.off_parts = align_up(L.off_flags_end, 128);
+  L.off_tt = align_up(L.off_parts + tc * 32, 128);
   L.off_sin = L.off_tt + tc * 64;
   L.off_ex = align_up(L.off_sin + tc * 16, 128);
   L.total = L.off_ex + tc * 7 * TG_NT * 8;
@@ -135,23 +140,19 @@ __device__ __forceinline__ TM tm_shfl_up(const TM& t, int d) {
             shfl_up_d(t.f, d), shfl_up_d(t.g, d)};
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+// 16-byte (payload, flag) words of the look-back records: one transaction each way, no fences
+__device__ __forceinline__ void st_word(void* p, double v, unsigned long long flag) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(flag) : "memory");
 }
-__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void ld_word(const void* p, double& v, unsigned long long& flag) {
+  long long bits;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(flag) : "l"(p) : "memory");
+  v = __longlong_as_double(bits);
 }
 // issue-now read-only load: volatile asm keeps it where it is written (ahead of the RNG work that hides its latency)
 __device__ __forceinline__ double ld_nc_now(const double* p) {
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ld_cg(const double* p) {
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layou
   __shared__ double s_tot[TS_NT / 32][7];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chain = blockIdx.x;
+  if (chain == 0 && tid == 0) ws->epoch = ws->epoch + 1;   // fresh flag values for the solve kernel that follows
   char* wsb = reinterpret_cast<char*>(ws);
   const double* tt = reinterpret_cast<const double*>(wsb + L.off_tt);
   double2* sin_ = reinterpret_cast<double2*>(wsb + L.off_sin);
@@ -531,7 +533,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   char* wsb = reinterpret_cast<char*>(ws);
   RecB* recs = reinterpret_cast<RecB*>(wsb + L.off_recb);
   RecB* rec = recs + tile * C + chain;
-  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
+  double* parts = reinterpret_cast<double*>(wsb + L.off_parts) + (tile * C + chain) * 4;
   const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
   const long long i_t = tile * TG_TILE;
   const bool solve = !DEBUG || a.x != nullptr;
@@ -717,27 +719,28 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     Aff R{1.0, 0.0};
     if (tile < T - 1) {
       if (tid == 0) {
-        rec->a = tot.a;
-        rec->b = tot.b;
-        st_release(&rec->flag, FLAG_A);
+        st_word(&rec->a, tot.a, FLAG_A);
+        st_word(&rec->b, tot.b, FLAG_A);
       }
       long long base = tile + 1;
       while (true) {
         const long long j = base + lane;
-        unsigned long long fl = FLAG_P;
-        const RecB* pr = nullptr;
-        if (j < T) {
-          pr = recs + j * C + chain;
-          do { fl = ld_acquire(&pr->flag); } while (fl != FLAG_A && fl != FLAG_P);
-        }
-        const unsigned pmask = __ballot_sync(FULL, fl == FLAG_P);
-        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
+        bool have_x = true;           // lanes beyond the chain's last tile: x = 0 terminates the walk
         Aff mine{1.0, 0.0};
         double px = 0.0;
-        if (pr) {
-          if (lane == lp) px = ld_cg(&pr->x_first);
-          else if (lane < lp) mine = Aff{ld_cg(&pr->a), ld_cg(&pr->b)};
+        if (j < T) {
+          const RecB* pr = recs + j * C + chain;
+          unsigned long long fa, fb, fx;
+          while (true) {
+            ld_word(&pr->x, px, fx);
+            ld_word(&pr->a, mine.a, fa);
+            ld_word(&pr->b, mine.b, fb);
+            have_x = (fx == FLAG_P);
+            if (have_x || (fa == FLAG_A && fb == FLAG_A)) break;
+          }
         }
+        const unsigned pmask = __ballot_sync(FULL, have_x);
+        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
         for (int l = 0; l < lp; ++l) R = aff_mul(R, Aff{shfl_d(mine.a, l), shfl_d(mine.b, l)});
         if (lp < 32) {
           xfar = shfl_d(px, lp);
@@ -747,10 +750,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
       }
     }
     const double x_in = fma(R.a, xfar, R.b);
-    if (tid == 0) {
-      rec->x_first = fma(tot.a, x_in, tot.b);
-      st_release(&rec->flag, FLAG_P);
-    }
+    if (tid == 0) st_word(&rec->x, fma(tot.a, x_in, tot.b), FLAG_P);
     // ---- descending pass: x and both quadratic forms; x overwrites y in shared memory
     double xn = fma(bex.a, x_in, bex.b);
     double rn = GENERAL ? xn - smu[j0 + TG_K] : xn;
@@ -806,48 +806,36 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
         if (i_t + j < n) xg[j] = sy[j];
     }
   }
-  if (warp == 0) {
-    unsigned int last = 0;
-    if (lane == 0) {
-      double sp = 0.0, sl = 0.0, ld = 0.0;
-      for (int w = 0; w < TG_NW; ++w) { sp += s_part[w]; sl += s_part[TG_NW + w]; ld += s_part[2 * TG_NW + w]; }
-      rec->part[0] = sp;
-      rec->part[1] = sl;
-      rec->part[2] = ld;
-      if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
-      __threadfence();
-      last = (atomicAdd(&chain_done[chain], 1u) == (unsigned int)(T - 1)) ? 1u : 0u;
-    }
-    last = __shfl_sync(FULL, last, 0);
-    if (last) {   // deterministic per-chain reduction of the tile partials
-      __threadfence();
-      double sp = 0.0, sl = 0.0, ld = 0.0;
-      for (long long t = lane; t < T; t += 32) {
-        const RecB* r = recs + t * C + chain;
-        sp += ld_cg(&r->part[0]);
-        sl += ld_cg(&r->part[1]);
-        ld += ld_cg(&r->part[2]);
-      }
-      sp = omc_warp_sum(sp);
-      sl = omc_warp_sum(sl);
-      ld = omc_warp_sum(ld);
-      if (lane == 0) {
-        if (solve && a.ss_prior) a.ss_prior[chain] = sp;
-        if (solve && a.ss_lik) a.ss_lik[chain] = sl;
-        if (DEBUG && a.logdet) a.logdet[chain] = ld;
-        chain_done[chain] = 0;
-      }
-    }
-    // ---- last CTA of the launch advances the epoch
-    if (lane == 0) {
-      __threadfence();
-      if (atomicAdd(&ws->done_b, 1u) == (unsigned int)(T * C - 1)) {
-        ws->done_b = 0;
-        ws->epoch = epoch + 1;
-        __threadfence();
-      }
-      if (solve) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
-    }
+  if (tid == 0) {   // per-tile partials; tg_partials_kernel reduces them per chain in a fixed order
+    double sp = 0.0, sl = 0.0, ld = 0.0;
+    for (int w = 0; w < TG_NW; ++w) { sp += s_part[w]; sl += s_part[TG_NW + w]; ld += s_part[2 * TG_NW + w]; }
+    *reinterpret_cast<double2*>(parts) = make_double2(sp, sl);
+    parts[2] = ld;
+    if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
+    if (solve && bulk_out) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
+  }
+}
+
+// Per-chain sums of the per-tile partials, fixed order (deterministic): one warp per chain.
+__global__ void __launch_bounds__(32) tg_partials_kernel(Workspace* ws, Layout L, int C, double* ss_prior, double* ss_lik,
+                                                          double* logdet) {
+  const int chain = blockIdx.x, lane = threadIdx.x;
+  const double* parts = reinterpret_cast<const double*>(reinterpret_cast<char*>(ws) + L.off_parts);
+  double sp = 0.0, sl = 0.0, ld = 0.0;
+  for (long long t = lane; t < L.n_tiles; t += 32) {
+    const double* p = parts + (t * C + chain) * 4;
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    sp += v.x;
+    sl += v.y;
+    if (logdet) ld += p[2];
+  }
+  sp = omc_warp_sum(sp);
+  sl = omc_warp_sum(sl);
+  ld = omc_warp_sum(ld);
+  if (lane == 0) {
+    if (ss_prior) ss_prior[chain] = sp;
+    if (ss_lik) ss_lik[chain] = sl;
+    if (logdet) logdet[chain] = ld;
   }
 }
 
@@ -856,17 +844,13 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
 // per-tile partials reduced per chain in a fixed order (deterministic).
 __global__ void __launch_bounds__(TG_NT) tg_quadforms_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   __shared__ double s_red[2 * TG_NW];
-  __shared__ unsigned int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.n_chains;
-  const long long T = L.n_tiles;
   const long long tile = blockIdx.x / C;
   const int chain = (int)(blockIdx.x % C);
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
-  RecB* recs = reinterpret_cast<RecB*>(wsb + L.off_recb);
-  RecB* rec = recs + tile * C + chain;
-  unsigned int* chain_done = reinterpret_cast<unsigned int*>(wsb + L.off_chain_done);
+  double* parts = reinterpret_cast<double*>(wsb + L.off_parts) + (tile * C + chain) * 4;
   const double* xg = a.x + (long long)chain * n;
   const double* mup = a.mu0.ptr ? a.mu0.ptr + (long long)chain * a.mu0.chain_stride : nullptr;
   const double* yp = a.y.ptr ? a.y.ptr + (long long)chain * a.y.chain_stride : nullptr;
@@ -896,33 +880,12 @@ __global__ void __launch_bounds__(TG_NT) tg_quadforms_kernel(omc_tridiag_nn_t a,
   if (tid == 0) {
     double sp = 0.0, sl = 0.0;
     for (int w = 0; w < TG_NW; ++w) { sp += s_red[w]; sl += s_red[TG_NW + w]; }
-    rec->part[0] = sp;
-    rec->part[1] = sl;
-    __threadfence();
-    const unsigned int dn = atomicAdd(&chain_done[chain], 1u);
-    s_last = (dn == (unsigned int)(T - 1)) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last && tid < 32) {
-    __threadfence();
-    double sp = 0.0, sl = 0.0;
-    for (long long t = tid; t < T; t += 32) {
-      const RecB* r = recs + t * C + chain;
-      sp += ld_cg(&r->part[0]);
-      sl += ld_cg(&r->part[1]);
-    }
-    sp = omc_warp_sum(sp);
-    sl = omc_warp_sum(sl);
-    if (tid == 0) {
-      if (a.ss_prior) a.ss_prior[chain] = sp;
-      if (a.ss_lik) a.ss_lik[chain] = sl;
-      chain_done[chain] = 0;
-    }
+    *reinterpret_cast<double2*>(parts) = make_double2(sp, sl);
   }
 }
 
 __global__ void tridiag_ws_init_kernel(Workspace* ws, Layout L) {
-  // zero the header, the per-chain counters and every tile record (flags)
+  // zero the header and every tile record (flags)
   const long long words = L.off_flags_end / 8;
   unsigned long long* p = reinterpret_cast<unsigned long long*>(ws);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (long long)gridDim.x * blockDim.x)
@@ -1002,8 +965,17 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   if (int rc = general ? launch_aggregate<true>(*a, ws, L, grid, st) : launch_aggregate<false>(*a, ws, L, grid, st)) return rc;
   tg_tilescan_kernel<<<a->n_chains, TS_NT, 0, st>>>(ws, L, a->n_chains);
   OMC_LAUNCH_CHECK();
-  if (general) return debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
-  return debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
+  int rc;
+  if (general) rc = debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
+  else rc = debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
+  if (rc) return rc;
+  const bool solve = a->x != nullptr;
+  if ((solve && (a->ss_prior || a->ss_lik)) || a->logdet) {
+    tg_partials_kernel<<<a->n_chains, 32, 0, st>>>(ws, L, a->n_chains, solve ? a->ss_prior : nullptr,
+                                                   solve ? a->ss_lik : nullptr, a->logdet);
+    OMC_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
@@ -1011,7 +983,10 @@ int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
   OMC_REQUIRE(a->x, "omc_tridiag_quadforms: x missing");
   const Layout L = make_layout(a->n_chains, a->n);
   const unsigned int grid = (unsigned int)(L.n_tiles * a->n_chains);
-  tg_quadforms_kernel<<<grid, TG_NT, 0, (cudaStream_t)stream>>>(*a, reinterpret_cast<Workspace*>(a->workspace), L);
+  Workspace* ws = reinterpret_cast<Workspace*>(a->workspace);
+  tg_quadforms_kernel<<<grid, TG_NT, 0, (cudaStream_t)stream>>>(*a, ws, L);
+  OMC_LAUNCH_CHECK();
+  tg_partials_kernel<<<a->n_chains, 32, 0, (cudaStream_t)stream>>>(ws, L, a->n_chains, a->ss_prior, a->ss_lik, nullptr);
   OMC_LAUNCH_CHECK();
   return 0;
 }

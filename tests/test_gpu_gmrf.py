@@ -152,7 +152,7 @@ def test_mcmc_replays_reference_gmrf_chain(name):
     np.testing.assert_allclose(M.store["lambda"], g["store_lambda"], rtol=1e-9)
     np.testing.assert_allclose(M.store["tau"], g["store_tau"], rtol=1e-9)
     np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
-    assert M.launches_per_sweep() <= 6   # forward + backward + two gamma draws + counter: the quadratic forms are fused
+    assert M.launches_per_sweep() <= 7   # aggregate + tile scan + solve + partials + two gamma draws + counter: the quadratic forms are fused
 
 
 def test_gmrf_free_running_smoother_recovers_truth():

@@ -3,10 +3,12 @@
 cd "$(dirname "$0")/.."
 OUT=tools/variants; mkdir -p $OUT
 SRC=openmcmc_b200/csrc
-build() { # name flags...
+build() { # name flags...   (only tridiag.cu is recompiled; the other objects come from the regular build)
   name=$1; shift
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -Xptxas -v "$@" \
-     $SRC/tridiag.cu $SRC/omc_api.cu $SRC/dense_draw.cu $SRC/logp.cu $SRC/reg_pass.cu $SRC/mh.cu -o $OUT/libomc_$name.so 2> $OUT/$name.log || { tail -5 $OUT/$name.log; return 1; }
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v "$@" \
+     -c $SRC/tridiag.cu -o $OUT/$name.o 2> $OUT/$name.log || { tail -5 $OUT/$name.log; return 1; }
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libomc_$name.so $OUT/$name.o \
+     $(ls $SRC/build/*.o | grep -v tridiag.o) && rm -f $OUT/$name.o
 }
 if [ "$1" == "build" ]; then
   shift
