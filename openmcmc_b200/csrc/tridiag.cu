@@ -36,6 +36,21 @@
 #include "omc_internal.h"
 #include "omc_logtab.cuh"
 
+#ifdef TG_EXP_TRACE
+// tuning aid (tools/tune_tridiag.sh): per-CTA phase timestamps of the solve kernel, read back with omc_debug_trace_read
+__device__ unsigned long long g_trace[32768 * 16];
+#define TG_TRACE(slot)                                                                      \
+  do {                                                                                      \
+    if (threadIdx.x == 0 && blockIdx.x < 32768) {                                           \
+      unsigned long long t_;                                                                \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                \
+      g_trace[blockIdx.x * 16 + (slot)] = t_;                                                \
+    }                                                                                       \
+  } while (0)
+#else
+#define TG_TRACE(slot)
+#endif
+
 namespace {
 
 #ifndef TG_K_DEF
@@ -50,6 +65,12 @@ constexpr int TG_NW = TG_NT / 32;
 constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per staged array
 constexpr int TG_PAIRS = TG_K / 2;
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef TG_RNG_GROUP
+#define TG_RNG_GROUP 3                    // Philox blocks advanced in lock-step per thread
+#endif
+#ifndef TG_LB_WIN
+#define TG_LB_WIN 4                       // successors polled in the first look-back round
+#endif
 #ifndef TG_SOLVE_MINB
 #define TG_SOLVE_MINB (512 / TG_NT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
 #endif
@@ -268,6 +289,28 @@ __device__ __forceinline__ uint4 normal_block(unsigned long long sw, uint2 key, 
   const uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u,
                                gchain, (site << 20) | (unsigned int)(pair & 0xFFFFFu));
   return philox4x32_10(ctr, key);
+}
+// Philox4x32-10 on G counter blocks in lock-step: G independent multiply chains in flight per thread (one block at a
+// time leaves the thread waiting on every dependent IMAD.WIDE -> LOP3 pair).  Same values as philox4x32_10.
+template <int G>
+__device__ __forceinline__ void philox_group(uint4 (&ctr)[G], uint2 key) {
+  const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const unsigned int hi0 = __umulhi(M0, ctr[i].x), lo0 = M0 * ctr[i].x;
+      const unsigned int hi1 = __umulhi(M1, ctr[i].z), lo1 = M1 * ctr[i].z;
+      ctr[i] = make_uint4(hi1 ^ ctr[i].y ^ key.x, lo1, hi0 ^ ctr[i].w ^ key.y, lo0);
+    }
+    key.x += W0;
+    key.y += W1;
+  }
+}
+__device__ __forceinline__ uint4 normal_counter(unsigned long long sw, unsigned int gchain, unsigned int site,
+                                                unsigned long long pair) {
+  return make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
+                    (site << 20) | (unsigned int)(pair & 0xFFFFFu));
 }
 __device__ __forceinline__ void normal_from(double jp1, double mm, int idx, uint4 b, double& z0, double& z1) {
   // ---- radius
@@ -542,6 +585,14 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   const long long i0 = i_t + j0;
   const int nvalid = (int)max(0ll, min((long long)TG_K, n - i0));   // this thread's elements inside the chain
 
+  TG_TRACE(0);
+#ifdef TG_EXP_TRACE
+  if (tid == 0 && blockIdx.x < 32768) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_trace[blockIdx.x * 16 + 7] = smid;
+  }
+#endif
   // ---- stage the tile (thread 0 issues the bulk copies; nobody waits yet)
   bool bulk;
   {
@@ -581,16 +632,27 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   const double tau = a.tau.ptr ? ld_nc_now(a.tau.ptr + (long long)chain * a.tau.chain_stride) : 1.0;
   // ---- this thread's 18 normals, drawn into registers while the tile loads are in flight
   double g[TG_K], m[TG_K];
+#ifdef TG_EXP_NORNG
+  if (false) {
+#else
   if (!inject && solve && nvalid > 0) {
+#endif
     const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
     const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
     const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
     const unsigned long long pair0 = (unsigned long long)(i0 >> 1);
     unsigned int redo = 0;
 #pragma unroll
-    for (int c = 0; c < TG_PAIRS; ++c) {
-      const uint4 b = normal_block(sweep, key, gchain, a.rng.site, pair0 + c);
-      if (!normal_pair_fast(b, g[2 * c], g[2 * c + 1])) redo |= 1u << c;
+    for (int c0 = 0; c0 < TG_PAIRS; c0 += TG_RNG_GROUP) {
+      uint4 b[TG_RNG_GROUP];
+#pragma unroll
+      for (int i = 0; i < TG_RNG_GROUP; ++i) b[i] = normal_counter(sweep, gchain, a.rng.site, pair0 + c0 + i);
+      philox_group<TG_RNG_GROUP>(b, key);
+#pragma unroll
+      for (int i = 0; i < TG_RNG_GROUP; ++i) {
+        const int c = c0 + i;
+        if (c < TG_PAIRS && !normal_pair_fast(b[i], g[2 * c], g[2 * c + 1])) redo |= 1u << c;
+      }
     }
     while (redo) {   // probability 2^-12 per pair
       const int c = __ffs(redo) - 1;
@@ -611,8 +673,10 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     iu_prev = q / p;
     f_prev = h / q;
   }
+  TG_TRACE(1);                   // thread 0: normals drawn
   __syncthreads();               // mbarrier initialised, plain-load fills visible
   if (bulk) mbar_wait(bar, 0);
+  TG_TRACE(2);                   // tile in shared memory
   if (inject) {
 #pragma unroll
     for (int c = 0; c < TG_PAIRS; ++c) {
@@ -690,6 +754,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     }
   }
   if (bad) s_bad = 1;
+  TG_TRACE(3);                   // ascending pass done (thread 0)
 
   double ssp = 0.0, ssp2 = 0.0, ssl = 0.0;
   bool bulk_out = false;
@@ -717,38 +782,52 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     //      (no CTA barrier, nobody idles); warp 0 publishes the tile's records.
     double xfar = 0.0;     // x beyond the last element is 0 (and its multiplier m_{n-1} is 0)
     Aff R{1.0, 0.0};
+    TG_TRACE(4);                 // CTA scan done, about to publish / poll
+#ifdef TG_EXP_NOLOOKBACK
+    if (false) {
+#else
     if (tile < T - 1) {
+#endif
       if (tid == 0) {
         st_word(&rec->a, tot.a, FLAG_A);
         st_word(&rec->b, tot.b, FLAG_A);
       }
+      TG_TRACE(8);               // aggregate published
+      // The first round polls only the TG_LB_WIN nearest successors: the resolving record is almost always among them,
+      // and records written long ago may have left L2 (a full-width first round paid a DRAM round trip for them).
       long long base = tile + 1;
+      int win = TG_LB_WIN;
       while (true) {
         const long long j = base + lane;
-        bool have_x = true;           // lanes beyond the chain's last tile: x = 0 terminates the walk
+        bool have_x = false;
         Aff mine{1.0, 0.0};
         double px = 0.0;
-        if (j < T) {
-          const RecB* pr = recs + j * C + chain;
-          unsigned long long fa, fb, fx;
-          while (true) {
-            ld_word(&pr->x, px, fx);
-            ld_word(&pr->a, mine.a, fa);
-            ld_word(&pr->b, mine.b, fb);
-            have_x = (fx == FLAG_P);
-            if (have_x || (fa == FLAG_A && fb == FLAG_A)) break;
+        if (lane < win) {
+          have_x = true;                // beyond the chain's last tile: x = 0 terminates the walk
+          if (j < T) {
+            const RecB* pr = recs + j * C + chain;
+            unsigned long long fa, fb, fx;
+            while (true) {
+              ld_word(&pr->x, px, fx);
+              ld_word(&pr->a, mine.a, fa);
+              ld_word(&pr->b, mine.b, fb);
+              have_x = (fx == FLAG_P);
+              if (have_x || (fa == FLAG_A && fb == FLAG_A)) break;
+            }
           }
         }
         const unsigned pmask = __ballot_sync(FULL, have_x);
-        const int lp = pmask ? (__ffs(pmask) - 1) : 32;
+        const int lp = pmask ? (__ffs(pmask) - 1) : win;
         for (int l = 0; l < lp; ++l) R = aff_mul(R, Aff{shfl_d(mine.a, l), shfl_d(mine.b, l)});
-        if (lp < 32) {
+        if (lp < win) {
           xfar = shfl_d(px, lp);
           break;
         }
-        base += 32;
+        base += win;
+        win = 32;
       }
     }
+    TG_TRACE(5);                 // look-back resolved (warp 0)
     const double x_in = fma(R.a, xfar, R.b);
     if (tid == 0) st_word(&rec->x, fma(tot.a, x_in, tot.b), FLAG_P);
     // ---- descending pass: x and both quadratic forms; x overwrites y in shared memory
@@ -814,6 +893,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
     if (solve && bulk_out) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
   }
+  TG_TRACE(6);
 }
 
 // Per-chain sums of the per-tile partials, fixed order (deterministic): one warp per chain.
@@ -939,6 +1019,12 @@ int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsi
 
 extern "C" {
 
+#ifdef TG_EXP_TRACE
+int omc_debug_trace_read(void* dst, long long bytes) {
+  return (int)cudaMemcpyFromSymbol(dst, g_trace, (size_t)bytes);
+}
+#endif
+
 int omc_tridiag_workspace(int n_chains, long long n, long long* bytes) {
   OMC_REQUIRE(n_chains >= 1 && n >= 1 && bytes, "omc_tridiag_workspace: bad argument");
   *bytes = make_layout(n_chains, n).total;
@@ -962,10 +1048,15 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
   const bool debug = a->debug_z || a->logdet || a->probe_l || a->probe_c || !a->x;
+#ifndef TG_EXP_SKIP_AGG
   if (int rc = general ? launch_aggregate<true>(*a, ws, L, grid, st) : launch_aggregate<false>(*a, ws, L, grid, st)) return rc;
+#endif
   tg_tilescan_kernel<<<a->n_chains, TS_NT, 0, st>>>(ws, L, a->n_chains);
   OMC_LAUNCH_CHECK();
   int rc;
+#ifdef TG_EXP_SKIP_SOLVE
+  return 0;
+#endif
   if (general) rc = debug ? launch_solve<true, true>(*a, ws, L, grid, st) : launch_solve<true, false>(*a, ws, L, grid, st);
   else rc = debug ? launch_solve<false, true>(*a, ws, L, grid, st) : launch_solve<false, false>(*a, ws, L, grid, st);
   if (rc) return rc;
