@@ -65,6 +65,9 @@ constexpr int TG_NW = TG_NT / 32;
 constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per staged array
 constexpr int TG_PAIRS = TG_K / 2;
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef TG_AGG_G
+#define TG_AGG_G 2                        // chains per CTA of the aggregate kernel (the shared P tile is staged once)
+#endif
 #ifndef TG_RNG_GROUP
 #define TG_RNG_GROUP 3                    // Philox blocks advanced in lock-step per thread
 #endif
@@ -240,7 +243,7 @@ struct Stage {
 // plain loads.  Returns whether the bulk path was taken; stage_wait() makes the data visible to every thread.
 template <int CNT>
 __device__ __forceinline__ bool stage_issue(const Stage (&st)[CNT], long long i_t, long long n, unsigned long long* bar,
-                                            int tid) {
+                                            int tid, int n_threads = TG_NT) {
   bool bulk = (i_t + TG_TILE < n);
 #pragma unroll
   for (int q = 0; q < CNT; ++q)
@@ -260,7 +263,7 @@ __device__ __forceinline__ bool stage_issue(const Stage (&st)[CNT], long long i_
 #pragma unroll
   for (int q = 0; q < CNT; ++q) {
     if (!st[q].dst || (st[q].src && bulk)) continue;
-    for (int j = tid; j < TG_TILE; j += TG_NT) {
+    for (int j = tid; j < TG_TILE; j += n_threads) {
       const long long i = i_t + j;
       st[q].dst[j] = (st[q].src && i < st[q].limit) ? __ldg(st[q].src + i) : st[q].fill;
     }
@@ -373,42 +376,56 @@ __device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 ke
 }
 
 // ---------------------------------------------------------------------------------------------- aggregate kernel
-template <bool GENERAL>
-__global__ void __launch_bounds__(TG_NT) tg_aggregate_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
+// G chains per CTA (G x TG_NT threads): the tile of the shared P is staged ONCE for the G chains, which halves (G = 2)
+// or quarters (G = 4) the shared memory per resident warp -- this kernel is a load -> compute -> store pipeline whose
+// only latency hiding is the number of CTAs resident next to each other.  GENERAL (weights / prior mean) keeps G = 1.
+template <bool GENERAL, int G>
+__global__ void __launch_bounds__(TG_NT* G) tg_aggregate_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L, int n_groups) {
+  static_assert(!GENERAL || G == 1, "GENERAL aggregate kernel stages per-chain arrays for one chain only");
   extern __shared__ __align__(128) double sm[];
-  __shared__ double s_tot[TG_NW][7];
+  __shared__ double s_tot[G][TG_NW][7];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
   double* spd = spe + TG_TILE;
-  double* sy = spd + TG_TILE;
-  double* sw = sy + TG_TILE;       // GENERAL only
+  double* sy0 = spd + TG_TILE;     // G tiles of y, one per chain of the group
+  double* sw = sy0 + TG_TILE;      // GENERAL only
   double* sh = sw + TG_TILE;       // GENERAL only
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
+  const int sub = threadIdx.x / TG_NT;            // which chain of the group
+  const int tid = threadIdx.x % TG_NT, lane = tid & 31, warp = tid >> 5;
+  if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
   const int C = a.n_chains;
-  const long long tile = blockIdx.x / C;     // tile-major: the chains read the same tile of the shared P together
-  const int chain = (int)(blockIdx.x % C);
+  const long long tile = blockIdx.x / n_groups;   // tile-major: the chains read the same tile of the shared P together
+  const int chain0 = (int)(blockIdx.x % n_groups) * G;
+  const int chain = chain0 + sub;
+  const bool live = chain < C;                    // ragged last group
+  const int cc = live ? chain : C - 1;
   const long long n = a.n;
   char* wsb = reinterpret_cast<char*>(ws);
   const long long i_t = tile * TG_TILE;
-  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)chain * a.lambda.chain_stride] : 1.0;
-  const double tau = a.tau.ptr ? a.tau.ptr[(long long)chain * a.tau.chain_stride] : 1.0;
+  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)cc * a.lambda.chain_stride] : 1.0;
+  const double tau = a.tau.ptr ? a.tau.ptr[(long long)cc * a.tau.chain_stride] : 1.0;
+  double* sy = sy0 + sub * TG_TILE;
 
-  const double* yp = a.y.ptr + (long long)chain * a.y.chain_stride;
-  if (tid == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+  if (threadIdx.x == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
   bool bulk;
   if (GENERAL) {
+    const double* yp = a.y.ptr + (long long)cc * a.y.chain_stride;
     const Stage st[5] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
-                         {a.w.ptr ? a.w.ptr + (long long)chain * a.w.chain_stride : nullptr, n, 1.0, sw},
-                         {a.h.ptr ? a.h.ptr + (long long)chain * a.h.chain_stride : nullptr, n, 0.0, sh}};
-    bulk = stage_issue<5>(st, i_t, n, bar, tid);
+                         {a.w.ptr ? a.w.ptr + (long long)cc * a.w.chain_stride : nullptr, n, 1.0, sw},
+                         {a.h.ptr ? a.h.ptr + (long long)cc * a.h.chain_stride : nullptr, n, 0.0, sh}};
+    bulk = stage_issue<5>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
   } else {
-    const Stage st[3] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy}};
-    bulk = stage_issue<3>(st, i_t, n, bar, tid);
+    Stage st[2 + G];
+    st[0] = Stage{a.pe, n - 1, 0.0, spe};
+    st[1] = Stage{a.pd, n, 1.0, spd};
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      st[2 + g] = Stage{a.y.ptr + (long long)min(chain0 + g, C - 1) * a.y.chain_stride, n, 0.0, sy0 + g * TG_TILE};
+    bulk = stage_issue<2 + G>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
   }
   stage_wait(bulk, bar);
 
@@ -455,25 +472,25 @@ __global__ void __launch_bounds__(TG_NT) tg_aggregate_kernel(omc_tridiag_nn_t a,
   }
   tm_normalize(inc);
   if (lane == 31) {
-    s_tot[warp][0] = inc.a; s_tot[warp][1] = inc.b; s_tot[warp][2] = inc.c; s_tot[warp][3] = inc.d;
-    s_tot[warp][4] = inc.e; s_tot[warp][5] = inc.f; s_tot[warp][6] = inc.g;
+    s_tot[sub][warp][0] = inc.a; s_tot[sub][warp][1] = inc.b; s_tot[sub][warp][2] = inc.c; s_tot[sub][warp][3] = inc.d;
+    s_tot[sub][warp][4] = inc.e; s_tot[sub][warp][5] = inc.f; s_tot[sub][warp][6] = inc.g;
   }
   __syncthreads();
   TM wex = tm_identity();   // composition of the warps below this one
   for (int w = 0; w < warp; ++w) {
-    const TM ww{s_tot[w][0], s_tot[w][1], s_tot[w][2], s_tot[w][3], s_tot[w][4], s_tot[w][5], s_tot[w][6]};
+    const TM ww{s_tot[sub][w][0], s_tot[sub][w][1], s_tot[sub][w][2], s_tot[sub][w][3], s_tot[sub][w][4], s_tot[sub][w][5], s_tot[sub][w][6]};
     wex = tm_mul(ww, wex);
   }
   TM ex = tm_shfl_up(inc, 1);
   if (lane == 0) ex = tm_identity();
   ex = tm_mul(ex, wex);       // exclusive prefix of this thread inside the tile
   tm_normalize(ex);
-  {
+  if (live) {
     double* exg = reinterpret_cast<double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + tile) * 7 * TG_NT + tid;
     exg[0 * TG_NT] = ex.a; exg[1 * TG_NT] = ex.b; exg[2 * TG_NT] = ex.c; exg[3 * TG_NT] = ex.d;
     exg[4 * TG_NT] = ex.e; exg[5 * TG_NT] = ex.f; exg[6 * TG_NT] = ex.g;
   }
-  if (tid == TG_NT - 1) {     // tile total = the last thread's inclusive prefix
+  if (live && tid == TG_NT - 1) {     // tile total = the last thread's inclusive prefix
     TM tot = tm_mul(inc, wex);
     tm_normalize(tot);
     double* tt = reinterpret_cast<double*>(wsb + L.off_tt) + (tile * C + chain) * 8;
@@ -993,16 +1010,17 @@ int check_args(const omc_tridiag_nn_t* a, const char* who) {
   return 0;
 }
 
-constexpr int aggregate_smem_doubles(bool general) { return 4 + (general ? 5 : 3) * TG_TILE + 4; }
+constexpr int aggregate_smem_doubles(bool general, int g) { return 4 + (general ? 5 : 2 + g) * TG_TILE + 4; }
 constexpr int solve_smem_doubles(bool general, bool debug) {
   return 4 + (3 + (debug ? 1 : 0) + (general ? 3 : 0)) * TG_TILE + 4;
 }
 
-template <bool GENERAL>
-int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
-  const int smem = aggregate_smem_doubles(GENERAL) * 8;
-  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_aggregate_kernel<GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tg_aggregate_kernel<GENERAL><<<grid, TG_NT, smem, st>>>(a, ws, L);
+template <bool GENERAL, int G>
+int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, cudaStream_t st) {
+  const int smem = aggregate_smem_doubles(GENERAL, G) * 8;
+  const int n_groups = (a.n_chains + G - 1) / G;
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_aggregate_kernel<GENERAL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tg_aggregate_kernel<GENERAL, G><<<(unsigned int)(L.n_tiles * n_groups), TG_NT * G, smem, st>>>(a, ws, L, n_groups);
   OMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1049,7 +1067,13 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
   const bool debug = a->debug_z || a->logdet || a->probe_l || a->probe_c || !a->x;
 #ifndef TG_EXP_SKIP_AGG
-  if (int rc = general ? launch_aggregate<true>(*a, ws, L, grid, st) : launch_aggregate<false>(*a, ws, L, grid, st)) return rc;
+  {
+    int rc;
+    if (general) rc = launch_aggregate<true, 1>(*a, ws, L, st);
+    else if (a->n_chains >= TG_AGG_G) rc = launch_aggregate<false, TG_AGG_G>(*a, ws, L, st);
+    else rc = launch_aggregate<false, 1>(*a, ws, L, st);
+    if (rc) return rc;
+  }
 #endif
   tg_tilescan_kernel<<<a->n_chains, TS_NT, 0, st>>>(ws, L, a->n_chains);
   OMC_LAUNCH_CHECK();

@@ -37,7 +37,7 @@ def _dev(a):
 @pytest.mark.parametrize("n,C,irregular,weighted,with_mu", [
     (1, 2, False, False, False), (2, 3, False, True, True), (7, 2, True, False, False), (2047, 2, False, False, True),
     (2048, 3, True, True, False), (2049, 2, False, False, False), (10000, 3, True, True, True),
-    (70001, 2, False, False, False)])
+    (70001, 2, False, False, False), (5000, 3, True, False, False), (4609, 5, False, False, False)])
 def test_tridiag_draw_matches_oracle(n, C, irregular, weighted, with_mu):
     import torch
 
