@@ -94,6 +94,15 @@ typedef struct {
   double* probe_L;      /* optional [n_chains][p*p] lower Cholesky factor                    */
   double* probe_mu;     /* optional [n_chains][p] posterior mean                             */
   int* status;          /* optional [n_chains], OR-ed with OMC_STATUS_*                      */
+  /* Truncated prior (domain_response_lower / upper on the Normal prior): the draw becomes ONE coordinate-wise Gibbs
+   * scan from the current beta,  beta_i ~ N(v_i (b_i - Q_i. beta + Q_ii beta_i), v_i = 1/Q_ii) truncated to
+   * [lo_i, hi_i], one truncnorm.rvs uniform per coordinate; p == 1 draws from N(b/Q, 1/Q) truncated.
+   *   ref: sampler.py:196-205, gmrf.py:201-266 (gibbs_canonical_truncated_normal), gmrf.py:269-292 */
+  int truncated;        /* 0: plain draw above (trunc_* ignored)                             */
+  omc_vec_t trunc_lo, trunc_hi; /* bounds, trunc_lo_len / trunc_hi_len in {1, p} values (NULL => -inf / +inf) */
+  int trunc_lo_len, trunc_hi_len;
+  const double* debug_u; /* injected uniforms behind truncnorm.rvs [n_chains][p]; NULL => Philox; strided by
+                            debug_sweep_stride like debug_z                                   */
 } omc_nn_dense_t;
 int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream);
 
@@ -164,6 +173,12 @@ int omc_logp_poisson(const omc_logp_poisson_t* args, void* stream);
 
 /* out[c] (+)= value  — constant log-densities such as Uniform (ref: distribution.py:422-442) */
 int omc_logp_const(double value, int n_chains, double* out, int accumulate, void* stream);
+
+/* out[c] += -inf when any of the n_elem values x[c] lies outside [lower, upper] (bounds: lo_len / hi_len in {1, n_elem}
+ * values, NULL => unbounded): the domain test of a truncated Normal, whose log_p ignores the truncation normaliser
+ * ref: location_scale.py:148-151,164-165 */
+int omc_logp_domain(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int lo_len, omc_vec_t upper, int hi_len,
+                    double* out, void* stream);
 
 /* yhat[c] = sum_t X_t[c] @ theta_t[c] for up to 4 terms (ref: parameter.py:162-197 LinearCombination.predictor) */
 typedef struct {

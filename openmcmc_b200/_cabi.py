@@ -53,6 +53,12 @@ class NNDense(C.Structure):
         ("probe_L", C.c_void_p),
         ("probe_mu", C.c_void_p),
         ("status", C.c_void_p),
+        ("truncated", C.c_int),
+        ("trunc_lo", Vec),
+        ("trunc_hi", Vec),
+        ("trunc_lo_len", C.c_int),
+        ("trunc_hi_len", C.c_int),
+        ("debug_u", C.c_void_p),
     ]
 
 
@@ -189,6 +195,7 @@ PROTOTYPES = {
     "omc_logp_gamma": (C.c_int, [C.POINTER(LogpGamma), C.c_void_p]),
     "omc_logp_poisson": (C.c_int, [C.POINTER(LogpPoisson), C.c_void_p]),
     "omc_logp_const": (C.c_int, [C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "omc_logp_domain": (C.c_int, [C.c_int, C.c_int, Vec, Vec, C.c_int, Vec, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -8,6 +8,7 @@
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"
+#include "omc_special.cuh"
 
 namespace {
 
@@ -67,6 +68,44 @@ __global__ void __launch_bounds__(DD_THREADS) nn_dense_draw_kernel(omc_nn_dense_
     s += tau * rec[p * p + i];
     b[i] = s;
     if (a.probe_b) a.probe_b[(long long)chain * p + i] = s;
+  }
+  if (a.truncated) {
+    // ---- truncated prior: one coordinate-wise Gibbs scan from the current beta (gmrf.py:201-266), warp 0
+    __syncthreads();
+    if (warp == 0) {
+      double* bt = a.beta + (long long)chain * p;
+      double x0 = (lane < p) ? bt[lane] : 0.0, x1 = (lane + 32 < p) ? bt[lane + 32] : 0.0;
+      const double* du = a.debug_u
+                             ? a.debug_u + (a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride +
+                                   (long long)chain * p
+                             : nullptr;
+      OmcRng rng = to_rng(a.rng);
+      for (int i = 0; i < p; ++i) {
+        double part = 0.0;
+        if (lane < p) part = Q[i * ld + lane] * x0;
+        if (lane + 32 < p) part = fma(Q[i * ld + lane + 32], x1, part);
+        const double dot = omc_warp_sum(part);
+        const double xi = __shfl_sync(0xffffffffu, (i < 32) ? x0 : x1, i & 31);
+        const double qii = Q[i * ld + i];
+        const double v = 1.0 / qii;
+        const double mean = (p == 1) ? b[0] / qii : v * (b[i] - dot + qii * xi);
+        const double lo = a.trunc_lo.ptr ? vec_at(a.trunc_lo, chain, a.trunc_lo_len > 1 ? i : 0, 0.0) : -INFINITY;
+        const double hi = a.trunc_hi.ptr ? vec_at(a.trunc_hi, chain, a.trunc_hi_len > 1 ? i : 0, 0.0) : INFINITY;
+        double u;
+        if (du) u = du[i];
+        else {
+          const uint4 blk = omc_rng_block(rng, chain, (unsigned int)i);
+          u = omc_u01(blk.x, blk.y);
+        }
+        const double xn = omc_truncated_normal_rv(mean, sqrt(v), lo, hi, u);
+        if (!(qii > 0.0) && lane == 0) bad = 1;
+        if (lane == (i & 31)) { if (i < 32) x0 = xn; else x1 = xn; }
+      }
+      if (lane < p) bt[lane] = x0;
+      if (lane + 32 < p) bt[lane + 32] = x1;
+      if (lane == 0 && bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
+    }
+    return;
   }
   // z: injected or Philox/Box-Muller
   if (a.debug_z) {

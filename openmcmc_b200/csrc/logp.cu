@@ -109,6 +109,18 @@ __global__ void __launch_bounds__(64) logdet_dense_kernel(const double* P, int n
   }
   if (tid == 0) out[blockIdx.x] = ld;
 }
+__global__ void logp_domain_kernel(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int lo_len, omc_vec_t upper,
+                                   int hi_len, double* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  bool outside = false;
+  for (int i = 0; i < n_elem; ++i) {
+    const double v = x.ptr[(long long)c * x.chain_stride + i];
+    if (lower.ptr && v < lower.ptr[(long long)c * lower.chain_stride + (lo_len > 1 ? i : 0)]) outside = true;
+    if (upper.ptr && v > upper.ptr[(long long)c * upper.chain_stride + (hi_len > 1 ? i : 0)]) outside = true;
+  }
+  if (outside) out[c] = -INFINITY;
+}
 }  // namespace
 
 extern "C" {
@@ -146,6 +158,14 @@ int omc_logp_poisson(const omc_logp_poisson_t* a, void* stream) {
 int omc_logp_const(double value, int n_chains, double* out, int accumulate, void* stream) {
   OMC_REQUIRE(out && n_chains >= 1, "omc_logp_const: bad argument");
   logp_const_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(value, n_chains, out, accumulate);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_logp_domain(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int lo_len, omc_vec_t upper, int hi_len,
+                    double* out, void* stream) {
+  OMC_REQUIRE(out && x.ptr && n_chains >= 1 && n_elem >= 1, "omc_logp_domain: bad argument");
+  logp_domain_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_chains, n_elem, x, lower, lo_len, upper,
+                                                                              hi_len, out);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -511,8 +511,6 @@ def compile_log_post(plan: Plan, host_state, model, out):
         if isinstance(dist, NullDistribution):
             continue
         if isinstance(dist, Normal):
-            if dist.domain_response_lower is not None or dist.domain_response_upper is not None:
-                raise PlanError("log_post with truncated Normal members is not supported on the device yet")
             mname, sname = _scalar_and_matrix(dist.precision)
             ss_vec, _, qname = get_quadratic_form(plan, host_state, dist)
             P = ensure_matrix(st, host_state, mname)
@@ -526,6 +524,24 @@ def compile_log_post(plan: Plan, host_state, model, out):
                                  K.vec(logdet) if logdet is not None else K.vec(None), out, acc)
 
             plan.emit(launch, f"logp_normal[{dist.response}]")
+            if dist.domain_response_lower is not None or dist.domain_response_upper is not None:
+                # -inf outside the domain; the truncation normaliser is ignored (location_scale.py:148-151,164-165)
+                x = st[dist.response]
+
+                def bound(v, size=x.size):
+                    if v is None:
+                        return K.vec(None), 1
+                    t = plan.keep_tensor(torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1)).to(st.device))
+                    if t.numel() not in (1, size):
+                        raise ValueError(f"domain bound of size {t.numel()} for a response of size {size}")
+                    return K.vec(t), int(t.numel())
+
+                (lo_v, lo_n), (hi_v, hi_n) = bound(dist.domain_response_lower), bound(dist.domain_response_upper)
+
+                def launch(x=x, lo_v=lo_v, lo_n=lo_n, hi_v=hi_v, hi_n=hi_n):
+                    K.logp_domain(C, x.size, x.vec(), lo_v, lo_n, hi_v, hi_n, out)
+
+                plan.emit(launch, f"logp_domain[{dist.response}]")
         elif isinstance(dist, Gamma):
             x = st[dist.response]
             if not isinstance(dist.shape, Identity) or not isinstance(dist.rate, Identity):

@@ -82,8 +82,14 @@ def reg_pass(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_
 
 
 def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, rng_, debug_z=None, probe_Q=None,
-                  probe_b=None, probe_L=None, probe_mu=None, status=None, debug_sweep_stride=0):
+                  probe_b=None, probe_L=None, probe_mu=None, status=None, debug_sweep_stride=0, trunc=None,
+                  debug_u=None):
+    """trunc = (lo_vec, lo_len, hi_vec, hi_len) switches to the truncated-prior Gibbs scan (omc.h)."""
     a = _cabi.NNDense()
+    if trunc is not None:
+        a.truncated = 1
+        a.trunc_lo, a.trunc_lo_len, a.trunc_hi, a.trunc_hi_len = trunc
+        a.debug_u = debug_u.data_ptr() if debug_u is not None else None
     a.n_chains, a.p = n_chains, p
     a.stats = Vec(stats.data_ptr(), p * p + p + 2)
     a.tau, a.prior_kind, a.prior_P, a.lam, a.mu0 = tau, prior_kind, prior_P, lam, mu0
@@ -132,6 +138,11 @@ def logp_gamma(n_chains, n_elem, x, shape, shape_len, rate, rate_len, out, accum
 def logp_poisson(n_chains, n_elem, k, rate, rate_len, out, accumulate):
     a = _cabi.LogpPoisson(n_chains, n_elem, rate_len, k, rate, out.data_ptr(), int(accumulate))
     check(lib().omc_logp_poisson(C.byref(a), stream_ptr()), "omc_logp_poisson")
+
+
+def logp_domain(n_chains, n_elem, x, lower, lo_len, upper, hi_len, out):
+    check(lib().omc_logp_domain(n_chains, n_elem, x, lower, int(lo_len), upper, int(hi_len), _ptr(out), stream_ptr()),
+          "omc_logp_domain")
 
 
 def logp_const(value, n_chains, out, accumulate):

@@ -77,7 +77,10 @@ class NormalNormal(MCMCSampler):
                   any small (p <= 64) prior precision          -> omc_reg_pass + omc_nn_dense_draw
       * banded  : one Normal likelihood with mean = param (Identity), diagonal/identity response precision, tridiagonal
                   prior precision (temporal GMRF)              -> omc_tridiag_nn_draw
-    Truncated priors (gibbs_canonical_truncated_normal) are SURVEY §8 f3 ("next").
+    Truncated priors (domain_response_lower / upper on the Normal prior; sampler.py:196-205 ->
+    gmrf.gibbs_canonical_truncated_normal) are supported on the dense path: the draw becomes one
+    coordinate-wise truncated-normal Gibbs scan from the current value.  `debug_draws={"u": ...}` injects the uniforms
+    behind the reference's truncnorm.rvs calls.
     """
 
     def __post_init__(self):
@@ -88,8 +91,6 @@ class NormalNormal(MCMCSampler):
         prior = self.model[self.param]
         if not isinstance(prior, Normal):
             raise engine.PlanError("NormalNormal needs a Normal prior on the sampled parameter")
-        if prior.domain_response_lower is not None or prior.domain_response_upper is not None:
-            raise engine.PlanError("truncated NormalNormal is outside the round-1 hot path (SURVEY.md §8 f3)")
         liks = [d for k, d in self.model.items() if not self._is_response[k]]
         if len(liks) != 1 or not isinstance(liks[0], Normal):
             raise engine.PlanError("the device NormalNormal supports exactly one Normal likelihood term")
@@ -97,6 +98,9 @@ class NormalNormal(MCMCSampler):
         from openmcmc_b200 import gmrf_plan
 
         if gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, lik):
+            if prior.domain_response_lower is not None or prior.domain_response_upper is not None:
+                raise engine.PlanError("a truncated prior on the tridiagonal (GMRF) path is not supported: the "
+                                       "coordinate-wise scan of gmrf.py:201-266 is sequential over 1e6 elements")
             return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, lik, debug_draws)
         if isinstance(lik.mean, LinearCombination):
             return self._compile_dense(plan, host_state, prior, lik, debug_draws)
@@ -130,16 +134,32 @@ class NormalNormal(MCMCSampler):
                 probes = {k: plan.new(C, p, p) for k in ("Q", "L")}
                 probes.update({k: plan.new(C, p) for k in ("b", "mu")})
                 plan.probes[self.param] = ctx["probes"] = probes
-        rng, dz, dz_stride, probes = ctx["rng"], ctx["dz"], ctx["dz_stride"], ctx["probes"]
+            ctx["trunc"] = None
+            lo, hi = prior.domain_response_lower, prior.domain_response_upper
+            if lo is not None or hi is not None:
+                # ref gmrf.py:236-243: missing bounds are -inf / +inf, scalars broadcast over the p coordinates
+                def bound(v):
+                    if v is None:
+                        return K.vec(None), 1
+                    t = plan.keep_tensor(engine.torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1)).to(st.device))
+                    if t.numel() not in (1, p):
+                        raise ValueError(f"truncation bound of size {t.numel()} for a parameter of size {p}")
+                    return K.vec(t), int(t.numel())
+
+                (lo_v, lo_n), (hi_v, hi_n) = bound(lo), bound(hi)
+                ctx["trunc"] = (lo_v, lo_n, hi_v, hi_n)
+                if debug_draws and "u" in debug_draws:
+                    ctx["dz"], ctx["dz_stride"] = plan.debug_tensor(debug_draws["u"], p)
+        rng, dz, dz_stride, probes, trunc = ctx["rng"], ctx["dz"], ctx["dz_stride"], ctx["probes"], ctx["trunc"]
         plan.require(rl.q_gg)
 
         def launch():
             K.nn_dense_draw(
                 C, p, rl.stats, tau.vec() if tau else K.vec(None), engine._mat_kind(P0), P0.vec(),
-                lam.vec() if lam else K.vec(None), mu0.vec(), beta.data, rng, debug_z=dz,
+                lam.vec() if lam else K.vec(None), mu0.vec(), beta.data, rng, debug_z=None if trunc else dz,
                 probe_Q=probes["Q"] if probes else None, probe_b=probes["b"] if probes else None,
                 probe_L=probes["L"] if probes else None, probe_mu=probes["mu"] if probes else None, status=plan.status,
-                debug_sweep_stride=dz_stride)
+                debug_sweep_stride=dz_stride, trunc=trunc, debug_u=dz if trunc else None)
 
         plan.emit(launch, f"nn_dense_draw[{self.param}]")
         plan.wrote(self.param)

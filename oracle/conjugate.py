@@ -57,6 +57,22 @@ def normal_normal_dense(G, g, tau, P0, lam, mu0, z):
     return {"Q": Q, "b": b, "L": L, "mu": mu, "x": x}
 
 
+def normal_normal_dense_truncated(G, g, tau, P0, lam, mu0, x, lower, upper, u):
+    """NormalNormal.sample with a truncated Normal prior: same (Q, b) as normal_normal_dense, then ONE coordinate-wise
+    Gibbs scan from the current value x.  ref: sampler.py:196-205 -> gmrf.gibbs_canonical_truncated_normal."""
+    p = G.shape[0]
+    P0 = np.asarray(P0, dtype=np.float64)
+    if P0.ndim == 0:
+        P0 = float(P0) * np.eye(p)
+    elif P0.ndim == 1:
+        P0 = np.diag(P0)
+    mu0 = np.zeros((p, 1)) if mu0 is None else np.asarray(mu0, dtype=np.float64).reshape(p, 1)
+    Q_prior = float(lam) * P0
+    Q = Q_prior + float(tau) * G
+    b = Q_prior @ mu0 + float(tau) * np.asarray(g, dtype=np.float64).reshape(p, 1)
+    return {"Q": Q, "b": b, "x": gmrf.gibbs_canonical_truncated_normal(b, Q, x, lower, upper, u)}
+
+
 def normal_gamma(a0, b0, ss, cnt, g):
     """NormalGamma.sample for a scalar precision.  ref: sampler.py:252-288.
 

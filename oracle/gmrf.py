@@ -241,3 +241,28 @@ def truncated_normal_log_pdf(x, mean, scale, lower, upper):
         out = -0.5 * z * z - 0.5 * np.log(2 * np.pi) - _log_gauss_mass(a, b) - np.log(scale)
     out = np.where((z < a) | (z > b), -np.inf, out)
     return out
+
+
+def gibbs_canonical_truncated_normal(b, Q, x, lower, upper, u):
+    """One coordinate-wise Gibbs scan of x ~ N_c(Q^-1 b, Q^-1) truncated to [lower, upper] (Rue & Held lemma 2.1).
+
+    ref: gmrf.py:201-266.  `u` [p] are the uniforms behind the p truncnorm.rvs calls (one per coordinate, in order);
+    bounds are scalars or [p] (None => -inf / +inf, gmrf.py:236-243).  p == 1 draws from N(b/Q, 1/Q) truncated (:245-248).
+    """
+    Q = np.asarray(Q, dtype=np.float64)
+    p = Q.shape[0]
+    b = np.asarray(b, dtype=np.float64).reshape(p)
+    x = np.array(x, dtype=np.float64).reshape(p)
+    u = np.asarray(u, dtype=np.float64).reshape(p)
+    lower = np.broadcast_to(-np.inf if lower is None else np.asarray(lower, dtype=np.float64).reshape(-1), (p,))
+    upper = np.broadcast_to(np.inf if upper is None else np.asarray(upper, dtype=np.float64).reshape(-1), (p,))
+    if p == 1:
+        x[0] = truncated_normal_rv(b[0] / Q[0, 0], 1.0 / np.sqrt(Q[0, 0]), lower[0], upper[0], u[0])
+        return x.reshape(p, 1)
+    for i in range(p):
+        q_ii = Q[i, i]
+        v_i = 1.0 / q_ii
+        cond_mean = v_i * (b[i] - Q[i, :] @ x + q_ii * x[i])
+        x[i] = truncated_normal_rv(cond_mean, np.sqrt(v_i), lower[i], upper[i], u[i])
+    return x.reshape(p, 1)
+

@@ -83,7 +83,9 @@ class Streams:
 
 
 # ----------------------------------------------------------------------------------------------- regression (C1 shape)
-def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "lambda"), prior="eye"):
+def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "lambda"), prior="eye", trunc=None):
+    """trunc = (lower, upper) (size-1 arrays or None): truncated Normal prior on beta -> NormalNormal.sample runs
+    gmrf.gibbs_canonical_truncated_normal (sampler.py:196-205); its truncnorm.rvs uniforms are recorded in `tn_u`."""
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((n, p))
     X[:, 0] = 1.0
@@ -104,7 +106,9 @@ def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "l
     mu = rng.standard_normal((p, 1)) * 0.1
     mdl = Model(
         [Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
-         Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+         Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda"),
+                domain_response_lower=None if trunc is None else trunc[0],
+                domain_response_upper=None if trunc is None else trunc[1]),
          Gamma("tau", shape="a_tau", rate="b_tau"),
          Gamma("lambda", shape="a_lambda", rate="b_lambda")],
         response={"y": "mean"},
@@ -130,6 +134,10 @@ def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "l
         "store_beta": M.store["beta"], "store_tau": M.store["tau"], "store_lambda": M.store["lambda"],
         "store_log_post": M.store["log_post"], "store_y": M.store["y"],
     }
+    if trunc is not None:
+        out["tn_u"] = s.stack("tn_u").reshape(n_iter, p)
+        out["lower"] = np.array([-np.inf]) if trunc[0] is None else np.asarray(trunc[0], dtype=float).ravel()
+        out["upper"] = np.array([np.inf]) if trunc[1] is None else np.asarray(trunc[1], dtype=float).ravel()
     return out
 
 
@@ -450,6 +458,10 @@ def main():
         "regression_n300_p17_dense_reordered": regression_case(300, 17, 2, 4, order=("tau", "lambda", "beta"),
                                                                prior="dense"),
         "regression_n1000_p64": regression_case(1000, 64, 3, 3),
+        "truncreg_n120_p6_two_sided": regression_case(120, 6, 4, 5, trunc=(np.array([[-0.2]]), np.array([[0.6]]))),
+        "truncreg_n80_p40_upper_dense": regression_case(80, 40, 5, 3, prior="dense", weighted=True,
+                                                        trunc=(None, np.array([[0.25]]))),
+        "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
     }
     which = sys.argv[1:] or ["regression", "mh", "gmrf", "rj"]
     if "regression" not in which:

@@ -44,6 +44,32 @@ def test_regression_chain_replay(name):
         np.testing.assert_allclose(lp, g["store_log_post"][it, 0], rtol=1e-10)
 
 
+@pytest.mark.parametrize("name", sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "truncreg_*.npz"))))
+def test_truncated_regression_chain_replay(name):
+    """Truncated Normal prior on beta: NormalNormal.sample is one coordinate-wise truncated Gibbs scan
+    (sampler.py:196-205, gmrf.py:201-266); replay of the reference chain with its truncnorm.rvs uniforms injected."""
+    g = _load(name)
+    X, y, mu = g["X"], g["y"], g["mu"]
+    n, p = X.shape
+    w = g["w"] if g["w"].size else None
+    P0 = g["P_lambda"]
+    state = {"beta": np.zeros((p, 1)), "tau": 1.0, "lambda": 0.01}
+    if p == 1:
+        assert g["lower"][0] > 0   # the start value 0 lies outside: the p == 1 branch ignores it (gmrf.py:245-248)
+    for it in range(g["store_beta"].shape[1]):
+        G, gv, _, _ = conjugate.regression_suffstats(X, y, w)
+        state["beta"] = conjugate.normal_normal_dense_truncated(G, gv, state["tau"], P0, state["lambda"], mu,
+                                                                state["beta"], g["lower"], g["upper"], g["tn_u"][it])["x"]
+        np.testing.assert_allclose(state["beta"].ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-12)
+        assert np.all(state["beta"] >= g["lower"][0]) and np.all(state["beta"] <= g["upper"][0])
+        _, _, rss, cnt = conjugate.regression_suffstats(X, y, w, state["beta"])
+        state["tau"], _, _ = conjugate.normal_gamma(1e-3, 1e-3, rss, cnt, g["g_tau"][it])
+        ss, cnt = conjugate.quadform(P0, state["beta"], mu)
+        state["lambda"], _, _ = conjugate.normal_gamma(1e-3, 1e-3, ss, cnt, g["g_lambda"][it])
+        np.testing.assert_allclose(state["tau"], g["store_tau"][0, it], rtol=1e-10)
+        np.testing.assert_allclose(state["lambda"], g["store_lambda"][0, it], rtol=1e-10)
+
+
 def test_truncnorm_restatement_matches_scipy():
     """oracle.gmrf truncated-normal helpers == scipy.stats.truncnorm (what gmrf.py:269-318 calls)."""
     from scipy import stats
