@@ -187,6 +187,7 @@ typedef struct {
   omc_vec_t X[4];      /* [n x p_t] row-major */
   omc_vec_t theta[4];  /* [p_t]               */
   double* out;         /* [n_chains][n]       */
+  int transform_exp[4]; /* term t uses exp(theta_t) (ref: parameter.py:232-297 LinearCombinationWithTransform) */
 } omc_linear_predictor_t;
 int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
 
@@ -244,6 +245,13 @@ int omc_tridiag_matvec(const double* pd, const double* pe, omc_vec_t v, int n_ch
 #define OMC_TERM_GAMMA_RESPONSE 2   /* theta ~ Gamma(shape p1, rate p2)              ref: distribution.py:241-261          */
 #define OMC_TERM_NORMAL_RESPONSE 3  /* theta ~ N(p1, (scalar*P)^-1), optional domain ref: location_scale.py:145-188,222-232 */
 #define OMC_TERM_UNIFORM_RESPONSE 4 /* theta ~ U(p1, p2): constant log-density       ref: distribution.py:422-442          */
+#define OMC_TERM_LOGNORMAL_RESPONSE 5 /* theta ~ LogNormal(p1, (scalar*P)^-1) (fields as NORMAL) ref: location_scale.py:276-418 */
+#define OMC_TERM_NORMAL_LINEAR 6    /* data y ~ N(X f(theta), (scalar*W)^-1), f = identity or exp (transform_exp), W = eye or
+                                       diagonal: evaluated through the data-only record  G = X'WX | g = X'Wy | y'Wy | cnt  of
+                                       omc_reg_pass(beta = NULL):  S(f) = y'Wy - 2 g'f + f'G f,
+                                       log p = (n_data log scalar + logdet - n_data log 2pi - scalar S)/2,
+                                       grad = scalar f'(theta) o (g - G f),  H = scalar diag(f') G diag(f')
+                                       ref: location_scale.py:145-167, 234-250; parameter.py:162-228, 232-297              */
 typedef struct {
   int kind;
   int mat_kind;        /* NORMAL: 0 eye / 1 diag / 2 dense storage of P                         */
@@ -254,6 +262,9 @@ typedef struct {
   omc_vec_t scalar;    /* NORMAL: scalar multiplying P (NULL => 1)                               */
   omc_vec_t logdet;    /* NORMAL: log|P| (NULL => 0)                                             */
   double dom_lo, dom_hi; /* NORMAL: log_p = -inf outside [dom_lo, dom_hi] (+-inf = unbounded)    */
+  omc_vec_t stats;     /* NORMAL_LINEAR: regression record (chain_stride = n_elem^2 + n_elem + 2)  */
+  int n_data;          /* NORMAL_LINEAR: length of the response y                                  */
+  int transform_exp;   /* NORMAL_LINEAR: mean = X exp(theta) (LinearCombinationWithTransform)      */
 } omc_term_t;
 typedef struct {
   int n_chains, n_elem, n_terms;
@@ -262,6 +273,8 @@ typedef struct {
 
 /* out[c] = sum of the terms' log-densities at theta[c]  (theta: [n_chains][n_elem]) */
 int omc_mh_logp(const omc_mh_model_t* model, const double* theta, double* out, void* stream);
+/* same, out[c] += ... when accumulate != 0 (log_post of distributions that have no dedicated omc_logp_* kernel) */
+int omc_mh_logp_acc(const omc_mh_model_t* model, const double* theta, double* out, int accumulate, void* stream);
 /* grad [n_chains][n_elem] of the POSITIVE log-density, hess [n_chains][n_elem^2] of the NEGATIVE log-density (may be NULL).
  * method 0: analytic derivatives (what the samplers use)
  * method 1: the reference's central finite differences, step 1e-4, Hessian = FD of the FD gradient, applied per term as

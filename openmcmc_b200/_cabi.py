@@ -120,7 +120,7 @@ class LinearPredictor(C.Structure):
     """omc_linear_predictor_t"""
 
     _fields_ = [("n_chains", C.c_int), ("n", C.c_int), ("n_terms", C.c_int), ("p", C.c_int * 4), ("X", Vec * 4),
-                ("theta", Vec * 4), ("out", C.c_void_p)]
+                ("theta", Vec * 4), ("out", C.c_void_p), ("transform_exp", C.c_int * 4)]
 
 
 class Term(C.Structure):
@@ -128,7 +128,7 @@ class Term(C.Structure):
 
     _fields_ = [("kind", C.c_int), ("mat_kind", C.c_int), ("p1_len", C.c_int), ("p2_len", C.c_int), ("data", Vec),
                 ("p1", Vec), ("p2", Vec), ("P", Vec), ("scalar", Vec), ("logdet", Vec), ("dom_lo", C.c_double),
-                ("dom_hi", C.c_double)]
+                ("dom_hi", C.c_double), ("stats", Vec), ("n_data", C.c_int), ("transform_exp", C.c_int)]
 
 
 class MHModel(C.Structure):
@@ -205,6 +205,7 @@ PROTOTYPES = {
     "omc_tridiag_quadforms": (C.c_int, [C.POINTER(TridiagNN), C.c_void_p]),
     "omc_tridiag_matvec": (C.c_int, [C.c_void_p, C.c_void_p, Vec, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_mh_logp": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "omc_mh_logp_acc": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "omc_mh_grad_hess": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_random_walk": (C.c_int, [C.POINTER(RandomWalkArgs), C.c_void_p]),
     "omc_mmala": (C.c_int, [C.POINTER(MMalaArgs), C.c_void_p]),

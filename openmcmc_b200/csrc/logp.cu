@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(LP_THREADS) linear_predictor_kernel(omc_linear
       const int p = a.p[t];
       const double* x = a.X[t].ptr + (long long)c * a.X[t].chain_stride + (long long)r * p;
       const double* th = a.theta[t].ptr + (long long)c * a.theta[t].chain_stride;
-      for (int j = lane; j < p; j += 32) acc = fma(x[j], th[j], acc);
+      if (a.transform_exp[t]) {
+        for (int j = lane; j < p; j += 32) acc = fma(x[j], exp(th[j]), acc);
+      } else {
+        for (int j = lane; j < p; j += 32) acc = fma(x[j], th[j], acc);
+      }
     }
     acc = omc_warp_sum(acc);
     if (lane == 0) a.out[row] = acc;

@@ -81,6 +81,42 @@ __device__ double term_logp_warp(const omc_term_t& t, int n, int chain, const do
       for (int i = lane; i < n; i += 32)
         acc -= log(vat(t.p2, chain, t.p2_len > 1 ? i : 0, 1.0) - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0));
       break;
+    case OMC_TERM_LOGNORMAL_RESPONSE: {
+      // MVN log-pdf at log(theta) minus sum log(theta) (location_scale.py:296-303); theta <= 0 gives NaN / -inf as numpy
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      double sumlog = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double li = log(th[i]);
+        const double ri = li - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0);
+        double q;
+        if (t.mat_kind == OMC_MAT_DENSE) {
+          q = 0.0;
+          for (int j = 0; j < n; ++j)
+            q += mat_at(OMC_MAT_DENSE, t.P, chain, n, i, j) * (log(th[j]) - vat(t.p1, chain, t.p1_len > 1 ? j : 0, 0.0));
+        } else {
+          q = mat_at(t.mat_kind, t.P, chain, n, i, i) * ri;
+        }
+        acc += ri * q;
+        sumlog += li;
+      }
+      acc = omc_warp_sum(acc);
+      sumlog = omc_warp_sum(sumlog);
+      return 0.5 * (n * log(s) + vat(t.logdet, chain, 0, 0.0) - n * LOG_2PI - s * acc) - sumlog;
+    }
+    case OMC_TERM_NORMAL_LINEAR: {
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      const double* rec = t.stats.ptr + (long long)chain * t.stats.chain_stride;
+      const double* G = rec;
+      const double* gv = rec + n * n;
+      for (int j = lane; j < n; j += 32) {
+        double gf = 0.0;
+        for (int k = 0; k < n; ++k) gf = fma(G[j * n + k], t.transform_exp ? exp(th[k]) : th[k], gf);
+        const double fj = t.transform_exp ? exp(th[j]) : th[j];
+        acc = fma(fj, gf - 2.0 * gv[j], acc);
+      }
+      const double S = rec[n * n + n] + omc_warp_sum(acc);
+      return 0.5 * (t.n_data * log(s) + vat(t.logdet, chain, 0, 0.0) - t.n_data * LOG_2PI - s * S);
+    }
     default:
       break;
   }
@@ -133,6 +169,47 @@ __device__ void term_grad_hess_analytic(const omc_term_t& t, int n, int chain, c
       }
       break;
     }
+    case OMC_TERM_LOGNORMAL_RESPONSE: {
+      // grad = -(1 + Q r) / theta ; H = diag(1/theta) Q diag(1/theta) - diag((1 + Q r) / theta^2), r = log(theta) - mu
+      // ref: location_scale.py:340-343 (gradient), :383-399 (Hessian)
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      for (int i = tid; i < n; i += nthr) {
+        const double ti = th[i], rci = 1.0 / ti;
+        double q = 0.0;
+        if (t.mat_kind == OMC_MAT_DENSE) {
+          for (int j = 0; j < n; ++j) {
+            const double pij = mat_at(OMC_MAT_DENSE, t.P, chain, n, i, j);
+            q += pij * (log(th[j]) - vat(t.p1, chain, t.p1_len > 1 ? j : 0, 0.0));
+            if (H) H[i * ldh + j] += rci * (s * pij) * (1.0 / th[j]);
+          }
+        } else {
+          const double pii = mat_at(t.mat_kind, t.P, chain, n, i, i);
+          q = pii * (log(ti) - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0));
+          if (H) H[i * ldh + i] += rci * (s * pii) * rci;
+        }
+        const double one_qr = 1.0 + s * q;
+        g[i] += -rci * one_qr;
+        if (H) H[i * ldh + i] -= rci * rci * one_qr;
+      }
+      break;
+    }
+    case OMC_TERM_NORMAL_LINEAR: {
+      const double s = vat(t.scalar, chain, 0, 1.0);
+      const double* rec = t.stats.ptr + (long long)chain * t.stats.chain_stride;
+      const double* G = rec;
+      const double* gv = rec + n * n;
+      for (int j = tid; j < n; j += nthr) {
+        const double dj = t.transform_exp ? exp(th[j]) : 1.0;   // d f_j / d theta_j
+        double gf = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double ek = t.transform_exp ? exp(th[k]) : 1.0;
+          gf = fma(G[j * n + k], t.transform_exp ? ek : th[k], gf);
+          if (H) H[j * ldh + k] += s * dj * G[j * n + k] * ek;
+        }
+        g[j] += s * dj * (gv[j] - gf);
+      }
+      break;
+    }
     default:
       break;
   }
@@ -171,7 +248,8 @@ __device__ void model_grad_hess_warp(const omc_mh_model_t& m, int chain, const d
   __syncwarp();
   for (int k = 0; k < m.n_terms; ++k) {
     const omc_term_t& t = m.terms[k];
-    if (method == 0 || t.kind == OMC_TERM_NORMAL_RESPONSE) {
+    if (method == 0 || t.kind == OMC_TERM_NORMAL_RESPONSE || t.kind == OMC_TERM_LOGNORMAL_RESPONSE ||
+        t.kind == OMC_TERM_NORMAL_LINEAR) {   // the reference differentiates these analytically too
       term_grad_hess_analytic(t, n, chain, th, g, H, ldh, lane, 32);
       __syncwarp();
       continue;
@@ -207,7 +285,8 @@ __device__ void model_grad_hess_warp(const omc_mh_model_t& m, int chain, const d
 }
 
 // ---------------------------------------------------------------------------------------------- probes
-__global__ void __launch_bounds__(MH_WARPS * 32) mh_logp_kernel(omc_mh_model_t m, const double* theta, double* out) {
+__global__ void __launch_bounds__(MH_WARPS * 32) mh_logp_kernel(omc_mh_model_t m, const double* theta, double* out,
+                                                               int accumulate) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chain = blockIdx.x * MH_WARPS + warp;
@@ -216,7 +295,7 @@ __global__ void __launch_bounds__(MH_WARPS * 32) mh_logp_kernel(omc_mh_model_t m
   for (int i = lane; i < m.n_elem; i += 32) th[i] = theta[(long long)chain * m.n_elem + i];
   __syncwarp();
   const double lp = model_logp_warp(m, chain, th);
-  if (lane == 0) out[chain] = lp;
+  if (lane == 0) out[chain] = accumulate ? out[chain] + lp : lp;
 }
 
 __global__ void __launch_bounds__(MH_WARPS * 32) mh_grad_hess_kernel(omc_mh_model_t m, const double* theta, int method,
@@ -474,10 +553,12 @@ int check_model(const omc_mh_model_t* m, const char* who) {
   OMC_REQUIRE(m->n_chains >= 1 && m->n_elem >= 1 && m->n_terms >= 0 && m->n_terms <= 4, "%s: bad model shape", who);
   for (int k = 0; k < m->n_terms; ++k) {
     const omc_term_t& t = m->terms[k];
-    OMC_REQUIRE(t.kind >= 1 && t.kind <= 4, "%s: unknown term kind %d", who, t.kind);
+    OMC_REQUIRE(t.kind >= 1 && t.kind <= 6, "%s: unknown term kind %d", who, t.kind);
     if (t.kind == OMC_TERM_POISSON_RATE) OMC_REQUIRE(t.data.ptr, "%s: Poisson term without counts", who);
-    if (t.kind == OMC_TERM_NORMAL_RESPONSE)
+    if (t.kind == OMC_TERM_NORMAL_RESPONSE || t.kind == OMC_TERM_LOGNORMAL_RESPONSE)
       OMC_REQUIRE(t.mat_kind == OMC_MAT_EYE || t.P.ptr, "%s: Normal term without precision", who);
+    if (t.kind == OMC_TERM_NORMAL_LINEAR)
+      OMC_REQUIRE(t.stats.ptr && t.n_data >= 1 && m->n_elem <= 64, "%s: Normal-linear term needs a regression record", who);
   }
   return 0;
 }
@@ -486,14 +567,17 @@ int check_model(const omc_mh_model_t* m, const char* who) {
 
 extern "C" {
 
-int omc_mh_logp(const omc_mh_model_t* model, const double* theta, double* out, void* stream) {
+int omc_mh_logp_acc(const omc_mh_model_t* model, const double* theta, double* out, int accumulate, void* stream) {
   OMC_REQUIRE(model && theta && out, "omc_mh_logp: null argument");
   if (int rc = check_model(model, "omc_mh_logp")) return rc;
   const int blocks = (model->n_chains + MH_WARPS - 1) / MH_WARPS;
   const size_t smem = (size_t)MH_WARPS * model->n_elem * sizeof(double);
-  mh_logp_kernel<<<blocks, MH_WARPS * 32, smem, (cudaStream_t)stream>>>(*model, theta, out);
+  mh_logp_kernel<<<blocks, MH_WARPS * 32, smem, (cudaStream_t)stream>>>(*model, theta, out, accumulate);
   OMC_LAUNCH_CHECK();
   return 0;
+}
+int omc_mh_logp(const omc_mh_model_t* model, const double* theta, double* out, void* stream) {
+  return omc_mh_logp_acc(model, theta, out, 0, stream);
 }
 
 int omc_mh_grad_hess(const omc_mh_model_t* model, const double* theta, int method, double* grad, double* hess,

@@ -34,7 +34,8 @@ def build_terms(plan: "engine.Plan", host_state: dict, model, param: str):
     Returns (omc_mh_model_t, labels).  Raises PlanError for combinations the device path does not implement.
     """
     from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
-    from openmcmc_b200.distribution.location_scale import Normal, NullDistribution
+    from openmcmc_b200.distribution.location_scale import LogNormal, Normal, NullDistribution
+    from openmcmc_b200.parameter import LinearCombination
 
     st = plan.state
     theta = st[param]
@@ -55,6 +56,33 @@ def build_terms(plan: "engine.Plan", host_state: dict, model, param: str):
             (v1, l1), (v2, l2) = _expand(plan, st[dist.shape.form], p_dim, n_rep), _expand(plan, st[dist.rate.form],
                                                                                          p_dim, n_rep)
             terms.append(K.term(K.TERM_GAMMA_RESPONSE, p1=v1, p1_len=l1, p2=v2, p2_len=l2))
+        elif isinstance(dist, LogNormal) and dist.response == param:
+            # location_scale.py:296-303 (log_p), :340-343 / :383-399 (response-branch gradient and Hessian)
+            if not isinstance(dist.mean, Identity):
+                raise engine.PlanError("MH on a LogNormal response needs an Identity mean parameter")
+            mname, sname = engine._scalar_and_matrix(dist.precision)
+            P = engine.ensure_matrix(st, host_state, mname)
+            if P.kind == "tridiag" or (n_rep != 1 and P.kind != "eye"):
+                raise engine.PlanError("MH on a LogNormal response supports eye / diagonal / dense precisions, n_rep = 1")
+            v1, l1 = _expand(plan, st[dist.mean.form], p_dim, n_rep)
+            logdet = engine.logdet_of(plan, P)
+            terms.append(K.term(K.TERM_LOGNORMAL_RESPONSE, mat_kind=engine._mat_kind(P), p1=v1, p1_len=l1, P=P.vec(),
+                                scalar=st[sname].vec() if sname else None,
+                                logdet=K.vec(logdet, 1 if P.per_chain else None) if logdet is not None else None))
+        elif (isinstance(dist, Normal) and isinstance(dist.mean, LinearCombination) and param in dist.mean.form
+              and dist.response != param):
+            # theta enters the mean of a Normal response linearly (optionally through exp): location_scale.py:234-250 with
+            # parameter.py:199-228 / 283-297.  Evaluated from the data-only regression record (omc.h: NORMAL_LINEAR).
+            if n_rep != 1:
+                raise engine.PlanError("MH through a linear Normal mean needs a column-vector parameter")
+            rl = engine.get_regression(plan, host_state, dist, param, data_only=True)
+            plan.require(rl.q_gg)
+            logdet = engine.logdet_of(plan, rl.W)
+            transform = bool((getattr(dist.mean, "transform", None) or {}).get(param, False))
+            terms.append(K.term(K.TERM_NORMAL_LINEAR, stats=K.vec(rl.stats, rl.rec), n_data=rl.n,
+                                scalar=st[rl.scalar].vec() if rl.scalar else None,
+                                logdet=K.vec(logdet, 1 if rl.W.per_chain else None) if logdet is not None else None,
+                                transform_exp=transform))
         elif isinstance(dist, Normal) and dist.response == param:
             if not isinstance(dist.mean, Identity):
                 raise engine.PlanError("MH on a Normal response needs an Identity mean parameter")
@@ -136,7 +164,8 @@ def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, metho
         raise ValueError("method must be 'fd' (the reference's finite differences) or 'analytic'")
     plan, st = _one_chain_plan(state, per_chain=(param,))
     shape = np.shape(state[param])
-    if isinstance(dist, Normal) and isinstance(dist.mean, LinearCombination) and param in dist.mean.form:
+    if (isinstance(dist, Normal) and isinstance(dist.mean, LinearCombination) and param in dist.mean.form
+            and not (getattr(dist.mean, "transform", None) or {}).get(param, False)):
         # linear-mean branch (location_scale.py:234-242): H = scalar * X'WX, g = scalar * X'W(y - X beta) from the fused
         # regression pass
         rl = engine.get_regression(plan, state, dist, param)
@@ -152,7 +181,10 @@ def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, metho
         beta = np.asarray(state[param], dtype=np.float64).reshape(p, 1)
         grad = tau * (rec[p * p: p * p + p].reshape(p, 1) - G @ beta)
         return (grad.reshape(shape), tau * G) if hessian_required else grad.reshape(shape)
+    plan.ops = []
     model, _ = build_terms(plan, state, Model([dist]), param)
+    for _, fn in plan.ops:      # derived quantities the terms read (e.g. the data-only regression record)
+        fn()
     theta = st[param].data
     n = model.n_elem
     grad = plan.new(1, n)

@@ -1,6 +1,6 @@
 """Location-scale distributions: Normal, NullDistribution (host-side mirror).  ref: distribution/location_scale.py
 
-LogNormal is SURVEY §8 f4 ("next") and not provided in round 1.
+LogNormal: response-branch log_p / gradient / Hessian run as an MH term on the device.
 """
 
 from abc import ABC
@@ -23,7 +23,7 @@ from openmcmc_b200.parameter import (
 class LocationScale(Distribution, ABC):
     """ref: location_scale.py:31-62"""
 
-    mean: Union[str, Identity, LinearCombination, MixtureParameterVector]
+    mean: Union[str, Identity, LinearCombination, MixtureParameterVector]  # incl. LinearCombinationWithTransform
     precision: Union[str, Identity, ScaledMatrix, MixtureParameterMatrix]
 
     @property
@@ -78,6 +78,30 @@ class Normal(LocationScale):
 
     def rvs(self, state: dict, n: int = 1):
         """ref: location_scale.py:252-272"""
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.rvs(self, state, n)
+
+
+@dataclass
+class LogNormal(LocationScale):
+    """Multivariate log-normal in precision form.  ref: location_scale.py:275-418
+
+    log_p = MVN log-pdf at log(x) minus sum(log x) (:296-303); as the response of an MH-sampled parameter the gradient is
+    -(1 + Q r)/x and the Hessian diag(1/x) Q diag(1/x) - diag((1 + Q r)/x^2), r = log x - mean (:340-343, :383-399).
+    """
+
+    def log_p(self, state: dict, by_observation: bool = False):
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.log_p(self, state, by_observation)
+
+    def grad_log_p(self, state: dict, param: str, hessian_required: bool = True, method: str = "analytic"):
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.grad_log_p(self, state, param, hessian_required, method)
+
+    def rvs(self, state: dict, n: int = 1):
         from openmcmc_b200 import hostcalls
 
         return hostcalls.rvs(self, state, n)

@@ -321,11 +321,14 @@ def ensure_matrix(state: DeviceState, host_state: dict, name: str) -> DevArray:
 class RegressionLikelihood:
     """y ~ N(X beta (+ nothing else), (tau * W)^-1) with W = I or diag: owner of the fused pass (omc_reg_pass)."""
 
-    def __init__(self, plan: Plan, host_state, dist, param):
+    def __init__(self, plan: Plan, host_state, dist, param, data_only=False):
+        """data_only: the pass runs with beta = NULL, so the record holds rss = y'Wy and depends on the data alone (the
+        form the Normal-linear MH term consumes: S(f) = y'Wy - 2 g'f + f'G f for any candidate f)."""
         st = plan.state
         self.plan = plan
         self.dist = dist
         self.param = param
+        self.data_only = data_only
         form = dist.mean.form
         if list(form.keys()) != [param]:
             raise PlanError("LinearCombination means with more than one term are not supported by the device path yet")
@@ -348,18 +351,21 @@ class RegressionLikelihood:
         ns, ws = K.reg_pass_workspace(C, self.n, self.p)
         self.work = plan.new(max(ws, 1))
         deps_data = frozenset({form[param], dist.response, mname})
-        self.q_gg = f"gram[{dist.response}]"
-        self.q_rss = f"rss[{dist.response}]"
+        tag = "data:" if data_only else ""
+        self.q_gg = f"gram[{tag}{dist.response}]"
+        self.q_rss = f"rss[{tag}{dist.response}]"
         plan.add_quantity(Quantity(self.q_gg, deps_data, self._emit_pass, (self.q_rss,)))
-        plan.add_quantity(Quantity(self.q_rss, deps_data | {param}, self._emit_pass, (self.q_gg,)))
+        plan.add_quantity(Quantity(self.q_rss, deps_data if data_only else deps_data | {param}, self._emit_pass,
+                                   (self.q_gg,)))
 
     def _emit_pass(self):
         C, n, p = self.plan.state.n_chains, self.n, self.p
         X, y, W, beta, stats, work = self.X, self.y, self.W, self.beta, self.stats, self.work
         w = W.data if W.kind == "diag" else None
+        beta_data = None if self.data_only else beta.data
 
         def launch():
-            K.reg_pass(X.data, y.data, w, beta.data, stats, work, C, n, p, x_shared=not X.per_chain,
+            K.reg_pass(X.data, y.data, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain,
                        y_shared=not y.per_chain, w_shared=True)
 
         self.plan.emit(launch, "reg_pass")
@@ -382,16 +388,17 @@ def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
     if isinstance(par, LinearCombination):
         now = plan.new(C, n)
         terms = []
+        transform = getattr(par, "transform", None) or {}
         for prm, pref in par.form.items():
             X, th = st[pref], st[prm]
             if X.kind != "dense" or th.cols != 1:
                 raise PlanError("fitted values: unsupported LinearCombination term")
-            terms.append((X, th))
+            terms.append((X, th, bool(transform.get(prm, False))))
         if len(terms) > 4:
             raise PlanError("fitted values: more than 4 LinearCombination terms")
 
         def launch():
-            K.linear_predictor(C, n, [(X.vec(), th.vec(), X.cols) for X, th in terms], now)
+            K.linear_predictor(C, n, [(X.vec(), th.vec(), X.cols, tr) for X, th, tr in terms], now)
             K.store_copy(now, buf, C * n, plan.iter_counter, n_iter)
 
         plan.emit(launch, f"fitted[{dist.response}]")
@@ -419,11 +426,11 @@ def as_chain_tensor(value, n_chains, size, device):
     return torch.as_tensor(np.ascontiguousarray(a)).to(device)
 
 
-def get_regression(plan: Plan, host_state, lik, param) -> RegressionLikelihood:
+def get_regression(plan: Plan, host_state, lik, param, data_only=False) -> RegressionLikelihood:
     cache = plan.__dict__.setdefault("_regressions", {})
-    key = lik.response
+    key = (lik.response, data_only) if data_only else lik.response
     if key not in cache:
-        cache[key] = RegressionLikelihood(plan, host_state, lik, param)
+        cache[key] = RegressionLikelihood(plan, host_state, lik, param, data_only=data_only)
     return cache[key]
 
 
@@ -501,7 +508,7 @@ def logdet_of(plan: Plan, P: DevArray):
 def compile_log_post(plan: Plan, host_state, model, out):
     """Emit kernels accumulating model.log_p(state) per chain into `out` [C].  ref: mcmc.py:108, model.py:57-70."""
     from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
-    from openmcmc_b200.distribution.location_scale import Normal, NullDistribution
+    from openmcmc_b200.distribution.location_scale import LogNormal, Normal, NullDistribution
 
     st = plan.state
     C = st.n_chains
@@ -510,7 +517,24 @@ def compile_log_post(plan: Plan, host_state, model, out):
         acc = 0 if first else 1
         if isinstance(dist, NullDistribution):
             continue
-        if isinstance(dist, Normal):
+        transformed = isinstance(dist, Normal) and any((getattr(dist.mean, "transform", None) or {}).values())
+        if isinstance(dist, LogNormal) or transformed:
+            # no dedicated kernel: the distribution as a one-term MH model of its response (LogNormal) or of the
+            # transformed coefficient vector (Normal with a LinearCombinationWithTransform mean)
+            from openmcmc_b200 import devdist
+            from openmcmc_b200.model import Model
+
+            if transformed and len(dist.mean.form) != 1:
+                raise PlanError("log_post: LinearCombinationWithTransform means with more than one term are not supported")
+            prm = dist.response if isinstance(dist, LogNormal) else next(iter(dist.mean.form))
+            tm, _ = devdist.build_terms(plan, host_state, Model([dist]), prm)
+            x = st[prm]
+
+            def launch(tm=tm, x=x, acc=acc):
+                K.mh_logp(tm, x.data, out, accumulate=acc)
+
+            plan.emit(launch, f"logp_terms[{dist.response}]")
+        elif isinstance(dist, Normal):
             mname, sname = _scalar_and_matrix(dist.precision)
             ss_vec, _, qname = get_quadratic_form(plan, host_state, dist)
             P = ensure_matrix(st, host_state, mname)

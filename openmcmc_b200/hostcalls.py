@@ -62,14 +62,14 @@ def linear_predictor(state: dict, terms):
     n = None
     vt = []
     n_rep = 1
-    for xname, tname in terms:
+    for xname, tname, *flag in terms:
         X, th = st[xname], st[tname]
         if X.kind != "dense":
             raise engine.PlanError("LinearCombination.predictor with structured prefactors is not supported yet")
         if th.cols != 1:
             raise engine.PlanError("LinearCombination.predictor with replicated parameters is not supported yet")
         n = X.rows
-        vt.append((X.vec(), th.vec(), X.cols))
+        vt.append((X.vec(), th.vec(), X.cols, bool(flag[0]) if flag else False))
     out = torch.empty(1, n, dtype=torch.float64, device=st.device)
     for i in range(0, len(vt), 4):
         part = out if i == 0 else torch.empty_like(out)

@@ -150,13 +150,14 @@ def logp_const(value, n_chains, out, accumulate):
 
 
 def linear_predictor(n_chains, n, terms, out):
-    """terms: list of (X_vec, theta_vec, p)."""
+    """terms: list of (X_vec, theta_vec, p[, transform_exp])."""
     a = _cabi.LinearPredictor()
     a.n_chains, a.n, a.n_terms = n_chains, n, len(terms)
-    for i, (xv, tv, p) in enumerate(terms):
+    for i, (xv, tv, p, *rest) in enumerate(terms):
         a.p[i] = p
         a.X[i] = xv
         a.theta[i] = tv
+        a.transform_exp[i] = int(bool(rest[0])) if rest else 0
     a.out = out.data_ptr()
     check(lib().omc_linear_predictor(C.byref(a), stream_ptr()), "omc_linear_predictor")
 
@@ -221,14 +222,16 @@ def store_copy(src, dst, count, iter_counter, max_iter):
 
 # ----------------------------------------------------------------------------- Metropolis-Hastings family
 TERM_POISSON_RATE, TERM_GAMMA_RESPONSE, TERM_NORMAL_RESPONSE, TERM_UNIFORM_RESPONSE = 1, 2, 3, 4
+TERM_LOGNORMAL_RESPONSE, TERM_NORMAL_LINEAR = 5, 6
 
 
 def term(kind, mat_kind=0, p1_len=1, p2_len=1, data=None, p1=None, p2=None, P=None, scalar=None, logdet=None,
-         dom_lo=float("-inf"), dom_hi=float("inf")) -> "_cabi.Term":
+         dom_lo=float("-inf"), dom_hi=float("inf"), stats=None, n_data=0, transform_exp=False) -> "_cabi.Term":
     """Build an omc_term_t; operands are omc_vec_t (see `vec`) or None."""
     none = Vec(None, 0)
     return _cabi.Term(int(kind), int(mat_kind), int(p1_len), int(p2_len), data or none, p1 or none, p2 or none,
-                      P or none, scalar or none, logdet or none, float(dom_lo), float(dom_hi))
+                      P or none, scalar or none, logdet or none, float(dom_lo), float(dom_hi), stats or none,
+                      int(n_data), int(bool(transform_exp)))
 
 
 def mh_model(n_chains, n_elem, terms) -> "_cabi.MHModel":
@@ -241,8 +244,9 @@ def mh_model(n_chains, n_elem, terms) -> "_cabi.MHModel":
     return m
 
 
-def mh_logp(model, theta, out):
-    check(lib().omc_mh_logp(C.byref(model), _ptr(theta), _ptr(out), stream_ptr()), "omc_mh_logp")
+def mh_logp(model, theta, out, accumulate=False):
+    check(lib().omc_mh_logp_acc(C.byref(model), _ptr(theta), _ptr(out), int(bool(accumulate)), stream_ptr()),
+          "omc_mh_logp")
 
 
 def mh_grad_hess(model, theta, method, grad, hess=None):

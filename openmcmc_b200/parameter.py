@@ -72,12 +72,21 @@ class LinearCombination(Parameter):
 
 @dataclass
 class LinearCombinationWithTransform(LinearCombination):
-    """f = sum_i X_i @ exp(theta_i).  ref: parameter.py:231-297.  Declared for API completeness (next)."""
+    """f = sum_i X_i @ (exp(theta_i) if transform[theta_i] else theta_i).  ref: parameter.py:231-297."""
 
     transform: dict = None
 
     def predictor_conditional(self, state: dict, term_to_exclude: Union[str, list] = None):
-        raise NotImplementedError("LinearCombinationWithTransform is outside the round-1 hot path (SURVEY.md §8 f4)")
+        """ref: parameter.py:255-281; the products (and the exp) run in omc_linear_predictor."""
+        from openmcmc_b200 import hostcalls
+
+        if term_to_exclude is None:
+            term_to_exclude = []
+        if isinstance(term_to_exclude, str):
+            term_to_exclude = [term_to_exclude]
+        terms = [(prefactor, prm, bool(self.transform[prm])) for prm, prefactor in self.form.items()
+                 if prm not in term_to_exclude]
+        return hostcalls.linear_predictor(state, terms)
 
 
 @dataclass

@@ -92,6 +92,44 @@ def normal_grad_linear_mean(y, X, beta, Q):
     return gtp @ r, y.shape[1] * gtp @ X
 
 
+def lognormal_log_p(x, mu, Q):
+    """LogNormal.log_p: MVN log-pdf at log(x) minus sum(log x).  ref: location_scale.py:296-303"""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    with np.errstate(all="ignore"):
+        lx = np.log(x)
+        return normal_log_p(lx, mu, Q) - float(np.sum(lx))
+
+
+def lognormal_grad_response(x, mu, Q):
+    """Response branch: grad = -(1/x)(1 + Q r), r = log x - mu (location_scale.py:340-343); Hessian of -log p =
+    diag(1/x) Q diag(1/x) - diag((1 + Q r)/x^2) (location_scale.py:383-399, n = 1 replicate)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    mu = np.asarray(mu, dtype=np.float64).reshape(-1, 1)
+    Q = np.asarray(Q, dtype=np.float64)
+    r = np.log(x) - mu
+    rec = 1.0 / x
+    one_qr = 1.0 + Q @ r
+    g = -rec * one_qr
+    H = (rec * Q * rec.T) - np.diagflat(rec ** 2 * one_qr)
+    return g, H
+
+
+def normal_linear_log_p(y, X, theta, Q, transform=False):
+    """Normal.log_p with mean X f(theta), f = exp when transform.  ref: location_scale.py:145-167, parameter.py:255-281"""
+    f = np.exp(theta) if transform else np.asarray(theta, dtype=np.float64)
+    return normal_log_p(np.asarray(y, float).reshape(-1, 1), X @ f.reshape(-1, 1), Q)
+
+
+def normal_linear_grad(y, X, theta, Q, transform=False):
+    """Mean-parameter branch: grad = J Q r, H = n_rep J Q J' with J = mean.grad(state, param) = X' (times exp(theta)
+    row-wise when transformed).  ref: location_scale.py:234-250, parameter.py:199-228, 283-297"""
+    theta = np.asarray(theta, dtype=np.float64).reshape(-1, 1)
+    f = np.exp(theta) if transform else theta
+    J = (np.exp(theta) * X.T) if transform else X.T
+    r = np.asarray(y, float).reshape(-1, 1) - X @ f
+    return J @ Q @ r, J @ Q @ J.T
+
+
 def gamma_grad_response(x, shape, rate):
     """d/dx log Gamma(x; a, b) = (a-1)/x - b ; -d2/dx2 = (a-1)/x^2 (diagonal).  (analytic counterpart of the FD default)"""
     x, shape, rate = np.broadcast_arrays(np.asarray(x, float), np.asarray(shape, float), np.asarray(rate, float))

@@ -17,7 +17,8 @@ from oracle import dist, gmrf
 class Term:
     """One member distribution of the conditional model, as a function of the sampled parameter theta (p, n)."""
 
-    kind: str             # 'poisson_rate' | 'gamma_response' | 'normal_response' | 'uniform_response'
+    kind: str             # 'poisson_rate' | 'gamma_response' | 'normal_response' | 'uniform_response' |
+                          # 'lognormal_response' (p1 = mean, Q) | 'normal_linear' (data = y, X, Q, transform)
     data: np.ndarray = None     # poisson counts
     p1: np.ndarray = None       # gamma shape | normal mean | uniform lower
     p2: np.ndarray = None       # gamma rate | uniform upper
@@ -25,6 +26,8 @@ class Term:
     dom_lo: float = -np.inf
     dom_hi: float = np.inf
     analytic_in_reference: bool = False   # Normal has analytic derivatives (location_scale.py:190-250)
+    X: np.ndarray = None        # normal_linear: design matrix
+    transform: bool = False     # normal_linear: mean = X exp(theta) (parameter.py:232-297)
 
     def log_p(self, theta):
         theta = np.asarray(theta, float)
@@ -38,6 +41,10 @@ class Term:
             return dist.normal_log_p(theta.reshape(-1, 1), np.broadcast_to(self.p1, theta.shape).reshape(-1, 1), self.Q)
         if self.kind == "uniform_response":
             return dist.uniform_log_p(self.p1, self.p2, theta.shape[0], theta.shape[1])
+        if self.kind == "lognormal_response":                                         # location_scale.py:296-303
+            return dist.lognormal_log_p(theta.reshape(-1, 1), np.broadcast_to(self.p1, theta.shape).reshape(-1, 1), self.Q)
+        if self.kind == "normal_linear":
+            return dist.normal_linear_log_p(self.data, self.X, theta, self.Q, self.transform)
         raise ValueError(self.kind)
 
     def grad_hess_analytic(self, theta):
@@ -49,6 +56,10 @@ class Term:
             g, H = dist.gamma_grad_response(theta, np.broadcast_to(self.p1, theta.shape), np.broadcast_to(self.p2, theta.shape))
         elif self.kind == "normal_response":
             g, H = dist.normal_grad_response(theta.reshape(-1, 1), np.broadcast_to(self.p1, theta.shape).reshape(-1, 1), self.Q)
+        elif self.kind == "lognormal_response":
+            g, H = dist.lognormal_grad_response(theta.reshape(-1, 1), np.broadcast_to(self.p1, theta.shape).reshape(-1, 1), self.Q)
+        elif self.kind == "normal_linear":
+            g, H = dist.normal_linear_grad(self.data, self.X, theta, self.Q, self.transform)
         else:
             g, H = np.zeros(n), np.zeros((n, n))
         return np.asarray(g, float).reshape(theta.shape), np.asarray(H, float).reshape(n, n)
@@ -56,7 +67,7 @@ class Term:
     def grad_hess_reference(self, theta):
         """What the reference computes: finite differences unless the distribution overrides grad_log_p
         (distribution.py:90-198; Normal: location_scale.py:190-250)."""
-        if self.kind == "normal_response":
+        if self.kind in ("normal_response", "lognormal_response", "normal_linear"):
             return self.grad_hess_analytic(theta)
         g = dist.grad_fd(self.log_p, theta)
         H = dist.hessian_fd(lambda x: dist.grad_fd(self.log_p, x), theta)

@@ -20,7 +20,8 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 from openmcmc import gmrf  # noqa: E402
 from openmcmc.distribution.distribution import Gamma, Poisson, Uniform  # noqa: E402
-from openmcmc.distribution.location_scale import Normal  # noqa: E402
+from openmcmc.distribution.location_scale import LogNormal, Normal  # noqa: E402
+from openmcmc.parameter import LinearCombinationWithTransform  # noqa: E402
 from openmcmc.mcmc import MCMC  # noqa: E402
 from openmcmc.model import Model  # noqa: E402
 from openmcmc.parameter import Identity, LinearCombination, ScaledMatrix  # noqa: E402
@@ -202,6 +203,75 @@ def mmala_normal_case(p, seed, n_iter, step):
             "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
 
 
+def lognormal_case(p, seed, n_iter, step, sampler="mmala", prior="dense"):
+    """theta ~ LogNormal(mu, (lam P)^-1) observed through yobs ~ N(theta, (tau W)^-1); every derivative is
+    analytic in the reference (location_scale.py:340-343, 383-399), so chains replay to 1e-9."""
+    rng = np.random.default_rng(seed)
+    if prior == "dense":
+        A = rng.standard_normal((p, p))
+        P = A @ A.T / p + np.eye(p)
+    else:
+        P = sparse.diags(rng.random(p) + 0.5, format="csc")
+    theta0 = np.exp(0.3 * rng.standard_normal((p, 1)))
+    state = {"theta": theta0.copy(), "mu": 0.2 * rng.standard_normal((p, 1)), "P": P, "lam": 1.3,
+             "yobs": theta0 + 0.3 * rng.standard_normal((p, 1)), "W": sparse.diags(rng.random(p) + 0.5, format="csc"),
+             "tau": 4.0}
+    mdl = Model([LogNormal("theta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam")),
+                 Normal("yobs", mean="theta", precision=ScaledMatrix(matrix="W", scalar="tau"))])
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    sc = {**state0, "lam": np.array([[1.3]]), "tau": np.array([[4.0]])}
+    prior_only = Model([mdl["theta"]])
+    g0, H0 = prior_only.grad_log_p(sc, "theta", hessian_required=True)
+    lp0 = prior_only.log_p(sc)
+    with Streams(seed + 10) as s:
+        if sampler == "mmala":
+            smp = ManifoldMALA("theta", mdl, step=np.array([[step]]))
+        else:
+            smp = RandomWalk("theta", mdl, step=np.array([[step]]))
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"theta0": state0["theta"], "mu": state0["mu"], "P": (P.toarray() if sparse.issparse(P) else P),
+            "prior": prior, "lam": 1.3, "yobs": state0["yobs"], "w": np.asarray(state0["W"].diagonal()), "tau": 4.0,
+            "step": step, "sampler": sampler, "grad0": g0, "hess0": np.asarray(H0), "logp0": lp0,
+            "z": s.stack("z"), "u": s.stack("u").ravel(), "store_theta": M.store["theta"],
+            "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
+def mmala_regression_case(n, p, seed, n_iter, step, transform=False, weighted=True):
+    """SURVEY a4 / f4 in an MH sampler: beta enters the mean of y ~ N(X f(beta), (tau W)^-1) linearly (f = exp with
+    LinearCombinationWithTransform), Normal prior on beta: the mean-parameter branch of Normal.grad_log_p
+    (location_scale.py:234-250) with parameter.py:199-228 / 283-297; analytic in the reference."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, p))
+    if transform:
+        X = np.abs(X)
+    beta_true = 0.5 * rng.standard_normal((p, 1))
+    f_true = np.exp(beta_true) if transform else beta_true
+    y = X @ f_true + 0.5 * rng.standard_normal((n, 1))
+    W = sparse.diags(rng.random(n) + 0.5, format="csc") if weighted else sparse.identity(n, format="csc")
+    A = rng.standard_normal((p, p))
+    P = A @ A.T / p + np.eye(p)
+    mean = (LinearCombinationWithTransform(form={"beta": "X"}, transform={"beta": True}) if transform
+            else LinearCombination(form={"beta": "X"}))
+    mdl = Model([Normal("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
+                 Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam"))])
+    state = {"y": y, "X": X, "beta": beta_true + 0.1 * rng.standard_normal((p, 1)), "W": W, "tau": 1.7,
+             "mu": np.zeros((p, 1)), "P": P, "lam": 0.8}
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    sc = {**state0, "lam": np.array([[0.8]]), "tau": np.array([[1.7]])}
+    lik_only = Model([mdl["y"]])
+    g0, H0 = lik_only.grad_log_p(sc, "beta", hessian_required=True)
+    lp0 = lik_only.log_p(sc)
+    with Streams(seed + 10) as s:
+        smp = ManifoldMALA("beta", mdl, step=np.array([[step]]))
+        M = _run_ref(state, [smp], mdl, n_iter)
+    return {"X": X, "y": y, "beta0": state0["beta"], "w": np.asarray(W.diagonal()), "weighted": weighted, "tau": 1.7,
+            "P": P, "lam": 0.8, "transform": transform, "step": step, "grad0": g0, "hess0": np.asarray(H0), "logp0": lp0,
+            "z": s.stack("z"), "u": s.stack("u").ravel(), "store_beta": M.store["beta"],
+            "store_log_post": M.store["log_post"],
+            "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
+
+
 def rwl_case(p, seed, n_iter, step):
     """RandomWalkLoop over a (1, p) parameter with truncated proposals on [0, inf) (the only working form)."""
     state, mdl = poisson_gamma_state(p, seed, layout="row")
@@ -268,6 +338,17 @@ def mh_cases():
         "rw_poisson_gamma_p6": rw_case(6, 16, 10, truncated=False),
         "rw_trunc_scalar": rw_case(1, 17, 12, truncated=True),
         "truncnorm_grid": truncnorm_grid(),
+    }
+
+
+def mh_f4_cases():
+    return {
+        "lognormal_mmala_p5_dense": lognormal_case(5, 21, 10, 0.7),
+        "lognormal_mmala_p24_diag": lognormal_case(24, 22, 6, 0.3, prior="diag"),
+        "lognormal_rw_p6_dense": lognormal_case(6, 23, 12, 0.08, sampler="rw"),
+        "mhreg_mmala_n60_p6": mmala_regression_case(60, 6, 24, 10, 0.8),
+        "mhreg_mmala_n200_p30_eye": mmala_regression_case(200, 30, 25, 4, 0.9, weighted=False),
+        "mhreg_exp_mmala_n80_p5": mmala_regression_case(80, 5, 26, 10, 0.7, transform=True),
     }
 
 
@@ -463,11 +544,13 @@ def main():
                                                         trunc=(None, np.array([[0.25]]))),
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
     }
-    which = sys.argv[1:] or ["regression", "mh", "gmrf", "rj"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "gmrf", "rj"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
         cases.update(mh_cases())
+    if "mh_f4" in which:
+        cases.update(mh_f4_cases())
     if "gmrf" in which:
         cases.update(gmrf_cases())
     if "rj" in which:

@@ -253,3 +253,103 @@ def test_mmala_invalid_proposal_rejects_and_flags():
     np.testing.assert_array_equal(M.store["lam"][:, 0], g["lam0"].ravel())
     assert M.status[0] == 4
     assert smp.accept_rate.count == {"accept": 0, "proposal": 1}
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY f4 / a4 in MH
+def _lognormal_model_state(g):
+    from openmcmc_b200.distribution.location_scale import LogNormal, Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import ScaledMatrix
+
+    mdl = Model([LogNormal("theta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam")),
+                 Normal("yobs", mean="theta", precision=ScaledMatrix(matrix="W", scalar="tau"))])
+    P = g["P"] if str(g["prior"]) == "dense" else sparse.csc_matrix(g["P"])
+    state = {"theta": g["theta0"].copy(), "mu": g["mu"], "P": P, "lam": float(g["lam"]), "yobs": g["yobs"],
+             "W": sparse.diags(g["w"], format="csc"), "tau": float(g["tau"])}
+    return mdl, state
+
+
+@pytest.mark.parametrize("name", ["lognormal_mmala_p5_dense", "lognormal_mmala_p24_diag", "lognormal_rw_p6_dense"])
+def test_lognormal_logp_grad_hess_and_chain(name):
+    """LogNormal (location_scale.py:275-418): log_p, response-branch gradient / Hessian to 1e-10 against the reference's
+    values, then the mMALA / RandomWalk chain replayed with the reference's draws to 1e-9."""
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA, RandomWalk
+
+    g = _load(name)
+    mdl, state = _lognormal_model_state(g)
+    np.testing.assert_allclose(mdl["theta"].log_p(state), g["logp0"], rtol=1e-10)
+    gr, H = mdl["theta"].grad_log_p(state, "theta", hessian_required=True)
+    np.testing.assert_allclose(gr, g["grad0"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(H, g["hess0"], rtol=1e-10, atol=1e-12)
+    step = np.array([[float(g["step"])]])
+    smp = ManifoldMALA("theta", mdl, step=step) if str(g["sampler"]) == "mmala" else RandomWalk("theta", mdl, step=step)
+    n_iter = g["store_theta"].shape[1]
+    M = MCMC(state, [smp], model=mdl, n_burn=0, n_iter=n_iter, debug_draws={"theta": {"z": g["z"], "u": g["u"]}})
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["theta"], g["store_theta"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
+    assert smp.accept_rate.count == {"accept": int(g["accept"][0]), "proposal": int(g["accept"][1])}
+
+
+def _mhreg_model_state(g):
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, LinearCombinationWithTransform, ScaledMatrix
+
+    mean = (LinearCombinationWithTransform(form={"beta": "X"}, transform={"beta": True}) if bool(g["transform"])
+            else LinearCombination(form={"beta": "X"}))
+    mdl = Model([Normal("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
+                 Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam"))])
+    n = g["y"].shape[0]
+    W = sparse.diags(g["w"], format="csc") if bool(g["weighted"]) else sparse.identity(n, format="csc")
+    state = {"y": g["y"], "X": g["X"], "beta": g["beta0"].copy(), "W": W, "tau": float(g["tau"]),
+             "mu": np.zeros_like(g["beta0"]), "P": g["P"], "lam": float(g["lam"])}
+    return mdl, state
+
+
+@pytest.mark.parametrize("name", ["mhreg_mmala_n60_p6", "mhreg_mmala_n200_p30_eye", "mhreg_exp_mmala_n80_p5"])
+def test_mmala_on_regression_coefficients(name):
+    """Mean-parameter branch of Normal.grad_log_p inside ManifoldMALA (location_scale.py:234-250), also through the exp
+    transform of LinearCombinationWithTransform (parameter.py:232-297): evaluated from the data-only regression record."""
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA
+
+    g = _load(name)
+    mdl, state = _mhreg_model_state(g)
+    np.testing.assert_allclose(mdl["y"].log_p(state), g["logp0"], rtol=1e-10)
+    gr, H = mdl["y"].grad_log_p(state, "beta", hessian_required=True)
+    np.testing.assert_allclose(gr, g["grad0"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(H, g["hess0"], rtol=1e-10, atol=1e-12)
+    if bool(g["transform"]):
+        np.testing.assert_allclose(mdl["y"].mean.predictor(state), g["X"] @ np.exp(g["beta0"]), rtol=1e-12)
+    smp = ManifoldMALA("beta", mdl, step=np.array([[float(g["step"])]]))
+    n_iter = g["store_beta"].shape[1]
+    M = MCMC(state, [smp], model=mdl, n_burn=0, n_iter=n_iter, debug_draws={"beta": {"z": g["z"], "u": g["u"]}})
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["beta"], g["store_beta"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
+    assert smp.accept_rate.count == {"accept": int(g["accept"][0]), "proposal": int(g["accept"][1])}
+
+
+def test_mmala_regression_free_running_matches_conjugate_posterior():
+    """Free-running mMALA on regression coefficients (fixed tau, lambda): the posterior is Gaussian in closed form, so
+    per-coordinate means / variances over many chains must agree within Monte-Carlo error."""
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA
+
+    g = _load("mhreg_mmala_n60_p6")
+    mdl, state = _mhreg_model_state(g)
+    C = 256
+    smp = ManifoldMALA("beta", mdl, step=np.array([[0.9]]))
+    M = MCMC(state, [smp], model=mdl, n_burn=60, n_iter=40, n_thin=2, n_chains=C, seed=2)
+    M.run_mcmc()
+    b = M.store["beta"]                                               # (C, p, n_iter)
+    X, y, w = g["X"], g["y"], g["w"]
+    Q = float(g["tau"]) * X.T @ (w[:, None] * X) + float(g["lam"]) * g["P"]
+    mean = np.linalg.solve(Q, float(g["tau"]) * X.T @ (w[:, None] * y)).ravel()
+    sd = np.sqrt(np.diag(np.linalg.inv(Q)))
+    draws = b[:, :, ::8].transpose(1, 0, 2).reshape(b.shape[1], -1)      # thinned further: ~independent
+    se = sd / np.sqrt(draws.shape[1] / 2)
+    assert np.all(np.abs(draws.mean(axis=1) - mean) < 5 * se), (draws.mean(axis=1), mean, se)
+    assert np.all(np.abs(draws.std(axis=1) / sd - 1) < 0.15)

@@ -89,6 +89,59 @@ def test_random_walk_chain(name):
     assert n_acc == g["accept"][0]
 
 
+def lognormal_terms(g):
+    return [mh.Term("lognormal_response", p1=g["mu"], Q=g["lam"] * g["P"]),
+            mh.Term("normal_response", p1=g["yobs"], Q=g["tau"] * np.diag(g["w"]))]
+
+
+def mhreg_terms(g):
+    return [mh.Term("normal_linear", data=g["y"], X=g["X"], Q=g["tau"] * np.diag(g["w"]), transform=bool(g["transform"])),
+            mh.Term("normal_response", p1=np.zeros_like(g["beta0"]), Q=g["lam"] * g["P"])]
+
+
+@pytest.mark.parametrize("name", ["lognormal_mmala_p5_dense", "lognormal_mmala_p24_diag", "lognormal_rw_p6_dense"])
+def test_lognormal_chain(name):
+    """LogNormal prior (location_scale.py:275-418), response branch; analytic in the reference."""
+    g = _load(name)
+    terms = lognormal_terms(g)
+    g0, H0 = terms[0].grad_hess_analytic(g["theta0"])
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(terms[0].log_p(g["theta0"]), g["logp0"], rtol=1e-13)
+    theta = g["theta0"]
+    n_acc = 0
+    for it in range(g["store_theta"].shape[1]):
+        if str(g["sampler"]) == "mmala":
+            theta, info = mh.mmala_step(terms, theta, float(g["step"]), g["z"][it], g["u"][it], "analytic")
+        else:
+            theta, info = mh.random_walk_step(terms, theta, np.array([[float(g["step"])]]), g["z"][it].reshape(theta.shape),
+                                              g["u"][it], None)
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_theta"][:, it], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-11)
+    assert n_acc == g["accept"][0]
+
+
+@pytest.mark.parametrize("name", ["mhreg_mmala_n60_p6", "mhreg_mmala_n200_p30_eye", "mhreg_exp_mmala_n80_p5"])
+def test_mh_regression_chain(name):
+    """SURVEY a4 in an MH sampler / f4: linear (optionally exp-transformed) Normal mean, mean-parameter branch of
+    Normal.grad_log_p (location_scale.py:234-250; parameter.py:199-228, 283-297)."""
+    g = _load(name)
+    terms = mhreg_terms(g)
+    g0, H0 = terms[0].grad_hess_analytic(g["beta0"])
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(terms[0].log_p(g["beta0"]), g["logp0"], rtol=1e-13)
+    theta = g["beta0"]
+    n_acc = 0
+    for it in range(g["store_beta"].shape[1]):
+        theta, info = mh.mmala_step(terms, theta, float(g["step"]), g["z"][it], g["u"][it], "analytic")
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-10)
+    assert n_acc == g["accept"][0]
+
+
 def test_truncnorm_grid():
     g = _load("truncnorm_grid")
     x = gmrf.truncated_normal_rv(g["mean"], g["scale"], g["lower"], g["upper"], g["u"])
