@@ -129,8 +129,50 @@ typedef struct {
   long long debug_sweep_stride;
   double* probe_a;      /* optional [n_chains] posterior shape */
   double* probe_b;      /* optional [n_chains] posterior rate  */
+  /* vector-valued precision (the K-loop of sampler.py:281-284 over mixture components): n_elem draws per chain,
+   * element k reads a0[k or 0], b0[k or 0], ss[k*ss_stride], cnt[k*cnt_stride]; out / debug_g / probes are
+   * [n_chains][n_elem].  n_elem == 0 means 1 (the scalar update above). */
+  int n_elem, a0_len, b0_len;
+  long long ss_stride, cnt_stride;
 } omc_ng_draw_t;
 int omc_ng_draw(const omc_ng_draw_t* args, void* stream);
+
+/* ------------------------------------------------------------------ mixture models
+ * x_i ~ N(mu[z_i], 1/tau[z_i]), z_i ~ Categorical(prob), i < n, K components; allocations are float64 integers.
+ * omc_mixture_allocation: z_i = #{k : U_i > cumsum_k(gam)}, gam_k = prob_k N(x_i; mu_k, 1/tau_k) normalised
+ *   ref: sampler.py:292-355 (MixtureAllocation.sample)
+ * omc_mixture_stats: per component  n_k, sum_{z_i=k} x_i, sum_{z_i=k} (x_i - mu_k)^2  (what the NormalGamma K-loop,
+ *   sampler.py:272-288 with parameter.py:522-538, and a NormalNormal update of mu need); optionally the same numbers as
+ *   a regression-format record  G = diag(tau_k n_k) | g = tau_k sum x | rss = sum_k tau_k S2_k | cnt = n  for
+ *   omc_nn_dense_draw, the gathers mu[z_i] / tau[z_i] (MixtureParameterVector / Matrix predictors, parameter.py:437-446,
+ *   494-504) and the Normal log-density of x, 0.5 (sum_k n_k log tau_k - n log 2 pi - sum_k tau_k S2_k). */
+typedef struct {
+  int n_chains, n, K;
+  omc_vec_t x;            /* [n]                                     */
+  omc_vec_t mu, tau;      /* [K]                                     */
+  omc_vec_t prob;         /* [prob_rows][K], prob_rows in {1, n}     */
+  int prob_rows;
+  double* z;              /* [n_chains][n] out                       */
+  omc_rng_t rng;
+  const double* debug_u;  /* injected uniforms [n_chains][n] (the reference's uniform.rvs(size=(n,1))) */
+  long long debug_sweep_stride;
+} omc_mixture_alloc_t;
+int omc_mixture_allocation(const omc_mixture_alloc_t* args, void* stream);
+typedef struct {
+  int n_chains, n, K;
+  omc_vec_t x, mu, tau;
+  const double* z;        /* [n_chains][n]                           */
+  double* stats;          /* out [n_chains][K][4]: n_k, sum x, sum (x - mu_k)^2, 0 */
+  double* record;         /* optional out [n_chains][K*K + K + 2]    */
+  double* gather_mu;      /* optional out [n_chains][n]              */
+  double* gather_tau;     /* optional out [n_chains][n]              */
+  double* logp;           /* optional out [n_chains]                 */
+  int accumulate;
+} omc_mixture_stats_t;
+int omc_mixture_stats(const omc_mixture_stats_t* args, void* stream);
+/* out[c] (+)= sum_i log prob[i or 0][z_i]   (ref: distribution.py:318-345, multinomial(n = 1) log-pmf) */
+int omc_logp_categorical(int n_chains, int n, int K, const double* z, omc_vec_t prob, int prob_rows, double* out,
+                         int accumulate, void* stream);
 
 /* ------------------------------------------------------------------ log-densities (ref: Model.log_p, model.py:57-70)
  * Every kernel writes out[c] (accumulate = 0) or adds to it (accumulate = 1), one value per chain. */

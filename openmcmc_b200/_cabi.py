@@ -92,7 +92,28 @@ class NGDraw(C.Structure):
         ("debug_sweep_stride", C.c_longlong),
         ("probe_a", C.c_void_p),
         ("probe_b", C.c_void_p),
+        ("n_elem", C.c_int),
+        ("a0_len", C.c_int),
+        ("b0_len", C.c_int),
+        ("ss_stride", C.c_longlong),
+        ("cnt_stride", C.c_longlong),
     ]
+
+
+class MixtureAlloc(C.Structure):
+    """omc_mixture_alloc_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n", C.c_int), ("K", C.c_int), ("x", Vec), ("mu", Vec), ("tau", Vec),
+                ("prob", Vec), ("prob_rows", C.c_int), ("z", C.c_void_p), ("rng", Rng), ("debug_u", C.c_void_p),
+                ("debug_sweep_stride", C.c_longlong)]
+
+
+class MixtureStats(C.Structure):
+    """omc_mixture_stats_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n", C.c_int), ("K", C.c_int), ("x", Vec), ("mu", Vec), ("tau", Vec),
+                ("z", C.c_void_p), ("stats", C.c_void_p), ("record", C.c_void_p), ("gather_mu", C.c_void_p),
+                ("gather_tau", C.c_void_p), ("logp", C.c_void_p), ("accumulate", C.c_int)]
 
 
 class LogpNormalSS(C.Structure):
@@ -195,6 +216,10 @@ PROTOTYPES = {
     "omc_logp_gamma": (C.c_int, [C.POINTER(LogpGamma), C.c_void_p]),
     "omc_logp_poisson": (C.c_int, [C.POINTER(LogpPoisson), C.c_void_p]),
     "omc_logp_const": (C.c_int, [C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "omc_mixture_allocation": (C.c_int, [C.POINTER(MixtureAlloc), C.c_void_p]),
+    "omc_mixture_stats": (C.c_int, [C.POINTER(MixtureStats), C.c_void_p]),
+    "omc_logp_categorical": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, Vec, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p]),
     "omc_logp_domain": (C.c_int, [C.c_int, C.c_int, Vec, Vec, C.c_int, Vec, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),

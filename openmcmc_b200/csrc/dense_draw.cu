@@ -224,17 +224,19 @@ __global__ void quadform_kernel(omc_quadform_t a) {
 }
 
 __global__ void ng_draw_kernel(omc_ng_draw_t a) {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= a.n_chains) return;
-  const double shape = vec_at(a.a0, chain, 0, 0.0) + 0.5 * vec_at(a.cnt, chain, 0, 0.0);
-  const double rate = vec_at(a.b0, chain, 0, 0.0) + 0.5 * vec_at(a.ss, chain, 0, 0.0);
-  if (a.probe_a) a.probe_a[chain] = shape;
-  if (a.probe_b) a.probe_b[chain] = rate;
+  const int ne = a.n_elem > 0 ? a.n_elem : 1;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.n_chains * ne) return;
+  const int chain = (int)(t / ne), k = (int)(t - (long long)chain * ne);
+  const double shape = vec_at(a.a0, chain, a.a0_len > 1 ? k : 0, 0.0) + 0.5 * vec_at(a.cnt, chain, k * a.cnt_stride, 0.0);
+  const double rate = vec_at(a.b0, chain, a.b0_len > 1 ? k : 0, 0.0) + 0.5 * vec_at(a.ss, chain, k * a.ss_stride, 0.0);
+  if (a.probe_a) a.probe_a[t] = shape;
+  if (a.probe_b) a.probe_b[t] = rate;
   double gvar;
-  if (a.debug_g) gvar = a.debug_g[(a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride + chain];
-  else gvar = omc_std_gamma(to_rng(a.rng), chain, 0, shape);
+  if (a.debug_g) gvar = a.debug_g[(a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride + t];
+  else gvar = omc_std_gamma(to_rng(a.rng), chain, (unsigned int)k << 12, shape);   // 4096 Philox blocks per element
   // reference: scale = inf when rate == 0 (sampler.py:285-286)
-  a.out[chain] = (rate == 0.0) ? INFINITY : gvar * (1.0 / rate);
+  a.out[t] = (rate == 0.0) ? INFINITY : gvar * (1.0 / rate);
 }
 
 }  // namespace
@@ -266,7 +268,8 @@ extern "C" int omc_quadform(const omc_quadform_t* args, void* stream) {
 extern "C" int omc_ng_draw(const omc_ng_draw_t* args, void* stream) {
   OMC_REQUIRE(args && args->out, "omc_ng_draw: null argument");
   const int threads = 128;
-  ng_draw_kernel<<<(args->n_chains + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(*args);
+  const long long total = (long long)args->n_chains * (args->n_elem > 0 ? args->n_elem : 1);
+  ng_draw_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*args);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -142,3 +142,31 @@ class Poisson(Distribution):
         from openmcmc_b200 import hostcalls
 
         return hostcalls.rvs(self, state, n)
+
+
+@dataclass
+class Categorical(Distribution):
+    """Categorical allocation prior: response in {0, ..., n_cat - 1}, prob of shape (1 or p, n_cat).
+    ref: distribution.py:282-374.  log_p = sum_i log prob[i, z_i] (the multinomial(n = 1) log-pmf of :318-345)."""
+
+    prob: Union[str, Identity]
+
+    def __post_init__(self):
+        if isinstance(self.prob, str):
+            self.prob = Identity(self.prob)
+        if not isinstance(self.prob, Identity):
+            raise TypeError("prob expected to be Identity")
+
+    @property
+    def _dist_params(self) -> list:
+        return self.prob.get_param_list()
+
+    def log_p(self, state: dict, by_observation: bool = False):
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.log_p(self, state, by_observation)
+
+    def rvs(self, state, n: int = 1):
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.rvs(self, state, n)

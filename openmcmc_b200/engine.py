@@ -378,6 +378,65 @@ class RegressionLikelihood:
         return K.vec((self.stats[:, self.p * self.p + self.p + 1:], self.rec))
 
 
+class MixtureNormal:
+    """x_i ~ N(mu[z_i], 1/tau[z_i]) (MixtureParameterVector mean, MixtureParameterMatrix precision): owner of the
+    per-component sufficient statistics, the regression-format record for a NormalNormal update of mu, and the gathers
+    mu[z], tau[z] a NormalNormal update of x uses as its prior.  ref: parameter.py:377-538, sampler.py:272-355."""
+
+    def __init__(self, plan: Plan, host_state, dist):
+        from openmcmc_b200.parameter import MixtureParameterMatrix, MixtureParameterVector
+
+        if not isinstance(dist.mean, MixtureParameterVector) or not isinstance(dist.precision, MixtureParameterMatrix):
+            raise PlanError("a mixture Normal needs a MixtureParameterVector mean and a MixtureParameterMatrix precision")
+        if dist.mean.allocation != dist.precision.allocation:
+            raise PlanError("mixture mean and precision must share their allocation parameter")
+        st = plan.state
+        self.plan, self.dist = plan, dist
+        self.names = (dist.response, dist.mean.param, dist.precision.param, dist.mean.allocation)
+        self.x, self.mu, self.tau, self.z = (st[nm] for nm in self.names)
+        if self.x.cols != 1:
+            raise PlanError("replicated mixture responses (n_rep > 1) are not supported by the device path")
+        if not self.z.per_chain:
+            self.z = st.put(dist.mean.allocation, host_state[dist.mean.allocation], per_chain=True)
+        self.n, self.K = self.x.rows, self.mu.size
+        if self.tau.size != self.K or self.K > 64:
+            raise PlanError(f"mixture with {self.mu.size} means / {self.tau.size} precisions (at most 64 components)")
+        C = st.n_chains
+        self.rec = self.K * self.K + self.K + 2
+        self.stats = plan.new(C, self.K, 4, fill=0.0)
+        self.record = plan.new(C, self.rec, fill=0.0)
+        self.g_mu, self.g_tau = plan.new(C, self.n), plan.new(C, self.n)
+        self.qname = f"mixture[{dist.response}]"
+        plan.add_quantity(Quantity(self.qname, frozenset(self.names), self._emit))
+
+    def _emit(self):
+        C = self.plan.state.n_chains
+
+        def launch():
+            K.mixture_stats(C, self.n, self.K, self.x.vec(), self.mu.vec(), self.tau.vec(), self.z.data, self.stats,
+                            record=self.record, gather_mu=self.g_mu, gather_tau=self.g_tau)
+
+        self.plan.emit(launch, f"mixture_stats[{self.dist.response}]")
+
+    def emit_log_p(self, out, acc):
+        """Normal log-density of x under the current allocation (fresh pass: log_post runs after the sweep)."""
+        C = self.plan.state.n_chains
+        scratch = self.plan.new(C, self.K, 4)
+
+        def launch():
+            K.mixture_stats(C, self.n, self.K, self.x.vec(), self.mu.vec(), self.tau.vec(), self.z.data, scratch,
+                            logp=out, accumulate=acc)
+
+        self.plan.emit(launch, f"logp_mixture[{self.dist.response}]")
+
+
+def get_mixture(plan: Plan, host_state, dist) -> MixtureNormal:
+    cache = plan.__dict__.setdefault("_mixtures", {})
+    if dist.response not in cache:
+        cache[dist.response] = MixtureNormal(plan, host_state, dist)
+    return cache[dist.response]
+
+
 def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
     """Fitted values store[response][:, it] = dist.<predictor>.predictor(state).  ref: mcmc.py:109-111."""
     st = plan.state
@@ -507,8 +566,9 @@ def logdet_of(plan: Plan, P: DevArray):
 
 def compile_log_post(plan: Plan, host_state, model, out):
     """Emit kernels accumulating model.log_p(state) per chain into `out` [C].  ref: mcmc.py:108, model.py:57-70."""
-    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.distribution import Categorical, Gamma, Poisson, Uniform
     from openmcmc_b200.distribution.location_scale import LogNormal, Normal, NullDistribution
+    from openmcmc_b200.parameter import MixtureParameterMatrix
 
     st = plan.state
     C = st.n_chains
@@ -534,6 +594,23 @@ def compile_log_post(plan: Plan, host_state, model, out):
                 K.mh_logp(tm, x.data, out, accumulate=acc)
 
             plan.emit(launch, f"logp_terms[{dist.response}]")
+        elif isinstance(dist, Normal) and isinstance(dist.precision, MixtureParameterMatrix):
+            get_mixture(plan, host_state, dist).emit_log_p(out, acc)
+        elif isinstance(dist, Categorical):
+            z, prob = st[dist.response], st[dist.prob.form]
+            if z.cols != 1:
+                raise PlanError("log_post: replicated Categorical responses are not supported on the device")
+            if not z.per_chain:
+                z = st.put(dist.response, host_state[dist.response], per_chain=True)
+            kk = prob.cols
+            prob_rows = prob.rows
+            if prob_rows not in (1, z.rows):
+                raise PlanError("Categorical: prob must have 1 or n rows")
+
+            def launch(z=z, prob=prob, kk=kk, prob_rows=prob_rows, acc=acc):
+                K.logp_categorical(C, z.rows, kk, z.data, prob.vec(), prob_rows, out, acc)
+
+            plan.emit(launch, f"logp_categorical[{dist.response}]")
         elif isinstance(dist, Normal):
             mname, sname = _scalar_and_matrix(dist.precision)
             ss_vec, _, qname = get_quadratic_form(plan, host_state, dist)

@@ -112,8 +112,11 @@ def quadform(n_chains, p, x, mu, kind, P, ss, cnt):
     check(lib().omc_quadform(C.byref(a), stream_ptr()), "omc_quadform")
 
 
-def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None, debug_sweep_stride=0):
+def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None, debug_sweep_stride=0,
+            n_elem=0, a0_len=1, b0_len=1, ss_stride=0, cnt_stride=0):
+    """n_elem > 0: vector-valued update, element k reads ss[k*ss_stride], cnt[k*cnt_stride] (omc.h)."""
     a = _cabi.NGDraw()
+    a.n_elem, a.a0_len, a.b0_len, a.ss_stride, a.cnt_stride = int(n_elem), int(a0_len), int(b0_len), int(ss_stride), int(cnt_stride)
     a.n_chains, a.a0, a.b0, a.ss, a.cnt = n_chains, a0, b0, ss, cnt
     a.out = out.data_ptr()
     a.rng = rng_
@@ -122,6 +125,32 @@ def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, pr
     a.probe_a = probe_a.data_ptr() if probe_a is not None else None
     a.probe_b = probe_b.data_ptr() if probe_b is not None else None
     check(lib().omc_ng_draw(C.byref(a), stream_ptr()), "omc_ng_draw")
+
+
+# ----------------------------------------------------------------------------- mixture models
+def mixture_allocation(n_chains, n, K, x, mu, tau, prob, prob_rows, z, rng_, debug_u=None, debug_sweep_stride=0):
+    a = _cabi.MixtureAlloc()
+    a.n_chains, a.n, a.K, a.x, a.mu, a.tau, a.prob, a.prob_rows = n_chains, n, K, x, mu, tau, prob, int(prob_rows)
+    a.z = z.data_ptr()
+    a.rng = rng_
+    a.debug_u = debug_u.data_ptr() if debug_u is not None else None
+    a.debug_sweep_stride = int(debug_sweep_stride)
+    check(lib().omc_mixture_allocation(C.byref(a), stream_ptr()), "omc_mixture_allocation")
+
+
+def mixture_stats(n_chains, n, K, x, mu, tau, z, stats, record=None, gather_mu=None, gather_tau=None, logp=None,
+                  accumulate=False):
+    a = _cabi.MixtureStats()
+    a.n_chains, a.n, a.K, a.x, a.mu, a.tau = n_chains, n, K, x, mu, tau
+    a.z, a.stats = z.data_ptr(), stats.data_ptr()
+    a.record, a.gather_mu, a.gather_tau, a.logp = _ptr(record), _ptr(gather_mu), _ptr(gather_tau), _ptr(logp)
+    a.accumulate = int(bool(accumulate))
+    check(lib().omc_mixture_stats(C.byref(a), stream_ptr()), "omc_mixture_stats")
+
+
+def logp_categorical(n_chains, n, K, z, prob, prob_rows, out, accumulate):
+    check(lib().omc_logp_categorical(n_chains, n, K, _ptr(z), prob, int(prob_rows), _ptr(out), int(bool(accumulate)),
+                                     stream_ptr()), "omc_logp_categorical")
 
 
 # ----------------------------------------------------------------------------- log densities / predictors

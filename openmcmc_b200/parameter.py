@@ -124,7 +124,11 @@ class MixtureParameter(Parameter, ABC):
         return [self.param, self.allocation]
 
     def predictor(self, state: dict):
-        raise NotImplementedError("Mixture parameters are outside the round-1 hot path (SURVEY.md §8 f2)")
+        """param[allocation] (parameter.py:437-446; the Matrix flavour wraps it in a sparse diagonal, :494-504): a plain
+        index gather of constant-shaped host arrays, no arithmetic."""
+        import numpy as np
+
+        return np.asarray(state[self.param])[np.asarray(state[self.allocation]).astype(int).flatten()]
 
 
 @dataclass

@@ -3,7 +3,8 @@
 The classes keep the reference's constructor signatures and `.sample(state) -> state` contract.  Numerically they are
 *plan fragments*: `compile(plan, host_state)` appends the CUDA kernel launches of one update to the sweep plan
 (engine.Plan); `.sample()` on a host dict compiles and runs a one-sampler plan on the device (n_chains = 1).
-MixtureAllocation is SURVEY §8 f2 ("next") and not provided in round 1.
+MixtureAllocation draws the allocations of a mixture Normal; NormalGamma / NormalNormal understand the
+MixtureParameterVector / MixtureParameterMatrix parameters of that Normal.
 """
 
 from abc import ABC, abstractmethod
@@ -16,7 +17,13 @@ from openmcmc_b200 import engine
 from openmcmc_b200 import kernels as K
 from openmcmc_b200.distribution.location_scale import Normal
 from openmcmc_b200.model import Model
-from openmcmc_b200.parameter import Identity, LinearCombination, MixtureParameterMatrix, ScaledMatrix
+from openmcmc_b200.parameter import (
+    Identity,
+    LinearCombination,
+    MixtureParameterMatrix,
+    MixtureParameterVector,
+    ScaledMatrix,
+)
 
 
 @dataclass
@@ -97,7 +104,8 @@ class NormalNormal(MCMCSampler):
         lik = liks[0]
         from openmcmc_b200 import gmrf_plan
 
-        if gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, lik):
+        if (not isinstance(prior.precision, MixtureParameterMatrix)
+                and gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, lik)):
             if prior.domain_response_lower is not None or prior.domain_response_upper is not None:
                 raise engine.PlanError("a truncated prior on the tridiagonal (GMRF) path is not supported: the "
                                        "coordinate-wise scan of gmrf.py:201-266 is sequential over 1e6 elements")
@@ -108,20 +116,33 @@ class NormalNormal(MCMCSampler):
             f"NormalNormal: a likelihood mean of type {type(lik.mean).__name__} with a small dense prior is not "
             "supported by the device path (write it as LinearCombination({param: X}))")
 
-    def _compile_dense(self, plan, host_state, prior, lik, debug_draws):
+    def _compile_dense(self, plan, host_state, prior, lik, debug_draws, source=None):
+        """source (mixture-mean update): the likelihood record comes from engine.MixtureNormal instead of the regression
+        pass.  A mixture PRIOR (MixtureParameterVector mean / MixtureParameterMatrix precision on the sampled vector,
+        the reference's tests/test_sampler.py:113-147 model) enters as a per-chain diagonal prior tau[z] with mean mu[z]."""
         st = plan.state
         C = st.n_chains
-        rl = engine.get_regression(plan, host_state, lik, self.param)
-        p = rl.p
-        if not isinstance(prior.mean, Identity):
-            raise engine.PlanError("NormalNormal: prior mean must be an Identity parameter")
-        mu0 = st[prior.mean.form]
-        pm_name, lam_name = engine._scalar_and_matrix(prior.precision)
-        P0 = engine.ensure_matrix(st, host_state, pm_name)
-        if P0.kind == "tridiag":
-            raise engine.PlanError("tridiagonal prior with a regression likelihood is not supported")
-        lam = st[lam_name] if lam_name else None
-        tau = st[rl.scalar] if rl.scalar else None
+        if source is None:
+            rl = engine.get_regression(plan, host_state, lik, self.param)
+            source = dict(stats=rl.stats, rec=rl.rec, p=rl.p, tau=st[rl.scalar] if rl.scalar else None, require=rl.q_gg)
+        p = source["p"]
+        tau = source["tau"]
+        requires = [source["require"]]
+        if isinstance(prior.mean, MixtureParameterVector) and isinstance(prior.precision, MixtureParameterMatrix):
+            mix = engine.get_mixture(plan, host_state, prior)
+            requires.append(mix.qname)
+            mu0_vec = lambda: K.vec(mix.g_mu, mix.n)          # noqa: E731
+            P0_kind, P0_vec, lam = K.MAT_DIAG, (lambda: K.vec(mix.g_tau, mix.n)), None
+        else:
+            if not isinstance(prior.mean, Identity):
+                raise engine.PlanError("NormalNormal: prior mean must be an Identity (or mixture) parameter")
+            mu0 = st[prior.mean.form]
+            pm_name, lam_name = engine._scalar_and_matrix(prior.precision)
+            P0 = engine.ensure_matrix(st, host_state, pm_name)
+            if P0.kind == "tridiag":
+                raise engine.PlanError("tridiagonal prior with a regression likelihood is not supported")
+            lam = st[lam_name] if lam_name else None
+            mu0_vec, P0_kind, P0_vec = mu0.vec, engine._mat_kind(P0), P0.vec
         beta = st[self.param]
         ctx = plan.ctx(self)
         if "rng" not in ctx:
@@ -151,12 +172,14 @@ class NormalNormal(MCMCSampler):
                 if debug_draws and "u" in debug_draws:
                     ctx["dz"], ctx["dz_stride"] = plan.debug_tensor(debug_draws["u"], p)
         rng, dz, dz_stride, probes, trunc = ctx["rng"], ctx["dz"], ctx["dz_stride"], ctx["probes"], ctx["trunc"]
-        plan.require(rl.q_gg)
+        for q in requires:
+            plan.require(q)
+        stats = source["stats"]
 
         def launch():
             K.nn_dense_draw(
-                C, p, rl.stats, tau.vec() if tau else K.vec(None), engine._mat_kind(P0), P0.vec(),
-                lam.vec() if lam else K.vec(None), mu0.vec(), beta.data, rng, debug_z=None if trunc else dz,
+                C, p, stats, tau.vec() if tau else K.vec(None), P0_kind, P0_vec(),
+                lam.vec() if lam else K.vec(None), mu0_vec(), beta.data, rng, debug_z=None if trunc else dz,
                 probe_Q=probes["Q"] if probes else None, probe_b=probes["b"] if probes else None,
                 probe_L=probes["L"] if probes else None, probe_mu=probes["mu"] if probes else None, status=plan.status,
                 debug_sweep_stride=dz_stride, trunc=trunc, debug_u=dz if trunc else None)
@@ -192,6 +215,8 @@ class NormalGamma(MCMCSampler):
         nrm = self.model[self.normal_param]
         if not isinstance(gam, Gamma) or not isinstance(gam.shape, Identity) or not isinstance(gam.rate, Identity):
             raise engine.PlanError("NormalGamma needs a Gamma prior with Identity shape and rate")
+        if isinstance(nrm.precision, MixtureParameterMatrix) and nrm.precision.param == self.param:
+            return self._compile_mixture(plan, host_state, gam, nrm, debug_draws)
         if not isinstance(nrm.precision, ScaledMatrix) or nrm.precision.scalar != self.param:
             raise engine.PlanError("NormalGamma: the Normal precision must be ScaledMatrix(matrix, scalar=param)")
         out = st[self.param]
@@ -217,4 +242,85 @@ class NormalGamma(MCMCSampler):
                       debug_sweep_stride=dg_stride)
 
         plan.emit(launch, f"ng_draw[{self.param}]")
+        plan.wrote(self.param)
+
+    def _compile_mixture(self, plan, host_state, gam, nrm, debug_draws):
+        """The K-loop of sampler.py:281-284 over the components of a MixtureParameterMatrix precision: a*_k = a_k +
+        n_k / 2, b*_k = b_k + sum_{z_i = k} (x_i - mu[z_i])^2 / 2 (parameter.py:522-538: the un-scaled precision of
+        component k is the 0/1 diagonal of its allocation matches), all K Gamma draws in one launch."""
+        st = plan.state
+        C = st.n_chains
+        mix = engine.get_mixture(plan, host_state, nrm)
+        out = st[self.param]
+        a0, b0 = st[gam.shape.form], st[gam.rate.form]
+        for v, what in ((a0, "shape"), (b0, "rate")):
+            if v.size not in (1, mix.K):
+                raise engine.PlanError(f"NormalGamma: Gamma {what} of size {v.size} for {mix.K} mixture components")
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["dg"], ctx["dg_stride"] = (None, 0)
+            if debug_draws and "g" in debug_draws:
+                ctx["dg"], ctx["dg_stride"] = plan.debug_tensor(debug_draws["g"], mix.K)
+            ctx["probes"] = None
+            if plan.probes is not None and plan.probes.get("enable"):
+                plan.probes[self.param] = ctx["probes"] = {"a": plan.new(C, mix.K), "b": plan.new(C, mix.K)}
+        rng, dg, dg_stride, probes = ctx["rng"], ctx["dg"], ctx["dg_stride"], ctx["probes"]
+        plan.require(mix.qname)
+        stride = mix.K * 4
+
+        def launch():
+            K.ng_draw(C, a0.vec(), b0.vec(), K.vec((mix.stats[:, 0, 2:], stride)), K.vec((mix.stats, stride)), out.data,
+                      rng, debug_g=dg, probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
+                      debug_sweep_stride=dg_stride, n_elem=mix.K, a0_len=a0.size, b0_len=b0.size, ss_stride=4,
+                      cnt_stride=4)
+
+        plan.emit(launch, f"ng_draw[{self.param}]")
+        plan.wrote(self.param)
+
+
+@dataclass
+class MixtureAllocation(MCMCSampler):
+    """Conjugate draw of the allocations of a mixture Normal: z_i ~ Cat(gam_i), gam_ik proportional to
+    prob_k N(x_i; mu_k, 1/tau_k).  ref: sampler.py:292-355.  `debug_draws={"u": ...}` injects the uniforms of the
+    reference's uniform.rvs(size=(n, 1))."""
+
+    response_param: Union[str, None] = None
+
+    def __post_init__(self):
+        from openmcmc_b200.distribution.distribution import Categorical
+
+        self.model = Model([self.model[self.param], self.model[self.response_param]])
+        nrm = self.model[self.response_param]
+        if not isinstance(nrm, Normal):
+            raise TypeError("Mixture model currently only implemented for Normal case")
+        if not isinstance(nrm.mean, MixtureParameterVector):
+            raise TypeError("Mean must be of type MixtureParameterVector")
+        if not isinstance(nrm.precision, MixtureParameterMatrix):
+            raise TypeError("Mean must be of type MixtureParameterMatrix")
+        if not isinstance(self.model[self.param], Categorical):
+            raise TypeError("the allocation parameter needs a Categorical prior")
+
+    def compile(self, plan, host_state, debug_draws=None):
+        st = plan.state
+        C = st.n_chains
+        nrm = self.model[self.response_param]
+        mix = engine.get_mixture(plan, host_state, nrm)
+        prob = st[self.model[self.param].prob.form]
+        if prob.cols != mix.K or prob.rows not in (1, mix.n):
+            raise engine.PlanError(f"allocation prior of shape ({prob.rows},{prob.cols}) for {mix.n} responses and "
+                                   f"{mix.K} components")
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["du"], ctx["du_stride"] = (None, 0)
+            if debug_draws and "u" in debug_draws:
+                ctx["du"], ctx["du_stride"] = plan.debug_tensor(debug_draws["u"], mix.n)
+        rng, du, du_stride = ctx["rng"], ctx["du"], ctx["du_stride"]
+
+        def launch():
+            K.mixture_allocation(C, mix.n, mix.K, mix.x.vec(), mix.mu.vec(), mix.tau.vec(), prob.vec(), prob.rows,
+                                 mix.z.data, rng, debug_u=du, debug_sweep_stride=du_stride)
+
+        plan.emit(launch, f"mixture_allocation[{self.param}]")
         plan.wrote(self.param)

@@ -166,3 +166,68 @@ def gmrf_log_post(pd, pe, w, y, mu0, s):
     lp += dist.normal_log_p_from_ss(n, s["lambda"], gmrf.tridiag_logdet(pd, pe), gmrf.tridiag_quadform(pd, pe, s["b"] - mu0))
     lp += dist.gamma_log_p(s["lambda"], s["a_lam"], s["b_lam"]) + dist.gamma_log_p(s["tau"], s["a_tau"], s["b_tau"])
     return lp
+
+
+# ----------------------------------------------------------------------------------------------- mixture model (f2)
+def mixture_allocation(x, mu, tau, prob, u):
+    """MixtureAllocation.sample: gam_ik = prob_k N(x_i; mu_k, 1/tau_k) normalised over k; z_i = #{k: u_i > cumsum_k}.
+    ref: sampler.py:331-355.  x [n], mu / tau [K], prob [1 or n, K], u [n]."""
+    from scipy.stats import norm
+
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    mu, tau = np.asarray(mu, float).ravel(), np.asarray(tau, float).ravel()
+    prob = np.atleast_2d(np.asarray(prob, float))
+    gam = np.empty((x.shape[0], mu.size))
+    for k in range(mu.size):
+        gam[:, [k]] = prob[:, [k]] * norm.pdf(x, loc=mu[k], scale=1 / np.sqrt(tau[k]))
+    gam = gam / np.sum(gam, axis=1).reshape(-1, 1)
+    return np.sum(np.asarray(u, float).reshape(-1, 1) > np.cumsum(gam, axis=1), axis=1).astype(np.float64)
+
+
+def mixture_stats(x, mu, z, K):
+    """Per component: n_k, sum x, sum (x - mu_k)^2 over the observations allocated to it (parameter.py:522-538)."""
+    x, z = np.asarray(x, float).ravel(), np.asarray(z).ravel().astype(int)
+    mu = np.asarray(mu, float).ravel()
+    out = np.zeros((K, 3))
+    for k in range(K):
+        m = z == k
+        out[k] = (m.sum(), x[m].sum(), np.sum((x[m] - mu[k]) ** 2))
+    return out
+
+
+def mixture_normal_gamma(x, mu, z, a0, b0, g):
+    """NormalGamma K-loop: a*_k = a_k + n_k/2, b*_k = b_k + S2_k/2, tau_k = g_k / b*_k.  ref: sampler.py:272-288."""
+    K = np.asarray(mu).size
+    st = mixture_stats(x, mu, z, K)
+    a_post = np.broadcast_to(np.asarray(a0, float).ravel(), (K,)) + st[:, 0] / 2
+    b_post = np.broadcast_to(np.asarray(b0, float).ravel(), (K,)) + st[:, 2] / 2
+    return np.asarray(g, float).ravel() / b_post, a_post, b_post
+
+
+def mixture_normal_log_p(x, mu, tau, z):
+    """Normal.log_p with MixtureParameterVector mean / MixtureParameterMatrix precision.  ref: location_scale.py:145-167"""
+    x, z = np.asarray(x, float).ravel(), np.asarray(z).ravel().astype(int)
+    m, t = np.asarray(mu, float).ravel()[z], np.asarray(tau, float).ravel()[z]
+    return float(0.5 * (np.sum(np.log(t)) - x.size * np.log(2 * np.pi) - np.sum(t * (x - m) ** 2)))
+
+
+def categorical_log_p(z, prob):
+    """Categorical.log_p for a (p, 1) response: sum_i log prob[i or 0, z_i].  ref: distribution.py:318-345"""
+    z = np.asarray(z).ravel().astype(int)
+    prob = np.atleast_2d(np.asarray(prob, float))
+    rows = np.arange(z.size) if prob.shape[0] > 1 else np.zeros(z.size, dtype=int)
+    return float(np.sum(np.log(prob[rows, z])))
+
+
+def gibbs_mixture_sweep(X, y, w, state, prob, a_tau, b_tau, z_beta, g, u):
+    """One sweep of the standard mixture model (tests/test_sampler.py:113-147 form): NormalNormal(beta) with the
+    mixture prior N(mu[z], diag(tau[z])^-1), NormalGamma(tau) K-loop, MixtureAllocation(z)."""
+    s = dict(state)
+    G, gv, _, _ = regression_suffstats(X, y, w)
+    zi = np.asarray(s["z"]).ravel().astype(int)
+    s["beta"] = normal_normal_dense(G, gv, 1.0, np.asarray(s["tau"], float).ravel()[zi], 1.0,
+                                    np.asarray(s["mu"], float).ravel()[zi], z_beta)["x"]
+    s["tau"], _, _ = mixture_normal_gamma(s["beta"], s["mu"], s["z"], a_tau, b_tau, g)
+    s["z"] = mixture_allocation(s["beta"], s["mu"], s["tau"], prob, u)
+    return s
+

@@ -19,14 +19,14 @@ sys.path.insert(0, REF)
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 from openmcmc import gmrf  # noqa: E402
-from openmcmc.distribution.distribution import Gamma, Poisson, Uniform  # noqa: E402
+from openmcmc.distribution.distribution import Categorical, Gamma, Poisson, Uniform  # noqa: E402
 from openmcmc.distribution.location_scale import LogNormal, Normal  # noqa: E402
 from openmcmc.parameter import LinearCombinationWithTransform  # noqa: E402
 from openmcmc.mcmc import MCMC  # noqa: E402
 from openmcmc.model import Model  # noqa: E402
 from openmcmc.parameter import Identity, LinearCombination, ScaledMatrix  # noqa: E402
 from openmcmc.sampler.metropolis_hastings import ManifoldMALA, RandomWalk, RandomWalkLoop  # noqa: E402
-from openmcmc.sampler.sampler import NormalGamma, NormalNormal  # noqa: E402
+from openmcmc.sampler.sampler import MixtureAllocation, NormalGamma, NormalNormal  # noqa: E402
 from openmcmc.sampler.reversible_jump import ReversibleJump  # noqa: E402
 from openmcmc.distribution.location_scale import NullDistribution  # noqa: E402
 from openmcmc.parameter import MixtureParameterMatrix, MixtureParameterVector  # noqa: E402
@@ -352,6 +352,61 @@ def mh_f4_cases():
     }
 
 
+# ----------------------------------------------------------------------------------------------- mixture model
+def mixture_case(n, p, n_cat, seed, n_iter, sample_mean=True, prob_rows=1):
+    """The reference's standard mixture model (tests/test_sampler.py:113-147): y ~ N(X beta, W^-1), beta_i ~
+    N(mu[z_i], 1/tau[z_i]), z_i ~ Cat(prob), tau_k ~ Gamma; optionally mu ~ N(m0, (lam0 I)^-1).  Samplers:
+    NormalNormal(beta), [NormalNormal(mu)], NormalGamma(tau) with its K-loop, MixtureAllocation(z)."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, p))
+    z_true = rng.integers(0, n_cat, size=(p, 1))
+    mu_true = np.linspace(-3, 3, n_cat).reshape(n_cat, 1)
+    beta_true = mu_true[z_true.ravel()] + 0.3 * rng.standard_normal((p, 1))
+    y = X @ beta_true + 0.5 * rng.standard_normal((n, 1))
+    W = sparse.diags(rng.random(n) + 0.5, format="csc")
+    prob = rng.random((prob_rows, n_cat)) + 0.2
+    prob = prob / prob.sum(axis=1, keepdims=True)
+    dists = [Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=Identity("W")),
+             Normal("beta", mean=MixtureParameterVector(param="mu", allocation="z"),
+                    precision=MixtureParameterMatrix(param="tau", allocation="z")),
+             Gamma("tau", shape="a_tau", rate="b_tau"),
+             Categorical("z", prob="prob")]
+    if sample_mean:
+        dists.append(Normal("mu", mean="m0", precision=ScaledMatrix(matrix="P_mu", scalar="lam0")))
+    mdl = Model(dists)
+    samplers = [NormalNormal("beta", mdl)]
+    if sample_mean:
+        samplers.append(NormalNormal("mu", mdl))
+    samplers += [NormalGamma("tau", mdl), MixtureAllocation("z", mdl, response_param="beta")]
+    state = {"y": y, "X": X, "W": W, "beta": np.zeros((p, 1)), "mu": mu_true + 0.5 * rng.standard_normal((n_cat, 1)),
+             "tau": 1.0 + rng.random((n_cat, 1)), "z": rng.integers(0, n_cat, size=(p, 1)), "prob": prob,
+             "a_tau": 2.0 * np.ones((n_cat, 1)), "b_tau": 0.5 + rng.random((n_cat, 1)),
+             "m0": np.zeros((n_cat, 1)), "P_mu": sparse.identity(n_cat, format="csc"), "lam0": 0.1}
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    with Streams(seed + 1) as s:
+        M = _run_ref(state, samplers, mdl, n_iter)
+    z_all = s.stack("z")                               # NormalNormal(beta) [p], then NormalNormal(mu) [n_cat] per sweep
+    zb = np.array([r for r in s.log["z"] if r.size == p]) if p != n_cat else None
+    zm = np.array([r for r in s.log["z"] if r.size == n_cat]) if sample_mean else np.zeros((0, n_cat))
+    out = {"X": X, "y": y, "w": np.asarray(W.diagonal()), "prob": prob, "sample_mean": sample_mean,
+           "beta0": state0["beta"], "mu0": state0["mu"], "tau0": state0["tau"], "z0": state0["z"].astype(float),
+           "a_tau": state0["a_tau"], "b_tau": state0["b_tau"], "lam0": 0.1,
+           "z_beta": zb, "z_mu": zm, "g": s.stack("g").reshape(n_iter, n_cat), "u": s.stack("u").reshape(n_iter, p),
+           "store_beta": M.store["beta"], "store_tau": M.store["tau"], "store_z": M.store["z"].astype(float),
+           "store_log_post": M.store["log_post"]}
+    if sample_mean:
+        out["store_mu"] = M.store["mu"]
+    del z_all
+    return out
+
+
+def mixture_cases():
+    return {
+        "mixture_n80_p12_k3": mixture_case(80, 12, 3, 31, 6, sample_mean=False),
+        "mixture_n60_p20_k4_rowprob": mixture_case(60, 20, 4, 32, 5, sample_mean=False, prob_rows=20),
+    }
+
+
 # ----------------------------------------------------------------------------------------------- temporal GMRF (C3 shape)
 def gmrf_case(n, seed, n_iter, form="notebook", irregular=False, weighted=False, nonzero_mu=False,
               order=("b", "lambda", "tau")):
@@ -544,13 +599,15 @@ def main():
                                                         trunc=(None, np.array([[0.25]]))),
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "gmrf", "rj"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
         cases.update(mh_cases())
     if "mh_f4" in which:
         cases.update(mh_f4_cases())
+    if "mixture" in which:
+        cases.update(mixture_cases())
     if "gmrf" in which:
         cases.update(gmrf_cases())
     if "rj" in which:

@@ -70,6 +70,27 @@ def test_truncated_regression_chain_replay(name):
         np.testing.assert_allclose(state["lambda"], g["store_lambda"][0, it], rtol=1e-10)
 
 
+@pytest.mark.parametrize("name", sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "mixture_*.npz"))))
+def test_mixture_chain_replay(name):
+    """NormalNormal with a mixture prior, the NormalGamma K-loop and MixtureAllocation replay the reference
+    chain (sampler.py:154-207, 272-288, 292-355) with its norm / gamma / uniform draws injected."""
+    g = _load(name)
+    X, y, w, prob = g["X"], g["y"], g["w"], g["prob"]
+    n = X.shape[0]
+    s = {"beta": g["beta0"], "mu": g["mu0"], "tau": g["tau0"], "z": g["z0"]}
+    for it in range(g["store_beta"].shape[1]):
+        s = conjugate.gibbs_mixture_sweep(X, y, w, s, prob, g["a_tau"], g["b_tau"], g["z_beta"][it], g["g"][it], g["u"][it])
+        np.testing.assert_allclose(s["beta"].ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(np.ravel(s["tau"]), g["store_tau"][:, it], rtol=1e-10)
+        np.testing.assert_array_equal(np.ravel(s["z"]), g["store_z"][:, it])
+        _, _, rss, _ = conjugate.regression_suffstats(X, y, w, s["beta"])
+        lp = (dist.normal_log_p_from_ss(n, 1.0, float(np.sum(np.log(w))), rss)
+              + conjugate.mixture_normal_log_p(s["beta"], s["mu"], s["tau"], s["z"])
+              + dist.gamma_log_p(np.ravel(s["tau"]), np.ravel(g["a_tau"]), np.ravel(g["b_tau"]))
+              + conjugate.categorical_log_p(s["z"], prob))
+        np.testing.assert_allclose(lp, g["store_log_post"][it, 0], rtol=1e-10)
+
+
 def test_truncnorm_restatement_matches_scipy():
     """oracle.gmrf truncated-normal helpers == scipy.stats.truncnorm (what gmrf.py:269-318 calls)."""
     from scipy import stats
