@@ -482,6 +482,7 @@ def run_b200(args, wl, key):
         e2e = {"value": C * world * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": M2.timing["h2d_bytes"] / args.steps,
                "d2h_bytes_per_step": M2.timing["d2h_bytes"] / args.steps, "seconds": dt,
+               "phases_s": {k: round(M2.timing[k], 4) for k in ("prepare_s", "sweeps_s", "collect_s") if k in M2.timing},
                "note": "MCMC(...).run_mcmc() with pinned host inputs: upload + plan compile + graph capture + "
                        f"{args.steps} sweeps + download of all stored samples"}
 

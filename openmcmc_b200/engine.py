@@ -113,7 +113,7 @@ class DeviceState:
         if not a.flags.writeable:
             a = a.copy()
         self.h2d_bytes += a.nbytes
-        return torch.from_numpy(a).to(self.device, non_blocking=False)
+        return K.upload(a, self.device)
 
     def put(self, name, value, per_chain=None, as_matrix=False):
         """Upload one entry.  2-D host arrays are shared by all chains unless per_chain=True (then replicated);
@@ -191,7 +191,7 @@ class DeviceState:
         a = self.arrays[name]
         if a.data is None:
             return sparse.identity(a.rows, format="csc")
-        h = a.data.cpu().numpy()
+        h = K.download(a.data)
         if a.per_chain and self.n_chains == 1:
             h = h[0]
         return h

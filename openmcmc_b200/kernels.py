@@ -6,6 +6,8 @@ kernels.  Tensors are float64 CUDA tensors; per-chain operands have a leading ch
 
 import ctypes as C
 
+import numpy as np
+
 import torch
 
 from openmcmc_b200 import _cabi
@@ -33,6 +35,84 @@ def init_device(device=None) -> int:
 
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ----------------------------------------------------------------------------- host <-> device staging
+# Pageable transfers through the driver run at ~2 GB/s on the B200 boxes and pinning a fresh multi-GB buffer costs as
+# much (tools/microbench/d2h_paths.py); two persistent pinned buffers and a copy pipeline reach 15-20 GB/s into / out of
+# ordinary numpy arrays.  Host plumbing only: bytes are moved, never computed on.
+_STAGE_BYTES = 64 << 20
+_stage = {}
+
+
+def _staging(dev):
+    if dev not in _stage:
+        _stage[dev] = ([torch.empty(_STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+                       [torch.cuda.Event(), torch.cuda.Event()])
+    return _stage[dev]
+
+
+def download(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> new numpy array (same shape / dtype), staged through the pinned buffers on the current stream."""
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=np.float64 if t.dtype == torch.float64 else
+                   {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8}[t.dtype])
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return out
+    src = t.view(-1).view(torch.uint8)
+    dst = torch.from_numpy(out.reshape(-1)).view(torch.uint8)
+    if nbytes <= (1 << 20):
+        dst.copy_(src)           # small: one synchronous copy
+        return out
+    bufs, evs = _staging(t.device.index)
+    pending = []
+    k = 0
+    for off in range(0, nbytes, _STAGE_BYTES):
+        if len(pending) == 2:
+            po, pb, cnt = pending.pop(0)
+            evs[pb].synchronize()
+            dst[po:po + cnt].copy_(bufs[pb][:cnt])
+        b = k & 1
+        cnt = min(_STAGE_BYTES, nbytes - off)
+        bufs[b][:cnt].copy_(src[off:off + cnt], non_blocking=True)
+        evs[b].record()
+        pending.append((off, b, cnt))
+        k += 1
+    for po, pb, cnt in pending:
+        evs[pb].synchronize()
+        dst[po:po + cnt].copy_(bufs[pb][:cnt])
+    return out
+
+
+def upload(a: np.ndarray, device) -> torch.Tensor:
+    """numpy array -> new device tensor through the pinned staging buffers (pinned torch tensors should be passed to
+    the engine directly: they go over in one asynchronous copy)."""
+    a = np.ascontiguousarray(a)
+    out = torch.empty(a.shape, dtype=torch.from_numpy(a.reshape(-1)[:1]).dtype if a.size else torch.float64, device=device)
+    nbytes = a.nbytes
+    if nbytes <= (4 << 20):
+        if nbytes:
+            out.copy_(torch.from_numpy(a))
+        return out
+    if not a.flags.writeable:
+        a = a.copy()
+    src = torch.from_numpy(a.reshape(-1)).view(torch.uint8)
+    dst = out.view(-1).view(torch.uint8)
+    bufs, evs = _staging(out.device.index)
+    k = 0
+    for off in range(0, nbytes, _STAGE_BYTES):
+        b = k & 1
+        if k >= 2:
+            evs[b].synchronize()          # the device copy that last read this buffer has finished
+        cnt = min(_STAGE_BYTES, nbytes - off)
+        bufs[b][:cnt].copy_(src[off:off + cnt])
+        dst[off:off + cnt].copy_(bufs[b][:cnt], non_blocking=True)
+        evs[b].record()
+        k += 1
+    evs[0].synchronize()
+    evs[1].synchronize()
+    return out
 
 
 def _ptr(t):

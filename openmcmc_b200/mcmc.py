@@ -195,18 +195,18 @@ class MCMC:
                 owner.setdefault(name, s)
         for name in self._store_names:
             s = owner[name]
-            buf = self._dev_store[name][: self.n_iter].cpu().numpy()          # [n_iter, C, size]
+            buf = K.download(self._dev_store[name][: self.n_iter])             # [n_iter, C, size]
             d2h += buf.nbytes
             arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
             if name == s.param:
                 arr = self._shape_store(s, arr, st[name])
             self.store[name] = arr[0] if C == 1 else arr
         self._mask_padded_store()
-        lp = self._dev_logpost[: self.n_iter].cpu().numpy()
+        lp = K.download(self._dev_logpost[: self.n_iter])
         d2h += lp.nbytes
         self.store["log_post"] = lp.reshape(self.n_iter, 1) if C == 1 else lp
         for response, buf in self._dev_fitted.items():
-            h = buf[: self.n_iter].cpu().numpy()
+            h = K.download(buf[: self.n_iter])
             d2h += h.nbytes
             arr = np.transpose(h, (1, 2, 0))
             self.store[response] = arr[0] if C == 1 else arr
@@ -271,9 +271,17 @@ class MCMC:
 
     def run_mcmc(self):
         """ref: mcmc.py:87-115"""
+        import time
+
+        t0 = time.perf_counter()
         self.prepare()
+        t1 = time.perf_counter()
         self.run_device()
+        self.stream.synchronize()
+        t2 = time.perf_counter()
         self.collect()
+        t3 = time.perf_counter()
+        self.timing.update({"prepare_s": t1 - t0, "sweeps_s": t2 - t1, "collect_s": t3 - t2})
         if np.any(self.status & 1):
             bad = int(np.sum((self.status & 1) != 0))
             if self.n_chains == 1:
