@@ -317,6 +317,39 @@ __global__ void __launch_bounds__(MH_WARPS * 32) mh_grad_hess_kernel(omc_mh_mode
 }
 
 // ---------------------------------------------------------------------------------------------- random walk
+// Contribution of element e (value x) to a term that is a SUM over elements (Poisson / Gamma / Uniform / Normal with an
+// identity or diagonal precision), up to constants that do not depend on x.  Used by the column-parallel
+// RandomWalkLoop: for such models the accept ratio of a column step involves only that column's elements.
+__device__ __forceinline__ bool term_is_separable(const omc_term_t& t) {
+  return t.kind == OMC_TERM_POISSON_RATE || t.kind == OMC_TERM_GAMMA_RESPONSE || t.kind == OMC_TERM_UNIFORM_RESPONSE ||
+         (t.kind == OMC_TERM_NORMAL_RESPONSE && t.mat_kind != OMC_MAT_DENSE);
+}
+__device__ double term_logp_elem(const omc_term_t& t, int n, int chain, int e, double x) {
+  switch (t.kind) {
+    case OMC_TERM_POISSON_RATE: {
+      const double k = vat(t.data, chain, e, 0.0);
+      double lp = omc_xlogy(k, x) - lgamma(k + 1.0) - x;
+      if (!(x >= 0.0)) lp = nan("");
+      else if (!(k >= 0.0) || floor(k) != k) lp = -INFINITY;
+      return lp;
+    }
+    case OMC_TERM_GAMMA_RESPONSE: {
+      const double sh = vat(t.p1, chain, t.p1_len > 1 ? e : 0, 1.0), rt = vat(t.p2, chain, t.p2_len > 1 ? e : 0, 1.0);
+      const double scale = 1.0 / rt, y = x / scale;
+      double lp = omc_xlogy(sh - 1.0, y) - y - lgamma(sh) - log(scale);
+      if (!(y >= 0.0)) lp = isnan(y) ? y : -INFINITY;
+      return lp;
+    }
+    case OMC_TERM_NORMAL_RESPONSE: {
+      if (x < t.dom_lo || x > t.dom_hi) return -INFINITY;
+      const double r = x - vat(t.p1, chain, t.p1_len > 1 ? e : 0, 0.0);
+      return -0.5 * vat(t.scalar, chain, 0, 1.0) * mat_at(t.mat_kind, t.P, chain, n, e, e) * r * r;
+    }
+    default:
+      return 0.0;   // Uniform: constant
+  }
+}
+
 __global__ void __launch_bounds__(MH_WARPS * 32) random_walk_kernel(omc_random_walk_t a) {
   extern __shared__ double sm[];
   const omc_mh_model_t& m = a.model;
@@ -337,6 +370,85 @@ __global__ void __launch_bounds__(MH_WARPS * 32) random_walk_kernel(omc_random_w
   const double* du = a.debug_u ? a.debug_u + sw * a.debug_sweep_stride_u + (long long)chain * n_steps : nullptr;
   double logp_cur = model_logp_warp(m, chain, cur);
   long long n_acc = 0;
+  bool separable = a.loop != 0;
+  for (int k = 0; k < m.n_terms; ++k) separable = separable && term_is_separable(m.terms[k]);
+  if (separable) {
+    // ---- column-parallel RandomWalkLoop: every term is a sum over elements, so the MH step of column `stp` reads and
+    //      writes that column only and log_accept = sum_rows [lp(new) - lp(old)] + lq_rev - lq_fwd; the n_rep steps are
+    //      independent and run one per lane, with the very random numbers (Philox block indices) of the sequential
+    //      loop.  The running total the sequential loop carries (logp_cur) is rebuilt by a prefix sum for the probes.
+    for (int stp0 = 0; stp0 < n_steps; stp0 += 32) {
+      const int stp = stp0 + lane;
+      const bool live = stp < n_steps;
+      double lq_fwd = 0.0, lq_rev = 0.0, dlp = 0.0;
+      if (live) {
+        for (int q = 0; q < p_prop; ++q) {
+          const int row = q, col = stp, e = row * a.n_rep + col;
+          const double stepv = vat(a.step, chain, (a.step_rows > 1 ? row : 0) * (a.step_cols > 1 ? a.n_rep : 1) +
+                                                      (a.step_cols > 1 ? col : 0), 0.2);
+          double var;
+          if (dz) var = dz[(long long)stp * p_prop + q];
+          else {
+            uint4 b = omc_rng_block(rng, chain, stp * blocks_per_step + (unsigned)(q >> 1));
+            if (a.limits) var = (q & 1) ? omc_u01(b.z, b.w) : omc_u01(b.x, b.y);
+            else {
+              double z0, z1;
+              omc_normal2(rng, chain, stp * blocks_per_step + (unsigned)(q >> 1), z0, z1);
+              var = (q & 1) ? z1 : z0;
+            }
+          }
+          const double mu = cur[e];
+          double z;
+          if (a.limits) {
+            const double lb = a.limits[2 * row], ub = a.limits[2 * row + 1];
+            z = omc_truncated_normal_rv(mu, stepv, lb, ub, var);
+            lq_fwd += omc_truncated_normal_log_pdf(z, mu, stepv, lb, ub);
+            lq_rev += omc_truncated_normal_log_pdf(mu, z, stepv, lb, ub);
+          } else {
+            z = mu + stepv * var;
+          }
+          prop[e] = z;
+          for (int k = 0; k < m.n_terms; ++k)
+            dlp += term_logp_elem(m.terms[k], n, chain, e, z) - term_logp_elem(m.terms[k], n, chain, e, mu);
+        }
+      }
+      double u = 0.5;
+      if (live) {
+        if (du) u = du[stp];
+        else {
+          uint4 b = omc_rng_block(rng, chain, stp * blocks_per_step + blocks_per_step - 1);
+          u = omc_u01(b.x, b.y);
+        }
+      }
+      const double log_accept = dlp + lq_rev - lq_fwd;
+      const bool accept = live && (log(u) < log_accept);
+      // running total before this lane's step = logp_cur + accepted increments of the lower lanes
+      double inc = accept ? dlp : 0.0, pre = inc;
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += o;
+      }
+      const double before = logp_cur + (pre - inc);
+      if (a.probe && live) {
+        double* pr = a.probe + ((long long)chain * n_steps + stp) * 5;
+        pr[0] = before; pr[1] = before + dlp; pr[2] = lq_fwd; pr[3] = lq_rev; pr[4] = accept ? 1.0 : 0.0;
+      }
+      if (live)
+        for (int q = 0; q < p_prop; ++q) {
+          const int e = q * a.n_rep + stp;
+          if (accept) cur[e] = prop[e];
+        }
+      logp_cur += __shfl_sync(0xffffffffu, pre, 31);
+      n_acc += __popc(__ballot_sync(0xffffffffu, accept));
+      __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) gth[i] = cur[i];
+    if (a.counters && lane == 0) {
+      a.counters[2 * (long long)chain] += n_acc;
+      a.counters[2 * (long long)chain + 1] += n_steps;
+    }
+    return;
+  }
   for (int stp = 0; stp < n_steps; ++stp) {
     // ---- proposal for the elements of this step: element e = i*n_rep + col (loop) or e = q (joint)
     double lq_fwd = 0.0, lq_rev = 0.0;
@@ -538,6 +650,114 @@ __global__ void __launch_bounds__(MM_THREADS) mmala_kernel(omc_mmala_t a) {
   }
 }
 
+// ---- warp-per-chain ManifoldMALA (n_elem <= 32): the whole step of mmala_kernel by one warp, MW_WARPS chains per CTA.
+// The CTA-per-chain kernel above spends its time in __syncthreads around a 32 x 32 Cholesky that three of its four warps
+// barely take part in; here nothing synchronises beyond a warp, and 4-5x as many chains are resident per SM.  Same
+// operation order per element => same numbers as mmala_kernel.
+constexpr int MW_WARPS = 4;
+
+__device__ bool mmala_params_warp(const omc_mmala_t& a, int chain, const double* th, double* Hm, int ld, double* g,
+                                  double* mu, double* scratch) {
+  const int n = a.model.n_elem, lane = threadIdx.x & 31;
+  model_grad_hess_warp(a.model, chain, th, a.method, g, Hm, ld, scratch);
+  __syncwarp();
+  const double inv_s2 = 1.0 / (a.step * a.step);
+  bool bad = false;
+  for (int e = lane; e < n * n; e += 32) {
+    const double v = Hm[(e / n) * ld + (e % n)] * inv_s2;
+    Hm[(e / n) * ld + (e % n)] = v;
+    if (isnan(v) || isinf(v)) bad = true;
+  }
+  for (int i = lane; i < n; i += 32)
+    if (isnan(g[i]) || isinf(g[i])) bad = true;
+  __syncwarp();
+  if (__any_sync(0xffffffffu, bad)) return false;
+  if (!omc_chol_warp(Hm, n, ld)) return false;
+  __syncwarp();
+  double x0 = (lane < n) ? g[lane] : 0.0, x1 = 0.0;
+  omc_warp_solve_lower(Hm, n, ld, x0, x1);
+  omc_warp_solve_lower_T(Hm, n, ld, x0, x1);
+  if (lane < n) mu[lane] = th[lane] + 0.5 * x0;
+  __syncwarp();
+  return true;
+}
+
+__global__ void __launch_bounds__(MW_WARPS * 32) mmala_warp_kernel(omc_mmala_t a) {
+  extern __shared__ double sm[];
+  const int n = a.model.n_elem, ld = n + 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * MW_WARPS + warp;
+  if (chain >= a.model.n_chains) return;
+  double* Hm = sm + (size_t)warp * (n * ld + 8 * n);   // n x ld
+  double* cur = Hm + n * ld;
+  double* prop = cur + n;
+  double* g = prop + n;
+  double* mu = g + n;
+  double* zv = mu + n;
+  double* scratch = zv + n;     // 3n
+  double* gth = a.theta + (long long)chain * n;
+  if (lane < n) cur[lane] = gth[lane];
+  __syncwarp();
+  const long long sw = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+  const OmcRng rng = to_rng(a.rng);
+  int status = 0;
+  double lpc = 0.0, lpp = 0.0, lq = 0.0, lqr = 0.0;
+  bool ok = mmala_params_warp(a, chain, cur, Hm, ld, g, mu, scratch);
+  if (!ok) status |= OMC_STATUS_NOT_PD;
+  if (ok) {
+    if (a.debug_z) {
+      const double* dz = a.debug_z + sw * a.debug_sweep_stride_z + (long long)chain * n;
+      if (lane < n) zv[lane] = dz[lane];
+    } else if (2 * lane < n) {
+      double z0, z1;
+      omc_normal2(rng, chain, lane, z0, z1);
+      zv[2 * lane] = z0;
+      if (2 * lane + 1 < n) zv[2 * lane + 1] = z1;
+    }
+    __syncwarp();
+    double x0 = (lane < n) ? zv[lane] : 0.0, x1 = 0.0;
+    omc_warp_solve_lower_T(Hm, n, ld, x0, x1);
+    if (lane < n) prop[lane] = x0 + mu[lane];
+    __syncwarp();
+    lq = mmala_log_density_warp(Hm, n, ld, prop, mu);
+    lpc = model_logp_warp(a.model, chain, cur);
+    lpp = model_logp_warp(a.model, chain, prop);
+    if (a.probe_mu && lane < n) a.probe_mu[(long long)chain * n + lane] = mu[lane];
+    if (a.probe_prop && lane < n) a.probe_prop[(long long)chain * n + lane] = prop[lane];
+    if (a.probe_L)
+      for (int e = lane; e < n * n; e += 32)
+        a.probe_L[(long long)chain * n * n + e] = ((e % n) <= (e / n)) ? Hm[(e / n) * ld + (e % n)] : 0.0;
+    __syncwarp();
+    const bool ok2 = mmala_params_warp(a, chain, prop, Hm, ld, g, mu, scratch);
+    if (!ok2) { status |= OMC_STATUS_OUT_OF_SUPPORT; ok = false; }
+    else lqr = mmala_log_density_warp(Hm, n, ld, cur, mu);
+  }
+  bool accept = false;
+  double log_accept = nan("");
+  if (ok) {
+    double u;
+    if (a.debug_u) u = a.debug_u[sw * a.debug_sweep_stride_u + chain];
+    else {
+      uint4 b = omc_rng_block(rng, chain, 0xFFFFu);
+      u = omc_u01(b.x, b.y);
+    }
+    log_accept = lpp + lqr - (lpc + lq);
+    accept = log(u) < log_accept;
+    if (isnan(log_accept)) status |= isnan(lpc) ? OMC_STATUS_NAN : OMC_STATUS_OUT_OF_SUPPORT;
+  }
+  if (accept && lane < n) gth[lane] = prop[lane];
+  if (lane == 0) {
+    if (a.counters) {
+      a.counters[2 * (long long)chain] += accept ? 1 : 0;
+      a.counters[2 * (long long)chain + 1] += 1;
+    }
+    if (a.status && status) atomicOr(&a.status[chain], status);
+    if (a.probe_scalars) {
+      double* ps = a.probe_scalars + (long long)chain * 6;
+      ps[0] = lpc; ps[1] = lpp; ps[2] = lq; ps[3] = lqr; ps[4] = log_accept; ps[5] = accept ? 1.0 : 0.0;
+    }
+  }
+}
+
 __global__ void truncnorm_rv_kernel(const double* mean, const double* scale, const double* lower, const double* upper,
                                     const double* u, long long n, double* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -617,6 +837,13 @@ int omc_mmala(const omc_mmala_t* a, void* stream) {
   OMC_REQUIRE(n <= 64, "omc_mmala: n_elem=%d > 64 is not supported", n);
   OMC_REQUIRE(a->step > 0.0, "omc_mmala: step=%g", a->step);
   const size_t smem = (size_t)(n * (n + 1) + 8 * n) * sizeof(double);
+  if (n <= 32) {   // one warp per chain
+    const size_t smem_w = smem * MW_WARPS;
+    OMC_CHECK_CUDA(cudaFuncSetAttribute(mmala_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    mmala_warp_kernel<<<(a->model.n_chains + MW_WARPS - 1) / MW_WARPS, MW_WARPS * 32, smem_w, (cudaStream_t)stream>>>(*a);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
   mmala_kernel<<<a->model.n_chains, MM_THREADS, smem, (cudaStream_t)stream>>>(*a);
   OMC_LAUNCH_CHECK();
   return 0;

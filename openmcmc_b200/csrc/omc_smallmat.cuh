@@ -27,6 +27,29 @@ __device__ __forceinline__ bool omc_chol_block(double* Q, int p, int ld) {
   return true;
 }
 
+// The same factorisation by ONE warp (no CTA barriers): lane c owns column c (and c + 32) of the trailing update.  Every
+// element sees the same operations in the same order as in omc_chol_block, so the factors are bit-identical.
+__device__ __forceinline__ bool omc_chol_warp(double* Q, int p, int ld) {
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < p; ++j) {
+    const double djj = Q[j * ld + j];
+    if (!(djj > 0.0)) return false;
+    const double d = sqrt(djj);
+    __syncwarp();
+    for (int i = j + lane; i < p; i += 32) {
+      if (i == j) Q[j * ld + j] = d;
+      else Q[i * ld + j] = Q[i * ld + j] / d;
+    }
+    __syncwarp();
+    for (int c = j + 1 + lane; c < p; c += 32) {
+      const double lcj = Q[c * ld + j];
+      for (int i = c; i < p; ++i) Q[i * ld + c] -= Q[i * ld + j] * lcj;
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
 // One warp solves L w = b (forward) in registers: lane owns rows lane and lane+32; x0/x1 in/out.
 __device__ __forceinline__ void omc_warp_solve_lower(const double* L, int p, int ld, double& x0, double& x1) {
   const int lane = threadIdx.x & 31;
