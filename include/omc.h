@@ -230,6 +230,8 @@ typedef struct {
   omc_vec_t theta[4];  /* [p_t]               */
   double* out;         /* [n_chains][n]       */
   int transform_exp[4]; /* term t uses exp(theta_t) (ref: parameter.py:232-297 LinearCombinationWithTransform) */
+  omc_vec_t residual_of; /* optional [n]: out = residual_of - yhat, i.e. y - predictor_conditional(exclude) of
+                            NormalNormal.sample for a mean with several terms (ref: sampler.py:188-192)          */
 } omc_linear_predictor_t;
 int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
 

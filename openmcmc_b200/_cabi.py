@@ -141,7 +141,7 @@ class LinearPredictor(C.Structure):
     """omc_linear_predictor_t"""
 
     _fields_ = [("n_chains", C.c_int), ("n", C.c_int), ("n_terms", C.c_int), ("p", C.c_int * 4), ("X", Vec * 4),
-                ("theta", Vec * 4), ("out", C.c_void_p), ("transform_exp", C.c_int * 4)]
+                ("theta", Vec * 4), ("out", C.c_void_p), ("transform_exp", C.c_int * 4), ("residual_of", Vec)]
 
 
 class Term(C.Structure):

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(LP_THREADS) linear_predictor_kernel(omc_linear
       }
     }
     acc = omc_warp_sum(acc);
-    if (lane == 0) a.out[row] = acc;
+    if (lane == 0)
+      a.out[row] = a.residual_of.ptr ? a.residual_of.ptr[(long long)c * a.residual_of.chain_stride + r] - acc : acc;
   }
 }
 __global__ void __launch_bounds__(LP_THREADS) sum_log_kernel(const double* x, long long n, double* out) {

@@ -330,11 +330,21 @@ class RegressionLikelihood:
         self.param = param
         self.data_only = data_only
         form = dist.mean.form
-        if list(form.keys()) != [param]:
-            raise PlanError("LinearCombination means with more than one term are not supported by the device path yet")
+        if param not in form:
+            raise PlanError(f"'{param}' is not a term of the mean of '{dist.response}'")
+        # other terms of the mean: the pass runs on y - predictor_conditional(exclude param) (sampler.py:188-192)
+        self.others = [(st[pref], st[prm], bool((getattr(dist.mean, "transform", None) or {}).get(prm, False)), prm, pref)
+                       for prm, pref in form.items() if prm != param]
+        if len(self.others) > 4:
+            raise PlanError("LinearCombination means with more than 5 terms are not supported by the device path")
+        if data_only and self.others:
+            raise PlanError("MH through a linear Normal mean supports a single-term LinearCombination")
         self.X = st[form[param]]
         self.y = st[dist.response]
         self.beta = st[param]
+        for Xo, tho, _, prm, _ in self.others:
+            if Xo.kind != "dense" or tho.cols != 1 or Xo.rows != self.X.rows:
+                raise PlanError(f"unsupported term '{prm}' in the mean of '{dist.response}'")
         if self.y.cols != 1 or self.beta.cols != 1:
             raise PlanError("replicated responses (n_rep > 1) are not supported by the regression device path yet")
         self.n, self.p = self.X.rows, self.X.cols
@@ -350,8 +360,10 @@ class RegressionLikelihood:
         self.stats = plan.new(C, self.rec, fill=0.0)
         ns, ws = K.reg_pass_workspace(C, self.n, self.p)
         self.work = plan.new(max(ws, 1))
-        deps_data = frozenset({form[param], dist.response, mname})
-        tag = "data:" if data_only else ""
+        self.y_eff = plan.new(C, self.n) if self.others else None
+        deps_other = frozenset(x for _, _, _, prm, pref in self.others for x in (prm, pref))
+        deps_data = frozenset({form[param], dist.response, mname}) | deps_other
+        tag = ("data:" if data_only else "") + (f"{param}|" if self.others else "")
         self.q_gg = f"gram[{tag}{dist.response}]"
         self.q_rss = f"rss[{tag}{dist.response}]"
         plan.add_quantity(Quantity(self.q_gg, deps_data, self._emit_pass, (self.q_rss,)))
@@ -363,8 +375,15 @@ class RegressionLikelihood:
         X, y, W, beta, stats, work = self.X, self.y, self.W, self.beta, self.stats, self.work
         w = W.data if W.kind == "diag" else None
         beta_data = None if self.data_only else beta.data
+        others, y_eff = self.others, self.y_eff
 
         def launch():
+            if others:
+                K.linear_predictor(C, n, [(Xo.vec(), tho.vec(), Xo.cols, tr) for Xo, tho, tr, _, _ in others], y_eff,
+                                   residual_of=y.vec())
+                K.reg_pass(X.data, y_eff, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain, y_shared=False,
+                           w_shared=True)
+                return
             K.reg_pass(X.data, y.data, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain,
                        y_shared=not y.per_chain, w_shared=True)
 
@@ -488,6 +507,8 @@ def as_chain_tensor(value, n_chains, size, device):
 def get_regression(plan: Plan, host_state, lik, param, data_only=False) -> RegressionLikelihood:
     cache = plan.__dict__.setdefault("_regressions", {})
     key = (lik.response, data_only) if data_only else lik.response
+    if isinstance(lik.mean, LinearCombination) and len(lik.mean.form) > 1:
+        key = (lik.response, param, data_only)      # one record per term of a multi-term mean
     if key not in cache:
         cache[key] = RegressionLikelihood(plan, host_state, lik, param, data_only=data_only)
     return cache[key]

@@ -258,9 +258,11 @@ def logp_const(value, n_chains, out, accumulate):
     check(lib().omc_logp_const(float(value), n_chains, _ptr(out), int(accumulate), stream_ptr()), "omc_logp_const")
 
 
-def linear_predictor(n_chains, n, terms, out):
-    """terms: list of (X_vec, theta_vec, p[, transform_exp])."""
+def linear_predictor(n_chains, n, terms, out, residual_of=None):
+    """terms: list of (X_vec, theta_vec, p[, transform_exp]); residual_of (omc_vec_t): out = residual_of - yhat."""
     a = _cabi.LinearPredictor()
+    if residual_of is not None:
+        a.residual_of = residual_of
     a.n_chains, a.n, a.n_terms = n_chains, n, len(terms)
     for i, (xv, tv, p, *rest) in enumerate(terms):
         a.p[i] = p

@@ -142,6 +142,38 @@ def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "l
     return out
 
 
+def regression_two_term_case(n, p, q, seed, n_iter):
+    """Mean with two terms, y ~ N(X beta + Z gamma, (tau W)^-1): each NormalNormal works on y minus the other term
+    (predictor_conditional(term_to_exclude), sampler.py:188-192); NormalGamma(tau) sees the full residual."""
+    rng = np.random.default_rng(seed)
+    X, Z = rng.standard_normal((n, p)), rng.standard_normal((n, q))
+    y = X @ rng.standard_normal((p, 1)) + Z @ (0.5 * rng.standard_normal((q, 1))) + 0.3 * rng.standard_normal((n, 1))
+    W = sparse.diags(rng.random(n) + 0.5, format="csc")
+    A = rng.standard_normal((p, p))
+    P_b = A @ A.T / p + np.eye(p)
+    mdl = Model(
+        [Normal("y", mean=LinearCombination(form={"beta": "X", "gamma": "Z"}), precision=ScaledMatrix(matrix="W", scalar="tau")),
+         Normal("beta", mean="mu_b", precision=ScaledMatrix(matrix="P_b", scalar="lam_b")),
+         Normal("gamma", mean="mu_g", precision=ScaledMatrix(matrix="P_g", scalar="lam_g")),
+         Gamma("tau", shape="a_tau", rate="b_tau"),
+         Gamma("lam_b", shape="a_lam", rate="b_lam")],
+        response={"y": "mean"},
+    )
+    samplers = [NormalNormal("beta", mdl), NormalNormal("gamma", mdl), NormalGamma("tau", mdl), NormalGamma("lam_b", mdl)]
+    state = {"y": y, "X": X, "Z": Z, "W": W, "beta": np.zeros((p, 1)), "gamma": np.zeros((q, 1)), "tau": 1.0,
+             "mu_b": 0.1 * rng.standard_normal((p, 1)), "P_b": P_b, "lam_b": 0.5, "mu_g": np.zeros((q, 1)),
+             "P_g": sparse.identity(q, format="csc"), "lam_g": 2.0, "a_tau": 1e-3, "b_tau": 1e-3, "a_lam": 1.0, "b_lam": 1.0}
+    mu_b = state["mu_b"].copy()
+    with Streams(seed + 1) as s:
+        M = _run_ref(state, samplers, mdl, n_iter)
+    zs = s.log["z"]
+    g = s.stack("g")
+    return {"X": X, "Z": Z, "y": y, "w": np.asarray(W.diagonal()), "P_b": P_b, "mu_b": mu_b, "lam_g": 2.0,
+            "z_beta": np.array(zs[0::2]), "z_gamma": np.array(zs[1::2]), "g_tau": g[0::2, 0], "g_lam": g[1::2, 0],
+            "store_beta": M.store["beta"], "store_gamma": M.store["gamma"], "store_tau": M.store["tau"],
+            "store_lam_b": M.store["lam_b"], "store_log_post": M.store["log_post"], "store_y": M.store["y"]}
+
+
 # ----------------------------------------------------------------------------------------------- Metropolis-Hastings (C4 shape)
 def _run_ref(state, samplers, mdl, n_iter):
     import openmcmc.mcmc as m
@@ -598,6 +630,7 @@ def main():
         "truncreg_n80_p40_upper_dense": regression_case(80, 40, 5, 3, prior="dense", weighted=True,
                                                         trunc=(None, np.array([[0.25]]))),
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
+        "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
     which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj"]
     if "regression" not in which:

@@ -122,6 +122,44 @@ def test_truncated_free_running_stays_inside_and_matches_oracle_chain():
     assert np.all(np.abs(gpu_mean - cpu_mean) < 0.15 * sd + 5e-3), (gpu_mean, cpu_mean, sd)
 
 
+def test_mcmc_replays_two_term_mean_chain():
+    """y ~ N(X beta + Z gamma, .): every NormalNormal runs the fused pass on y minus the other term's predictor
+    (omc_linear_predictor(residual_of=y), sampler.py:188-192); fitted values and log_post use both terms."""
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    g = dict(np.load(os.path.join(GOLD, "twoterm_n150_p7_q4.npz")))
+    n, p, q = g["X"].shape[0], g["X"].shape[1], g["Z"].shape[1]
+    mdl = Model(
+        [Normal("y", mean=LinearCombination(form={"beta": "X", "gamma": "Z"}), precision=ScaledMatrix(matrix="W", scalar="tau")),
+         Normal("beta", mean="mu_b", precision=ScaledMatrix(matrix="P_b", scalar="lam_b")),
+         Normal("gamma", mean="mu_g", precision=ScaledMatrix(matrix="P_g", scalar="lam_g")),
+         Gamma("tau", shape="a_tau", rate="b_tau"),
+         Gamma("lam_b", shape="a_lam", rate="b_lam")],
+        response={"y": "mean"})
+    samplers = [NormalNormal("beta", mdl), NormalNormal("gamma", mdl), NormalGamma("tau", mdl), NormalGamma("lam_b", mdl)]
+    state = {"y": g["y"], "X": g["X"], "Z": g["Z"], "W": sparse.diags(g["w"], format="csc"), "beta": np.zeros((p, 1)),
+             "gamma": np.zeros((q, 1)), "tau": 1.0, "mu_b": g["mu_b"], "P_b": g["P_b"], "lam_b": 0.5,
+             "mu_g": np.zeros((q, 1)), "P_g": sparse.identity(q, format="csc"), "lam_g": float(g["lam_g"]),
+             "a_tau": 1e-3, "b_tau": 1e-3, "a_lam": 1.0, "b_lam": 1.0}
+    dd = {"beta": {"z": g["z_beta"]}, "gamma": {"z": g["z_gamma"]}, "tau": {"g": g["g_tau"]}, "lam_b": {"g": g["g_lam"]}}
+    C = 3
+    dd_c = {k: {kk: np.repeat(np.asarray(vv)[:, None], C, axis=1) for kk, vv in v.items()} for k, v in dd.items()}
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=g["store_beta"].shape[1], n_chains=C, debug_draws=dd_c)
+    M.run_mcmc()
+    for c in range(C):
+        np.testing.assert_allclose(M.store["beta"][c], g["store_beta"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(M.store["gamma"][c], g["store_gamma"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(M.store["tau"][c], g["store_tau"], rtol=1e-9)
+        np.testing.assert_allclose(M.store["lam_b"][c], g["store_lam_b"], rtol=1e-9)
+        np.testing.assert_allclose(M.store["y"][c], g["store_y"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(M.store["log_post"][:, 0], g["store_log_post"][:, 0], rtol=1e-10)
+
+
 def test_mcmc_burn_thin_schedule_and_chains():
     """Iteration numbering (mcmc.py:97-103): (n_burn+n_iter)*n_thin sweeps; identical injected draws on every chain
     give identical chains; batched shapes (C, size, n_iter)."""

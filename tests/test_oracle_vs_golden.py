@@ -91,6 +91,29 @@ def test_mixture_chain_replay(name):
         np.testing.assert_allclose(lp, g["store_log_post"][it, 0], rtol=1e-10)
 
 
+def test_two_term_regression_chain_replay():
+    """Mean with two LinearCombination terms: each NormalNormal conditions on y minus the other term's predictor
+    (sampler.py:188-192); NormalGamma(tau) uses the full residual (sampler.py:275-276)."""
+    g = _load("twoterm_n150_p7_q4")
+    X, Z, y, w = g["X"], g["Z"], g["y"], g["w"]
+    n, p, q = X.shape[0], X.shape[1], Z.shape[1]
+    beta, gamma, tau, lam_b = np.zeros((p, 1)), np.zeros((q, 1)), 1.0, 0.5
+    for it in range(g["store_beta"].shape[1]):
+        G, gv, _, _ = conjugate.regression_suffstats(X, y - Z @ gamma, w)
+        beta = conjugate.normal_normal_dense(G, gv, tau, g["P_b"], lam_b, g["mu_b"], g["z_beta"][it])["x"]
+        G, gv, _, _ = conjugate.regression_suffstats(Z, y - X @ beta, w)
+        gamma = conjugate.normal_normal_dense(G, gv, tau, 1.0, float(g["lam_g"]), None, g["z_gamma"][it])["x"]
+        _, _, rss, cnt = conjugate.regression_suffstats(X, y - Z @ gamma, w, beta)
+        tau, _, _ = conjugate.normal_gamma(1e-3, 1e-3, rss, cnt, g["g_tau"][it])
+        ss, cnt = conjugate.quadform(g["P_b"], beta, g["mu_b"])
+        lam_b, _, _ = conjugate.normal_gamma(1.0, 1.0, ss, cnt, g["g_lam"][it])
+        np.testing.assert_allclose(beta.ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(gamma.ravel(), g["store_gamma"][:, it], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(tau, g["store_tau"][0, it], rtol=1e-10)
+        np.testing.assert_allclose(lam_b, g["store_lam_b"][0, it], rtol=1e-10)
+        np.testing.assert_allclose((X @ beta + Z @ gamma).ravel(), g["store_y"][:, it], rtol=1e-9, atol=1e-11)
+
+
 def test_truncnorm_restatement_matches_scipy():
     """oracle.gmrf truncated-normal helpers == scipy.stats.truncnorm (what gmrf.py:269-318 calls)."""
     from scipy import stats

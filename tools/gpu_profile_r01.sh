@@ -18,6 +18,16 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:reg_
   python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rj_kernel" -c 3 -s 6 -o gpurun_out/r01_rj -f \
   python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c5.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mmala_kernel|random_walk_kernel" -c 1 -s 3 -o gpurun_out/r01_mmala -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mmala|random_walk" -c 1 -s 3 -o gpurun_out/r01_mmala -f \
   python bench.py --workload c4a --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c4a.log 2>&1
-ls -la gpurun_out | tail -30
+# RandomWalkLoop (c4b) full capture as well
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"random_walk" -c 1 -s 3 -o gpurun_out/r01_rwl -f \
+  python bench.py --workload c4b --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c4b.log 2>&1
+# the reports (with sources) exceed what gpurun brings back: export the raw pages here, keep only the CSVs
+for r in gpurun_out/r01_*.ncu-rep; do
+  ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
+  rm -f $r
+done
+rm -f gpurun_out/ncu_*.log
+ls -la gpurun_out | tail -40
+du -sh gpurun_out
