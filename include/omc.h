@@ -440,6 +440,38 @@ int omc_reversible_jump(const omc_rj_t* args, void* stream);
 /* B[c][r][j] = N(X_r; theta_cj, omega_cj) for j < n_c, 0 beyond (ref: make_basis, tests/test_reversible_jump.py:23-40) */
 int omc_rj_basis(const omc_rj_t* args, void* stream);
 
+/* Companion moves of the RJ model on the same padded state (the other samplers of tests/test_reversible_jump.py:213-252).
+ * omc_rj_knot_walk: RandomWalkLoop over the knots (which = 0) or widths (which = 1): per live component one truncated-
+ *   Gaussian step on [lim_lo, lim_hi], basis column rebuilt for the proposal (the reference's state_update_function =
+ *   make_basis), accept on the full model (only the response and the moved component's prior change).
+ *   ref: metropolis_hastings.py:212-289, :127-173, :201-210; gmrf.py:269-318
+ *   debug_tn_u / debug_u: injected truncnorm.rvs / accept uniforms [n_chains][n_max] (component j at index j).
+ * omc_rj_coef_mmala: ManifoldMALA on the live coefficients: response Normal(y | B beta, (tau_y I)^-1) or Null, prior
+ *   iid N(mu_beta, 1/tau_beta).  ref: metropolis_hastings.py:292-373, location_scale.py:222-250
+ *   debug_z [n_chains][n_max], debug_u [n_chains]; probe [n_chains][6] = rss_cur, rss_prop, logq_fwd, logq_rev,
+ *   log_accept, accepted.  model.size_class (optional scratch) lets chains with few live coefficients run from a small
+ *   shared-memory footprint. */
+typedef struct {
+  omc_rj_t model;
+  int which;
+  double step, lim_lo, lim_hi;
+  const double* debug_tn_u;
+  const double* debug_u;
+  long long debug_sweep_stride;
+  long long* counters;         /* optional [n_chains][2]: accepted, proposed */
+} omc_rj_walk_t;
+int omc_rj_knot_walk(const omc_rj_walk_t* args, void* stream);
+typedef struct {
+  omc_rj_t model;
+  double step;
+  const double* debug_z;
+  const double* debug_u;
+  long long debug_sweep_stride_z, debug_sweep_stride_u;
+  long long* counters;         /* optional [n_chains][2] */
+  double* probe;               /* optional [n_chains][6] */
+} omc_rj_mmala_t;
+int omc_rj_coef_mmala(const omc_rj_mmala_t* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

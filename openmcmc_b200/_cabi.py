@@ -250,7 +250,7 @@ PROTOTYPES.update({
     "omc_chain_stats": (C.c_int, [C.POINTER(ChainStats), C.c_void_p]),
     "omc_rhat_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 })
-EXTRA_STRUCTS = {"omc_chain_stats_t": ChainStats}
+EXTRA_STRUCTS["omc_chain_stats_t"] = ChainStats
 
 
 class RJArgs(C.Structure):
@@ -272,6 +272,30 @@ PROTOTYPES.update({
     "omc_rj_basis": (C.c_int, [C.POINTER(RJArgs), C.c_void_p]),
 })
 EXTRA_STRUCTS["omc_rj_t"] = RJArgs
+
+
+class RJWalk(C.Structure):
+    """omc_rj_walk_t"""
+
+    _fields_ = [("model", RJArgs), ("which", C.c_int), ("step", C.c_double), ("lim_lo", C.c_double),
+                ("lim_hi", C.c_double), ("debug_tn_u", C.c_void_p), ("debug_u", C.c_void_p),
+                ("debug_sweep_stride", C.c_longlong), ("counters", C.c_void_p)]
+
+
+class RJMmala(C.Structure):
+    """omc_rj_mmala_t"""
+
+    _fields_ = [("model", RJArgs), ("step", C.c_double), ("debug_z", C.c_void_p), ("debug_u", C.c_void_p),
+                ("debug_sweep_stride_z", C.c_longlong), ("debug_sweep_stride_u", C.c_longlong), ("counters", C.c_void_p),
+                ("probe", C.c_void_p)]
+
+
+PROTOTYPES.update({
+    "omc_rj_knot_walk": (C.c_int, [C.POINTER(RJWalk), C.c_void_p]),
+    "omc_rj_coef_mmala": (C.c_int, [C.POINTER(RJMmala), C.c_void_p]),
+})
+EXTRA_STRUCTS["omc_rj_walk_t"] = RJWalk
+EXTRA_STRUCTS["omc_rj_mmala_t"] = RJMmala
 
 
 def lib_path() -> str:

@@ -485,3 +485,34 @@ def reversible_jump(args, logp_only=False):
 
 def rj_basis(args):
     check(lib().omc_rj_basis(C.byref(args), stream_ptr()), "omc_rj_basis")
+
+
+def rj_knot_walk(rj_args_, which, step, lim_lo, lim_hi, debug_tn_u=None, debug_u=None, debug_sweep_stride=0,
+                 counters=None, rng_=None):
+    """RandomWalkLoop over the knots (which = 0) / widths (which = 1) of the padded RJ state (omc.h)."""
+    w = _cabi.RJWalk()
+    C.memmove(C.byref(w.model), C.byref(rj_args_), C.sizeof(_cabi.RJArgs))
+    if rng_ is not None:
+        w.model.rng = rng_
+    w.which, w.step, w.lim_lo, w.lim_hi = int(which), float(step), float(lim_lo), float(lim_hi)
+    w.debug_tn_u = debug_tn_u.data_ptr() if debug_tn_u is not None else None
+    w.debug_u = debug_u.data_ptr() if debug_u is not None else None
+    w.debug_sweep_stride = int(debug_sweep_stride)
+    w.counters = counters.data_ptr() if counters is not None else None
+    check(lib().omc_rj_knot_walk(C.byref(w), stream_ptr()), "omc_rj_knot_walk")
+
+
+def rj_coef_mmala(rj_args_, step, debug_z=None, debug_u=None, stride_z=0, stride_u=0, counters=None, probe=None,
+                  rng_=None):
+    """ManifoldMALA on the live coefficients of the padded RJ state (omc.h)."""
+    m = _cabi.RJMmala()
+    C.memmove(C.byref(m.model), C.byref(rj_args_), C.sizeof(_cabi.RJArgs))
+    if rng_ is not None:
+        m.model.rng = rng_
+    m.step = float(step)
+    m.debug_z = debug_z.data_ptr() if debug_z is not None else None
+    m.debug_u = debug_u.data_ptr() if debug_u is not None else None
+    m.debug_sweep_stride_z, m.debug_sweep_stride_u = int(stride_z), int(stride_u)
+    m.counters = counters.data_ptr() if counters is not None else None
+    m.probe = probe.data_ptr() if probe is not None else None
+    check(lib().omc_rj_coef_mmala(C.byref(m), stream_ptr()), "omc_rj_coef_mmala")

@@ -75,6 +75,9 @@ class MCMC:
             from openmcmc_b200 import gmrf_plan
 
             gmrf_plan.discover(plan, self.state, list(self.model.values()))
+            rj = self._rj_sampler()
+            if rj is not None:
+                rj.setup(plan, self.state, dd.get(rj.param))
             # pass A (dry): learn which derived quantities are valid at the end of a sweep
             plan.ops = []
             for s in self.samplers:
@@ -225,7 +228,10 @@ class MCMC:
     def _rj_sampler(self):
         from openmcmc_b200.sampler.reversible_jump import ReversibleJump
 
-        return next((s for s in self.samplers if isinstance(s, ReversibleJump)), None)
+        rj = next((s for s in self.samplers if isinstance(s, ReversibleJump)), None)
+        if rj is None:   # a companion sampler of an RJ model run on its own names its RJ sampler explicitly
+            rj = next((s.rj for s in self.samplers if getattr(s, "rj", None) is not None), None)
+        return rj
 
     def _mask_padded_store(self):
         """Variable-dimension parameters are stored at capacity n_max: entries beyond the stored count become NaN, the

@@ -40,6 +40,14 @@ class MetropolisHastings(MCMCSampler):
     step: np.ndarray = field(default_factory=lambda: np.array([0.2], ndmin=2), init=True)
     accept_rate: AcceptRate = field(default_factory=lambda: AcceptRate(), init=False)
 
+    def _rj_of(self, plan):
+        """The ReversibleJump sampler whose padded state holds self.param (None when there is none)."""
+        rj = plan.__dict__.get("_rj")
+        if rj is None or rj.basis is None:
+            return None
+        names = (rj.basis.knots, rj.basis.widths, rj.matching_params["variable"])
+        return rj if self.param in names else None
+
     def _collect_accept(self, plan):
         ctx = plan.ctx(self)
         cnt = ctx.get("counters")
@@ -82,6 +90,7 @@ class RandomWalk(MetropolisHastings):
 
     domain_limits: np.ndarray = None
     state_update_function: Callable = None
+    rj: object = None      # extension: the ReversibleJump sampler of the model when this sampler runs without it
     _loop = 0
 
     def __post_init__(self):
@@ -94,6 +103,9 @@ class RandomWalk(MetropolisHastings):
         from openmcmc_b200 import devdist, engine
         from openmcmc_b200 import kernels as K
 
+        rj = self._rj_of(plan)
+        if rj is not None:
+            return self._compile_rj_walk(plan, rj, debug_draws)
         if callable(self.state_update_function):
             raise engine.PlanError("state_update_function is a Python callback and cannot run on the device (SURVEY F10)")
         st = plan.state
@@ -136,6 +148,53 @@ class RandomWalk(MetropolisHastings):
         plan.wrote(self.param)
 
 
+    def extra_state_names(self):
+        """State this sampler rewrites besides self.param: the basis matrix when it moves RJ knots / widths (MCMC's
+        warm-up pass saves and restores it together with the sampled parameter)."""
+        rj = getattr(self, "_rj_bound", None)
+        return [rj.basis.matrix] if rj is not None else []
+
+    def _compile_rj_walk(self, plan, rj, debug_draws):
+        """Knots / widths of a ReversibleJump model: one truncated step per live component with the basis column
+        rebuilt for the proposal (omc_rj_knot_walk).  The basis is the RJ sampler's declared GaussianKernelBasis; a
+        `state_update_function` given for reference compatibility (its tests pass make_basis) is not called."""
+        from openmcmc_b200 import engine
+        from openmcmc_b200 import kernels as K
+
+        if not self._loop:
+            raise engine.PlanError("knots / widths of a ReversibleJump model are moved by RandomWalkLoop")
+        self._rj_bound = rj
+        if self.domain_limits is None:
+            raise ValueError("RandomWalkLoop needs domain_limits (SURVEY F5)")
+        lim = np.asarray(self.domain_limits, dtype=np.float64).reshape(-1, 2)
+        step = np.asarray(self.step, dtype=np.float64)
+        if lim.shape[0] != 1 or step.size != 1:
+            raise engine.PlanError("RandomWalkLoop on RJ knots / widths needs one (lower, upper) pair and a scalar step")
+        args = rj.setup(plan, None)
+        which = 0 if self.param == rj.basis.knots else 1
+        n_max = int(rj.n_max)
+        import torch
+
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["counters"] = torch.zeros(plan.state.n_chains, 2, dtype=torch.int64, device=plan.state.device)
+            ctx["dz"], ctx["du"], ctx["stride"] = None, None, 0
+            if debug_draws:
+                if "tn_u" in debug_draws:
+                    ctx["dz"], ctx["stride"] = plan.debug_tensor(debug_draws["tn_u"], n_max)
+                if "u" in debug_draws:
+                    ctx["du"], ctx["stride"] = plan.debug_tensor(debug_draws["u"], n_max)
+
+        def launch():
+            K.rj_knot_walk(args, which, float(step.item()), lim[0, 0], lim[0, 1], debug_tn_u=ctx["dz"], debug_u=ctx["du"],
+                           debug_sweep_stride=ctx["stride"], counters=ctx["counters"], rng_=ctx["rng"])
+
+        plan.emit(launch, f"rj_knot_walk[{self.param}]")
+        plan.wrote(self.param)
+        plan.wrote(rj.basis.matrix)
+
+
 @dataclass
 class RandomWalkLoop(RandomWalk):
     """One MH step per replicate column of the (p_dim, n_rep) parameter.  ref: metropolis_hastings.py:272-289"""
@@ -154,6 +213,42 @@ class ManifoldMALA(MetropolisHastings):
     """
 
     derivatives: str = "analytic"
+    rj: object = None      # extension: see RandomWalk.rj
+
+    def _compile_rj(self, plan, rj, debug_draws):
+        """Coefficients of a ReversibleJump model (variable length on the padded state): omc_rj_coef_mmala."""
+        import torch
+
+        from openmcmc_b200 import engine
+        from openmcmc_b200 import kernels as K
+
+        step = np.asarray(self.step, dtype=np.float64)
+        if step.size != 1:
+            raise engine.PlanError("ManifoldMALA on the device needs a scalar step")
+        args = rj.setup(plan, None)
+        n_max = int(rj.n_max)
+        C = plan.state.n_chains
+        ctx = plan.ctx(self)
+        if "rng" not in ctx:
+            ctx["rng"] = plan.rng_site()
+            ctx["counters"] = torch.zeros(C, 2, dtype=torch.int64, device=plan.state.device)
+            ctx["dz"], ctx["dz_stride"], ctx["du"], ctx["du_stride"] = None, 0, None, 0
+            if debug_draws:
+                if "z" in debug_draws:
+                    ctx["dz"], ctx["dz_stride"] = plan.debug_tensor(debug_draws["z"], n_max)
+                if "u" in debug_draws:
+                    ctx["du"], ctx["du_stride"] = plan.debug_tensor(debug_draws["u"], 1)
+            ctx["probe"] = None
+            if plan.probes is not None and plan.probes.get("enable"):
+                ctx["probe"] = plan.new(C, 6, fill=0.0)
+                plan.probes[self.param] = {"step": ctx["probe"]}
+
+        def launch():
+            K.rj_coef_mmala(args, float(step.item()), debug_z=ctx["dz"], debug_u=ctx["du"], stride_z=ctx["dz_stride"],
+                            stride_u=ctx["du_stride"], counters=ctx["counters"], probe=ctx["probe"], rng_=ctx["rng"])
+
+        plan.emit(launch, f"rj_coef_mmala[{self.param}]")
+        plan.wrote(self.param)
 
     def compile(self, plan, host_state, debug_draws=None):
         from openmcmc_b200 import devdist, engine
@@ -161,6 +256,9 @@ class ManifoldMALA(MetropolisHastings):
 
         if self.derivatives not in ("analytic", "fd"):
             raise ValueError("derivatives must be 'analytic' or 'fd'")
+        rj = self._rj_of(plan)
+        if rj is not None:
+            return self._compile_rj(plan, rj, debug_draws)
         st = plan.state
         C = st.n_chains
         theta = st[self.param]

@@ -117,7 +117,10 @@ class ReversibleJump(MetropolisHastings):
             raise engine.PlanError(f"ReversibleJump: model lacks {sorted(need - seen)}")
         return out
 
-    def compile(self, plan, host_state, debug_draws=None):
+    def setup(self, plan, host_state, debug_draws=None):
+        """Create the padded device state and the omc_rj_t description once per plan.  Called by MCMC.prepare before
+        any sampler compiles, so that the companion samplers of the RJ model (ManifoldMALA on the coefficients,
+        RandomWalkLoop on knots / widths) find the padded state whatever the sampler order."""
         import torch
 
         st = plan.state
@@ -169,7 +172,10 @@ class ReversibleJump(MetropolisHastings):
             plan.keep.extend([n_dev, theta, omega, beta, Bm])
             K.rj_basis(ctx["args"])     # basis of the initial knots (the host copy is not trusted to be padded)
             plan.__dict__["_rj"] = self
-        args = ctx["args"]
+        return ctx["args"]
+
+    def compile(self, plan, host_state, debug_draws=None):
+        args = self.setup(plan, host_state, debug_draws)
         plan.emit(lambda: K.reversible_jump(args), f"reversible_jump[{self.param}]")
         for name in [self.param] + self.extra_state_names():
             plan.wrote(name)

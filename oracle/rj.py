@@ -142,3 +142,79 @@ def rj_step(m, st, draws):
     info = dict(birth=birth, del_index=d, logp_cur=lp_c, logp_prop=lp_p, lq_fwd=lq_f, lq_rev=lq_r, log_accept=log_accept,
                 accepted=acc, prop=prop)
     return (prop if acc else st), info
+
+
+# ----------------------------------------------------------------------------------------------- companion samplers
+def knot_walk_sweep(m, st, which, step, limits, tn_u, u):
+    """RandomWalkLoop.sample over the knots (which = 'theta') or widths ('omega') with the basis rebuilt for every
+    proposal (the reference tests' move_function = make_basis as state_update_function).
+
+    ref: metropolis_hastings.py:276-289 (loop over columns), :212-269 (truncated proposal of one column, densities),
+    :127-161 (accept on the FULL model: RandomWalk keeps it when a state_update_function is given, :201-210).
+    tn_u / u: per component, the uniform behind truncnorm.rvs and the accept uniform.  Returns (state, n_accepted)."""
+    from oracle import gmrf
+
+    st = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in st.items()}
+    n, lo, hi = st["n"], limits[0], limits[1]
+    n_acc = 0
+    for j in range(n):
+        cur = st[which][j]
+        z = float(gmrf.truncated_normal_rv(cur, step, lo, hi, tn_u[j]))
+        lq_f = float(gmrf.truncated_normal_log_pdf(z, cur, step, lo, hi))
+        lq_r = float(gmrf.truncated_normal_log_pdf(cur, z, step, lo, hi))
+        prop = dict(st)
+        prop[which] = st[which].copy()
+        prop[which][j] = z
+        prop["B"] = make_basis(m["X"], prop["theta"], prop["omega"])
+        lp_c = model_log_p(m, n, st["theta"], st["omega"], st["beta"], st["B"])
+        lp_p = model_log_p(m, n, prop["theta"], prop["omega"], prop["beta"], prop["B"])
+        with np.errstate(all="ignore"):
+            if bool(np.log(u[j]) < lp_p + lq_r - (lp_c + lq_f)):
+                st = prop
+                n_acc += 1
+    return st, n_acc
+
+
+def coef_mmala_step(m, st, step, z, u):
+    """ManifoldMALA.sample on the live coefficients.  Conditional model: response Normal(y | B beta, (tau_y I)^-1) (or
+    Null) and the iid Normal prior; gradient / Hessian by the mean-parameter and response branches of
+    Normal.grad_log_p (location_scale.py:222-250); proposal N(beta + Hs^-1 g / 2, Hs^-1), Hs = H / step^2, forward and
+    reverse (metropolis_hastings.py:301-373).  Returns (state, info)."""
+    n, beta, B = st["n"], st["beta"], st["B"]
+
+    def grad_hess(b):
+        g = -m["tau_beta"] * (b - m["mu_beta"])
+        H = m["tau_beta"] * np.eye(n)
+        if m["y"] is not None:
+            g = g + m["tau_y"] * (B.T @ (m["y"] - B @ b))
+            H = H + m["tau_y"] * (B.T @ B)
+        return g, H
+
+    def params(b):
+        g, H = grad_hess(b)
+        L = np.linalg.cholesky(H / step ** 2)
+        return b + 0.5 * np.linalg.solve(L.T, np.linalg.solve(L, g)), L
+
+    def log_density(x, mean, L):      # up to the constant the reference drops as well (:350-373)
+        w = L.T @ (x - mean)
+        return float(np.sum(np.log(np.diag(L))) - 0.5 * w @ w)
+
+    def cond_log_p(b):
+        lp = 0.0
+        if m["y"] is not None:
+            r = m["y"] - B @ b
+            lp += 0.5 * (r.size * np.log(m["tau_y"]) - r.size * np.log(2 * np.pi) - m["tau_y"] * float(r @ r))
+        d = b - m["mu_beta"]
+        return lp + 0.5 * (n * np.log(m["tau_beta"]) - n * np.log(2 * np.pi) - m["tau_beta"] * float(d @ d))
+
+    mu_f, L = params(beta)
+    prop = mu_f + np.linalg.solve(L.T, np.asarray(z, float)[:n])
+    mu_r, L_r = params(prop)
+    lq_f, lq_r = log_density(prop, mu_f, L), log_density(beta, mu_r, L_r)
+    log_accept = cond_log_p(prop) + lq_r - (cond_log_p(beta) + lq_f)
+    acc = bool(np.log(u) < log_accept)
+    out = dict(st)
+    if acc:
+        out["beta"] = prop
+    return out, dict(prop=prop, lq_fwd=lq_f, lq_rev=lq_r, log_accept=log_accept, accepted=acc)
+

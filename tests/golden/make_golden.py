@@ -610,6 +610,93 @@ def rj_case(seed, n_data, n0, n_max, n_steps, response="normal", with_omega=True
     return out
 
 
+def rj_companion_case(seed, n_data, n0, n_max, n_sweeps, response="normal"):
+    """The other three samplers of the reference's RJ model (tests/test_reversible_jump.py:213-252) driven call by call
+    on states whose size the (unrecorded) ReversibleJump steps in between keep changing: ManifoldMALA on beta,
+    RandomWalkLoop on theta and on omega with move_function = make_basis as state_update_function.  Every call records
+    the state before, its variates and the state after."""
+    rng = np.random.default_rng(seed)
+    lo, hi, wlo, whi = -10.0, 10.0, 0.5, 2.0
+    X = lo + (hi - lo) * np.sort(rng.random((n_data, 1)), axis=0)
+    theta = lo + (hi - lo) * rng.random((1, n0))
+    omega = 0.7 + 0.8 * rng.random((1, n0))
+    B = _rj_basis(X, theta, omega)
+    tau_beta, tau_y, rho = 0.25, 100.0, float(n0)
+    beta = 2.0 * rng.standard_normal((n0, 1))
+    y = B @ beta + 0.1 * rng.standard_normal((n_data, 1))
+    state = {"y": y, "beta": beta + 0.05 * rng.standard_normal((n0, 1)), "tau_y": np.array([[tau_y]]), "P": sparse.eye(n_data),
+             "B": B, "n_basis": np.array([[float(n0)]]), "X": X, "theta": theta, "omega": omega, "mu_beta": np.zeros((1, 1)),
+             "tau_beta": tau_beta * np.ones((1, 1)), "rho": np.array([[rho]]), "alloc_beta": np.zeros((n0, 1), dtype=int),
+             "a_omega": 3.0 * np.ones((1, 1)), "b_omega": 2.0 * np.ones((1, 1))}
+    mean = LinearCombination(form={"beta": "B"})
+    prec = ScaledMatrix(matrix="P", scalar="tau_y")
+    resp = (Normal if response == "normal" else NullDistribution)(response="y", mean=mean, precision=prec)
+    mdl = Model([resp,
+                 Normal(response="beta", mean=MixtureParameterVector(param="mu_beta", allocation="alloc_beta"),
+                        precision=MixtureParameterMatrix(param="tau_beta", allocation="alloc_beta")),
+                 Poisson(response="n_basis", rate="rho"),
+                 Uniform(response="theta", domain_response_lower=np.array([lo], ndmin=2),
+                         domain_response_upper=np.array([hi], ndmin=2)),
+                 Gamma("omega", shape="a_omega", rate="b_omega")])
+
+    def move_fn(st, param_index):
+        st["B"] = _rj_basis(st["X"], st["theta"], st["omega"])
+        return st, 0.0, 0.0
+
+    def birth_fn(current_state, prop_state):
+        prop_state["B"] = _rj_basis(prop_state["X"], prop_state["theta"], prop_state["omega"])
+        prop_state["alloc_beta"] = np.concatenate((prop_state["alloc_beta"], np.array([0], ndmin=2)), axis=0)
+        return prop_state, 0.0, 0.0
+
+    def death_fn(current_state, prop_state, deletion_index):
+        prop_state["B"] = np.delete(prop_state["B"], obj=deletion_index, axis=1)
+        prop_state["alloc_beta"] = np.delete(prop_state["alloc_beta"], obj=deletion_index, axis=0)
+        return prop_state, 0.0, 0.0
+
+    step_b, step_t, step_w = 0.5, 0.3, 0.1
+    mmala = ManifoldMALA(param="beta", model=mdl, step=np.array(step_b), max_variable_size=n_max)
+    rw_t = RandomWalkLoop(param="theta", model=mdl, step=np.array(step_t), max_variable_size=n_max,
+                          domain_limits=np.array([lo, hi], ndmin=2), state_update_function=move_fn)
+    rw_w = RandomWalkLoop(param="omega", model=mdl, step=np.array(step_w), max_variable_size=n_max,
+                          domain_limits=np.array([wlo, whi], ndmin=2), state_update_function=move_fn)
+    rj = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta", "omega"], n_max=n_max,
+                        state_birth_function=birth_fn, state_death_function=death_fn,
+                        matching_params={"variable": "beta", "matrix": "B", "scale": 1.0, "limits": [-10.0, 10.0]})
+
+    def pad(a):
+        out = np.zeros(n_max)
+        a = np.asarray(a, dtype=float).ravel()
+        out[: a.size] = a
+        return out
+
+    rec = {k: [] for k in ("kind", "n", "theta_before", "omega_before", "beta_before", "theta_after", "omega_after",
+                           "beta_after", "z", "tn_u", "u", "accepted")}
+    kinds = {"beta": 0, "theta": 1, "omega": 2}
+    for it in range(n_sweeps):
+        for smp in (mmala, rw_t, rw_w):
+            n = int(np.asarray(state["n_basis"]).ravel()[0])
+            before = {k: pad(state[k]) for k in ("theta", "omega", "beta")}
+            a0 = smp.accept_rate.count["accept"]
+            with Streams(seed + 77 * it + kinds[smp.param]) as S:
+                state = smp.sample(state)
+            rec["kind"].append(float(kinds[smp.param]))
+            rec["n"].append(float(n))
+            for k in ("theta", "omega", "beta"):
+                rec[k + "_before"].append(before[k])
+                rec[k + "_after"].append(pad(state[k]))
+            rec["z"].append(pad(np.concatenate(S.log["z"])) if S.log["z"] else np.zeros(n_max))
+            rec["tn_u"].append(pad(np.concatenate(S.log["tn_u"])) if S.log["tn_u"] else np.zeros(n_max))
+            rec["u"].append(pad(np.concatenate(S.log["u"])))
+            rec["accepted"].append(float(smp.accept_rate.count["accept"] - a0))
+        with Streams(seed + 5000 + it):
+            state = rj.sample(state)      # unrecorded: changes the size of the state between the recorded calls
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(X=X.ravel(), y=y.ravel(), tau_y=tau_y, tau_beta=tau_beta, mu_beta=0.0, rho=rho, a_omega=3.0, b_omega=2.0,
+               theta_lo=lo, theta_hi=hi, omega_lo=wlo, omega_hi=whi, n_max=n_max, step_beta=step_b, step_theta=step_t,
+               step_omega=step_w, response=response)
+    return out
+
+
 def rj_cases():
     return {
         "rj_normal_n50_k4": rj_case(0, 50, 4, 12, 60),
@@ -632,7 +719,7 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
@@ -645,6 +732,9 @@ def main():
         cases.update(gmrf_cases())
     if "rj" in which:
         cases.update(rj_cases())
+    if "rj_moves" in which:
+        cases.update({"rjmoves_normal_n60_k5": rj_companion_case(41, 60, 5, 12, 6),
+                      "rjmoves_null_n40_k3": rj_companion_case(42, 40, 3, 8, 5, response="null")})
     for name, d in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, {k: np.shape(v) for k, v in d.items() if k.startswith("store")})

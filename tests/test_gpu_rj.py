@@ -329,3 +329,95 @@ def test_reversible_jump_with_python_callbacks_is_refused():
                          matching_params={"variable": "beta", "matrix": "B", "scale": 1.0, "limits": None})
     with pytest.raises(engine.PlanError):
         MCMC({"n_basis": 2, "theta": np.zeros((1, 2))}, [rjs], model=mdl, n_burn=0, n_iter=1).run_mcmc()
+
+
+# ------------------------------------------------------------------------------------------------ companion samplers
+MOVE_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "rjmoves_*.npz")))
+
+
+def _full_rj_setup(g, n, th, om, be, response):
+    """Model, state and the four samplers of the reference's RJ model (tests/test_reversible_jump.py:213-252) with the
+    declarative basis instead of its Python callbacks."""
+    from scipy import sparse
+
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA, RandomWalkLoop
+    from openmcmc_b200.sampler.reversible_jump import GaussianKernelBasis, ReversibleJump
+    from oracle import rj
+
+    g = dict(g)
+    g["with_omega"] = True
+    mdl = _rj_model(g, response)
+    n_max, nd = int(g["n_max"]), g["X"].size
+    rjs = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta", "omega"], n_max=n_max,
+                         matching_params={"variable": "beta", "matrix": "B", "scale": 1.0, "limits": [-10.0, 10.0]},
+                         basis=GaussianKernelBasis(matrix="B", locations="X", knots="theta", widths="omega"))
+    mm = ManifoldMALA(param="beta", model=mdl, step=np.array(float(g["step_beta"])), max_variable_size=n_max, rj=rjs)
+    rt = RandomWalkLoop(param="theta", model=mdl, step=np.array(float(g["step_theta"])), max_variable_size=n_max,
+                        domain_limits=np.array([float(g["theta_lo"]), float(g["theta_hi"])], ndmin=2), rj=rjs)
+    rw = RandomWalkLoop(param="omega", model=mdl, step=np.array(float(g["step_omega"])), max_variable_size=n_max,
+                        domain_limits=np.array([float(g["omega_lo"]), float(g["omega_hi"])], ndmin=2), rj=rjs)
+    state = {"y": g["y"].reshape(-1, 1), "beta": be.reshape(-1, 1).copy(), "tau_y": float(g["tau_y"]), "P": sparse.eye(nd),
+             "B": rj.make_basis(g["X"], th, om), "n_basis": n, "X": g["X"].reshape(-1, 1), "theta": th.reshape(1, -1).copy(),
+             "omega": om.reshape(1, -1).copy(), "mu_beta": np.zeros((1, 1)), "tau_beta": float(g["tau_beta"]) * np.ones((1, 1)),
+             "rho": float(g["rho"]), "alloc_beta": np.zeros((n, 1)), "a_omega": float(g["a_omega"]) * np.ones((1, 1)),
+             "b_omega": float(g["b_omega"]) * np.ones((1, 1))}
+    return mdl, state, dict(beta=mm, theta=rt, omega=rw, n_basis=rjs)
+
+
+@pytest.mark.parametrize("name", MOVE_NAMES)
+def test_rj_companion_samplers_replay_reference_calls(name):
+    """ManifoldMALA on the variable-length coefficients and RandomWalkLoop on knots / widths (omc_rj_coef_mmala,
+    omc_rj_knot_walk) on the padded state, call by call against the live reference (its variates injected)."""
+    from openmcmc_b200.mcmc import MCMC
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    n_max = int(g["n_max"])
+    response = str(g["response"])
+    for it in range(g["kind"].size):
+        n, kind = int(g["n"][it]), int(g["kind"][it])
+        th, om, be = (g[k + "_before"][it][:n] for k in ("theta", "omega", "beta"))
+        mdl, state, smp = _full_rj_setup(g, n, th, om, be, response)
+        param = ("beta", "theta", "omega")[kind]
+        if kind == 0:
+            dd = {"beta": {"z": g["z"][it].reshape(1, 1, n_max), "u": g["u"][it][:1].reshape(1, 1, 1)}}
+        else:
+            dd = {param: {"tn_u": g["tn_u"][it].reshape(1, 1, n_max), "u": g["u"][it].reshape(1, 1, n_max)}}
+        M = MCMC(state, [smp[param]], model=mdl, n_burn=0, n_iter=1, debug_draws=dd)
+        M.run_mcmc()
+        got = np.asarray(M.store[param]).reshape(-1)[:n]
+        np.testing.assert_allclose(got, g[param + "_after"][it][:n], rtol=1e-9, atol=1e-10, err_msg=f"call {it} {param}")
+        assert smp[param].accept_rate.count["accept"] == int(g["accepted"][it]), (it, param)
+        assert smp[param].accept_rate.count["proposal"] == (1 if kind == 0 else n)
+
+
+def test_rj_full_model_free_running_fits_the_data():
+    """All four samplers of the RJ model together, free-running on data from three well-separated kernels: the chains
+    must end up explaining the data (residual near the noise level) with every chain healthy."""
+    from openmcmc_b200.mcmc import MCMC
+    from oracle import rj
+
+    rng = np.random.default_rng(12)
+    nd, n_max = 120, 16
+    X = np.linspace(-10, 10, nd)
+    th_true, om_true, be_true = np.array([-6.0, 0.5, 6.5]), np.array([1.0, 0.8, 1.2]), np.array([4.0, -3.0, 5.0])
+    y = rj.make_basis(X, th_true, om_true) @ be_true + 0.05 * rng.standard_normal(nd)
+    g = {"X": X, "y": y, "tau_y": 400.0, "tau_beta": 0.05, "mu_beta": 0.0, "rho": 3.0, "a_omega": 3.0, "b_omega": 2.0,
+         "theta_lo": -10.0, "theta_hi": 10.0, "omega_lo": 0.5, "omega_hi": 2.0, "n_max": n_max, "step_beta": 0.8,
+         "step_theta": 0.3, "step_omega": 0.1}
+    th0, om0, be0 = np.array([-5.0, 0.0, 5.0, 8.0]), np.ones(4), np.zeros(4)
+    mdl, state, smp = _full_rj_setup(g, 4, th0, om0, be0, "normal")
+    C = 32
+    M = MCMC(state, [smp["beta"], smp["theta"], smp["omega"], smp["n_basis"]], model=mdl, n_burn=1500, n_iter=20, n_thin=5,
+             n_chains=C, seed=4)
+    M.run_mcmc()
+    assert np.all((M.status & 3) == 0)
+    n_last = M.store["n_basis"][:, 0, -1].astype(int)
+    rmse = []
+    for c in range(C):
+        k = n_last[c]
+        th, om, be = (M.store[p][c, :k, -1] for p in ("theta", "omega", "beta"))
+        rmse.append(np.sqrt(np.mean((rj.make_basis(X, th, om) @ be - y) ** 2)))
+    assert np.median(rmse) < 0.15, np.sort(rmse)
+    assert 3 <= np.median(n_last) <= 6
+    for p in ("beta", "theta", "omega"):
+        assert 0 < smp[p].accept_rate.count["accept"] < smp[p].accept_rate.count["proposal"]

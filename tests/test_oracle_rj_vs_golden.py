@@ -107,3 +107,41 @@ def test_reference_known_answers_overlap_and_no_overlap():
     np.testing.assert_allclose(info["prop"]["beta"][-1], 2.0, atol=1e-5)
     p_birth, p_death = rj.move_probabilities(4, 20, 0.5, False)
     np.testing.assert_allclose(info["lq_fwd"] - np.log(p_death), np.log(0.5), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ companion samplers
+MOVE_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "rjmoves_*.npz")))
+
+
+def moves_model_of(g):
+    return dict(X=g["X"], y=g["y"] if str(g["response"]) == "normal" else None, tau_y=float(g["tau_y"]),
+                tau_beta=float(g["tau_beta"]), mu_beta=float(g["mu_beta"]), rho=float(g["rho"]), a_omega=float(g["a_omega"]),
+                b_omega=float(g["b_omega"]), theta_lo=float(g["theta_lo"]), theta_hi=float(g["theta_hi"]),
+                n_max=int(g["n_max"]))
+
+
+@pytest.mark.parametrize("name", MOVE_NAMES)
+def test_rj_companion_oracle_replays_reference_calls(name):
+    """ManifoldMALA on the coefficients and RandomWalkLoop on knots / widths (basis rebuilt per proposal) of the RJ
+    model, call by call against the live reference's recorded states and variates."""
+    from oracle import rj
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    m = moves_model_of(g)
+    seen = set()
+    for it in range(g["kind"].size):
+        n, kind = int(g["n"][it]), int(g["kind"][it])
+        th, om, be = (g[k + "_before"][it][:n] for k in ("theta", "omega", "beta"))
+        st = dict(n=n, theta=th, omega=om, beta=be, B=rj.make_basis(g["X"], th, om))
+        if kind == 0:
+            new, info = rj.coef_mmala_step(m, st, float(g["step_beta"]), g["z"][it][:n], g["u"][it][0])
+            n_acc = int(info["accepted"])
+        else:
+            which = "theta" if kind == 1 else "omega"
+            lim = (m["theta_lo"], m["theta_hi"]) if kind == 1 else (float(g["omega_lo"]), float(g["omega_hi"]))
+            new, n_acc = rj.knot_walk_sweep(m, st, which, float(g["step_" + which]), lim, g["tn_u"][it][:n], g["u"][it][:n])
+        assert n_acc == int(g["accepted"][it]), (it, kind)
+        for k in ("theta", "omega", "beta"):
+            np.testing.assert_allclose(new[k], g[k + "_after"][it][:n], rtol=1e-9, atol=1e-10, err_msg=f"{it} {kind} {k}")
+        seen.add((kind, n))
+    assert len({k for k, _ in seen}) == 3 and len({n for _, n in seen}) >= 2
