@@ -51,6 +51,12 @@ WORKLOADS = {
     "c5": dict(name="ReversibleJump birth/death, Gaussian-kernel basis model: 8192 chains/GPU, n_data=512, n_max=128, "
                     "rho=32, Normal response, matched transitions", kind="rj", chains=8192, n=512, p=128, thin=1,
                dominant="reversible_jump", cpu=dict(chains_per_worker=2, sweeps=300), ref=dict(chains_per_worker=1, sweeps=100)),
+    # the same model with all four samplers of the reference's RJ model: ManifoldMALA on the coefficients, RandomWalkLoop
+    # on knots and widths (basis rebuilt per proposal), ReversibleJump (the CPU port times the RJ step only)
+    "c5full": dict(name="full RJ source model: ManifoldMALA(beta) + RandomWalkLoop(theta) + RandomWalkLoop(omega) + "
+                        "ReversibleJump, 8192 chains/GPU, n_data=512, n_max=128, rho=32", kind="rj", full=True, chains=8192,
+                   n=512, p=128, thin=1, dominant="reversible_jump", cpu=dict(chains_per_worker=1, sweeps=40),
+                   ref=dict(chains_per_worker=1, sweeps=10)),
 }
 
 
@@ -246,7 +252,7 @@ def build_mh(C, n, p, dev, rank, host, loop):
     return mdl, [smp], state
 
 
-def build_rj(C, n_data, n_max, dev, rank, host):
+def build_rj(C, n_data, n_max, dev, rank, host, full=False):
     """the reference RJ test model scaled — n_data points on [-10, 10], capacity n_max, rho = n_max / 4,
     Gaussian-kernel basis, truncated matching [-10, 10] with scale 1; every chain has its own response."""
     import numpy as np
@@ -284,6 +290,16 @@ def build_rj(C, n_data, n_max, dev, rank, host):
              "X": X.reshape(-1, 1), "theta": theta, "omega": omega, "mu_beta": np.zeros((1, 1)),
              "tau_beta": 0.25 * np.ones((1, 1)), "rho": rho, "alloc_beta": np.zeros((k0, 1)),
              "a_omega": 3.0 * np.ones((1, 1)), "b_omega": 2.0 * np.ones((1, 1))}
+    if full:
+        from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA, RandomWalkLoop
+
+        samplers = [ManifoldMALA(param="beta", model=mdl, step=np.array(0.8), max_variable_size=n_max),
+                    RandomWalkLoop(param="theta", model=mdl, step=np.array(0.3), max_variable_size=n_max,
+                                   domain_limits=np.array([-10.0, 10.0], ndmin=2)),
+                    RandomWalkLoop(param="omega", model=mdl, step=np.array(0.1), max_variable_size=n_max,
+                                   domain_limits=np.array([0.5, 2.0], ndmin=2)),
+                    smp]
+        return mdl, samplers, state
     return mdl, [smp], state
 
 
@@ -301,7 +317,7 @@ def build(wl, C, n, dev, rank, host=False):
     if wl["kind"] == "gmrf":
         return build_gmrf(C, n, wl["p"], dev, rank, host)
     if wl["kind"] == "rj":
-        return build_rj(C, n, wl["p"], dev, rank, host)
+        return build_rj(C, n, wl["p"], dev, rank, host, full=wl.get("full", False))
     return build_mh(C, n, wl["p"], dev, rank, host, loop=wl["dominant"] == "random_walk_loop")
 
 

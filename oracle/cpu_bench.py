@@ -26,12 +26,12 @@ def _worker(workload, chains, sweeps, seed, n, p):
         return _worker_gmrf(rng, chains, sweeps, n)
     if workload in ("c4a", "c4b"):
         return _worker_mh(rng, chains, sweeps, p, workload)
-    if workload == "c5":
-        return _worker_rj(rng, chains, sweeps, n, p)
+    if workload in ("c5", "c5full"):
+        return _worker_rj(rng, chains, sweeps, n, p, full=workload == "c5full")
     raise ValueError(workload)
 
 
-def _worker_rj(rng, chains, sweeps, n_data, n_max):
+def _worker_rj(rng, chains, sweeps, n_data, n_max, full=False):
     """C5: ReversibleJump steps on the Gaussian-kernel basis model (n_data points, rho = n_max / 4 expected knots) with a
     Normal response, plus the per-iteration log_post (mcmc.py:108)."""
     import numpy as np
@@ -53,6 +53,11 @@ def _worker_rj(rng, chains, sweeps, n_data, n_max):
     t0 = time.perf_counter()
     for m, st in data:
         for _ in range(sweeps):
+            if full:   # the other three samplers of the RJ model: ManifoldMALA(beta), RandomWalkLoop(theta / omega)
+                k = st["n"]
+                st, _ = rj.coef_mmala_step(m, st, 0.8, rng.standard_normal(k), rng.random())
+                st, _ = rj.knot_walk_sweep(m, st, "theta", 0.3, (-10.0, 10.0), rng.random(k), rng.random(k))
+                st, _ = rj.knot_walk_sweep(m, st, "omega", 0.1, (0.5, 2.0), rng.random(k), rng.random(k))
             d = dict(u_move=rng.random(), theta_new=rng.uniform(-10, 10), omega_new=rng.gamma(3.0) / 2.0, beta_new=None,
                      u_trunc=rng.random(), del_index=float(rng.integers(0, st["n"])), u_accept=rng.random())
             st, _ = rj.rj_step(m, st, d)
