@@ -45,7 +45,6 @@ __device__ __forceinline__ OmcRng to_rng(const omc_rng_t& r) {
 }
 
 struct WalkShared {
-  double z, lq_f, lq_r, dprior, u;
   int accept;
 };
 
@@ -61,6 +60,9 @@ __global__ void __launch_bounds__(RM_NT) rj_knot_walk_kernel(omc_rj_walk_t w) {
   double* th = cnew + nd;      // cap
   double* om = th + cap;       // cap
   double* be = om + cap;       // cap
+  double* pz = be + cap;       // cap : proposals of all components (a component's proposal depends on its own value only)
+  double* plq = pz + cap;      // cap : lq_rev - lq_fwd + prior difference of the moved component
+  double* pu = plq + cap;      // cap : accept uniforms
   const int k = (int)a.n_basis[chain];
   if (k < 1 || k > cap) {
     if (tid == 0 && a.status) atomicOr(&a.status[chain], OMC_STATUS_NAN);
@@ -97,21 +99,25 @@ __global__ void __launch_bounds__(RM_NT) rj_knot_walk_kernel(omc_rj_walk_t w) {
   const double* du = w.debug_u ? w.debug_u + sw * w.debug_sweep_stride + (long long)chain * cap : nullptr;
   const OmcRng rng = to_rng(a.rng);
   long long n_acc = 0;
+  // ---- all proposals up front, one component per thread: the truncated-normal inverse CDF and the two proposal
+  //      densities are the expensive scalar part of a step and do not depend on what the other components did
+  for (int j = tid; j < k; j += RM_NT) {
+    const double cur = w.which ? om[j] : th[j];
+    const uint4 b = omc_rng_block(rng, chain, (unsigned int)j);
+    const double var = dtn ? dtn[j] : omc_u01(b.x, b.y);
+    const double z = omc_truncated_normal_rv(cur, w.step, w.lim_lo, w.lim_hi, var);
+    const double lq_f = omc_truncated_normal_log_pdf(z, cur, w.step, w.lim_lo, w.lim_hi);
+    const double lq_r = omc_truncated_normal_log_pdf(cur, z, w.step, w.lim_lo, w.lim_hi);
+    // prior of the moved component: Uniform knots are constant, widths carry their Gamma prior when it is in the model
+    const double dprior = (w.which && a.sample_omega) ? gamma_logpdf(z, shape_w, rate_w) - gamma_logpdf(cur, shape_w, rate_w) : 0.0;
+    pz[j] = z;
+    plq[j] = dprior + lq_r - lq_f;
+    pu[j] = du ? du[j] : omc_u01(b.z, b.w);
+  }
+  __syncthreads();
   for (int j = 0; j < k; ++j) {
-    if (tid == 0) {
-      const double cur = w.which ? om[j] : th[j];
-      const uint4 b = omc_rng_block(rng, chain, (unsigned int)j);
-      const double var = dtn ? dtn[j] : omc_u01(b.x, b.y);
-      const double z = omc_truncated_normal_rv(cur, w.step, w.lim_lo, w.lim_hi, var);
-      sh.z = z;
-      sh.lq_f = omc_truncated_normal_log_pdf(z, cur, w.step, w.lim_lo, w.lim_hi);
-      sh.lq_r = omc_truncated_normal_log_pdf(cur, z, w.step, w.lim_lo, w.lim_hi);
-      // prior of the moved component: Uniform knots are constant, widths carry their Gamma prior when it is in the model
-      sh.dprior = (w.which && a.sample_omega) ? gamma_logpdf(z, shape_w, rate_w) - gamma_logpdf(cur, shape_w, rate_w) : 0.0;
-      sh.u = du ? du[j] : omc_u01(b.z, b.w);
-    }
-    __syncthreads();
-    const double tj = w.which ? th[j] : sh.z, oj = w.which ? sh.z : om[j];
+    const double zj = pz[j];
+    const double tj = w.which ? th[j] : zj, oj = w.which ? zj : om[j];
     double part = 0.0;
     for (int i = tid; i < nd; i += RM_NT) {
       const double c = normpdf(a.X[i], tj, oj);
@@ -124,10 +130,9 @@ __global__ void __launch_bounds__(RM_NT) rj_knot_walk_kernel(omc_rj_walk_t w) {
     double rss_new = rss;
     if (yp) rss_new = omc_block_sum(part, s_red);
     if (tid == 0) {
-      double dlp = sh.dprior;
-      if (yp) dlp += -0.5 * tau_y * (rss_new - rss);
-      const double log_accept = dlp + sh.lq_r - sh.lq_f;
-      sh.accept = (log(sh.u) < log_accept) ? 1 : 0;
+      double log_accept = plq[j];
+      if (yp) log_accept += -0.5 * tau_y * (rss_new - rss);
+      sh.accept = (log(pu[j]) < log_accept) ? 1 : 0;
     }
     __syncthreads();
     if (sh.accept) {
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(RM_NT) rj_knot_walk_kernel(omc_rj_walk_t w) {
         *bij = cnew[i];
       }
       if (tid == 0) {
-        if (w.which) om[j] = sh.z; else th[j] = sh.z;
+        if (w.which) om[j] = zj; else th[j] = zj;
       }
       rss = rss_new;
       ++n_acc;
@@ -392,7 +397,7 @@ int omc_rj_knot_walk(const omc_rj_walk_t* w, void* stream) {
   if (int rc = rm_check(&w->model, "omc_rj_knot_walk")) return rc;
   OMC_REQUIRE(w->which == 0 || w->which == 1, "omc_rj_knot_walk: which=%d", w->which);
   OMC_REQUIRE(w->step > 0.0 && w->lim_hi > w->lim_lo, "omc_rj_knot_walk: step / limits");
-  const int smem = (2 * w->model.n_data + 3 * w->model.n_max) * 8;
+  const int smem = (2 * w->model.n_data + 6 * w->model.n_max) * 8;
   OMC_REQUIRE(smem <= 200 * 1024, "omc_rj_knot_walk: n_data=%d too large", w->model.n_data);
   OMC_CHECK_CUDA(cudaFuncSetAttribute(rj_knot_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   rj_knot_walk_kernel<<<w->model.n_chains, RM_NT, smem, (cudaStream_t)stream>>>(*w);
