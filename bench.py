@@ -30,11 +30,11 @@ UNIT = "chain-iterations/s"
 WORKLOADS = {
     # BASELINE.json configs[1]: batched Bayesian linear regression (the config the metric is quoted on; fits 1 GPU)
     "c2": dict(name="batched Bayesian linear regression: 4096 chains/GPU, n=10000, p=64, NormalNormal+NormalGamma Gibbs",
-               kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="reg_pass",
+               kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="reg_rss",
                cpu=dict(chains_per_worker=8, sweeps=100), ref=dict(chains_per_worker=2, sweeps=5)),
     # BASELINE.json configs[0]: example-3 regression, single chain (latency bound)
     "c1": dict(name="examples/3_linear_regression: 1 chain, n=1000, p=3", kind="regression", chains=1, n=1000, p=3,
-               thin=1, dominant="reg_pass", cpu=dict(chains_per_worker=1, sweeps=4000),
+               thin=1, dominant="reg_rss", cpu=dict(chains_per_worker=1, sweeps=4000),
                ref=dict(chains_per_worker=1, sweeps=500)),
     # BASELINE.json configs[2]: example-4 GMRF smoother scaled up (sparse-enabled form)
     "c3": dict(name="temporal GMRF smoother: 64 chains/GPU, n=1e6 grid points, tridiagonal NormalNormal + 2x NormalGamma",
@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=None, help="override chains per GPU (debug only)")
     ap.add_argument("--n", type=int, default=None, help="override n (debug only)")
+    ap.add_argument("--upload-blocks", type=int, default=None,
+                    help="chain blocks of the e2e run (upload of block k+1 under the sweeps of block k); default: "
+                         "MCMC's automatic choice, one block per 4 GB of per-chain host input")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -321,20 +324,26 @@ def build(wl, C, n, dev, rank, host=False):
     return build_mh(C, n, wl["p"], dev, rank, host, loop=wl["dominant"] == "random_walk_loop")
 
 
-def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak):
+def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None):
     """Algorithmic work of the dominant op per launch over its measured duration."""
     hbm_peak, hbm_src = peaks
     sec = op_ms * 1e-3
     if wl["kind"] == "regression":
-        flops = C * (n * p * (p + 1) + 4 * n * p)       # SYRK + X'y + residual per chain (SURVEY §8d)
+        # per sweep: ONE stream over X, y for the residual (omc_reg_rss; SURVEY §8d bytes = 8 n (p+1) per chain-iteration);
+        # G = X'X and g = X'y depend on the data alone and come from one omc_reg_pass (DMMA SYRK) in the prologue
         byts = C * 8 * n * (p + 1)
-        return {"bound": "tensor", "kernel": "reg_pass_kernel (FP64 DMMA SYRK + X'y + rss)",
-                "achieved": flops / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": flops / sec / 1e12 / fp64_peak if fp64_peak else None,
+        roof = {"bound": "hbm", "kernel": "reg_pass_kernel<SYRK=false> (omc_reg_rss: residual pass over X, y)",
+                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
+                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+        if syrk_ms:
+            flops = C * (n * p * (p + 1) + 4 * n * p)   # SYRK + X'y + residual per chain (SURVEY §8d)
+            tf = flops / (syrk_ms * 1e-3) / 1e12
+            roof["prologue_syrk"] = {
+                "bound": "tensor", "kernel": "reg_pass_kernel (FP64 DMMA SYRK + X'y + rss), once per run (prologue)",
+                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                 "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
-                "hbm": {"achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-                        "peak_source": hbm_src}}
+                "kernel_ms": syrk_ms}
+        return roof
     if wl["kind"] == "gmrf":
         byts = C * 32 * n                                 # read y, P diag + off, write b (SURVEY §8d)
         return {"bound": "hbm", "kernel": "omc_tridiag_nn_draw (tg_aggregate_kernel + tg_tilescan_kernel + tg_solve_kernel)",
@@ -419,6 +428,20 @@ def run_b200(args, wl, key):
         k1.record()
     barrier()
     op_ms = k0.elapsed_time(k1) / reps
+    syrk_ms = None
+    if wl["kind"] == "regression":   # the data-only SYRK pass of the prologue, timed the same way (it runs once per run)
+        op2 = next((fn for label, fn in M._ops["prologue"] if label.startswith("reg_pass")), None)
+        if op2 is not None:
+            with torch.cuda.stream(M.stream):
+                g2 = K.Graph.capture(op2)
+                q0 = torch.cuda.Event(enable_timing=True)
+                q1 = torch.cuda.Event(enable_timing=True)
+                g2.launch(1)
+                q0.record()
+                g2.launch(reps)
+                q1.record()
+            barrier()
+            syrk_ms = q0.elapsed_time(q1) / reps
     clk = clocks.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -477,13 +500,31 @@ def run_b200(args, wl, key):
     e2e = None
     if not args.no_e2e:
         del M, op, op_graph, state, summ
+        op2 = g2 = None
         torch.cuda.empty_cache()
-        mdl, samplers2, hstate = build(wl, C, n, dev, rank, host=True)
+        # host-memory guard: every rank of the node pins its own copy of the inputs (c2: 21 GB per rank); when the
+        # node cannot hold them all, the e2e leg runs on the largest chain count per rank that fits and says so
+        Ce, e2e_note = C, ""
+        per_chain_host = 8.0 * n * (p + 1) if wl["kind"] == "regression" else 8.0 * n * 2 if wl["kind"] == "gmrf" else 0.0
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            budget = 0.6 * avail / max(local_world, 1)
+            if per_chain_host * C > budget:
+                Ce = max(64, int(budget / per_chain_host) // 64 * 64)
+                e2e_note = (f" [e2e on {Ce} of {C} chains per GPU: {local_world} ranks x {per_chain_host * C / 1e9:.1f} GB of "
+                            f"pinned host input exceed 60% of the node's {avail / 1e9:.0f} GB of free host memory]")
+        except Exception:
+            pass
+        mdl, samplers2, hstate = build(wl, Ce, n, dev, rank, host=True)
         torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         M2 = MCMC(hstate, samplers2, model=mdl, n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter,
-                  n_thin=thin, n_chains=C, seed=7, device=local, chain_offset=rank * C)
+                  n_thin=thin, n_chains=Ce, seed=7, device=local, chain_offset=rank * C,
+                  upload_blocks=args.upload_blocks)
         import contextlib
         import io
 
@@ -495,15 +536,17 @@ def run_b200(args, wl, key):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": C * world * args.steps / dt, "unit": UNIT,
+        e2e = {"value": Ce * world * args.steps / dt, "unit": UNIT, "chains_per_gpu": Ce,
+               "upload_blocks": M2.timing.get("upload_blocks", 1),
                "h2d_bytes_per_step": M2.timing["h2d_bytes"] / args.steps,
                "d2h_bytes_per_step": M2.timing["d2h_bytes"] / args.steps, "seconds": dt,
                "phases_s": {k: round(M2.timing[k], 4) for k in ("prepare_s", "sweeps_s", "collect_s") if k in M2.timing},
                "note": "MCMC(...).run_mcmc() with pinned host inputs: upload + plan compile + graph capture + "
-                       f"{args.steps} sweeps + download of all stored samples"}
+                       f"{args.steps} sweeps + download of all stored samples; upload_blocks > 1: the chains run as "
+                       "chain blocks, block k+1 uploading while block k sweeps" + e2e_note}
 
     if rank == 0:
-        roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak)
+        roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak, syrk_ms)
         try:
             roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", f"{key}_traffic.json")))["dram_bytes_per_launch"]
         except Exception:

@@ -73,6 +73,14 @@ int omc_reg_pass_workspace(int n_chains, int n, int p, int* n_split_out, long lo
 int omc_reg_pass(const double* X, long long strideX, const double* y, long long strideY, const double* w,
                  long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
                  double* stats, double* workspace, void* stream);
+/* omc_reg_rss: the residual-only pass.  rss = (y - X beta)' W (y - X beta) and cnt are written into the same record;
+ *   G and g are left as they are: they depend on the data alone, so a Gibbs sweep whose likelihood weights are not
+ *   sampled keeps them from one omc_reg_pass in the prologue and streams X once per sweep for the residual only
+ *   (HBM-bound, no tensor work).  Same arguments as omc_reg_pass; beta must not be NULL.
+ *   ref: sampler.py:275-284 (residual.T @ P @ residual of NormalGamma.sample), mcmc.py:108 (log_post) */
+int omc_reg_rss(const double* X, long long strideX, const double* y, long long strideY, const double* w,
+                long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
+                double* stats, double* workspace, void* stream);
 
 /* omc_nn_dense_draw: NormalNormal conditional draw for a dense p x p posterior precision (p <= 64)
  *   Q = lambda*P0 + tau*G ; b = lambda*P0*mu0 + tau*g ; L = chol(Q) ; mu = L^-T L^-1 b ; beta = mu + L^-T z

@@ -209,6 +209,11 @@ PROTOTYPES = {
         [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "omc_reg_rss": (
+        C.c_int,
+        [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "omc_nn_dense_draw": (C.c_int, [C.POINTER(NNDense), C.c_void_p]),
     "omc_quadform": (C.c_int, [C.POINTER(Quadform), C.c_void_p]),
     "omc_ng_draw": (C.c_int, [C.POINTER(NGDraw), C.c_void_p]),

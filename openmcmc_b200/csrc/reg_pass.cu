@@ -119,7 +119,9 @@ struct Cfg {
   static constexpr int BYTES = SMEM_DOUBLES * 8 + 64;  // + mbarriers
 };
 
-template <int PB, bool WEIGHTED>
+// SYRK = false: the residual-only pass (omc_reg_rss): no tensor work, no X'y; the same staging and fragment reads feed
+// the per-row dot products only, so the pass is bound by the HBM stream of X.
+template <int PB, bool WEIGHTED, bool SYRK = true>
 struct Worker {
   using C = Cfg<PB>;
   double acc[C::NTG][2];
@@ -148,12 +150,12 @@ struct Worker {
   template <int G, bool CHUNKED>
   __device__ __forceinline__ void stage(const double* Xs, int rg) {
     constexpr int LD = C::LD;
-    constexpr bool DO_G = (G == 0);
-    constexpr bool DO_RSS = (G == C::TG - 1);
+    constexpr bool DO_G = SYRK && (G == 0);
+    constexpr bool DO_RSS = !SYRK || (G == C::TG - 1);
     const double* ys = Xs + KC * LD;
     const double* ws = ys + KC;
 #pragma unroll 2
-    for (int ks = rg; ks < KC / 4; ks += C::RG) {
+    for (int ks = rg; ks < KC / 4; ks += (SYRK ? C::RG : NWARP)) {
       // padded layout: row 4ks+kq at stride LD ; chunked layout: row ks of chunk kq
       const int r = CHUNKED ? kq * C::RC + ks : 4 * ks + kq;
       const double* xr = CHUNKED ? Xs + kq * C::CH + ks * (8 * PB) + g : Xs + r * LD + g;
@@ -171,21 +173,27 @@ struct Worker {
         for (int jb = 0; jb < PB; ++jb) bf[jb] = af[jb];
       }
       // SYRK tiles of this group (lower triangle of the 8x8-block grid, row-major enumeration)
+      if (SYRK) {
 #pragma unroll
-      for (int i = 0; i < PB; ++i)
+        for (int i = 0; i < PB; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          const int t = i * (i + 1) / 2 + j;
-          if (t / C::NTG == G) dmma884(acc[t - G * C::NTG][0], acc[t - G * C::NTG][1], af[i], bf[j]);
-        }
+          for (int j = 0; j <= i; ++j) {
+            const int t = i * (i + 1) / 2 + j;
+            if (t / C::NTG == G) dmma884(acc[t - G * C::NTG][0], acc[t - G * C::NTG][1], af[i], bf[j]);
+          }
+      }
       if (DO_G) {  // X' W y
 #pragma unroll
         for (int jb = 0; jb < PB; ++jb) gacc[jb] = fma(bf[jb], yv, gacc[jb]);
       }
       if (DO_RSS) {  // residual of the 4 rows of this k-step
-        double dot = 0.0;
+        double dot = 0.0, dot1 = 0.0;   // two chains of fused multiply-adds (the residual-only pass has no DMMA to hide them)
 #pragma unroll
-        for (int jb = 0; jb < PB; ++jb) dot = fma(af[jb], bfrag[jb], dot);
+        for (int jb = 0; jb < PB; jb += 2) {
+          dot = fma(af[jb], bfrag[jb], dot);
+          if (jb + 1 < PB) dot1 = fma(af[jb + 1], bfrag[jb + 1], dot1);
+        }
+        dot += dot1;
         dot += omc_shfl_xor(dot, 4);
         dot += omc_shfl_xor(dot, 8);
         dot += omc_shfl_xor(dot, 16);
@@ -201,8 +209,8 @@ struct Worker {
 //               (cp.async.bulk, completion on an mbarrier) -- no LSU traffic for staging, so the DMMA fragment LDS never
 //               queue behind LDGSTS; the < KC-row tail is staged synchronously.
 // BULK = false: generic cp.async (LDGSTS) path with zero-fill into the padded layout, any p / alignment.
-template <int PB, bool WEIGHTED, bool BULK>
-__global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg_pass_kernel(RegPassArgs a) {
+template <int PB, bool WEIGHTED, bool BULK, bool SYRK>
+__global__ void __launch_bounds__(NTHREADS, (PB > 4 && SYRK) ? OMC_RP_MINBLOCKS : 4) reg_pass_kernel(RegPassArgs a) {
   using C = Cfg<PB>;
   constexpr int LD = C::LD;
   extern __shared__ __align__(16) double smem[];
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg
     cp_async_commit();
   };
 
-  Worker<PB, WEIGHTED> wk;
+  Worker<PB, WEIGHTED, SYRK> wk;
   wk.init(a, chain, lane);
 
 #pragma unroll
@@ -311,7 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg
       issue_stage(st + NSTAGE - 1);
     }
     const double* Xs = smem + (st % NSTAGE) * C::STAGE_DOUBLES;
-    if (C::TG == 1 || tg == 0) wk.template stage<0, BULK>(Xs, rg);
+    if (!SYRK) wk.template stage<0, BULK>(Xs, warp);   // residual-only: every warp is a row group of its own
+    else if (C::TG == 1 || tg == 0) wk.template stage<0, BULK>(Xs, rg);
     else wk.template stage<C::TG - 1, BULK>(Xs, rg);
   }
   if (!BULK) cp_async_wait<0>();
@@ -330,9 +339,33 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg
       if (WEIGHTED) ys[KC + r] = (r < valid) ? wc[r_base + r] : 0.0;
     }
     __syncthreads();
-    if (C::TG == 1 || tg == 0) wk.template stage<0, true>(Xs, rg);
+    if (!SYRK) wk.template stage<0, true>(Xs, warp);
+    else if (C::TG == 1 || tg == 0) wk.template stage<0, true>(Xs, rg);
     else wk.template stage<C::TG - 1, true>(Xs, rg);
     __syncthreads();
+  }
+  if (!SYRK) {
+    // ---- residual-only pass: rss and cnt are the only outputs; G and g of the record stay as they are
+    double r = (lane >> 2) == 0 ? wk.rss : 0.0, c = (lane >> 2) == 0 ? wk.cnt : 0.0;
+    r = omc_warp_sum(r);
+    c = omc_warp_sum(c);
+    if (lane == 0) {
+      smem[2 * warp] = r;
+      smem[2 * warp + 1] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double rs = 0.0, cs = 0.0;
+      for (int q = 0; q < NWARP; ++q) {
+        rs += smem[2 * q];
+        cs += smem[2 * q + 1];
+      }
+      const int rec = p * p + p + 2;
+      double* o = a.out + ((long long)chain * a.n_split + split) * rec;
+      o[p * p + p] = rs;
+      o[p * p + p + 1] = WEIGHTED ? cs : (double)nrows;
+    }
+    return;
   }
 
   // ---- combine the row groups through shared memory (per warp: tiles | g | rss, cnt)
@@ -404,36 +437,86 @@ __global__ void __launch_bounds__(NTHREADS, (PB > 4) ? OMC_RP_MINBLOCKS : 4) reg
   }
 }
 
-// sum the per-split records: out[c][:] = sum_s part[c][s][:]
-__global__ void reg_reduce_kernel(const double* part, double* out, int n_split, int rec, long long total) {
+// sum the per-split records: out[c][e] = sum_s part[c][s][e] for the entries e >= e0 of a record
+__global__ void reg_reduce_kernel(const double* part, double* out, int n_split, int rec, int e0, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  long long c = i / rec;
-  int e = (int)(i - c * rec);
+  const int span = rec - e0;
+  long long c = i / span;
+  int e = e0 + (int)(i - c * span);
   const double* src = part + (c * n_split) * rec + e;
   double s = 0.0;
   for (int k = 0; k < n_split; ++k) s += src[(long long)k * rec];
-  out[i] = s;
+  out[c * rec + e] = s;
 }
 
-template <int PB, bool W, bool B>
+template <int PB, bool W, bool B, bool SYRK>
 int launch_one(const RegPassArgs& a, cudaStream_t st) {
   dim3 grid(a.n_split, a.n_chains);
   const int smem = Cfg<PB>::BYTES;
-  OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, W, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  reg_pass_kernel<PB, W, B><<<grid, NTHREADS, smem, st>>>(a);
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(reg_pass_kernel<PB, W, B, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  reg_pass_kernel<PB, W, B, SYRK><<<grid, NTHREADS, smem, st>>>(a);
   OMC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int PB>
+template <int PB, bool SYRK>
 int launch_pb(const RegPassArgs& a, bool weighted, cudaStream_t st) {
   // bulk (TMA-engine) copies need fully packed rows (p == 8*PB) and 16-byte aligned chunk starts for X, y and w
   auto al16 = [](const void* q) { return (((unsigned long long)q) & 15ull) == 0; };
   const bool bulk = OMC_RP_USE_BULK && (a.p == 8 * PB) && al16(a.X) && (a.strideX % 2 == 0) && al16(a.y) &&
                     (a.strideY % 2 == 0) && (!weighted || (al16(a.w) && (a.strideW % 2 == 0)));
-  if (weighted) return bulk ? launch_one<PB, true, true>(a, st) : launch_one<PB, true, false>(a, st);
-  return bulk ? launch_one<PB, false, true>(a, st) : launch_one<PB, false, false>(a, st);
+  if (weighted) return bulk ? launch_one<PB, true, true, SYRK>(a, st) : launch_one<PB, true, false, SYRK>(a, st);
+  return bulk ? launch_one<PB, false, true, SYRK>(a, st) : launch_one<PB, false, false, SYRK>(a, st);
+}
+
+template <bool SYRK>
+int launch_any(const RegPassArgs& a, bool weighted, cudaStream_t st) {
+  switch ((a.p + 7) / 8) {
+    case 1: return launch_pb<1, SYRK>(a, weighted, st);
+    case 2: return launch_pb<2, SYRK>(a, weighted, st);
+    case 3: return launch_pb<3, SYRK>(a, weighted, st);
+    case 4: return launch_pb<4, SYRK>(a, weighted, st);
+    case 5: return launch_pb<5, SYRK>(a, weighted, st);
+    case 6: return launch_pb<6, SYRK>(a, weighted, st);
+    case 7: return launch_pb<7, SYRK>(a, weighted, st);
+    default: return launch_pb<8, SYRK>(a, weighted, st);
+  }
+}
+
+// Shared body of omc_reg_pass (SYRK = true) and omc_reg_rss (SYRK = false).
+template <bool SYRK>
+int reg_pass_impl(const double* X, long long strideX, const double* y, long long strideY, const double* w,
+                  long long strideW, const double* beta, long long strideB, int n_chains, int n, int p, double* stats,
+                  double* workspace, void* stream, const char* who) {
+  int n_split = 1;
+  long long ws = 0;
+  int rc = omc_reg_pass_workspace(n_chains, n, p, &n_split, &ws);
+  if (rc) return rc;
+  OMC_REQUIRE(X && y && stats, "%s: null pointer", who);
+  OMC_REQUIRE(SYRK || beta, "%s: beta missing", who);
+  OMC_REQUIRE(n_split == 1 || workspace != nullptr, "%s: workspace required (n_split=%d)", who, n_split);
+  OMC_REQUIRE(n_chains <= 65535, "%s: n_chains=%d exceeds grid.y; shard the chains", who, n_chains);
+  cudaStream_t st = (cudaStream_t)stream;
+  RegPassArgs a;
+  a.X = X; a.y = y; a.w = w; a.beta = beta;
+  a.strideX = strideX; a.strideY = strideY; a.strideW = strideW; a.strideB = strideB;
+  a.n = n; a.p = p; a.n_chains = n_chains; a.n_split = n_split;
+  int rps = (n + n_split - 1) / n_split;
+  rps = ((rps + KC - 1) / KC) * KC;
+  if (rps < KC) rps = KC;
+  a.rows_per_split = rps;
+  a.out = (n_split > 1) ? workspace : stats;
+  rc = launch_any<SYRK>(a, w != nullptr, st);
+  if (rc) return rc;
+  if (n_split > 1) {
+    const int rec = p * p + p + 2;
+    const int e0 = SYRK ? 0 : p * p + p;   // the residual-only pass owns rss | cnt, G | g stay as they are
+    long long total = (long long)n_chains * (rec - e0);
+    reg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, stats, n_split, rec, e0, total);
+    OMC_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 }  // namespace
@@ -454,41 +537,15 @@ extern "C" int omc_reg_pass_workspace(int n_chains, int n, int p, int* n_split_o
 extern "C" int omc_reg_pass(const double* X, long long strideX, const double* y, long long strideY, const double* w,
                             long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
                             double* stats, double* workspace, void* stream) {
-  int n_split = 1;
-  long long ws = 0;
-  int rc = omc_reg_pass_workspace(n_chains, n, p, &n_split, &ws);
-  if (rc) return rc;
-  OMC_REQUIRE(X && y && stats, "omc_reg_pass: null pointer");
-  OMC_REQUIRE(n_split == 1 || workspace != nullptr, "omc_reg_pass: workspace required (n_split=%d)", n_split);
-  OMC_REQUIRE(n_chains <= 65535, "omc_reg_pass: n_chains=%d exceeds grid.y; shard the chains", n_chains);
-  cudaStream_t st = (cudaStream_t)stream;
-  RegPassArgs a;
-  a.X = X; a.y = y; a.w = w; a.beta = beta;
-  a.strideX = strideX; a.strideY = strideY; a.strideW = strideW; a.strideB = strideB;
-  a.n = n; a.p = p; a.n_chains = n_chains; a.n_split = n_split;
-  int rps = (n + n_split - 1) / n_split;
-  rps = ((rps + KC - 1) / KC) * KC;
-  if (rps < KC) rps = KC;
-  a.rows_per_split = rps;
-  a.out = (n_split > 1) ? workspace : stats;
-  const int pb = (p + 7) / 8;
-  const bool weighted = (w != nullptr);
-  switch (pb) {
-    case 1: rc = launch_pb<1>(a, weighted, st); break;
-    case 2: rc = launch_pb<2>(a, weighted, st); break;
-    case 3: rc = launch_pb<3>(a, weighted, st); break;
-    case 4: rc = launch_pb<4>(a, weighted, st); break;
-    case 5: rc = launch_pb<5>(a, weighted, st); break;
-    case 6: rc = launch_pb<6>(a, weighted, st); break;
-    case 7: rc = launch_pb<7>(a, weighted, st); break;
-    default: rc = launch_pb<8>(a, weighted, st); break;
-  }
-  if (rc) return rc;
-  if (n_split > 1) {
-    const int rec = p * p + p + 2;
-    long long total = (long long)n_chains * rec;
-    reg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, stats, n_split, rec, total);
-    OMC_LAUNCH_CHECK();
-  }
-  return 0;
+  return reg_pass_impl<true>(X, strideX, y, strideY, w, strideW, beta, strideB, n_chains, n, p, stats, workspace, stream,
+                             "omc_reg_pass");
+}
+
+// Residual-only pass: rss = (y - X beta)' W (y - X beta) and cnt into the record, G and g untouched (they depend on the
+// data alone; the sweep plan keeps them from the prologue's omc_reg_pass).  ref: sampler.py:276,283-284
+extern "C" int omc_reg_rss(const double* X, long long strideX, const double* y, long long strideY, const double* w,
+                           long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
+                           double* stats, double* workspace, void* stream) {
+  return reg_pass_impl<false>(X, strideX, y, strideY, w, strideW, beta, strideB, n_chains, n, p, stats, workspace, stream,
+                              "omc_reg_rss");
 }

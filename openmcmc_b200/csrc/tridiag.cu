@@ -64,6 +64,14 @@ constexpr int TG_NT = TG_NT_DEF;           // threads per CTA
 constexpr int TG_NW = TG_NT / 32;
 constexpr int TG_TILE = TG_K * TG_NT;      // 2304 elements = 18432 bytes per staged array
 constexpr int TG_PAIRS = TG_K / 2;
+#ifndef TG_SNT_DEF
+#define TG_SNT_DEF 128
+#endif
+constexpr int TG_SNT = TG_SNT_DEF;         // threads per CTA of the SOLVE kernel: a solve tile is a 1/TG_SUB slice of an
+constexpr int TG_SNW = TG_SNT / 32;        // aggregate tile (the backward look-back runs at this granularity; with 32
+constexpr int TG_SUB = TG_NT / TG_SNT;     // threads a solve CTA is one warp and has no CTA barrier to wait at)
+constexpr int TG_STILE = TG_K * TG_SNT;
+static_assert(TG_NT % TG_SNT == 0 && TG_SNT % 32 == 0, "solve tile must divide the aggregate tile");
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef TG_AGG_G
 #define TG_AGG_G 2                        // chains per CTA of the aggregate kernel (the shared P tile is staged once)
@@ -75,7 +83,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #define TG_LB_WIN 4                       // successors polled in the first look-back round
 #endif
 #ifndef TG_SOLVE_MINB
-#define TG_SOLVE_MINB (512 / TG_NT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
+#define TG_SOLVE_MINB (512 / TG_SNT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
 #endif
 
 // Look-back record of one tile.  Every payload travels in ONE 16-byte word together with its flag (16-byte accesses
@@ -92,7 +100,7 @@ struct __align__(64) RecB {
 struct Workspace {
   unsigned long long epoch;   // advanced by the tile-scan kernel of every draw
   unsigned int pad[14];
-  // followed by: RecB[n_tiles][n_chains], per-tile partial sums double[n_tiles][n_chains][4],
+  // followed by: RecB[n_stiles][n_chains], per-tile partial sums double[n_stiles][n_chains][4],
   //              tile totals double[n_tiles][n_chains][8], tile inputs double2[n_tiles][n_chains],
   //              thread prefixes double[n_chains][n_tiles][7][TG_NT]
 };
@@ -101,16 +109,19 @@ __host__ __device__ inline long long align_up(long long x, long long a) { return
 
 struct Layout {
   long long off_recb, off_flags_end, off_parts, off_tt, off_sin, off_ex, total;
-  long long n_tiles;
+  long long n_tiles;    // aggregate tiles (TG_TILE elements): tile totals / inputs / thread prefixes
+  long long n_stiles;   // solve tiles (TG_STILE elements): look-back records, partial sums
 };
 __host__ __device__ inline Layout make_layout(int n_chains, long long n) {
   Layout L;
   L.n_tiles = (n + TG_TILE - 1) / TG_TILE;
+  L.n_stiles = (n + TG_STILE - 1) / TG_STILE;
   const long long tc = L.n_tiles * n_chains;
+  const long long tcs = L.n_stiles * n_chains;
   L.off_recb = align_up(sizeof(Workspace), 128);
-  L.off_flags_end = L.off_recb + tc * (long long)sizeof(RecB);
+  L.off_flags_end = L.off_recb + tcs * (long long)sizeof(RecB);
   L.off_parts = align_up(L.off_flags_end, 128);
-  L.off_tt = align_up(L.off_parts + tc * 32, 128);
+  L.off_tt = align_up(L.off_parts + tcs * 32, 128);
   L.off_sin = L.off_tt + tc * 64;
   L.off_ex = align_up(L.off_sin + tc * 16, 128);
   L.total = L.off_ex + tc * 7 * TG_NT * 8;
@@ -241,9 +252,10 @@ struct Stage {
 // Stage CNT arrays for the tile starting at element i_t.  Full interior tiles with 16-byte aligned sources go through
 // cp.async.bulk (issued here, completion on `bar`); everything else (last tile, odd alignments, absent arrays) through
 // plain loads.  Returns whether the bulk path was taken; stage_wait() makes the data visible to every thread.
-template <int CNT>
+template <int CNT, int TILE = TG_TILE>
 __device__ __forceinline__ bool stage_issue(const Stage (&st)[CNT], long long i_t, long long n, unsigned long long* bar,
                                             int tid, int n_threads = TG_NT) {
+  constexpr int TG_TILE = TILE;   // (shadows the aggregate tile size inside this function)
   bool bulk = (i_t + TG_TILE < n);
 #pragma unroll
   for (int q = 0; q < CNT; ++q)
@@ -315,9 +327,11 @@ __device__ __forceinline__ uint4 normal_counter(unsigned long long sw, unsigned 
   return make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (unsigned int)(pair >> 20) * 0x9E3779B9u, gchain,
                     (site << 20) | (unsigned int)(pair & 0xFFFFFu));
 }
-__device__ __forceinline__ void normal_from(double jp1, double mm, int idx, uint4 b, double& z0, double& z1) {
+template <bool SMEM_TAB = false>
+__device__ __forceinline__ void normal_from(double jp1, double mm, int idx, uint4 b, double& z0, double& z1,
+                                            const double2* stab = nullptr) {
   // ---- radius
-  const double2 tab = __ldg(reinterpret_cast<const double2*>(omc_logtab) + idx);
+  const double2 tab = SMEM_TAB ? stab[idx] : __ldg(reinterpret_cast<const double2*>(omc_logtab) + idx);
   const double rr = fma(mm, tab.x, -1.0);
   double p = fma(rr, 1.0 / 7.0, -1.0 / 6.0);
   p = fma(p, rr, 1.0 / 5.0);
@@ -356,10 +370,11 @@ __device__ __forceinline__ void normal_from(double jp1, double mm, int idx, uint
   z1 = __hiloint2double(__double2hiint(a1) ^ (int)((b.w << 9) & 0x80000000u), __double2loint(a1));
 }
 // fast path; returns false when the pair has to be redone by normal_pair_slow
-__device__ __forceinline__ bool normal_pair_fast(uint4 b, double& z0, double& z1) {
+template <bool SMEM_TAB = false>
+__device__ __forceinline__ bool normal_pair_fast(uint4 b, double& z0, double& z1, const double2* stab = nullptr) {
   const int j = __clz((int)b.y);
   const double mm = __hiloint2double((int)((b.y & 0x000FFFFFu) | 0x3FF00000u), (int)b.x);
-  normal_from((double)(j + 1), mm, (int)((b.y >> 13) & 127u), b, z0, z1);
+  normal_from<SMEM_TAB>((double)(j + 1), mm, (int)((b.y >> 13) & 127u), b, z0, z1, stab);
   return b.y >= (1u << 20);
 }
 __device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
@@ -568,24 +583,24 @@ __global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layou
 // Tiles are taken in blockIdx order, top tile first: the reverse look-back of a tile waits only on tiles with a LOWER
 // block index, which the hardware dispatches earlier (the usual assumption of single-pass scans).
 template <bool GENERAL, bool DEBUG>
-__global__ void __launch_bounds__(TG_NT, DEBUG ? 1 : (GENERAL ? 2 : TG_SOLVE_MINB))
+__global__ void __launch_bounds__(TG_SNT, DEBUG ? 1 : (GENERAL ? 2 * TG_SUB : TG_SOLVE_MINB))
 tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   extern __shared__ __align__(128) double sm[];
-  __shared__ double s_red[2 * TG_NW];
-  __shared__ double s_part[3 * TG_NW];
+  __shared__ double s_red[2 * TG_SNW];
+  __shared__ double s_part[3 * TG_SNW];
   __shared__ int s_bad;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
-  double* spd = spe + TG_TILE;
-  double* sy = spd + TG_TILE;
-  double* sz = sy + TG_TILE;                          // DEBUG: the injected debug_z tile
-  double* sw = DEBUG ? sz + TG_TILE : sz;             // GENERAL
-  double* sh = sw + TG_TILE;                          // GENERAL
-  double* smu = sh + TG_TILE;                         // GENERAL (TG_TILE + 2: mu0 of the next tile's first element)
+  double* spd = spe + TG_STILE;
+  double* sy = spd + TG_STILE;
+  double* sz = sy + TG_STILE;                          // DEBUG: the injected debug_z tile
+  double* sw = DEBUG ? sz + TG_STILE : sz;             // GENERAL
+  double* sh = sw + TG_STILE;                          // GENERAL
+  double* smu = sh + TG_STILE;                         // GENERAL (TG_STILE + 2: mu0 of the next tile's first element)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ws->epoch);
   const int C = a.n_chains;
-  const long long T = L.n_tiles;
+  const long long T = L.n_stiles;            // solve tiles per chain
   const long long work = blockIdx.x;
   const long long tile = T - 1 - work / C;   // top tiles first; tile-major over the chains
   const int chain = (int)(work % C);
@@ -595,13 +610,18 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   RecB* rec = recs + tile * C + chain;
   double* parts = reinterpret_cast<double*>(wsb + L.off_parts) + (tile * C + chain) * 4;
   const unsigned long long FLAG_A = epoch * 4 + 1, FLAG_P = epoch * 4 + 2;
-  const long long i_t = tile * TG_TILE;
+  const long long i_t = tile * TG_STILE;
   const bool solve = !DEBUG || a.x != nullptr;
   const bool inject = DEBUG && a.debug_z != nullptr;
   const int j0 = tid * TG_K;
   const long long i0 = i_t + j0;
   const int nvalid = (int)max(0ll, min((long long)TG_K, n - i0));   // this thread's elements inside the chain
 
+#ifdef TG_LOGTAB_SMEM
+  __shared__ double2 s_logtab[128];   // the -ln U table next to the SM (the lookups were L1 round trips)
+  for (int j = tid; j < 128; j += TG_SNT) s_logtab[j] = __ldg(reinterpret_cast<const double2*>(omc_logtab) + j);
+  if (TG_SNT > 32) __syncthreads(); else __syncwarp();
+#endif
   TG_TRACE(0);
 #ifdef TG_EXP_TRACE
   if (tid == 0 && blockIdx.x < 32768) {
@@ -627,7 +647,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
       mbar_init(bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
       spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
-      if (GENERAL) smu[TG_TILE] = (mp && i_t + TG_TILE < n) ? __ldg(mp + i_t + TG_TILE) : 0.0;
+      if (GENERAL) smu[TG_STILE] = (mp && i_t + TG_STILE < n) ? __ldg(mp + i_t + TG_STILE) : 0.0;
     }
     const Stage st[7] = {{a.pe, n - 1, 0.0, spe},
                          {a.pd, n, 1.0, spd},
@@ -636,11 +656,13 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
                          {hp, n, 0.0, GENERAL ? sh : nullptr},
                          {mp, n, 0.0, GENERAL ? smu : nullptr},
                          {zp, n, 0.0, inject ? sz : nullptr}};
-    bulk = stage_issue<7>(st, i_t, n, bar, tid);
+    bulk = stage_issue<7, TG_STILE>(st, i_t, n, bar, tid, TG_SNT);
   }
   // ---- loads of the thread prefix / tile input / scalars go out now; their latency hides under the normals
-  const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * T + tile) * 7 * TG_NT + tid;
-  const double* sin_p = reinterpret_cast<const double*>(wsb + L.off_sin) + (tile * C + chain) * 2;
+  const long long atile = tile / TG_SUB;     // the aggregate tile this solve tile is a slice of
+  const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + atile) * 7 * TG_NT +
+                      (int)(tile % TG_SUB) * TG_SNT + tid;
+  const double* sin_p = reinterpret_cast<const double*>(wsb + L.off_sin) + (atile * C + chain) * 2;
   const double ea = ld_nc_now(exg), eb = ld_nc_now(exg + TG_NT), ec = ld_nc_now(exg + 2 * TG_NT),
                ed = ld_nc_now(exg + 3 * TG_NT), ee = ld_nc_now(exg + 4 * TG_NT), ef = ld_nc_now(exg + 5 * TG_NT),
                eg = ld_nc_now(exg + 6 * TG_NT);
@@ -668,7 +690,11 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
 #pragma unroll
       for (int i = 0; i < TG_RNG_GROUP; ++i) {
         const int c = c0 + i;
+#ifdef TG_LOGTAB_SMEM
+        if (c < TG_PAIRS && !normal_pair_fast<true>(b[i], g[2 * c], g[2 * c + 1], s_logtab)) redo |= 1u << c;
+#else
         if (c < TG_PAIRS && !normal_pair_fast(b[i], g[2 * c], g[2 * c + 1])) redo |= 1u << c;
+#endif
       }
     }
     while (redo) {   // probability 2^-12 per pair
@@ -788,7 +814,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     Aff wex{1.0, 0.0};    // composition of the warps above this one
     Aff tot{1.0, 0.0};    // the whole tile
 #pragma unroll
-    for (int w = TG_NW - 1; w >= 0; --w) {
+    for (int w = TG_SNW - 1; w >= 0; --w) {
       if (w == warp) wex = tot;
       tot = aff_mul(Aff{s_red[2 * w], s_red[2 * w + 1]}, tot);
     }
@@ -880,8 +906,10 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
       }
       *reinterpret_cast<double2*>(sy + j0 + 2 * c) = x2;
     }
-    bulk_out = (i_t + TG_TILE <= n) && al16(a.x + (long long)chain * n + i_t);
+    bulk_out = (i_t + TG_STILE <= n) && al16(a.x + (long long)chain * n + i_t);
+#ifndef TG_GENERIC_STORE
     if (bulk_out) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#endif
   }
   // ---- per-tile partial sums (fixed order: shuffle tree, then the 4 warps in order)
   ssp = omc_warp_sum(fma(2.0, ssp2, ssp));
@@ -889,37 +917,45 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   if (DEBUG) logdet = omc_warp_sum(logdet);
   if (lane == 0) {
     s_part[warp] = ssp;
-    s_part[TG_NW + warp] = ssl;
-    s_part[2 * TG_NW + warp] = logdet;
+    s_part[TG_SNW + warp] = ssl;
+    s_part[2 * TG_SNW + warp] = logdet;
   }
   __syncthreads();
   if (solve) {   // x tile: shared -> global (one bulk store for full aligned tiles)
     double* xg = a.x + (long long)chain * n + i_t;
     if (bulk_out) {
-      if (tid == 0) bulk_s2g(xg, sy, TG_TILE * 8);
+#ifdef TG_GENERIC_STORE
+#pragma unroll 3
+      for (int j = 2 * tid; j < TG_STILE; j += 2 * TG_SNT)    // coalesced 16-byte stores: no proxy fence, no bulk wait
+        *reinterpret_cast<double2*>(xg + j) = *reinterpret_cast<const double2*>(sy + j);
+#else
+      if (tid == 0) bulk_s2g(xg, sy, TG_STILE * 8);
+#endif
     } else {
-      for (int j = tid; j < TG_TILE; j += TG_NT)
+      for (int j = tid; j < TG_STILE; j += TG_SNT)
         if (i_t + j < n) xg[j] = sy[j];
     }
   }
   if (tid == 0) {   // per-tile partials; tg_partials_kernel reduces them per chain in a fixed order
     double sp = 0.0, sl = 0.0, ld = 0.0;
-    for (int w = 0; w < TG_NW; ++w) { sp += s_part[w]; sl += s_part[TG_NW + w]; ld += s_part[2 * TG_NW + w]; }
+    for (int w = 0; w < TG_SNW; ++w) { sp += s_part[w]; sl += s_part[TG_SNW + w]; ld += s_part[2 * TG_SNW + w]; }
     *reinterpret_cast<double2*>(parts) = make_double2(sp, sl);
     parts[2] = ld;
     if (s_bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
+#ifndef TG_GENERIC_STORE
     if (solve && bulk_out) bulk_store_wait();   // shared memory must stay alive until the bulk store has read it
+#endif
   }
   TG_TRACE(6);
 }
 
 // Per-chain sums of the per-tile partials, fixed order (deterministic): one warp per chain.
-__global__ void __launch_bounds__(32) tg_partials_kernel(Workspace* ws, Layout L, int C, double* ss_prior, double* ss_lik,
-                                                          double* logdet) {
+__global__ void __launch_bounds__(32) tg_partials_kernel(Workspace* ws, Layout L, long long n_parts, int C, double* ss_prior,
+                                                          double* ss_lik, double* logdet) {
   const int chain = blockIdx.x, lane = threadIdx.x;
   const double* parts = reinterpret_cast<const double*>(reinterpret_cast<char*>(ws) + L.off_parts);
   double sp = 0.0, sl = 0.0, ld = 0.0;
-  for (long long t = lane; t < L.n_tiles; t += 32) {
+  for (long long t = lane; t < n_parts; t += 32) {
     const double* p = parts + (t * C + chain) * 4;
     const double2 v = *reinterpret_cast<const double2*>(p);
     sp += v.x;
@@ -1006,13 +1042,13 @@ __global__ void tridiag_matvec_kernel(const double* pd, const double* pe, omc_ve
 int check_args(const omc_tridiag_nn_t* a, const char* who) {
   OMC_REQUIRE(a && a->pd && a->workspace, "%s: null argument", who);
   OMC_REQUIRE(a->n_chains >= 1 && a->n >= 1, "%s: n_chains=%d n=%lld", who, a->n_chains, a->n);
-  OMC_REQUIRE((long long)a->n_chains * ((a->n + TG_TILE - 1) / TG_TILE) < 0x7fffffffll, "%s: too many tiles", who);
+  OMC_REQUIRE((long long)a->n_chains * ((a->n + TG_STILE - 1) / TG_STILE) < 0x7fffffffll, "%s: too many tiles", who);
   return 0;
 }
 
 constexpr int aggregate_smem_doubles(bool general, int g) { return 4 + (general ? 5 : 2 + g) * TG_TILE + 4; }
 constexpr int solve_smem_doubles(bool general, bool debug) {
-  return 4 + (3 + (debug ? 1 : 0) + (general ? 3 : 0)) * TG_TILE + 4;
+  return 4 + (3 + (debug ? 1 : 0) + (general ? 3 : 0)) * TG_STILE + 4;
 }
 
 template <bool GENERAL, int G>
@@ -1028,7 +1064,7 @@ template <bool GENERAL, bool DEBUG>
 int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
   const int smem = solve_smem_doubles(GENERAL, DEBUG) * 8;
   OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_solve_kernel<GENERAL, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tg_solve_kernel<GENERAL, DEBUG><<<grid, TG_NT, smem, st>>>(a, ws, L);
+  tg_solve_kernel<GENERAL, DEBUG><<<grid, TG_SNT, smem, st>>>(a, ws, L);
   OMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1061,7 +1097,7 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   if (int rc = check_args(a, "omc_tridiag_nn_draw")) return rc;
   OMC_REQUIRE(a->y.ptr, "omc_tridiag_nn_draw: y missing");
   const Layout L = make_layout(a->n_chains, a->n);
-  const unsigned int grid = (unsigned int)(L.n_tiles * a->n_chains);
+  const unsigned int grid = (unsigned int)(L.n_stiles * a->n_chains);
   Workspace* ws = reinterpret_cast<Workspace*>(a->workspace);
   cudaStream_t st = (cudaStream_t)stream;
   const bool general = a->w.ptr || a->h.ptr || a->mu0.ptr;
@@ -1086,7 +1122,7 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   if (rc) return rc;
   const bool solve = a->x != nullptr;
   if ((solve && (a->ss_prior || a->ss_lik)) || a->logdet) {
-    tg_partials_kernel<<<a->n_chains, 32, 0, st>>>(ws, L, a->n_chains, solve ? a->ss_prior : nullptr,
+    tg_partials_kernel<<<a->n_chains, 32, 0, st>>>(ws, L, L.n_stiles, a->n_chains, solve ? a->ss_prior : nullptr,
                                                    solve ? a->ss_lik : nullptr, a->logdet);
     OMC_LAUNCH_CHECK();
   }
@@ -1101,7 +1137,8 @@ int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
   Workspace* ws = reinterpret_cast<Workspace*>(a->workspace);
   tg_quadforms_kernel<<<grid, TG_NT, 0, (cudaStream_t)stream>>>(*a, ws, L);
   OMC_LAUNCH_CHECK();
-  tg_partials_kernel<<<a->n_chains, 32, 0, (cudaStream_t)stream>>>(ws, L, a->n_chains, a->ss_prior, a->ss_lik, nullptr);
+  tg_partials_kernel<<<a->n_chains, 32, 0, (cudaStream_t)stream>>>(ws, L, L.n_tiles, a->n_chains, a->ss_prior, a->ss_lik,
+                                                                    nullptr);
   OMC_LAUNCH_CHECK();
   return 0;
 }

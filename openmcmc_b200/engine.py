@@ -367,27 +367,36 @@ class RegressionLikelihood:
         self.q_gg = f"gram[{tag}{dist.response}]"
         self.q_rss = f"rss[{tag}{dist.response}]"
         plan.add_quantity(Quantity(self.q_gg, deps_data, self._emit_pass, (self.q_rss,)))
-        plan.add_quantity(Quantity(self.q_rss, deps_data if data_only else deps_data | {param}, self._emit_pass,
+        plan.add_quantity(Quantity(self.q_rss, deps_data if data_only else deps_data | {param}, self._emit_rss,
                                    (self.q_gg,)))
 
-    def _emit_pass(self):
+    def _emit_rss(self):
+        """rss is stale.  While G | g (data only) are still valid, X is streamed for the residual alone (omc_reg_rss,
+        HBM-bound); otherwise the full pass refreshes the whole record."""
+        if self.data_only or not self.plan.valid[self.q_gg]:
+            return self._emit_pass()
+        return self._emit_pass(rss_only=True)
+
+    def _emit_pass(self, rss_only=False):
         C, n, p = self.plan.state.n_chains, self.n, self.p
         X, y, W, beta, stats, work = self.X, self.y, self.W, self.beta, self.stats, self.work
         w = W.data if W.kind == "diag" else None
         beta_data = None if self.data_only else beta.data
         others, y_eff = self.others, self.y_eff
 
+        kernel = K.reg_rss if rss_only else K.reg_pass
+
         def launch():
             if others:
                 K.linear_predictor(C, n, [(Xo.vec(), tho.vec(), Xo.cols, tr) for Xo, tho, tr, _, _ in others], y_eff,
                                    residual_of=y.vec())
-                K.reg_pass(X.data, y_eff, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain, y_shared=False,
-                           w_shared=True)
+                kernel(X.data, y_eff, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain, y_shared=False,
+                       w_shared=True)
                 return
-            K.reg_pass(X.data, y.data, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain,
-                       y_shared=not y.per_chain, w_shared=True)
+            kernel(X.data, y.data, w, beta_data, stats, work, C, n, p, x_shared=not X.per_chain,
+                   y_shared=not y.per_chain, w_shared=True)
 
-        self.plan.emit(launch, "reg_pass")
+        self.plan.emit(launch, "reg_rss" if rss_only else "reg_pass")
 
     # views into the record
     def rss_vec(self):

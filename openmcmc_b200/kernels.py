@@ -161,6 +161,16 @@ def reg_pass(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_
     )
 
 
+def reg_rss(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_shared=False, w_shared=False):
+    """Residual-only pass: stats[c][rss | cnt] for the current beta; the G | g part of the record is left untouched."""
+    check(
+        lib().omc_reg_rss(
+            _ptr(X), 0 if x_shared else n * p, _ptr(y), 0 if y_shared else n, _ptr(w), 0 if w_shared else n,
+            _ptr(beta), p, n_chains, n, p, _ptr(stats), _ptr(workspace), stream_ptr()),
+        "omc_reg_rss",
+    )
+
+
 def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, rng_, debug_z=None, probe_Q=None,
                   probe_b=None, probe_L=None, probe_mu=None, status=None, debug_sweep_stride=0, trunc=None,
                   debug_u=None):

@@ -35,6 +35,10 @@ class MCMC:
     chain_offset: int = 0
     debug_draws: dict = None   # {param: {"z"|"g"|"u": array [n_sweeps, (C,) size]}} injected random streams
     probes: bool = False       # keep per-sampler intermediates (Q, b, L, mu, a*, b*) of the LAST sweep
+    upload_blocks: int = None  # > 1: run the chains as that many contiguous chain blocks, block k+1 being uploaded and
+    #                            compiled while block k sweeps (chains are independent and the RNG is keyed by the
+    #                            global chain id, so the draws are the same); None = one block per 4 GB of per-chain
+    #                            HOST input, at most 8; see _run_blocked
     store: dict = field(default_factory=dict, init=False)
 
     def __post_init__(self):
@@ -130,12 +134,14 @@ class MCMC:
             # prologue: quantities the steady-state sweep assumes valid, computed from the initial state
             plan.ops = prologue_ops = []
             done = set()
+            plan.valid = {k: False for k in saved_valid}   # nothing is valid yet: every compute() emits its full form
             for qname, ok in valid_end.items():
                 if ok and qname not in done:
                     q = plan.quantities[qname]
                     q.compute()
                     done.add(qname)
                     done.update(q.siblings)
+            plan.valid = saved_valid
             self.plan = plan
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
             self._warm_up(plan, st, sampled)
@@ -275,10 +281,76 @@ class MCMC:
         out[:, :size, :] = arr
         return out
 
+    # ------------------------------------------------------------------ chain blocks: upload under compute
+    def _n_blocks(self):
+        """Chain blocks run_mcmc() uses: `upload_blocks`, limited so that every block keeps at least 2 chains; 1 when
+        the run injects draws / keeps probes / holds a ReversibleJump sampler (their host-side set-up is per run)."""
+        B = self.upload_blocks
+        if B is None:   # automatic: only per-chain inputs that still live on the host count
+            C, host_bytes = self.n_chains, 0
+            for v in self.state.values():
+                if isinstance(v, np.ndarray) and v.ndim == 3 and v.shape[0] == C:
+                    host_bytes += v.nbytes
+                elif isinstance(v, torch.Tensor) and v.dim() == 3 and v.shape[0] == C and not v.is_cuda:
+                    host_bytes += v.numel() * v.element_size()
+            B = min(8, int(host_bytes // 4e9))
+        B = min(int(B), self.n_chains // 2)
+        if B <= 1 or self.debug_draws or self.probes or self._rj_sampler() is not None:
+            return 1
+        return B
+
+    def _run_blocked(self, B):
+        """The chains as B contiguous blocks, each a sub-run with `chain_offset` = its first global chain id.  A block's
+        host->device upload, plan compile and graph capture happen on the host thread while the previous blocks' sweeps
+        run asynchronously on their own streams, so the PCIe transfer of X hides under the sweeps (and vice versa).
+        Results are merged into the shapes of an unblocked run and equal it bit for bit as long as the blocks pick the
+        same row split in omc_reg_pass (always the case once a block has a few hundred chains)."""
+        import time
+
+        C = self.n_chains
+        bounds = [(C * b // B, C * (b + 1) // B) for b in range(B)]
+        t0 = time.perf_counter()
+        subs = []
+        for lo, hi in bounds:
+            st = {}
+            for key, v in self.state.items():
+                per_chain = isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim == 3 and v.shape[0] == C
+                st[key] = v[lo:hi] if per_chain else v
+            sub = MCMC(st, self.samplers, self.model, n_burn=self.n_burn, n_iter=self.n_iter, n_thin=self.n_thin,
+                       n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo)
+            sub.prepare()
+            sub.run_device()      # asynchronous: the next block's upload starts right away
+            subs.append(sub)
+        t1 = time.perf_counter()
+        for sub in subs:
+            sub.stream.synchronize()
+        t2 = time.perf_counter()
+        for sub in subs:
+            sub.collect()
+        self.store = {}
+        for key in subs[0].store:
+            axis = 1 if key == "log_post" else 0
+            self.store[key] = np.concatenate([sub.store[key] for sub in subs], axis=axis)
+        for s in self.samplers:
+            for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
+                self.state[name] = np.concatenate([sub.state[name] for sub in subs], axis=0)
+        self.status = np.concatenate([sub.status for sub in subs])
+        self._blocks = subs
+        t3 = time.perf_counter()
+        self.timing = {"h2d_bytes": sum(sub.timing["h2d_bytes"] for sub in subs),
+                       "d2h_bytes": sum(sub.timing["d2h_bytes"] for sub in subs),
+                       "stored_iterations": subs[0].timing["stored_iterations"], "upload_blocks": B,
+                       "prepare_s": t1 - t0, "sweeps_s": t2 - t1, "collect_s": t3 - t2}
+
     def run_mcmc(self):
         """ref: mcmc.py:87-115"""
         import time
 
+        B = self._n_blocks()
+        if B > 1:
+            self._run_blocked(B)
+            self._finish([sub.plan for sub in self._blocks])
+            return
         t0 = time.perf_counter()
         self.prepare()
         t1 = time.perf_counter()
@@ -288,6 +360,10 @@ class MCMC:
         self.collect()
         t3 = time.perf_counter()
         self.timing.update({"prepare_s": t1 - t0, "sweeps_s": t2 - t1, "collect_s": t3 - t2})
+        self._finish([self.plan])
+
+    def _finish(self, plans):
+        """Status and acceptance report of a finished run (ref: mcmc.py:113-115)."""
         if np.any(self.status & 1):
             bad = int(np.sum((self.status & 1) != 0))
             if self.n_chains == 1:
@@ -297,5 +373,10 @@ class MCMC:
 
         for sampler in self.samplers:
             if isinstance(sampler, MetropolisHastings):
-                sampler._collect_accept(self.plan)
+                counts = []
+                for plan in plans:
+                    sampler._collect_accept(plan)
+                    counts.append(getattr(sampler, "accept_counts", None))
+                if len(plans) > 1 and all(c is not None for c in counts):
+                    sampler.accept_counts = np.concatenate(counts, axis=0)
                 print(f"{sampler.param}: {sampler.accept_rate.get_acceptance_rate()}")

@@ -56,6 +56,17 @@ def test_reg_pass_matches_oracle(C, n, p, weighted):
         assert _rel(out[c, p * p : p * p + p], g.ravel()) < RTOL
         assert abs(out[c, p * p + p] - rss) <= RTOL * abs(rss) + 1e-300
         assert out[c, p * p + p + 1] == cnt
+    # residual-only pass (omc_reg_rss) with another beta: rss | cnt refreshed, G | g left untouched bit for bit
+    beta2 = beta + 0.25
+    stats[:, p * p + p:] = float("nan")
+    K.reg_rss(dX, dy, dw, torch.tensor(beta2, device="cuda"), stats, work, C, n, p)
+    torch.cuda.synchronize()
+    out2 = stats.cpu().numpy()
+    assert np.array_equal(out2[:, : p * p + p], out[:, : p * p + p])
+    for c in range(C):
+        _, _, rss, cnt = conjugate.regression_suffstats(X[c], y[c], None if w is None else w[c], beta2[c])
+        assert abs(out2[c, p * p + p] - rss) <= RTOL * abs(rss) + 1e-300
+        assert out2[c, p * p + p + 1] == cnt
 
 
 @pytest.mark.parametrize("prior", ["eye", "diag", "dense"])
