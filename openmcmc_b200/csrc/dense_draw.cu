@@ -32,7 +32,7 @@ __device__ __forceinline__ double mat_at(int kind, const omc_vec_t& P, int chain
   return P.ptr ? P.ptr[(long long)chain * P.chain_stride] : 1.0;
 }
 
-__global__ void __launch_bounds__(DD_THREADS) nn_dense_draw_kernel(omc_nn_dense_t a) {
+__global__ void __launch_bounds__(DD_THREADS) nn_truncated_scan_kernel(omc_nn_dense_t a) {
   extern __shared__ double sm[];
   const int p = a.p, ld = p + 1;
   double* Q = sm;                 // p x ld, becomes L (lower triangle)
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(DD_THREADS) nn_dense_draw_kernel(omc_nn_dense_
     b[i] = s;
     if (a.probe_b) a.probe_b[(long long)chain * p + i] = s;
   }
-  if (a.truncated) {
+  {
     // ---- truncated prior: one coordinate-wise Gibbs scan from the current beta (gmrf.py:201-266), warp 0
     __syncthreads();
     if (warp == 0) {
@@ -105,91 +105,174 @@ __global__ void __launch_bounds__(DD_THREADS) nn_dense_draw_kernel(omc_nn_dense_
       if (lane + 32 < p) bt[lane + 32] = x1;
       if (lane == 0 && bad && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
     }
-    return;
   }
-  // z: injected or Philox/Box-Muller
-  if (a.debug_z) {
-    const double* dz = a.debug_z + (a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride;
-    for (int i = tid; i < p; i += DD_THREADS) z[i] = dz[(long long)chain * p + i];
-  } else {
-    OmcRng rng = to_rng(a.rng);
-    for (int t = tid; 2 * t < p; t += DD_THREADS) {
-      double z0, z1;
-      omc_normal2(rng, chain, t, z0, z1);
-      z[2 * t] = z0;
-      if (2 * t + 1 < p) z[2 * t + 1] = z1;
-    }
-  }
-  __syncthreads();
+}
 
-  // ---- right-looking Cholesky in shared memory (lower), 2 barriers per column
+// ---- NormalNormal draw, dense p x p posterior precision: one thread per COLUMN, the column in registers.
+// Thread c owns Q[i][c], i >= c (the lower triangle is all the reference's Cholesky reads).  Right-looking Cholesky:
+// at step j thread j scales its column by 1/sqrt(Q_jj) and publishes it in shared memory (column-major L, which the
+// triangular solves read afterwards); the other threads read it back as broadcasts and update their own column with
+// statically indexed registers (the loop over rows is unrolled, the loop over j is not).  The right-hand side b rides
+// along as one more row, so w = L^-1 b is there when the factorisation ends (ONE barrier per column, none in the solves).
+// Two warps then run the backward solves L' mu = w and L' v = z (lane = row, shuffle broadcast of the pivot element).
+// The previous CTA-wide kernel (256 threads, matrix in shared memory, 3 barriers per column) took 0.66 ms for the
+// 4096 chains of C2, a fifth of the sweep once the pass over X became a pure stream.
+template <int PR>
+__global__ void __launch_bounds__((PR < 32 ? 32 : PR), (PR == 64 ? 5 : (PR == 32 ? 10 : 16))) nn_dense_draw_kernel(omc_nn_dense_t a) {
+  constexpr int NT = PR < 32 ? 32 : PR;
+  constexpr int LD = PR + 2;                 // column stride (doubles): 16-byte aligned columns
+  extern __shared__ __align__(16) double sm[];
+  double* sL = sm;                           // sL[j * LD + i] = L[i][j], i >= j
+  double* sw = sL + PR * LD;                 // b -> w = L^-1 b -> mu
+  double* sz = sw + PR;                      // z -> v = L^-T z
+  double* sinv = sz + PR;                    // 1 / L_jj
+  double* sraw = sinv + PR;                  // 2 x PR: the unscaled column of the current step (double-buffered)
+  __shared__ int s_bad;
+  const int chain = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5, p = a.p;
+  const bool live = c < p;
+  if (c == 0) s_bad = 0;
+  const double* rec = a.stats.ptr + (long long)chain * a.stats.chain_stride;
+  const double tau = vec_at(a.tau, chain, 0, 1.0);
+  const double lam = vec_at(a.lambda, chain, 0, 1.0);
+
+  // ---- column c of Q = lam*P0 + tau*G (sampler.py:180-186), consecutive threads read consecutive addresses.  The
+  //      loads are kept free of stores (a probe store between them would order every load behind the previous one).
+  double col[PR];
+  double diag = 0.0, bc = 0.0;
+  {
+    const double* gcol = rec + c;             // G[i][c] at gcol[i * p]
+    const bool dense = a.prior_kind == OMC_MAT_DENSE;
+    const double* pcol = dense ? a.prior_P.ptr + (long long)chain * a.prior_P.chain_stride + c : gcol;
+    const double lam_d = dense ? lam : 0.0;   // one loop for the three prior kinds: the off-diagonal prior term is
+#pragma unroll                                // lam * P0[i][c] for a dense prior and nothing otherwise
+    for (int i = 0; i < PR; ++i) {
+      double q = 0.0;
+      if (live && i < p && i > c) q = fma(lam_d, pcol[i * p], tau * gcol[i * p]);
+      col[i] = q;
+    }
+    if (live) diag = lam * mat_at(a.prior_kind, a.prior_P, chain, p, c, c) + tau * gcol[c * p];
+  }
+  if (a.probe_Q && live) {
+    for (int i = 0; i < p; ++i)
+      a.probe_Q[(long long)chain * p * p + i * p + c] =
+          lam * mat_at(a.prior_kind, a.prior_P, chain, p, i, c) + tau * rec[i * p + c];
+  }
+  if (live) {   // b = (lam*P0) mu0 + tau*g
+    double sacc = 0.0;
+    if (a.prior_kind == OMC_MAT_DENSE) {
+      for (int j = 0; j < p; ++j) sacc += lam * mat_at(OMC_MAT_DENSE, a.prior_P, chain, p, c, j) * vec_at(a.mu0, chain, j, 0.0);
+    } else {
+      sacc = lam * mat_at(a.prior_kind, a.prior_P, chain, p, c, c) * vec_at(a.mu0, chain, c, 0.0);
+    }
+    bc = sacc + tau * rec[p * p + c];
+    if (a.probe_b) a.probe_b[(long long)chain * p + c] = bc;
+    // z: injected or Philox / Box-Muller (pair t = elements 2t, 2t+1; both threads of a pair draw it)
+    double zc;
+    if (a.debug_z) {
+      zc = a.debug_z[(a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride + (long long)chain * p + c];
+    } else {
+      double z0, z1;
+      omc_normal2(to_rng(a.rng), chain, c >> 1, z0, z1);
+      zc = (c & 1) ? z1 : z0;
+    }
+    sz[c] = zc;
+  }
+
+  // ---- right-looking Cholesky with the forward solve riding along.  Thread j publishes its column UNSCALED together
+  //      with rd = 1/sqrt(Q_jj) (its serial section is a reciprocal square root and 32 stores); thread i > j scales its
+  //      own entry L[i][j] = Q[i][j] * rd, stores it for the solves, and updates its column with the factor
+  //      L[i][j] * rd.  The raw column is double-buffered, so ONE barrier per step is enough.  Pairs of rows that are
+  //      dead for the whole warp (i <= j, or above the warp's first column) are skipped with a warp-uniform branch.
+  const int warp_lo = warp * 32;
   for (int j = 0; j < p; ++j) {
-    const double djj = Q[j * ld + j];
-    if (!(djj > 0.0)) {  // uniform across the CTA (same smem value)
-      if (tid == 0) bad = 1;
-      break;
-    }
-    const double d = sqrt(djj), rd = 1.0 / d;
-    __syncthreads();  // everyone has read Q[j][j] before it is overwritten
-    for (int i = j + tid; i < p; i += DD_THREADS) {
-      if (i == j) { Q[j * ld + j] = d; invd[j] = rd; }
-      else Q[i * ld + j] = Q[i * ld + j] / d;
+    double* colj = sraw + (j & 1) * PR;
+    if (c == j) {
+      if (!(diag > 0.0)) s_bad = j + 1;      // step-stamped: a fast thread of step j + 1 cannot end step j early
+      double rd;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(diag));
+      const double hd = 0.5 * diag;
+      double e = fma(-hd, rd * rd, 0.5);
+      rd = fma(rd, e, rd);
+      e = fma(-hd, rd * rd, 0.5);
+      rd = fma(rd, e, rd);                   // 1/sqrt(Q_jj), relative error ~1e-16
+#pragma unroll
+      for (int i = 0; i < PR; i += 2)          // all of it (rows <= j are never read): no branches in the serial section
+        *reinterpret_cast<double2*>(colj + i) = make_double2(col[i], col[i + 1]);
+      sL[j * LD + j] = diag * rd;            // L_jj
+      sinv[j] = rd;
+      sw[j] = bc * rd;                       // w_j
     }
     __syncthreads();
-    for (int i = j + 1 + warp; i < p; i += nwarp) {
-      const double lij = Q[i * ld + j];
-      for (int c = j + 1 + lane; c <= i; c += 32) Q[i * ld + c] -= lij * Q[c * ld + j];
+    {
+      const int sb = s_bad;
+      if (sb != 0 && sb <= j + 1) break;     // uniform: every thread sees the stamp of step j after the barrier
     }
-    __syncthreads();
+    if (c > j && live) {
+      const double rd = sinv[j];
+      const double lc = colj[c] * rd;        // L[c][j]
+      const double f = lc * rd;
+      sL[j * LD + c] = lc;
+      diag = fma(-lc, lc, diag);
+      bc = fma(-lc, sw[j], bc);
+      const int lo = max(j, warp_lo);
+#pragma unroll
+      for (int i0 = 0; i0 < PR; i0 += 16) {   // chunks of 16 rows: the loads of a chunk go out together
+        if (i0 + 15 > lo) {                   // warp-uniform
+          double2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const double2*>(colj + i0 + 2 * k);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {         // rows <= c of a live chunk are updated too: they are never read
+            const int i = i0 + 2 * k;
+            col[i] = fma(-v[k].x, f, col[i]);
+            col[i + 1] = fma(-v[k].y, f, col[i + 1]);
+          }
+        }
+      }
+    }
   }
   __syncthreads();
-  if (bad) {
-    if (tid == 0 && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
-    for (int i = tid; i < p; i += DD_THREADS) a.beta[(long long)chain * p + i] = nan("");
+  if (s_bad) {
+    if (c == 0 && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
+    if (live) a.beta[(long long)chain * p + c] = nan("");
     return;
   }
   if (a.probe_L) {
-    for (int e = tid; e < p * p; e += DD_THREADS) {
-      int i = e / p, j = e - i * p;
-      a.probe_L[(long long)chain * p * p + e] = (j <= i) ? Q[i * ld + j] : 0.0;
+    for (int e = c; e < p * p; e += NT) {
+      const int i = e / p, j = e - i * p;
+      a.probe_L[(long long)chain * p * p + e] = (j <= i) ? sL[j * LD + i] : 0.0;
     }
   }
-
-  // ---- triangular solves, one warp each: warp 0: L w = b, L' mu = w ; warp 1: L' v = z
-  // each lane owns rows lane and lane+32
-  if (warp == 0) {
-    double x0 = (lane < p) ? b[lane] : 0.0, x1 = (lane + 32 < p) ? b[lane + 32] : 0.0;
-    for (int j = 0; j < p; ++j) {  // forward, column oriented
-      double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) / Q[j * ld + j];
-      if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-      if (lane > j && lane < p) x0 -= Q[lane * ld + j] * xj;
-      if (lane + 32 > j && lane + 32 < p) x1 -= Q[(lane + 32) * ld + j] * xj;
-    }
-    for (int j = p - 1; j >= 0; --j) {  // backward with L' : uses row j of L
-      double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) / Q[j * ld + j];
-      if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-      if (lane < j) x0 -= Q[j * ld + lane] * xj;
-      if (lane + 32 < j) x1 -= Q[j * ld + lane + 32] * xj;
-    }
-    if (lane < p) b[lane] = x0;
-    if (lane + 32 < p) b[lane + 32] = x1;
-  } else if (warp == 1) {
-    double x0 = (lane < p) ? z[lane] : 0.0, x1 = (lane + 32 < p) ? z[lane + 32] : 0.0;
+  // ---- backward solves with L' (uses row j of L): warp 0: L' mu = w ; the last warp: L' v = z ; lane owns rows
+  //      lane and lane + 32
+  auto backsolve = [&](double* x) {
+    double x0 = (lane < p) ? x[lane] : 0.0, x1 = (lane + 32 < p) ? x[lane + 32] : 0.0;
     for (int j = p - 1; j >= 0; --j) {
-      double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) / Q[j * ld + j];
+      const double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) * sinv[j];
       if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-      if (lane < j) x0 -= Q[j * ld + lane] * xj;
-      if (lane + 32 < j) x1 -= Q[j * ld + lane + 32] * xj;
+      if (lane < j) x0 = fma(-sL[lane * LD + j], xj, x0);
+      if (lane + 32 < j) x1 = fma(-sL[(lane + 32) * LD + j], xj, x1);
     }
-    if (lane < p) z[lane] = x0;
-    if (lane + 32 < p) z[lane + 32] = x1;
-  }
+    if (lane < p) x[lane] = x0;
+    if (lane + 32 < p) x[lane + 32] = x1;
+  };
+  if (warp == 0) backsolve(sw);
+  if (warp == NT / 32 - 1) backsolve(sz);
   __syncthreads();
-  for (int i = tid; i < p; i += DD_THREADS) {
-    const double m = b[i];
-    if (a.probe_mu) a.probe_mu[(long long)chain * p + i] = m;
-    a.beta[(long long)chain * p + i] = m + z[i];
+  if (live) {
+    const double m = sw[c];
+    if (a.probe_mu) a.probe_mu[(long long)chain * p + c] = m;
+    a.beta[(long long)chain * p + c] = m + sz[c];
   }
+}
+
+template <int PR>
+int launch_dense_draw(const omc_nn_dense_t& a, cudaStream_t st) {
+  constexpr int NT = PR < 32 ? 32 : PR;
+  const size_t smem = (size_t)(PR * (PR + 2) + 5 * PR) * sizeof(double);
+  nn_dense_draw_kernel<PR><<<a.n_chains, NT, smem, st>>>(a);
+  OMC_LAUNCH_CHECK();
+  return 0;
 }
 
 __global__ void quadform_kernel(omc_quadform_t a) {
@@ -248,10 +331,16 @@ extern "C" int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream) {
   OMC_REQUIRE(args->prior_kind >= 0 && args->prior_kind <= 2, "omc_nn_dense_draw: prior_kind=%d", args->prior_kind);
   OMC_REQUIRE(args->prior_kind == OMC_MAT_EYE || args->prior_P.ptr, "omc_nn_dense_draw: prior_P missing");
   const int p = args->p;
-  const size_t smem = (size_t)(p * (p + 1) + 4 * p) * sizeof(double);
-  nn_dense_draw_kernel<<<args->n_chains, DD_THREADS, smem, (cudaStream_t)stream>>>(*args);
-  OMC_LAUNCH_CHECK();
-  return 0;
+  if (args->truncated) {
+    const size_t smem = (size_t)(p * (p + 1) + 4 * p) * sizeof(double);
+    nn_truncated_scan_kernel<<<args->n_chains, DD_THREADS, smem, (cudaStream_t)stream>>>(*args);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
+  if (p <= 8) return launch_dense_draw<8>(*args, (cudaStream_t)stream);
+  if (p <= 16) return launch_dense_draw<16>(*args, (cudaStream_t)stream);
+  if (p <= 32) return launch_dense_draw<32>(*args, (cudaStream_t)stream);
+  return launch_dense_draw<64>(*args, (cudaStream_t)stream);
 }
 
 extern "C" int omc_quadform(const omc_quadform_t* args, void* stream) {
