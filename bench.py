@@ -121,8 +121,9 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (host time, csv line)
         self.proc = None
+        self.t_mark = None
 
     def start(self):
         try:
@@ -135,7 +136,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: the sampler itself starts before the warm-up (nvidia-smi needs a second or more
+        to come up on an 8-GPU node), samples from here on are the ones reported."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -147,7 +153,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region + dominant-op timing"
+        if not timed:     # the timed region was shorter than one sampling period: report the warm-up samples instead
+            timed, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than one sample)"
+        for r in timed:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -161,7 +171,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------- workloads (B200 arm)
@@ -334,7 +344,11 @@ def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None):
         byts = C * 8 * n * (p + 1)
         roof = {"bound": "hbm", "kernel": "reg_pass_kernel<SYRK=false> (omc_reg_rss: residual pass over X, y)",
                 "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
+                "peak_note": "MEASURED_PEAKS.json's hbm_gbs is a COPY (half reads, half writes, bus turnarounds); this "
+                             "kernel only reads, and a read-only stream runs faster than a copy on HBM3e, so frac can "
+                             "exceed 1 against the copy figure (ncu: dram__bytes_read = 21.30 GB per launch, "
+                             "profiles/r01b_ncu_c2.txt); against the 8 TB/s nominal it is achieved / 8000"}
         if syrk_ms:
             flops = C * (n * p * (p + 1) + 4 * n * p)   # SYRK + X'y + residual per chain
             tf = flops / (syrk_ms * 1e-3) / 1e12
@@ -402,10 +416,11 @@ def run_b200(args, wl, key):
             torch.cuda.synchronize()
 
     # warm-up (untimed), then exactly K timed sweeps; every n_thin-th sweep is followed by the store graph
-    M.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
-    barrier()
     clocks = ClockSampler(local)
     clocks.start()
+    M.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
+    barrier()
+    clocks.mark()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(M.stream):
@@ -443,6 +458,38 @@ def run_b200(args, wl, key):
             barrier()
             syrk_ms = q0.elapsed_time(q1) / reps
     clk = clocks.stop()
+    # the reference's form of the sweep (A'QA recomputed by every NormalNormal.sample): the full fused pass, DMMA SYRK
+    # included, every sweep -- timed on the same resident inputs for comparison with the shipped data-only caching
+    syrk_sweep = None
+    if wl["kind"] == "regression":
+        from openmcmc_b200 import engine
+
+        engine.CACHE_DATA_ONLY = False
+        try:
+            M3 = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7, device=local,
+                      chain_offset=rank * C)
+            M3.prepare()
+        finally:
+            engine.CACHE_DATA_ONLY = True
+        M3.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(M3.stream):
+            s0.record()
+        M3.run_device(n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter, n_thin=thin)
+        with torch.cuda.stream(M3.stream):
+            s1.record()
+        barrier()
+        t3 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms3 = float(t3.item())
+        syrk_sweep = {"value": C * world * args.steps / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / args.steps,
+                      "note": "same workload with G = X'X and g = X'y recomputed by the fused DMMA pass in EVERY sweep "
+                              "(engine.CACHE_DATA_ONLY = False), as the reference does; the shipped plan keeps them "
+                              "from the prologue because they depend on the data alone"}
+        del M3
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -563,6 +610,8 @@ def run_b200(args, wl, key):
             "gpu_launches": launches_per_sweep * args.steps + store_launches * n_iter,
             "roofline": roof, "cpu_baseline": cpu_baseline, "ess": ess,
         }
+        if syrk_sweep is not None:
+            line["syrk_every_sweep"] = syrk_sweep
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,12 @@ from openmcmc_b200.parameter import Identity, LinearCombination, ScaledMatrix
 
 F64 = torch.float64
 
+# Data-only parts of a derived record (G = X'WX, g = X'Wy of the regression record) are kept across sweeps and only the
+# state-dependent part (the residual sum of squares) is refreshed.  False re-runs the full fused pass (DMMA SYRK
+# included) every sweep, the way the reference recomputes A'QA in every NormalNormal.sample (sampler.py:180-186);
+# bench.py times that form next to the shipped one.
+CACHE_DATA_ONLY = True
+
 
 # ============================================================================================== device state
 @dataclass
@@ -373,7 +379,7 @@ class RegressionLikelihood:
     def _emit_rss(self):
         """rss is stale.  While G | g (data only) are still valid, X is streamed for the residual alone (omc_reg_rss,
         HBM-bound); otherwise the full pass refreshes the whole record."""
-        if self.data_only or not self.plan.valid[self.q_gg]:
+        if self.data_only or not self.plan.valid[self.q_gg] or not CACHE_DATA_ONLY:
             return self._emit_pass()
         return self._emit_pass(rss_only=True)
 

@@ -322,3 +322,86 @@ def test_upload_blocks_give_identical_draws():
             assert np.array_equal(np.asarray(Bk.state[key]), np.asarray(A.state[key])), key
         assert np.array_equal(Bk.status, A.status)
     assert not np.array_equal(A.store["beta"][0], A.store["beta"][1])
+
+
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size (4096 chains, n = 10,000, p = 64; 21 GB of X on the device): size-independent
+    properties instead of an oracle run.  (a) the record of sampled chains against torch fp64 (G = X'X, g = X'y,
+    rss(beta) of the fused pass and of the residual-only pass), (b) rss(beta = NULL) = y'y for every chain,
+    (c) three free-running Gibbs sweeps of all chains equal, bit for bit, the same sweeps of a 1024-chain slice run on
+    its own with chain_offset (chains are independent and the RNG is keyed by the global chain id; the slice is large
+    enough for omc_reg_pass to pick the same row split, 592 chains or more -- with fewer chains per launch the rows
+    are split over more CTAs and the sums agree to rounding instead)."""
+    import torch
+    from scipy import sparse
+
+    from openmcmc_b200 import kernels as K
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    K.init_device(0)
+    if torch.cuda.mem_get_info()[0] < 60e9:
+        pytest.skip("needs 60 GB of free HBM")
+    C, n, p = 4096, 10_000, 64
+    gen = torch.Generator(device="cuda").manual_seed(2024)
+    X = torch.randn(C, n, p, dtype=torch.float64, device="cuda", generator=gen)
+    X[:, :, 0] = 1.0
+    bt = torch.randn(C, p, 1, dtype=torch.float64, device="cuda", generator=gen)
+    y = torch.bmm(X, bt) + 0.1 * torch.randn(C, n, 1, dtype=torch.float64, device="cuda", generator=gen)
+    beta = torch.randn(C, p, dtype=torch.float64, device="cuda", generator=gen)
+    rec = p * p + p + 2
+    stats = torch.empty(C, rec, dtype=torch.float64, device="cuda")
+    ns, ws = K.reg_pass_workspace(C, n, p)
+    work = torch.empty(max(ws, 1), dtype=torch.float64, device="cuda")
+    # (b) beta = NULL: rss = y'y
+    K.reg_pass(X, y, None, None, stats, work, C, n, p)
+    yy = (y[:, :, 0] ** 2).sum(dim=1)
+    assert float(((stats[:, p * p + p] - yy).abs() / yy).max()) < 1e-12
+    # (a) fused pass, then the residual-only pass with another beta
+    K.reg_pass(X, y, None, beta, stats, work, C, n, p)
+    first = stats.clone()
+    beta2 = beta + 0.5
+    K.reg_rss(X, y, None, beta2, stats, work, C, n, p)
+    torch.cuda.synchronize()
+    assert torch.equal(stats[:, : p * p + p], first[:, : p * p + p])
+    for c in (0, 1, 777, 2048, 4095):
+        G = X[c].T @ X[c]
+        g = X[c].T @ y[c, :, 0]
+        assert float((first[c, : p * p].reshape(p, p) - G).abs().max() / G.abs().max()) < 1e-12
+        assert float((first[c, p * p : p * p + p] - g).abs().max() / g.abs().max()) < 1e-12
+        for st, b in ((first, beta), (stats, beta2)):
+            r = y[c, :, 0] - X[c] @ b[c]
+            rss = float(r @ r)
+            assert abs(float(st[c, p * p + p]) - rss) < 1e-11 * rss
+        assert float(first[c, p * p + p + 1]) == n
+    del stats, first, work
+    # (c) sharding invariance of the whole Gibbs sweep at full size
+    mdl = Model([
+        Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
+        Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+        Gamma("tau", shape="a_tau", rate="b_tau"),
+        Gamma("lambda", shape="a_lambda", rate="b_lambda")])
+    samplers = [NormalNormal("beta", mdl), NormalGamma("tau", mdl), NormalGamma("lambda", mdl)]
+
+    def run(Xs, ys, nch, off):
+        state = {"y": ys, "X": Xs, "beta": np.zeros((p, 1)), "P_tau": sparse.identity(n, format="csc"), "tau": 1.0,
+                 "P_lambda": sparse.identity(p, format="csc"), "mu": np.zeros((p, 1)), "lambda": 0.01,
+                 "a_tau": 1e-3, "b_tau": 1e-3, "a_lambda": 1e-3, "b_lambda": 1e-3}
+        M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=3, n_chains=nch, seed=9, chain_offset=off)
+        M.run_mcmc()
+        return M
+
+    full = run(X, y, C, 0)
+    assert int((full.status != 0).sum()) == 0
+    lo, hi = 1000, 2024
+    part = run(X[lo:hi].contiguous(), y[lo:hi].contiguous(), hi - lo, lo)
+    for key in ("beta", "tau", "lambda"):
+        assert np.array_equal(full.store[key][lo:hi], part.store[key]), key
+    assert np.array_equal(full.store["log_post"][:, lo:hi], part.store["log_post"])
+    # the posterior mean of beta after 3 sweeps is already at the least-squares solution of its chain (noise sd 0.1)
+    err = np.abs(full.store["beta"][:, :, -1] - bt[:, :, 0].cpu().numpy()).max()
+    assert err < 0.05, err
