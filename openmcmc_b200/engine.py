@@ -65,22 +65,15 @@ class DevArray:
 def classify_matrix(m):
     """Structure of a (host) square matrix: returns (kind, main, off).  Host-side inspection of constant data."""
     if sparse.issparse(m):
-        m = m.tocoo()
+        m = m.tocsc(copy=True)        # canonical form: duplicates summed, explicit zeros dropped
+        m.sum_duplicates()
+        m.eliminate_zeros()
         n = m.shape[0]
-        offs = np.abs(m.row - m.col)
-        nz = m.data != 0
-        if np.all(offs[nz] == 0):
-            d = np.zeros(n)
-            np.add.at(d, m.row[nz], m.data[nz])
+        d = m.diagonal(0)
+        if m.nnz == np.count_nonzero(d):
             return ("eye", None, None) if np.all(d == 1.0) else ("diag", d, None)
-        if np.all(offs[nz] <= 1):
-            r, c, v = m.row[nz], m.col[nz], m.data[nz]
-            d = np.zeros(n)
-            e_lo = np.zeros(max(n - 1, 0))
-            e_up = np.zeros(max(n - 1, 0))
-            np.add.at(d, r[r == c], v[r == c])
-            np.add.at(e_lo, c[r == c + 1], v[r == c + 1])
-            np.add.at(e_up, r[c == r + 1], v[c == r + 1])
+        e_lo, e_up = m.diagonal(-1), m.diagonal(1)
+        if m.nnz == np.count_nonzero(d) + np.count_nonzero(e_lo) + np.count_nonzero(e_up):
             if not np.array_equal(e_lo, e_up):
                 raise NotImplementedError("non-symmetric tridiagonal precision matrix")
             return "tridiag", d, e_lo
