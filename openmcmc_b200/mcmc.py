@@ -202,6 +202,7 @@ class MCMC:
         for s in self.samplers:
             for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
                 owner.setdefault(name, s)
+        self._mask_padded_store_device()
         for name in self._store_names:
             s = owner[name]
             buf = K.download(self._dev_store[name][: self.n_iter])             # [n_iter, C, size]
@@ -210,7 +211,6 @@ class MCMC:
             if name == s.param:
                 arr = self._shape_store(s, arr, st[name])
             self.store[name] = arr[0] if C == 1 else arr
-        self._mask_padded_store()
         lp = K.download(self._dev_logpost[: self.n_iter])
         d2h += lp.nbytes
         self.store["log_post"] = lp.reshape(self.n_iter, 1) if C == 1 else lp
@@ -239,18 +239,22 @@ class MCMC:
             rj = next((s.rj for s in self.samplers if getattr(s, "rj", None) is not None), None)
         return rj
 
-    def _mask_padded_store(self):
+    def _mask_padded_store_device(self):
         """Variable-dimension parameters are stored at capacity n_max: entries beyond the stored count become NaN, the
-        layout `max_variable_size` gives the reference's store (sampler.py:69-118)."""
+        layout `max_variable_size` gives the reference's store (sampler.py:69-118).  Done on the device store
+        [n_iter, C, size] before the download (on the host it was a boolean-mask assignment over 6e7 elements per
+        parameter, most of the C5 collect time)."""
         rj = self._rj_sampler()
-        if rj is None or rj.param not in self.store:
+        if rj is None or rj.param not in self._dev_store:
             return
-        cnt = self.store[rj.param]                                  # [(C,) 1, n_iter]
-        for name in rj.extra_state_names():
-            if name in self.store:
-                a = self.store[name]
-                idx = np.arange(a.shape[-2]).reshape(-1, 1)
-                a[np.broadcast_to(idx >= cnt[..., :1, :], a.shape)] = np.nan
+        with torch.cuda.stream(self.stream):
+            cnt = self._dev_store[rj.param][: self.n_iter]                  # [n_iter, C, 1]
+            for name in rj.stored_state_names():
+                if name in self._dev_store:
+                    buf = self._dev_store[name][: self.n_iter]
+                    idx = torch.arange(buf.shape[-1], device=buf.device, dtype=buf.dtype).view(1, 1, -1)
+                    buf.masked_fill_(idx >= cnt, float("nan"))
+        self.stream.synchronize()
 
     def _trim_padded_state(self):
         """Final state of one chain in the reference's exact shapes (theta (1,n), beta (n,1), B (n_data,n))."""
