@@ -243,8 +243,9 @@ __device__ void model_grad_hess_warp(const omc_mh_model_t& m, int chain, const d
                                      double* H, int ldh, double* scratch) {
   const int lane = threadIdx.x & 31, n = m.n_elem;
   for (int i = lane; i < n; i += 32) g[i] = 0.0;
-  if (H)
-    for (int e = lane; e < n * n; e += 32) H[(e / n) * ldh + (e % n)] = 0.0;
+  if (H)   // row by row, lanes over the columns: no integer division by a run-time n
+    for (int r = 0; r < n; ++r)
+      for (int c = lane; c < n; c += 32) H[r * ldh + c] = 0.0;
   __syncwarp();
   for (int k = 0; k < m.n_terms; ++k) {
     const omc_term_t& t = m.terms[k];
@@ -663,11 +664,12 @@ __device__ bool mmala_params_warp(const omc_mmala_t& a, int chain, const double*
   __syncwarp();
   const double inv_s2 = 1.0 / (a.step * a.step);
   bool bad = false;
-  for (int e = lane; e < n * n; e += 32) {
-    const double v = Hm[(e / n) * ld + (e % n)] * inv_s2;
-    Hm[(e / n) * ld + (e % n)] = v;
-    if (isnan(v) || isinf(v)) bad = true;
-  }
+  for (int r = 0; r < n; ++r)
+    for (int c = lane; c < n; c += 32) {
+      const double v = Hm[r * ld + c] * inv_s2;
+      Hm[r * ld + c] = v;
+      if (isnan(v) || isinf(v)) bad = true;
+    }
   for (int i = lane; i < n; i += 32)
     if (isnan(g[i]) || isinf(g[i])) bad = true;
   __syncwarp();
@@ -745,6 +747,139 @@ __global__ void __launch_bounds__(MW_WARPS * 32) mmala_warp_kernel(omc_mmala_t a
     if (isnan(log_accept)) status |= isnan(lpc) ? OMC_STATUS_NAN : OMC_STATUS_OUT_OF_SUPPORT;
   }
   if (accept && lane < n) gth[lane] = prop[lane];
+  if (lane == 0) {
+    if (a.counters) {
+      a.counters[2 * (long long)chain] += accept ? 1 : 0;
+      a.counters[2 * (long long)chain + 1] += 1;
+    }
+    if (a.status && status) atomicOr(&a.status[chain], status);
+    if (a.probe_scalars) {
+      double* ps = a.probe_scalars + (long long)chain * 6;
+      ps[0] = lpc; ps[1] = lpp; ps[2] = lq; ps[3] = lqr; ps[4] = log_accept; ps[5] = accept ? 1.0 : 0.0;
+    }
+  }
+}
+
+// ---- ManifoldMALA on a model whose terms are all sums over elements (Poisson rate, Gamma / Uniform response, Normal
+// response with an identity or diagonal precision): the Hessian is DIAGONAL, so L = sqrt(diag), the two triangular
+// solves are two divisions, and the whole step of mmala_warp_kernel is O(n) per chain with one element per lane and no
+// matrix in shared memory.  Every expression is the one the dense path evaluates on that diagonal (its Cholesky of a
+// diagonal matrix takes the square roots and leaves exact zeros), so the chains are the same numbers.  C4a (Poisson
+// counts with a Gamma prior) is this case: 40k issued warp instructions per chain step became ~2k.
+constexpr int MD_WARPS = 8;
+
+// gradient (positive log-pdf) and Hessian diagonal (negative log-pdf) of element i at x; same expressions and the same
+// accumulation order over the terms as term_grad_hess_analytic
+__device__ __forceinline__ void elem_grad_hess(const omc_mh_model_t& m, int n, int chain, int i, double x, double& g,
+                                               double& h) {
+  g = 0.0;
+  h = 0.0;
+  for (int k = 0; k < m.n_terms; ++k) {
+    const omc_term_t& t = m.terms[k];
+    switch (t.kind) {
+      case OMC_TERM_POISSON_RATE: {
+        const double kk = vat(t.data, chain, i, 0.0);
+        g += kk / x - 1.0;
+        h += kk / (x * x);
+        break;
+      }
+      case OMC_TERM_GAMMA_RESPONSE: {
+        const double sh = vat(t.p1, chain, t.p1_len > 1 ? i : 0, 1.0), rt = vat(t.p2, chain, t.p2_len > 1 ? i : 0, 1.0);
+        g += (sh - 1.0) / x - rt;
+        h += (sh - 1.0) / (x * x);
+        break;
+      }
+      case OMC_TERM_NORMAL_RESPONSE: {
+        const double s = vat(t.scalar, chain, 0, 1.0);
+        const double pii = mat_at(t.mat_kind, t.P, chain, n, i, i);
+        const double q = pii * (x - vat(t.p1, chain, t.p1_len > 1 ? i : 0, 0.0));
+        h += s * pii;
+        g += -s * q;
+        break;
+      }
+      default:
+        break;   // Uniform: constant
+    }
+  }
+}
+
+// proposal parameters of element `lane` at x: L = sqrt(h / step^2), mu = x + 1/2 (g / L) / L; false (uniformly) when any
+// element is NaN / inf or has a non-positive pivot (what mmala_params_warp reports for the dense form)
+__device__ __forceinline__ bool mmala_params_diag(const omc_mmala_t& a, int n, int chain, int lane, double x, double& L,
+                                                  double& mu) {
+  double g = 0.0, h = 1.0;
+  if (lane < n) elem_grad_hess(a.model, n, chain, lane, x, g, h);
+  const double v = h * (1.0 / (a.step * a.step));
+  const bool bad = (lane < n) && (isnan(v) || isinf(v) || isnan(g) || isinf(g) || !(v > 0.0));
+  if (__any_sync(0xffffffffu, bad)) return false;
+  L = sqrt(v);
+  double x0 = g / L;
+  x0 = x0 / L;
+  mu = x + 0.5 * x0;
+  return true;
+}
+__device__ __forceinline__ double mmala_log_density_diag(int n, int lane, double L, double x, double mu) {
+  const double w0 = (lane < n) ? L * (x - mu) : 0.0;
+  const double ld_sum = omc_warp_sum((lane < n) ? log(L) : 0.0);
+  const double ww = omc_warp_sum(w0 * w0 + 0.0 * 0.0);
+  return ld_sum - 0.5 * ww;
+}
+
+__global__ void __launch_bounds__(MD_WARPS * 32) mmala_diag_kernel(omc_mmala_t a) {
+  extern __shared__ double sm[];
+  const int n = a.model.n_elem, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * MD_WARPS + warp;
+  if (chain >= a.model.n_chains) return;
+  double* cur = sm + (size_t)warp * 2 * n;     // model_logp_warp reads the states through memory
+  double* prop = cur + n;
+  double* gth = a.theta + (long long)chain * n;
+  const double xc = (lane < n) ? gth[lane] : 0.0;
+  if (lane < n) cur[lane] = xc;
+  __syncwarp();
+  const long long sw = a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll;
+  const OmcRng rng = to_rng(a.rng);
+  int status = 0;
+  double lpc = 0.0, lpp = 0.0, lq = 0.0, lqr = 0.0, L = 1.0, mu = 0.0, xp = 0.0;
+  bool ok = mmala_params_diag(a, n, chain, lane, xc, L, mu);
+  if (!ok) status |= OMC_STATUS_NOT_PD;
+  if (ok) {
+    double z = 0.0;
+    if (a.debug_z) {
+      if (lane < n) z = a.debug_z[sw * a.debug_sweep_stride_z + (long long)chain * n + lane];
+    } else if (lane < n) {
+      double z0, z1;
+      omc_normal2(rng, chain, lane >> 1, z0, z1);   // pair t holds elements 2t, 2t + 1
+      z = (lane & 1) ? z1 : z0;
+    }
+    xp = z / L + mu;
+    if (lane < n) prop[lane] = xp;
+    __syncwarp();
+    lq = mmala_log_density_diag(n, lane, L, xp, mu);
+    lpc = model_logp_warp(a.model, chain, cur);
+    lpp = model_logp_warp(a.model, chain, prop);
+    if (a.probe_mu && lane < n) a.probe_mu[(long long)chain * n + lane] = mu;
+    if (a.probe_prop && lane < n) a.probe_prop[(long long)chain * n + lane] = xp;
+    if (a.probe_L && lane < n)
+      for (int c = 0; c < n; ++c) a.probe_L[(long long)chain * n * n + lane * n + c] = (c == lane) ? L : 0.0;
+    double L2 = 1.0, mu2 = 0.0;
+    const bool ok2 = mmala_params_diag(a, n, chain, lane, xp, L2, mu2);
+    if (!ok2) { status |= OMC_STATUS_OUT_OF_SUPPORT; ok = false; }
+    else lqr = mmala_log_density_diag(n, lane, L2, xc, mu2);
+  }
+  bool accept = false;
+  double log_accept = nan("");
+  if (ok) {
+    double u;
+    if (a.debug_u) u = a.debug_u[sw * a.debug_sweep_stride_u + chain];
+    else {
+      uint4 b = omc_rng_block(rng, chain, 0xFFFFu);
+      u = omc_u01(b.x, b.y);
+    }
+    log_accept = lpp + lqr - (lpc + lq);
+    accept = log(u) < log_accept;
+    if (isnan(log_accept)) status |= isnan(lpc) ? OMC_STATUS_NAN : OMC_STATUS_OUT_OF_SUPPORT;
+  }
+  if (accept && lane < n) gth[lane] = xp;
   if (lane == 0) {
     if (a.counters) {
       a.counters[2 * (long long)chain] += accept ? 1 : 0;
@@ -837,6 +972,22 @@ int omc_mmala(const omc_mmala_t* a, void* stream) {
   OMC_REQUIRE(n <= 64, "omc_mmala: n_elem=%d > 64 is not supported", n);
   OMC_REQUIRE(a->step > 0.0, "omc_mmala: step=%g", a->step);
   const size_t smem = (size_t)(n * (n + 1) + 8 * n) * sizeof(double);
+  bool separable = (a->method == 0);   // analytic derivatives of a model whose terms are sums over elements
+  for (int k = 0; k < a->model.n_terms; ++k) {
+    const omc_term_t& t = a->model.terms[k];
+    separable = separable && (t.kind == OMC_TERM_POISSON_RATE || t.kind == OMC_TERM_GAMMA_RESPONSE ||
+                              t.kind == OMC_TERM_UNIFORM_RESPONSE ||
+                              (t.kind == OMC_TERM_NORMAL_RESPONSE && t.mat_kind != OMC_MAT_DENSE));
+  }
+#ifdef OMC_MMALA_NO_DIAG
+  separable = false;
+#endif
+  if (n <= 32 && separable) {   // diagonal Hessian: one element per lane, no matrix
+    const size_t smem_d = (size_t)MD_WARPS * 2 * n * sizeof(double);
+    mmala_diag_kernel<<<(a->model.n_chains + MD_WARPS - 1) / MD_WARPS, MD_WARPS * 32, smem_d, (cudaStream_t)stream>>>(*a);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
   if (n <= 32) {   // one warp per chain
     const size_t smem_w = smem * MW_WARPS;
     OMC_CHECK_CUDA(cudaFuncSetAttribute(mmala_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));

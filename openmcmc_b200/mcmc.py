@@ -18,6 +18,28 @@ from openmcmc_b200 import kernels as K
 from openmcmc_b200.model import Model
 
 
+class LazyHostArray:
+    """A final-state entry that stays on the device until somebody looks at it (`np.asarray`, indexing, `.shape`).
+
+    Used for the padded basis matrix of a multi-chain ReversibleJump run ([C, n_data, n_max]: 4.3 GB at the C5 size, a
+    quantity derived from knots and widths that most callers never read)."""
+
+    def __init__(self, fetch, shape):
+        self._fetch, self._value, self.shape = fetch, None, tuple(shape)
+        self.ndim, self.dtype = len(self.shape), np.dtype(np.float64)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._value is None:
+            self._value = self._fetch()
+        return self._value if dtype is None else self._value.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.__array__()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
 @dataclass
 class MCMC:
     """ref: mcmc.py:18-85.  For n_chains == 1 `store[param]` has the reference shape (size, n_iter); for n_chains > 1
@@ -219,8 +241,14 @@ class MCMC:
             d2h += h.nbytes
             arr = np.transpose(h, (1, 2, 0))
             self.store[response] = arr[0] if C == 1 else arr
+        rj = self._rj_sampler()
+        lazy = {rj.basis.matrix} if (rj is not None and rj.basis is not None and C > 1) else set()
         for s in self.samplers:
             for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
+                if name in lazy:     # derived from knots / widths: downloaded when somebody reads it
+                    arr = st.arrays[name]
+                    self.state[name] = LazyHostArray((lambda name=name: st.get_host(name)), arr.data.shape)
+                    continue
                 new = st.get_host(name)
                 self.state[name] = new
                 d2h += new.nbytes
