@@ -42,6 +42,21 @@ __device__ __forceinline__ double gamma_logpdf(double x, double shape, double ra
   return omc_xlogy(shape - 1.0, y) - y - lgamma(shape) + log(rate);
 }
 
+// CTA-wide loop over the elements (i, c) of a rows x cols block, element e = i * cols + c handled by thread e % RJ_NT in
+// the order e, e + RJ_NT, ...; (i, c) advance incrementally, so the loop costs ONE integer division per thread instead
+// of one per element (the run-time divisor made e / cols the most expensive instruction of these loops).
+template <class F>
+__device__ __forceinline__ void rj_for2d(int rows, int cols, F f) {
+  const int q = RJ_NT / cols, rr = RJ_NT - q * cols;
+  int i = threadIdx.x / cols, c = threadIdx.x - i * cols;
+  while (i < rows) {
+    f(i, c);
+    c += rr;
+    i += q;
+    if (c >= cols) { c -= cols; ++i; }
+  }
+}
+
 // In-place inverse of the SPD matrix A (m x m, row stride ld) by Gauss-Jordan without pivoting.  colv: m doubles of
 // scratch.  Returns false (uniformly) on a non-positive pivot.
 __device__ bool gj_inverse_spd(double* A, int m, int ld, double* colv) {
@@ -55,10 +70,9 @@ __device__ bool gj_inverse_spd(double* A, int m, int ld, double* colv) {
     const double ip = 1.0 / piv;
     for (int c = tid; c < m; c += RJ_NT) A[p * ld + c] = (c == p ? 1.0 : A[p * ld + c]) * ip;
     __syncthreads();
-    for (int e = tid; e < m * m; e += RJ_NT) {
-      const int i = e / m, c = e - i * m;
+    rj_for2d(m, m, [&](int i, int c) {
       if (i != p) A[i * ld + c] = (c == p ? 0.0 : A[i * ld + c]) - colv[i] * A[p * ld + c];
-    }
+    });
     __syncthreads();
   }
   return true;
@@ -103,10 +117,11 @@ __device__ double lu_logdet_solve(double* F, int m, int ld, double* rhs, int* pi
     for (int i = j + 1 + tid; i < m; i += RJ_NT) F[i * ld + j] /= d;
     __syncthreads();
     const int w = m - 1 - j;
-    for (int e = tid; e < w * w; e += RJ_NT) {
-      const int i = j + 1 + e / w, c = j + 1 + e % w;
-      F[i * ld + c] -= F[i * ld + j] * F[j * ld + c];
-    }
+    if (w > 0)
+      rj_for2d(w, w, [&](int ii, int cc) {
+        const int i = j + 1 + ii, c = j + 1 + cc;
+        F[i * ld + c] -= F[i * ld + j] * F[j * ld + c];
+      });
     if (rhs)
       for (int i = j + 1 + tid; i < m; i += RJ_NT) rhs[i] -= F[i * ld + j] * rhs[j];
     __syncthreads();
@@ -152,6 +167,7 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
   double* be = om + lv;                   // current coefficients
   double* bp = be + lv;                   // proposed coefficients (laid out on the LARGER basis)
   double* colv = bp + lv;
+  unsigned short* ptab = reinterpret_cast<unsigned short*>(colv + lv);   // (i, j) of every lower-triangle pair
   const int k = (int)a.n_basis[chain];
   if (cls >= 0 && a.size_class[chain] != cls) return;   // another launch of this step owns the chain
   double* thg = a.theta + (long long)chain * cap;
@@ -240,22 +256,28 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
     if (tid == 0) { th[k] = sh.theta_new; om[k] = sh.omega_new; }
   }
   for (int e = tid; e < m * ld; e += RJ_NT) A[e] = 0.0;
+  // pair index -> (i, j) of the lower triangle, decoded once per step (it was a double-precision square root per pair
+  // and per 16-row chunk)
+  const int npair = m * (m + 1) / 2;
+  for (int pi = tid; pi < npair; pi += RJ_NT) {
+    int i = (int)((sqrt(8.0 * pi + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= pi) ++i;
+    while (i * (i + 1) / 2 > pi) --i;
+    ptab[pi] = (unsigned short)((i << 8) | (pi - i * (i + 1) / 2));
+  }
   __syncthreads();
   // ---- pass 1 over the data rows: Gram matrix of the larger basis (lower triangle) and the current residual sum
+  //      (Prefetching the next chunk into registers while the current one is multiplied was tried and bought nothing:
+  //      the other resident CTAs already cover that latency.)
   double rss_c = 0.0;
-  const int npair = m * (m + 1) / 2;
   for (int r0 = 0; r0 < nd; r0 += RJ_ROWS) {
     const int rows = min(RJ_ROWS, nd - r0);
-    for (int e = tid; e < rows * m; e += RJ_NT) {
-      const int r_ = e / m, j = e - r_ * m;
+    rj_for2d(rows, m, [&](int r_, int j) {
       chunk[r_ * ld + j] = (j < k) ? Bg[(long long)(r0 + r_) * cap + j] : bnew[r0 + r_];
-    }
+    });
     __syncthreads();
     for (int pi = tid; pi < npair; pi += RJ_NT) {
-      int i = (int)((sqrt(8.0 * pi + 1.0) - 1.0) * 0.5);
-      while ((i + 1) * (i + 2) / 2 <= pi) ++i;
-      while (i * (i + 1) / 2 > pi) --i;
-      const int j = pi - i * (i + 1) / 2;
+      const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
       double s = 0.0;
       for (int r_ = 0; r_ < rows; ++r_) s = fma(chunk[r_ * ld + i], chunk[r_ * ld + j], s);
       A[i * ld + j] += s;
@@ -269,10 +291,7 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
     __syncthreads();
   }
   for (int pi = tid; pi < npair; pi += RJ_NT) {   // symmetrise, add the ridge
-    int i = (int)((sqrt(8.0 * pi + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= pi) ++i;
-    while (i * (i + 1) / 2 > pi) --i;
-    const int j = pi - i * (i + 1) / 2;
+    const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
     if (i == j) A[i * ld + i] += RJ_EPS;
     else A[j * ld + i] = A[i * ld + j];
   }
@@ -284,10 +303,7 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
     if (tid == 0 && a.counters) a.counters[(long long)chain * 2 + 1] += 1;
     return;
   }
-  for (int e = tid; e < m * m; e += RJ_NT) {
-    const int i = e / m, c = e - i * m;
-    A[i * ld + c] = (i == c ? 1.0 : 0.0) - RJ_EPS * A[i * ld + c];
-  }
+  rj_for2d(m, m, [&](int i, int c) { A[i * ld + c] = (i == c ? 1.0 : 0.0) - RJ_EPS * A[i * ld + c]; });
   __syncthreads();
   double logdetF;
   if (birth) {
@@ -459,7 +475,8 @@ int rj_check(const omc_rj_t* a, const char* who) {
 extern "C" {
 
 static int rj_smem_for_ld(int n_data, int n_max, int ld) {
-  return (ld * ld + RJ_ROWS * ld + n_data + 5 * (n_max + 1)) * 8;
+  const int pair_table_doubles = (ld * (ld + 1) / 2 * 2 + 7) / 8;   // 16-bit (i, j) per lower-triangle pair
+  return (ld * ld + RJ_ROWS * ld + n_data + 5 * (n_max + 1) + pair_table_doubles) * 8;
 }
 
 int omc_rj_smem_bytes(int n_data, int n_max) { return rj_smem_for_ld(n_data, n_max, n_max + 1); }

@@ -193,6 +193,20 @@ struct MalaShared {
   int ok;
 };
 
+// CTA-wide loop over the elements (i, c) of a rows x cols block in the order e = i * cols + c, e += RM_NT, with (i, c)
+// advanced incrementally: one integer division per thread instead of one per element (same helper as in rj.cu).
+template <class F>
+__device__ __forceinline__ void rm_for2d(int rows, int cols, F f) {
+  const int q = RM_NT / cols, rr = RM_NT - q * cols;
+  int i = threadIdx.x / cols, c = threadIdx.x - i * cols;
+  while (i < rows) {
+    f(i, c);
+    c += rr;
+    i += q;
+    if (c >= cols) { c -= cols; ++i; }
+  }
+}
+
 __global__ void __launch_bounds__(RM_NT) rj_coef_mmala_kernel(omc_rj_mmala_t m, int ld, int cls) {
   extern __shared__ __align__(16) double sm[];
   __shared__ MalaShared sh;
@@ -214,6 +228,7 @@ __global__ void __launch_bounds__(RM_NT) rj_coef_mmala_kernel(omc_rj_mmala_t m, 
   double* g = pr + ld;                   // gradient / work vector
   double* mu = g + ld;                   // proposal mean
   double* zv = mu + ld;
+  unsigned short* ptab = reinterpret_cast<unsigned short*>(zv + ld);   // (i, j) of every lower-triangle pair
   double* beg = a.beta + (long long)chain * cap;
   const double* Bg = a.B + (long long)chain * nd * cap;
   const double* yp = a.y.ptr ? a.y.ptr + (long long)chain * a.y.chain_stride : nullptr;
@@ -225,18 +240,19 @@ __global__ void __launch_bounds__(RM_NT) rj_coef_mmala_kernel(omc_rj_mmala_t m, 
   double rss_c = 0.0;
   if (yp) {
     const int npair = k * (k + 1) / 2;
+    for (int pi = tid; pi < npair; pi += RM_NT) {   // pair index -> (i, j), decoded once per step
+      int i = (int)((sqrt(8.0 * pi + 1.0) - 1.0) * 0.5);
+      while ((i + 1) * (i + 2) / 2 <= pi) ++i;
+      while (i * (i + 1) / 2 > pi) --i;
+      ptab[pi] = (unsigned short)((i << 8) | (pi - i * (i + 1) / 2));
+    }
+    __syncthreads();
     for (int r0 = 0; r0 < nd; r0 += RM_ROWS) {
       const int rows = min(RM_ROWS, nd - r0);
-      for (int e = tid; e < rows * k; e += RM_NT) {
-        const int r_ = e / k, j = e - r_ * k;
-        chunk[r_ * ld + j] = Bg[(long long)(r0 + r_) * cap + j];
-      }
+      rm_for2d(rows, k, [&](int r_, int j) { chunk[r_ * ld + j] = Bg[(long long)(r0 + r_) * cap + j]; });
       __syncthreads();
       for (int pi = tid; pi < npair; pi += RM_NT) {
-        int i = (int)((sqrt(8.0 * pi + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= pi) ++i;
-        while (i * (i + 1) / 2 > pi) --i;
-        const int j = pi - i * (i + 1) / 2;
+        const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
         double s = 0.0;
         for (int r_ = 0; r_ < rows; ++r_) s = fma(chunk[r_ * ld + i], chunk[r_ * ld + j], s);
         S[i * ld + j] += s;
@@ -254,10 +270,9 @@ __global__ void __launch_bounds__(RM_NT) rj_coef_mmala_kernel(omc_rj_mmala_t m, 
       }
       __syncthreads();
     }
-    for (int e = tid; e < k * k; e += RM_NT) {
-      const int i = e / k, j = e - i * k;
+    rm_for2d(k, k, [&](int i, int j) {
       if (j > i) S[i * ld + j] = S[j * ld + i];
-    }
+    });
     rss_c = omc_block_sum(rss_c, s_red);
   }
   __syncthreads();
@@ -273,10 +288,9 @@ __global__ void __launch_bounds__(RM_NT) rj_coef_mmala_kernel(omc_rj_mmala_t m, 
   __syncthreads();
   // ---- Hs = (tau_y S + tau_b I) / step^2, L = chol(Hs)   (metropolis_hastings.py:325-348)
   const double inv_s2 = 1.0 / (m.step * m.step);
-  for (int e = tid; e < k * k; e += RM_NT) {
-    const int i = e / k, j = e - i * k;
+  rm_for2d(k, k, [&](int i, int j) {
     S[i * ld + j] = ((yp ? tau_y * S[i * ld + j] : 0.0) + (i == j ? tau_b : 0.0)) * inv_s2;
-  }
+  });
   __syncthreads();
   const bool pd = omc_chol_block(S, k, ld);
   __syncthreads();
@@ -411,7 +425,7 @@ int omc_rj_coef_mmala(const omc_rj_mmala_t* m, void* stream) {
   if (int rc = rm_check(a, "omc_rj_coef_mmala")) return rc;
   OMC_REQUIRE(m->step > 0.0, "omc_rj_coef_mmala: step=%g", m->step);
   cudaStream_t st = (cudaStream_t)stream;
-  auto smem_for = [&](int ld) { return (ld * ld + RM_ROWS * ld + 6 * ld) * 8; };
+  auto smem_for = [&](int ld) { return (ld * ld + RM_ROWS * ld + 6 * ld + (ld * (ld + 1) / 2 * 2 + 7) / 8) * 8; };
   const int full = smem_for(a->n_max + 1);
   OMC_REQUIRE(smem_for(a->n_max <= 64 ? a->n_max + 1 : 65) <= 220 * 1024 && (a->n_max <= 64 || full <= 227 * 1024 || a->size_class),
               "omc_rj_coef_mmala: n_max=%d needs too much shared memory", a->n_max);

@@ -309,6 +309,8 @@ class MCMC:
             out = np.full((C,) + tuple(mvs) + (n_iter,), np.nan)
             out[:, : dev_arr.rows, : dev_arr.cols, :] = arr.reshape(C, dev_arr.rows, dev_arr.cols, n_iter)
             return out
+        if size == int(mvs):      # stored at capacity already (padded ReversibleJump state): nothing to pad
+            return arr
         out = np.full((C, int(mvs), n_iter), np.nan)
         out[:, :size, :] = arr
         return out
