@@ -85,8 +85,10 @@ class MCMC:
         self.timing = {}
 
     # ------------------------------------------------------------------ device pipeline
-    def prepare(self):
-        """Upload + compile + capture.  Returns self (idempotent)."""
+    def prepare(self, warm_up=True, wait=True):
+        """Upload + compile + capture.  Returns self (idempotent).  `warm_up=False` skips the eager pass in front of
+        the captures (for a plan whose kernels an earlier plan of this process has launched already: the chain blocks
+        after the first), `wait=False` leaves the prologue running on the engine's stream."""
         if self._prepared is not None:
             return self
         dev = K.init_device(self.device)
@@ -166,12 +168,14 @@ class MCMC:
             plan.valid = saved_valid
             self.plan = plan
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
-            self._warm_up(plan, st, sampled)
+            if warm_up:
+                self._warm_up(plan, st, sampled)
             self._sweep_graph = K.Graph.capture(lambda: [fn() for _, fn in sweep_ops])
             self._store_graph = K.Graph.capture(lambda: [fn() for _, fn in store_ops])
             for _, fn in prologue_ops:
                 fn()
-        self.stream.synchronize()
+        if wait:
+            self.stream.synchronize()
         self._prepared = st
         return self
 
@@ -344,17 +348,48 @@ class MCMC:
         C = self.n_chains
         bounds = [(C * b // B, C * (b + 1) // B) for b in range(B)]
         t0 = time.perf_counter()
-        subs = []
-        for lo, hi in bounds:
+        dev = torch.device("cuda", K.init_device(self.device))
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def per_chain(v):
+            return isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim == 3 and v.shape[0] == C
+
+        def stage(lo, hi):
+            """Queue the host->device copies of a block's pinned per-chain tensors on the copy stream.  The copies of
+            block k+1 are queued BEFORE the host turns to block k's plan, so the PCIe link never waits for Python."""
+            out, nbytes = {}, 0
+            with torch.cuda.stream(copy_stream):
+                for key, v in self.state.items():
+                    if per_chain(v) and isinstance(v, torch.Tensor) and not v.is_cuda and v.is_pinned():
+                        out[key] = v[lo:hi].to(dev, non_blocking=True)
+                        nbytes += out[key].numel() * out[key].element_size()
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return out, ev, nbytes
+
+        subs, staged_bytes, block_log = [], 0, []
+        staged = stage(*bounds[0])
+        for b, (lo, hi) in enumerate(bounds):
+            on_dev, ev, nbytes = staged
+            tb0 = time.perf_counter()
+            staged = stage(*bounds[b + 1]) if b + 1 < B else None
+            tb1 = time.perf_counter()
+            ev.synchronize()       # this block's inputs are in HBM; the next block's are on their way
+            tb2 = time.perf_counter()
+            staged_bytes += nbytes
             st = {}
             for key, v in self.state.items():
-                per_chain = isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim == 3 and v.shape[0] == C
-                st[key] = v[lo:hi] if per_chain else v
+                st[key] = on_dev[key] if key in on_dev else (v[lo:hi] if per_chain(v) else v)
             sub = MCMC(st, self.samplers, self.model, n_burn=self.n_burn, n_iter=self.n_iter, n_thin=self.n_thin,
-                       n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo)
-            sub.prepare()
-            sub.run_device()      # asynchronous: the next block's upload starts right away
+                       n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo,
+                       upload_blocks=1)
+            # the first block warms every kernel of the plan up (module load, local-memory pool) before its captures;
+            # the later blocks launch the same kernels and go straight to the capture, without waiting for the GPU
+            sub.prepare(warm_up=(b == 0), wait=(b == 0))
+            sub.run_device()      # asynchronous: the host goes on to the next block
             subs.append(sub)
+            block_log.append({"queue_next_s": round(tb1 - tb0, 4), "upload_wait_s": round(tb2 - tb1, 4),
+                              "plan_s": round(time.perf_counter() - tb2, 4)})
         t1 = time.perf_counter()
         for sub in subs:
             sub.stream.synchronize()
@@ -371,9 +406,9 @@ class MCMC:
         self.status = np.concatenate([sub.status for sub in subs])
         self._blocks = subs
         t3 = time.perf_counter()
-        self.timing = {"h2d_bytes": sum(sub.timing["h2d_bytes"] for sub in subs),
+        self.timing = {"h2d_bytes": staged_bytes + sum(sub.timing["h2d_bytes"] for sub in subs),
                        "d2h_bytes": sum(sub.timing["d2h_bytes"] for sub in subs),
-                       "stored_iterations": subs[0].timing["stored_iterations"], "upload_blocks": B,
+                       "stored_iterations": subs[0].timing["stored_iterations"], "upload_blocks": B, "blocks": block_log,
                        "prepare_s": t1 - t0, "sweeps_s": t2 - t1, "collect_s": t3 - t2}
 
     def run_mcmc(self):

@@ -70,7 +70,8 @@ def test_reg_pass_matches_oracle(C, n, p, weighted):
 
 
 @pytest.mark.parametrize("prior", ["eye", "diag", "dense"])
-@pytest.mark.parametrize("C,n,p", [(4, 500, 3), (3, 400, 64), (2, 100, 31)])
+@pytest.mark.parametrize("C,n,p", [(4, 500, 3), (3, 400, 64), (2, 100, 31), (2, 300, 45), (3, 200, 17), (5, 60, 8),
+                                   (2, 50, 1), (300, 130, 64)])
 def test_nn_dense_draw_injected_z(C, n, p, prior):
     import torch
 

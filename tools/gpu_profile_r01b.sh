@@ -12,6 +12,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_c2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"reg_pass_kernel|nn_dense_draw" -c 4 -s 2 -o gpurun_out/r01b_c2_full -f \
   python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c2.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_c4a.csv \
+  python bench.py --workload c4a --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_c4a.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_c5.csv \
+  python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_c5.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mmala" -c 1 -s 3 -o gpurun_out/r01b_mmala_diag -f \
+  python bench.py --workload c4a --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full_c4a.log 2>&1
 for r in gpurun_out/r01b_*.ncu-rep; do
   ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
   rm -f $r
