@@ -1,0 +1,102 @@
+"""GPU parity of the one-call `openmcmc_b200.gmrf` functions against numpy / scipy restatements
+of the reference's formulas (gmrf.py:29-61, 167-198, 269-348) with injected variates; tolerances of the north star
+(deterministic quantities rel 1e-10, draws with injected z 1e-9)."""
+
+import numpy as np
+import pytest
+from scipy import sparse, stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _alg25(Q, b, z):
+    """Rue & Held Alg. 2.5 in numpy: x = mu + L^-T z, mu = Q^-1 b (gmrf.py:167-198, 29-61)."""
+    Qd = Q.toarray() if sparse.issparse(Q) else np.asarray(Q)
+    L = np.linalg.cholesky(Qd)
+    mu = np.linalg.solve(L.T, np.linalg.solve(L, b))
+    return mu + np.linalg.solve(L.T, z)
+
+
+@pytest.mark.parametrize("p,kind", [(7, "dense"), (64, "dense"), (1, "dense"), (5, "diag"), (300, "tridiag"), (5000, "tridiag"),
+                                    (2500, "diag")])
+def test_sample_normal_canonical_matches_algorithm_2_5(p, kind):
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(p)
+    if kind == "dense":
+        A = rng.standard_normal((p, p))
+        Q = A @ A.T + p * np.eye(p)
+    elif kind == "diag":
+        Q = sparse.diags([rng.random(p) + 0.5], [0], format="csc")
+    else:
+        Q = (3.0 * gmrf.precision_irregular(np.cumsum(rng.exponential(size=p))) + sparse.identity(p) * 0.7).tocsc()
+    b = rng.standard_normal((p, 1))
+    z = rng.standard_normal((p, 1))
+    x = gmrf.sample_normal_canonical(b, Q=Q, z=z)
+    ref = _alg25(Q, b, z)
+    assert x.shape == (p, 1)
+    assert np.max(np.abs(x - ref)) <= 1e-9 * max(1.0, np.max(np.abs(ref)))
+    # sample_normal: mu + L^-T z, column per draw
+    Z = rng.standard_normal((p, 2))
+    mu = rng.standard_normal((p, 1))
+    xs = gmrf.sample_normal(mu, Q=Q, n=2, z=Z)
+    ref2 = mu + np.linalg.solve(np.linalg.cholesky(Q.toarray() if sparse.issparse(Q) else Q).T, Z)
+    assert xs.shape == (p, 2) and np.max(np.abs(xs - ref2)) <= 1e-9 * max(1.0, np.max(np.abs(ref2)))
+
+
+def test_free_running_draws_are_fresh_and_standardise():
+    from openmcmc_b200 import gmrf
+
+    p = 4000
+    Q = (2.0 * gmrf.precision_irregular(np.arange(p) * 0.5) + sparse.identity(p)).tocsc()
+    b = np.zeros((p, 1))
+    x1 = gmrf.sample_normal_canonical(b, Q=Q, seed=5)
+    x2 = gmrf.sample_normal_canonical(b, Q=Q, seed=5)
+    assert not np.array_equal(x1, x2)                    # successive calls advance the generator
+    L = np.linalg.cholesky(Q.toarray())
+    w = L.T @ x1                                          # L'x ~ N(0, I)
+    assert stats.kstest(w.ravel(), "norm").pvalue > 1e-3 and abs(w.std() - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("sparse_q", [False, True])
+def test_multivariate_normal_pdf_matches_scipy(sparse_q):
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(11)
+    p, n = (6, 5) if not sparse_q else (400, 3)
+    if sparse_q:
+        Q = (1.5 * gmrf.precision_irregular(np.cumsum(rng.exponential(size=p))) + 0.3 * sparse.identity(p)).tocsc()
+        Qd = Q.toarray()
+    else:
+        A = rng.standard_normal((p, p))
+        Q = Qd = A @ A.T + p * np.eye(p)
+    mu = rng.standard_normal((p, 1))
+    x = mu + rng.standard_normal((p, n))
+    ref = stats.multivariate_normal(mean=mu.ravel(), cov=np.linalg.inv(Qd)).logpdf(x.T)
+    got = gmrf.multivariate_normal_pdf(x, mu, Q, by_observation=True)
+    np.testing.assert_allclose(got, np.atleast_1d(ref), rtol=1e-10)
+    np.testing.assert_allclose(gmrf.multivariate_normal_pdf(x, mu, Q), np.sum(ref), rtol=1e-10)
+    with pytest.raises(np.linalg.LinAlgError):
+        gmrf.multivariate_normal_pdf(x[:3], mu[:3], -np.eye(3))
+
+
+def test_truncated_normal_functions_match_scipy():
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(2)
+    mean = rng.standard_normal(50) * 2
+    scale = rng.random(50) + 0.2
+    lower, upper = mean - rng.random(50) * 3, mean + rng.random(50) * 3
+    u = rng.random(50)
+    a, b = (lower - mean) / scale, (upper - mean) / scale
+    x = gmrf.truncated_normal_rv(mean, scale, lower, upper, u=u)
+    np.testing.assert_allclose(x, stats.truncnorm.ppf(u, a, b, loc=mean, scale=scale), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gmrf.truncated_normal_log_pdf(x, mean, scale, lower, upper),
+                               stats.truncnorm.logpdf(x, a, b, loc=mean, scale=scale), rtol=1e-10, atol=1e-12)
+    # one-sided (None = infinite), outside the support, free-running draws stay inside
+    lp = gmrf.truncated_normal_log_pdf(np.array([-1.0, 0.5]), 0.0, 1.0, 0.0, None)
+    assert lp[0] == -np.inf and np.isclose(lp[1], stats.truncnorm.logpdf(0.5, 0.0, np.inf))
+    d = gmrf.truncated_normal_rv(np.zeros(2000), np.ones(2000), -0.5, 2.0, seed=3)
+    assert d.shape == (2000,) and d.min() >= -0.5 and d.max() <= 2.0
+    assert stats.kstest(d, stats.truncnorm(-0.5, 2.0).cdf).pvalue > 1e-3
+    assert gmrf.truncated_normal_rv(0.0, 1.0, -1.0, 1.0, size=7, seed=1).shape == (7,)

@@ -123,3 +123,30 @@ def test_division_free_2d_loop_visits_every_element_once_in_flat_order(rows, col
                 i += 1
             e += nt
     assert np.all(seen == 1)
+
+
+def test_precision_builders_match_the_rw1_definition():
+    """gmrf.precision_irregular / precision_temporal (gmrf.py:351-411): diagonal 1/d_{i-1} + 1/d_i, off-diagonal -1/d_i,
+    sparse CSC or dense, a single location gives [[1]]; checked against the oracle's diagonals and the defining
+    property x' P x = sum (x_{i+1} - x_i)^2 / d_i."""
+    import pandas as pd
+
+    from openmcmc_b200 import gmrf
+    from oracle import gmrf as ogmrf
+
+    rng = np.random.default_rng(3)
+    s = np.cumsum(rng.exponential(size=40)) + 5.0
+    P = gmrf.precision_irregular(s)
+    assert sparse.issparse(P) and P.format == "csc" and P.shape == (40, 40)
+    d, e = ogmrf.precision_irregular_diagonals(s)
+    assert np.array_equal(P.diagonal(0), d) and np.array_equal(P.diagonal(1), e) and np.array_equal(P.diagonal(-1), e)
+    Pd = gmrf.precision_irregular(s.reshape(-1, 1), is_sparse=False)
+    assert isinstance(Pd, np.ndarray) and np.array_equal(Pd, P.toarray())
+    x = rng.standard_normal(40)
+    assert np.isclose(x @ (P @ x), np.sum(np.diff(x) ** 2 / np.diff(s)), rtol=1e-12)
+    assert np.allclose(P @ np.ones(40), 0.0, atol=1e-12)          # constants are in the null space (rank n - 1)
+    assert np.array_equal(gmrf.precision_irregular(np.array([2.5])), np.array([[1]]))
+    t = pd.date_range(start="2022-04-01T01:00:00", end="2022-04-01T01:01:00", periods=100)
+    Pt = gmrf.precision_temporal(t)
+    assert np.allclose(Pt.diagonal(1), -99.0 / 60.0) and np.isclose(Pt[0, 0], 99.0 / 60.0)
+    assert np.allclose(gmrf.precision_temporal(t, unit_length=60.0).diagonal(1), -99.0)
