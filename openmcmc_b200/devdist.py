@@ -141,6 +141,7 @@ def log_p_host(dist, state: dict, by_observation: bool = False):
 
     if by_observation:
         raise engine.PlanError("log_p(by_observation=True) is only used by MixtureAllocation (SURVEY.md §8 f2: next)")
+    (dist,), state, _ = engine.unreplicate([dist], state)
     plan, st = _one_chain_plan(state)
     out = plan.new(1)
     plan.ops = []
@@ -162,6 +163,7 @@ def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, metho
 
     if method not in ("fd", "analytic"):
         raise ValueError("method must be 'fd' (the reference's finite differences) or 'analytic'")
+    (dist,), state, _ = engine.unreplicate([dist], state, sampled=frozenset({param}))
     plan, st = _one_chain_plan(state, per_chain=(param,))
     shape = np.shape(state[param])
     if (isinstance(dist, Normal) and isinstance(dist.mean, LinearCombination) and param in dist.mean.form

@@ -33,13 +33,22 @@ def _run_ops(ops):
 def sample_once(sampler, state: dict, debug_draws: dict = None) -> dict:
     """ref: MCMCSampler.sample contract (sampler.py:57-67): returns the state with state[param] replaced."""
     dev = K.init_device()
+    from openmcmc_b200 import gmrf_plan
+    from openmcmc_b200.model import Model
+
+    user_state, user_model = state, sampler.model
+    dists, state, changed = engine.unreplicate(list(sampler.model.values()), state, frozenset({sampler.param}))
     st = engine.DeviceState(1, dev, state, per_chain_names={sampler.param})
     plan = engine.Plan(st, seed=_default_seed)
     plan.sweep_counter.fill_(next(_call_counter))
-    from openmcmc_b200 import gmrf_plan
-
-    gmrf_plan.discover(plan, state, list(sampler.model.values()))
-    sampler.compile(plan, state, debug_draws)
+    try:
+        if changed:   # replicated data response: compiled in its single-column form, the caller's objects stay as they are
+            sampler.model = Model(dists, response=getattr(user_model, "response", None))
+        gmrf_plan.discover(plan, state, list(sampler.model.values()))
+        sampler.compile(plan, state, debug_draws)
+    finally:
+        sampler.model = user_model
+    state = user_state
     _run_ops(plan.ops)
     torch.cuda.synchronize()
     status = int(plan.status.max().item())

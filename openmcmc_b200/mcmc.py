@@ -94,6 +94,25 @@ class MCMC:
         dev = K.init_device(self.device)
         C = self.n_chains
         sampled = {s.param for s in self.samplers}
+        # replicated data responses (y of shape (dim, n_rep)) are compiled in their single-column form
+        # (engine.unreplicate); the user's model, samplers and state come back unchanged after the run
+        user_model, user_sampler_models = self.model, [s.model for s in self.samplers]
+        dists, state_c, changed = engine.unreplicate(list(self.model.values()), self.state, frozenset(sampled))
+        if changed:
+            twin = {id(a): b for a, b in zip(self.model.values(), dists)}
+            self._rep_restore = {k: self.state.get(k) for k in state_c if state_c[k] is not self.state.get(k)}
+            self.state = state_c
+            self.model = Model(dists, response=self.model.response)
+            for s in self.samplers:
+                s.model = Model([twin.get(id(d), d) for d in s.model.values()], response=getattr(s.model, "response", None))
+        try:
+            return self._prepare(dev, C, sampled, warm_up, wait)
+        finally:
+            self.model = user_model
+            for s, m in zip(self.samplers, user_sampler_models):
+                s.model = m
+
+    def _prepare(self, dev, C, sampled, warm_up, wait):
         st = engine.DeviceState(C, dev, self.state, per_chain_names=sampled)
         self.stream = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
@@ -257,6 +276,11 @@ class MCMC:
                 self.state[name] = new
                 d2h += new.nbytes
         self._trim_padded_state()
+        for key, original in getattr(self, "_rep_restore", {}).items():   # the user's replicated arrays come back
+            if original is None:
+                self.state.pop(key, None)
+            else:
+                self.state[key] = original
         self.status = self.plan.status.cpu().numpy()
         self.timing["d2h_bytes"] = d2h
         self.timing["h2d_bytes"] = st.h2d_bytes

@@ -706,6 +706,41 @@ def rj_cases():
     }
 
 
+def replicated_case(dim, n_rep, seed, n_iter, scaled=False):
+    """The model of the reference's examples 1 and 2 (y of shape (dim, n_rep): replicates in columns, Identity mean):
+    log_p / gradient / Hessian at the start state, a RandomWalk chain and a NormalNormal chain on the mean."""
+    rng = np.random.default_rng(seed)
+    h_true = 160 + 10 * rng.standard_normal((dim, 1))
+    y = h_true + 12 * rng.standard_normal((dim, n_rep))
+    pdiag = 0.5 + rng.random(dim)
+    if scaled:
+        prec = ScaledMatrix(matrix="P", scalar="tau")
+        extra = {"P": sparse.diags([pdiag], [0], format="csc"), "tau": np.array(1 / 150, ndmin=2)}
+    else:
+        prec = "tau"
+        extra = {"tau": np.array(1 / 200, ndmin=2) if dim == 1 else np.diag(pdiag / 150)}
+    mdl = Model([Normal("y", mean="h", precision=prec), Normal("h", mean="mu", precision="lambda")])
+    state = {"y": y, "h": 200.0 * np.ones((dim, 1)), "mu": 160.0 * np.ones((dim, 1)),
+             "lambda": np.array(1 / 100, ndmin=2) if dim == 1 else np.eye(dim) / 100, **extra}
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    out = {"y": y, "h0": state0["h"], "mu": state0["mu"], "lam": np.asarray(state0["lambda"]), "pdiag": pdiag,
+           "tau": np.asarray(state0["tau"]), "scaled": np.array(int(scaled)), "logp0": np.array(mdl.log_p(state))}
+    g, H = mdl.grad_log_p(state, "h")
+    out["grad0"], out["hess0"] = np.asarray(g), np.asarray(H.todense() if sparse.issparse(H) else H)
+    with Streams(seed + 1) as s:
+        smp = RandomWalk("h", mdl, step=np.array([[4.0]]))
+        M = _run_ref({k: (v.copy() if hasattr(v, "copy") else v) for k, v in state0.items()}, [smp], mdl, n_iter)
+    out.update({"rw_z": s.stack("z").reshape(n_iter, dim), "rw_u": s.stack("u").ravel(), "rw_store_h": M.store["h"],
+                "rw_store_log_post": M.store["log_post"],
+                "rw_accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])})
+    with Streams(seed + 2) as s:
+        M = _run_ref({k: (v.copy() if hasattr(v, "copy") else v) for k, v in state0.items()}, [NormalNormal("h", mdl)],
+                     mdl, n_iter)
+    out.update({"nn_z": s.stack("z").reshape(n_iter, dim), "nn_store_h": M.store["h"],
+                "nn_store_log_post": M.store["log_post"]})
+    return out
+
+
 def main():
     cases = {
         "regression_n50_p3": regression_case(50, 3, 0, 6),
@@ -719,7 +754,7 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated"]
     if "regression" not in which:
         cases = {}
     if "mh" in which:
@@ -735,6 +770,10 @@ def main():
     if "rj_moves" in which:
         cases.update({"rjmoves_normal_n60_k5": rj_companion_case(41, 60, 5, 12, 6),
                       "rjmoves_null_n40_k3": rj_companion_case(42, 40, 3, 8, 5, response="null")})
+    if "replicated" in which:
+        cases.update({"replicated_d1_r5": replicated_case(1, 5, 51, 8),
+                      "replicated_d3_r7_scaled": replicated_case(3, 7, 52, 6, scaled=True),
+                      "replicated_d2_r4_diag": replicated_case(2, 4, 53, 6)})
     for name, d in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, {k: np.shape(v) for k, v in d.items() if k.startswith("store")})

@@ -353,3 +353,61 @@ def test_mmala_regression_free_running_matches_conjugate_posterior():
     se = sd / np.sqrt(draws.shape[1] / 2)
     assert np.all(np.abs(draws.mean(axis=1) - mean) < 5 * se), (draws.mean(axis=1), mean, se)
     assert np.all(np.abs(draws.std(axis=1) / sd - 1) < 0.15)
+
+
+# ------------------------------------------------------------------------------------------------ replicated responses
+def _replicated_model_state(g):
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import ScaledMatrix
+
+    dim = g["y"].shape[0]
+    if int(g["scaled"]):
+        prec = ScaledMatrix(matrix="P", scalar="tau")
+        extra = {"P": sparse.diags([g["pdiag"]], [0], format="csc"), "tau": g["tau"].copy()}
+    else:
+        prec, extra = "tau", {"tau": g["tau"].copy()}
+    mdl = Model([Normal("y", mean="h", precision=prec), Normal("h", mean="mu", precision="lambda")])
+    state = {"y": g["y"].copy(), "h": g["h0"].copy(), "mu": g["mu"].copy(), "lambda": g["lam"].copy(), **extra}
+    assert state["y"].shape[0] == dim
+    return mdl, state
+
+
+@pytest.mark.parametrize("name", ["replicated_d1_r5", "replicated_d3_r7_scaled", "replicated_d2_r4_diag"])
+def test_replicated_response_matches_reference(name):
+    """y of shape (dim, n_rep) with replicates in its columns and an Identity mean (the reference's examples 1 and 2;
+    distribution.py:8-10): log_p / gradient / Hessian at the start state (1e-10) and RandomWalk / NormalNormal chains on
+    the mean with the reference's variates injected (1e-9), recorded from the live reference.  The device path compiles
+    the single-column form (engine.unreplicate); the caller's model and state come back as they were."""
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.sampler.metropolis_hastings import RandomWalk
+    from openmcmc_b200.sampler.sampler import NormalNormal
+
+    g = _load(name)
+    dim, n_rep = g["y"].shape
+    mdl, state = _replicated_model_state(g)
+    np.testing.assert_allclose(mdl.log_p(state), float(g["logp0"]), rtol=1e-10)
+    gr, H = mdl.grad_log_p(state, "h")
+    np.testing.assert_allclose(gr, g["grad0"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(H, g["hess0"], rtol=1e-10, atol=1e-14)
+    n_iter = g["rw_store_h"].shape[1]
+    smp = RandomWalk("h", mdl, step=np.array([[4.0]]))
+    M = MCMC(state, [smp], model=mdl, n_burn=0, n_iter=n_iter, debug_draws={"h": {"z": g["rw_z"], "u": g["rw_u"]}})
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["h"], g["rw_store_h"], rtol=1e-9)
+    np.testing.assert_allclose(M.store["log_post"], g["rw_store_log_post"], rtol=1e-10)
+    assert smp.accept_rate.count == {"accept": int(g["rw_accept"][0]), "proposal": int(g["rw_accept"][1])}
+    assert M.state["y"].shape == (dim, n_rep) and not any(k.startswith("__replicates__") for k in M.state)
+    assert type(mdl["y"].mean).__name__ == "Identity" and smp.model["y"] is mdl["y"]
+    mdl, state = _replicated_model_state(g)
+    M = MCMC(state, [NormalNormal("h", mdl)], model=mdl, n_burn=0, n_iter=n_iter, debug_draws={"h": {"z": g["nn_z"]}})
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["h"], g["nn_store_h"], rtol=1e-9)
+    np.testing.assert_allclose(M.store["log_post"], g["nn_store_log_post"], rtol=1e-10)
+    # many chains at once share the replicated data
+    M = MCMC(state, [NormalNormal("h", mdl)], model=mdl, n_burn=50, n_iter=200, n_chains=64, seed=3)
+    M.run_mcmc()
+    prec = np.asarray(g["lam"]).reshape(-1)[0] + n_rep * (float(np.ravel(g["tau"])[0]) * (g["pdiag"][0] if int(g["scaled"]) else 1.0)
+                                                          if dim == 1 or int(g["scaled"]) else np.ravel(g["tau"])[0])
+    post_mean0 = (np.asarray(g["lam"]).reshape(-1)[0] * g["mu"][0, 0] + (prec - np.asarray(g["lam"]).reshape(-1)[0]) * g["y"][0].mean()) / prec
+    assert abs(M.store["h"][:, 0, :].mean() - post_mean0) < 5 * prec ** -0.5 / np.sqrt(64 * 200 / 4)
