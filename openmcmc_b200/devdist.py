@@ -7,6 +7,7 @@ location_scale.py:145-250.  Host logic only (shapes and matching); every value i
 
 import numpy as np
 import torch
+from scipy import sparse
 
 from openmcmc_b200 import engine
 from openmcmc_b200 import kernels as K
@@ -199,8 +200,61 @@ def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, metho
     return g
 
 
+_rvs_calls = 0
+
+
 def rvs_host(dist, state: dict, n: int = 1):
-    """Prior draws for parameters missing from the initial state (mcmc.py:78-80)."""
-    raise engine.PlanError(
-        f"{type(dist).__name__}.rvs on the device is not provided: give an initial value for '{dist.response}' in the "
-        "state (prior draws at start-up are outside the per-sweep hot path)")
+    """dist.rvs(state, n): p x n draws on the device -- the prior draws of parameters missing from the initial state
+    (mcmc.py:78-80) and the reference's stand-alone use.  Start-up only, never inside a sweep: Normal goes through the
+    Alg. 2.5 kernels (`gmrf.sample_normal`), Gamma through `omc_ng_draw` (Philox, Marsaglia-Tsang); Poisson, Uniform
+    and Categorical use torch's device generators as glue.  Parity unpinned (free-running variates).
+    ref: location_scale.py:252-272, distribution.py:263-278, 354-374, 444-458, 510-523"""
+    global _rvs_calls
+    from openmcmc_b200 import gmrf as G
+    from openmcmc_b200 import hostcalls
+    from openmcmc_b200.distribution.distribution import Categorical, Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.parameter import Identity, ScaledMatrix
+
+    _rvs_calls += 1
+    seed = hostcalls._default_seed * 1_000_003 + _rvs_calls
+    dev = torch.device("cuda", K.init_device())
+    col = lambda v: np.asarray(v, dtype=np.float64).reshape(-1, 1) if np.ndim(v) < 2 else np.asarray(v, dtype=np.float64)
+    if type(dist) is Normal:
+        if dist.domain_response_lower is not None or dist.domain_response_upper is not None:
+            raise engine.PlanError("rvs of a truncated Normal is not provided: give an initial value in the state")
+        mean = col(dist.mean.predictor(state))
+        if isinstance(dist.precision, ScaledMatrix):
+            Q = state[dist.precision.matrix] * float(np.asarray(state[dist.precision.scalar]).item())
+        elif isinstance(dist.precision, Identity):
+            Q = state[dist.precision.form]
+        else:
+            raise engine.PlanError("rvs of a Normal with a mixture precision is not provided")
+        Q = Q if sparse.issparse(Q) else np.atleast_2d(np.asarray(Q, dtype=np.float64))
+        return G.sample_normal(mean[:, :1], Q=Q, n=n, seed=seed)
+    if type(dist) is Gamma:
+        shape, rate = col(dist.shape.predictor(state)), col(dist.rate.predictor(state))
+        p = max(shape.shape[0], rate.shape[0])
+        a0 = torch.as_tensor(shape.reshape(-1)).to(dev)
+        b0 = torch.as_tensor(rate.reshape(-1)).to(dev)
+        out = torch.empty(n, p, dtype=torch.float64, device=dev)
+        sweep = torch.full((1,), _rvs_calls, dtype=torch.int64, device=dev)
+        K.ng_draw(n, K.vec(a0, 0), K.vec(b0, 0), K.vec(None), K.vec(None), out, K.rng(seed=seed, sweep=sweep, site=1),
+                  n_elem=p, a0_len=a0.numel(), b0_len=b0.numel())
+        torch.cuda.synchronize()
+        return out.cpu().numpy().T.copy()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    if type(dist) is Poisson:
+        rate = torch.as_tensor(col(dist.rate.predictor(state))).to(dev)
+        return torch.poisson(rate.expand(rate.shape[0], n).contiguous(), generator=gen).cpu().numpy()
+    if type(dist) is Uniform:
+        lo, hi = dist.domain_response_lower, dist.domain_response_upper
+        p = np.shape(state[dist.response])[0] if dist.response in state else max(lo.shape[0], hi.shape[0])
+        u = torch.rand(p, n, dtype=torch.float64, device=dev, generator=gen).cpu().numpy()
+        return lo + (hi - lo) * u
+    if type(dist) is Categorical:
+        prob = torch.as_tensor(col(dist.prob.predictor(state))).to(dev)
+        return torch.multinomial(prob, n, replacement=True, generator=gen).to(torch.float64).cpu().numpy()
+    raise engine.PlanError(f"{type(dist).__name__}.rvs on the device is not provided: give an initial value for "
+                           f"'{dist.response}' in the state")

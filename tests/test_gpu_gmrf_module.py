@@ -100,3 +100,47 @@ def test_truncated_normal_functions_match_scipy():
     assert d.shape == (2000,) and d.min() >= -0.5 and d.max() <= 2.0
     assert stats.kstest(d, stats.truncnorm(-0.5, 2.0).cdf).pvalue > 1e-3
     assert gmrf.truncated_normal_rv(0.0, 1.0, -1.0, 1.0, size=7, seed=1).shape == (7,)
+
+
+def test_distribution_rvs_and_missing_initial_values():
+    """dist.rvs(state, n) (p x n draws; location_scale.py:252-272, distribution.py:263-278, 354-374, 444-458, 510-523) and
+    the start-up draw of a sampled parameter that is missing from the initial state (mcmc.py:78-80).  Free-running
+    variates: checked in distribution (KS / moments)."""
+    from openmcmc_b200.distribution.distribution import Categorical, Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    rng = np.random.default_rng(4)
+    g = Gamma("tau", shape="a", rate="b")
+    x = g.rvs({"a": np.array([[3.0]]), "b": np.array([[2.0]])}, n=4000)
+    assert x.shape == (1, 4000) and stats.kstest(x.ravel(), stats.gamma(3.0, scale=0.5).cdf).pvalue > 1e-3
+    xv = g.rvs({"a": np.array([[2.0], [5.0]]), "b": np.array([[1.0]])}, n=3000)
+    assert xv.shape == (2, 3000) and abs(xv[0].mean() - 2.0) < 0.15 and abs(xv[1].mean() - 5.0) < 0.2
+    nm = Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam"))
+    st = {"mu": np.array([[1.0], [-2.0], [0.5]]), "P": sparse.diags([[1.0, 4.0, 0.25]], [0], format="csc"), "lam": 4.0}
+    b = nm.rvs(st, n=400)
+    assert b.shape == (3, 400) and np.all(np.abs(b.mean(axis=1) - st["mu"].ravel()) < 0.25)
+    assert np.allclose(b.std(axis=1), [0.5, 0.25, 1.0], rtol=0.2)
+    k = Poisson("k", rate="r").rvs({"r": np.array([[2.0], [9.0]])}, n=3000)
+    assert k.shape == (2, 3000) and np.all(k == np.floor(k)) and abs(k[0].mean() - 2.0) < 0.15 and abs(k[1].mean() - 9.0) < 0.3
+    u = Uniform("x", domain_response_lower=np.array([[-1.0]]), domain_response_upper=np.array([[3.0]])).rvs(
+        {"x": np.zeros((2, 1))}, n=2000)
+    assert u.shape == (2, 2000) and u.min() >= -1.0 and u.max() <= 3.0 and abs(u.mean() - 1.0) < 0.1
+    z = Categorical("z", prob="pr").rvs({"pr": np.array([[0.2, 0.8], [0.9, 0.1]])}, n=2000)
+    assert z.shape == (2, 2000) and abs(z[0].mean() - 0.8) < 0.05 and abs(z[1].mean() - 0.1) < 0.05
+    # a sampled parameter without an initial value is drawn from its prior (mcmc.py:78-80)
+    n, p = 60, 3
+    X = rng.standard_normal((n, p))
+    y = X @ np.array([[1.0], [-1.0], [0.5]]) + 0.1 * rng.standard_normal((n, 1))
+    mdl = Model([Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
+                 Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+                 Gamma("tau", shape="a_tau", rate="b_tau")])
+    state = {"y": y, "X": X, "P_tau": sparse.identity(n, format="csc"), "P_lambda": sparse.identity(p, format="csc"),
+             "mu": np.zeros((p, 1)), "lambda": 0.01, "a_tau": 1.0, "b_tau": 1.0}
+    M = MCMC(state, [NormalNormal("beta", mdl), NormalGamma("tau", mdl)], model=mdl, n_burn=20, n_iter=50, n_thin=2)
+    assert M.state["beta"].shape == (p, 1) and M.state["tau"].shape == (1, 1) and M.state["tau"][0, 0] > 0
+    M.run_mcmc()
+    assert np.all(np.abs(M.store["beta"].mean(axis=1) - [1.0, -1.0, 0.5]) < 0.1)
