@@ -112,9 +112,11 @@ class RandomWalk(MetropolisHastings):
         theta = st[self.param]
         p_dim, n_rep = theta.rows, theta.cols
         loop = self._loop
-        if loop and self.domain_limits is None and n_rep > 1:
-            # the reference raises here as well: the full-shape normal cannot be assigned to one column
-            raise ValueError(f"could not broadcast input array from shape ({p_dim},{n_rep}) into shape ({p_dim},)")
+        if loop and self.domain_limits is None and (n_rep > 1 or p_dim > 1):
+            # the reference raises here as well (metropolis_hastings.py:250,262): column mu of shape (p_dim,)
+            # plus a full-shape normal (p_dim, n_rep) cannot be assigned back into one column unless both are 1
+            shape = (p_dim, n_rep) if n_rep > 1 else (p_dim, p_dim)
+            raise ValueError(f"could not broadcast input array from shape {shape} into shape ({p_dim},)")
         n_steps = n_rep if loop else 1
         p_prop = p_dim if loop else p_dim * n_rep
         model, _ = devdist.build_terms(plan, host_state, self.model, self.param)
