@@ -141,16 +141,33 @@ def sample_normal(mu, Q=None, L=None, n: int = 1, z=None, seed: int = 0):
 
 def multivariate_normal_pdf(x, mu, Q, by_observation: bool = False):
     """Log-density of N(mu, Q^-1) at the columns of x (dim x n): 1/2 (log|Q| - dim log 2 pi - |L'(x - mu)|^2); summed
-    over the observations unless `by_observation`.  log|Q| comes from the device factorisation, the quadratic form
-    (x - mu)' Q (x - mu) = |L'(x - mu)|^2 from a host product with the constant Q.  ref: gmrf.py:321-348"""
+    over the observations unless `by_observation`.  log|Q| comes from the device factorisation, the quadratic forms
+    (x - mu)' Q (x - mu) = |L'(x - mu)|^2 from `omc_quadform` / `omc_tridiag_matvec`.  ref: gmrf.py:321-348"""
     x = np.asarray(x, dtype=np.float64)
     x = x.reshape(-1, 1) if x.ndim == 1 else x
     mu = np.asarray(mu, dtype=np.float64).reshape(-1, 1)
-    dim = x.shape[0]
+    dim, n_obs = x.shape
     _, _, logdet = _factor_and_solve(Q, None, np.zeros(dim), 0, want_logdet=True)
-    r = x - mu
-    quad = np.sum(r * (Q @ r), axis=0)
-    log_p = 0.5 * (logdet - dim * np.log(2.0 * np.pi) - np.asarray(quad).reshape(-1))
+    # quadratic forms (x_r - mu)' Q (x_r - mu) on the device, one observation per "chain" of the kernel
+    dev = _dev()
+    kind, main, off = classify_matrix(Q)
+    xd, mud = _t(x.T, dev), _t(mu.reshape(-1), dev)                 # [n_obs, dim], [dim]
+    quad = torch.empty(n_obs, dtype=torch.float64, device=dev)
+    if kind == "tridiag":
+        r = (xd - mud).contiguous()
+        Qr = torch.empty_like(r)
+        K.tridiag_matvec(_t(main, dev), _t(off, dev), K.vec(r, dim), n_obs, dim, Qr)
+        quad = (r * Qr).sum(dim=1)
+    else:
+        cnt = torch.empty(n_obs, dtype=torch.float64, device=dev)
+        if kind == "eye":
+            K.quadform(n_obs, dim, K.vec(xd, dim), K.vec(mud, 0), K.MAT_EYE, K.vec(None), quad, cnt)
+        elif kind == "diag":
+            K.quadform(n_obs, dim, K.vec(xd, dim), K.vec(mud, 0), K.MAT_DIAG, K.vec(_t(main, dev), 0), quad, cnt)
+        else:
+            K.quadform(n_obs, dim, K.vec(xd, dim), K.vec(mud, 0), K.MAT_DENSE, K.vec(_t(np.asarray(main), dev), 0), quad, cnt)
+    torch.cuda.synchronize()
+    log_p = 0.5 * (logdet - dim * np.log(2.0 * np.pi) - quad.cpu().numpy().reshape(-1))
     return log_p if by_observation else np.sum(log_p)
 
 
