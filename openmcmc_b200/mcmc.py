@@ -407,9 +407,10 @@ class MCMC:
             sub = MCMC(st, self.samplers, self.model, n_burn=self.n_burn, n_iter=self.n_iter, n_thin=self.n_thin,
                        n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo,
                        upload_blocks=1)
-            # the first block warms every kernel of the plan up (module load, local-memory pool) before its captures;
-            # the later blocks launch the same kernels and go straight to the capture, without waiting for the GPU
-            sub.prepare(warm_up=(b == 0), wait=(b == 0))
+            # every block keeps the eager warm-up pass in front of its captures: skipping it for the later blocks
+            # bought nothing (the host waits behind the next block's transfer anyway) and a capture can be
+            # invalidated by the first-time allocations of a block with a different chain count
+            sub.prepare()
             sub.run_device()      # asynchronous: the host goes on to the next block
             subs.append(sub)
             block_log.append({"queue_next_s": round(tb1 - tb0, 4), "upload_wait_s": round(tb2 - tb1, 4),
