@@ -568,16 +568,26 @@ def run_b200(args, wl, key):
         except Exception:
             pass
         mdl, samplers2, hstate = build(wl, Ce, n, dev, rank, host=True)
-        barrier()
-        t0 = time.perf_counter()
-        M2 = MCMC(hstate, samplers2, model=mdl, n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter,
-                  n_thin=thin, n_chains=Ce, seed=7, device=local, chain_offset=rank * C,
-                  upload_blocks=args.upload_blocks)
         import contextlib
         import io
 
-        with contextlib.redirect_stdout(io.StringIO()):
-            M2.run_mcmc()
+        def e2e_run(blocks, first=True):
+            if first:
+                barrier()
+            else:               # a retry on one rank must not wait on a collective the other ranks have passed
+                torch.cuda.synchronize()
+            t_start = time.perf_counter()
+            run = MCMC(hstate, samplers2, model=mdl, n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter,
+                       n_thin=thin, n_chains=Ce, seed=7, device=local, chain_offset=rank * C, upload_blocks=blocks)
+            with contextlib.redirect_stdout(io.StringIO()):
+                run.run_mcmc()
+            return run, t_start
+
+        try:
+            M2, t0 = e2e_run(args.upload_blocks)
+        except Exception as exc:   # never lose the whole line to the e2e leg: one more try as a single block, and say so
+            e2e_note += f" [first e2e attempt failed ({type(exc).__name__}: {str(exc)[:120]}); re-run with upload_blocks=1]"
+            M2, t0 = e2e_run(1, first=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
