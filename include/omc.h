@@ -82,7 +82,8 @@ int omc_reg_rss(const double* X, long long strideX, const double* y, long long s
                 long long strideW, const double* beta, long long strideB, int n_chains, int n, int p,
                 double* stats, double* workspace, void* stream);
 
-/* omc_nn_dense_draw: NormalNormal conditional draw for a dense p x p posterior precision (p <= 64)
+/* omc_nn_dense_draw: NormalNormal conditional draw for a dense p x p posterior precision (p <= 512; p <= 32 one
+ *   thread per column in registers, above that a blocked Cholesky with a DMMA trailing update)
  *   Q = lambda*P0 + tau*G ; b = lambda*P0*mu0 + tau*g ; L = chol(Q) ; mu = L^-T L^-1 b ; beta = mu + L^-T z
  *   ref: sampler.py:154-207 (NormalNormal.sample), gmrf.py:167-198 (sample_normal_canonical), gmrf.py:29-61 */
 typedef struct {
@@ -111,8 +112,48 @@ typedef struct {
   int trunc_lo_len, trunc_hi_len;
   const double* debug_u; /* injected uniforms behind truncnorm.rvs [n_chains][p]; NULL => Philox; strided by
                             debug_sweep_stride like debug_z                                   */
+  /* Re-centred sufficient statistics: with the per-chain centre record  beta_hat [p] | c0 = X'W(y - X beta_hat) [p] |
+   * rss0 = (y - X beta_hat)'W(y - X beta_hat)  (chain_stride >= 2p+1) the draw also writes
+   *   rss(beta) = rss0 - 2 d'c0 + d'G d,  d = beta - beta_hat,
+   * to rss_out[chain * stats.chain_stride]: the residual sum of squares NormalGamma.sample and log_post need
+   * (sampler.py:275-284, mcmc.py:108) without a pass over X.  No cancellation when beta_hat is the least-squares
+   * point (c0 ~ 0, both remaining terms >= 0).  NULL => not written. */
+  omc_vec_t center;
+  double* rss_out;
+  int mode;             /* 0: draw; 1: solve only: beta = (Q with diag *= 1 + ridge_rel)^-1 b, no z, no status bit (a
+                           non-PD matrix gives beta = 0): how the prologue gets the centre beta_hat              */
+  double ridge_rel;
+  double* workspace;    /* p above the shared-memory limit (see omc_nn_dense_workspace): scratch for the factor   */
 } omc_nn_dense_t;
 int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream);
+/* doubles of workspace omc_nn_dense_draw / omc_dense_factor need for n_chains matrices of size p (0 while the augmented
+ * matrix fits in shared memory, p <= 136) */
+int omc_nn_dense_workspace(int n_chains, int p, long long* doubles);
+
+/* omc_dense_factor: stand-alone dense SPD factorisation and solves, one CTA per matrix (n <= 512), the blocked Cholesky
+ * with the DMMA trailing update that omc_nn_dense_draw runs:
+ *   L = chol(Q)                              ref: gmrf.py:465-486 (cholesky), 489-520 (sparse_cholesky, dense branch)
+ *   logdet = 2 sum log L_jj                  ref: gmrf.py:321-348 (multivariate_normal_pdf)
+ *   mean = L^-T L^-1 b                       ref: gmrf.py:437-462 (cho_solve)
+ *   x = mean + L^-T z                        ref: gmrf.py:167-198 (sample_normal_canonical), 29-61 (sample_normal),
+ *                                                 414-434 (solve(L.T, z): b = NULL)
+ *   factored = 1: Q already holds a lower Cholesky factor L (gmrf functions that accept a precomputed L)
+ *   backward_only = 1: mean = L^-T b (no forward solve) */
+typedef struct {
+  int n_mats, n;
+  const double* Q;      /* [n_mats][n*n] row-major (lower triangle read), matrices Q_stride doubles apart (0 = shared) */
+  long long Q_stride;
+  const double* b;      /* optional [n_mats][n] */
+  const double* z;      /* optional [n_mats][n] */
+  double* L;            /* optional out [n_mats][n*n] lower factor, zeros above the diagonal */
+  double* logdet;       /* optional out [n_mats] */
+  double* mean;         /* optional out [n_mats][n] */
+  double* x;            /* optional out [n_mats][n] */
+  int* status;          /* optional [n_mats], OR-ed with OMC_STATUS_NOT_PD */
+  int factored, backward_only;
+  double* workspace;    /* omc_nn_dense_workspace(n_mats, n) doubles when that is > 0 */
+} omc_dense_factor_t;
+int omc_dense_factor(const omc_dense_factor_t* args, void* stream);
 
 /* omc_quadform: ss = (x-mu)' P (x-mu), cnt = #(diag P > 0) per chain  (ref: sampler.py:276-284 for a prior precision) */
 typedef struct {

@@ -59,7 +59,20 @@ class NNDense(C.Structure):
         ("trunc_lo_len", C.c_int),
         ("trunc_hi_len", C.c_int),
         ("debug_u", C.c_void_p),
+        ("center", Vec),
+        ("rss_out", C.c_void_p),
+        ("mode", C.c_int),
+        ("ridge_rel", C.c_double),
+        ("workspace", C.c_void_p),
     ]
+
+
+class DenseFactor(C.Structure):
+    """omc_dense_factor_t"""
+
+    _fields_ = [("n_mats", C.c_int), ("n", C.c_int), ("Q", C.c_void_p), ("Q_stride", C.c_longlong), ("b", C.c_void_p),
+                ("z", C.c_void_p), ("L", C.c_void_p), ("logdet", C.c_void_p), ("mean", C.c_void_p), ("x", C.c_void_p),
+                ("status", C.c_void_p), ("factored", C.c_int), ("backward_only", C.c_int), ("workspace", C.c_void_p)]
 
 
 class Quadform(C.Structure):
@@ -187,7 +200,7 @@ class TridiagNN(C.Structure):
                 ("status", C.c_void_p), ("workspace", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"omc_tridiag_nn_t": TridiagNN}
+EXTRA_STRUCTS = {"omc_tridiag_nn_t": TridiagNN, "omc_dense_factor_t": DenseFactor}
 
 # name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
 PROTOTYPES = {
@@ -215,6 +228,8 @@ PROTOTYPES = {
          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "omc_nn_dense_draw": (C.c_int, [C.POINTER(NNDense), C.c_void_p]),
+    "omc_nn_dense_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "omc_dense_factor": (C.c_int, [C.POINTER(DenseFactor), C.c_void_p]),
     "omc_quadform": (C.c_int, [C.POINTER(Quadform), C.c_void_p]),
     "omc_ng_draw": (C.c_int, [C.POINTER(NGDraw), C.c_void_p]),
     "omc_logp_normal_ss": (C.c_int, [C.POINTER(LogpNormalSS), C.c_void_p]),

@@ -2,18 +2,20 @@
 //   omc_nn_dense_draw : Q = lambda*P0 + tau*G, Cholesky, posterior mean, MVN draw  (Rue & Held Alg. 2.5)
 //   omc_quadform      : (x-mu)' P (x-mu) and #(diag P > 0)
 //   omc_ng_draw       : Gamma(a0 + cnt/2, b0 + ss/2) draw
-// One CTA per chain for the p x p work (matrix resident in shared memory, p <= 64); one thread per chain for the
-// scalar Gamma draw.  These are latency-bound and account for a few % of a C2 sweep (profiles/), the pass in
-// reg_pass.cu is the roofline kernel.
+// p <= 32: one thread per COLUMN of Q with the column in registers (nn_dense_draw_kernel below); above that the blocked
+// Cholesky with the DMMA trailing update of dense_blocked.cu.  One thread per chain for the scalar Gamma draw.  With the
+// re-centred statistics (omc_nn_dense_t.center) the draw also leaves rss(beta) in the record, so a steady-state C2
+// sweep is these latency-bound kernels alone: no pass over X.
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"
 #include "omc_special.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int DD_THREADS = 256;
-constexpr int PMAX = 64;
+constexpr int PMAX = 512;
 
 __device__ __forceinline__ double vec_at(const omc_vec_t& v, int chain, int i, double dflt) {
   return v.ptr ? v.ptr[(long long)chain * v.chain_stride + i] : dflt;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__((PR < 32 ? 32 : PR), (PR == 64 ? 5 : (PR == 32
       col[i] = q;
     }
     if (live) diag = lam * mat_at(a.prior_kind, a.prior_P, chain, p, c, c) + tau * gcol[c * p];
+    if (a.mode == 1) diag *= 1.0 + a.ridge_rel;
   }
   if (a.probe_Q && live) {
     for (int i = 0; i < p; ++i)
@@ -168,7 +171,9 @@ __global__ void __launch_bounds__((PR < 32 ? 32 : PR), (PR == 64 ? 5 : (PR == 32
     if (a.probe_b) a.probe_b[(long long)chain * p + c] = bc;
     // z: injected or Philox / Box-Muller (pair t = elements 2t, 2t+1; both threads of a pair draw it)
     double zc;
-    if (a.debug_z) {
+    if (a.mode == 1) {
+      zc = 0.0;
+    } else if (a.debug_z) {
       zc = a.debug_z[(a.rng.sweep ? (long long)(*a.rng.sweep) : 0ll) * a.debug_sweep_stride + (long long)chain * p + c];
     } else {
       double z0, z1;
@@ -233,6 +238,10 @@ __global__ void __launch_bounds__((PR < 32 ? 32 : PR), (PR == 64 ? 5 : (PR == 32
   }
   __syncthreads();
   if (s_bad) {
+    if (a.mode == 1) {      // the centre of the re-centred statistics may be any point: fall back to the origin
+      if (live) a.beta[(long long)chain * p + c] = 0.0;
+      return;
+    }
     if (c == 0 && a.status) atomicOr(&a.status[chain], OMC_STATUS_NOT_PD);
     if (live) a.beta[(long long)chain * p + c] = nan("");
     return;
@@ -259,17 +268,32 @@ __global__ void __launch_bounds__((PR < 32 ? 32 : PR), (PR == 64 ? 5 : (PR == 32
   if (warp == 0) backsolve(sw);
   if (warp == NT / 32 - 1) backsolve(sz);
   __syncthreads();
+  const double* cen = a.center.ptr ? a.center.ptr + (long long)chain * a.center.chain_stride : nullptr;
   if (live) {
     const double m = sw[c];
     if (a.probe_mu) a.probe_mu[(long long)chain * p + c] = m;
-    a.beta[(long long)chain * p + c] = m + sz[c];
+    const double bnew = a.mode == 1 ? m : m + sz[c];
+    a.beta[(long long)chain * p + c] = bnew;
+    if (cen) sraw[c] = bnew - cen[c];
+  }
+  if (cen && a.rss_out) {
+    // rss(beta) = rss0 - 2 d'c0 + d'G d from the centre record (omc.h); G is symmetric: (G d)_c from coalesced rows
+    __syncthreads();
+    double acc = 0.0;
+    if (live) {
+      double gd = 0.0;
+      for (int r = 0; r < p; ++r) gd = fma(rec[r * p + c], sraw[r], gd);
+      acc = sraw[c] * (gd - 2.0 * cen[p + c]);
+    }
+    const double total = omc_block_sum(acc, sraw + PR);
+    if (c == 0) a.rss_out[(long long)chain * a.stats.chain_stride] = cen[2 * p] + total;
   }
 }
 
 template <int PR>
 int launch_dense_draw(const omc_nn_dense_t& a, cudaStream_t st) {
   constexpr int NT = PR < 32 ? 32 : PR;
-  const size_t smem = (size_t)(PR * (PR + 2) + 5 * PR) * sizeof(double);
+  const size_t smem = (size_t)(PR * (PR + 2) + 5 * PR + 32) * sizeof(double);
   nn_dense_draw_kernel<PR><<<a.n_chains, NT, smem, st>>>(a);
   OMC_LAUNCH_CHECK();
   return 0;
@@ -332,7 +356,9 @@ extern "C" int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream) {
   OMC_REQUIRE(args->prior_kind == OMC_MAT_EYE || args->prior_P.ptr, "omc_nn_dense_draw: prior_P missing");
   const int p = args->p;
   if (args->truncated) {
+    OMC_REQUIRE(p <= 128, "omc_nn_dense_draw: the truncated-prior scan holds Q in shared memory (p=%d > 128)", p);
     const size_t smem = (size_t)(p * (p + 1) + 4 * p) * sizeof(double);
+    OMC_CHECK_CUDA(cudaFuncSetAttribute(nn_truncated_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nn_truncated_scan_kernel<<<args->n_chains, DD_THREADS, smem, (cudaStream_t)stream>>>(*args);
     OMC_LAUNCH_CHECK();
     return 0;
@@ -340,7 +366,10 @@ extern "C" int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream) {
   if (p <= 8) return launch_dense_draw<8>(*args, (cudaStream_t)stream);
   if (p <= 16) return launch_dense_draw<16>(*args, (cudaStream_t)stream);
   if (p <= 32) return launch_dense_draw<32>(*args, (cudaStream_t)stream);
-  return launch_dense_draw<64>(*args, (cudaStream_t)stream);
+  // OMC_DENSE_DRAW_IMPL=columns: the one-thread-per-column register kernel at 32 < p <= 64 (A/B timing, tools/)
+  static const bool columns = [] { const char* e = getenv("OMC_DENSE_DRAW_IMPL"); return e && e[0] == 'c'; }();
+  if (columns && p <= 64) return launch_dense_draw<64>(*args, (cudaStream_t)stream);
+  return omc_launch_blocked_draw(*args, (cudaStream_t)stream);
 }
 
 extern "C" int omc_quadform(const omc_quadform_t* args, void* stream) {

@@ -7,3 +7,9 @@ int omc_sm_count();
 //   1: diagonal vector  (p entries)
 //   2: dense row-major  (p x p)
 enum OmcMatKind { OMC_MAT_EYE = 0, OMC_MAT_DIAG = 1, OMC_MAT_DENSE = 2 };
+
+// dense_blocked.cu: blocked Cholesky (DMMA trailing update) form of omc_nn_dense_draw, p <= 512
+#include "../../include/omc.h"
+#include <cuda_runtime.h>
+int omc_launch_blocked_draw(const omc_nn_dense_t& a, cudaStream_t st);
+long long omc_blocked_workspace_doubles(int p);

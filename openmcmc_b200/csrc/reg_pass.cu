@@ -484,6 +484,170 @@ int launch_any(const RegPassArgs& a, bool weighted, cudaStream_t st) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// p > 64: column panels.  G is built block by block: CTA (split, pair, chain) owns the 64 x 64 block (bi, bj), bi >= bj,
+// of G = X'WX over its rows: A fragments from panel bi, B fragments from panel bj, all 64 8x8 tiles on the FP64 tensor
+// pipe (DMMA.8x8x4); the pairs with bj == 0 also accumulate g = X'Wy for panel bi.  rss / cnt come from a separate
+// streaming kernel (one warp per row, lanes over columns).  These run once per run (prologue) for models whose
+// likelihood weights are data; staging is synchronous (no pipeline) -- the sweep itself never touches X (omc.h:
+// omc_nn_dense_t.center).
+constexpr int WK = 32;            // rows per stage
+constexpr int WLD = 64 + 4;       // padded row stride of a staged panel
+constexpr int WIDE_MAX_P = 512;
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(NTHREADS) gram_wide_kernel(RegPassArgs a, int npan) {
+  __shared__ __align__(16) double As[WK * WLD];
+  __shared__ __align__(16) double Bs[WK * WLD];
+  __shared__ double ys[WK], ws[WK];
+  const int split = blockIdx.x, chain = blockIdx.z;
+  int bi = 0, bj = 0;
+  {  // pair index -> (bi, bj), bi >= bj
+    int q = blockIdx.y;
+    while (q > bi) { q -= bi + 1; ++bi; }
+    bj = q;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, kq = lane & 3;
+  const int p = a.p, n = a.n;
+  const int row0 = split * a.rows_per_split, row1 = min(n, row0 + a.rows_per_split);
+  const double* Xc = a.X + (long long)chain * a.strideX;
+  const double* yc = a.y + (long long)chain * a.strideY;
+  const double* wc = WEIGHTED ? a.w + (long long)chain * a.strideW : nullptr;
+  const bool diag = bi == bj;
+  const double* Bsm = diag ? As : Bs;
+  // warp w owns the tile rows 2w, 2w+1 of the block (16 tiles, 64 accumulator registers) over ALL rows: no cross-warp sum
+  double acc[16][2];
+  double gacc[2];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t][0] = acc[t][1] = 0.0;
+  gacc[0] = gacc[1] = 0.0;
+  for (int r0 = row0; r0 < row1; r0 += WK) {
+    __syncthreads();
+    for (int idx = tid; idx < WK * 64; idx += NTHREADS) {
+      const int r = idx >> 6, c = idx & 63, row = r0 + r;
+      const int ca = 64 * bi + c, cb = 64 * bj + c;
+      const bool rok = row < row1;
+      As[r * WLD + c] = (rok && ca < p) ? Xc[(long long)row * p + ca] : 0.0;
+      if (!diag) Bs[r * WLD + c] = (rok && cb < p) ? Xc[(long long)row * p + cb] : 0.0;
+    }
+    for (int r = tid; r < WK; r += NTHREADS) {
+      const int row = r0 + r;
+      ys[r] = row < row1 ? yc[row] : 0.0;
+      ws[r] = row < row1 ? (WEIGHTED ? wc[row] : 1.0) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < WK / 4; ++ks) {
+      const int r = 4 * ks + kq;
+      const double wv = ws[r], yv = ys[r];
+      double af[2], bf[8];
+      af[0] = As[r * WLD + 16 * warp + g];
+      af[1] = As[r * WLD + 16 * warp + 8 + g];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = Bsm[r * WLD + 8 * j + g] * wv;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(acc[i * 8 + j][0], acc[i * 8 + j][1], af[i], bf[j]);
+      if (bj == 0) {
+        gacc[0] = fma(af[0] * wv, yv, gacc[0]);
+        gacc[1] = fma(af[1] * wv, yv, gacc[1]);
+      }
+    }
+  }
+  const int rec = p * p + p + 2;
+  double* o = a.out + ((long long)chain * a.n_split + split) * rec;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = 64 * bi + 16 * warp + 8 * i + g, cc = 64 * bj + 8 * j + 2 * kq + e;
+        if (rr < p && cc < p && (!diag || cc <= rr)) {
+          const double v = acc[i * 8 + j][e];
+          o[(long long)rr * p + cc] = v;
+          if (rr != cc) o[(long long)cc * p + rr] = v;
+        }
+      }
+  if (bj == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double v = gacc[i];
+      v += omc_shfl_xor(v, 1);
+      v += omc_shfl_xor(v, 2);
+      const int cc = 64 * bi + 16 * warp + 8 * i + g;
+      if (kq == 0 && cc < p) o[(long long)p * p + cc] = v;
+    }
+  }
+}
+
+// rss = (y - X beta)' W (y - X beta) and cnt for any p: one warp per row, lanes over the columns (coalesced), beta in
+// shared memory.  beta == NULL gives y'Wy.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) rss_wide_kernel(RegPassArgs a) {
+  extern __shared__ double sbeta[];
+  __shared__ double scratch[32];
+  const int split = blockIdx.x, chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = a.p, n = a.n;
+  const int row0 = split * a.rows_per_split, row1 = min(n, row0 + a.rows_per_split);
+  for (int c = tid; c < p; c += 256) sbeta[c] = a.beta ? a.beta[(long long)chain * a.strideB + c] : 0.0;
+  __syncthreads();
+  const double* Xc = a.X + (long long)chain * a.strideX;
+  const double* yc = a.y + (long long)chain * a.strideY;
+  const double* wc = WEIGHTED ? a.w + (long long)chain * a.strideW : nullptr;
+  double rss = 0.0, cnt = 0.0;
+  for (int r = row0 + warp; r < row1; r += 16) {
+    const int r2 = r + 8;
+    const double* x1 = Xc + (long long)r * p;
+    const double* x2 = Xc + (long long)r2 * p;
+    const bool two = r2 < row1;
+    double d1 = 0.0, d2 = 0.0;
+    for (int c = lane; c < p; c += 32) {
+      const double b = sbeta[c];
+      d1 = fma(x1[c], b, d1);
+      if (two) d2 = fma(x2[c], b, d2);
+    }
+    d1 = omc_warp_sum(d1);
+    d2 = omc_warp_sum(d2);
+    if (lane == 0) {
+      const double w1 = WEIGHTED ? wc[r] : 1.0, e1 = yc[r] - d1;
+      rss = fma(w1 * e1, e1, rss);
+      cnt += (w1 > 0.0) ? 1.0 : 0.0;
+      if (two) {
+        const double w2 = WEIGHTED ? wc[r2] : 1.0, e2 = yc[r2] - d2;
+        rss = fma(w2 * e2, e2, rss);
+        cnt += (w2 > 0.0) ? 1.0 : 0.0;
+      }
+    }
+  }
+  rss = omc_block_sum(rss, scratch);
+  cnt = omc_block_sum(cnt, scratch);
+  if (tid == 0) {
+    const int rec = p * p + p + 2;
+    double* o = a.out + ((long long)chain * a.n_split + split) * rec;
+    o[p * p + p] = rss;
+    o[p * p + p + 1] = cnt;
+  }
+}
+
+template <bool SYRK>
+int launch_wide(const RegPassArgs& a, bool weighted, cudaStream_t st) {
+  const int npan = (a.p + 63) / 64;
+  if (SYRK) {
+    dim3 grid(a.n_split, npan * (npan + 1) / 2, a.n_chains);
+    if (weighted) gram_wide_kernel<true><<<grid, NTHREADS, 0, st>>>(a, npan);
+    else gram_wide_kernel<false><<<grid, NTHREADS, 0, st>>>(a, npan);
+    OMC_LAUNCH_CHECK();
+  }
+  dim3 grid2(a.n_split, a.n_chains);
+  if (weighted) rss_wide_kernel<true><<<grid2, 256, a.p * sizeof(double), st>>>(a);
+  else rss_wide_kernel<false><<<grid2, 256, a.p * sizeof(double), st>>>(a);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
 // Shared body of omc_reg_pass (SYRK = true) and omc_reg_rss (SYRK = false).
 template <bool SYRK>
 int reg_pass_impl(const double* X, long long strideX, const double* y, long long strideY, const double* w,
@@ -507,7 +671,14 @@ int reg_pass_impl(const double* X, long long strideX, const double* y, long long
   if (rps < KC) rps = KC;
   a.rows_per_split = rps;
   a.out = (n_split > 1) ? workspace : stats;
-  rc = launch_any<SYRK>(a, w != nullptr, st);
+  if (p > 64) {
+    OMC_REQUIRE(n_chains <= 65535, "%s: n_chains=%d exceeds the grid; shard the chains", who, n_chains);
+    int rw = (n + n_split - 1) / n_split;
+    a.rows_per_split = ((rw + WK - 1) / WK) * WK;
+    rc = launch_wide<SYRK>(a, w != nullptr, st);
+  } else {
+    rc = launch_any<SYRK>(a, w != nullptr, st);
+  }
   if (rc) return rc;
   if (n_split > 1) {
     const int rec = p * p + p + 2;
@@ -523,11 +694,13 @@ int reg_pass_impl(const double* X, long long strideX, const double* y, long long
 
 extern "C" int omc_reg_pass_workspace(int n_chains, int n, int p, int* n_split_out, long long* workspace_doubles) {
   OMC_REQUIRE(n_chains > 0 && n >= 0 && p > 0, "omc_reg_pass_workspace: bad shape C=%d n=%d p=%d", n_chains, n, p);
-  OMC_REQUIRE(p <= 64, "omc_reg_pass: p=%d > 64 is not supported yet (column panels are a round-2 item)", p);
+  OMC_REQUIRE(p <= WIDE_MAX_P, "omc_reg_pass: p=%d > %d is not supported", p, WIDE_MAX_P);
   int sms = omc_sm_count();
   int max_split = (n + KC - 1) / KC;
   if (max_split < 1) max_split = 1;
-  int want = (4 * sms + n_chains - 1) / n_chains;  // aim for >= 4 CTAs per SM when chains are few
+  long long ctas_per_split = n_chains;              // p > 64: one CTA per (chain, 64-column panel pair)
+  if (p > 64) ctas_per_split *= ((p + 63) / 64) * (((p + 63) / 64) + 1) / 2;
+  int want = (int)((4ll * sms + ctas_per_split - 1) / ctas_per_split);  // aim for >= 4 CTAs per SM when chains are few
   int s = want < 1 ? 1 : (want > max_split ? max_split : want);
   *n_split_out = s;
   *workspace_doubles = (s > 1) ? (long long)n_chains * s * ((long long)p * p + p + 2) : 0;

@@ -26,6 +26,11 @@ F64 = torch.float64
 # included) every sweep, the way the reference recomputes A'QA in every NormalNormal.sample (sampler.py:180-186);
 # bench.py times that form next to the shipped one.
 CACHE_DATA_ONLY = True
+# With G | g cached, the residual sum of squares of the CURRENT beta needs no pass over X either: the prologue fixes a
+# centre beta_hat (the least-squares point), streams X once more for c0 = X'W(y - X beta_hat) and rss0, and the draw
+# kernel's epilogue evaluates rss(beta) = rss0 - 2 d'c0 + d'G d, d = beta - beta_hat (omc.h: omc_nn_dense_t.center).
+# False keeps the explicit residual pass (omc_reg_rss) in every sweep; tests compare the two forms.
+RECENTER = True
 
 
 # ============================================================================================== device state
@@ -77,7 +82,7 @@ def classify_matrix(m):
             if not np.array_equal(e_lo, e_up):
                 raise NotImplementedError("non-symmetric tridiagonal precision matrix")
             return "tridiag", d, e_lo
-        if n <= 64:
+        if n <= 512:
             return "dense", np.asarray(m.todense(), dtype=np.float64), None
         raise NotImplementedError(f"sparse {n}x{n} precision with bandwidth > 1 is not supported by the device path")
     m = np.asarray(m, dtype=np.float64)
@@ -228,6 +233,7 @@ class Plan:
     debug: dict = field(default_factory=dict)         # site name -> injected draw tensors
     probes: dict = field(default_factory=dict)        # name -> tensor with intermediates (parity tests)
     keep: list = field(default_factory=list)          # tensors that must outlive the captured graph
+    recenter: bool = True                             # False for one-call plans: a centre would cost 3 passes over X
 
     def __post_init__(self):
         dev = self.state.device
@@ -397,8 +403,8 @@ class RegressionLikelihood:
         if self.y.cols != 1 or self.beta.cols != 1:
             raise PlanError("replicated responses (n_rep > 1) are not supported by the regression device path yet")
         self.n, self.p = self.X.rows, self.X.cols
-        if self.p > 64:
-            raise PlanError(f"p={self.p} > 64 regression coefficients are not supported yet")
+        if self.p > 512:
+            raise PlanError(f"p={self.p} > 512 regression coefficients are not supported by the device path")
         mname, self.scalar = _scalar_and_matrix(dist.precision)
         W = ensure_matrix(st, host_state, mname)
         if W.kind not in ("eye", "diag"):
@@ -418,6 +424,43 @@ class RegressionLikelihood:
         plan.add_quantity(Quantity(self.q_gg, deps_data, self._emit_pass, (self.q_rss,)))
         plan.add_quantity(Quantity(self.q_rss, deps_data if data_only else deps_data | {param}, self._emit_rss,
                                    (self.q_gg,)))
+        ws = K.nn_dense_workspace(C, self.p)
+        self.dense_ws = plan.new(ws) if ws else None
+        # re-centred statistics: only when G | g | centre depend on data alone (nothing they read is sampled)
+        self.center = None
+        if (RECENTER and plan.recenter and CACHE_DATA_ONLY and not data_only and not self.others
+                and not (deps_data & set(st.per_chain_names))):
+            self.center = plan.new(C, 2 * self.p + 2, fill=0.0)     # beta_hat | c0 | rss0 | cnt
+            self.q_center = f"center[{dist.response}]"
+            plan.add_quantity(Quantity(self.q_center, deps_data, self._emit_center))
+
+    def _emit_center(self):
+        """Prologue only: centre beta_hat = (G with a 1e-12 relative diagonal jitter)^-1 g, then ONE explicit-residual
+        stream r0 = y - X beta_hat and the fused pass on (X, r0): c0 = X'W r0, rss0 = r0'W r0."""
+        plan, st = self.plan, self.plan.state
+        C, n, p = st.n_chains, self.n, self.p
+        X, y, W = self.X, self.y, self.W
+        w = W.data if W.kind == "diag" else None
+        zero = plan.new(1, fill=0.0)
+        plan.require(self.q_gg)
+
+        def launch():
+            dev = st.device
+            beta_hat = torch.empty(C, p, dtype=F64, device=dev)
+            K.nn_dense_draw(C, p, self.stats, K.vec(None), K.MAT_EYE, K.vec(None), K.vec(zero), K.vec(None), beta_hat,
+                            K.rng(), solve_only=True, ridge_rel=1e-12, workspace=self.dense_ws)
+            r0 = torch.empty(C, n, dtype=F64, device=dev)
+            K.linear_predictor(C, n, [(X.vec(), K.vec(beta_hat, p), p, False)], r0, residual_of=y.vec())
+            scratch = torch.empty(C, self.rec, dtype=F64, device=dev)
+            K.reg_pass(X.data, r0, w, None, scratch, self.work, C, n, p, x_shared=not X.per_chain, y_shared=False,
+                       w_shared=True)
+            self.center[:, :p].copy_(beta_hat)                        # plumbing: the kernels did the arithmetic
+            self.center[:, p:].copy_(scratch[:, p * p:])
+
+        plan.emit(launch, "reg_center")
+
+    def rss_ptr(self):
+        return self.stats.data_ptr() + 8 * (self.p * self.p + self.p)
 
     def _emit_rss(self):
         """rss is stale.  While G | g (data only) are still valid, X is streamed for the residual alone (omc_reg_rss,

@@ -39,7 +39,7 @@ def sample_once(sampler, state: dict, debug_draws: dict = None) -> dict:
     user_state, user_model = state, sampler.model
     dists, state, changed = engine.unreplicate(list(sampler.model.values()), state, frozenset({sampler.param}))
     st = engine.DeviceState(1, dev, state, per_chain_names={sampler.param})
-    plan = engine.Plan(st, seed=_default_seed)
+    plan = engine.Plan(st, seed=_default_seed, recenter=False)
     plan.sweep_counter.fill_(next(_call_counter))
     try:
         if changed:   # replicated data response: compiled in its single-column form, the caller's objects stay as they are

@@ -171,10 +171,19 @@ def reg_rss(X, y, w, beta, stats, workspace, n_chains, n, p, x_shared=False, y_s
     )
 
 
+def nn_dense_workspace(n_chains, p) -> int:
+    """Doubles of scratch omc_nn_dense_draw / omc_dense_factor need (0 while the matrix fits in shared memory)."""
+    d = C.c_longlong(0)
+    check(lib().omc_nn_dense_workspace(int(n_chains), int(p), C.byref(d)), "omc_nn_dense_workspace")
+    return d.value
+
+
 def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, rng_, debug_z=None, probe_Q=None,
                   probe_b=None, probe_L=None, probe_mu=None, status=None, debug_sweep_stride=0, trunc=None,
-                  debug_u=None):
-    """trunc = (lo_vec, lo_len, hi_vec, hi_len) switches to the truncated-prior Gibbs scan (omc.h)."""
+                  debug_u=None, center=None, rss_out=None, solve_only=False, ridge_rel=0.0, workspace=None):
+    """trunc = (lo_vec, lo_len, hi_vec, hi_len) switches to the truncated-prior Gibbs scan (omc.h).
+    center [C, 2p+1] (beta_hat | c0 | rss0) + rss_out (pointer into the record's rss slot): the draw also leaves
+    rss(beta) there (re-centred sufficient statistics); solve_only: beta = posterior mean of the jittered system."""
     a = _cabi.NNDense()
     if trunc is not None:
         a.truncated = 1
@@ -192,7 +201,26 @@ def nn_dense_draw(n_chains, p, stats, tau, prior_kind, prior_P, lam, mu0, beta, 
     a.probe_L = probe_L.data_ptr() if probe_L is not None else None
     a.probe_mu = probe_mu.data_ptr() if probe_mu is not None else None
     a.status = status.data_ptr() if status is not None else None
+    if center is not None:
+        a.center = Vec(center.data_ptr(), center.shape[1])
+        a.rss_out = rss_out
+    a.mode, a.ridge_rel = int(bool(solve_only)), float(ridge_rel)
+    a.workspace = workspace.data_ptr() if workspace is not None else None
     check(lib().omc_nn_dense_draw(C.byref(a), stream_ptr()), "omc_nn_dense_draw")
+
+
+def dense_factor(Q, n, b=None, z=None, L=None, logdet=None, mean=None, x=None, status=None, factored=False,
+                 backward_only=False, workspace=None, n_mats=None):
+    """omc_dense_factor: blocked Cholesky / solves of n_mats dense SPD matrices [n_mats, n, n] (omc.h)."""
+    a = _cabi.DenseFactor()
+    m = int(n_mats if n_mats is not None else (Q.shape[0] if Q.dim() == 3 else 1))
+    a.n_mats, a.n = m, int(n)
+    a.Q, a.Q_stride = Q.data_ptr(), (n * n if Q.dim() == 3 and Q.shape[0] == m else 0)
+    for name, t in (("b", b), ("z", z), ("L", L), ("logdet", logdet), ("mean", mean), ("x", x), ("status", status),
+                    ("workspace", workspace)):
+        setattr(a, name, t.data_ptr() if t is not None else None)
+    a.factored, a.backward_only = int(bool(factored)), int(bool(backward_only))
+    check(lib().omc_dense_factor(C.byref(a), stream_ptr()), "omc_dense_factor")
 
 
 def quadform(n_chains, p, x, mu, kind, P, ss, cnt):

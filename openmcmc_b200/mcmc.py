@@ -176,14 +176,10 @@ class MCMC:
             plan.valid = saved_valid
             # prologue: quantities the steady-state sweep assumes valid, computed from the initial state
             plan.ops = prologue_ops = []
-            done = set()
-            plan.valid = {k: False for k in saved_valid}   # nothing is valid yet: every compute() emits its full form
+            plan.valid = {k: False for k in plan.valid}    # nothing is valid yet: every compute() emits its full form
             for qname, ok in valid_end.items():
-                if ok and qname not in done:
-                    q = plan.quantities[qname]
-                    q.compute()
-                    done.add(qname)
-                    done.update(q.siblings)
+                if ok:
+                    plan.require(qname)                    # (a compute() may require other quantities first)
             plan.valid = saved_valid
             self.plan = plan
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}

@@ -124,7 +124,8 @@ class NormalNormal(MCMCSampler):
         C = st.n_chains
         if source is None:
             rl = engine.get_regression(plan, host_state, lik, self.param)
-            source = dict(stats=rl.stats, rec=rl.rec, p=rl.p, tau=st[rl.scalar] if rl.scalar else None, require=rl.q_gg)
+            source = dict(stats=rl.stats, rec=rl.rec, p=rl.p, tau=st[rl.scalar] if rl.scalar else None, require=rl.q_gg,
+                          regression=rl)
         p = source["p"]
         tau = source["tau"]
         requires = [source["require"]]
@@ -172,9 +173,20 @@ class NormalNormal(MCMCSampler):
                 if debug_draws and "u" in debug_draws:
                     ctx["dz"], ctx["dz_stride"] = plan.debug_tensor(debug_draws["u"], p)
         rng, dz, dz_stride, probes, trunc = ctx["rng"], ctx["dz"], ctx["dz_stride"], ctx["probes"], ctx["trunc"]
+        # re-centred statistics: the draw leaves rss(beta_new) in the regression record (no pass over X; engine.RECENTER)
+        rl = source.get("regression")
+        centred = rl is not None and rl.center is not None and trunc is None
+        if centred:
+            requires.append(rl.q_center)
         for q in requires:
             plan.require(q)
         stats = source["stats"]
+        center, rss_out = (rl.center, rl.rss_ptr()) if centred else (None, None)
+        if rl is not None:
+            workspace = rl.dense_ws
+        else:
+            ws = K.nn_dense_workspace(C, p)
+            workspace = ctx.setdefault("workspace", plan.new(ws) if ws else None)
 
         def launch():
             K.nn_dense_draw(
@@ -182,10 +194,13 @@ class NormalNormal(MCMCSampler):
                 lam.vec() if lam else K.vec(None), mu0_vec(), beta.data, rng, debug_z=None if trunc else dz,
                 probe_Q=probes["Q"] if probes else None, probe_b=probes["b"] if probes else None,
                 probe_L=probes["L"] if probes else None, probe_mu=probes["mu"] if probes else None, status=plan.status,
-                debug_sweep_stride=dz_stride, trunc=trunc, debug_u=dz if trunc else None)
+                debug_sweep_stride=dz_stride, trunc=trunc, debug_u=dz if trunc else None, center=center,
+                rss_out=rss_out, workspace=workspace)
 
         plan.emit(launch, f"nn_dense_draw[{self.param}]")
         plan.wrote(self.param)
+        if centred:
+            plan.valid[rl.q_rss] = True
 
 
 @dataclass

@@ -84,14 +84,15 @@ class Streams:
 
 
 # ----------------------------------------------------------------------------------------------- regression (C1 shape)
-def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "lambda"), prior="eye", trunc=None):
+def regression_case(n, p, seed, n_iter, weighted=False, order=("beta", "tau", "lambda"), prior="eye", trunc=None,
+                    noise=0.1):
     """trunc = (lower, upper) (size-1 arrays or None): truncated Normal prior on beta -> NormalNormal.sample runs
     gmrf.gibbs_canonical_truncated_normal (sampler.py:196-205); its truncnorm.rvs uniforms are recorded in `tn_u`."""
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((n, p))
     X[:, 0] = 1.0
     beta_true = rng.standard_normal((p, 1))
-    y = X @ beta_true + 0.1 * rng.standard_normal((n, 1))
+    y = X @ beta_true + noise * rng.standard_normal((n, 1))
     if weighted:
         w = rng.random(n) + 0.2  # strictly positive: a singular P_tau breaks the reference's own log_p
         P_tau = sparse.diags(w, format="csc")
@@ -754,9 +755,18 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2"]
     if "regression" not in which:
         cases = {}
+    if "round2" in which:
+        # round 2: high signal-to-noise (the re-centred rss must not cancel), p > 64 (blocked Cholesky, column panels),
+        # RandomWalkLoop at the BASELINE C4b width (1, 32)
+        cases.update({
+            "regression_n400_p12_highsnr": regression_case(400, 12, 21, 5, noise=1e-4),
+            "regression_n600_p128": regression_case(600, 128, 22, 3),
+            "regression_n700_p200_dense_weighted": regression_case(700, 200, 23, 2, weighted=True, prior="dense"),
+            "rwl_poisson_gamma_1x32": rwl_case(32, 24, 6, 0.5),
+        })
     if "mh" in which:
         cases.update(mh_cases())
     if "mh_f4" in which:

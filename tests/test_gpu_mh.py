@@ -156,14 +156,17 @@ def test_mmala_poisson_gamma_chains(name):
         assert bool(sc[5]) == info["accepted"]
 
 
-def test_random_walk_loop_replays_reference_chain():
+@pytest.mark.parametrize("name", ["rwl_poisson_gamma_1x8", "rwl_poisson_gamma_1x32"])
+def test_random_walk_loop_replays_reference_chain(name):
+    """(1, 32) is the BASELINE C4b layout: the column-parallel (lane = column) kernel at its full warp width."""
     from openmcmc_b200.mcmc import MCMC
     from openmcmc_b200.sampler.metropolis_hastings import RandomWalkLoop
 
-    g = _load("rwl_poisson_gamma_1x8")
+    g = _load(name)
+    width = g["store_lam"].shape[1]
     mdl = _pg_model()
     smp = RandomWalkLoop("lam", mdl, step=np.array([[float(g["step"])]]), domain_limits=g["limits"],
-                         max_variable_size=(1, 8))
+                         max_variable_size=(1, width))
     n_iter = g["store_lam"].shape[2]
     M = MCMC(_pg_state(g), [smp], model=mdl, n_burn=0, n_iter=n_iter,
              debug_draws={"lam": {"tn_u": g["tn_u"], "u": g["u"]}})
@@ -172,7 +175,7 @@ def test_random_walk_loop_replays_reference_chain():
     np.testing.assert_allclose(M.store["lam"], g["store_lam"], rtol=1e-9)
     np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
     assert smp.accept_rate.count == {"accept": int(g["accept"][0]), "proposal": int(g["accept"][1])}
-    assert M.state["lam"].shape == (1, 8)
+    assert M.state["lam"].shape == (1, width)
 
 
 @pytest.mark.parametrize("name", ["rw_poisson_gamma_p6", "rw_trunc_scalar"])
@@ -203,14 +206,14 @@ def test_random_walk_loop_without_limits_raises_like_reference():
 
 
 # ------------------------------------------------------------------------------------------------ free-running chains
-@pytest.mark.parametrize("kind", ["mmala", "rwl"])
-def test_free_running_poisson_gamma_posterior(kind):
+@pytest.mark.parametrize("kind,p", [("mmala", 8), ("rwl", 8), ("rwl", 32), ("mmala", 32)])
+def test_free_running_poisson_gamma_posterior(kind, p):
     """Poisson counts with a Gamma(a, b) prior are conjugate: lam_j | y ~ Gamma(a + y_j, b + 1).  One draw per chain
     after burn-in is an independent posterior sample: KS p > 0.01 per coordinate (north_star), means within MC error."""
     from openmcmc_b200.mcmc import MCMC
     from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA, RandomWalkLoop
 
-    p, C = 8, 2048
+    C = 2048
     rng = np.random.default_rng(3)
     y = rng.poisson(rng.gamma(5.0, 1.0, size=p)).astype(float)
     mdl = _pg_model()

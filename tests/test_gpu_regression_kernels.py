@@ -31,7 +31,10 @@ def _make(C, n, p, seed, weighted):
 @pytest.mark.parametrize(
     "C,n,p,weighted",
     [(3, 1000, 3, False), (2, 257, 64, False), (5, 64, 8, True), (2, 1031, 17, True), (1, 5, 2, False),
-     (4, 300, 33, False), (300, 130, 64, False), (1, 20000, 64, True), (2, 1, 1, False), (2, 4096, 40, True)],
+     (4, 300, 33, False), (300, 130, 64, False), (1, 20000, 64, True), (2, 1, 1, False), (2, 4096, 40, True),
+     # p > 64: 64-column panel pairs (gram_wide_kernel) + the streaming rss kernel
+     (2, 500, 128, False), (3, 333, 100, True), (1, 3001, 256, True), (2, 70, 65, False), (150, 96, 72, False),
+     (1, 700, 300, False)],
 )
 def test_reg_pass_matches_oracle(C, n, p, weighted):
     import torch
@@ -71,7 +74,8 @@ def test_reg_pass_matches_oracle(C, n, p, weighted):
 
 @pytest.mark.parametrize("prior", ["eye", "diag", "dense"])
 @pytest.mark.parametrize("C,n,p", [(4, 500, 3), (3, 400, 64), (2, 100, 31), (2, 300, 45), (3, 200, 17), (5, 60, 8),
-                                   (2, 50, 1), (300, 130, 64)])
+                                   (2, 50, 1), (300, 130, 64), (2, 120, 33), (2, 300, 100), (3, 400, 128),
+                                   (2, 500, 136), (2, 500, 200), (1, 700, 256), (1, 900, 300)])
 def test_nn_dense_draw_injected_z(C, n, p, prior):
     import torch
 
@@ -106,8 +110,11 @@ def test_nn_dense_draw_injected_z(C, n, p, prior):
     pmu = torch.empty_like(pb)
     status = torch.zeros(C, dtype=torch.int32, device="cuda")
     stride = 0 if P0 is None else int(np.prod(P0.shape[1:]))
+    ws = K.nn_dense_workspace(C, p)
+    dws = torch.empty(ws, dtype=torch.float64, device="cuda") if ws else None
     K.nn_dense_draw(C, p, stats, K.vec(dtau, 1), kind, K.vec(dP0, stride), K.vec(dlam, 1), K.vec(dmu0, p), beta,
-                    K.rng(seed=1, site=3), debug_z=dz, probe_Q=pQ, probe_b=pb, probe_L=pL, probe_mu=pmu, status=status)
+                    K.rng(seed=1, site=3), debug_z=dz, probe_Q=pQ, probe_b=pb, probe_L=pL, probe_mu=pmu, status=status,
+                    workspace=dws)
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0
     for c in range(C):

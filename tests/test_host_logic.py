@@ -33,8 +33,12 @@ def test_classify_matrix_structures():
         classify_matrix(sparse.diags([e, d, 2 * e], [-1, 0, 1], format="csc"))
     small = sparse.csc_matrix(np.array([[2.0, 1, 0.5], [1, 2, 1], [0.5, 1, 2]]))
     assert classify_matrix(small)[0] == "dense"
+    assert classify_matrix(sparse.diags([e[:-1], e, d, e, e[:-1]], [-2, -1, 0, 1, 2], format="csc"))[0] == (
+        "dense" if n <= 512 else "banded")
+    nb = 600
     with pytest.raises(NotImplementedError):
-        classify_matrix(sparse.diags([e[:-1], e, d, e, e[:-1]], [-2, -1, 0, 1, 2], format="csc"))
+        classify_matrix(sparse.diags([np.ones(nb - 2), np.ones(nb - 1), 4 * np.ones(nb), np.ones(nb - 1), np.ones(nb - 2)],
+                                     [-2, -1, 0, 1, 2], format="csc"))
     # dense inputs
     assert classify_matrix(np.eye(5))[0] == "eye"
     assert classify_matrix(np.diag(d[:5]))[0] == "diag"

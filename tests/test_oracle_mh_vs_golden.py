@@ -62,8 +62,9 @@ def test_mmala_analytic_chain(name):
         np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-11)
 
 
-def test_random_walk_loop_chain():
-    g = _load("rwl_poisson_gamma_1x8")
+@pytest.mark.parametrize("name", ["rwl_poisson_gamma_1x8", "rwl_poisson_gamma_1x32"])
+def test_random_walk_loop_chain(name):
+    g = _load(name)
     terms = poisson_gamma_terms(g)
     theta = g["lam0"]
     n_acc = 0
@@ -72,7 +73,7 @@ def test_random_walk_loop_chain():
         n_acc += sum(i["accepted"] for i in infos)
         np.testing.assert_allclose(theta, g["store_lam"][:, :, it], rtol=1e-11)
         np.testing.assert_allclose(mh.log_p(terms, theta), g["store_log_post"][it, 0], rtol=1e-12)
-    assert n_acc == g["accept"][0] and g["accept"][1] == g["store_lam"].shape[2] * 8
+    assert n_acc == g["accept"][0] and g["accept"][1] == g["store_lam"].shape[2] * g["store_lam"].shape[1]
 
 
 @pytest.mark.parametrize("name", ["rw_poisson_gamma_p6", "rw_trunc_scalar"])

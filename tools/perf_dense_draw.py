@@ -23,11 +23,13 @@ beta = torch.empty(C, p, dtype=torch.float64, device="cuda")
 pmu = torch.empty(C, p, dtype=torch.float64, device="cuda")
 sweep = torch.zeros(1, dtype=torch.int64, device="cuda")
 status = torch.zeros(C, dtype=torch.int32, device="cuda")
+_ws = K.nn_dense_workspace(C, p)
+ws = torch.empty(_ws, dtype=torch.float64, device="cuda") if _ws else None
 
 
 def call(probe=None):
     K.nn_dense_draw(C, p, stats, K.vec(tau, 1), K.MAT_EYE, K.vec(None), K.vec(lam, 1), K.vec(mu0, 0), beta,
-                    K.rng(seed=1, sweep=sweep, site=3), probe_mu=probe, status=status)
+                    K.rng(seed=1, sweep=sweep, site=3), probe_mu=probe, status=status, workspace=ws)
 
 
 call(pmu)
@@ -45,5 +47,6 @@ for _ in range(reps):
     call()
 e1.record()
 torch.cuda.synchronize()
-print(json.dumps({"C": C, "p": p, "ms": e0.elapsed_time(e1) / reps, "mean_rel_err_vs_torch": err,
+import os
+print(json.dumps({"impl": os.environ.get("OMC_DENSE_DRAW_IMPL", "default"), "C": C, "p": p, "ms": e0.elapsed_time(e1) / reps, "mean_rel_err_vs_torch": err,
                   "status_bad": int((status != 0).sum())}))
