@@ -30,11 +30,11 @@ UNIT = "chain-iterations/s"
 WORKLOADS = {
     # BASELINE.json configs[1]: batched Bayesian linear regression (the config the metric is quoted on; fits 1 GPU)
     "c2": dict(name="batched Bayesian linear regression: 4096 chains/GPU, n=10000, p=64, NormalNormal+NormalGamma Gibbs",
-               kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="reg_rss",
+               kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="nn_dense_draw",
                cpu=dict(chains_per_worker=8, sweeps=100), ref=dict(chains_per_worker=2, sweeps=5)),
     # BASELINE.json configs[0]: example-3 regression, single chain (latency bound)
     "c1": dict(name="examples/3_linear_regression: 1 chain, n=1000, p=3", kind="regression", chains=1, n=1000, p=3,
-               thin=1, dominant="reg_rss", cpu=dict(chains_per_worker=1, sweeps=4000),
+               thin=1, dominant="nn_dense_draw", cpu=dict(chains_per_worker=1, sweeps=4000),
                ref=dict(chains_per_worker=1, sweeps=500)),
     # BASELINE.json configs[2]: example-4 GMRF smoother scaled up (sparse-enabled form)
     "c3": dict(name="temporal GMRF smoother: 64 chains/GPU, n=1e6 grid points, tridiagonal NormalNormal + 2x NormalGamma",

@@ -63,6 +63,11 @@ int omc_run_schedule(omc_graph_t* sweep, omc_graph_t* store, void* stream, long 
 /* store[iter] <- src : `count` doubles into dst + (*iter_counter)*count   (ref: sampler.py:89-118) */
 int omc_store_copy(const double* src, double* dst, long long count, const unsigned long long* iter_counter,
                    long long max_iter, void* stream);
+/* streamed store: slab (*iter_counter % ring) of a device ring [ring][count]; the host drains slab k to pinned memory on
+ * a copy stream while the sweeps of the next stored iterations run (north star: "samples stream asynchronously to
+ * pinned host memory"; ref: mcmc.py:105-111, sampler.py:89-118) */
+int omc_store_copy_ring(const double* src, double* dst, long long count, const unsigned long long* iter_counter,
+                        long long ring, void* stream);
 
 /* ------------------------------------------------------------------ conjugate regression (C1 / C2)
  * omc_reg_pass: one fused pass over (X, y[, w]) per chain -> record  G = X'WX | g = X'Wy | rss | cnt

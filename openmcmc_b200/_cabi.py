@@ -216,6 +216,7 @@ PROTOTYPES = {
     "omc_graph_num_kernel_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
     "omc_run_schedule": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong]),
     "omc_store_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "omc_store_copy_ring": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "omc_reg_pass_workspace": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "omc_reg_pass": (
         C.c_int,

@@ -140,19 +140,44 @@ __device__ bool blocked_cholesky(const Workspace& W, int p, int n_extra, int* s_
       const int T0 = k1 >> 3;                               // k1 is a multiple of 16 here
       const int Tr = (W.rows_pad >> 3) - T0, Tc = ((p + 7) >> 3) - T0;
       const int g = lane >> 2, kq = lane & 3;
-      int idx = 0;
-      for (int ti = 0; ti < Tr; ++ti) {
-        const int jmax = min(ti, Tc - 1);
-        for (int tj = 0; tj <= jmax; ++tj, ++idx) {
-          if ((idx & (NW - 1)) != warp) continue;
-          const double* pa = W.Pn + (8 * (T0 + ti) + g) * PLD + kq;
-          const double* pb = W.Pn + (8 * (T0 + tj) + g) * PLD + kq;
-          double2* pc = reinterpret_cast<double2*>(A + (long long)(8 * (T0 + ti) + g) * LD + 8 * (T0 + tj) + 2 * kq);
-          double2 c = *pc;
+      // this warp's tiles (round-robin over the row-major enumeration of the lower triangle), four at a time: the C
+      // loads of a batch go out together and its 16 DMMAs interleave (a store -> load pair per tile would serialise
+      // them: the compiler cannot prove that Pn and A do not alias)
+      constexpr int TB = 4;
+      int ti = 0, tj = 0, idx = 0;
+      const long long total = (long long)Tc * (Tc + 1) / 2 + (long long)(Tr - Tc) * Tc;
+      auto advance = [&]() {
+        ++idx;
+        if (++tj > min(ti, Tc - 1)) { tj = 0; ++ti; }
+      };
+      while (idx < total && (idx & (NW - 1)) != warp) advance();
+      while (idx < total) {
+        double2* pc[TB];
+        const double* pa[TB];
+        const double* pb[TB];
+        double2 c[TB];
+        int nb = 0;
 #pragma unroll
-          for (int ks = 0; ks < NB / 4; ++ks) dmma884(c.x, c.y, -pa[4 * ks], pb[4 * ks]);
-          *pc = c;
+        for (int q = 0; q < TB; ++q) {
+          if (idx < total) {
+            pa[q] = W.Pn + (8 * (T0 + ti) + g) * PLD + kq;
+            pb[q] = W.Pn + (8 * (T0 + tj) + g) * PLD + kq;
+            pc[q] = reinterpret_cast<double2*>(A + (long long)(8 * (T0 + ti) + g) * LD + 8 * (T0 + tj) + 2 * kq);
+            nb = q + 1;
+            for (int s = 0; s < NW && idx < total; ++s) advance();
+          } else {
+            pa[q] = pa[0]; pb[q] = pb[0]; pc[q] = pc[0];
+          }
         }
+#pragma unroll
+        for (int q = 0; q < TB; ++q) c[q] = *pc[q];
+#pragma unroll
+        for (int ks = 0; ks < NB / 4; ++ks)
+#pragma unroll
+          for (int q = 0; q < TB; ++q) dmma884(c[q].x, c[q].y, -pa[q][4 * ks], pb[q][4 * ks]);
+#pragma unroll
+        for (int q = 0; q < TB; ++q)
+          if (q < nb) *pc[q] = c[q];
       }
       __syncthreads();
     }
@@ -217,20 +242,63 @@ __device__ __forceinline__ Workspace carve(double* sm, double* global_A, int p, 
   return W;
 }
 
-// rss(beta) from the centre record (see the header comment); sd = d = beta - beta_hat in shared memory
-__device__ void centered_rss(const omc_nn_dense_t& a, int chain, const double* rec, const double* sd, double* red) {
-  const int p = a.p, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+// rss(beta) from the centre record (see the header comment); sd = d = beta - beta_hat in shared memory.  G is symmetric:
+// thread (c, row group) sums G[r][c] d_r over its rows -- consecutive threads read consecutive addresses and the loads
+// of a thread are independent, so they all go out together.
+__device__ void centered_rss(const omc_nn_dense_t& a, int chain, const double* __restrict__ rec,
+                             const double* __restrict__ sd, double* red) {
+  const int p = a.p, tid = threadIdx.x, nt = blockDim.x;
   const double* cen = a.center.ptr + (long long)chain * a.center.chain_stride;
   double acc = 0.0;
-  for (int r = warp; r < p; r += nw) {
-    double s = 0.0;
-    for (int c = lane; c < p; c += 32) s = fma(rec[(long long)r * p + c], sd[c], s);
-    s = omc_warp_sum(s);
-    if (lane == 0) acc = fma(sd[r], s, acc);
+  if (p <= nt) {
+    const int groups = nt / p, c = tid % p, grp = tid / p;
+    if (grp < groups) {
+      const int per = (p + groups - 1) / groups, r0 = grp * per, r1 = min(p, r0 + per);
+      double gd = 0.0;
+#pragma unroll 8
+      for (int r = r0; r < r1; ++r) gd = fma(rec[(long long)r * p + c], sd[r], gd);
+      acc = sd[c] * gd;
+      if (grp == 0) acc = fma(-2.0 * cen[p + c], sd[c], acc);
+    }
+  } else {
+    for (int c = tid; c < p; c += nt) {
+      double gd = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < p; ++r) gd = fma(rec[(long long)r * p + c], sd[r], gd);
+      acc = fma(sd[c], gd - 2.0 * cen[p + c], acc);
+    }
   }
-  for (int c = tid; c < p; c += blockDim.x) acc = fma(-2.0 * cen[p + c], sd[c], acc);
   const double total = omc_block_sum(acc, red);
   if (tid == 0) a.rss_out[(long long)chain * a.stats.chain_stride] = cen[2 * p] + total;
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP): the rows of G go straight into the padded matrix
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
 }
 
 template <int NT, bool GLOBAL_A>
@@ -253,19 +321,39 @@ __global__ void __launch_bounds__(NT) nn_blocked_draw_kernel(omc_nn_dense_t a) {
   const double lam = bvec_at(a.lambda, chain, 0, 1.0);
   const bool solve_only = a.mode == 1;
 
-  // ---- zero the padding, then the lower triangle of Q = lam*P0 + tau*G (sampler.py:180-186), row by row (coalesced)
+  // ---- the lower triangle of Q = lam*P0 + tau*G (sampler.py:180-186).  Shared-memory storage with an aligned, even-p
+  //      record: one elected thread sends the rows of G through the TMA engine (1-D bulk copies, row r up to its
+  //      diagonal), everybody zeroes the padding meanwhile, then the rows are scaled in place.  Otherwise plain
+  //      coalesced loads, row by row.
+  __shared__ __align__(8) unsigned long long bar;
+  const bool dense = a.prior_kind == OMC_MAT_DENSE;
+  const double* P0 = dense ? a.prior_P.ptr + (long long)chain * a.prior_P.chain_stride : nullptr;
+  const bool bulk = !GLOBAL_A && (p & 1) == 0 && ((((unsigned long long)rec) & 15ull) == 0);
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned total = 0;
+      for (int r = 0; r < p; ++r) total += (unsigned)(((r + 2) & ~1) * 8);
+      mbar_expect_tx(&bar, total);
+      for (int r = 0; r < p; ++r)
+        bulk_g2s(W.A + (long long)r * LD, rec + (long long)r * p, (unsigned)(((r + 2) & ~1) * 8), &bar);
+    }
+  }
   for (int e = tid; e < W.rows_pad * PLD; e += NT) W.Pn[e] = 0.0;
   for (int r = p + 1 + warp; r < W.rows_pad; r += NW)
     for (int c = lane; c < LD; c += 32) W.A[(long long)r * LD + c] = 0.0;
-  const bool dense = a.prior_kind == OMC_MAT_DENSE;
-  const double* P0 = dense ? a.prior_P.ptr + (long long)chain * a.prior_P.chain_stride : nullptr;
+  if (bulk) mbar_wait(&bar, 0);
   for (int r = warp; r < p; r += NW) {
     double* arow = W.A + (long long)r * LD;
     const double* grow = rec + (long long)r * p;
     for (int c = lane; c < LD; c += 32) {
       double q = 0.0;
       if (c <= r) {
-        q = tau * grow[c];
+        q = tau * (bulk ? arow[c] : grow[c]);
         if (dense) q = fma(lam, P0[(long long)r * p + c], q);
         else if (c == r) q = fma(lam, bmat_at(a.prior_kind, a.prior_P, chain, p, r, r), q);
         if (c == r && solve_only) q *= 1.0 + a.ridge_rel;     // multiplicative jitter: the centre needs no exact solve

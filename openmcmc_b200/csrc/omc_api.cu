@@ -32,10 +32,14 @@ struct omc_graph {
 namespace {
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
 
+// RING = false: row `it` of a [max_iter, count] store (rows beyond it are dropped); RING = true: slot it % max_iter of a
+// ring of max_iter slabs that a copy stream drains to the host while the next sweeps run
+template <bool RING>
 __global__ void store_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, long long count,
                                   const unsigned long long* iter, long long max_iter) {
-  const unsigned long long it = *iter;
-  if ((long long)it >= max_iter) return;
+  unsigned long long it = *iter;
+  if (RING) it %= (unsigned long long)max_iter;
+  else if ((long long)it >= max_iter) return;
   double* d = dst + it * count;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     d[i] = src[i];
@@ -139,7 +143,18 @@ int omc_store_copy(const double* src, double* dst, long long count, const unsign
   if (count == 0) return 0;
   long long blocks = (count + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  store_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, count, iter_counter, max_iter);
+  store_copy_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, count, iter_counter, max_iter);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_store_copy_ring(const double* src, double* dst, long long count, const unsigned long long* iter_counter,
+                        long long ring, void* stream) {
+  OMC_REQUIRE(src && dst && iter_counter && count >= 0 && ring >= 1, "omc_store_copy_ring: bad argument");
+  if (count == 0) return 0;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  store_copy_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, count, iter_counter, ring);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -75,19 +75,23 @@ def summarize(mcmc, params=None, elem_stride=None, max_lag: int = 127, group=Non
     [n_local, n_sel, 8], and after the all-gather `rhat`, `ess` (sum over all chains), `mean`, `var_plus` [n_sel].
     `elem_stride[param]` thins long parameters (C3: a strided subset of the field)."""
     out = {}
-    stored = int(mcmc.plan.iter_counter.item())
-    with torch.cuda.stream(mcmc.stream):
-        for s in mcmc.samplers:
-            if params is not None and s.param not in params:
-                continue
-            buf = mcmc._dev_store[s.param][:stored]
-            stride = (elem_stride or {}).get(s.param, 1)
-            rec = chain_stats(buf, elem_stride=stride, max_lag=max_lag)
-            allrec = gather_records(rec, group)
-            comb = rhat_combine(allrec)
-            out[s.param] = {"records": rec, "all_records": allrec, "rhat": comb[:, 0], "ess": comb[:, 1],
-                            "mean": comb[:, 2], "var_plus": comb[:, 3], "n_chains_total": allrec.shape[0]}
-    mcmc.stream.synchronize()
+    blocks = getattr(mcmc, "_blocks", None) or [mcmc]       # a run in chain blocks keeps its plans / stores per block
+    for s in mcmc.samplers:
+        if params is not None and s.param not in params:
+            continue
+        stride = (elem_stride or {}).get(s.param, 1)
+        recs = []
+        for blk in blocks:
+            with torch.cuda.stream(blk.stream):
+                buf, eff_stride = blk.device_samples(s.param, stride)
+                recs.append(chain_stats(buf, elem_stride=eff_stride, max_lag=max_lag))
+            blk.stream.synchronize()
+        rec = recs[0] if len(recs) == 1 else torch.cat(recs, dim=0)     # chain order = block order
+        allrec = gather_records(rec, group)
+        comb = rhat_combine(allrec)
+        out[s.param] = {"records": rec, "all_records": allrec, "rhat": comb[:, 0], "ess": comb[:, 1],
+                        "mean": comb[:, 2], "var_plus": comb[:, 3], "n_chains_total": allrec.shape[0]}
+    torch.cuda.synchronize()
     return out
 
 

@@ -557,8 +557,9 @@ def get_mixture(plan: Plan, host_state, dist) -> MixtureNormal:
     return cache[dist.response]
 
 
-def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
-    """Fitted values store[response][:, it] = dist.<predictor>.predictor(state).  ref: mcmc.py:109-111."""
+def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int, ring: bool = False):
+    """Fitted values store[response][:, it] = dist.<predictor>.predictor(state).  ref: mcmc.py:109-111.
+    n_iter rows, or (ring) a ring of n_iter slabs for the streamed store."""
     st = plan.state
     C = st.n_chains
     par = getattr(dist, predictor)
@@ -578,7 +579,7 @@ def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
 
         def launch():
             K.linear_predictor(C, n, [(X.vec(), th.vec(), X.cols, tr) for X, th, tr in terms], now)
-            K.store_copy(now, buf, C * n, plan.iter_counter, n_iter)
+            K.store_copy(now, buf, C * n, plan.iter_counter, n_iter, ring=ring)
 
         plan.emit(launch, f"fitted[{dist.response}]")
     elif isinstance(par, Identity):
@@ -587,7 +588,7 @@ def compile_fitted(plan: Plan, host_state, dist, predictor: str, n_iter: int):
             src = st.put(par.form, src.data, per_chain=True)
 
         def launch():
-            K.store_copy(src.data, buf, C * n, plan.iter_counter, n_iter)
+            K.store_copy(src.data, buf, C * n, plan.iter_counter, n_iter, ring=ring)
 
         plan.emit(launch, f"fitted[{dist.response}]")
     else:

@@ -57,6 +57,10 @@ def sample_once(sampler, state: dict, debug_draws: dict = None) -> dict:
     new = st.get_host(sampler.param)
     old = state[sampler.param]
     state[sampler.param] = new.reshape(np.shape(old)) if np.ndim(old) == 2 else new
+    if hasattr(sampler, "trim_host_state") and list(getattr(sampler, "extra_state_names", lambda: [])()):
+        # ReversibleJump rewrites knots, widths, coefficients and the basis matrix together with the count: the returned
+        # state is consistent, in the reference's shapes (sampler.py:57-67 contract)
+        sampler.trim_host_state(state, st.get_host)
     if hasattr(sampler, "_after_sample"):
         sampler._after_sample(plan)
     return state

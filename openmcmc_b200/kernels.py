@@ -316,7 +316,14 @@ def sum_log(x, n, out):
 
 
 def logdet_dense(P, n, out):
-    check(lib().omc_logdet_dense(_ptr(P), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_logdet_dense")
+    """log|P| of out.numel() dense SPD matrices; above n = 64 through the blocked factorisation (omc_dense_factor)."""
+    if n <= 64:
+        check(lib().omc_logdet_dense(_ptr(P), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_logdet_dense")
+        return
+    m = out.numel()
+    ws = nn_dense_workspace(m, n)
+    work = torch.empty(ws, dtype=torch.float64, device=P.device) if ws else None
+    dense_factor(P.reshape(m, n, n), n, logdet=out, workspace=work, n_mats=m)
 
 
 # ----------------------------------------------------------------------------- graphs / schedule
@@ -364,9 +371,10 @@ def run_schedule(sweep: Graph, store, n_burn, n_iter, n_thin):
     )
 
 
-def store_copy(src, dst, count, iter_counter, max_iter):
-    check(lib().omc_store_copy(_ptr(src), _ptr(dst), int(count), _ptr(iter_counter), int(max_iter), stream_ptr()),
-          "omc_store_copy")
+def store_copy(src, dst, count, iter_counter, max_iter, ring=False):
+    """Row *iter_counter of a [max_iter, count] store, or (ring=True) slab *iter_counter % max_iter of a ring."""
+    fn = lib().omc_store_copy_ring if ring else lib().omc_store_copy
+    check(fn(_ptr(src), _ptr(dst), int(count), _ptr(iter_counter), int(max_iter), stream_ptr()), "omc_store_copy")
 
 
 # ----------------------------------------------------------------------------- Metropolis-Hastings family

@@ -40,6 +40,10 @@ class LazyHostArray:
         return self.shape[0]
 
 
+STREAM_STORE_BYTES = 1 << 30   # device stores above this are streamed to the host during the run (stream_store=None)
+RING_BYTES = 2 << 30           # budget of the device ring of a streamed store (at least 2 slabs)
+
+
 @dataclass
 class MCMC:
     """ref: mcmc.py:18-85.  For n_chains == 1 `store[param]` has the reference shape (size, n_iter); for n_chains > 1
@@ -57,6 +61,10 @@ class MCMC:
     chain_offset: int = 0
     debug_draws: dict = None   # {param: {"z"|"g"|"u": array [n_sweeps, (C,) size]}} injected random streams
     probes: bool = False       # keep per-sampler intermediates (Q, b, L, mu, a*, b*) of the LAST sweep
+    stream_store: bool = None  # True: stored iterations leave the device as they are produced (device ring -> pinned
+    #                            staging -> host arrays on a copy stream, stream_store.py) and n_iter is no longer
+    #                            bounded by HBM; False: resident device store, one download at the end; None: stream when
+    #                            the store would exceed STREAM_STORE_BYTES
     upload_blocks: int = None  # > 1: run the chains as that many contiguous chain blocks, block k+1 being uploaded and
     #                            compiled while block k sweeps (chains are independent and the RNG is keyed by the
     #                            global chain id, so the draws are the same); None = one block per 4 GB of per-chain
@@ -83,6 +91,33 @@ class MCMC:
         self._prepared = None
         self.status = None
         self.timing = {}
+        self._init_store()
+
+    def _init_store(self):
+        """ref: mcmc.py:81-85 -- NaN-filled sample arrays exist before the run (through sampler.init_store, reference
+        shapes; a leading chain axis when n_chains > 1).  Skipped above 64 MB: the run allocates what it fills."""
+        total = 0
+        for s in self.samplers:
+            v = self.state.get(s.param)
+            total += int(np.size(v)) if v is not None and not isinstance(v, torch.Tensor) else 0
+        if total == 0 or total * max(self.n_iter, 1) * self.n_chains * 8 > (64 << 20):
+            return
+        try:
+            one = {}
+            for s in self.samplers:
+                one = s.init_store(current_state=self.state, store=one, n_iterations=self.n_iter)
+            one["log_post"] = np.full((self.n_iter, 1), np.nan)
+            if self.model.response is not None:
+                for response in self.model.response:
+                    one[response] = np.full((np.size(self.state[response]), self.n_iter), np.nan)
+        except Exception:      # a sampler without host-side shapes yet (e.g. per-chain tensors): the run fills the store
+            return
+        if self.n_chains == 1:
+            self.store = one
+        else:
+            C = self.n_chains
+            self.store = {k: (np.full((self.n_iter, C), np.nan) if k == "log_post" else np.broadcast_to(
+                v, (C,) + v.shape).copy()) for k, v in one.items()}
 
     # ------------------------------------------------------------------ device pipeline
     def prepare(self, warm_up=True, wait=True):
@@ -141,23 +176,37 @@ class MCMC:
                     s.compile(plan, self.state, dd.get(s.param))
                 valid_end = {k: False for k in plan.valid}
             sweep_ops.append(("sweep_counter", lambda: K.counter_add(plan.sweep_counter, 1)))
-            # store epilogue (ref: mcmc.py:105-111)
+            # store epilogue (ref: mcmc.py:105-111): resident [n_iter, C, size] buffers, or -- streamed -- a ring of a few
+            # slabs that stream_store.StoreStreamer drains to the host while the next sweeps run
             plan.ops = store_ops = []
             n_iter = max(self.n_iter, 1)
             self._dev_store = {}
             self._store_names = []
+            stored = []
             for s in self.samplers:
-                names = [s.param] + list(getattr(s, "stored_state_names", lambda: [])())
-                for name in names:
-                    if name in self._dev_store:
-                        continue
-                    arr = st[name]
-                    buf = plan.new(n_iter, C, arr.size, fill=float("nan"))
-                    self._dev_store[name] = buf
-                    self._store_names.append(name)
-                    store_ops.append((f"store[{name}]", (lambda arr=arr, buf=buf: K.store_copy(
-                        arr.data, buf, C * arr.size, plan.iter_counter, n_iter))))
-            self._dev_logpost = plan.new(n_iter, C, fill=float("nan"))
+                for name in [s.param] + list(getattr(s, "stored_state_names", lambda: [])()):
+                    if name not in [nm for nm, _ in stored]:
+                        stored.append((name, st[name]))
+            slab = 8 * C * (sum(arr.size for _, arr in stored) + 1)
+            if self.model.response is not None:
+                slab += 8 * C * sum(st[r].rows for r in self.model.response)
+            streamed = self.stream_store if self.stream_store is not None else slab * n_iter > STREAM_STORE_BYTES
+            self._streamed = bool(streamed) and self.n_iter >= 1
+            self._ring = max(2, min(8, int(RING_BYTES // max(slab, 1)))) if self._streamed else 0
+            self._slab_bytes = slab
+            rows = self._ring if self._streamed else n_iter
+            ring = self._streamed
+            if self._streamed:
+                from openmcmc_b200 import stream_store
+
+                self._staging_warm = stream_store.warm(dev)
+            for name, arr in stored:
+                buf = plan.new(rows, C, arr.size, fill=float("nan"))
+                self._dev_store[name] = buf
+                self._store_names.append(name)
+                store_ops.append((f"store[{name}]", (lambda arr=arr, buf=buf: K.store_copy(
+                    arr.data, buf, C * arr.size, plan.iter_counter, rows, ring=ring))))
+            self._dev_logpost = plan.new(rows, C, fill=float("nan"))
             self._logpost_now = plan.new(C)
             saved_valid = dict(plan.valid)
             rj = plan.__dict__.get("_rj")
@@ -166,12 +215,12 @@ class MCMC:
             else:
                 engine.compile_log_post(plan, self.state, self.model, self._logpost_now)
             store_ops.append(("store[log_post]", lambda: K.store_copy(self._logpost_now, self._dev_logpost, C,
-                                                                        plan.iter_counter, n_iter)))
+                                                                        plan.iter_counter, rows, ring=ring)))
             self._dev_fitted = {}
             if self.model.response is not None:
                 for response, predictor in self.model.response.items():
                     self._dev_fitted[response] = engine.compile_fitted(plan, self.state, self.model[response],
-                                                                       predictor, n_iter)
+                                                                       predictor, rows, ring=ring)
             store_ops.append(("iter_counter", lambda: K.counter_add(plan.iter_counter, 1)))
             plan.valid = saved_valid
             # prologue: quantities the steady-state sweep assumes valid, computed from the initial state
@@ -229,7 +278,37 @@ class MCMC:
         n_iter = self.n_iter if n_iter is None else n_iter
         n_thin = self.n_thin if n_thin is None else n_thin
         with torch.cuda.stream(self.stream):
+            self.plan.iter_counter.zero_()     # a run stores from iteration 0 again, as the reference overwrites its store
+            if self._streamed and n_iter > 0:
+                return self._run_streamed(n_burn, n_iter, n_thin)
             K.run_schedule(self._sweep_graph, self._store_graph, n_burn, n_iter, n_thin)
+
+    def _run_streamed(self, n_burn, n_iter, n_thin):
+        """The schedule of omc_run_schedule with the store graph of every stored iteration fenced against the copy
+        stream that drains the device ring (stream_store.py).  Returns when the last slab has landed in host memory."""
+        from openmcmc_b200 import stream_store
+
+        st, C = self._prepared, self.n_chains
+        self._staging_warm.join()
+        self._host_store = {name: np.empty((n_iter, C, st[name].size)) for name in self._store_names}
+        self._host_logpost = np.empty((n_iter, C))
+        self._host_fitted = {r: np.empty((n_iter, C, buf.shape[-1])) for r, buf in self._dev_fitted.items()}
+        entries = [(self._dev_store[name], self._host_store[name]) for name in self._store_names]
+        entries.append((self._dev_logpost, self._host_logpost))
+        entries += [(self._dev_fitted[r], self._host_fitted[r]) for r in self._dev_fitted]
+        streamer = stream_store.StoreStreamer(st.device, entries, self._ring, n_iter)
+        try:
+            if n_burn:
+                K.run_schedule(self._sweep_graph, None, n_burn, 0, n_thin)
+            for it in range(n_iter):
+                K.run_schedule(self._sweep_graph, None, 1, 0, n_thin)     # the n_thin sweeps of stored iteration `it`
+                streamer.before_store(it, self.stream)
+                self._store_graph.launch(1)
+                streamer.after_store(it, self.stream)
+        finally:
+            streamer.finish()
+        self._streamed_rows = n_iter
+        self.timing["streamed_d2h_bytes"] = streamer.d2h_bytes
 
     def collect(self):
         """Download the stored samples and the final state (ref shapes; see class docstring)."""
@@ -243,20 +322,24 @@ class MCMC:
         for s in self.samplers:
             for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
                 owner.setdefault(name, s)
-        self._mask_padded_store_device()
+        streamed = self._streamed and getattr(self, "_streamed_rows", 0) > 0
+        if streamed:
+            self._mask_padded_store_host()
+        else:
+            self._mask_padded_store_device()
         for name in self._store_names:
             s = owner[name]
-            buf = K.download(self._dev_store[name][: self.n_iter])             # [n_iter, C, size]
+            buf = self._host_store[name] if streamed else K.download(self._dev_store[name][: self.n_iter])  # [n_iter, C, size]
             d2h += buf.nbytes
             arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
             if name == s.param:
                 arr = self._shape_store(s, arr, st[name])
             self.store[name] = arr[0] if C == 1 else arr
-        lp = K.download(self._dev_logpost[: self.n_iter])
+        lp = self._host_logpost if streamed else K.download(self._dev_logpost[: self.n_iter])
         d2h += lp.nbytes
         self.store["log_post"] = lp.reshape(self.n_iter, 1) if C == 1 else lp
         for response, buf in self._dev_fitted.items():
-            h = K.download(buf[: self.n_iter])
+            h = self._host_fitted[response] if streamed else K.download(buf[: self.n_iter])
             d2h += h.nbytes
             arr = np.transpose(h, (1, 2, 0))
             self.store[response] = arr[0] if C == 1 else arr
@@ -308,18 +391,32 @@ class MCMC:
                     buf.masked_fill_(idx >= cnt, float("nan"))
         self.stream.synchronize()
 
+    def _mask_padded_store_host(self):
+        """The same NaN mask on a streamed store (host arrays [n_iter, C, size])."""
+        rj = self._rj_sampler()
+        if rj is None or rj.param not in self._host_store:
+            return
+        cnt = self._host_store[rj.param]                                    # [n_iter, C, 1]
+        for name in rj.stored_state_names():
+            if name in self._host_store:
+                buf = self._host_store[name]
+                buf[np.arange(buf.shape[-1]).reshape(1, 1, -1) >= cnt] = np.nan
+
+    def device_samples(self, name, elem_stride=1):
+        """Stored draws of `name` as a device tensor [n_stored, C, n_sel] for the diagnostics kernels: a view of the
+        resident store, or -- streamed -- the strided selection of the host store uploaded again."""
+        n_done = int(self.plan.iter_counter.item())
+        if self._streamed and getattr(self, "_streamed_rows", 0) > 0:
+            sel = np.ascontiguousarray(self._host_store[name][:n_done, :, ::elem_stride])
+            return K.upload(sel, self._prepared.device), 1
+        return self._dev_store[name][:n_done], elem_stride
+
     def _trim_padded_state(self):
         """Final state of one chain in the reference's exact shapes (theta (1,n), beta (n,1), B (n_data,n))."""
         rj = self._rj_sampler()
         if rj is None or self.n_chains != 1:
             return
-        n = int(np.ravel(self.state[rj.param])[0])
-        b = rj.basis
-        self.state[b.knots] = np.asarray(self.state[b.knots]).reshape(1, -1)[:, :n]
-        self.state[b.widths] = np.asarray(self.state[b.widths]).reshape(1, -1)[:, :n]
-        var = rj.matching_params["variable"]
-        self.state[var] = np.asarray(self.state[var]).reshape(-1, 1)[:n]
-        self.state[b.matrix] = np.asarray(self.state[b.matrix])[:, :n]
+        rj.trim_host_state(self.state, lambda name: self.state[name])
 
     @staticmethod
     def _shape_store(sampler, arr, dev_arr):
@@ -402,7 +499,7 @@ class MCMC:
                 st[key] = on_dev[key] if key in on_dev else (v[lo:hi] if per_chain(v) else v)
             sub = MCMC(st, self.samplers, self.model, n_burn=self.n_burn, n_iter=self.n_iter, n_thin=self.n_thin,
                        n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo,
-                       upload_blocks=1)
+                       upload_blocks=1, stream_store=False)   # blocks sweep asynchronously: their stores stay resident
             # every block keeps the eager warm-up pass in front of its captures: skipping it for the later blocks
             # bought nothing (the host waits behind the next block's transfer anyway) and a capture can be
             # invalidated by the first-time allocations of a block with a different chain count

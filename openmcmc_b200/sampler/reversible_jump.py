@@ -58,6 +58,27 @@ class ReversibleJump(MetropolisHastings):
         b = self.basis
         return [b.knots, b.widths, self.matching_params["variable"]] if b is not None else []
 
+    def trim_host_state(self, state: dict, fetch):
+        """Padded device state (one chain) -> the reference's exact shapes in `state`: count scalar, knots / widths
+        (1, n), coefficients (n, 1), basis (n_data, n).  The allocation vector of a mixture prior on the coefficients
+        follows the count, as the reference's birth / death callbacks grow / shrink it
+        (tests/test_reversible_jump.py:91,117 of the reference).  `fetch(name)` returns the padded host copy."""
+        from openmcmc_b200.parameter import MixtureParameterVector
+
+        b, var = self.basis, self.matching_params["variable"]
+        n = int(np.ravel(np.asarray(fetch(self.param)))[0])
+        state[b.knots] = np.asarray(fetch(b.knots)).reshape(1, -1)[:, :n]
+        state[b.widths] = np.asarray(fetch(b.widths)).reshape(1, -1)[:, :n]
+        state[var] = np.asarray(fetch(var)).reshape(-1, 1)[:n]
+        Bm = np.asarray(fetch(b.matrix))
+        state[b.matrix] = Bm.reshape(-1, Bm.shape[-1])[:, :n]
+        prior = self.model.get(var) if hasattr(self.model, "get") else None
+        if prior is not None and isinstance(getattr(prior, "mean", None), MixtureParameterVector):
+            alloc = prior.mean.allocation
+            if alloc in state and np.size(state[alloc]) != n:
+                state[alloc] = np.zeros((n, 1), dtype=np.asarray(state[alloc]).dtype)
+        return n
+
     def _pattern(self, plan, host_state):
         """Match the attached model onto the kernel's fixed structure; PlanError for anything else."""
         from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform

@@ -421,3 +421,46 @@ def test_rj_full_model_free_running_fits_the_data():
     assert 3 <= np.median(n_last) <= 6
     for p in ("beta", "theta", "omega"):
         assert 0 < smp[p].accept_rate.count["accept"] < smp[p].accept_rate.count["proposal"]
+
+
+def test_reversible_jump_sample_call_returns_a_consistent_state():
+    """`rj.sample(state)` outside an MCMC run (the reference's sampler contract, sampler.py:57-67): the returned dict
+    holds the new count TOGETHER with the knots, widths, coefficients, basis matrix and allocation vector of that
+    count, step by step along a golden reference chain."""
+    from scipy import sparse
+
+    from openmcmc_b200.sampler.reversible_jump import GaussianKernelBasis, ReversibleJump
+    from oracle import rj
+    from test_oracle_rj_vs_golden import tol_of
+
+    g = dict(np.load(os.path.join(GOLD, "rj_normal_n50_k4.npz")))
+    n_steps, n_max, nd = g["birth"].size, int(g["n_max"]), g["X"].size
+    n0 = int(g["n_before"][0])
+    th0, om0, be0 = (g[k + "_before"][0][:n0] for k in ("theta", "omega", "beta"))
+    mdl = _rj_model(g, str(g["response"]))
+    lim = g["match_limits"]
+    rjs = ReversibleJump(param="n_basis", model=mdl, associated_params=["theta", "omega"] if g["with_omega"] else ["theta"],
+                         n_max=n_max, birth_probability=float(g["birth_probability"]),
+                         matching_params={"variable": "beta", "matrix": "B", "scale": float(g["match_scale"]),
+                                          "limits": None if np.isnan(lim[0]) else [float(lim[0]), float(lim[1])]},
+                         basis=GaussianKernelBasis(matrix="B", locations="X", knots="theta", widths="omega"))
+    state = {"y": g["y"].reshape(-1, 1), "beta": be0.reshape(-1, 1), "tau_y": float(g["tau_y"]), "P": sparse.eye(nd),
+             "B": rj.make_basis(g["X"], th0, om0), "n_basis": np.array([[float(n0)]]), "X": g["X"].reshape(-1, 1),
+             "theta": th0.reshape(1, -1), "omega": om0.reshape(1, -1), "mu_beta": np.zeros((1, 1)),
+             "tau_beta": float(g["tau_beta"]) * np.ones((1, 1)), "rho": float(g["rho"]), "alloc_beta": np.zeros((n0, 1)),
+             "a_omega": float(g["a_omega"]) * np.ones((1, 1)), "b_omega": float(g["b_omega"]) * np.ones((1, 1))}
+    dbg = np.stack([g["u_move"], g["theta_new"], g["omega_new"], g["beta_new"], g["del_index"], g["u_accept"]], axis=1)
+    changed = 0
+    for it in range(min(n_steps, 12)):
+        before = int(np.ravel(state["n_basis"])[0])
+        state = rjs.sample(state, debug_draws={"rj": dbg[it].reshape(1, 1, 6)})
+        na = int(g["n_after"][it])
+        changed += na != before
+        assert int(np.ravel(state["n_basis"])[0]) == na
+        assert state["theta"].shape == (1, na) and state["omega"].shape == (1, na) and state["beta"].shape == (na, 1)
+        assert state["B"].shape == (nd, na) and state["alloc_beta"].shape == (na, 1)
+        np.testing.assert_allclose(state["theta"].ravel(), g["theta_after"][it][:na], rtol=1e-12)
+        np.testing.assert_allclose(state["beta"].ravel(), g["beta_after"][it][:na], rtol=1e-8, atol=tol_of(g, it) * (it + 1))
+        np.testing.assert_allclose(state["B"], rj.make_basis(g["X"], state["theta"].ravel(), state["omega"].ravel()),
+                                   rtol=1e-12, atol=1e-300)
+    assert changed >= 1     # the golden chain has accepted births / deaths among these steps
