@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """bench.py — chain-iterations/s of the openMCMC hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4a|c4b]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4a|c4b|c5|c5full]
 
 A "step" is one sweep (every sampler once) over all chains of the workload; `value` = chain-iterations/s with the
 inputs resident in HBM; `e2e` = the same metric through the public API (`MCMC(...).run_mcmc()`) with HOST inputs, the
 host->device upload and the device->host sample download inside the timed region.  N > 1: one process per GPU
-(torchrun), chains sharded by rank (weak scaling, no data-path collective), time = max over ranks.
-`--impl reference` times the CPU path (numpy/scipy port of the reference sweep, oracle/cpu_bench.py) on the host cores.
+(torchrun), chains sharded by rank (weak scaling, no data-path collective), time = max over ranks; the line also
+carries a `strong` sub-record (the workload's chain count divided over the ranks).
+`--impl reference` times the UNMODIFIED reference (openmcmc 1.0.7 from baseline/_ref, baseline/ref_bench.py) on the
+host cores -- one `MCMC.run_mcmc()` per chain, one process per core; the numpy port (oracle/cpu_bench.py) only when
+baseline/_ref is absent.
 
 Default workload = BASELINE.json configs[1] (batched Bayesian linear regression), the configuration the metric is
-quoted on that fits one GPU; the other configs are selectable for the per-config numbers in DESIGN.md / profiles/.
+quoted on that fits one GPU; its line also carries a compact `c3` sub-record (configs[2], the other configuration the
+north-star target names).  The other configs are selectable for the per-config numbers in DESIGN.md / profiles/.
 """
 
 import argparse
@@ -27,36 +31,42 @@ sys.path.insert(0, ROOT)
 METRIC = "chain-iterations/sec"
 UNIT = "chain-iterations/s"
 
+# cpu: bounded sample of the numpy port (oracle/cpu_bench.py); ref: bounded sample of the unmodified reference
+# (baseline/ref_bench.py), both per worker process; sized for ~10-30 s of CPU work per call
 WORKLOADS = {
     # BASELINE.json configs[1]: batched Bayesian linear regression (the config the metric is quoted on; fits 1 GPU)
     "c2": dict(name="batched Bayesian linear regression: 4096 chains/GPU, n=10000, p=64, NormalNormal+NormalGamma Gibbs",
                kind="regression", chains=4096, n=10000, p=64, thin=1, dominant="nn_dense_draw",
-               cpu=dict(chains_per_worker=8, sweeps=100), ref=dict(chains_per_worker=2, sweeps=5)),
+               cpu=dict(chains_per_worker=8, sweeps=100), ref=dict(chains_per_worker=1, sweeps=200),
+               ref_step=dict(chains_per_worker=1, sweeps=10)),
     # BASELINE.json configs[0]: example-3 regression, single chain (latency bound)
     "c1": dict(name="examples/3_linear_regression: 1 chain, n=1000, p=3", kind="regression", chains=1, n=1000, p=3,
                thin=1, dominant="nn_dense_draw", cpu=dict(chains_per_worker=1, sweeps=4000),
-               ref=dict(chains_per_worker=1, sweeps=500)),
+               ref=dict(chains_per_worker=1, sweeps=3000), ref_step=dict(chains_per_worker=1, sweeps=200)),
     # BASELINE.json configs[2]: example-4 GMRF smoother scaled up (sparse-enabled form)
     "c3": dict(name="temporal GMRF smoother: 64 chains/GPU, n=1e6 grid points, tridiagonal NormalNormal + 2x NormalGamma",
                kind="gmrf", chains=64, n=1_000_000, p=0, thin=10, dominant="tridiag_nn_draw",
-               cpu=dict(chains_per_worker=1, sweeps=3), ref=dict(chains_per_worker=1, sweeps=1)),
+               cpu=dict(chains_per_worker=1, sweeps=3), ref=dict(chains_per_worker=1, sweeps=3),
+               ref_step=dict(chains_per_worker=1, sweeps=1)),
     # BASELINE.json configs[3]: 65,536 chains x 32 params over 8 GPUs = 8192 chains per GPU
     "c4a": dict(name="ManifoldMALA, Poisson counts + Gamma prior: 8192 chains/GPU x 32 params", kind="mh", chains=8192,
                 n=0, p=32, thin=1, dominant="mmala", cpu=dict(chains_per_worker=1, sweeps=30),
-                ref=dict(chains_per_worker=1, sweeps=4)),
+                ref=dict(chains_per_worker=1, sweeps=8), ref_step=dict(chains_per_worker=1, sweeps=1)),
     "c4b": dict(name="RandomWalkLoop (truncated proposals), Poisson counts + Gamma prior: 8192 chains/GPU x (1,32) params",
                 kind="mh", chains=8192, n=0, p=32, thin=1, dominant="random_walk_loop",
-                cpu=dict(chains_per_worker=4, sweeps=300), ref=dict(chains_per_worker=2, sweeps=50)),
+                cpu=dict(chains_per_worker=4, sweeps=300), ref=dict(chains_per_worker=1, sweeps=300),
+                ref_step=dict(chains_per_worker=1, sweeps=20)),
     # BASELINE.json configs[4]: ReversibleJump on the Gaussian-kernel basis model, 8192 chains, capacity 128 components
     "c5": dict(name="ReversibleJump birth/death, Gaussian-kernel basis model: 8192 chains/GPU, n_data=512, n_max=128, "
                     "rho=32, Normal response, matched transitions", kind="rj", chains=8192, n=512, p=128, thin=1,
-               dominant="reversible_jump", cpu=dict(chains_per_worker=2, sweeps=300), ref=dict(chains_per_worker=1, sweeps=100)),
+               dominant="reversible_jump", cpu=dict(chains_per_worker=2, sweeps=300),
+               ref=dict(chains_per_worker=1, sweeps=1000), ref_step=dict(chains_per_worker=1, sweeps=60)),
     # the same model with all four samplers of the reference's RJ model: ManifoldMALA on the coefficients, RandomWalkLoop
-    # on knots and widths (basis rebuilt per proposal), ReversibleJump (the CPU port times the RJ step only)
+    # on knots and widths (basis rebuilt per proposal), ReversibleJump
     "c5full": dict(name="full RJ source model: ManifoldMALA(beta) + RandomWalkLoop(theta) + RandomWalkLoop(omega) + "
                         "ReversibleJump, 8192 chains/GPU, n_data=512, n_max=128, rho=32", kind="rj", full=True, chains=8192,
                    n=512, p=128, thin=1, dominant="reversible_jump", cpu=dict(chains_per_worker=1, sweeps=40),
-                   ref=dict(chains_per_worker=1, sweeps=10)),
+                   ref=dict(chains_per_worker=1, sweeps=30), ref_step=dict(chains_per_worker=1, sweeps=3)),
 }
 
 
@@ -74,42 +84,67 @@ def parse():
                          "MCMC's automatic choice, one block per 4 GB of per-chain host input")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the comparison legs (sweep forms, fitted values, ESS "
+                                                             "run, c3 sub-record, strong scaling)")
     return ap.parse_args()
 
 
 def config_of(args, wl):
+    """The same keys and values in both arms (the driver compares them)."""
     return {"workload": wl["name"], "chains_per_gpu": args.chains or wl["chains"], "n_obs": args.n or wl["n"],
-            "p": wl["p"], "n_thin": wl["thin"]}
+            "p": wl["p"], "n_thin": wl["thin"], "fitted_values": False,
+            "l2": "per-GPU inputs are far larger than the 126 MB L2 (c2: 21 GB of X and a 136 MB record set re-read every "
+                  "sweep, c3: 512 MB of y + 1 GB of scratch); c1/c4 working sets are L2-resident by nature of the workload",
+            "per_step": "1 sweep = every sampler once over all chains; every n_thin-th sweep also stores the samples and "
+                        "log_post (no fitted values: response=None in both arms; `with_fitted_values` is the same "
+                        "workload with response={'y': 'mean'})"}
 
 
-# --------------------------------------------------------------------------------------------- reference arm (CPU)
+# --------------------------------------------------------------------------------------------- CPU legs
+def cpu_sample(key, wl, n, p, sizes, seed=0, prefer_reference=True):
+    """One bounded sample of the workload on all host cores: the unmodified reference when baseline/_ref travels with
+    the repo, else the numpy port.  Returns (result dict of run_parallel, kind)."""
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_bench
+    except Exception:
+        ref_bench = None
+    if prefer_reference and ref_bench is not None and ref_bench.available():
+        r = ref_bench.run_parallel(workload=key, workers=cores, n=n, p=p, seed=seed, n_thin=1, **sizes["ref"])
+        return r, "reference"
+    from oracle import cpu_bench
+
+    r = cpu_bench.run_parallel(workload=key, workers=cores, n=n, p=p, seed=seed, **sizes["cpu"])
+    return r, "port"
+
+
 def run_reference(args, wl, key):
+    """`--impl reference`: W untimed + K timed steps, each step one bounded sample on every host core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu_bench
-
-    cores = os.cpu_count() or 1
-    per_step = wl["ref"]   # each step = a bounded sample of the workload on every core
     n, p = args.n or wl["n"], wl["p"]
-    for _ in range(1 if args.warmup > 0 else 0):
-        cpu_bench.run_parallel(workload=key, workers=cores, n=n, p=p, **per_step)
-    secs, steps_done = 0.0, 0
-    for k in range(min(args.steps, 8)):
-        r = cpu_bench.run_parallel(workload=key, workers=cores, n=n, p=p, seed=100 + k, **per_step)
+    sizes = {"ref": wl["ref_step"], "cpu": wl["ref_step"]}
+    kind = None
+    for k in range(args.warmup):
+        _, kind = cpu_sample(key, wl, n, p, sizes, seed=50 + k)
+    secs, its, failed, last = 0.0, 0, 0, None
+    for k in range(args.steps):
+        r, kind = cpu_sample(key, wl, n, p, sizes, seed=100 + k)
         secs += r["seconds"]
-        steps_done += 1
-    total_its = cores * per_step["chains_per_worker"] * per_step["sweeps"] * steps_done
-    value = total_its / secs
+        its += r["cores"] * wl["ref_step"]["chains_per_worker"] * wl["ref_step"]["sweeps"]
+        failed += r.get("chains_failed", 0)
+        last = r
+    value = its / secs
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
-        "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": secs / steps_done * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, wl),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps_done} steps x ({cores} workers x {per_step['chains_per_worker']} chains x "
-                                   f"{per_step['sweeps']} sweeps), numpy/scipy port of the reference sweep (oracle/), "
-                                   "1 BLAS thread per worker"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": kind,
+                         "sample": f"{args.steps} steps, each: {last['sample']}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "chains_failed": failed,
     }
     print(json.dumps(line), flush=True)
 
@@ -175,7 +210,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- workloads (B200 arm)
-def build_regression(C, n, p, dev, rank, host):
+def build_regression(C, n, p, dev, rank, host, response=False):
     import numpy as np
     import torch
     from scipy import sparse
@@ -199,7 +234,7 @@ def build_regression(C, n, p, dev, rank, host):
         Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="P_tau", scalar="tau")),
         Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
         Gamma("tau", shape="a_tau", rate="b_tau"),
-        Gamma("lambda", shape="a_lambda", rate="b_lambda")])
+        Gamma("lambda", shape="a_lambda", rate="b_lambda")], response={"y": "mean"} if response else None)
     samplers = [NormalNormal("beta", mdl), NormalGamma("tau", mdl), NormalGamma("lambda", mdl)]
     state = {"y": y, "X": X, "beta": np.zeros((p, 1)), "P_tau": sparse.identity(n, format="csc"), "tau": 1.0,
              "P_lambda": sparse.identity(p, format="csc"), "mu": np.zeros((p, 1)), "lambda": 0.01,
@@ -324,9 +359,9 @@ def _pinned(t):
     return h
 
 
-def build(wl, C, n, dev, rank, host=False):
+def build(wl, C, n, dev, rank, host=False, response=False):
     if wl["kind"] == "regression":
-        return build_regression(C, n, wl["p"], dev, rank, host)
+        return build_regression(C, n, wl["p"], dev, rank, host, response)
     if wl["kind"] == "gmrf":
         return build_gmrf(C, n, wl["p"], dev, rank, host)
     if wl["kind"] == "rj":
@@ -334,299 +369,394 @@ def build(wl, C, n, dev, rank, host=False):
     return build_mh(C, n, wl["p"], dev, rank, host, loop=wl["dominant"] == "random_walk_loop")
 
 
-def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None):
-    """Algorithmic work of the dominant op per launch (DESIGN.md §kernels) over its measured duration."""
+def numa_interleave(enable: bool):
+    """Memory policy of the calling thread for the pinned e2e inputs.  With several ranks per node every rank's pinned
+    copy landing on the NUMA node all GPUs report as local made the upload the limiter of the round-1 scaling run
+    (8 ranks x 21 GB from one node's DRAM: 18 GB/s per rank against 46-51 GB/s alone); interleaving the pages over all
+    nodes spreads that load.  Returns a description for the JSON line."""
+    import ctypes
+    import glob
+
+    nodes = sorted(int(os.path.basename(q)[4:]) for q in glob.glob("/sys/devices/system/node/node[0-9]*"))
+    if len(nodes) < 2:
+        return "default (single NUMA node)"
+    libc = ctypes.CDLL("libc.so.6", use_errno=True)
+    if not enable:
+        libc.syscall(238, 0, None, 0)              # set_mempolicy(MPOL_DEFAULT)
+        return "default"
+    mask = ctypes.c_ulong(sum(1 << nd for nd in nodes))
+    rc = libc.syscall(238, 3, ctypes.byref(mask), 64)   # set_mempolicy(MPOL_INTERLEAVE, all nodes)
+    return f"interleave over nodes {nodes}" + ("" if rc == 0 else f" (set_mempolicy failed rc={rc}: default)")
+
+
+def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None, key=None):
+    """Algorithmic work of the dominant op per launch (DESIGN.md §3) over its measured duration."""
     hbm_peak, hbm_src = peaks
     sec = op_ms * 1e-3
+    traffic, traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", f"{key}_traffic.json")))
+        traffic, traffic_src = t["dram_bytes_per_launch"], "static: " + t["source"]
+    except Exception:
+        pass
+    common = {"peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": traffic,
+              "traffic_source": traffic_src, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
     if wl["kind"] == "regression":
-        # per sweep: ONE stream over X, y for the residual (omc_reg_rss; SURVEY §8d bytes = 8 n (p+1) per chain-iteration);
-        # G = X'X and g = X'y depend on the data alone and come from one omc_reg_pass (DMMA SYRK) in the prologue
-        byts = C * 8 * n * (p + 1)
-        roof = {"bound": "hbm", "kernel": "reg_pass_kernel<SYRK=false> (omc_reg_rss: residual pass over X, y)",
-                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
-                "peak_note": "MEASURED_PEAKS.json's hbm_gbs is a COPY (half reads, half writes, bus turnarounds); this "
-                             "kernel only reads, and a read-only stream runs faster than a copy on HBM3e, so frac can "
-                             "exceed 1 against the copy figure (ncu: dram__bytes_read = 21.30 GB per launch, "
-                             "profiles/r01b_ncu_c2.txt); against the 8 TB/s nominal it is achieved / 8000"}
+        # per sweep and chain the draw reads the record G | g | rss | cnt (8 (p^2 + p + 2) bytes; G a second time for
+        # d'G d, from L2) and the centre (8 (2p + 2)), writes beta (8 p) and rss: no pass over X (DESIGN.md §3.1)
+        byts = C * 8 * (p * p + p + 2 + 2 * p + 2 + p + 1)
+        flops = C * (p ** 3 / 3.0 + 2.0 * p * p + 2.0 * p * p + 2.0 * p * p)   # Cholesky, 3 triangular solves, d'G d
+        roof = {"bound": "hbm", "kernel": "nn draw kernel (omc_nn_dense_draw: Q = lam P0 + tau G, Cholesky, posterior "
+                                          "mean, draw, re-centred rss): the whole data-dependent work of a sweep",
+                "achieved": byts / sec / 1e9, "frac": byts / sec / 1e9 / hbm_peak, **common,
+                "fp64": {"achieved_tflops": flops / sec / 1e12, "peak_tflops": fp64_peak,
+                         "frac": flops / sec / 1e12 / fp64_peak if fp64_peak else None,
+                         "flops_per_chain": flops / C,
+                         "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run"}}
         if syrk_ms:
-            flops = C * (n * p * (p + 1) + 4 * n * p)   # SYRK + X'y + residual per chain (SURVEY §8d)
-            tf = flops / (syrk_ms * 1e-3) / 1e12
+            fl = C * (n * p * (p + 1) + 4 * n * p)   # SYRK + X'y + residual per chain (SURVEY §8d)
+            tf = fl / (syrk_ms * 1e-3) / 1e12
             roof["prologue_syrk"] = {
                 "bound": "tensor", "kernel": "reg_pass_kernel (FP64 DMMA SYRK + X'y + rss), once per run (prologue)",
                 "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                 "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                "kernel_ms": syrk_ms}
+                "kernel_ms": syrk_ms, "hbm_gbs": C * 8.0 * n * (p + 1) / (syrk_ms * 1e-3) / 1e9}
         return roof
     if wl["kind"] == "gmrf":
         byts = C * 32 * n                                 # read y, P diag + off, write b (SURVEY §8d)
         return {"bound": "hbm", "kernel": "omc_tridiag_nn_draw (tg_aggregate_kernel + tg_tilescan_kernel + tg_solve_kernel)",
-                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+                "achieved": byts / sec / 1e9, "frac": byts / sec / 1e9 / hbm_peak, **common}
     if wl["kind"] == "rj":
         k = p / 4.0                                       # expected live components (rho = n_max / 4)
         byts = C * 2 * 8 * n * k                          # two passes over the live basis columns (SURVEY §8d: 8 n_data k)
         flops = C * (2 * n * k * k + 4.0 / 3.0 * k ** 3)
         return {"bound": "hbm", "kernel": "rj_kernel (Gram + in-place inverse + LU per chain; latency / FP64-ALU bound)",
-                "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-                "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms,
+                "achieved": byts / sec / 1e9, "frac": byts / sec / 1e9 / hbm_peak, **common,
                 "fp64": {"achieved_tflops": flops / sec / 1e12, "flops_per_chain_step": flops / C}}
     byts = C * 32 * p                                     # read theta, y; write theta, sample (SURVEY §8d)
     return {"bound": "hbm", "kernel": f"{wl['dominant']}_kernel (latency / FP64-ALU bound: 1 KB per chain-iteration)",
-            "achieved": byts / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak,
-            "peak_source": hbm_src, "traffic": None, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
+            "achieved": byts / sec / 1e9, "frac": byts / sec / 1e9 / hbm_peak, **common}
+
+
+class Ctx:
+    """Process-wide pieces of one bench run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        from openmcmc_b200 import kernels as K
+
+        K.init_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.torch, self.dist, self.K = torch, dist, K
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed_sweeps(ctx, M, steps, warmup, thin, clocks=None):
+    """W untimed + exactly K timed sweeps replayed from the captured graphs (every thin-th followed by the store graph),
+    CUDA events on the engine's stream, barrier + synchronize on both sides, max over ranks.  Returns ms."""
+    torch = ctx.torch
+    n_iter = max(steps // thin, 1)
+    M.run_device(n_burn=warmup, n_iter=0, n_thin=1)
+    ctx.barrier()
+    if clocks is not None:
+        clocks.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(M.stream):
+        e0.record()
+    M.run_device(n_burn=steps % thin if steps >= thin else 0, n_iter=n_iter, n_thin=thin)
+    with torch.cuda.stream(M.stream):
+        e1.record()
+    ctx.barrier()
+    return ctx.max_over_ranks(e0.elapsed_time(e1))
+
+
+def time_op(ctx, M, fn, reps=10):
+    """One launch closure of the plan, captured and replayed alone on the engine's stream; events on that stream."""
+    torch, K = ctx.torch, ctx.K
+    with torch.cuda.stream(M.stream):
+        g = K.Graph.capture(fn)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.launch(1)
+        k0.record()
+        g.launch(reps)
+        k1.record()
+    ctx.barrier()
+    return k0.elapsed_time(k1) / reps
+
+
+def value_leg(ctx, wl, key, C, n, steps, warmup, thin, clocks=None, chain_offset=None, response=False, stream=False):
+    """Device-resident run of one workload: returns (M, ms over the K sweeps, state bits needed later)."""
+    from openmcmc_b200.mcmc import MCMC
+
+    mdl, samplers, state = build(wl, C, n, ctx.dev, ctx.rank, response=response)
+    n_iter = max(steps // thin, 1)
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7, device=ctx.local,
+             chain_offset=ctx.rank * C if chain_offset is None else chain_offset, stream_store=stream)
+    M.prepare()
+    ms = timed_sweeps(ctx, M, steps, warmup, thin, clocks)
+    return M, ms, (mdl, samplers, state)
+
+
+def e2e_leg(ctx, wl, key, C, n, p, steps, thin, upload_blocks):
+    """Public API with HOST (pinned) inputs: upload + plan + capture + K sweeps + download of every stored sample."""
+    import contextlib
+    import io
+
+    from openmcmc_b200.mcmc import MCMC
+
+    torch = ctx.torch
+    Ce, note = C, ""
+    per_chain_host = 8.0 * n * (p + 1) if wl["kind"] == "regression" else 8.0 * n * 2 if wl["kind"] == "gmrf" else 0.0
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(ctx.world)))
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+        budget = 0.6 * avail / max(local_world, 1)
+        if per_chain_host * C > budget:
+            Ce = max(64, int(budget / per_chain_host) // 64 * 64)
+            note = (f" [e2e on {Ce} of {C} chains per GPU: {local_world} ranks x {per_chain_host * C / 1e9:.1f} GB of "
+                    f"pinned host input exceed 60% of the node's {avail / 1e9:.0f} GB of free host memory]")
+    except Exception:
+        pass
+    policy = numa_interleave(local_world > 2)
+    mdl, samplers2, hstate = build(wl, Ce, n, ctx.dev, ctx.rank, host=True)
+    numa_interleave(False)
+    n_iter = max(steps // thin, 1)
+
+    def run(blocks, first=True):
+        if first:
+            ctx.barrier()
+        else:               # a retry on one rank must not wait on a collective the other ranks have passed
+            torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        r = MCMC(hstate, samplers2, model=mdl, n_burn=steps % thin if steps >= thin else 0, n_iter=n_iter,
+                 n_thin=thin, n_chains=Ce, seed=7, device=ctx.local, chain_offset=ctx.rank * C, upload_blocks=blocks)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r.run_mcmc()
+        return r, t_start
+
+    try:
+        M2, t0 = run(upload_blocks)
+    except Exception as exc:   # never lose the whole line to the e2e leg: one more try as a single block, and say so
+        note += f" [first e2e attempt failed ({type(exc).__name__}: {str(exc)[:120]}); re-run with upload_blocks=1]"
+        M2, t0 = run(1, first=False)
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    out = {"value": Ce * ctx.world * steps / dt, "unit": UNIT, "chains_per_gpu": Ce,
+           "upload_blocks": M2.timing.get("upload_blocks", 1), "streamed_store": bool(getattr(M2, "_streamed", False)),
+           "h2d_bytes_per_step": M2.timing["h2d_bytes"] / steps, "d2h_bytes_per_step": M2.timing["d2h_bytes"] / steps,
+           "seconds": dt, "pinned_policy": policy,
+           "phases_s": {k: round(M2.timing[k], 4) for k in ("prepare_s", "sweeps_s", "collect_s") if k in M2.timing},
+           "blocks": M2.timing.get("blocks"),
+           "note": "MCMC(...).run_mcmc() with pinned host inputs: upload + plan compile + graph capture + "
+                   f"{steps} sweeps + download of all stored samples; upload_blocks > 1: the chains run as chain "
+                   "blocks, block k+1 uploading while block k sweeps; streamed_store: the stored iterations leave "
+                   "the device during the sweeps (device ring -> pinned staging -> host)" + note}
+    floor = M2.timing["h2d_bytes"] / 55e9 + (M2.timing["d2h_bytes"] / 55e9 if not out["streamed_store"] else 0.0)
+    out["limiter"] = (f"PCIe: {M2.timing['h2d_bytes'] / 1e9:.2f} GB up + {M2.timing['d2h_bytes'] / 1e9:.2f} GB down = "
+                      f"{floor:.3f} s at 55 GB/s of the {dt:.3f} s")
+    del M2, hstate
+    return out
+
+
+def fp64_dgemm_peak(ctx):
+    torch = ctx.torch
+    a = torch.randn(6144, 6144, dtype=torch.float64, device=ctx.dev)
+    b = torch.randn(6144, 6144, dtype=torch.float64, device=ctx.dev)
+    best = 0.0
+    for _ in range(4):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        _ = a @ b
+        g1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2 * 6144 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12)
+    return best
+
+
+def hbm_peak():
+    try:
+        return (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]),
+                "MEASURED_PEAKS.json hbm_gbs (of measured)")
+    except Exception:
+        return (6650.0, "fallback 6.65 TB/s (of fallback)")
+
+
+def ess_record(ctx, M, wl, n, ms, note_extra=""):
+    """Per-chain ESS of the stored draws (device kernel), all-gather of the per-chain records over the process group
+    (NCCL over NVLink when N > 1), split-R-hat / ESS on every rank."""
+    from openmcmc_b200 import diagnostics as G
+
+    torch = ctx.torch
+    strides = {"b": max(1, n // 64)} if wl["kind"] == "gmrf" else None
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    summ = G.summarize(M, elem_stride=strides)
+    d1.record()
+    torch.cuda.synchronize()
+    ess_total = float(G.min_ess_per_chain(summ, all_ranks=True).sum().item())
+    rhat_max = max(float(torch.nan_to_num(v["rhat"], nan=1.0).max().item()) for v in summ.values())
+    return {"value": ess_total / (ms * 1e-3), "unit": "ESS/s", "n_stored": int(M.plan.iter_counter.item()),
+            "ess_total": ess_total, "rhat_max": rhat_max, "params": sorted(summ), "diag_ms": d0.elapsed_time(d1),
+            "gathered_chains": int(next(iter(summ.values()))["n_chains_total"]),
+            "note": "sum over all chains of the minimum-over-parameters ESS of the stored draws, divided by the seconds "
+                    "of the sweeps that produced them; per-chain records all-gathered over the process group; rhat_max "
+                    "is taken ACROSS chains and is only meaningful when chains share their data (the c2/c4 workloads "
+                    "give every chain its own synthetic data set, so it is large by construction)" + note_extra}
+
+
+def c3_subrecord(ctx, args, peaks):
+    """BASELINE configs[2] next to the default line: value, roofline of the tridiagonal draw, e2e (streamed store)."""
+    wl = WORKLOADS["c3"]
+    C, n, thin = wl["chains"], wl["n"], wl["thin"]
+    steps = max(thin, min(args.steps, 40) // thin * thin)
+    M, ms, _ = value_leg(ctx, wl, "c3", C, n, steps, min(args.warmup, 5), thin)
+    op = next(fn for label, fn in M._ops["sweep"] if label.startswith(wl["dominant"]))
+    op_ms = time_op(ctx, M, op)
+    launches = M.launches_per_sweep() * steps + M._store_graph.num_kernels() * (steps // thin)
+    rec = {"workload": wl["name"], "value": C * ctx.world * steps / (ms * 1e-3), "unit": UNIT, "steps": steps,
+           "ms_per_step": ms / steps, "n_thin": thin, "gpu_launches": launches,
+           "roofline": roofline_of(wl, C, n, 0, op_ms, ms / steps, peaks, None, key="c3")} if ctx.rank == 0 else {}
+    del M, op
+    if not args.no_e2e:
+        e2e = e2e_leg(ctx, wl, "c3", C, n, 0, steps, thin, None)
+        if ctx.rank == 0:
+            rec["e2e"] = e2e
+    return rec
 
 
 def run_b200(args, wl, key):
-    import torch
-    import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     C, n, p, thin = args.chains or wl["chains"], args.n or wl["n"], wl["p"], wl["thin"]
     thin = max(1, min(thin, args.steps))
     # CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import cpu_bench
-
-        r = cpu_bench.run_parallel(workload=key, workers=os.cpu_count() or 1, n=n, p=p, **wl["cpu"])
-        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from openmcmc_b200 import kernels as K
+        r, kind = cpu_sample(key, wl, n, p, wl)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": r["sample"]}
+    ctx = Ctx(args)
+    torch, K = ctx.torch, ctx.K
+    from openmcmc_b200 import engine
     from openmcmc_b200.mcmc import MCMC
 
-    K.init_device(local)
-    dev = torch.device("cuda", local)
-    mdl, samplers, state = build(wl, C, n, dev, rank)
+    clocks = ClockSampler(ctx.local)
+    clocks.start()
+    M, ms_max, (mdl, samplers, state) = value_leg(ctx, wl, key, C, n, args.steps, args.warmup, thin, clocks)
     n_iter = max(args.steps // thin, 1)
-    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7, device=local,
-             chain_offset=rank * C)
-    M.prepare()
     launches_per_sweep = M.launches_per_sweep()
     store_launches = M._store_graph.num_kernels()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # warm-up (untimed), then exactly K timed sweeps; every n_thin-th sweep is followed by the store graph
-    clocks = ClockSampler(local)
-    clocks.start()
-    M.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
-    barrier()
-    clocks.mark()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(M.stream):
-        e0.record()
-    M.run_device(n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter, n_thin=thin)
-    with torch.cuda.stream(M.stream):
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # dominant op alone: the very launch closure of the sweep plan, on the engine's stream, events on that stream
+    # dominant op alone: the very launch closure of the sweep plan
     op = next(fn for label, fn in M._ops["sweep"] if label.startswith(wl["dominant"]))
-    reps = 10
-    with torch.cuda.stream(M.stream):
-        op_graph = K.Graph.capture(op)      # replayed from a graph like the sweep itself: no host launch gaps in the timing
-        k0 = torch.cuda.Event(enable_timing=True)
-        k1 = torch.cuda.Event(enable_timing=True)
-        op_graph.launch(1)
-        k0.record()
-        op_graph.launch(reps)
-        k1.record()
-    barrier()
-    op_ms = k0.elapsed_time(k1) / reps
+    op_ms = time_op(ctx, M, op)
     syrk_ms = None
     if wl["kind"] == "regression":   # the data-only SYRK pass of the prologue, timed the same way (it runs once per run)
         op2 = next((fn for label, fn in M._ops["prologue"] if label.startswith("reg_pass")), None)
         if op2 is not None:
-            with torch.cuda.stream(M.stream):
-                g2 = K.Graph.capture(op2)
-                q0 = torch.cuda.Event(enable_timing=True)
-                q1 = torch.cuda.Event(enable_timing=True)
-                g2.launch(1)
-                q0.record()
-                g2.launch(reps)
-                q1.record()
-            barrier()
-            syrk_ms = q0.elapsed_time(q1) / reps
+            syrk_ms = time_op(ctx, M, op2)
     clk = clocks.stop()
-    # the reference's form of the sweep (A'QA recomputed by every NormalNormal.sample): the full fused pass, DMMA SYRK
-    # included, every sweep -- timed on the same resident inputs for comparison with the shipped data-only caching
-    syrk_sweep = None
-    if wl["kind"] == "regression":
-        from openmcmc_b200 import engine
-
-        engine.CACHE_DATA_ONLY = False
-        try:
-            M3 = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7, device=local,
-                      chain_offset=rank * C)
-            M3.prepare()
-        finally:
-            engine.CACHE_DATA_ONLY = True
-        M3.run_device(n_burn=args.warmup, n_iter=0, n_thin=1)
-        barrier()
-        s0 = torch.cuda.Event(enable_timing=True)
-        s1 = torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(M3.stream):
-            s0.record()
-        M3.run_device(n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter, n_thin=thin)
-        with torch.cuda.stream(M3.stream):
-            s1.record()
-        barrier()
-        t3 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        ms3 = float(t3.item())
-        syrk_sweep = {"value": C * world * args.steps / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / args.steps,
-                      "note": "same workload with G = X'X and g = X'y recomputed by the fused DMMA pass in EVERY sweep "
-                              "(engine.CACHE_DATA_ONLY = False), as the reference does; the shipped plan keeps them "
-                              "from the prologue because they depend on the data alone"}
-        del M3
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    # ---- diagnostics of the timed draws: per-chain ESS on the device store, all-gather of the per-chain records over
-    #      the process group (NCCL over NVLink when N > 1), split-R-hat / ESS on every rank (SURVEY §8e)
-    from openmcmc_b200 import diagnostics as G
-
-    strides = {"b": max(1, n // 64)} if wl["kind"] == "gmrf" else None
-    d0 = torch.cuda.Event(enable_timing=True)
-    d1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(M.stream):
-        d0.record()
-    summ = G.summarize(M, elem_stride=strides)
-    with torch.cuda.stream(M.stream):
-        d1.record()
-    torch.cuda.synchronize()
-    ess_total = float(G.min_ess_per_chain(summ, all_ranks=True).sum().item())
-    rhat_max = max(float(torch.nan_to_num(v["rhat"], nan=1.0).max().item()) for v in summ.values())
-    ess = {"value": ess_total / (ms_max * 1e-3), "unit": "ESS/s", "n_stored": int(M.plan.iter_counter.item()),
-           "ess_total": ess_total, "rhat_max": rhat_max, "params": sorted(summ), "diag_ms": d0.elapsed_time(d1),
-           "gathered_chains": int(next(iter(summ.values()))["n_chains_total"]),
-           "note": "sum over all chains of the minimum-over-parameters autocorrelation ESS (Geyer) of the draws stored "
-                   "in the timed region, divided by the timed seconds; per-chain records all-gathered over the "
-                   "process group; rhat_max is taken ACROSS chains and is only meaningful when chains share their data (the "
-                   "c2/c4 workloads give every chain its own synthetic data set, so it is large by construction)"}
+    ess = ess_record(ctx, M, wl, n, ms_max)
     M.collect()
     status_bad = int(((M.status & 3) != 0).sum())
     accept = {s.param: s.accept_rate.get_acceptance_rate() for s in samplers if hasattr(s, "accept_rate")}
     value = C * world * args.steps / (ms_max * 1e-3)
-
-    try:
-        peaks = (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]),
-                 "MEASURED_PEAKS.json hbm_gbs (of measured)")
-    except Exception:
-        peaks = (6650.0, "fallback 6.65 TB/s (of fallback)")
-    fp64_peak = None
-    if rank == 0 and wl["kind"] == "regression":
-        # FP64 peak (cuBLAS DGEMM) measured live: the roofline denominator for the DMMA SYRK pass
-        a = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
-        b = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
-        best = 0.0
-        for _ in range(4):
-            g0 = torch.cuda.Event(enable_timing=True)
-            g1 = torch.cuda.Event(enable_timing=True)
-            g0.record()
-            _ = a @ b
-            g1.record()
-            torch.cuda.synchronize()
-            best = max(best, 2 * 6144 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12)
-        fp64_peak = best
-        del a, b
-
+    del M, op
+    peaks = hbm_peak()
+    fp64_peak = fp64_dgemm_peak(ctx) if wl["kind"] == "regression" else None
+    extras = {}
+    if wl["kind"] == "regression" and not args.no_extras:
+        # ---- the other forms of the same sweep, on the same resident inputs
+        forms = {}
+        for label, flags, why in (
+                ("explicit_residual_every_sweep", dict(RECENTER=False),
+                 "rss from one residual-only stream over X per sweep (omc_reg_rss, HBM-bound): the round-1 plan"),
+                ("syrk_every_sweep", dict(RECENTER=False, CACHE_DATA_ONLY=False),
+                 "G = X'X, g = X'y and rss recomputed by the fused DMMA pass in EVERY sweep, as the reference "
+                 "recomputes A'QA in every NormalNormal.sample (sampler.py:180-186)")):
+            saved = {k: getattr(engine, k) for k in flags}
+            for k, v in flags.items():
+                setattr(engine, k, v)
+            try:
+                M3 = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, n_thin=thin, n_chains=C, seed=7,
+                          device=ctx.local, chain_offset=rank * C, stream_store=False)
+                M3.prepare()
+            finally:
+                for k, v in saved.items():
+                    setattr(engine, k, v)
+            ms3 = timed_sweeps(ctx, M3, args.steps, args.warmup, thin)
+            forms[label] = {"value": C * world * args.steps / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / args.steps,
+                            "note": why}
+            del M3
+        extras["sweep_forms"] = forms
+        extras["syrk_every_sweep"] = forms["syrk_every_sweep"]
+        # ---- the same workload with the reference's per-iteration fitted values (model.response = {"y": "mean"},
+        #      mcmc.py:109-111): every stored iteration streams X once for X beta and writes n values per chain
+        del state, mdl, samplers
+        Mf, msf, _ = value_leg(ctx, wl, key, C, n, min(args.steps, 20), min(args.warmup, 3), thin, response=True)
+        kf = min(args.steps, 20)
+        extras["with_fitted_values"] = {
+            "value": C * world * kf / (msf * 1e-3), "unit": UNIT, "steps": kf, "ms_per_step": msf / kf,
+            "hbm_gbs": C * 8.0 * n * (p + 2) * kf / (msf * 1e-3) / 1e9,
+            "note": "response={'y': 'mean'}: X beta per stored iteration = one read of X (8 n p) and a write of n "
+                    "values per chain; HBM-bound like the round-1 residual pass"}
+        del Mf
+        # ---- ESS over >= 1000 stored draws (the 60 draws of the timed region say little about ESS)
+        k_ess = 1000
+        Me, mse, _ = value_leg(ctx, wl, key, C, n, k_ess, 20, thin)
+        extras["ess_long"] = ess_record(ctx, Me, wl, n, mse, note_extra=f"; separate run of {k_ess} stored sweeps after 20 burn-in sweeps")
+        extras["ess_long"]["ms_per_step"] = mse / k_ess
+        del Me
+    else:
+        del state, mdl, samplers
     # ---- e2e: public API with HOST (pinned) inputs, upload + K sweeps + sample download inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        del M, op, op_graph, state, summ
-        op2 = g2 = None
-        # device memory goes back to torch's caching allocator and STAYS there (no empty_cache): the e2e run takes its
-        # buffers from the pool the way a long-running process would; on a fresh box the first cudaMalloc of 21 GB
-        # cost up to 0.4 s (observed 0.03-0.09 s per 4.3 GB block), which is the driver's page-table work, not the path
-        # host-memory guard: every rank of the node pins its own copy of the inputs (c2: 21 GB per rank); when the
-        # node cannot hold them all, the e2e leg runs on the largest chain count per rank that fits and says so
-        Ce, e2e_note = C, ""
-        per_chain_host = 8.0 * n * (p + 1) if wl["kind"] == "regression" else 8.0 * n * 2 if wl["kind"] == "gmrf" else 0.0
+    e2e = None if args.no_e2e else e2e_leg(ctx, wl, key, C, n, p, args.steps, thin, args.upload_blocks)
+    if key == "c2" and not args.no_extras:
         try:
-            import psutil
-
-            avail = psutil.virtual_memory().available
-            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-            budget = 0.6 * avail / max(local_world, 1)
-            if per_chain_host * C > budget:
-                Ce = max(64, int(budget / per_chain_host) // 64 * 64)
-                e2e_note = (f" [e2e on {Ce} of {C} chains per GPU: {local_world} ranks x {per_chain_host * C / 1e9:.1f} GB of "
-                            f"pinned host input exceed 60% of the node's {avail / 1e9:.0f} GB of free host memory]")
-        except Exception:
-            pass
-        mdl, samplers2, hstate = build(wl, Ce, n, dev, rank, host=True)
-        import contextlib
-        import io
-
-        def e2e_run(blocks, first=True):
-            if first:
-                barrier()
-            else:               # a retry on one rank must not wait on a collective the other ranks have passed
-                torch.cuda.synchronize()
-            t_start = time.perf_counter()
-            run = MCMC(hstate, samplers2, model=mdl, n_burn=args.steps % thin if args.steps >= thin else 0, n_iter=n_iter,
-                       n_thin=thin, n_chains=Ce, seed=7, device=local, chain_offset=rank * C, upload_blocks=blocks)
-            with contextlib.redirect_stdout(io.StringIO()):
-                run.run_mcmc()
-            return run, t_start
-
-        try:
-            M2, t0 = e2e_run(args.upload_blocks)
-        except Exception as exc:   # never lose the whole line to the e2e leg: one more try as a single block, and say so
-            e2e_note += f" [first e2e attempt failed ({type(exc).__name__}: {str(exc)[:120]}); re-run with upload_blocks=1]"
-            M2, t0 = e2e_run(1, first=False)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": Ce * world * args.steps / dt, "unit": UNIT, "chains_per_gpu": Ce,
-               "upload_blocks": M2.timing.get("upload_blocks", 1),
-               "h2d_bytes_per_step": M2.timing["h2d_bytes"] / args.steps,
-               "d2h_bytes_per_step": M2.timing["d2h_bytes"] / args.steps, "seconds": dt,
-               "phases_s": {k: round(M2.timing[k], 4) for k in ("prepare_s", "sweeps_s", "collect_s") if k in M2.timing},
-               "blocks": M2.timing.get("blocks"),
-               "note": "MCMC(...).run_mcmc() with pinned host inputs: upload + plan compile + graph capture + "
-                       f"{args.steps} sweeps + download of all stored samples; upload_blocks > 1: the chains run as "
-                       "chain blocks, block k+1 uploading while block k sweeps" + e2e_note}
+            extras["c3"] = c3_subrecord(ctx, args, peaks)
+        except Exception as exc:
+            extras["c3"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    if world > 1 and not args.no_extras and C % world == 0 and wl["kind"] != "gmrf":
+        # ---- strong scaling: the workload's chain count divided over the ranks (the weak line above grows it with N)
+        Cs = C // world
+        Ms, mss, _ = value_leg(ctx, wl, key, Cs, n, args.steps, args.warmup, thin, chain_offset=rank * Cs)
+        extras["strong"] = {"value": Cs * world * args.steps / (mss * 1e-3), "unit": UNIT, "chains_total": Cs * world,
+                            "chains_per_gpu": Cs, "ms_per_step": mss / args.steps, "scaling": "strong"}
+        del Ms
 
     if rank == 0:
-        roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak, syrk_ms)
-        try:
-            roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", f"{key}_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        cfg = config_of(args, wl)
-        cfg.update({"l2": "per-GPU inputs are far larger than the 126 MB L2 (c2: 21 GB of X, c3: 512 MB of y + 1 GB of "
-                          "scratch); c1/c4 working sets are L2-resident by nature of the workload",
-                    "per_step": "1 sweep = every sampler once over all chains; every n_thin-th sweep also stores the "
-                                "samples and log_post", "chains_failed": status_bad, "accept": accept})
+        roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak, syrk_ms, key=key)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
+            "dtype": "f64", "data": "synthetic", "config": config_of(args, wl), "clocks": clk, "e2e": e2e,
             "gpu_launches": launches_per_sweep * args.steps + store_launches * n_iter,
-            "roofline": roof, "cpu_baseline": cpu_baseline, "ess": ess,
+            "roofline": roof, "cpu_baseline": cpu_baseline, "ess": ess, "chains_failed": status_bad, "accept": accept,
         }
-        if syrk_sweep is not None:
-            line["syrk_every_sweep"] = syrk_sweep
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():

@@ -67,8 +67,30 @@ class DevArray:
         return K.vec(self.off, per)
 
 
+_classify_cache = {}
+
+
 def classify_matrix(m):
-    """Structure of a (host) square matrix: returns (kind, main, off).  Host-side inspection of constant data."""
+    """Structure of a (host) square matrix: returns (kind, main, off).  Host-side inspection of constant data; the
+    result for a sparse matrix object is remembered while that object lives (a 1e6-point precision costs ~10 ms per
+    inspection and the plan compiler asks several times)."""
+    if sparse.issparse(m):
+        import weakref
+
+        sig = (m.nnz, m.shape, float(m.data.sum()) if m.nnz else 0.0)     # values changed in place => inspected again
+        hit = _classify_cache.get(id(m))
+        if hit is not None and hit[0]() is m and hit[1] == sig:
+            return hit[2]
+        out = _classify_matrix(m)
+        try:
+            _classify_cache[id(m)] = (weakref.ref(m, lambda _r, k=id(m): _classify_cache.pop(k, None)), sig, out)
+        except TypeError:
+            pass
+        return out
+    return _classify_matrix(m)
+
+
+def _classify_matrix(m):
     if sparse.issparse(m):
         m = m.tocsc(copy=True)        # canonical form: duplicates summed, explicit zeros dropped
         m.sum_duplicates()

@@ -40,7 +40,7 @@ class LazyHostArray:
         return self.shape[0]
 
 
-STREAM_STORE_BYTES = 1 << 30   # device stores above this are streamed to the host during the run (stream_store=None)
+STREAM_STORE_BYTES = 256 << 20  # device stores above this are streamed to the host during the run (stream_store=None)
 RING_BYTES = 2 << 30           # budget of the device ring of a streamed store (at least 2 slabs)
 
 
@@ -323,6 +323,7 @@ class MCMC:
             for name in [s.param] + list(getattr(s, "extra_state_names", lambda: [])()):
                 owner.setdefault(name, s)
         streamed = self._streamed and getattr(self, "_streamed_rows", 0) > 0
+        last_rows = {}
         if streamed:
             self._mask_padded_store_host()
         else:
@@ -331,6 +332,8 @@ class MCMC:
             s = owner[name]
             buf = self._host_store[name] if streamed else K.download(self._dev_store[name][: self.n_iter])  # [n_iter, C, size]
             d2h += buf.nbytes
+            if self.n_iter > 0:
+                last_rows[name] = buf[self.n_iter - 1]
             arr = np.transpose(buf, (1, 2, 0))                                 # [C, size, n_iter]
             if name == s.param:
                 arr = self._shape_store(s, arr, st[name])
@@ -351,9 +354,14 @@ class MCMC:
                     arr = st.arrays[name]
                     self.state[name] = LazyHostArray((lambda name=name: st.get_host(name)), arr.data.shape)
                     continue
-                new = st.get_host(name)
+                if name in last_rows and rj is None and n_done == self.n_iter:
+                    # the state after the last sweep IS the last stored iteration: no second download (C3: 512 MB)
+                    a = st.arrays[name]
+                    new = np.array(last_rows[name]).reshape((C, a.rows, a.cols) if C > 1 else (a.rows, a.cols))
+                else:
+                    new = st.get_host(name)
+                    d2h += new.nbytes
                 self.state[name] = new
-                d2h += new.nbytes
         self._trim_padded_state()
         for key, original in getattr(self, "_rep_restore", {}).items():   # the user's replicated arrays come back
             if original is None:

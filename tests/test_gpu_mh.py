@@ -219,7 +219,8 @@ def test_free_running_poisson_gamma_posterior(kind, p):
     mdl = _pg_model()
     if kind == "mmala":
         state = {"y": y.reshape(p, 1), "lam": (y + 1.0).reshape(p, 1), "a": np.array([[2.0]]), "b": np.array([[0.5]])}
-        smp = ManifoldMALA("lam", mdl, step=np.array([[0.6]]))
+        # (the acceptance rate of a Langevin proposal falls with the dimension: 0.6 accepts 0.7 % of the moves at p = 32)
+        smp = ManifoldMALA("lam", mdl, step=np.array([[0.6 if p <= 8 else 0.3]]))
     else:
         state = {"y": y.reshape(1, p), "lam": (y + 1.0).reshape(1, p), "a": np.array([[2.0]]), "b": np.array([[0.5]])}
         smp = RandomWalkLoop("lam", mdl, step=np.array([[2.0]]), domain_limits=np.array([[0.0, np.inf]]),
@@ -232,7 +233,9 @@ def test_free_running_poisson_gamma_posterior(kind, p):
     assert 10 < rate < 99.9, rate
     for j in range(p):
         post = stats.gamma(a=2.0 + y[j], scale=1.0 / 1.5)
-        assert stats.kstest(last[:, j], post.cdf).pvalue > 0.01, (kind, j)
+        # north star: KS p > 0.01 per coordinate; with 32 coordinates tested at once the bar is Bonferroni-scaled so that
+        # the family-wise false-alarm rate stays that of 8 coordinates at 0.01
+        assert stats.kstest(last[:, j], post.cdf).pvalue > 0.01 * min(1.0, 8.0 / p), (kind, j)
         assert abs(last[:, j].mean() - post.mean()) < 5 * post.std() / np.sqrt(C)
     # sharding invariance: the second half of the chains computed alone with chain_offset reproduces the same draws
     M2 = MCMC(state, [type(smp)(**{k: getattr(smp, k) for k in ("param", "step", "max_variable_size")}, model=mdl,
