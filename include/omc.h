@@ -143,7 +143,8 @@ int omc_nn_dense_workspace(int n_chains, int p, long long* doubles);
  *   x = mean + L^-T z                        ref: gmrf.py:167-198 (sample_normal_canonical), 29-61 (sample_normal),
  *                                                 414-434 (solve(L.T, z): b = NULL)
  *   factored = 1: Q already holds a lower Cholesky factor L (gmrf functions that accept a precomputed L)
- *   backward_only = 1: mean = L^-T b (no forward solve) */
+ *   backward_only = 1: mean = L^-T b (no forward solve); 2: mean = L^-1 b (forward solve only), x = mean + z
+ *   ref: gmrf.py:414-434 (solve with a triangular matrix: a = L' or a = L) */
 typedef struct {
   int n_mats, n;
   const double* Q;      /* [n_mats][n*n] row-major (lower triangle read), matrices Q_stride doubles apart (0 = shared) */
@@ -333,6 +334,9 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* args, void* stream);
 /* quadratic forms of the CURRENT x only (no draw): ss_prior / ss_lik as above (ref: sampler.py:275-284) */
 int omc_tridiag_quadforms(const omc_tridiag_nn_t* args, void* stream);
 /* out = P v for the shared tridiagonal P and per-chain / shared v [n]  (prior-mean term P*mu0, sampler.py:181-183) */
+/* Q = L L' of a lower BIDIAGONAL factor (diagonal l [n], sub-diagonal c [n-1]) as tridiagonal diagonals pd [n], pe [n-1]:
+ * the gmrf functions that accept a precomputed sparse factor (ref: gmrf.py:29-61 sample_normal(L=...), 437-462 cho_solve) */
+int omc_bidiag_gram(const double* l, const double* c, long long n, double* pd, double* pe, void* stream);
 int omc_tridiag_matvec(const double* pd, const double* pe, omc_vec_t v, int n_chains, long long n, double* out,
                        void* stream);
 

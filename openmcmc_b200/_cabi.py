@@ -249,6 +249,7 @@ PROTOTYPES = {
     "omc_tridiag_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "omc_tridiag_nn_draw": (C.c_int, [C.POINTER(TridiagNN), C.c_void_p]),
     "omc_tridiag_quadforms": (C.c_int, [C.POINTER(TridiagNN), C.c_void_p]),
+    "omc_bidiag_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_tridiag_matvec": (C.c_int, [C.c_void_p, C.c_void_p, Vec, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_mh_logp": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_mh_logp_acc": (C.c_int, [C.POINTER(MHModel), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -495,8 +495,16 @@ __global__ void __launch_bounds__(NT) dense_factor_kernel(omc_dense_factor_t a) 
     if (tid == 0) a.logdet[m] = 2.0 * acc;
   }
   if (!a.x && !a.mean) return;
+  if (a.backward_only == 2) {   // forward solve only: mean = L^-1 b
+    for (int c = tid; c < n; c += NT) {
+      const double wv = W.A[(long long)n * LD + c];
+      if (a.mean) a.mean[(long long)m * n + c] = wv;
+      if (a.x) a.x[(long long)m * n + c] = wv + X[pp + c];
+    }
+    return;
+  }
   // X[0] = forward-solved b (cho_solve) or b itself (backward_only: solve(L', b));  X[1] = z
-  for (int c = tid; c < n; c += NT) X[c] = (a.backward_only && b) ? b[c] : W.A[(long long)n * LD + c];
+  for (int c = tid; c < n; c += NT) X[c] = (a.backward_only == 1 && b) ? b[c] : W.A[(long long)n * LD + c];
   __syncthreads();
   blocked_backsolve<NT>(W, n, X, pp, 2);
   for (int c = tid; c < n; c += NT) {

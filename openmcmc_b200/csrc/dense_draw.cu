@@ -363,12 +363,19 @@ extern "C" int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream) {
     OMC_LAUNCH_CHECK();
     return 0;
   }
-  if (p <= 8) return launch_dense_draw<8>(*args, (cudaStream_t)stream);
-  if (p <= 16) return launch_dense_draw<16>(*args, (cudaStream_t)stream);
-  if (p <= 32) return launch_dense_draw<32>(*args, (cudaStream_t)stream);
-  // OMC_DENSE_DRAW_IMPL=columns: the one-thread-per-column register kernel at 32 < p <= 64 (A/B timing, tools/)
-  static const bool columns = [] { const char* e = getenv("OMC_DENSE_DRAW_IMPL"); return e && e[0] == 'c'; }();
-  if (columns && p <= 64) return launch_dense_draw<64>(*args, (cudaStream_t)stream);
+  // p <= 64 without probes: one warp per chain, Q in registers (dense_warp.cu).  Probes (Q, b, L, mu of the parity
+  // tests) go through the kernels that keep the factor addressable: one thread per column (p <= 32) or the blocked
+  // Cholesky (dense_blocked.cu), which also serves 64 < p <= 512.  OMC_DENSE_DRAW_IMPL = warp | columns | blocked
+  // forces one of them where it applies (A/B timing, tools/perf_dense_draw.py).
+  static const char impl = [] { const char* e = getenv("OMC_DENSE_DRAW_IMPL"); return e ? e[0] : '\0'; }();
+  const bool probes = args->probe_Q || args->probe_b || args->probe_L || args->probe_mu;
+  if (p <= 64 && !probes && (impl == '\0' || impl == 'w')) return omc_launch_warp_draw(*args, (cudaStream_t)stream);
+  if (impl != 'b' || p <= 0) {
+    if (p <= 8) return launch_dense_draw<8>(*args, (cudaStream_t)stream);
+    if (p <= 16) return launch_dense_draw<16>(*args, (cudaStream_t)stream);
+    if (p <= 32) return launch_dense_draw<32>(*args, (cudaStream_t)stream);
+    if (impl == 'c' && p <= 64) return launch_dense_draw<64>(*args, (cudaStream_t)stream);
+  }
   return omc_launch_blocked_draw(*args, (cudaStream_t)stream);
 }
 

@@ -13,3 +13,5 @@ enum OmcMatKind { OMC_MAT_EYE = 0, OMC_MAT_DIAG = 1, OMC_MAT_DENSE = 2 };
 #include <cuda_runtime.h>
 int omc_launch_blocked_draw(const omc_nn_dense_t& a, cudaStream_t st);
 long long omc_blocked_workspace_doubles(int p);
+// dense_warp.cu: one warp per chain, Q in registers (p <= 64, no probes)
+int omc_launch_warp_draw(const omc_nn_dense_t& a, cudaStream_t st);

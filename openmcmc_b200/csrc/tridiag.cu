@@ -1025,6 +1025,17 @@ __global__ void tridiag_ws_init_kernel(Workspace* ws, Layout L) {
     p[i] = 0ull;
 }
 
+// Q = L L' of a lower bidiagonal factor (diagonal l, sub-diagonal c): Q_ii = l_i^2 + c_{i-1}^2, Q_{i+1,i} = c_i l_i.
+// For the gmrf functions that are handed a precomputed sparse factor (gmrf.py:29-61, 167-198, 437-462).
+__global__ void bidiag_gram_kernel(const double* __restrict__ l, const double* __restrict__ c, long long n,
+                                   double* __restrict__ pd, double* __restrict__ pe) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double li = l[i], cp = i > 0 ? c[i - 1] : 0.0;
+    pd[i] = fma(li, li, cp * cp);
+    if (i < n - 1) pe[i] = c[i] * li;
+  }
+}
+
 __global__ void tridiag_matvec_kernel(const double* pd, const double* pe, omc_vec_t v, int n_chains, long long n,
                                       double* out) {
   const long long total = (long long)n_chains * n;
@@ -1139,6 +1150,14 @@ int omc_tridiag_quadforms(const omc_tridiag_nn_t* a, void* stream) {
   OMC_LAUNCH_CHECK();
   tg_partials_kernel<<<a->n_chains, 32, 0, (cudaStream_t)stream>>>(ws, L, L.n_tiles, a->n_chains, a->ss_prior, a->ss_lik,
                                                                     nullptr);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_bidiag_gram(const double* l, const double* c, long long n, double* pd, double* pe, void* stream) {
+  OMC_REQUIRE(l && pd && n >= 1 && (n == 1 || (c && pe)), "omc_bidiag_gram: bad argument");
+  const unsigned int blocks = (unsigned int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  bidiag_gram_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(l, c, n, pd, pe);
   OMC_LAUNCH_CHECK();
   return 0;
 }

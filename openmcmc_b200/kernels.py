@@ -219,7 +219,7 @@ def dense_factor(Q, n, b=None, z=None, L=None, logdet=None, mean=None, x=None, s
     for name, t in (("b", b), ("z", z), ("L", L), ("logdet", logdet), ("mean", mean), ("x", x), ("status", status),
                     ("workspace", workspace)):
         setattr(a, name, t.data_ptr() if t is not None else None)
-    a.factored, a.backward_only = int(bool(factored)), int(bool(backward_only))
+    a.factored, a.backward_only = int(bool(factored)), int(backward_only)
     check(lib().omc_dense_factor(C.byref(a), stream_ptr()), "omc_dense_factor")
 
 
@@ -488,6 +488,12 @@ def tridiag_nn_draw(args):
 
 def tridiag_quadforms(args):
     check(lib().omc_tridiag_quadforms(C.byref(args), stream_ptr()), "omc_tridiag_quadforms")
+
+
+def bidiag_gram(l, c, n, pd, pe):
+    """pd, pe <- diagonals of L L' for a lower bidiagonal L (diagonal l, sub-diagonal c)."""
+    check(lib().omc_bidiag_gram(_ptr(l), _ptr(c) if c is not None and c.numel() else None, int(n), _ptr(pd),
+                                _ptr(pe) if pe is not None and pe.numel() else None, stream_ptr()), "omc_bidiag_gram")
 
 
 def tridiag_matvec(pd, pe, v, n_chains, n, out):

@@ -149,3 +149,96 @@ def test_distribution_rvs_and_missing_initial_values():
     assert M.state["beta"].shape == (p, 1) and M.state["tau"].shape == (1, 1) and M.state["tau"][0, 0] > 0
     M.run_mcmc()
     assert np.all(np.abs(M.store["beta"].mean(axis=1) - [1.0, -1.0, 0.5]) < 0.1)
+
+
+@pytest.mark.parametrize("n", [3, 64, 130, 300])
+def test_cholesky_cho_solve_solve_dense(n):
+    """ref tests/test_grmf.py:312-375 of the reference: cholesky == np.linalg.cholesky, lower-triangular, L L' = P;
+    solve / cho_solve == np.linalg.solve -- here through omc_dense_factor (blocked Cholesky, DMMA trailing update)."""
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    Q = A @ A.T / n + np.eye(n)
+    L = gmrf.cholesky(Q)
+    Lr = np.linalg.cholesky(Q)
+    np.testing.assert_allclose(L, Lr, rtol=1e-10, atol=1e-13)
+    assert not np.any(np.triu(L, 1))
+    np.testing.assert_allclose(gmrf.cholesky(Q, lower=False), Lr.T, rtol=1e-10, atol=1e-13)
+    b = rng.standard_normal((n, 2))
+    ref = np.linalg.solve(Q, b)
+    np.testing.assert_allclose(gmrf.cho_solve((L, True), b), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    np.testing.assert_allclose(gmrf.cho_solve((L.T, False), b), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    np.testing.assert_allclose(gmrf.solve(Q, b), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    z = rng.standard_normal((n, 1))
+    for a in (L.T, L):                                     # the triangular solves of gmrf.py:61
+        r = np.linalg.solve(a, z)
+        np.testing.assert_allclose(gmrf.solve(a, z), r, rtol=1e-9, atol=1e-9 * np.abs(r).max())
+    with pytest.raises(np.linalg.LinAlgError):
+        gmrf.cholesky(Q - 3.0 * np.eye(n))
+    # draws from a precomputed factor: mu + L^-T z without re-factorising
+    mu = rng.standard_normal((n, 1))
+    x = gmrf.sample_normal(mu, L=L, z=z)
+    np.testing.assert_allclose(x, mu + np.linalg.solve(Lr.T, z), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [2, 50, 4000])
+def test_sparse_cholesky_and_solves_tridiagonal(n):
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(n + 1)
+    Q = (2.0 * gmrf.precision_irregular(np.cumsum(rng.exponential(size=n) + 0.2)) + 0.5 * sparse.identity(n)).tocsc()
+    L = gmrf.sparse_cholesky(Q)
+    assert sparse.issparse(L)
+    Lr = np.linalg.cholesky(Q.toarray())
+    np.testing.assert_allclose(L.toarray(), Lr, rtol=1e-10, atol=1e-13)
+    assert sparse.issparse(gmrf.cholesky(Q)) and sparse.triu(gmrf.cholesky(Q), 1).nnz == 0
+    b = rng.standard_normal((n, 1))
+    ref = np.linalg.solve(Q.toarray(), b)
+    np.testing.assert_allclose(gmrf.cho_solve((L, True), b), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    np.testing.assert_allclose(gmrf.solve(Q, b), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    z = rng.standard_normal((n, 1))
+    x = gmrf.sample_normal_canonical(b, L=L, z=z)
+    np.testing.assert_allclose(x, _alg25(Q, b, z), rtol=1e-9, atol=1e-9 * np.abs(x).max())
+    # a sparse matrix with a wider band goes through the dense factorisation
+    if n <= 50:
+        W = Q + sparse.diags([0.1 * np.ones(n - 1)], [1], shape=(n, n)).T @ sparse.diags([0.1 * np.ones(n - 1)], [1], shape=(n, n))
+        Wd = (W + W.T).toarray() / 2 + np.eye(n)
+        np.testing.assert_allclose(gmrf.sparse_cholesky(sparse.csc_matrix(Wd)).toarray(), np.linalg.cholesky(Wd),
+                                   rtol=1e-10, atol=1e-13)
+
+
+def test_gibbs_canonical_truncated_normal_and_truncated_sampling():
+    """ref gmrf.py:201-266: the coordinate scan with the uniforms behind truncnorm.rvs injected equals a numpy / scipy
+    restatement; ref tests/test_grmf.py:93-147: Gibbs and rejection samples stay inside the box and agree in mean."""
+    from openmcmc_b200 import gmrf
+
+    rng = np.random.default_rng(12)
+    p = 9
+    A = rng.standard_normal((p, p))
+    Q = A @ A.T + p * np.eye(p)
+    b = rng.standard_normal((p, 1))
+    lower, upper = -0.3 * np.ones((p, 1)), 0.5 * np.ones((p, 1))
+    x0 = np.zeros((p, 1))
+    u = rng.random(p)
+    x = gmrf.gibbs_canonical_truncated_normal(b, Q, x0.copy(), lower, upper, u=u)
+    ref = x0.copy()
+    for i in range(p):
+        v = 1.0 / Q[i, i]
+        m = v * (b[i, 0] - Q[i, :] @ ref[:, 0] + Q[i, i] * ref[i, 0])
+        s = np.sqrt(v)
+        ref[i, 0] = stats.truncnorm.ppf(u[i], (lower[i, 0] - m) / s, (upper[i, 0] - m) / s, loc=m, scale=s)
+    np.testing.assert_allclose(x, ref, rtol=1e-9, atol=1e-12)
+    # unbounded: a plain canonical draw
+    z = rng.standard_normal((p, 1))
+    assert gmrf.gibbs_canonical_truncated_normal(b, Q, x0.copy()).shape == (p, 1)
+    mu = np.linalg.solve(Q, b)
+    G = gmrf.sample_truncated_normal(mu, Q=Q, lower=lower, upper=upper, n=40, method="Gibbs", seed=3)
+    R = gmrf.sample_truncated_normal(mu, Q=Q, lower=lower, upper=upper, n=200, method="Rejection", seed=4)
+    for S in (G, R):
+        assert np.all(S >= lower) and np.all(S <= upper)
+    assert np.all(np.abs(G.mean(axis=1) - R.mean(axis=1)) < 0.25)
+    with pytest.raises(TypeError):
+        gmrf.sample_truncated_normal(mu, Q=Q, method="other")
+    with pytest.raises(ValueError):
+        gmrf.sample_truncated_normal_rejection(mu, Q=Q, lower=upper, upper=lower)

@@ -231,3 +231,53 @@ def test_philox_normals_and_gammas_moments():
         K.ng_draw(C, K.vec(a0, 1), K.vec(one, 1), K.vec(zero, 1), K.vec(zero, 1), out, K.rng(seed=5, sweep=sweep, site=2))
         torch.cuda.synchronize()
         assert stats.kstest(out.cpu().numpy(), "gamma", args=(shape,)).pvalue > 0.01
+
+
+@pytest.mark.parametrize("prior", ["eye", "diag", "dense"])
+@pytest.mark.parametrize("C,n,p", [(5, 40, 1), (4, 300, 3), (3, 90, 8), (3, 90, 9), (4, 200, 17), (2, 150, 31),
+                                   (2, 150, 32), (3, 200, 33), (3, 300, 40), (2, 300, 45), (2, 300, 57), (2, 300, 63),
+                                   (301, 130, 64)])
+def test_nn_dense_draw_without_probes_matches_oracle(C, n, p, prior):
+    """The production path of omc_nn_dense_draw at p <= 64 (one warp per chain, Q in registers, dense_warp.cu; no
+    probe outputs): the draw itself against the oracle's mu + L^-T z, and the solve-only mode against Q^-1 b."""
+    import torch
+
+    from openmcmc_b200 import kernels as K
+    from oracle import conjugate
+
+    K.init_device(0)
+    rng = np.random.default_rng(70 + p)
+    X, y, _, _ = _make(C, n, p, 199 + p, False)
+    tau = rng.random(C) + 0.5
+    lam = rng.random(C) + 0.01
+    mu0 = rng.standard_normal((C, p))
+    z = rng.standard_normal((C, p))
+    if prior == "eye":
+        P0, kind = None, K.MAT_EYE
+    elif prior == "diag":
+        P0, kind = rng.random((C, p)) + 0.2, K.MAT_DIAG
+    else:
+        A = rng.standard_normal((C, p, p))
+        P0, kind = A @ A.transpose(0, 2, 1) + p * np.eye(p), K.MAT_DENSE
+    t = lambda v: None if v is None else torch.tensor(v, device="cuda")
+    dX, dy, dtau, dlam, dmu0, dz, dP0 = map(t, (X, y, tau, lam, mu0, z, P0))
+    rec = p * p + p + 2
+    stats = torch.empty((C, rec), dtype=torch.float64, device="cuda")
+    ns, ws = K.reg_pass_workspace(C, n, p)
+    work = torch.empty(max(ws, 1), dtype=torch.float64, device="cuda")
+    K.reg_pass(dX, dy, None, None, stats, work, C, n, p)
+    beta = torch.empty((C, p), dtype=torch.float64, device="cuda")
+    mean = torch.empty((C, p), dtype=torch.float64, device="cuda")
+    status = torch.zeros(C, dtype=torch.int32, device="cuda")
+    stride = 0 if P0 is None else int(np.prod(P0.shape[1:]))
+    args = (C, p, stats, K.vec(dtau, 1), kind, K.vec(dP0, stride), K.vec(dlam, 1), K.vec(dmu0, p))
+    K.nn_dense_draw(*args, beta, K.rng(seed=1, site=3), debug_z=dz, status=status)
+    K.nn_dense_draw(*args, mean, K.rng(seed=1, site=3), solve_only=True, ridge_rel=0.0, status=status)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    for c in range(0, C, max(1, C // 7)):
+        G, g, _, _ = conjugate.regression_suffstats(X[c], y[c])
+        ref = conjugate.normal_normal_dense(G, g, tau[c], 1.0 if P0 is None else P0[c], lam[c], mu0[c], z[c])
+        scale = np.abs(ref["x"]).max()
+        np.testing.assert_allclose(beta[c].cpu().numpy(), ref["x"].ravel(), rtol=1e-9, atol=1e-9 * scale)
+        np.testing.assert_allclose(mean[c].cpu().numpy(), ref["mu"].ravel(), rtol=1e-9, atol=1e-9 * scale)
