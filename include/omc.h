@@ -277,6 +277,44 @@ int omc_logp_const(double value, int n_chains, double* out, int accumulate, void
 int omc_logp_domain(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int lo_len, omc_vec_t upper, int hi_len,
                     double* out, void* stream);
 
+/* out[c][i] = sum_t scale_t[c] * x_t[c][i], t < n_terms <= 4, i < len (scale == NULL or scale_t.ptr == NULL => 1).
+ *   - ScaledMatrix.predictor: scalar * matrix (ref: parameter.py:319-329), one "chain", the matrix values as x_0
+ *   - NormalNormal with several likelihood terms: the records tau_l * (G_l | g_l) summed into one (ref: sampler.py:179-192,
+ *     Q += Q_dist, b += A' Q_rsp (y - d) for every distribution of the conditional model) */
+int omc_combine(int n_chains, long long len, int n_terms, const omc_vec_t* x, const omc_vec_t* scale, double* out,
+                void* stream);
+
+/* omc_fused_small: up to OMC_FUSED_MAX_OPS of the per-chain O(1) / O(p) operations above in ONE launch, executed in
+ * order by the thread that owns the chain (their dependencies are per chain: e.g. the Gamma draw of tau reads the rss
+ * of its own chain).  A Gibbs sweep of the regression model is the draw kernel + one fused launch (Gamma draws,
+ * quadratic form) + the counter; its store epilogue (sample copies, the log-density terms of mcmc.py:108, the log_post
+ * copy) is one more.  Launch-bound sweeps (C1, C4) spend most of their time between kernels otherwise.
+ *   kinds: the argument structs of omc_logp_normal_ss / omc_logp_gamma / omc_logp_poisson / omc_logp_const /
+ *          omc_ng_draw / omc_quadform (scaled-identity and diagonal P) / omc_store_copy(_ring)
+ *   store copies are spread over all threads of the grid (coalesced); a copy whose source is produced by an earlier op
+ *   of the same launch must have count == n_chains (element c is then copied by the thread of chain c). */
+#define OMC_FUSED_MAX_OPS 12
+enum { OMC_FOP_LOGP_NORMAL_SS = 1, OMC_FOP_LOGP_GAMMA = 2, OMC_FOP_LOGP_POISSON = 3, OMC_FOP_LOGP_CONST = 4,
+       OMC_FOP_NG_DRAW = 5, OMC_FOP_QUADFORM = 6, OMC_FOP_STORE_COPY = 7 };
+typedef struct {
+  int kind;
+  union {
+    omc_logp_normal_ss_t normal_ss;
+    omc_logp_gamma_t gamma;
+    omc_logp_poisson_t poisson;
+    struct { double value; double* out; int accumulate; } konst;
+    omc_ng_draw_t ng;
+    omc_quadform_t quad;
+    struct { const double* src; double* dst; long long count; const unsigned long long* iter_counter; long long max_iter;
+             int ring; } copy;
+  } u;
+} omc_fop_t;
+typedef struct {
+  int n_chains, n_ops;
+  omc_fop_t ops[OMC_FUSED_MAX_OPS];
+} omc_fused_small_t;
+int omc_fused_small(const omc_fused_small_t* args, void* stream);
+
 /* yhat[c] = sum_t X_t[c] @ theta_t[c] for up to 4 terms (ref: parameter.py:162-197 LinearCombination.predictor) */
 typedef struct {
   int n_chains, n, n_terms;

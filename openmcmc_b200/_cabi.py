@@ -200,7 +200,38 @@ class TridiagNN(C.Structure):
                 ("status", C.c_void_p), ("workspace", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"omc_tridiag_nn_t": TridiagNN, "omc_dense_factor_t": DenseFactor}
+class _FKonst(C.Structure):
+    _fields_ = [("value", C.c_double), ("out", C.c_void_p), ("accumulate", C.c_int)]
+
+
+class _FCopy(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("count", C.c_longlong), ("iter_counter", C.c_void_p),
+                ("max_iter", C.c_longlong), ("ring", C.c_int)]
+
+
+class _FUnion(C.Union):
+    _fields_ = [("normal_ss", LogpNormalSS), ("gamma", LogpGamma), ("poisson", LogpPoisson), ("konst", _FKonst),
+                ("ng", NGDraw), ("quad", Quadform), ("copy", _FCopy)]
+
+
+class FOp(C.Structure):
+    """omc_fop_t"""
+
+    _fields_ = [("kind", C.c_int), ("u", _FUnion)]
+
+
+FUSED_MAX_OPS = 12
+FOP_LOGP_NORMAL_SS, FOP_LOGP_GAMMA, FOP_LOGP_POISSON, FOP_LOGP_CONST, FOP_NG_DRAW, FOP_QUADFORM, FOP_STORE_COPY = range(1, 8)
+
+
+class FusedSmall(C.Structure):
+    """omc_fused_small_t"""
+
+    _fields_ = [("n_chains", C.c_int), ("n_ops", C.c_int), ("ops", FOp * FUSED_MAX_OPS)]
+
+
+EXTRA_STRUCTS = {"omc_tridiag_nn_t": TridiagNN, "omc_dense_factor_t": DenseFactor, "omc_fop_t": FOp,
+                 "omc_fused_small_t": FusedSmall}
 
 # name -> (restype, argtypes); every symbol include/omc.h declares must be listed here (tests check both ways)
 PROTOTYPES = {
@@ -232,6 +263,7 @@ PROTOTYPES = {
     "omc_nn_dense_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "omc_dense_factor": (C.c_int, [C.POINTER(DenseFactor), C.c_void_p]),
     "omc_quadform": (C.c_int, [C.POINTER(Quadform), C.c_void_p]),
+    "omc_fused_small": (C.c_int, [C.POINTER(FusedSmall), C.c_void_p]),
     "omc_ng_draw": (C.c_int, [C.POINTER(NGDraw), C.c_void_p]),
     "omc_logp_normal_ss": (C.c_int, [C.POINTER(LogpNormalSS), C.c_void_p]),
     "omc_logp_gamma": (C.c_int, [C.POINTER(LogpGamma), C.c_void_p]),
@@ -243,6 +275,7 @@ PROTOTYPES = {
                                        C.c_void_p]),
     "omc_logp_domain": (C.c_int, [C.c_int, C.c_int, Vec, Vec, C.c_int, Vec, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
+    "omc_combine": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.POINTER(Vec), C.POINTER(Vec), C.c_void_p, C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_tridiag_workspace": (C.c_int, [C.c_int, C.c_longlong, C.POINTER(C.c_longlong)]),

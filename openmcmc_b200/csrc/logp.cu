@@ -114,6 +114,20 @@ __global__ void __launch_bounds__(64) logdet_dense_kernel(const double* P, int n
   }
   if (tid == 0) out[blockIdx.x] = ld;
 }
+// out[c][i] = sum_t scale_t[c] * x_t[c][i]  (t < n_terms <= 4; scale NULL => 1)
+__global__ void combine_kernel(int n_chains, long long len, int n_terms, omc_vec_t x0, omc_vec_t x1, omc_vec_t x2,
+                               omc_vec_t x3, omc_vec_t s0, omc_vec_t s1, omc_vec_t s2, omc_vec_t s3, double* out) {
+  const long long total = (long long)n_chains * len;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / len);
+    const long long i = e - (long long)c * len;
+    double v = vat(s0, c, 0, 1.0) * vat(x0, c, i, 0.0);
+    if (n_terms > 1) v = fma(vat(s1, c, 0, 1.0), vat(x1, c, i, 0.0), v);
+    if (n_terms > 2) v = fma(vat(s2, c, 0, 1.0), vat(x2, c, i, 0.0), v);
+    if (n_terms > 3) v = fma(vat(s3, c, 0, 1.0), vat(x3, c, i, 0.0), v);
+    out[e] = v;
+  }
+}
 __global__ void logp_domain_kernel(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int lo_len, omc_vec_t upper,
                                    int hi_len, double* out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,6 +185,26 @@ int omc_logp_domain(int n_chains, int n_elem, omc_vec_t x, omc_vec_t lower, int 
   OMC_REQUIRE(out && x.ptr && n_chains >= 1 && n_elem >= 1, "omc_logp_domain: bad argument");
   logp_domain_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_chains, n_elem, x, lower, lo_len, upper,
                                                                               hi_len, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_combine(int n_chains, long long len, int n_terms, const omc_vec_t* x, const omc_vec_t* scale, double* out,
+                void* stream) {
+  OMC_REQUIRE(out && x && n_chains >= 1 && len >= 0 && n_terms >= 1 && n_terms <= 4, "omc_combine: bad argument");
+  if (len == 0) return 0;
+  const omc_vec_t none = {nullptr, 0};
+  omc_vec_t xs[4], ss[4];
+  for (int t = 0; t < 4; ++t) {
+    xs[t] = t < n_terms ? x[t] : none;
+    ss[t] = (t < n_terms && scale) ? scale[t] : none;
+    OMC_REQUIRE(t >= n_terms || xs[t].ptr, "omc_combine: term %d is NULL", t);
+  }
+  const long long total = (long long)n_chains * len;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)omc_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  combine_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_chains, len, n_terms, xs[0], xs[1], xs[2], xs[3], ss[0],
+                                                                     ss[1], ss[2], ss[3], out);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -31,6 +31,9 @@ CACHE_DATA_ONLY = True
 # kernel's epilogue evaluates rss(beta) = rss0 - 2 d'c0 + d'G d, d = beta - beta_hat (omc.h: omc_nn_dense_t.center).
 # False keeps the explicit residual pass (omc_reg_rss) in every sweep; tests compare the two forms.
 RECENTER = True
+# Consecutive per-chain O(1) / O(p) operations of a sweep or of the store epilogue (Gamma draws, small quadratic forms,
+# log-density terms, sample copies) are issued as ONE launch (omc_fused_small).  False keeps one kernel per operation.
+FUSE_SMALL = True
 
 
 # ============================================================================================== device state
@@ -302,8 +305,12 @@ class Plan:
         self.keep.append(t)
         return t, (C * size if a.shape[0] > 1 else 0)
 
-    def emit(self, fn, label):
+    def emit(self, fn, label, fop=None):
+        """Append a launch.  `fop` (optional): a callable returning the omc_fop_t descriptor of the same operation, which
+        makes it eligible for fusion with its neighbours (fuse_small_ops)."""
         self.ops.append((label, fn))
+        if fop is not None:
+            self.__dict__.setdefault("_fops", {})[id(fn)] = (fn, fop)
 
     def add_quantity(self, q: Quantity):
         self.quantities[q.name] = q
@@ -321,6 +328,35 @@ class Plan:
         for q in self.quantities.values():
             if param in q.deps:
                 self.valid[q.name] = False
+
+
+def fuse_small_ops(plan: Plan, ops: list) -> list:
+    """Replace every run of >= 2 consecutive fusable launches of `ops` by one omc_fused_small launch (same order)."""
+    if not FUSE_SMALL:
+        return ops
+    fops = plan.__dict__.get("_fops", {})
+    C = plan.state.n_chains
+    out, run = [], []
+
+    def flush():
+        while run:
+            chunk = run[:K._cabi.FUSED_MAX_OPS]
+            del run[:K._cabi.FUSED_MAX_OPS]
+            if len(chunk) == 1:
+                out.append(chunk[0][:2])
+            else:
+                label = "fused[" + " + ".join(lbl for lbl, _, _ in chunk) + "]"
+                out.append((label, K.fused_small(C, [mk() for _, _, mk in chunk])))
+
+    for label, fn in ops:
+        hit = fops.get(id(fn))
+        if hit is not None and hit[0] is fn:
+            run.append((label, fn, hit[1]))
+        else:
+            flush()
+            out.append((label, fn))
+    flush()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- replicated responses
@@ -684,7 +720,9 @@ def get_quadratic_form(plan: Plan, host_state, nrm):
         def launch():
             K.quadform(C, p, x.vec(), mu.vec(), _mat_kind(P), P.vec(), ss, cnt)
 
-        plan.emit(launch, f"quadform[{nrm.response}]")
+        fop = (lambda: K.fop_quadform(C, p, x.vec(), mu.vec(), _mat_kind(P), P.vec(), ss, cnt)) \
+            if P.kind in ("eye", "diag") and p <= 512 else None
+        plan.emit(launch, f"quadform[{nrm.response}]", fop=fop)
 
     plan.add_quantity(Quantity(qname, frozenset({nrm.response, nrm.mean.form, mname}), compute))
     out = (lambda: K.vec(ss, 1), lambda: K.vec(cnt, 1), qname)
@@ -765,11 +803,12 @@ def compile_log_post(plan: Plan, host_state, model, out):
             dim = st[dist.response].rows
             plan.require(qname)
 
-            def launch(dim=dim, ss_vec=ss_vec, scal=scal, logdet=logdet, acc=acc):
-                K.logp_normal_ss(C, dim, ss_vec(), scal.vec() if scal else K.vec(None),
-                                 K.vec(logdet) if logdet is not None else K.vec(None), out, acc)
+            def nargs(dim=dim, ss_vec=ss_vec, scal=scal, logdet=logdet, acc=acc):
+                return (C, dim, ss_vec(), scal.vec() if scal else K.vec(None),
+                        K.vec(logdet) if logdet is not None else K.vec(None), out, acc)
 
-            plan.emit(launch, f"logp_normal[{dist.response}]")
+            plan.emit((lambda nargs=nargs: K.logp_normal_ss(*nargs())), f"logp_normal[{dist.response}]",
+                      fop=(lambda nargs=nargs: K.fop_logp_normal_ss(*nargs())))
             if dist.domain_response_lower is not None or dist.domain_response_upper is not None:
                 # -inf outside the domain; the truncation normaliser is ignored (location_scale.py:148-151,164-165)
                 x = st[dist.response]
@@ -794,29 +833,29 @@ def compile_log_post(plan: Plan, host_state, model, out):
                 raise PlanError("log_post: Gamma with non-Identity shape/rate is not supported on the device yet")
             sh, rt = st[dist.shape.form], st[dist.rate.form]
 
-            def launch(x=x, sh=sh, rt=rt, acc=acc):
-                K.logp_gamma(C, x.size, x.vec(), sh.vec(), sh.size, rt.vec(), rt.size, out, acc)
+            def gargs(x=x, sh=sh, rt=rt, acc=acc):
+                return (C, x.size, x.vec(), sh.vec(), sh.size, rt.vec(), rt.size, out, acc)
 
-            plan.emit(launch, f"logp_gamma[{dist.response}]")
+            plan.emit((lambda gargs=gargs: K.logp_gamma(*gargs())), f"logp_gamma[{dist.response}]",
+                      fop=(lambda gargs=gargs: K.fop_logp_gamma(*gargs())) if x.size <= 256 else None)
         elif isinstance(dist, Poisson):
             k = st[dist.response]
             if not isinstance(dist.rate, Identity):
                 raise PlanError("log_post: Poisson with non-Identity rate is not supported on the device yet")
             rt = st[dist.rate.form]
 
-            def launch(k=k, rt=rt, acc=acc):
-                K.logp_poisson(C, k.size, k.vec(), rt.vec(), rt.size, out, acc)
+            def pargs(k=k, rt=rt, acc=acc):
+                return (C, k.size, k.vec(), rt.vec(), rt.size, out, acc)
 
-            plan.emit(launch, f"logp_poisson[{dist.response}]")
+            plan.emit((lambda pargs=pargs: K.logp_poisson(*pargs())), f"logp_poisson[{dist.response}]",
+                      fop=(lambda pargs=pargs: K.fop_logp_poisson(*pargs())) if k.size <= 256 else None)
         elif isinstance(dist, Uniform):
             x = st[dist.response]
             rng_ = np.broadcast_to(dist.domain_response_upper - dist.domain_response_lower, (x.rows, 1))
             value = -float(np.sum(np.log(rng_))) * x.cols
 
-            def launch(value=value, acc=acc):
-                K.logp_const(value, C, out, acc)
-
-            plan.emit(launch, f"logp_uniform[{dist.response}]")
+            plan.emit((lambda value=value, acc=acc: K.logp_const(value, C, out, acc)), f"logp_uniform[{dist.response}]",
+                      fop=(lambda value=value, acc=acc: K.fop_logp_const(value, C, out, acc)))
         else:
             raise PlanError(f"log_post: distribution {type(dist).__name__} is not supported on the device")
         first = False

@@ -94,9 +94,45 @@ def linear_predictor(state: dict, terms):
 
 
 def scaled_matrix(state: dict, matrix: str, scalar: str):
-    raise engine.PlanError(
-        "ScaledMatrix.predictor materialises scalar*matrix on the host in the reference (parameter.py:329); the device "
-        "path never forms it (kernels take the scalar and the un-scaled matrix separately)")
+    """scalar * matrix in the format of the matrix (ref: parameter.py:319-329; the scalar must hold one value, as the
+    reference's `.item()` demands).  The values are scaled on the device (omc_combine)."""
+    from scipy import sparse
+
+    sc = np.asarray(state[scalar], dtype=np.float64)
+    if sc.size != 1:
+        raise ValueError("can only convert an array of size 1 to a Python scalar")
+    m = state[matrix]
+    dev = torch.device("cuda", K.init_device())
+    vals = m.data if sparse.issparse(m) else np.asarray(m, dtype=np.float64)
+    if vals.size == 0:
+        return m.copy()
+    x = K.upload(np.ascontiguousarray(vals, dtype=np.float64).reshape(-1), dev)
+    s_dev = K.upload(sc.reshape(1), dev)
+    out = torch.empty_like(x)
+    K.combine(1, x.numel(), [K.vec(x)], [K.vec(s_dev)], out)
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    if sparse.issparse(m):
+        r = m.astype(np.float64).copy()
+        r.data = res
+        return r
+    return res.reshape(np.shape(m))
+
+
+def scale_columns(X, theta):
+    """X * exp(theta)' (column j scaled by exp(theta_j)), the Jacobian factor of LinearCombinationWithTransform.grad
+    (ref: parameter.py:282-297): exp and the products run in omc_linear_predictor, one column at a time."""
+    from scipy import sparse
+
+    Xd = X.toarray() if sparse.issparse(X) else np.asarray(X, dtype=np.float64)
+    n, p = Xd.shape
+    dev = torch.device("cuda", K.init_device())
+    th = K.upload(np.asarray(theta, dtype=np.float64).reshape(-1), dev)
+    out = torch.empty(p, n, dtype=torch.float64, device=dev)
+    cols = K.upload(np.ascontiguousarray(Xd.T), dev)              # [p, n]: "chain" j = column j, a 1-term predictor each
+    K.linear_predictor(p, n, [(K.vec(cols, n), K.vec(th, 1), 1, True)], out)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().T
 
 
 def log_p(dist, state: dict, by_observation: bool = False):

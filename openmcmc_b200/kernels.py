@@ -223,15 +223,20 @@ def dense_factor(Q, n, b=None, z=None, L=None, logdet=None, mean=None, x=None, s
     check(lib().omc_dense_factor(C.byref(a), stream_ptr()), "omc_dense_factor")
 
 
-def quadform(n_chains, p, x, mu, kind, P, ss, cnt):
+def _quadform_args(n_chains, p, x, mu, kind, P, ss, cnt):
     a = _cabi.Quadform()
     a.n_chains, a.p, a.x, a.mu, a.kind, a.P = n_chains, p, x, mu, kind, P
     a.ss, a.cnt = ss.data_ptr(), cnt.data_ptr()
+    return a
+
+
+def quadform(n_chains, p, x, mu, kind, P, ss, cnt):
+    a = _quadform_args(n_chains, p, x, mu, kind, P, ss, cnt)
     check(lib().omc_quadform(C.byref(a), stream_ptr()), "omc_quadform")
 
 
-def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None, debug_sweep_stride=0,
-            n_elem=0, a0_len=1, b0_len=1, ss_stride=0, cnt_stride=0):
+def _ng_draw_args(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, probe_b=None, debug_sweep_stride=0,
+                  n_elem=0, a0_len=1, b0_len=1, ss_stride=0, cnt_stride=0):
     """n_elem > 0: vector-valued update, element k reads ss[k*ss_stride], cnt[k*cnt_stride] (omc.h)."""
     a = _cabi.NGDraw()
     a.n_elem, a.a0_len, a.b0_len, a.ss_stride, a.cnt_stride = int(n_elem), int(a0_len), int(b0_len), int(ss_stride), int(cnt_stride)
@@ -242,6 +247,12 @@ def ng_draw(n_chains, a0, b0, ss, cnt, out, rng_, debug_g=None, probe_a=None, pr
     a.debug_sweep_stride = int(debug_sweep_stride)
     a.probe_a = probe_a.data_ptr() if probe_a is not None else None
     a.probe_b = probe_b.data_ptr() if probe_b is not None else None
+    return a
+
+
+def ng_draw(*args, **kw):
+    """Gamma(a0 + cnt / 2, b0 + ss / 2) draws (omc.h); n_elem > 0: vector-valued update."""
+    a = _ng_draw_args(*args, **kw)
     check(lib().omc_ng_draw(C.byref(a), stream_ptr()), "omc_ng_draw")
 
 
@@ -311,6 +322,14 @@ def linear_predictor(n_chains, n, terms, out, residual_of=None):
     check(lib().omc_linear_predictor(C.byref(a), stream_ptr()), "omc_linear_predictor")
 
 
+def combine(n_chains, length, xs, scales, out):
+    """out[c][i] = sum_t scales[t][c] * xs[t][c][i]; xs / scales: lists of omc_vec_t (scale None => 1)."""
+    n = len(xs)
+    X = (Vec * n)(*xs)
+    S = (Vec * n)(*[s if s is not None else Vec(None, 0) for s in scales])
+    check(lib().omc_combine(int(n_chains), int(length), n, X, S, _ptr(out), stream_ptr()), "omc_combine")
+
+
 def sum_log(x, n, out):
     check(lib().omc_sum_log(_ptr(x), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_sum_log")
 
@@ -324,6 +343,62 @@ def logdet_dense(P, n, out):
     ws = nn_dense_workspace(m, n)
     work = torch.empty(ws, dtype=torch.float64, device=P.device) if ws else None
     dense_factor(P.reshape(m, n, n), n, logdet=out, workspace=work, n_mats=m)
+
+
+# ----------------------------------------------------------------------------- fused per-chain small ops
+FUSED_COPY_MAX = 4 << 20     # store copies above this many doubles keep their own (wider) kernel
+
+
+def _fop(kind, field, value):
+    f = _cabi.FOp()
+    f.kind = kind
+    setattr(f.u, field, value)
+    return f
+
+
+def fop_logp_normal_ss(n_chains, dim, ss, scalar, logdet, out, accumulate):
+    return _fop(_cabi.FOP_LOGP_NORMAL_SS, "normal_ss",
+                _cabi.LogpNormalSS(n_chains, float(dim), ss, scalar, logdet, out.data_ptr(), int(accumulate)))
+
+
+def fop_logp_gamma(n_chains, n_elem, x, shape, shape_len, rate, rate_len, out, accumulate):
+    return _fop(_cabi.FOP_LOGP_GAMMA, "gamma",
+                _cabi.LogpGamma(n_chains, n_elem, shape_len, rate_len, x, shape, rate, out.data_ptr(), int(accumulate)))
+
+
+def fop_logp_poisson(n_chains, n_elem, k, rate, rate_len, out, accumulate):
+    return _fop(_cabi.FOP_LOGP_POISSON, "poisson",
+                _cabi.LogpPoisson(n_chains, n_elem, rate_len, k, rate, out.data_ptr(), int(accumulate)))
+
+
+def fop_logp_const(value, n_chains, out, accumulate):
+    return _fop(_cabi.FOP_LOGP_CONST, "konst", _cabi._FKonst(float(value), out.data_ptr(), int(accumulate)))
+
+
+def fop_ng_draw(*args, **kw):
+    return _fop(_cabi.FOP_NG_DRAW, "ng", _ng_draw_args(*args, **kw))
+
+
+def fop_quadform(n_chains, p, x, mu, kind, P, ss, cnt):
+    return _fop(_cabi.FOP_QUADFORM, "quad", _quadform_args(n_chains, p, x, mu, kind, P, ss, cnt))
+
+
+def fop_store_copy(src, dst, count, iter_counter, max_iter, ring=False):
+    return _fop(_cabi.FOP_STORE_COPY, "copy", _cabi._FCopy(src.data_ptr(), dst.data_ptr(), int(count), iter_counter.data_ptr(),
+                                                          int(max_iter), int(bool(ring))))
+
+
+def fused_small(n_chains, fops):
+    """One launch running `fops` (omc_fop_t descriptors) in order; returns the launch closure (owns the argument block)."""
+    a = _cabi.FusedSmall()
+    a.n_chains, a.n_ops = int(n_chains), len(fops)
+    for i, f in enumerate(fops):
+        a.ops[i] = f
+
+    def launch():
+        check(lib().omc_fused_small(C.byref(a), stream_ptr()), "omc_fused_small")
+
+    return launch
 
 
 # ----------------------------------------------------------------------------- graphs / schedule

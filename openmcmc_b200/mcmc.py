@@ -204,8 +204,10 @@ class MCMC:
                 buf = plan.new(rows, C, arr.size, fill=float("nan"))
                 self._dev_store[name] = buf
                 self._store_names.append(name)
-                store_ops.append((f"store[{name}]", (lambda arr=arr, buf=buf: K.store_copy(
-                    arr.data, buf, C * arr.size, plan.iter_counter, rows, ring=ring))))
+                plan.emit((lambda arr=arr, buf=buf: K.store_copy(arr.data, buf, C * arr.size, plan.iter_counter, rows, ring=ring)),
+                          f"store[{name}]",
+                          fop=(lambda arr=arr, buf=buf: K.fop_store_copy(arr.data, buf, C * arr.size, plan.iter_counter, rows,
+                                                                         ring=ring)) if C * arr.size <= K.FUSED_COPY_MAX else None)
             self._dev_logpost = plan.new(rows, C, fill=float("nan"))
             self._logpost_now = plan.new(C)
             saved_valid = dict(plan.valid)
@@ -214,8 +216,9 @@ class MCMC:
                 rj.compile_log_post(plan, self._logpost_now)
             else:
                 engine.compile_log_post(plan, self.state, self.model, self._logpost_now)
-            store_ops.append(("store[log_post]", lambda: K.store_copy(self._logpost_now, self._dev_logpost, C,
-                                                                        plan.iter_counter, rows, ring=ring)))
+            plan.emit((lambda: K.store_copy(self._logpost_now, self._dev_logpost, C, plan.iter_counter, rows, ring=ring)),
+                      "store[log_post]",
+                      fop=(lambda: K.fop_store_copy(self._logpost_now, self._dev_logpost, C, plan.iter_counter, rows, ring=ring)))
             self._dev_fitted = {}
             if self.model.response is not None:
                 for response, predictor in self.model.response.items():
@@ -231,6 +234,10 @@ class MCMC:
                     plan.require(qname)                    # (a compute() may require other quantities first)
             plan.valid = saved_valid
             self.plan = plan
+            counter = sweep_ops.pop()                           # the sweep counter stays a launch of its own, last
+            sweep_ops = engine.fuse_small_ops(plan, sweep_ops) + [counter]
+            counter = store_ops.pop()
+            store_ops = engine.fuse_small_ops(plan, store_ops) + [counter]
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
             if warm_up:
                 self._warm_up(plan, st, sampled)

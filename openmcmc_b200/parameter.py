@@ -26,6 +26,11 @@ class Parameter(ABC):
     def get_grad_param_list(self) -> list:
         """State entries the gradient is defined for."""
 
+    def grad(self, state: dict, param: str):
+        """[n_param x n_data] Jacobian of the predictor with respect to `param`.  ref: parameter.py:61-71.  These are
+        structural: a prefactor matrix, an identity, a one-hot allocation pattern -- read off the state, not computed."""
+        raise NotImplementedError(f"{type(self).__name__}.grad")
+
 
 @dataclass
 class Identity(Parameter):
@@ -41,6 +46,16 @@ class Identity(Parameter):
 
     def get_grad_param_list(self) -> list:
         return [self.form]
+
+    def grad(self, state: dict, param: str):
+        """ref: parameter.py:125-141: the identity for the parameter itself, zeros otherwise."""
+        import numpy as np
+
+        value = np.asarray(state[self.form])
+        if value.ndim > 1 and value.shape[1] > 1:
+            raise ValueError("Gradient in Identity should not be used for variables 2D and above.")
+        p = value.size
+        return np.eye(p) if param == self.form else np.zeros(shape=(p, p))
 
 
 @dataclass
@@ -69,6 +84,10 @@ class LinearCombination(Parameter):
     def get_grad_param_list(self) -> list:
         return list(self.form.keys())
 
+    def grad(self, state: dict, param: str):
+        """ref: parameter.py:218-228: the transposed prefactor of `param`."""
+        return state[self.form[param]].T
+
 
 @dataclass
 class LinearCombinationWithTransform(LinearCombination):
@@ -87,6 +106,15 @@ class LinearCombinationWithTransform(LinearCombination):
         terms = [(prefactor, prm, bool(self.transform[prm])) for prm, prefactor in self.form.items()
                  if prm not in term_to_exclude]
         return hostcalls.linear_predictor(state, terms)
+
+    def grad(self, state: dict, param: str):
+        """ref: parameter.py:282-297: exp(theta) * X' for a transformed term (the scaling runs on the device)."""
+        X = state[self.form[param]]
+        if not self.transform[param]:
+            return X.T
+        from openmcmc_b200 import hostcalls
+
+        return hostcalls.scale_columns(X, state[param]).T
 
 
 @dataclass
@@ -107,6 +135,10 @@ class ScaledMatrix(Parameter):
     def get_grad_param_list(self) -> list:
         return [self.scalar]
 
+    def grad(self, state: dict, param: str):
+        """ref: parameter.py:349-360: the un-scaled matrix."""
+        return state[self.matrix]
+
     def precision_unscaled(self, state: dict, _):
         """ref: parameter.py:362-373"""
         return state[self.matrix]
@@ -114,8 +146,8 @@ class ScaledMatrix(Parameter):
 
 @dataclass
 class MixtureParameter(Parameter, ABC):
-    """ref: parameter.py:376-417.  Mixture parameters are SURVEY §8 f2 ("next"); declared so models that use them fail
-    at plan-compile time with a clear message rather than at import."""
+    """ref: parameter.py:376-417.  Mean / precision of a mixture Normal, indexed by an allocation vector (SURVEY §8 f2;
+    the device path: csrc/mixture.cu, engine.MixtureNormal)."""
 
     param: str
     allocation: str
@@ -137,6 +169,13 @@ class MixtureParameterVector(MixtureParameter):
 
     def get_grad_param_list(self) -> list:
         return [self.param]
+
+    def grad(self, state: dict, param: str):
+        """ref: parameter.py:448-463: the one-hot pattern [n_param x n_data] of the allocations."""
+        import numpy as np
+
+        alloc = np.asarray(state[self.allocation]).astype(int).reshape(-1)
+        return (np.arange(np.asarray(state[param]).size).reshape(-1, 1) == alloc.reshape(1, -1)).astype(np.float64)
 
 
 @dataclass

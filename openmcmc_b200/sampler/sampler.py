@@ -99,22 +99,63 @@ class NormalNormal(MCMCSampler):
         if not isinstance(prior, Normal):
             raise engine.PlanError("NormalNormal needs a Normal prior on the sampled parameter")
         liks = [d for k, d in self.model.items() if not self._is_response[k]]
-        if len(liks) != 1 or not isinstance(liks[0], Normal):
-            raise engine.PlanError("the device NormalNormal supports exactly one Normal likelihood term")
-        lik = liks[0]
+        if not liks or not all(isinstance(d, Normal) for d in liks):
+            raise engine.PlanError("the device NormalNormal needs Normal likelihood terms (and at least one)")
         from openmcmc_b200 import gmrf_plan
 
-        if (not isinstance(prior.precision, MixtureParameterMatrix)
-                and gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, lik)):
+        if (len(liks) == 1 and not isinstance(prior.precision, MixtureParameterMatrix)
+                and gmrf_plan.is_gmrf_update(plan, host_state, self.param, prior, liks[0])):
             if prior.domain_response_lower is not None or prior.domain_response_upper is not None:
                 raise engine.PlanError("a truncated prior on the tridiagonal (GMRF) path is not supported: the "
                                        "coordinate-wise scan of gmrf.py:201-266 is sequential over 1e6 elements")
-            return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, lik, debug_draws)
+            return gmrf_plan.compile_normal_normal_identity(self, plan, host_state, prior, liks[0], debug_draws)
+        # dense path: every likelihood term contributes a regression record (sampler.py:179-192).  A term whose mean is
+        # the parameter itself (Identity) is the regression on the p x p identity.
+        liks = [self._as_regression(plan, host_state, d) for d in liks]
+        if len(liks) == 1:
+            return self._compile_dense(plan, host_state, prior, liks[0], debug_draws)
+        return self._compile_dense(plan, host_state, prior, liks[0], debug_draws,
+                                   source=self._combined_source(plan, host_state, liks))
+
+    def _as_regression(self, plan, host_state, lik):
+        """The likelihood as Normal(y | X param + ..., .): LinearCombination means pass through, an Identity mean on the
+        sampled parameter becomes the regression on the identity matrix (b += Q_rsp y of sampler.py:187-188)."""
         if isinstance(lik.mean, LinearCombination):
-            return self._compile_dense(plan, host_state, prior, lik, debug_draws)
+            if self.param not in lik.mean.form:
+                raise engine.PlanError(f"'{self.param}' is not a term of the mean of '{lik.response}'")
+            return lik
+        if isinstance(lik.mean, Identity) and lik.mean.form == self.param:
+            p = plan.state[self.param].rows
+            if p > 512:
+                raise engine.PlanError(f"NormalNormal with an Identity-mean likelihood of dimension {p} and a dense "
+                                       "posterior precision: only the tridiagonal (GMRF) form scales beyond 512")
+            name = f"__eye{p}__"
+            if name not in host_state:
+                host_state[name] = np.eye(p)
+            return Normal(lik.response, mean=LinearCombination(form={self.param: name}), precision=lik.precision)
         raise engine.PlanError(
-            f"NormalNormal: a likelihood mean of type {type(lik.mean).__name__} with a small dense prior is not "
-            "supported by the device path (write it as LinearCombination({param: X}))")
+            f"NormalNormal: a likelihood mean of type {type(lik.mean).__name__} is not supported by the device path")
+
+    def _combined_source(self, plan, host_state, liks):
+        """Several likelihood terms: Q and b are sums over the terms (sampler.py:179-192), so their records
+        tau_l * (G_l | g_l) are added into one record per sweep (omc_combine) and the draw runs on that with tau = 1.
+        The residual sums of squares stay with their own records (explicit passes: no common centre)."""
+        st = plan.state
+        C = st.n_chains
+        rls = [engine.get_regression(plan, host_state, lik, self.param) for lik in liks]
+        p = rls[0].p
+        if any(r.p != p for r in rls):
+            raise engine.PlanError("NormalNormal: likelihood terms with different coefficient dimensions")
+        if len(rls) > 4:
+            raise engine.PlanError("NormalNormal with more than 4 likelihood terms is not supported by the device path")
+        rec = rls[0].rec
+        comb = plan.new(C, rec, fill=0.0)
+        taus = [st[r.scalar] if r.scalar else None for r in rls]
+
+        def launch():
+            K.combine(C, rec, [K.vec(r.stats, rec) for r in rls], [t.vec() if t else None for t in taus], comb)
+
+        return dict(stats=comb, rec=rec, p=p, tau=None, require=[r.q_gg for r in rls], pre=(launch, "combine_records"))
 
     def _compile_dense(self, plan, host_state, prior, lik, debug_draws, source=None):
         """source (mixture-mean update): the likelihood record comes from engine.MixtureNormal instead of the regression
@@ -128,7 +169,7 @@ class NormalNormal(MCMCSampler):
                           regression=rl)
         p = source["p"]
         tau = source["tau"]
-        requires = [source["require"]]
+        requires = list(source["require"]) if isinstance(source["require"], (list, tuple)) else [source["require"]]
         if isinstance(prior.mean, MixtureParameterVector) and isinstance(prior.precision, MixtureParameterMatrix):
             mix = engine.get_mixture(plan, host_state, prior)
             requires.append(mix.qname)
@@ -141,7 +182,17 @@ class NormalNormal(MCMCSampler):
             pm_name, lam_name = engine._scalar_and_matrix(prior.precision)
             P0 = engine.ensure_matrix(st, host_state, pm_name)
             if P0.kind == "tridiag":
-                raise engine.PlanError("tridiagonal prior with a regression likelihood is not supported")
+                # a GMRF prior on regression coefficients (example 4 with A != I): the posterior precision
+                # lambda P + tau X'X is dense, so the prior enters the dense draw as a dense p x p matrix
+                # (the tridiagonal form stays registered under its own name for the quadratic form / log-determinant)
+                Pm = host_state[pm_name]
+                dname = pm_name + "::dense"
+                if dname not in st.arrays:
+                    if Pm.shape[0] > 512:
+                        raise engine.PlanError("a tridiagonal prior with a regression likelihood gives a dense posterior "
+                                               f"precision: {Pm.shape[0]} > 512 coefficients are not supported")
+                    st.put(dname, Pm.toarray() if engine.sparse.issparse(Pm) else np.asarray(Pm, dtype=np.float64))
+                P0 = st.arrays[dname]
             lam = st[lam_name] if lam_name else None
             mu0_vec, P0_kind, P0_vec = mu0.vec, engine._mat_kind(P0), P0.vec
         beta = st[self.param]
@@ -187,6 +238,9 @@ class NormalNormal(MCMCSampler):
         else:
             ws = K.nn_dense_workspace(C, p)
             workspace = ctx.setdefault("workspace", plan.new(ws) if ws else None)
+
+        if source.get("pre"):
+            plan.emit(*source["pre"])
 
         def launch():
             K.nn_dense_draw(
@@ -251,12 +305,20 @@ class NormalGamma(MCMCSampler):
         rng, dg, dg_stride, probes = ctx["rng"], ctx["dg"], ctx["dg_stride"], ctx["probes"]
         plan.require(qname)
 
-        def launch():
-            K.ng_draw(C, a0.vec(), b0.vec(), ss_vec(), cnt_vec(), out.data, rng, debug_g=dg,
-                      probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
-                      debug_sweep_stride=dg_stride)
+        def ngargs():
+            return (C, a0.vec(), b0.vec(), ss_vec(), cnt_vec(), out.data, rng), dict(
+                debug_g=dg, probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
+                debug_sweep_stride=dg_stride)
 
-        plan.emit(launch, f"ng_draw[{self.param}]")
+        def launch():
+            a, kw = ngargs()
+            K.ng_draw(*a, **kw)
+
+        def fop():
+            a, kw = ngargs()
+            return K.fop_ng_draw(*a, **kw)
+
+        plan.emit(launch, f"ng_draw[{self.param}]", fop=fop)
         plan.wrote(self.param)
 
     def _compile_mixture(self, plan, host_state, gam, nrm, debug_draws):
@@ -284,13 +346,21 @@ class NormalGamma(MCMCSampler):
         plan.require(mix.qname)
         stride = mix.K * 4
 
-        def launch():
-            K.ng_draw(C, a0.vec(), b0.vec(), K.vec((mix.stats[:, 0, 2:], stride)), K.vec((mix.stats, stride)), out.data,
-                      rng, debug_g=dg, probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
-                      debug_sweep_stride=dg_stride, n_elem=mix.K, a0_len=a0.size, b0_len=b0.size, ss_stride=4,
-                      cnt_stride=4)
+        def ngargs():
+            return (C, a0.vec(), b0.vec(), K.vec((mix.stats[:, 0, 2:], stride)), K.vec((mix.stats, stride)), out.data,
+                    rng), dict(debug_g=dg, probe_a=probes["a"] if probes else None, probe_b=probes["b"] if probes else None,
+                               debug_sweep_stride=dg_stride, n_elem=mix.K, a0_len=a0.size, b0_len=b0.size, ss_stride=4,
+                               cnt_stride=4)
 
-        plan.emit(launch, f"ng_draw[{self.param}]")
+        def launch():
+            a, kw = ngargs()
+            K.ng_draw(*a, **kw)
+
+        def fop():
+            a, kw = ngargs()
+            return K.fop_ng_draw(*a, **kw)
+
+        plan.emit(launch, f"ng_draw[{self.param}]", fop=fop)
         plan.wrote(self.param)
 
 

@@ -231,3 +231,27 @@ def gibbs_mixture_sweep(X, y, w, state, prob, a_tau, b_tau, z_beta, g, u):
     s["z"] = mixture_allocation(s["beta"], s["mu"], s["tau"], prob, u)
     return s
 
+
+
+def multi_likelihood_sweep(terms, state, P0, mu0, z, g, a0=1e-3, b0=1e-3):
+    """One Gibbs sweep of a NormalNormal update with SEVERAL likelihood terms followed by the NormalGamma updates of
+    every precision scalar (the samplers in the order beta, tau_1 .. tau_L, lambda).
+
+    ref: sampler.py:179-192 -- Q = Q_prior + sum_l tau_l X_l' W_l X_l, b = Q_prior mu0 + sum_l tau_l X_l' W_l y_l (an
+    Identity-mean term is X_l = I, sampler.py:187-188); sampler.py:252-288 for the Gamma updates.
+    terms: list of (X, y, w or None); state: dict(beta, taus [L], lam); g: the L + 1 injected standard-gamma variates.
+    Returns the new state."""
+    p = state["beta"].size
+    G, gv = np.zeros((p, p)), np.zeros((p, 1))
+    for (X, y, w), tau in zip(terms, state["taus"]):
+        Gl, gl, _, _ = regression_suffstats(X, y, w)
+        G += float(tau) * Gl
+        gv += float(tau) * gl
+    beta = normal_normal_dense(G, gv, 1.0, P0, state["lam"], mu0, z)["x"]
+    taus = []
+    for (X, y, w), gk in zip(terms, g[:-1]):
+        _, _, rss, cnt = regression_suffstats(X, y, w, beta)
+        taus.append(normal_gamma(a0, b0, rss, cnt, gk)[0])
+    ss, cnt = quadform(P0, beta, mu0)
+    lam = normal_gamma(a0, b0, ss, cnt, g[-1])[0]
+    return {"beta": beta, "taus": taus, "lam": lam}

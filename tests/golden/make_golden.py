@@ -176,6 +176,50 @@ def regression_two_term_case(n, p, q, seed, n_iter):
 
 
 # ----------------------------------------------------------------------------------------------- Metropolis-Hastings (C4 shape)
+def multilik_case(n1, n2, p, seed, n_iter, identity_term=True, gmrf_prior=False):
+    """NormalNormal with SEVERAL likelihood terms (sampler.py:179-192): two regressions on the same coefficients, and
+    optionally a direct noisy observation of the coefficients (Identity mean, sampler.py:187-188); with gmrf_prior the
+    prior precision is the tridiagonal RW1 matrix (example 4's prior on regression coefficients)."""
+    rng = np.random.default_rng(seed)
+    X1, X2 = rng.standard_normal((n1, p)), rng.standard_normal((n2, p))
+    beta_true = np.cumsum(rng.standard_normal((p, 1)) * 0.3, axis=0) if gmrf_prior else rng.standard_normal((p, 1))
+    y1 = X1 @ beta_true + 0.1 * rng.standard_normal((n1, 1))
+    y2 = X2 @ beta_true + 0.3 * rng.standard_normal((n2, 1))
+    y3 = beta_true + 0.5 * rng.standard_normal((p, 1))
+    w2 = rng.random(n2) + 0.3
+    if gmrf_prior:
+        P_lambda = gmrf.precision_irregular(np.cumsum(rng.exponential(size=p) + 0.5)).tolil()
+        P_lambda[0, 0] += 0.1
+        P_lambda = P_lambda.tocsc()
+    else:
+        P_lambda = sparse.csc_matrix(np.eye(p))
+    dists = [Normal("y1", mean=LinearCombination(form={"beta": "X1"}), precision=ScaledMatrix(matrix="P1", scalar="tau1")),
+             Normal("y2", mean=LinearCombination(form={"beta": "X2"}), precision=ScaledMatrix(matrix="P2", scalar="tau2")),
+             Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+             Gamma("tau1", shape="a", rate="b"), Gamma("tau2", shape="a", rate="b"), Gamma("lambda", shape="a", rate="b")]
+    state = {"y1": y1, "y2": y2, "X1": X1, "X2": X2, "beta": np.zeros((p, 1)), "P1": sparse.identity(n1, format="csc"),
+             "P2": sparse.diags(w2, format="csc"), "tau1": 1.0, "tau2": 1.0, "P_lambda": P_lambda, "mu": np.zeros((p, 1)),
+             "lambda": 0.1, "a": 1e-3, "b": 1e-3}
+    names = ["beta", "tau1", "tau2", "lambda"]
+    if identity_term:
+        dists.insert(2, Normal("y3", mean="beta", precision=ScaledMatrix(matrix="P3", scalar="tau3")))
+        dists.append(Gamma("tau3", shape="a", rate="b"))
+        state.update({"y3": y3, "P3": sparse.identity(p, format="csc"), "tau3": 1.0})
+        names.insert(3, "tau3")
+    mdl = Model(dists)
+    samplers = [NormalNormal("beta", mdl)] + [NormalGamma(k, mdl) for k in names[1:]]
+    with Streams(seed + 1) as s:
+        M = _run_ref(state, samplers, mdl, n_iter)
+    g = s.stack("g")[:, 0].reshape(n_iter, len(names) - 1)
+    out = {"X1": X1, "X2": X2, "y1": y1, "y2": y2, "y3": y3, "w2": w2, "P_lambda": P_lambda.toarray(), "z": s.stack("z"),
+           "identity_term": identity_term, "gmrf_prior": gmrf_prior, "names": np.array(names),
+           "store_beta": M.store["beta"], "store_log_post": M.store["log_post"]}
+    for j, k in enumerate(names[1:]):
+        out["g_" + k] = g[:, j]
+        out["store_" + k] = M.store[k]
+    return out
+
+
 def _run_ref(state, samplers, mdl, n_iter):
     import openmcmc.mcmc as m
 
@@ -755,7 +799,7 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2", "round2b"]
     if "regression" not in which:
         cases = {}
     if "round2" in which:
@@ -766,6 +810,14 @@ def main():
             "regression_n600_p128": regression_case(600, 128, 22, 3),
             "regression_n700_p200_dense_weighted": regression_case(700, 200, 23, 2, weighted=True, prior="dense"),
             "rwl_poisson_gamma_1x32": rwl_case(32, 24, 6, 0.5),
+        })
+    if "round2b" in which:
+        # round 2: NormalNormal with several likelihood terms / an Identity-mean term / a tridiagonal prior on regression
+        # coefficients (sampler.py:179-192)
+        cases.update({
+            "multilik_n90_n60_p7_identity": multilik_case(90, 60, 7, 31, 5),
+            "multilik_n200_n150_p40": multilik_case(200, 150, 40, 32, 3, identity_term=False),
+            "multilik_gmrfprior_n120_n80_p24": multilik_case(120, 80, 24, 33, 4, identity_term=True, gmrf_prior=True),
         })
     if "mh" in which:
         cases.update(mh_cases())

@@ -405,3 +405,68 @@ def test_full_size_c2_properties():
     # the posterior mean of beta after 3 sweeps is already at the least-squares solution of its chain (noise sd 0.1)
     err = np.abs(full.store["beta"][:, :, -1] - bt[:, :, 0].cpu().numpy()).max()
     assert err < 0.05, err
+
+
+MULTILIK = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "multilik_*.npz")))
+
+
+@pytest.mark.parametrize("name", MULTILIK)
+def test_mcmc_replays_multi_likelihood_chain(name):
+    """NormalNormal with several likelihood terms (sampler.py:179-192): two regressions on the same coefficients,
+    optionally a direct observation (Identity mean, sampler.py:187-188), optionally a tridiagonal (GMRF) prior on the
+    coefficients -- golden chains of the live reference, its variates injected."""
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.sampler import NormalGamma, NormalNormal
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    n1, p = g["X1"].shape
+    n2 = g["X2"].shape[0]
+    names = [str(k) for k in g["names"]]
+    P_lambda = sparse.csc_matrix(g["P_lambda"])
+    dists = [Normal("y1", mean=LinearCombination(form={"beta": "X1"}), precision=ScaledMatrix(matrix="P1", scalar="tau1")),
+             Normal("y2", mean=LinearCombination(form={"beta": "X2"}), precision=ScaledMatrix(matrix="P2", scalar="tau2")),
+             Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P_lambda", scalar="lambda")),
+             Gamma("tau1", shape="a", rate="b"), Gamma("tau2", shape="a", rate="b"), Gamma("lambda", shape="a", rate="b")]
+    state = {"y1": g["y1"], "y2": g["y2"], "X1": g["X1"], "X2": g["X2"], "beta": np.zeros((p, 1)),
+             "P1": sparse.identity(n1, format="csc"), "P2": sparse.diags(g["w2"], format="csc"), "tau1": 1.0, "tau2": 1.0,
+             "P_lambda": P_lambda, "mu": np.zeros((p, 1)), "lambda": 0.1, "a": 1e-3, "b": 1e-3}
+    if bool(g["identity_term"]):
+        dists.insert(2, Normal("y3", mean="beta", precision=ScaledMatrix(matrix="P3", scalar="tau3")))
+        dists.append(Gamma("tau3", shape="a", rate="b"))
+        state.update({"y3": g["y3"], "P3": sparse.identity(p, format="csc"), "tau3": 1.0})
+    mdl = Model(dists)
+    samplers = [NormalNormal("beta", mdl)] + [NormalGamma(k, mdl) for k in names[1:]]
+    n_iter = g["store_beta"].shape[1]
+    dd = {"beta": {"z": g["z"]}}
+    dd.update({k: {"g": g["g_" + k]} for k in names[1:]})
+    M = MCMC(state, samplers, model=mdl, n_burn=0, n_iter=n_iter, debug_draws=dd)
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["beta"], g["store_beta"], rtol=1e-9, atol=1e-12)
+    for k in names[1:]:
+        np.testing.assert_allclose(M.store[k], g["store_" + k], rtol=1e-9)
+    np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
+
+
+def test_scaled_matrix_predictor_and_parameter_grads():
+    """ScaledMatrix.predictor (parameter.py:319-329) and Parameter.grad (parameter.py:125-141, 218-228, 282-297, 349-360)."""
+    from openmcmc_b200.parameter import Identity, LinearCombination, LinearCombinationWithTransform, ScaledMatrix
+
+    rng = np.random.default_rng(0)
+    P = sparse.diags([rng.random(6) + 1.0, -rng.random(5)], [0, 1], format="csc")
+    state = {"P": P, "tau": np.array([[2.5]]), "D": rng.standard_normal((4, 4)), "X": rng.standard_normal((5, 3)),
+             "b": rng.standard_normal((3, 1))}
+    sm = ScaledMatrix(matrix="P", scalar="tau")
+    out = sm.predictor(state)
+    assert sparse.issparse(out) and np.allclose(out.toarray(), 2.5 * P.toarray(), rtol=1e-15)
+    np.testing.assert_allclose(ScaledMatrix(matrix="D", scalar="tau").predictor(state), 2.5 * state["D"], rtol=1e-15)
+    assert sm.grad(state, "tau") is state["P"]
+    assert np.array_equal(Identity("b").grad(state, "b"), np.eye(3)) and not Identity("b").grad(state, "x").any()
+    assert np.array_equal(LinearCombination({"b": "X"}).grad(state, "b"), state["X"].T)
+    lt = LinearCombinationWithTransform(form={"b": "X"}, transform={"b": True})
+    np.testing.assert_allclose(lt.grad(state, "b"), np.exp(state["b"]) * state["X"].T, rtol=1e-14)
+    with pytest.raises(ValueError):
+        ScaledMatrix(matrix="D", scalar="D").predictor(state)

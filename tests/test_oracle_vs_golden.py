@@ -174,3 +174,32 @@ def test_gmrf_chain_replay(name):
         np.testing.assert_allclose(s["tau"], g["store_tau"][0, it], rtol=1e-9)
         np.testing.assert_allclose(conjugate.gmrf_log_post(g["pd"], g["pe"], g["w"], g["y"], g["mu"], s),
                                    g["store_log_post"][it, 0], rtol=1e-10)
+
+
+MULTILIK = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "multilik_*.npz")))
+
+
+def multilik_terms(g):
+    p = g["X1"].shape[1]
+    terms = [(g["X1"], g["y1"], None), (g["X2"], g["y2"], g["w2"])]
+    if bool(g["identity_term"]):
+        terms.append((np.eye(p), g["y3"], None))
+    return terms
+
+
+@pytest.mark.parametrize("name", MULTILIK)
+def test_multi_likelihood_normal_normal_chain(name):
+    """sampler.py:179-192: several likelihood terms (two regressions, optionally an Identity-mean observation of the
+    coefficients, optionally a tridiagonal prior) -- the oracle sweep against the live reference's chain."""
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    terms = multilik_terms(g)
+    p = g["X1"].shape[1]
+    names = [str(k) for k in g["names"]]
+    st = {"beta": np.zeros((p, 1)), "taus": [1.0] * len(terms), "lam": 0.1}
+    for it in range(g["store_beta"].shape[1]):
+        gam = [g["g_" + k][it] for k in names[1:]]
+        st = conjugate.multi_likelihood_sweep(terms, st, g["P_lambda"], np.zeros((p, 1)), g["z"][it], gam)
+        np.testing.assert_allclose(st["beta"].ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-12)
+        for k, v in zip(names[1:-1], st["taus"]):
+            np.testing.assert_allclose(v, g["store_" + k][0, it], rtol=1e-9)
+        np.testing.assert_allclose(st["lam"], g["store_lambda"][0, it], rtol=1e-9)
