@@ -35,6 +35,7 @@
 #include "omc_common.cuh"
 #include "omc_internal.h"
 #include "omc_logtab.cuh"
+#include "omc_zigtab.cuh"
 
 #ifdef TG_EXP_TRACE
 // tuning aid (tools/tune_tridiag.sh): per-CTA phase timestamps of the solve kernel, read back with omc_debug_trace_read
@@ -81,6 +82,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 #ifndef TG_LB_WIN
 #define TG_LB_WIN 4                       // successors polled in the first look-back round
+#endif
+#ifndef TG_ZIGGURAT
+#define TG_BOX_MULLER 1                   // normals of the solve kernel: Box-Muller pairs (default) or the ziggurat below
 #endif
 #ifndef TG_SOLVE_MINB
 #define TG_SOLVE_MINB (512 / TG_SNT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
@@ -390,6 +394,56 @@ __device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 ke
   return z;
 }
 
+// ---------------------------------------------------------------------------------------------- ziggurat normals
+// Alternative generator of the solve kernel (-DTG_ZIGGURAT; the Box-Muller pair above is the default because it
+// MEASURED faster, profiles/r02_tridiag_ziggurat_variants.txt: 0.605 ms per draw against 0.69 ms (256 layers, serial
+// slow path) and 0.76 ms (1024 layers, warp-cooperative slow path) at 64 x 1e6 -- the FP64-pipe share of the solve
+// kernel falls from 46 % to 23 %, but the random 16-byte table gathers double its long-scoreboard stalls and the
+// instruction count does not fall).  Marsaglia & Tsang's
+// ziggurat with 1024 layers and 52-bit candidates (tools/gen/zig_tables.py: tables, numpy model, tail checks): 64 random
+// bits give (layer: 10 bits, sign, j: 52 bits), x = j * w_layer, accepted at once when j < k_layer -- 99.6 % of the
+// candidates, about a dozen instructions of which two are FP64, against ~35 FP64 instructions per element for the
+// Box-Muller pair (log, 1/sqrt, sine and cosine polynomials).  One Philox block still serves two elements; the rest
+// (wedge test with exp, the tail beyond R by Marsaglia's exponential rejection, restart on rejection) runs in a
+// non-inlined slow path on blocks of a derived key, so a draw stays a pure function of (seed, sweep, chain, site,
+// element) whatever the tiling or sharding.
+__device__ __forceinline__ bool zig_fast(unsigned int lo, unsigned int hi, double& z) {
+  const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(omc_zig_kw) + (lo & (OMC_ZIG_LAYERS - 1)));   // one 16-byte gather
+  struct { unsigned long long k; double w; } t = {raw.x, __longlong_as_double((long long)raw.y)};
+  const unsigned int jhi = hi >> 12, jlo = (hi << 20) | (lo >> 12);          // j = bits 12..63
+  const double dj = __hiloint2double((int)(0x43300000u | jhi), (int)jlo) - 4503599627370496.0;   // exact: no int -> fp convert
+  const double x = dj * t.w;
+  z = __hiloint2double(__double2hiint(x) ^ (int)((lo << 21) & 0x80000000u), __double2loint(x));   // sign = bit 10
+  return (((unsigned long long)jhi << 32) | jlo) < t.k;
+}
+__device__ __noinline__ double zig_slow(unsigned long long sw, uint2 key, unsigned int gchain, unsigned int site,
+                                        unsigned long long elem) {
+  const uint4 ctr = normal_counter(sw, gchain, site, elem >> 1);
+  uint4 b = philox4x32_10(ctr, key);
+  unsigned int lo = (elem & 1ull) ? b.z : b.x, hi = (elem & 1ull) ? b.w : b.y;
+  unsigned int attempt = 0;
+  while (true) {
+    double z;
+    if (zig_fast(lo, hi, z)) return z;
+    const int i = (int)(lo & (OMC_ZIG_LAYERS - 1));
+    const bool neg = (lo >> 10) & 1u;
+    ++attempt;
+    b = philox4x32_10(ctr, make_uint2(key.x ^ 0x5A1C0DE5u, key.y + 2u * attempt + (unsigned int)(elem & 1ull)));
+    if (i == 0) {                       // the tail beyond R: x = R + E1 / R accepted when 2 E2 > (E1 / R)^2
+      while (true) {
+        const double xx = -log(omc_u01(b.x, b.y)) * OMC_ZIG_INV_R, yy = -log(omc_u01(b.z, b.w));
+        if (yy + yy > xx * xx) return neg ? -(OMC_ZIG_R + xx) : OMC_ZIG_R + xx;
+        ++attempt;
+        b = philox4x32_10(ctr, make_uint2(key.x ^ 0x5A1C0DE5u, key.y + 2u * attempt + (unsigned int)(elem & 1ull)));
+      }
+    }
+    const double f1 = __ldg(omc_zig_f + i), f0 = __ldg(omc_zig_f + i - 1);   // wedge: density at a uniform height of the layer
+    if (fma(f0 - f1, omc_u01(b.x, b.y), f1) < exp(-0.5 * z * z)) return z;
+    lo = b.z;                           // rejected: a fresh candidate
+    hi = b.w;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- aggregate kernel
 // G chains per CTA (G x TG_NT threads): the tile of the shared P is staged ONCE for the G chains, which halves (G = 2)
 // or quarters (G = 4) the shared memory per resident warp -- this kernel is a load -> compute -> store pipeline whose
@@ -588,6 +642,11 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
   extern __shared__ __align__(128) double sm[];
   __shared__ double s_red[2 * TG_SNW];
   __shared__ double s_part[3 * TG_SNW];
+#ifndef TG_BOX_MULLER
+  constexpr int ZIG_SLOTS = 64;
+  __shared__ unsigned short s_zig_item[TG_SNW][ZIG_SLOTS];
+  __shared__ double s_zig_val[TG_SNW][ZIG_SLOTS];
+#endif
   __shared__ int s_bad;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
   double* spe = sm + 4;
@@ -674,7 +733,11 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
 #ifdef TG_EXP_NORNG
   if (false) {
 #else
+#ifdef TG_BOX_MULLER
   if (!inject && solve && nvalid > 0) {
+#else
+  if (!inject && solve) {          // block-uniform: the rejected candidates are resolved by warp-collective code
+#endif
 #endif
     const unsigned long long sweep = a.rng.sweep ? *a.rng.sweep : 0ull;
     const uint2 key = make_uint2((unsigned int)a.rng.seed, (unsigned int)(a.rng.seed >> 32));
@@ -690,13 +753,21 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
 #pragma unroll
       for (int i = 0; i < TG_RNG_GROUP; ++i) {
         const int c = c0 + i;
+#ifdef TG_BOX_MULLER
 #ifdef TG_LOGTAB_SMEM
         if (c < TG_PAIRS && !normal_pair_fast<true>(b[i], g[2 * c], g[2 * c + 1], s_logtab)) redo |= 1u << c;
 #else
         if (c < TG_PAIRS && !normal_pair_fast(b[i], g[2 * c], g[2 * c + 1])) redo |= 1u << c;
 #endif
+#else
+        if (c < TG_PAIRS) {
+          if (!zig_fast(b[i].x, b[i].y, g[2 * c])) redo |= 1u << (2 * c);
+          if (!zig_fast(b[i].z, b[i].w, g[2 * c + 1])) redo |= 1u << (2 * c + 1);
+        }
+#endif
       }
     }
+#ifdef TG_BOX_MULLER
     while (redo) {   // probability 2^-12 per pair
       const int c = __ffs(redo) - 1;
       redo &= redo - 1;
@@ -705,6 +776,51 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
       for (int cc = 0; cc < TG_PAIRS; ++cc)
         if (cc == c) { g[2 * cc] = z.x; g[2 * cc + 1] = z.y; }
     }
+#else
+    // Rejected candidates (0.4 % of the elements: ~2 per warp and tile) are redone by the WARP together: the lanes
+    // list their rejected elements in shared memory and every item gets a lane of its own for the slow path (wedge /
+    // tail / restart), instead of the whole warp walking the slow path once per item of its unluckiest lane.
+    {
+      redo &= (1u << nvalid) - 1u;                                 // elements beyond the end of the chain need no draw
+      const int cnt = __popc(redo);
+      int pre = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(FULL, pre, d);
+        if (lane >= d) pre += o;
+      }
+      const int total = __shfl_sync(FULL, pre, 31);
+      pre -= cnt;                                                  // exclusive prefix
+      if (total > 0) {                                             // warp-uniform
+        unsigned short* list = s_zig_item[warp];
+        double* res = s_zig_val[warp];
+        {
+          unsigned int m = redo;
+          for (int k = pre; m; ++k) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            if (k < ZIG_SLOTS) list[k] = (unsigned short)(lane * 32 + e);
+          }
+        }
+        __syncwarp();
+        for (int it = lane; it < min(total, ZIG_SLOTS); it += 32) {
+          const int item = list[it];
+          const long long elem = i_t + (long long)(warp * 32 + (item >> 5)) * TG_K + (item & 31);
+          res[it] = zig_slow(sweep, key, gchain, a.rng.site, (unsigned long long)elem);
+        }
+        __syncwarp();
+        unsigned int m = redo;
+        for (int k = pre; m; ++k) {
+          const int e = __ffs(m) - 1;
+          m &= m - 1;
+          const double z = (k < ZIG_SLOTS) ? res[k] : zig_slow(sweep, key, gchain, a.rng.site, (unsigned long long)i0 + e);
+#pragma unroll
+          for (int ee = 0; ee < TG_K; ++ee)
+            if (ee == e) g[ee] = z;
+        }
+      }
+    }
+#endif
   } else {
 #pragma unroll
     for (int k = 0; k < TG_K; ++k) g[k] = 0.0;

@@ -141,7 +141,7 @@ def log_p_host(dist, state: dict, by_observation: bool = False):
     from openmcmc_b200.model import Model
 
     if by_observation:
-        raise engine.PlanError("log_p(by_observation=True) is only used by MixtureAllocation (SURVEY.md §8 f2: next)")
+        return _log_p_by_observation(dist, state)
     (dist,), state, _ = engine.unreplicate([dist], state)
     plan, st = _one_chain_plan(state)
     out = plan.new(1)
@@ -151,6 +151,52 @@ def log_p_host(dist, state: dict, by_observation: bool = False):
         fn()
     torch.cuda.synchronize()
     return float(out.item())
+
+
+def _log_p_by_observation(dist, state: dict):
+    """log_p(state, by_observation=True): one value per COLUMN of the response (its replicates), rows summed.
+    ref: distribution.py:241-261 (Gamma), 422-442 (Uniform), 490-508 (Poisson); location_scale.py:145-167 ->
+    gmrf.py:321-348 (Normal).  Every column is handed to the log-density kernels as a "chain" of its own."""
+    from openmcmc_b200 import gmrf
+    from openmcmc_b200.distribution.distribution import Gamma, Poisson, Uniform
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.parameter import Identity
+
+    x = np.asarray(state[dist.response], dtype=np.float64)
+    x = x.reshape(-1, 1) if x.ndim < 2 else x
+    p, n = x.shape
+    if isinstance(dist, Uniform):
+        rng_ = np.broadcast_to(dist.domain_response_upper - dist.domain_response_lower, (p, 1))
+        return np.ones(n) * -float(np.sum(np.log(rng_)))
+    if type(dist) is Normal:
+        lo, hi = dist.domain_response_lower, dist.domain_response_upper      # location_scale.py:164-165, 169-188
+        if (lo is not None and np.any(x < lo)) or (hi is not None and np.any(x > hi)):
+            return -np.inf
+        return gmrf.multivariate_normal_pdf(x, dist.mean.predictor(state), dist.precision.predictor(state), by_observation=True)
+    if isinstance(dist, (Gamma, Poisson)):
+        dev = torch.device("cuda", K.init_device())
+
+        def cols(par):      # [p or 1, n or 1] parameter -> per-column device rows [n, p'] (layout only)
+            if not isinstance(par, Identity):
+                raise engine.PlanError("log_p(by_observation=True): Identity shape / rate parameters only")
+            a = np.asarray(state[par.form], dtype=np.float64)
+            a = a.reshape(-1, 1) if a.ndim < 2 else a
+            if a.shape[0] not in (1, p) or a.shape[1] not in (1, n):
+                raise ValueError(f"parameter '{par.form}' of shape {a.shape} for a response of shape {(p, n)}")
+            t = K.upload(np.ascontiguousarray(a.T), dev)            # [n or 1, p or 1]
+            return t, (a.shape[0] if a.shape[1] == n else 0), a.shape[0]
+
+        xd = K.upload(np.ascontiguousarray(x.T), dev)               # [n, p]
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        if isinstance(dist, Gamma):
+            (sh, sh_stride, sh_len), (rt, rt_stride, rt_len) = cols(dist.shape), cols(dist.rate)
+            K.logp_gamma(n, p, K.vec(xd, p), K.vec((sh, sh_stride)), sh_len, K.vec((rt, rt_stride)), rt_len, out, 0)
+        else:
+            rt, rt_stride, rt_len = cols(dist.rate)
+            K.logp_poisson(n, p, K.vec(xd, p), K.vec((rt, rt_stride)), rt_len, out, 0)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+    raise engine.PlanError(f"log_p(by_observation=True) is not provided for {type(dist).__name__} on the device")
 
 
 def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, method: str):

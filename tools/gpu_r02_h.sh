@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-OUT=gpurun_out/r02h
+OUT=gpurun_out/r02i
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1
 echo "pytest rc=$?" | tee -a $OUT/summary.txt
@@ -13,6 +13,6 @@ python - <<'PY'
 import json
 for w in ("c2","c1","c4a","c4b"):
     try:
-        d=json.load(open(f"gpurun_out/r02h/bench_{w}.json")); print(w, d["value"], d["ms_per_step"], d["gpu_launches"], d["roofline"]["kernel_ms"])
+        d=json.load(open(f"gpurun_out/r02i/bench_{w}.json")); print(w, d["value"], d["ms_per_step"], d["gpu_launches"], d["roofline"]["kernel_ms"])
     except Exception as e: print(w, "failed", e)
 PY
