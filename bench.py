@@ -552,8 +552,19 @@ def e2e_leg(ctx, wl, key, C, n, p, steps, thin, upload_blocks):
         t_start = time.perf_counter()
         r = MCMC(hstate, samplers2, model=mdl, n_burn=steps % thin if steps >= thin else 0, n_iter=n_iter,
                  n_thin=thin, n_chains=Ce, seed=7, device=ctx.local, chain_offset=ctx.rank * C, upload_blocks=blocks)
+        prof = None
+        if os.environ.get("OMC_BENCH_PROFILE"):      # host-side profile of the e2e leg (tuning aid): top of cProfile -> stderr
+            import cProfile
+
+            prof = cProfile.Profile()
+            prof.enable()
         with contextlib.redirect_stdout(io.StringIO()):
             r.run_mcmc()
+        if prof is not None:
+            import pstats
+
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(40)
         return r, t_start
 
     try:

@@ -530,6 +530,14 @@ typedef struct {
   double* logp_out;            /* [n_chains] when logp_only                  */
   int* size_class;             /* optional scratch [n_chains]: the step is then launched per size class of live
                                   components (small shared-memory footprint for small chains)                   */
+  /* Live Gram matrix S = B'B of the current basis in the chain state (optional): [n_chains][n_max][n_max], lower
+   * triangle, valid where gram_valid[c] != 0.  The matched transitions need the Gram matrix of the LARGER basis
+   * (reversible_jump.py:240-242, 290-291): with it resident a birth costs the inner products of ONE new column
+   * (2 n_data k flops) and a death none, instead of 2 n_data k^2 per step; an accepted move appends / deletes a row and
+   * column.  Whatever rewrites basis columns (omc_rj_basis, omc_rj_knot_walk) clears gram_valid; the next step then
+   * recomputes S in full and stores it. */
+  double* gram;
+  int* gram_valid;
 } omc_rj_t;
 int omc_rj_smem_bytes(int n_data, int n_max);
 int omc_reversible_jump(const omc_rj_t* args, void* stream);

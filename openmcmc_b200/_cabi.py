@@ -318,7 +318,8 @@ class RJArgs(C.Structure):
                 ("birth_probability", C.c_double), ("match_scale", C.c_double), ("match_truncated", C.c_int),
                 ("match_lo", C.c_double), ("match_hi", C.c_double), ("rng", Rng), ("debug", C.c_void_p),
                 ("debug_sweep_stride", C.c_longlong), ("counters", C.c_void_p), ("status", C.c_void_p),
-                ("probe", C.c_void_p), ("logp_only", C.c_int), ("logp_out", C.c_void_p), ("size_class", C.c_void_p)]
+                ("probe", C.c_void_p), ("logp_only", C.c_int), ("logp_out", C.c_void_p), ("size_class", C.c_void_p),
+                ("gram", C.c_void_p), ("gram_valid", C.c_void_p)]
 
 
 PROTOTYPES.update({

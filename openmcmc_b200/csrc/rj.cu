@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
   double* be = om + lv;                   // current coefficients
   double* bp = be + lv;                   // proposed coefficients (laid out on the LARGER basis)
   double* colv = bp + lv;
-  unsigned short* ptab = reinterpret_cast<unsigned short*>(colv + lv);   // (i, j) of every lower-triangle pair
+  double* snew = colv + lv;               // birth: inner products of the new column with the larger basis (row k of S)
+  unsigned short* ptab = reinterpret_cast<unsigned short*>(snew + lv);   // (i, j) of every lower-triangle pair
   const int k = (int)a.n_basis[chain];
   if (cls >= 0 && a.size_class[chain] != cls) return;   // another launch of this step owns the chain
   double* thg = a.theta + (long long)chain * cap;
@@ -266,29 +267,105 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
     ptab[pi] = (unsigned short)((i << 8) | (pi - i * (i + 1) / 2));
   }
   __syncthreads();
-  // ---- pass 1 over the data rows: Gram matrix of the larger basis (lower triangle) and the current residual sum
-  //      (Prefetching the next chunk into registers while the current one is multiplied was tried and bought nothing:
-  //      the other resident CTAs already cover that latency.)
+  // ---- pass 1 over the data rows: Gram matrix of the larger basis (lower triangle) and the current residual sum.
+  //      With the live Gram matrix in the chain state (a.gram, valid) only the NEW column's inner products are formed:
+  //      a warp per data row, lanes over the columns (coalesced), the row's fitted value by a shuffle sum.
   double rss_c = 0.0;
-  for (int r0 = 0; r0 < nd; r0 += RJ_ROWS) {
-    const int rows = min(RJ_ROWS, nd - r0);
-    rj_for2d(rows, m, [&](int r_, int j) {
-      chunk[r_ * ld + j] = (j < k) ? Bg[(long long)(r0 + r_) * cap + j] : bnew[r0 + r_];
-    });
-    __syncthreads();
-    for (int pi = tid; pi < npair; pi += RJ_NT) {
+  double* Sg = a.gram ? a.gram + (long long)chain * cap * cap : nullptr;
+  const bool gram_on = Sg && a.gram_valid && cap <= 128;      // (the new-row pass covers 4 x 32 columns)
+  const bool have_gram = gram_on && a.gram_valid[chain] != 0;
+  if (have_gram) {
+    for (int pi = tid; pi < k * (k + 1) / 2; pi += RJ_NT) {
       const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
-      double s = 0.0;
-      for (int r_ = 0; r_ < rows; ++r_) s = fma(chunk[r_ * ld + i], chunk[r_ * ld + j], s);
-      A[i * ld + j] += s;
+      A[i * ld + j] = Sg[(long long)i * cap + j];
     }
-    if (yp && tid < rows) {
-      double f = 0.0;
-      for (int j = 0; j < k; ++j) f = fma(chunk[tid * ld + j], be[j], f);
-      const double q = yp[r0 + tid] - f;
-      rss_c = fma(q, q, rss_c);
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = RJ_NT / 32;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};           // this lane's columns lane, lane + 32, ... of the new row of S
+    double nn = 0.0;
+    // RB rows per warp and round: their loads go out together (one row at a time left 4 KB in flight per SM and the
+    // pass bound by HBM latency: 3.6 ms per sweep at the C5 shape, ncu long-scoreboard 5.6 per issue)
+    constexpr int RB = 8;
+    for (int r0 = warp * RB; r0 < nd; r0 += NWARP * RB) {
+      double v[RB][4], yv[RB];
+#pragma unroll
+      for (int t = 0; t < RB; ++t) {
+        const int r_ = r0 + t;
+        const double* row = Bg + (long long)min(r_, nd - 1) * cap;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = lane + 32 * q;
+          v[t][q] = (j < k && r_ < nd) ? row[j] : 0.0;
+        }
+        yv[t] = (yp && r_ < nd) ? yp[r_] : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < RB; ++t) {
+        const int r_ = r0 + t;
+        if (r_ >= nd) break;
+        const double bn = birth ? bnew[r_] : 0.0;
+        double f = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = lane + 32 * q;
+          if (j < k) {
+            f = fma(v[t][q], be[j], f);
+            part[q] = fma(bn, v[t][q], part[q]);
+          }
+        }
+        if (yp) {
+          f = omc_warp_sum(f);
+          const double q_ = yv[t] - f;
+          if (lane == 0) rss_c = fma(q_, q_, rss_c);
+        }
+        if (lane == 0) nn = fma(bn, bn, nn);
+      }
+    }
+    if (birth) {                                     // combine the warps in a fixed order (chunk is free in this path)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < k) chunk[warp * lv + lane + 32 * q] = part[q];
+      if (lane == 0) chunk[warp * lv + k] = nn;
+      __syncthreads();
+      for (int j = tid; j <= k; j += RJ_NT) {
+        double sacc = 0.0;
+        for (int w_ = 0; w_ < NWARP; ++w_) sacc += chunk[w_ * lv + j];
+        snew[j] = sacc;
+        A[k * ld + j] = sacc;
+      }
     }
     __syncthreads();
+  } else {
+    for (int r0 = 0; r0 < nd; r0 += RJ_ROWS) {
+      const int rows = min(RJ_ROWS, nd - r0);
+      rj_for2d(rows, m, [&](int r_, int j) {
+        chunk[r_ * ld + j] = (j < k) ? Bg[(long long)(r0 + r_) * cap + j] : bnew[r0 + r_];
+      });
+      __syncthreads();
+      for (int pi = tid; pi < npair; pi += RJ_NT) {
+        const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
+        double s = 0.0;
+        for (int r_ = 0; r_ < rows; ++r_) s = fma(chunk[r_ * ld + i], chunk[r_ * ld + j], s);
+        A[i * ld + j] += s;
+      }
+      if (yp && tid < rows) {
+        double f = 0.0;
+        for (int j = 0; j < k; ++j) f = fma(chunk[tid * ld + j], be[j], f);
+        const double q = yp[r0 + tid] - f;
+        rss_c = fma(q, q, rss_c);
+      }
+      __syncthreads();
+    }
+    if (gram_on) {                                   // first step after the basis was rewritten: keep S from here on
+      for (int pi = tid; pi < k * (k + 1) / 2; pi += RJ_NT) {
+        const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
+        Sg[(long long)i * cap + j] = A[i * ld + j];
+      }
+      if (birth)
+        for (int j = tid; j <= k; j += RJ_NT) snew[j] = A[k * ld + j];
+      if (tid == 0) a.gram_valid[chain] = 1;
+      __syncthreads();
+    }
   }
   for (int pi = tid; pi < npair; pi += RJ_NT) {   // symmetrise, add the ridge
     const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
@@ -365,21 +442,35 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
   rss_c = omc_block_sum(rss_c, s_red);
   __syncthreads();
   rss_p = omc_block_sum(rss_p, s_red);
+  // ---- prior terms of both states, one component per thread (they were a serial loop of thread 0 with two lgamma /
+  //      log evaluations per component while the other 127 threads waited at the barrier below: 13 % of the stall
+  //      samples of the step, profiles/r02_ncu_rj_lines.txt)
+  const double mu_b = vat(a.mu_beta, chain, 0.0);
+  double ss_c = 0.0, ss_p = 0.0, lw_c = 0.0, lw_p = 0.0;
+  for (int j = tid; j < m; j += RJ_NT) {
+    const double lw = a.sample_omega ? gamma_logpdf(om[j], shape_w, rate_w) : 0.0;
+    if (j < k) {
+      ss_c += (be[j] - mu_b) * (be[j] - mu_b);
+      lw_c += lw;
+    }
+    if (birth || j != d) {
+      ss_p += (bp[j] - mu_b) * (bp[j] - mu_b);
+      lw_p += lw;
+    }
+  }
+  __syncthreads();
+  ss_c = omc_block_sum(ss_c, s_red);
+  __syncthreads();
+  ss_p = omc_block_sum(ss_p, s_red);
+  __syncthreads();
+  lw_c = omc_block_sum(lw_c, s_red);
+  __syncthreads();
+  lw_p = omc_block_sum(lw_p, s_red);
   // ---- log-densities of the whole model at both states, transition densities, accept / reject (thread 0)
   if (tid == 0) {
-    const double tau_y = vat(a.tau_y, chain, 1.0), tau_b = vat(a.tau_beta, chain, 1.0), mu_b = vat(a.mu_beta, chain, 0.0);
+    const double tau_y = vat(a.tau_y, chain, 1.0), tau_b = vat(a.tau_beta, chain, 1.0);
     const double rho = vat(a.rho, chain, 1.0);
     const int kp = birth ? k + 1 : k - 1;
-    double ss_c = 0.0, ss_p = 0.0, lw_c = 0.0, lw_p = 0.0;
-    for (int j = 0; j < k; ++j) {
-      ss_c += (be[j] - mu_b) * (be[j] - mu_b);
-      if (a.sample_omega) lw_c += gamma_logpdf(om[j], shape_w, rate_w);
-    }
-    for (int j = 0; j < m; ++j) {
-      if (!birth && j == d) continue;
-      ss_p += (bp[j] - mu_b) * (bp[j] - mu_b);
-      if (a.sample_omega) lw_p += gamma_logpdf(om[j], shape_w, rate_w);
-    }
     auto logp = [&](int n, double rss, double ss, double lw) {
       double lp = 0.0;
       if (yp) lp += 0.5 * (nd * log(tau_y) - nd * RJ_LOG_2PI - tau_y * rss);
@@ -420,7 +511,10 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
   __syncthreads();
   if (!sh.accept) return;
   // ---- accepted: write the new state (padded layout)
+  const bool keep_gram = gram_on;
   if (birth) {
+    if (keep_gram)
+      for (int j = tid; j <= k; j += RJ_NT) Sg[(long long)k * cap + j] = snew[j];     // new row of S
     for (int j = tid; j <= k; j += RJ_NT) beg[j] = bp[j];
     for (int r_ = tid; r_ < nd; r_ += RJ_NT) Bg[(long long)r_ * cap + k] = bnew[r_];
     if (tid == 0) {
@@ -438,6 +532,21 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
     for (int r_ = tid; r_ < nd; r_ += RJ_NT) {
       double* row = Bg + (long long)r_ * cap;
       for (int j = d; j < k - 1; ++j) row[j] = row[j + 1];
+    }
+    if (keep_gram) {     // delete row / column d of S: rows >= d through shared memory (A is free now), then back
+      const int npk = k * (k + 1) / 2;
+      for (int pi = tid; pi < npk; pi += RJ_NT) {
+        const int i = ptab[pi] >> 8, j = ptab[pi] & 255;
+        if (i >= d) A[i * ld + j] = Sg[(long long)i * cap + j];
+      }
+      __syncthreads();
+      for (int pi = tid; pi < npk; pi += RJ_NT) {
+        const int i = ptab[pi] >> 8, j = ptab[pi] & 255;       // (i, j) of the NEW matrix, i < k - 1
+        if (i >= d && i < k - 1) {
+          const int si = i + 1, sj = j < d ? j : j + 1;
+          Sg[(long long)i * cap + j] = A[si * ld + sj];
+        }
+      }
     }
     if (tid == 0) a.n_basis[chain] = (double)(k - 1);
   }
@@ -461,6 +570,7 @@ __global__ void rj_basis_kernel(omc_rj_t a) {
   double v = 0.0;
   if (j < k) v = normpdf(a.X[r_], a.theta[(long long)chain * a.n_max + j], a.omega[(long long)chain * a.n_max + j]);
   a.B[((long long)chain * a.n_data + r_) * a.n_max + j] = v;
+  if (e == 0 && a.gram_valid) a.gram_valid[chain] = 0;          // the basis is rewritten: the live Gram matrix is stale
 }
 
 int rj_check(const omc_rj_t* a, const char* who) {
@@ -476,7 +586,7 @@ extern "C" {
 
 static int rj_smem_for_ld(int n_data, int n_max, int ld) {
   const int pair_table_doubles = (ld * (ld + 1) / 2 * 2 + 7) / 8;   // 16-bit (i, j) per lower-triangle pair
-  return (ld * ld + RJ_ROWS * ld + n_data + 5 * (n_max + 1) + pair_table_doubles) * 8;
+  return (ld * ld + RJ_ROWS * ld + n_data + 6 * (n_max + 1) + pair_table_doubles) * 8;
 }
 
 int omc_rj_smem_bytes(int n_data, int n_max) { return rj_smem_for_ld(n_data, n_max, n_max + 1); }

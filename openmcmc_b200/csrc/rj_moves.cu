@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(RM_NT) rj_knot_walk_kernel(omc_rj_walk_t w) {
   for (int j = tid; j < k; j += RM_NT) {
     if (w.which) omg[j] = om[j]; else thg[j] = th[j];
   }
+  if (tid == 0 && n_acc > 0 && w.model.gram_valid) w.model.gram_valid[chain] = 0;   // basis columns moved: S = B'B is stale
   if (tid == 0 && w.counters) {
     w.counters[2 * (long long)chain] += n_acc;
     w.counters[2 * (long long)chain + 1] += k;

@@ -70,7 +70,11 @@ class GMRFField:
             Cm = st.n_chains if mu0.per_chain else 1
             h = plan.new(Cm, self.n)
             K.tridiag_matvec(pd, pe, mu0.vec(), Cm, self.n, h)   # constant data: once at plan time
-        self.prior = dict(nrm=nrm, P=P, pd=pd, pe=pe, lam=st[sname] if sname else None, mu0=mu0, h=h,
+        Ph = host_state.get(mname)
+        logdet_key = None
+        if sparse.issparse(Ph):     # identity of the constant host matrix (and a checksum of its values) for the log|P| cache
+            logdet_key = (id(Ph), Ph.shape, Ph.nnz, float(Ph.data.sum()) if Ph.nnz else 0.0)
+        self.prior = dict(nrm=nrm, P=P, pd=pd, pe=pe, lam=st[sname] if sname else None, mu0=mu0, h=h, logdet_key=logdet_key,
                           h_per_chain=bool(mu0 is not None and mu0.per_chain), cnt=float(P.npos),
                           deps=frozenset({self.name, nrm.mean.form, mname}))
         self.q_prior = f"quad[{nrm.response}]"
@@ -134,13 +138,23 @@ class GMRFField:
             plan, pr = self.plan, self.prior
             dev = plan.state.device
             out = plan.new(1)
+            key = pr.get("logdet_key")
+            if key is not None and key in _LOGDET_CACHE:      # the same constant matrix in an earlier plan of this process
+                out.fill_(_LOGDET_CACHE[key])
+                self._logdet_P = out
+                return out
             zero = torch.zeros(1, dtype=torch.float64, device=dev)
             ws = torch.zeros(K.tridiag_workspace(1, self.n), dtype=torch.uint8, device=dev)
             K.tridiag_nn_draw(K.tridiag_args(1, self.n, pr["pd"], pr["pe"], ws, tau=K.vec(zero), y=K.vec(pr["pd"]),
                                              logdet=out))
             torch.cuda.current_stream().synchronize()
+            if key is not None:
+                _LOGDET_CACHE[key] = float(out.item())
             self._logdet_P = out
         return self._logdet_P
+
+
+_LOGDET_CACHE = {}     # logdet_key of a constant prior precision -> log|P| (one factorisation per matrix and process)
 
 
 def _fields(plan):

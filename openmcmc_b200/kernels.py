@@ -580,7 +580,7 @@ def tridiag_matvec(pd, pe, v, n_chains, n, out):
 def rj_args(n_chains, n_data, n_max, n_basis, theta, omega, beta, B, X, theta_lo, theta_hi, birth_probability=0.5,
             y=None, tau_y=None, sample_omega=True, omega_shape=None, omega_rate=None, mu_beta=None, tau_beta=None,
             rho=None, match_scale=1.0, match_limits=None, rng_=None, debug=None, debug_sweep_stride=0, counters=None,
-            status=None, probe=None, logp_out=None, size_class=None) -> "_cabi.RJArgs":
+            status=None, probe=None, logp_out=None, size_class=None, gram=None, gram_valid=None) -> "_cabi.RJArgs":
     """Build an omc_rj_t.  State tensors are padded to n_max; y/tau_y/... are omc_vec_t (see `vec`) or None."""
     none = Vec(None, 0)
     a = _cabi.RJArgs()
@@ -598,7 +598,7 @@ def rj_args(n_chains, n_data, n_max, n_basis, theta, omega, beta, B, X, theta_lo
     a.debug = debug.data_ptr() if debug is not None else None
     a.debug_sweep_stride = int(debug_sweep_stride)
     for name, t in (("counters", counters), ("status", status), ("probe", probe), ("logp_out", logp_out),
-                    ("size_class", size_class)):
+                    ("size_class", size_class), ("gram", gram), ("gram_valid", gram_valid)):
         setattr(a, name, t.data_ptr() if t is not None else None)
     a.logp_only = 0
     return a

@@ -272,6 +272,10 @@ class MCMC:
                 fn()
         for t, copy_ in saved:
             t.copy_(copy_)
+        for s in self.samplers:       # derived chain state a sampler keeps besides the state entries (live Gram matrix)
+            hook = getattr(s, "reset_derived", None)
+            if hook is not None:
+                hook(plan)
         torch.cuda.current_stream().synchronize()
 
     def launches_per_sweep(self) -> int:
@@ -364,7 +368,8 @@ class MCMC:
                 if name in last_rows and rj is None and n_done == self.n_iter:
                     # the state after the last sweep IS the last stored iteration: no second download (C3: 512 MB)
                     a = st.arrays[name]
-                    new = np.array(last_rows[name]).reshape((C, a.rows, a.cols) if C > 1 else (a.rows, a.cols))
+                    # (a view of the store's last row: a copy of a 512 MB field would cost what the download did)
+                    new = last_rows[name].reshape((C, a.rows, a.cols) if C > 1 else (a.rows, a.cols))
                 else:
                     new = st.get_host(name)
                     d2h += new.nbytes

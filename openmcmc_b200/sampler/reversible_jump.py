@@ -22,6 +22,11 @@ from openmcmc_b200 import kernels as K
 from openmcmc_b200.sampler.metropolis_hastings import MetropolisHastings
 
 
+# Keep S = B'B of every chain's live basis in the chain state and update it per birth / death (omc.h: omc_rj_t.gram).
+# False recomputes it in every step, the first round's form; tests compare the two.
+LIVE_GRAM = True
+
+
 @dataclass
 class GaussianKernelBasis:
     """matrix[:, j] = Normal pdf(locations; knots[j], widths[j])  (make_basis of the reference's RJ tests)."""
@@ -183,17 +188,29 @@ class ReversibleJump(MetropolisHastings):
             if pt["y"] is not None:
                 ya = st[pt["y"]]
                 yv = ya.vec()
+            live = LIVE_GRAM and n_max <= 128
+            ctx["gram_valid"] = plan.keep_tensor(torch.zeros(C, dtype=torch.int32, device=dev)) if live else None
             ctx["args"] = K.rj_args(
                 C, nd, n_max, n_dev, theta, omega, beta, Bm, X.data, pt["theta_lo"], pt["theta_hi"],
                 self.birth_probability, y=yv, tau_y=v("tau_y"), sample_omega=pt["sample_omega"],
                 omega_shape=v("omega_shape"), omega_rate=v("omega_rate"), mu_beta=v("mu_beta"), tau_beta=v("tau_beta"),
                 rho=v("rho"), match_scale=float(self.matching_params["scale"]), match_limits=lim, rng_=ctx["rng"],
                 debug=dbg, debug_sweep_stride=dbg_stride, counters=ctx["counters"], status=plan.status,
-                probe=ctx["probe"], size_class=plan.keep_tensor(torch.zeros(C, dtype=torch.int32, device=dev)))
+                probe=ctx["probe"], size_class=plan.keep_tensor(torch.zeros(C, dtype=torch.int32, device=dev)),
+                # the live Gram matrix B'B in the chain state (omc.h): a birth costs one new column of inner products
+                gram=plan.keep_tensor(torch.empty(C, n_max, n_max, dtype=torch.float64, device=dev)) if live else None,
+                gram_valid=ctx["gram_valid"])
             plan.keep.extend([n_dev, theta, omega, beta, Bm])
             K.rj_basis(ctx["args"])     # basis of the initial knots (the host copy is not trusted to be padded)
             plan.__dict__["_rj"] = self
         return ctx["args"]
+
+    def reset_derived(self, plan):
+        """After the chain state was put back by hand (the eager warm-up pass of MCMC.prepare): the live Gram matrices
+        belong to the state that was there before."""
+        gv = plan.ctx(self).get("gram_valid")
+        if gv is not None:
+            gv.zero_()
 
     def compile(self, plan, host_state, debug_draws=None):
         args = self.setup(plan, host_state, debug_draws)
