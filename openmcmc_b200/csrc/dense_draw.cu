@@ -349,6 +349,7 @@ __global__ void ng_draw_kernel(omc_ng_draw_t a) {
 }  // namespace
 
 extern "C" int omc_nn_dense_draw(const omc_nn_dense_t* args, void* stream) {
+  if (args) OMC_REQUIRE_SITE(args->rng, "omc_nn_dense_draw");
   OMC_REQUIRE(args && args->stats.ptr && args->beta, "omc_nn_dense_draw: null argument");
   OMC_REQUIRE(args->p >= 1 && args->p <= PMAX, "omc_nn_dense_draw: p=%d outside [1,%d]", args->p, PMAX);
   OMC_REQUIRE(args->n_chains >= 1, "omc_nn_dense_draw: n_chains=%d", args->n_chains);
@@ -391,6 +392,7 @@ extern "C" int omc_quadform(const omc_quadform_t* args, void* stream) {
 }
 
 extern "C" int omc_ng_draw(const omc_ng_draw_t* args, void* stream) {
+  if (args) OMC_REQUIRE_SITE(args->rng, "omc_ng_draw");
   OMC_REQUIRE(args && args->out, "omc_ng_draw: null argument");
   const int threads = 128;
   const long long total = (long long)args->n_chains * (args->n_elem > 0 ? args->n_elem : 1);

@@ -950,6 +950,7 @@ int omc_mh_grad_hess(const omc_mh_model_t* model, const double* theta, int metho
 }
 
 int omc_random_walk(const omc_random_walk_t* a, void* stream) {
+  if (a) OMC_REQUIRE_SITE(a->rng, "omc_random_walk");
   OMC_REQUIRE(a && a->theta, "omc_random_walk: null argument");
   if (int rc = check_model(&a->model, "omc_random_walk")) return rc;
   OMC_REQUIRE(a->p_dim >= 1 && a->n_rep >= 1 && a->p_dim * a->n_rep == a->model.n_elem,
@@ -966,6 +967,7 @@ int omc_random_walk(const omc_random_walk_t* a, void* stream) {
 }
 
 int omc_mmala(const omc_mmala_t* a, void* stream) {
+  if (a) OMC_REQUIRE_SITE(a->rng, "omc_mmala");
   OMC_REQUIRE(a && a->theta, "omc_mmala: null argument");
   if (int rc = check_model(&a->model, "omc_mmala")) return rc;
   const int n = a->model.n_elem;

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(MX_THREADS) logp_categorical_kernel(int n, int
 extern "C" {
 
 int omc_mixture_allocation(const omc_mixture_alloc_t* a, void* stream) {
+  if (a) OMC_REQUIRE_SITE(a->rng, "omc_mixture_allocation");
   OMC_REQUIRE(a && a->x.ptr && a->mu.ptr && a->tau.ptr && a->prob.ptr && a->z, "omc_mixture_allocation: null argument");
   OMC_REQUIRE(a->n_chains >= 1 && a->n >= 1 && a->K >= 1, "omc_mixture_allocation: bad shape");
   const long long total = (long long)a->n_chains * a->n;

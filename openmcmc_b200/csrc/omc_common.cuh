@@ -28,6 +28,8 @@ void omc_set_error(const char* fmt, ...);
     }                                              \
   } while (0)
 #define OMC_LAUNCH_CHECK() OMC_CHECK_CUDA(cudaGetLastError())
+// the Philox counter gives a site 12 bits (omc_rng_block below)
+#define OMC_REQUIRE_SITE(rng, who) OMC_REQUIRE((rng).site < 4096u, "%s: rng.site = %u, sites are 12 bits", who, (rng).site)
 
 // ---------------------------------------------------------------- RNG
 // One RNG "site" per sampler in the sweep plan.  Counter layout (128 bit):
@@ -57,7 +59,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 __device__ __forceinline__ uint4 omc_rng_block(const OmcRng& r, unsigned int chain, unsigned int block) {
   unsigned long long sw = r.sweep ? *r.sweep : 0ull;
-  uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32), r.chain_offset + chain,
+  // word 3 holds the site (12 bits: the host wrapper refuses sites >= 4096) and the low 20 bits of the block index;
+  // the bits above spill into word 1 (zero for every block < 2^20, so those streams are what they always were)
+  uint4 ctr = make_uint4((unsigned int)sw, (unsigned int)(sw >> 32) ^ (block >> 20) * 0x9E3779B9u, r.chain_offset + chain,
                          (r.site << 20) | (block & 0xFFFFFu));
   uint2 key = make_uint2((unsigned int)r.seed, (unsigned int)(r.seed >> 32));
   return philox4x32_10(ctr, key);

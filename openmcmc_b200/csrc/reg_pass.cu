@@ -8,14 +8,17 @@
 //     cnt = #(w > 0)                  -- the reference's  sum(P.diagonal() > 0),            sampler.py:283
 // W = diag(w) (or I when w == nullptr); tau is NOT folded in here (ScaledMatrix scalar is applied by the consumers).
 //
-// Kernel: one CTA (4 warps) per (chain, row-split).  X rows are streamed global->shared with a 4-stage cp.async
-// (LDGSTS.128) pipeline into a padded layout (row stride 8*PB+4 doubles => the fragment reads are bank-conflict free).
-// The SYRK runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native FP64 MMA shape on
-// sm_100a).  A = X' and B = X come from the same tile, so one PB-register fragment set per 4 rows feeds all
-// PB(PB+1)/2 lower-triangle 8x8 output tiles.  For PB >= 5 the tiles are split over two "tile-group" warps
-// (18 tiles = 72 accumulator registers each at p=64) so that 3 CTAs = 12 warps fit per SM and the LDS->DMMA latency
-// of one warp is hidden by the others (ncu: profiles/r01_*); rows (k-steps) are split over the remaining warps.
-// g rides on tile-group 0 and rss on tile-group 1 (FP64 FMA pipe, ~5% of the DMMA work).
+// reg_pass_kernel<PB, ..., SYRK>: one CTA (4 warps) per (chain, row split).  Rows are staged global -> shared by
+// cp.async.bulk (TMA engine, one mbarrier per stage; 3 stages of 64 rows) into a chunked layout -- a stage is four
+// contiguous chunks of 16 packed rows, chunk q shifted by 4 doubles, so that the four k-lanes of a DMMA fragment (one
+// row from each chunk) read distinct banks; shapes or alignments the bulk path cannot take fall back to 16-byte
+// cp.async (LDGSTS) into a padded row layout.  The SYRK runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS
+// DMMA.8x8x4, the only native FP64 MMA shape on sm_100a).  A = X' and B = X come from the same tile, so one
+// PB-register fragment set per 4 rows feeds all PB(PB+1)/2 lower-triangle 8x8 output tiles; at p = 64 every warp
+// owns all 36 tiles (254 registers, 2 CTAs per SM) and the four warps split the rows.  g and rss ride on the FP64 FMA
+// pipe (~5% of the DMMA work).  SYRK = false compiles the tensor work out: the explicit-residual stream (omc_reg_rss).
+// 64 < p <= 512: gram_wide_kernel (64 x 64 panel pairs, a warp per 16 x 64 strip) + rss_wide_kernel below.
+// With data-only weights both passes are PROLOGUE work: the sweep reads the record and the centre.
 // Roofline: 46.1 MFLOP of DMMA per chain at n=10^4,p=64 vs 5.2 MB of HBM traffic => FP64-pipe bound.
 #include "../../include/omc.h"
 #include "omc_common.cuh"

@@ -592,6 +592,7 @@ static int rj_smem_for_ld(int n_data, int n_max, int ld) {
 int omc_rj_smem_bytes(int n_data, int n_max) { return rj_smem_for_ld(n_data, n_max, n_max + 1); }
 
 int omc_reversible_jump(const omc_rj_t* a, void* stream) {
+  if (a) OMC_REQUIRE_SITE(a->rng, "omc_reversible_jump");
   if (int rc = rj_check(a, "omc_reversible_jump")) return rc;
   OMC_REQUIRE(a->birth_probability >= 0.0 && a->birth_probability <= 1.0, "omc_reversible_jump: birth_probability");
   OMC_REQUIRE(a->logp_only || a->match_scale > 0.0, "omc_reversible_jump: match_scale");

@@ -409,6 +409,7 @@ extern "C" {
 
 int omc_rj_knot_walk(const omc_rj_walk_t* w, void* stream) {
   OMC_REQUIRE(w, "omc_rj_knot_walk: null argument");
+  OMC_REQUIRE_SITE(w->model.rng, "omc_rj_knot_walk");
   if (int rc = rm_check(&w->model, "omc_rj_knot_walk")) return rc;
   OMC_REQUIRE(w->which == 0 || w->which == 1, "omc_rj_knot_walk: which=%d", w->which);
   OMC_REQUIRE(w->step > 0.0 && w->lim_hi > w->lim_lo, "omc_rj_knot_walk: step / limits");
@@ -422,6 +423,7 @@ int omc_rj_knot_walk(const omc_rj_walk_t* w, void* stream) {
 
 int omc_rj_coef_mmala(const omc_rj_mmala_t* m, void* stream) {
   OMC_REQUIRE(m, "omc_rj_coef_mmala: null argument");
+  OMC_REQUIRE_SITE(m->model.rng, "omc_rj_coef_mmala");
   const omc_rj_t* a = &m->model;
   if (int rc = rm_check(a, "omc_rj_coef_mmala")) return rc;
   OMC_REQUIRE(m->step > 0.0, "omc_rj_coef_mmala: step=%g", m->step);

@@ -18,8 +18,9 @@
 //                      h_i = b_i p_{i-1} - e_{i-1} h_{i-1}.  Element maps compose as 3x3 block-triangular matrices (7
 //                      entries, no divisions); thread aggregates -> CTA scan.  Pure streaming: writes every thread's
 //                      exclusive prefix inside its tile (56 B per 18 elements) and the tile total.
-//  tg_tilescan_kernel  one warp per chain scans the tile totals -> the exact (u, f) entering every tile.
-//  tg_solve_kernel     draws the tile's normals while its TMA loads are in flight, forms the exact (1/u, f) entering each
+//  tg_tilescan_kernel  one CTA per chain scans the tile totals -> the exact (u, f) entering every tile.
+//  tg_solve_kernel     draws the tile's normals (four per Philox block, fp32 special-function unit for the
+//                      transcendental parts) while its TMA loads are in flight, forms the exact (1/u, f) entering each
 //                      thread's 18 elements, re-runs the *sequential* recurrences on them (so every pivot / f / g comes
 //                      from the reference's operation sequence), keeps g and m in registers, builds the backward affine
 //                      aggregate on the way, scans it (CTA + reverse decoupled look-back over tiles), then walks back
@@ -80,11 +81,24 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef TG_RNG_GROUP
 #define TG_RNG_GROUP 3                    // Philox blocks advanced in lock-step per thread
 #endif
+#ifndef TG_AGG_NORM_A
+#define TG_AGG_NORM_A 4                   // thread aggregate: power-of-two renormalisation after element pairs A and B (and at the
+#define TG_AGG_NORM_B 4                   // end); entries grow like u^k, so one mid-way stop keeps |d| up to 1e30 in range
+#endif
+#ifndef TG_AGG_NORM_SCAN
+#define TG_AGG_NORM_SCAN 0                // normalised inputs grow by < 2^63 over the five levels of the warp scan
+#endif
+#ifndef TG_PREFETCH_AHEAD
+#define TG_PREFETCH_AHEAD 0               // work items ahead whose y tile a CTA pulls into L2 (0 = off)
+#endif
 #ifndef TG_LB_WIN
 #define TG_LB_WIN 4                       // successors polled in the first look-back round
 #endif
 #ifndef TG_ZIGGURAT
 #define TG_BOX_MULLER 1                   // normals of the solve kernel: Box-Muller pairs (default) or the ziggurat below
+#ifndef TG_NORMALS_F64
+#define TG_NORMALS_F32 1                  // ... with the fp32-assisted generator (-DTG_NORMALS_F64: all-fp64 Box-Muller)
+#endif
 #endif
 #ifndef TG_SOLVE_MINB
 #define TG_SOLVE_MINB (512 / TG_SNT_DEF)   // resident solve CTAs per SM the register allocation aims at (lean variant)
@@ -159,8 +173,15 @@ __device__ __forceinline__ TM tm_mul(const TM& x, const TM& y) {  // x after y
 }
 // scale by a power of two so that the projective block (a b c d) has magnitude ~1 (exact; entries grow like u^k)
 __device__ __forceinline__ void tm_normalize(TM& t) {
+#ifdef TG_NORM_FMAX
   const double mx = fmax(fmax(fabs(t.a), fabs(t.b)), fmax(fabs(t.c), fabs(t.d)));
   int ex = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+#else
+  // the high words of |a| .. |d| order like the magnitudes: the largest exponent comes out of three integer max
+  const int hmx = max(max(__double2hiint(t.a) & 0x7fffffff, __double2hiint(t.b) & 0x7fffffff),
+                      max(__double2hiint(t.c) & 0x7fffffff, __double2hiint(t.d) & 0x7fffffff));
+  int ex = (hmx >> 20) - 1023;
+#endif
   ex = max(-1000, min(1000, ex));
   const double s = __hiloint2double((1023 - ex) << 20, 0);
   t.a *= s; t.b *= s; t.c *= s; t.d *= s; t.e *= s; t.f *= s; t.g *= s;
@@ -195,16 +216,22 @@ __device__ __forceinline__ double ld_nc_now(const double* p) {
   return v;
 }
 
-// 1/sqrt(u): MUFU.RSQ64H seed (~2^-22) + two Newton steps (relative error ~1e-16; not correctly rounded, which the
+// 1/sqrt(u): MUFU.RSQ64H seed (~2^-22) + one third-order step (relative error ~1e-16; not correctly rounded, which the
 // 1e-10 parity bar does not need).  u <= 0 or NaN gives NaN/inf and is reported through the status word.
 __device__ __forceinline__ double fast_rsqrt(double u) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+#ifdef TG_RSQRT_NEWTON2
   const double hu = 0.5 * u;
   double e = fma(-hu, y * y, 0.5);
   y = fma(y, e, y);
   e = fma(-hu, y * y, 0.5);
   y = fma(y, e, y);
+#else
+  // one third-order step: with eps = 1 - u y^2 (|eps| ~ 2^-22), u^-1/2 = y (1 + eps/2 + 3 eps^2/8) + O(eps^3)
+  const double eps = fma(-u, y * y, 1.0);
+  y = fma(y, eps * fma(0.375, eps, 0.5), y);
+#endif
   return y;
 }
 
@@ -240,6 +267,9 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
                "r"(bytes)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -314,8 +344,11 @@ __device__ __forceinline__ uint4 normal_block(unsigned long long sw, uint2 key, 
 template <int G>
 __device__ __forceinline__ void philox_group(uint4 (&ctr)[G], uint2 key) {
   const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#ifndef TG_PHILOX_R
+#define TG_PHILOX_R 10                    // (experiment knob; anything but 10 leaves the Philox4x32-10 stream)
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < TG_PHILOX_R; ++r) {
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       const unsigned int hi0 = __umulhi(M0, ctr[i].x), lo0 = M0 * ctr[i].x;
@@ -394,6 +427,49 @@ __device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 ke
   return z;
 }
 
+// ---------------------------------------------------------------------------------------------- fp32-assisted normals
+// Default generator (TG_NORMALS_F32; 0.607 -> 0.522 ms per C3 draw against the all-fp64 pair generator above,
+// profiles/r02_tridiag_f32_normals.txt): FOUR normals per Philox4x32-10 block, Box-Muller with the transcendental parts on the special-
+// function unit in fp32 (lg2 / sqrt / sin / cos.approx, absolute error ~2^-21 each), the product r * (cos, sin) formed
+// in fp64 from the exactly converted factors.  The distribution differs from N(0,1) by ~1e-7 in Kolmogorov distance
+// (what curand_normal gives), invisible to any run shorter than ~1e13 draws per element, in exchange for ~45 of the
+// 68 instructions per element the fp64 generator above costs.  Stream layout: the thread's TG_K consecutive elements
+// (a "group") take blocks group * TG_F32_BLOCKS + k; words (x, y) of a block make elements 4k, 4k+1 of the group and
+// (z, w) elements 4k+2, 4k+3 -- a fixed function of the element index, independent of tiling and sharding.
+// A pair whose radius word is below 2^12 (probability 2^-20) is redone in fp64 with 32 more bits below it, so the
+// tail of the radius is exact beyond 6 sigma as well.
+constexpr int TG_F32_BLOCKS = (TG_PAIRS + 1) / 2;
+__device__ __forceinline__ bool normal_pair_f32(unsigned int w1, unsigned int w2, double& z0, double& z1) {
+  const unsigned int fb = __float_as_uint(__uint2float_rz(w1));                       // top 24 bits of w1, exactly
+  const float mant = __uint_as_float((fb & 0x007FFFFFu) | 0x3F800000u);               // [1, 2)
+  const float jp1 = __uint_as_float(0x4B000000u | (159u - (fb >> 23))) - 8388608.0f;  // 1 + leading zeros of w1
+  float lg, r, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(mant));
+  const float e2 = (jp1 - lg) * 1.38629436111989f;                                    // -2 ln U, U = mant 2^-(j+1)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e2));
+  const float th = (float)(int)w2 * 1.4629180792671596e-9f;                           // [-pi, pi]: 2 pi 2^-32
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(th));
+  const double rd = (double)r;
+  z0 = rd * (double)cs;
+  z1 = rd * (double)sn;
+  return w1 >= (1u << 12);
+}
+__device__ __noinline__ double2 normal_pair_f32_slow(unsigned long long sw, uint2 key, unsigned int gchain,
+                                                     unsigned int site, unsigned long long block, int half) {
+  const uint4 b = normal_block(sw, key, gchain, site, block);
+  const uint4 b2 = normal_block(sw, make_uint2(key.x ^ 0x5A1C0DE5u, key.y + 1u), gchain, site, block);
+  const unsigned int w1 = half ? b.z : b.x, w2 = half ? b.w : b.y;
+  const unsigned long long r = ((unsigned long long)w1 << 32) | (half ? b2.z : b2.x);
+  const int j = __clzll((long long)r);
+  const unsigned long long sh = (j >= 63) ? 0ull : (r << (j + 1));
+  const unsigned long long mb = sh >> 12;
+  const double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mb));
+  double2 z;
+  normal_from((double)(j + 1), mm, (int)(mb >> 45), make_uint4(0u, 0u, half ? b2.w : b2.y, w2), z.x, z.y);
+  return z;
+}
+
 // ---------------------------------------------------------------------------------------------- ziggurat normals
 // Alternative generator of the solve kernel (-DTG_ZIGGURAT; the Box-Muller pair above is the default because it
 // MEASURED faster, profiles/r02_tridiag_ziggurat_variants.txt: 0.605 ms per draw against 0.69 ms (256 layers, serial
@@ -444,148 +520,28 @@ __device__ __noinline__ double zig_slow(unsigned long long sw, uint2 key, unsign
   }
 }
 
-// ---------------------------------------------------------------------------------------------- aggregate kernel
-// G chains per CTA (G x TG_NT threads): the tile of the shared P is staged ONCE for the G chains, which halves (G = 2)
-// or quarters (G = 4) the shared memory per resident warp -- this kernel is a load -> compute -> store pipeline whose
-// only latency hiding is the number of CTAs resident next to each other.  GENERAL (weights / prior mean) keeps G = 1.
-template <bool GENERAL, int G>
-__global__ void __launch_bounds__(TG_NT* G) tg_aggregate_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L, int n_groups) {
-  static_assert(!GENERAL || G == 1, "GENERAL aggregate kernel stages per-chain arrays for one chain only");
-  extern __shared__ __align__(128) double sm[];
-  __shared__ double s_tot[G][TG_NW][7];
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
-  double* spe = sm + 4;
-  double* spd = spe + TG_TILE;
-  double* sy0 = spd + TG_TILE;     // G tiles of y, one per chain of the group
-  double* sw = sy0 + TG_TILE;      // GENERAL only
-  double* sh = sw + TG_TILE;       // GENERAL only
-  const int sub = threadIdx.x / TG_NT;            // which chain of the group
-  const int tid = threadIdx.x % TG_NT, lane = tid & 31, warp = tid >> 5;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  const int C = a.n_chains;
-  const long long tile = blockIdx.x / n_groups;   // tile-major: the chains read the same tile of the shared P together
-  const int chain0 = (int)(blockIdx.x % n_groups) * G;
-  const int chain = chain0 + sub;
-  const bool live = chain < C;                    // ragged last group
-  const int cc = live ? chain : C - 1;
-  const long long n = a.n;
-  char* wsb = reinterpret_cast<char*>(ws);
-  const long long i_t = tile * TG_TILE;
-  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)cc * a.lambda.chain_stride] : 1.0;
-  const double tau = a.tau.ptr ? a.tau.ptr[(long long)cc * a.tau.chain_stride] : 1.0;
-  double* sy = sy0 + sub * TG_TILE;
-
-  if (threadIdx.x == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
-  bool bulk;
-  if (GENERAL) {
-    const double* yp = a.y.ptr + (long long)cc * a.y.chain_stride;
-    const Stage st[5] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
-                         {a.w.ptr ? a.w.ptr + (long long)cc * a.w.chain_stride : nullptr, n, 1.0, sw},
-                         {a.h.ptr ? a.h.ptr + (long long)cc * a.h.chain_stride : nullptr, n, 0.0, sh}};
-    bulk = stage_issue<5>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
-  } else {
-    Stage st[2 + G];
-    st[0] = Stage{a.pe, n - 1, 0.0, spe};
-    st[1] = Stage{a.pd, n, 1.0, spd};
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      st[2 + g] = Stage{a.y.ptr + (long long)min(chain0 + g, C - 1) * a.y.chain_stride, n, 0.0, sy0 + g * TG_TILE};
-    bulk = stage_issue<2 + G>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
-  }
-  stage_wait(bulk, bar);
-
-  // ---- thread aggregate over its 18 elements (no divisions)
-  const int j0 = tid * TG_K;
-  TM t = tm_identity();
-  {
-    double eprev = lam * spe[j0 - 1];
-#pragma unroll
-    for (int c = 0; c < TG_PAIRS; ++c) {
-      const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
-      const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
-      const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
-      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0);
-      if (GENERAL) {
-        w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
-        h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
-      }
-      {
-        const double tw = GENERAL ? tau * w2.x : tau;
-        const double dd = fma(lam, pd2.x, tw);
-        const double bb = GENERAL ? fma(lam, h2.x, tw * y2.x) : tw * y2.x;
-        tm_step(t, dd, eprev * eprev, bb, eprev);
-        eprev = lam * pe2.x;
-      }
-      {
-        const double tw = GENERAL ? tau * w2.y : tau;
-        const double dd = fma(lam, pd2.y, tw);
-        const double bb = GENERAL ? fma(lam, h2.y, tw * y2.y) : tw * y2.y;
-        tm_step(t, dd, eprev * eprev, bb, eprev);
-        eprev = lam * pe2.y;
-      }
-      if (c == 2 || c == 5) tm_normalize(t);
-    }
-    tm_normalize(t);
-  }
-  // ---- CTA scan of the transfer matrices (thread order): inclusive within the warp, then across the 4 warps
-  TM inc = t;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const TM o = tm_shfl_up(inc, d);
-    if (lane >= d) inc = tm_mul(inc, o);
-    if (d == 4) tm_normalize(inc);
-  }
-  tm_normalize(inc);
-  if (lane == 31) {
-    s_tot[sub][warp][0] = inc.a; s_tot[sub][warp][1] = inc.b; s_tot[sub][warp][2] = inc.c; s_tot[sub][warp][3] = inc.d;
-    s_tot[sub][warp][4] = inc.e; s_tot[sub][warp][5] = inc.f; s_tot[sub][warp][6] = inc.g;
-  }
-  __syncthreads();
-  TM wex = tm_identity();   // composition of the warps below this one
-  for (int w = 0; w < warp; ++w) {
-    const TM ww{s_tot[sub][w][0], s_tot[sub][w][1], s_tot[sub][w][2], s_tot[sub][w][3], s_tot[sub][w][4], s_tot[sub][w][5], s_tot[sub][w][6]};
-    wex = tm_mul(ww, wex);
-  }
-  TM ex = tm_shfl_up(inc, 1);
-  if (lane == 0) ex = tm_identity();
-  ex = tm_mul(ex, wex);       // exclusive prefix of this thread inside the tile
-  tm_normalize(ex);
-  if (live) {
-    double* exg = reinterpret_cast<double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + tile) * 7 * TG_NT + tid;
-    exg[0 * TG_NT] = ex.a; exg[1 * TG_NT] = ex.b; exg[2 * TG_NT] = ex.c; exg[3 * TG_NT] = ex.d;
-    exg[4 * TG_NT] = ex.e; exg[5 * TG_NT] = ex.f; exg[6 * TG_NT] = ex.g;
-  }
-  if (live && tid == TG_NT - 1) {     // tile total = the last thread's inclusive prefix
-    TM tot = tm_mul(inc, wex);
-    tm_normalize(tot);
-    double* tt = reinterpret_cast<double*>(wsb + L.off_tt) + (tile * C + chain) * 8;
-    tt[0] = tot.a; tt[1] = tot.b; tt[2] = tot.c; tt[3] = tot.d; tt[4] = tot.e; tt[5] = tot.f; tt[6] = tot.g;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- tile scan kernel
-// One CTA per chain: exclusive scan of the tile totals -> (u, f) entering every tile.
-constexpr int TS_NT = 256;
-__global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layout L, int C) {
-  __shared__ double s_tot[TS_NT / 32][7];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chain = blockIdx.x;
+// ---------------------------------------------------------------------------------------------- tile scan
+// Exclusive scan of one chain's tile totals -> (u, f) entering every tile, by the NT threads of one CTA (a kernel of
+// its own, one CTA per chain: 11 us between the two big kernels.  Folding it into the aggregate kernel's tail -- the
+// CTA that finishes a chain's last tile scans it, fence + atomic hand-over -- MEASURED slower, 0.240 against 0.177 ms
+// for aggregate + scan: with tile-major work every chain finishes in the last wave, so nothing is hidden, and the
+// fence sits in every CTA; profiles/r02_tridiag_variants.txt).
+template <int NT>
+__device__ __forceinline__ void tilescan_chain(Workspace* ws, const Layout& L, int C, int chain, int tid,
+                                               double (&s_tot)[NT / 32][7]) {
+  const int lane = tid & 31, warp = tid >> 5;
   if (chain == 0 && tid == 0) ws->epoch = ws->epoch + 1;   // fresh flag values for the solve kernel that follows
   char* wsb = reinterpret_cast<char*>(ws);
   const double* tt = reinterpret_cast<const double*>(wsb + L.off_tt);
   double2* sin_ = reinterpret_cast<double2*>(wsb + L.off_sin);
   const long long T = L.n_tiles;
-  const long long per = (T + TS_NT - 1) / TS_NT;
+  const long long per = (T + NT - 1) / NT;
   TM agg = tm_identity();
   for (long long q = 0; q < per; ++q) {
     const long long t = tid * per + q;
     if (t < T) {
       const double* p = tt + (t * C + chain) * 8;
-      agg = tm_mul(TM{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}, agg);
+      agg = tm_mul(TM{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2), __ldcg(p + 3), __ldcg(p + 4), __ldcg(p + 5), __ldcg(p + 6)}, agg);
       tm_normalize(agg);
     }
   }
@@ -624,9 +580,230 @@ __global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layou
     if (t < T) {
       sin_[t * C + chain] = make_double2(u, f);
       const double* p = tt + (t * C + chain) * 8;
-      const double pp = fma(p[0], u, p[1]), qq = fma(p[2], u, p[3]), hh = fma(p[4], u, fma(p[6], f, p[5]));
+      const double pp = fma(__ldcg(p), u, __ldcg(p + 1)), qq = fma(__ldcg(p + 2), u, __ldcg(p + 3)),
+                   hh = fma(__ldcg(p + 4), u, fma(__ldcg(p + 6), f, __ldcg(p + 5)));
       u = pp / qq;
       f = hh / qq;
+    }
+  }
+}
+
+constexpr int TS_NT = 256;
+__global__ void __launch_bounds__(TS_NT) tg_tilescan_kernel(Workspace* ws, Layout L, int C) {
+  __shared__ double s_tot[TS_NT / 32][7];
+  tilescan_chain<TS_NT>(ws, L, C, (int)blockIdx.x, (int)threadIdx.x, s_tot);
+}
+
+// ---------------------------------------------------------------------------------------------- aggregate kernels
+// The compute part shared by the two aggregate kernels: thread aggregate over 18 staged elements, CTA scan, stores.
+template <bool GENERAL, int G>
+__device__ __forceinline__ void aggregate_compute(const omc_tridiag_nn_t& a, char* wsb, const Layout& L,
+                                                  double (&s_tot)[G][TG_NW][7], const double* spe, const double* spd,
+                                                  const double* sy, const double* sw, const double* sh, double lam,
+                                                  double tau, int sub, int tid, bool live, int chain, long long tile) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int C = a.n_chains;
+  // ---- thread aggregate over its 18 elements (no divisions)
+  const int j0 = tid * TG_K;
+  TM t = tm_identity();
+  {
+    double eprev = lam * spe[j0 - 1];
+#pragma unroll
+    for (int c = 0; c < TG_PAIRS; ++c) {
+      const double2 pd2 = *reinterpret_cast<const double2*>(spd + j0 + 2 * c);
+      const double2 pe2 = *reinterpret_cast<const double2*>(spe + j0 + 2 * c);
+      const double2 y2 = *reinterpret_cast<const double2*>(sy + j0 + 2 * c);
+      double2 w2 = make_double2(1.0, 1.0), h2 = make_double2(0.0, 0.0);
+      if (GENERAL) {
+        w2 = *reinterpret_cast<const double2*>(sw + j0 + 2 * c);
+        h2 = *reinterpret_cast<const double2*>(sh + j0 + 2 * c);
+      }
+      {
+        const double tw = GENERAL ? tau * w2.x : tau;
+        const double dd = fma(lam, pd2.x, tw);
+        const double bb = GENERAL ? fma(lam, h2.x, tw * y2.x) : tw * y2.x;
+        tm_step(t, dd, eprev * eprev, bb, eprev);
+        eprev = lam * pe2.x;
+      }
+      {
+        const double tw = GENERAL ? tau * w2.y : tau;
+        const double dd = fma(lam, pd2.y, tw);
+        const double bb = GENERAL ? fma(lam, h2.y, tw * y2.y) : tw * y2.y;
+        tm_step(t, dd, eprev * eprev, bb, eprev);
+        eprev = lam * pe2.y;
+      }
+      if (c == TG_AGG_NORM_A || c == TG_AGG_NORM_B) tm_normalize(t);
+    }
+    tm_normalize(t);
+  }
+  // ---- CTA scan of the transfer matrices (thread order): inclusive within the warp, then across the 4 warps
+  TM inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const TM o = tm_shfl_up(inc, d);
+    if (lane >= d) inc = tm_mul(inc, o);
+    if (TG_AGG_NORM_SCAN && d == 4) tm_normalize(inc);
+  }
+  tm_normalize(inc);
+  if (lane == 31) {
+    s_tot[sub][warp][0] = inc.a; s_tot[sub][warp][1] = inc.b; s_tot[sub][warp][2] = inc.c; s_tot[sub][warp][3] = inc.d;
+    s_tot[sub][warp][4] = inc.e; s_tot[sub][warp][5] = inc.f; s_tot[sub][warp][6] = inc.g;
+  }
+  __syncthreads();
+  TM wex = tm_identity();   // composition of the warps below this one
+  for (int w = 0; w < warp; ++w) {
+    const TM ww{s_tot[sub][w][0], s_tot[sub][w][1], s_tot[sub][w][2], s_tot[sub][w][3], s_tot[sub][w][4], s_tot[sub][w][5], s_tot[sub][w][6]};
+    wex = tm_mul(ww, wex);
+  }
+  TM ex = tm_shfl_up(inc, 1);
+  if (lane == 0) ex = tm_identity();
+  ex = tm_mul(ex, wex);       // exclusive prefix of this thread inside the tile
+  tm_normalize(ex);
+  if (live) {
+    double* exg = reinterpret_cast<double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + tile) * 7 * TG_NT + tid;
+    exg[0 * TG_NT] = ex.a; exg[1 * TG_NT] = ex.b; exg[2 * TG_NT] = ex.c; exg[3 * TG_NT] = ex.d;
+    exg[4 * TG_NT] = ex.e; exg[5 * TG_NT] = ex.f; exg[6 * TG_NT] = ex.g;
+  }
+  if (live && tid == TG_NT - 1) {     // tile total = the last thread's inclusive prefix
+    TM tot = tm_mul(inc, wex);
+    tm_normalize(tot);
+    double* tt = reinterpret_cast<double*>(wsb + L.off_tt) + (tile * C + chain) * 8;
+    tt[0] = tot.a; tt[1] = tot.b; tt[2] = tot.c; tt[3] = tot.d; tt[4] = tot.e; tt[5] = tot.f; tt[6] = tot.g;
+  }
+}
+
+// G chains per CTA (G x TG_NT threads): the tile of the shared P is staged ONCE for the G chains, which halves (G = 2)
+// or quarters (G = 4) the shared memory per resident warp -- this kernel is a load -> compute -> store pipeline whose
+// only latency hiding is the number of CTAs resident next to each other.  GENERAL (weights / prior mean) keeps G = 1.
+template <bool GENERAL, int G>
+__global__ void __launch_bounds__(TG_NT* G) tg_aggregate_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L, int n_groups) {
+  static_assert(!GENERAL || G == 1, "GENERAL aggregate kernel stages per-chain arrays for one chain only");
+  extern __shared__ __align__(128) double sm[];
+  __shared__ double s_tot[G][TG_NW][7];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);
+  double* spe = sm + 4;
+  double* spd = spe + TG_TILE;
+  double* sy0 = spd + TG_TILE;     // G tiles of y, one per chain of the group
+  double* sw = sy0 + TG_TILE;      // GENERAL only
+  double* sh = sw + TG_TILE;       // GENERAL only
+  const int sub = threadIdx.x / TG_NT;            // which chain of the group
+  const int tid = threadIdx.x % TG_NT;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int C = a.n_chains;
+  const long long tile = blockIdx.x / n_groups;   // tile-major: the chains read the same tile of the shared P together
+  const int chain0 = (int)(blockIdx.x % n_groups) * G;
+  const int chain = chain0 + sub;
+  const bool live = chain < C;                    // ragged last group
+  const int cc = live ? chain : C - 1;
+  const long long n = a.n;
+  char* wsb = reinterpret_cast<char*>(ws);
+  const long long i_t = tile * TG_TILE;
+  const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)cc * a.lambda.chain_stride] : 1.0;
+  const double tau = a.tau.ptr ? a.tau.ptr[(long long)cc * a.tau.chain_stride] : 1.0;
+  double* sy = sy0 + sub * TG_TILE;
+
+  if (threadIdx.x == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+  bool bulk;
+  if (GENERAL) {
+    const double* yp = a.y.ptr + (long long)cc * a.y.chain_stride;
+    const Stage st[5] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}, {yp, n, 0.0, sy},
+                         {a.w.ptr ? a.w.ptr + (long long)cc * a.w.chain_stride : nullptr, n, 1.0, sw},
+                         {a.h.ptr ? a.h.ptr + (long long)cc * a.h.chain_stride : nullptr, n, 0.0, sh}};
+    bulk = stage_issue<5>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
+  } else {
+    Stage st[2 + G];
+    st[0] = Stage{a.pe, n - 1, 0.0, spe};
+    st[1] = Stage{a.pd, n, 1.0, spd};
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      st[2 + g] = Stage{a.y.ptr + (long long)min(chain0 + g, C - 1) * a.y.chain_stride, n, 0.0, sy0 + g * TG_TILE};
+    bulk = stage_issue<2 + G>(st, i_t, n, bar, threadIdx.x, TG_NT * G);
+  }
+  stage_wait(bulk, bar);
+
+  aggregate_compute<GENERAL, G>(a, wsb, L, s_tot, spe, spd, sy, sw, sh, lam, tau, sub, tid, live, chain, tile);
+}
+
+// Persistent, double-buffered form of the lean aggregate kernel (no weights / prior mean): two CTAs per SM, each
+// walking a contiguous run of (tile, chain group) items in tile-major order.  The y tiles of item k+1 stream into the
+// other stage while item k is computed, and the shared P tile is re-staged only when the run crosses into the next
+// tile -- the one-shot kernel above is load -> compute -> store per CTA with nothing in flight during the compute
+// phase (ncu: a third of its stall samples sat on the tile's mbarrier, profiles/r02_ncu_tridiag_f32.txt).
+template <int G>
+__global__ void __launch_bounds__(TG_NT* G, 2)
+tg_aggregate_pipe_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L, int n_groups, long long n_items) {
+  extern __shared__ __align__(128) double sm[];
+  __shared__ double s_tot[G][TG_NW][7];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm);   // [0] P tile, [1], [2] the two y stages
+  double* spe = sm + 4;                                                    // (sm[3] is pe[-1])
+  double* spd = spe + TG_TILE;
+  double* sy0 = spd + TG_TILE;                                             // [2 stages][G chains][TG_TILE]
+  const int sub = threadIdx.x / TG_NT;
+  const int tid = threadIdx.x % TG_NT;
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init(bars + 2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int C = a.n_chains;
+  const long long n = a.n;
+  char* wsb = reinterpret_cast<char*>(ws);
+  const long long it0 = (long long)blockIdx.x * n_items / gridDim.x, it1 = (long long)(blockIdx.x + 1) * n_items / gridDim.x;
+  if (it0 >= it1) return;
+
+  auto issue_p = [&](long long tile) -> bool {
+    const long long i_t = tile * TG_TILE;
+    if (threadIdx.x == 0) spe[-1] = (a.pe && i_t > 0 && i_t - 1 < n - 1) ? __ldg(a.pe + i_t - 1) : 0.0;
+    const Stage st[2] = {{a.pe, n - 1, 0.0, spe}, {a.pd, n, 1.0, spd}};
+    return stage_issue<2>(st, i_t, n, bars, threadIdx.x, TG_NT * G);
+  };
+  auto issue_y = [&](long long item, int stage) -> bool {
+    const long long i_t = (item / n_groups) * TG_TILE;
+    const int chain0 = (int)(item % n_groups) * G;
+    Stage st[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      st[g] = Stage{a.y.ptr + (long long)min(chain0 + g, C - 1) * a.y.chain_stride, n, 0.0, sy0 + (stage * G + g) * TG_TILE};
+    return stage_issue<G>(st, i_t, n, bars + 1 + stage, threadIdx.x, TG_NT * G);
+  };
+
+  long long cur_tile = it0 / n_groups;
+  unsigned ph_p = 0, ph_y0 = 0, ph_y1 = 0;      // parities of the three barriers
+  bool p_bulk = issue_p(cur_tile), p_pending = true;
+  bool y_bulk[2];
+  y_bulk[0] = issue_y(it0, 0);
+  y_bulk[1] = false;
+  int stage = 0;
+  for (long long item = it0; item < it1; ++item, stage ^= 1) {
+    if (item + 1 < it1) y_bulk[stage ^ 1] = issue_y(item + 1, stage ^ 1);   // that stage was released by the barrier below
+    if (p_pending) {
+      if (p_bulk) { mbar_wait(bars, ph_p); ph_p ^= 1u; }
+      p_pending = false;
+    }
+    if (y_bulk[stage]) {
+      if (stage == 0) { mbar_wait(bars + 1, ph_y0); ph_y0 ^= 1u; }
+      else { mbar_wait(bars + 2, ph_y1); ph_y1 ^= 1u; }
+    }
+    __syncthreads();                            // plain-load fills (ragged last tile, odd alignments) visible
+    const long long tile = item / n_groups;
+    const int chain = (int)(item % n_groups) * G + sub;
+    const bool live = chain < C;
+    const int cc = live ? chain : C - 1;
+    const double lam = a.lambda.ptr ? a.lambda.ptr[(long long)cc * a.lambda.chain_stride] : 1.0;
+    const double tau = a.tau.ptr ? a.tau.ptr[(long long)cc * a.tau.chain_stride] : 1.0;
+    const double* sy = sy0 + (stage * G + sub) * TG_TILE;
+    aggregate_compute<false, G>(a, wsb, L, s_tot, spe, spd, sy, nullptr, nullptr, lam, tau, sub, tid, live, chain, tile);
+    __syncthreads();                            // everybody is done with this stage, the P tile and s_tot
+    if (item + 1 < it1 && (item + 1) / n_groups != cur_tile) {
+      cur_tile = (item + 1) / n_groups;
+      p_bulk = issue_p(cur_tile);
+      p_pending = true;
     }
   }
 }
@@ -717,6 +894,14 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
                          {zp, n, 0.0, inject ? sz : nullptr}};
     bulk = stage_issue<7, TG_STILE>(st, i_t, n, bar, tid, TG_SNT);
   }
+  if (TG_PREFETCH_AHEAD > 0 && tid == 32 % TG_SNT) {   // pull the y tile of a CTA that starts later into L2
+    const long long w2 = work + TG_PREFETCH_AHEAD;
+    if (w2 < (long long)gridDim.x) {
+      const long long i2 = (T - 1 - w2 / C) * TG_STILE;
+      const double* p2 = a.y.ptr + (w2 % C) * a.y.chain_stride + i2;
+      if (i2 + TG_STILE < n && al16(p2)) bulk_prefetch_l2(p2, TG_STILE * 8);
+    }
+  }
   // ---- loads of the thread prefix / tile input / scalars go out now; their latency hides under the normals
   const long long atile = tile / TG_SUB;     // the aggregate tile this solve tile is a slice of
   const double* exg = reinterpret_cast<const double*>(wsb + L.off_ex) + ((long long)chain * L.n_tiles + atile) * 7 * TG_NT +
@@ -744,6 +929,33 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
     const unsigned int gchain = a.rng.chain_offset + (unsigned int)chain;
     const unsigned long long pair0 = (unsigned long long)(i0 >> 1);
     unsigned int redo = 0;
+#ifdef TG_NORMALS_F32
+    const unsigned long long block0 = (unsigned long long)(i0 / TG_K) * TG_F32_BLOCKS;
+#ifndef TG_F32_GROUP
+#define TG_F32_GROUP 3
+#endif
+#pragma unroll
+    for (int k0 = 0; k0 < TG_F32_BLOCKS; k0 += TG_F32_GROUP) {
+      uint4 b[TG_F32_GROUP];
+#pragma unroll
+      for (int i = 0; i < TG_F32_GROUP; ++i) b[i] = normal_counter(sweep, gchain, a.rng.site, block0 + k0 + i);
+      philox_group<TG_F32_GROUP>(b, key);
+#pragma unroll
+      for (int i = 0; i < TG_F32_GROUP; ++i) {
+        const int k = k0 + i;
+        if (2 * k < TG_PAIRS && !normal_pair_f32(b[i].x, b[i].y, g[4 * k], g[4 * k + 1])) redo |= 1u << (2 * k);
+        if (2 * k + 1 < TG_PAIRS && !normal_pair_f32(b[i].z, b[i].w, g[4 * k + 2], g[4 * k + 3])) redo |= 1u << (2 * k + 1);
+      }
+    }
+    while (redo) {   // probability 2^-20 per pair
+      const int c = __ffs(redo) - 1;
+      redo &= redo - 1;
+      const double2 z = normal_pair_f32_slow(sweep, key, gchain, a.rng.site, block0 + (c >> 1), c & 1);
+#pragma unroll
+      for (int cc = 0; cc < TG_PAIRS; ++cc)
+        if (cc == c) { g[2 * cc] = z.x; g[2 * cc + 1] = z.y; }
+    }
+#else
 #pragma unroll
     for (int c0 = 0; c0 < TG_PAIRS; c0 += TG_RNG_GROUP) {
       uint4 b[TG_RNG_GROUP];
@@ -821,6 +1033,7 @@ tg_solve_kernel(omc_tridiag_nn_t a, Workspace* ws, Layout L) {
       }
     }
 #endif
+#endif   // TG_NORMALS_F32
   } else {
 #pragma unroll
     for (int k = 0; k < TG_K; ++k) g[k] = 0.0;
@@ -1187,6 +1400,26 @@ int launch_aggregate(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, 
   OMC_LAUNCH_CHECK();
   return 0;
 }
+#ifndef TG_AGG_PIPE
+#define TG_AGG_PIPE 0                     // lean aggregate pass: persistent double-buffered kernel (0: one CTA per item)
+#endif
+template <int G>
+int launch_aggregate_pipe(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, cudaStream_t st) {
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    OMC_CHECK_CUDA(cudaGetDevice(&dev));
+    OMC_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int smem = (4 + (2 + 2 * G) * TG_TILE) * 8;
+  const int n_groups = (a.n_chains + G - 1) / G;
+  const long long n_items = L.n_tiles * n_groups;
+  const unsigned int grid = (unsigned int)std::min<long long>(n_items, 2ll * n_sm);
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(tg_aggregate_pipe_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tg_aggregate_pipe_kernel<G><<<grid, TG_NT * G, smem, st>>>(a, ws, L, n_groups, n_items);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
 template <bool GENERAL, bool DEBUG>
 int launch_solve(const omc_tridiag_nn_t& a, Workspace* ws, const Layout& L, unsigned grid, cudaStream_t st) {
   const int smem = solve_smem_doubles(GENERAL, DEBUG) * 8;
@@ -1221,6 +1454,7 @@ int omc_tridiag_workspace_init(void* workspace, int n_chains, long long n, void*
 }
 
 int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
+  if (a) OMC_REQUIRE_SITE(a->rng, "omc_tridiag_nn_draw");
   if (int rc = check_args(a, "omc_tridiag_nn_draw")) return rc;
   OMC_REQUIRE(a->y.ptr, "omc_tridiag_nn_draw: y missing");
   const Layout L = make_layout(a->n_chains, a->n);
@@ -1233,6 +1467,7 @@ int omc_tridiag_nn_draw(const omc_tridiag_nn_t* a, void* stream) {
   {
     int rc;
     if (general) rc = launch_aggregate<true, 1>(*a, ws, L, st);
+    else if (TG_AGG_PIPE && a->n_chains >= TG_AGG_G) rc = launch_aggregate_pipe<TG_AGG_G>(*a, ws, L, st);
     else if (a->n_chains >= TG_AGG_G) rc = launch_aggregate<false, TG_AGG_G>(*a, ws, L, st);
     else rc = launch_aggregate<false, 1>(*a, ws, L, st);
     if (rc) return rc;

@@ -135,6 +135,8 @@ def vec(t, per_chain_elems=None) -> Vec:
 
 
 def rng(seed=0, sweep=None, chain_offset=0, site=0) -> Rng:
+    if not 0 <= int(site) < 4096:
+        raise ValueError(f"rng site {site}: the Philox counter gives a site 12 bits (4096 samplers per plan)")
     return Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, sweep.data_ptr() if sweep is not None else None, int(chain_offset),
                int(site))
 

@@ -41,7 +41,7 @@ class LazyHostArray:
 
 
 STREAM_STORE_BYTES = 256 << 20  # device stores above this are streamed to the host during the run (stream_store=None)
-RING_BYTES = 2 << 30           # budget of the device ring of a streamed store (at least 2 slabs)
+RING_BYTES = 1 << 30           # budget of the device ring of a streamed store (at least 2 slabs; the drain, not the ring, is the limit)
 
 
 @dataclass
@@ -85,9 +85,21 @@ class MCMC:
             elif term.ndim < 2:
                 term = np.atleast_2d(term).T
             self.state[key] = term
+        # Start values missing from the state are prior draws (mcmc.py:78-80) -- one PER CHAIN, column = global chain id,
+        # so that chains start over-dispersed (what split-R-hat assumes) and a sharded run starts where the unsharded one
+        # does.  The host state keeps the first local chain's draw (shapes, later hierarchical draws); the per-chain
+        # values go to the device in _prepare.
+        self._chain_starts = {}
         for sampler in self.samplers:
             if sampler.param not in self.state:
-                self.state[sampler.param] = sampler.model[sampler.param].rvs(self.state)
+                dist = sampler.model[sampler.param]
+                if self.n_chains > 1:
+                    draws = np.asarray(dist.rvs(self.state, n=self.chain_offset + self.n_chains), dtype=np.float64)
+                    draws = draws[:, self.chain_offset:]
+                    self.state[sampler.param] = draws[:, :1].copy()
+                    self._chain_starts[sampler.param] = np.ascontiguousarray(draws.T)[:, :, None]
+                else:
+                    self.state[sampler.param] = dist.rvs(self.state)
         self._prepared = None
         self.status = None
         self.timing = {}
@@ -148,7 +160,7 @@ class MCMC:
                 s.model = m
 
     def _prepare(self, dev, C, sampled, warm_up, wait):
-        st = engine.DeviceState(C, dev, self.state, per_chain_names=sampled)
+        st = engine.DeviceState(C, dev, {**self.state, **getattr(self, "_chain_starts", {})}, per_chain_names=sampled)
         self.stream = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
             plan = engine.Plan(st, seed=self.seed, chain_offset=self.chain_offset)
@@ -520,6 +532,7 @@ class MCMC:
             sub = MCMC(st, self.samplers, self.model, n_burn=self.n_burn, n_iter=self.n_iter, n_thin=self.n_thin,
                        n_chains=hi - lo, seed=self.seed, device=self.device, chain_offset=self.chain_offset + lo,
                        upload_blocks=1, stream_store=False)   # blocks sweep asynchronously: their stores stay resident
+            sub._chain_starts = {k: v[lo:hi] for k, v in getattr(self, "_chain_starts", {}).items()}
             # every block keeps the eager warm-up pass in front of its captures: skipping it for the later blocks
             # bought nothing (the host waits behind the next block's transfer anyway) and a capture can be
             # invalidated by the first-time allocations of a block with a different chain count

@@ -149,6 +149,21 @@ def test_distribution_rvs_and_missing_initial_values():
     assert M.state["beta"].shape == (p, 1) and M.state["tau"].shape == (1, 1) and M.state["tau"][0, 0] > 0
     M.run_mcmc()
     assert np.all(np.abs(M.store["beta"].mean(axis=1) - [1.0, -1.0, 0.5]) < 0.1)
+    # several chains: one prior draw PER CHAIN (column = global chain id), so a shard starts where the whole run does
+    def fresh(**kw):
+        hostcalls.set_seed(0)
+        devdist._rvs_calls, gmrf._calls = 0, 3000
+        return MCMC(dict(state), [NormalNormal("beta", mdl), NormalGamma("tau", mdl)], model=mdl, n_burn=0, n_iter=3, **kw)
+    M4 = fresh(n_chains=4)
+    b0 = M4._chain_starts["beta"]
+    assert b0.shape == (4, p, 1) and len({tuple(np.round(v.ravel(), 12)) for v in b0}) == 4
+    assert np.array_equal(M4.state["beta"], b0[0])
+    M2 = fresh(n_chains=2, chain_offset=2)
+    np.testing.assert_array_equal(M2._chain_starts["beta"], b0[2:])
+    np.testing.assert_array_equal(M2._chain_starts["tau"], M4._chain_starts["tau"][2:])
+    M4.run_mcmc()
+    M2.run_mcmc()
+    np.testing.assert_array_equal(M2.store["beta"], M4.store["beta"][2:])
 
 
 @pytest.mark.parametrize("n", [3, 64, 130, 300])
