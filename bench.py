@@ -402,9 +402,10 @@ def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None, key
     common = {"peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": traffic,
               "traffic_source": traffic_src, "kernel_ms": op_ms, "share_of_step": op_ms / step_ms}
     if wl["kind"] == "regression":
-        # per sweep and chain the draw reads the record G | g | rss | cnt (8 (p^2 + p + 2) bytes; G a second time for
-        # d'G d, from L2) and the centre (8 (2p + 2)), writes beta (8 p) and rss: no pass over X
-        byts = C * 8 * (p * p + p + 2 + 2 * p + 2 + p + 1)
+        # per sweep and chain the draw needs the record G | g | rss | cnt -- G symmetric: p (p + 1) / 2 unique entries (the
+        # kernel reads the lower block triangle, and G a second time for d'G d from L2) -- and the centre (8 (2p + 2)),
+        # and writes beta (8 p) and rss: no pass over X
+        byts = C * 8 * (p * (p + 1) // 2 + p + 2 + 2 * p + 2 + p + 1)
         flops = C * (p ** 3 / 3.0 + 2.0 * p * p + 2.0 * p * p + 2.0 * p * p)   # Cholesky, 3 triangular solves, d'G d
         roof = {"bound": "hbm", "kernel": "nn draw kernel (omc_nn_dense_draw: Q = lam P0 + tau G, Cholesky, posterior "
                                           "mean, draw, re-centred rss): the whole data-dependent work of a sweep",

@@ -6,7 +6,7 @@
 // The lower triangle of Q lives in the warp as 8 x 8 tiles in the accumulator layout of mma.sync.m8n8k4.f64: lane
 // (g = lane / 4, kq = lane % 4) holds elements [g][2kq], [g][2kq+1] of every tile -- 36 tiles = 72 doubles per lane at
 // p = 64.  No shared memory, no CTA barrier: the CTA-wide kernels of the first round spent 40-55 % of a chain's life
-// at barriers around their serial sections (profiles/r02_ncu_blocked64_lines.txt) with 4-5 chains resident per SM;
+// at barriers around their serial sections (profiles/r02_ncu_blocked64.txt) with 4-5 chains resident per SM;
 // here 8 chains are resident per SM and every one of them always has work to issue.
 //
 // Right-looking by block columns k (tools/gen/warp_chol_model.py is the lane-level numpy model of this file):
@@ -23,7 +23,7 @@
 // warp's NEXT chain is on its way into that warp's shared-memory slab (1-D bulk copies through the TMA engine, one per
 // row of the lower block triangle, completion on a per-warp mbarrier) while the current chain is factorised out of
 // registers: a third of a chain's life was the HBM latency of its 36 tile loads with nothing to overlap it
-// (profiles/r02_ncu_warp64_v1_lines.txt).
+// (profiles/r02_ncu_warp64_v1.txt, r02_ncu_warp64_lines.txt for the shipped kernel).
 #include "../../include/omc.h"
 #include "omc_common.cuh"
 #include "omc_internal.h"

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(RJ_NT) rj_kernel(omc_rj_t a, int ld, int cls) 
   rss_p = omc_block_sum(rss_p, s_red);
   // ---- prior terms of both states, one component per thread (they were a serial loop of thread 0 with two lgamma /
   //      log evaluations per component while the other 127 threads waited at the barrier below: 13 % of the stall
-  //      samples of the step, profiles/r02_ncu_rj_lines.txt)
+  //      samples of the step in profiles/r02_ncu_rj_v1.txt; r02_ncu_rj_lines.txt is the kernel as shipped)
   const double mu_b = vat(a.mu_beta, chain, 0.0);
   double ss_c = 0.0, ss_p = 0.0, lw_c = 0.0, lw_p = 0.0;
   for (int j = tid; j < m; j += RJ_NT) {

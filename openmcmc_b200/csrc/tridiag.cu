@@ -429,7 +429,7 @@ __device__ __noinline__ double2 normal_pair_slow(unsigned long long sw, uint2 ke
 
 // ---------------------------------------------------------------------------------------------- fp32-assisted normals
 // Default generator (TG_NORMALS_F32; 0.607 -> 0.522 ms per C3 draw against the all-fp64 pair generator above,
-// profiles/r02_tridiag_f32_normals.txt): FOUR normals per Philox4x32-10 block, Box-Muller with the transcendental parts on the special-
+// profiles/r02_tridiag_variants.txt): FOUR normals per Philox4x32-10 block, Box-Muller with the transcendental parts on the special-
 // function unit in fp32 (lg2 / sqrt / sin / cos.approx, absolute error ~2^-21 each), the product r * (cos, sin) formed
 // in fp64 from the exactly converted factors.  The distribution differs from N(0,1) by ~1e-7 in Kolmogorov distance
 // (what curand_normal gives), invisible to any run shorter than ~1e13 draws per element, in exchange for ~45 of the
