@@ -414,6 +414,14 @@ def roofline_of(wl, C, n, p, op_ms, step_ms, peaks, fp64_peak, syrk_ms=None, key
                          "frac": flops / sec / 1e12 / fp64_peak if fp64_peak else None,
                          "flops_per_chain": flops / C,
                          "peak_source": "cuBLAS DGEMM fp64 6144^3 measured in this run"}}
+        # SURVEY §8d quotes C2 on the REFERENCE algorithm's traffic -- one pass over (X, y) per chain-iteration,
+        # 8 n (p + 1) bytes.  Against that figure the sweep sits above the HBM roofline because it no longer reads X
+        # (re-centred statistics); `frac` above is the kernel's own bytes, this one is the contract's literal figure.
+        sv = C * 8.0 * n * (p + 1)
+        roof["survey_8d"] = {"bytes_per_chain_iteration": 8.0 * n * (p + 1), "achieved": sv / sec / 1e9,
+                             "frac": sv / sec / 1e9 / hbm_peak, "unit": "GB/s",
+                             "note": "reference-algorithm bytes (one pass over X, y per chain-iteration) / the draw "
+                                     "kernel's duration: > 1 because X left the steady-state sweep"}
         if syrk_ms:
             fl = C * (n * p * (p + 1) + 4 * n * p)   # SYRK + X'y + residual per chain
             tf = fl / (syrk_ms * 1e-3) / 1e12

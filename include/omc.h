@@ -332,6 +332,8 @@ int omc_linear_predictor(const omc_linear_predictor_t* args, void* stream);
  * n_mats matrices, each `n` diagonal entries (sum_log) or an n x n dense SPD matrix, n <= 64 (logdet_dense: 2*sum log diag chol).
  * ref: gmrf.py:339-342 */
 int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream);
+/* out[i] = log(x[i]): the log-response of a LogNormal whose response is data, ref: location_scale.py:296-303 */
+int omc_log_elements(const double* x, long long n, double* out, void* stream);
 int omc_logdet_dense(const double* P, int n_mats, int n, double* out, void* stream);
 
 /* ------------------------------------------------------------------ temporal GMRF: tridiagonal NormalNormal (C3)

@@ -277,6 +277,7 @@ PROTOTYPES = {
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_combine": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.POINTER(Vec), C.POINTER(Vec), C.c_void_p, C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "omc_log_elements": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_tridiag_workspace": (C.c_int, [C.c_int, C.c_longlong, C.POINTER(C.c_longlong)]),
     "omc_tridiag_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),

@@ -92,6 +92,12 @@ __global__ void __launch_bounds__(LP_THREADS) sum_log_kernel(const double* x, lo
   if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
 
+// out = log(x), element-wise (the log-response of a LogNormal whose response is data: location_scale.py:296-303)
+__global__ void __launch_bounds__(LP_THREADS) log_elements_kernel(const double* x, long long n, double* out) {
+  for (long long i = (long long)blockIdx.x * LP_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * LP_THREADS)
+    out[i] = log(x[i]);
+}
+
 // unblocked Cholesky of one small matrix per CTA (setup-time only)
 __global__ void __launch_bounds__(64) logdet_dense_kernel(const double* P, int n, double* out) {
   extern __shared__ double A[];
@@ -146,6 +152,13 @@ extern "C" {
 int omc_sum_log(const double* x, int n_mats, long long n, double* out, void* stream) {
   OMC_REQUIRE(x && out && n_mats >= 1 && n >= 0, "omc_sum_log: bad argument");
   sum_log_kernel<<<n_mats, LP_THREADS, 0, (cudaStream_t)stream>>>(x, n, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+int omc_log_elements(const double* x, long long n, double* out, void* stream) {
+  OMC_REQUIRE(x && out && n >= 1, "omc_log_elements: bad argument");
+  const long long blocks = (n + LP_THREADS - 1) / LP_THREADS;
+  log_elements_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), LP_THREADS, 0, (cudaStream_t)stream>>>(x, n, out);
   OMC_LAUNCH_CHECK();
   return 0;
 }

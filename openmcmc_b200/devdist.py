@@ -46,6 +46,10 @@ def build_terms(plan: "engine.Plan", host_state: dict, model, param: str):
     for dist in model.values():
         if param not in dist.param_list or isinstance(dist, NullDistribution):
             continue
+        if isinstance(dist, LogNormal) and dist.response != param:
+            # mean-parameter branch (location_scale.py:344-347, 401-404): the Normal of log(y); the Jacobian term
+            # -sum(log y) does not depend on theta
+            dist, _ = engine.lognormal_shim(plan, dist)
         if isinstance(dist, Poisson) and isinstance(dist.rate, Identity) and dist.rate.form == param:
             k = st[dist.response]
             if k.size != n_elem:
@@ -223,13 +227,18 @@ def grad_log_p_host(dist, state: dict, param: str, hessian_required: bool, metho
         for _, fn in plan.ops:
             fn()
         p = rl.p
-        torch.cuda.synchronize()
-        rec = rl.stats[0].cpu().numpy()
         tau = float(np.asarray(state[rl.scalar]).item()) if rl.scalar else 1.0
-        G = rec[: p * p].reshape(p, p)
-        beta = np.asarray(state[param], dtype=np.float64).reshape(p, 1)
-        grad = tau * (rec[p * p: p * p + p].reshape(p, 1) - G @ beta)
-        return (grad.reshape(shape), tau * G) if hessian_required else grad.reshape(shape)
+        rec = rl.stats[0]                                    # device record G | g | rss | cnt of the one chain
+        Gb = plan.new(1, p)                                  # G beta: the record's G as a p x p design (omc_linear_predictor)
+        K.linear_predictor(1, p, [(K.vec(rec[: p * p], 0), K.vec(st[param].data, 0), p)], Gb)
+        taus = torch.tensor([tau, -tau], dtype=torch.float64, device=rec.device)
+        out = plan.new(1, p + p * p)
+        K.combine(1, p, [K.vec(rec[p * p: p * p + p], 0), K.vec(Gb, 0)], [K.vec(taus[0:1], 0), K.vec(taus[1:2], 0)], out[:, :p])
+        K.combine(1, p * p, [K.vec(rec[: p * p], 0)], [K.vec(taus[0:1], 0)], out[:, p:])
+        torch.cuda.synchronize()
+        h = out.cpu().numpy().ravel()
+        grad = h[:p].reshape(shape)
+        return (grad, h[p:].reshape(p, p)) if hessian_required else grad
     plan.ops = []
     model, _ = build_terms(plan, state, Model([dist]), param)
     for _, fn in plan.ops:      # derived quantities the terms read (e.g. the data-only regression record)

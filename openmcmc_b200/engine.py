@@ -747,7 +747,34 @@ def logdet_of(plan: Plan, P: DevArray):
     return out
 
 
-def compile_log_post(plan: Plan, host_state, model, out):
+def lognormal_shim(plan: Plan, dist):
+    """A LogNormal whose response y is DATA, seen from its mean / precision parameters, is the Normal of log(y) with the
+    same mean and precision, minus the constant sum(log y) (location_scale.py:296-303; mean-parameter branch of the
+    gradient / Hessian :344-347, :401-404).  Returns (Normal on the derived state entry `__log[y]`, -sum(log y) per chain).
+    The log of the data is taken once, on the device, when the plan is built."""
+    from openmcmc_b200.distribution.location_scale import Normal
+
+    st = plan.state
+    if dist.response in st.per_chain_names:
+        raise PlanError(f"LogNormal '{dist.response}' is sampled and enters through its mean: not supported on the device")
+    shims = plan.__dict__.setdefault("_lognormal_shims", {})
+    if dist.response not in shims:
+        y = st[dist.response]
+        name = f"__log[{dist.response}]"
+        logy = torch.empty_like(y.data)
+        K.log_elements(y.data, logy)
+        st.put(name, logy)
+        m = st.n_chains if y.per_chain else 1
+        s = plan.new(m)
+        K.sum_log(y.data, y.size, s)
+        const = plan.new(st.n_chains)
+        K.combine(st.n_chains, 1, [K.vec(s, 1 if y.per_chain else None)], [K.vec(plan.new(1, fill=-1.0))], const)
+        shims[dist.response] = (name, const)
+    name, const = shims[dist.response]
+    return Normal(name, mean=dist.mean, precision=dist.precision), const
+
+
+def compile_log_post(plan: Plan, host_state, model, out, accumulate_first=False):
     """Emit kernels accumulating model.log_p(state) per chain into `out` [C].  ref: mcmc.py:108, model.py:57-70."""
     from openmcmc_b200.distribution.distribution import Categorical, Gamma, Poisson, Uniform
     from openmcmc_b200.distribution.location_scale import LogNormal, Normal, NullDistribution
@@ -755,13 +782,26 @@ def compile_log_post(plan: Plan, host_state, model, out):
 
     st = plan.state
     C = st.n_chains
-    first = True
+    first = not accumulate_first
     for dist in model.values():
         acc = 0 if first else 1
         if isinstance(dist, NullDistribution):
             continue
         transformed = isinstance(dist, Normal) and any((getattr(dist.mean, "transform", None) or {}).values())
-        if isinstance(dist, LogNormal) or transformed:
+        if (isinstance(dist, LogNormal) and not isinstance(dist.mean, Identity)
+                and dist.response not in st.per_chain_names):
+            # data response, structured mean: Normal of log(y) minus sum(log y)
+            from openmcmc_b200.model import Model
+
+            shim, const = lognormal_shim(plan, dist)
+            compile_log_post(plan, host_state, Model([shim]), out, accumulate_first=not first)
+            one = plan.new(1, fill=1.0)
+
+            def launch(const=const, one=one):
+                K.combine(C, 1, [K.vec(out, 1), K.vec(const, 1)], [K.vec(one), K.vec(one)], out)
+
+            plan.emit(launch, f"logp_lognormal_jacobian[{dist.response}]")
+        elif isinstance(dist, LogNormal) or transformed:
             # no dedicated kernel: the distribution as a one-term MH model of its response (LogNormal) or of the
             # transformed coefficient vector (Normal with a LinearCombinationWithTransform mean)
             from openmcmc_b200 import devdist

@@ -336,6 +336,10 @@ def sum_log(x, n, out):
     check(lib().omc_sum_log(_ptr(x), out.numel(), int(n), _ptr(out), stream_ptr()), "omc_sum_log")
 
 
+def log_elements(x, out):
+    check(lib().omc_log_elements(_ptr(x), x.numel(), _ptr(out), stream_ptr()), "omc_log_elements")
+
+
 def logdet_dense(P, n, out):
     """log|P| of out.numel() dense SPD matrices; above n = 64 through the blocked factorisation (omc_dense_factor)."""
     if n <= 64:

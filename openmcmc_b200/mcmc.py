@@ -160,7 +160,9 @@ class MCMC:
                 s.model = m
 
     def _prepare(self, dev, C, sampled, warm_up, wait):
-        st = engine.DeviceState(C, dev, {**self.state, **getattr(self, "_chain_starts", {})}, per_chain_names=sampled)
+        st = engine.DeviceState(C, dev, self.state, per_chain_names=sampled)
+        for name, arr in getattr(self, "_chain_starts", {}).items():   # per-chain prior draws of missing start values
+            st.put(name, arr, per_chain=True)
         self.stream = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
             plan = engine.Plan(st, seed=self.seed, chain_offset=self.chain_offset)

@@ -314,7 +314,7 @@ def lognormal_case(p, seed, n_iter, step, sampler="mmala", prior="dense"):
             "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
 
 
-def mmala_regression_case(n, p, seed, n_iter, step, transform=False, weighted=True):
+def mmala_regression_case(n, p, seed, n_iter, step, transform=False, weighted=True, lognormal=False):
     """SURVEY a4 / f4 in an MH sampler: beta enters the mean of y ~ N(X f(beta), (tau W)^-1) linearly (f = exp with
     LinearCombinationWithTransform), Normal prior on beta: the mean-parameter branch of Normal.grad_log_p
     (location_scale.py:234-250) with parameter.py:199-228 / 283-297; analytic in the reference."""
@@ -325,12 +325,14 @@ def mmala_regression_case(n, p, seed, n_iter, step, transform=False, weighted=Tr
     beta_true = 0.5 * rng.standard_normal((p, 1))
     f_true = np.exp(beta_true) if transform else beta_true
     y = X @ f_true + 0.5 * rng.standard_normal((n, 1))
+    if lognormal:      # round 2: LogNormal response, mean-parameter branch of LogNormal.grad_log_p (location_scale.py:344-347)
+        y = np.exp(0.3 * y)
     W = sparse.diags(rng.random(n) + 0.5, format="csc") if weighted else sparse.identity(n, format="csc")
     A = rng.standard_normal((p, p))
     P = A @ A.T / p + np.eye(p)
     mean = (LinearCombinationWithTransform(form={"beta": "X"}, transform={"beta": True}) if transform
             else LinearCombination(form={"beta": "X"}))
-    mdl = Model([Normal("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
+    mdl = Model([(LogNormal if lognormal else Normal)("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
                  Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam"))])
     state = {"y": y, "X": X, "beta": beta_true + 0.1 * rng.standard_normal((p, 1)), "W": W, "tau": 1.7,
              "mu": np.zeros((p, 1)), "P": P, "lam": 0.8}
@@ -343,7 +345,7 @@ def mmala_regression_case(n, p, seed, n_iter, step, transform=False, weighted=Tr
         smp = ManifoldMALA("beta", mdl, step=np.array([[step]]))
         M = _run_ref(state, [smp], mdl, n_iter)
     return {"X": X, "y": y, "beta0": state0["beta"], "w": np.asarray(W.diagonal()), "weighted": weighted, "tau": 1.7,
-            "P": P, "lam": 0.8, "transform": transform, "step": step, "grad0": g0, "hess0": np.asarray(H0), "logp0": lp0,
+            "P": P, "lam": 0.8, "transform": transform, "lognormal": lognormal, "step": step, "grad0": g0, "hess0": np.asarray(H0), "logp0": lp0,
             "z": s.stack("z"), "u": s.stack("u").ravel(), "store_beta": M.store["beta"],
             "store_log_post": M.store["log_post"],
             "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])}
@@ -799,7 +801,7 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2", "round2b"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2", "round2b", "round2c"]
     if "regression" not in which:
         cases = {}
     if "round2" in which:
@@ -819,6 +821,11 @@ def main():
             "multilik_n200_n150_p40": multilik_case(200, 150, 40, 32, 3, identity_term=False),
             "multilik_gmrfprior_n120_n80_p24": multilik_case(120, 80, 24, 33, 4, identity_term=True, gmrf_prior=True),
         })
+    if "round2c" in which:
+        # round 2: LogNormal response with a LinearCombination mean inside ManifoldMALA (mean-parameter branch)
+        cases.update({"mhreg_lognormal_mmala_n70_p5": mmala_regression_case(70, 5, 27, 10, 0.8, lognormal=True),
+                      "mhreg_lognormal_mmala_n150_p20_eye": mmala_regression_case(150, 20, 28, 5, 0.9, weighted=False,
+                                                                                  lognormal=True)})
     if "mh" in which:
         cases.update(mh_cases())
     if "mh_f4" in which:

@@ -300,13 +300,14 @@ def test_lognormal_logp_grad_hess_and_chain(name):
 
 
 def _mhreg_model_state(g):
-    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.distribution.location_scale import LogNormal, Normal
     from openmcmc_b200.model import Model
     from openmcmc_b200.parameter import LinearCombination, LinearCombinationWithTransform, ScaledMatrix
 
     mean = (LinearCombinationWithTransform(form={"beta": "X"}, transform={"beta": True}) if bool(g["transform"])
             else LinearCombination(form={"beta": "X"}))
-    mdl = Model([Normal("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
+    lik = LogNormal if ("lognormal" in g and bool(g["lognormal"])) else Normal
+    mdl = Model([lik("y", mean=mean, precision=ScaledMatrix(matrix="W", scalar="tau")),
                  Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam"))])
     n = g["y"].shape[0]
     W = sparse.diags(g["w"], format="csc") if bool(g["weighted"]) else sparse.identity(n, format="csc")
@@ -315,10 +316,13 @@ def _mhreg_model_state(g):
     return mdl, state
 
 
-@pytest.mark.parametrize("name", ["mhreg_mmala_n60_p6", "mhreg_mmala_n200_p30_eye", "mhreg_exp_mmala_n80_p5"])
+@pytest.mark.parametrize("name", ["mhreg_mmala_n60_p6", "mhreg_mmala_n200_p30_eye", "mhreg_exp_mmala_n80_p5",
+                                  "mhreg_lognormal_mmala_n70_p5", "mhreg_lognormal_mmala_n150_p20_eye"])
 def test_mmala_on_regression_coefficients(name):
     """Mean-parameter branch of Normal.grad_log_p inside ManifoldMALA (location_scale.py:234-250), also through the exp
-    transform of LinearCombinationWithTransform (parameter.py:232-297): evaluated from the data-only regression record."""
+    transform of LinearCombinationWithTransform (parameter.py:232-297): evaluated from the data-only regression record.
+    The LogNormal cases are the same branch of LogNormal.grad_log_p (location_scale.py:344-347, 401-404): the record is
+    built on log(y) and log_p carries the Jacobian -sum(log y)."""
     from openmcmc_b200.mcmc import MCMC
     from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA
 

@@ -143,6 +143,29 @@ def test_mh_regression_chain(name):
     assert n_acc == g["accept"][0]
 
 
+@pytest.mark.parametrize("name", ["mhreg_lognormal_mmala_n70_p5", "mhreg_lognormal_mmala_n150_p20_eye"])
+def test_mh_lognormal_regression_chain(name):
+    """LogNormal response with a linear mean, mean-parameter branch (location_scale.py:296-303, 344-347, 401-404): the
+    Normal-linear term on log(y); the Jacobian -sum(log y) only shifts log_p."""
+    g = _load(name)
+    logy = np.log(g["y"])
+    terms = [mh.Term("normal_linear", data=logy, X=g["X"], Q=g["tau"] * np.diag(g["w"]), transform=False),
+             mh.Term("normal_response", p1=np.zeros_like(g["beta0"]), Q=g["lam"] * g["P"])]
+    jac = -np.sum(logy)
+    g0, H0 = terms[0].grad_hess_analytic(g["beta0"])
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(terms[0].log_p(g["beta0"]) + jac, g["logp0"], rtol=1e-13)
+    theta = g["beta0"]
+    n_acc = 0
+    for it in range(g["store_beta"].shape[1]):
+        theta, info = mh.mmala_step(terms, theta, float(g["step"]), g["z"][it], g["u"][it], "analytic")
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(mh.log_p(terms, theta) + jac, g["store_log_post"][it, 0], rtol=1e-10)
+    assert n_acc == g["accept"][0]
+
+
 def test_truncnorm_grid():
     g = _load("truncnorm_grid")
     x = gmrf.truncated_normal_rv(g["mean"], g["scale"], g["lower"], g["upper"], g["u"])
