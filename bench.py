@@ -654,7 +654,7 @@ def c3_subrecord(ctx, args, peaks):
     M, ms, _ = value_leg(ctx, wl, "c3", C, n, steps, min(args.warmup, 5), thin)
     op = next(fn for label, fn in M._ops["sweep"] if label.startswith(wl["dominant"]))
     op_ms = time_op(ctx, M, op)
-    launches = M.launches_per_sweep() * steps + M._store_graph.num_kernels() * (steps // thin)
+    launches = M.launches_of(steps % thin if steps >= thin else 0, max(steps // thin, 1), thin)
     rec = {"workload": wl["name"], "value": C * ctx.world * steps / (ms * 1e-3), "unit": UNIT, "steps": steps,
            "ms_per_step": ms / steps, "n_thin": thin, "gpu_launches": launches,
            "roofline": roofline_of(wl, C, n, 0, op_ms, ms / steps, peaks, None, key="c3")} if ctx.rank == 0 else {}
@@ -685,8 +685,7 @@ def run_b200(args, wl, key):
     clocks.start()
     M, ms_max, (mdl, samplers, state) = value_leg(ctx, wl, key, C, n, args.steps, args.warmup, thin, clocks)
     n_iter = max(args.steps // thin, 1)
-    launches_per_sweep = M.launches_per_sweep()
-    store_launches = M._store_graph.num_kernels()
+    gpu_launches = M.launches_of(args.steps % thin if args.steps >= thin else 0, n_iter, thin)
     # dominant op alone: the very launch closure of the sweep plan
     op = next(fn for label, fn in M._ops["sweep"] if label.startswith(wl["dominant"]))
     op_ms = time_op(ctx, M, op)
@@ -770,7 +769,7 @@ def run_b200(args, wl, key):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_of(args, wl), "clocks": clk, "e2e": e2e,
-            "gpu_launches": launches_per_sweep * args.steps + store_launches * n_iter,
+            "gpu_launches": gpu_launches,
             "roofline": roof, "cpu_baseline": cpu_baseline, "ess": ess, "chains_failed": status_bad, "accept": accept,
         }
         line.update(extras)

@@ -47,6 +47,9 @@ const char* omc_last_error(void);
 int omc_device_init(int device);          /* cudaSetDevice + attribute cache; must precede everything else */
 int omc_device_sm_count(void);
 int omc_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
+/* both counters of a stored sweep (sweep counter, stored-iteration counter) in one launch */
+int omc_counter_add2(unsigned long long* c0, unsigned long long inc0, unsigned long long* c1, unsigned long long inc1,
+                     void* stream);
 
 /* ------------------------------------------------------------------ sweep execution (ref: mcmc.py:87-111)
  * A sweep is recorded once as a CUDA graph (capture between begin/end on `stream`, calling the op entry points

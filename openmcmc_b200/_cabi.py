@@ -240,6 +240,7 @@ PROTOTYPES = {
     "omc_device_init": (C.c_int, [C.c_int]),
     "omc_device_sm_count": (C.c_int, []),
     "omc_counter_add": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    "omc_counter_add2": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.c_void_p]),
     "omc_graph_capture_begin": (C.c_int, [C.c_void_p]),
     "omc_graph_capture_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "omc_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),

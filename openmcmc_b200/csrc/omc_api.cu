@@ -31,6 +31,11 @@ struct omc_graph {
 
 namespace {
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add2_kernel(unsigned long long* c0, unsigned long long inc0, unsigned long long* c1,
+                                    unsigned long long inc1) {
+  *c0 += inc0;
+  *c1 += inc1;
+}
 
 // RING = false: row `it` of a [max_iter, count] store (rows beyond it are dropped); RING = true: slot it % max_iter of a
 // ring of max_iter slabs that a copy stream drains to the host while the next sweeps run
@@ -68,6 +73,14 @@ int omc_device_sm_count(void) { return omc_sm_count(); }
 int omc_counter_add(unsigned long long* counter, unsigned long long inc, void* stream) {
   OMC_REQUIRE(counter, "omc_counter_add: null counter");
   counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_counter_add2(unsigned long long* c0, unsigned long long inc0, unsigned long long* c1, unsigned long long inc1,
+                     void* stream) {
+  OMC_REQUIRE(c0 && c1, "omc_counter_add2: null counter");
+  counter_add2_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(c0, inc0, c1, inc1);
   OMC_LAUNCH_CHECK();
   return 0;
 }

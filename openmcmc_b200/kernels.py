@@ -145,6 +145,10 @@ def counter_add(counter, inc=1):
     check(lib().omc_counter_add(_ptr(counter), int(inc), stream_ptr()), "omc_counter_add")
 
 
+def counter_add2(c0, inc0, c1, inc1):
+    check(lib().omc_counter_add2(_ptr(c0), int(inc0), _ptr(c1), int(inc1), stream_ptr()), "omc_counter_add2")
+
+
 # ----------------------------------------------------------------------------- conjugate regression
 def reg_pass_workspace(n_chains, n, p):
     ns = C.c_int(0)

@@ -41,6 +41,7 @@ class LazyHostArray:
 
 
 STREAM_STORE_BYTES = 256 << 20  # device stores above this are streamed to the host during the run (stream_store=None)
+FUSE_STORED_SWEEP = True       # n_thin = 1: sweep + store epilogue captured as one graph, small ops fused across
 RING_BYTES = 1 << 30           # budget of the device ring of a streamed store (at least 2 slabs; the drain, not the ring, is the limit)
 
 
@@ -249,14 +250,25 @@ class MCMC:
             plan.valid = saved_valid
             self.plan = plan
             counter = sweep_ops.pop()                           # the sweep counter stays a launch of its own, last
+            sweep_raw = list(sweep_ops)
             sweep_ops = engine.fuse_small_ops(plan, sweep_ops) + [counter]
             counter = store_ops.pop()
+            store_raw = list(store_ops)
             store_ops = engine.fuse_small_ops(plan, store_ops) + [counter]
             self._ops = {"prologue": prologue_ops, "sweep": sweep_ops, "store": store_ops}
+            # n_thin = 1: every sweep is a stored one, so sweep + store epilogue are ONE graph whose small per-chain ops
+            # (conjugate scalar draws, log-density terms, store copies) fuse across the boundary, both counters last
+            stored_sweep_ops = None
+            if FUSE_STORED_SWEEP and self.n_thin == 1 and not self._streamed and self.n_iter >= 1:
+                stored_sweep_ops = engine.fuse_small_ops(plan, sweep_raw + store_raw) + [
+                    ("counters", lambda: K.counter_add2(plan.sweep_counter, 1, plan.iter_counter, 1))]
+                self._ops["stored_sweep"] = stored_sweep_ops
             if warm_up:
                 self._warm_up(plan, st, sampled)
             self._sweep_graph = K.Graph.capture(lambda: [fn() for _, fn in sweep_ops])
             self._store_graph = K.Graph.capture(lambda: [fn() for _, fn in store_ops])
+            self._stored_sweep_graph = (K.Graph.capture(lambda: [fn() for _, fn in stored_sweep_ops])
+                                        if stored_sweep_ops is not None else None)
             for _, fn in prologue_ops:
                 fn()
         if wait:
@@ -281,8 +293,8 @@ class MCMC:
                 saved.append((ctx["counters"], ctx["counters"].clone()))
         for t in (plan.sweep_counter, plan.iter_counter, plan.status):
             saved.append((t, t.clone()))
-        for phase in ("prologue", "sweep", "store"):
-            for _, fn in self._ops[phase]:
+        for phase in ("prologue", "sweep", "store", "stored_sweep"):
+            for _, fn in self._ops.get(phase, []):
                 fn()
         for t, copy_ in saved:
             t.copy_(copy_)
@@ -296,6 +308,14 @@ class MCMC:
         self.prepare()
         return self._sweep_graph.num_kernels()
 
+    def launches_of(self, n_burn: int, n_iter: int, n_thin: int) -> int:
+        """Kernel launches run_device(n_burn, n_iter, n_thin) replays."""
+        self.prepare()
+        sw, store = self._sweep_graph.num_kernels(), self._store_graph.num_kernels()
+        if n_thin == 1 and n_iter > 0 and not self._streamed and self._stored_sweep_graph is not None:
+            return n_burn * sw + n_iter * self._stored_sweep_graph.num_kernels()
+        return (n_burn + n_iter * n_thin) * sw + n_iter * store
+
     def run_device(self, n_burn=None, n_iter=None, n_thin=None):
         """Replay the captured sweep graph on the engine's stream (asynchronous)."""
         self.prepare()
@@ -306,6 +326,11 @@ class MCMC:
             self.plan.iter_counter.zero_()     # a run stores from iteration 0 again, as the reference overwrites its store
             if self._streamed and n_iter > 0:
                 return self._run_streamed(n_burn, n_iter, n_thin)
+            if n_thin == 1 and n_iter > 0 and getattr(self, "_stored_sweep_graph", None) is not None:
+                if n_burn:
+                    K.run_schedule(self._sweep_graph, None, n_burn, 0, 1)
+                self._stored_sweep_graph.launch(n_iter)
+                return
             K.run_schedule(self._sweep_graph, self._store_graph, n_burn, n_iter, n_thin)
 
     def _run_streamed(self, n_burn, n_iter, n_thin):

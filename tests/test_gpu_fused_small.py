@@ -56,3 +56,33 @@ def test_fused_mh_store_matches_unfused():
     a, b = _run(True, build, **kw), _run(False, build, **kw)
     assert np.array_equal(a.store["lam"], b.store["lam"])
     np.testing.assert_allclose(a.store["log_post"], b.store["log_post"], rtol=1e-13)
+
+
+def test_stored_sweep_graph_is_bit_identical_and_three_launches():
+    """n_thin = 1: sweep and store epilogue replay as ONE graph whose small ops fuse across the boundary (draw, fused
+    small ops, both counters) -- the same chains, stores and counters as the two-graph schedule."""
+    from openmcmc_b200 import mcmc
+    from test_gpu_stream_store import _regression
+
+    def run(flag):
+        old = mcmc.FUSE_STORED_SWEEP
+        mcmc.FUSE_STORED_SWEEP = flag
+        try:
+            mdl, samplers, state = _regression(9, 250, 10, 33)
+            mdl.response = None                                # no fitted values: nothing unfusable in the store epilogue
+            M = mcmc.MCMC(state, samplers, model=mdl, n_burn=3, n_iter=12, n_thin=1, n_chains=9, seed=5)
+            M.run_mcmc()
+        finally:
+            mcmc.FUSE_STORED_SWEEP = old
+        return M
+
+    a, b = run(True), run(False)
+    assert a._stored_sweep_graph is not None and b._stored_sweep_graph is None
+    assert a._stored_sweep_graph.num_kernels() == 3, [label for label, _ in a._ops["stored_sweep"]]
+    assert a.launches_of(3, 12, 1) == 3 * 3 + 12 * 3 and b.launches_of(3, 12, 1) == 15 * 3 + 12 * b._store_graph.num_kernels()
+    for key in b.store:
+        assert np.array_equal(a.store[key], b.store[key]), key
+    for key in ("beta", "tau", "lambda"):
+        assert np.array_equal(a.state[key], b.state[key]), key
+    assert int(a.plan.sweep_counter.item()) == int(b.plan.sweep_counter.item()) == 15
+    assert int(a.plan.iter_counter.item()) == int(b.plan.iter_counter.item()) == 12
