@@ -81,7 +81,7 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="override n (debug only)")
     ap.add_argument("--upload-blocks", type=int, default=None,
                     help="chain blocks of the e2e run (upload of block k+1 under the sweeps of block k); default: "
-                         "MCMC's automatic choice, one block per 4 GB of per-chain host input")
+                         "MCMC's automatic choice, one block per 1.4 GB of per-chain host input, at most 16")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the comparison legs (sweep forms, fitted values, ESS "

@@ -41,6 +41,7 @@ class LazyHostArray:
 
 
 STREAM_STORE_BYTES = 256 << 20  # device stores above this are streamed to the host during the run (stream_store=None)
+UPLOAD_PIECE_BYTES = 256 << 20  # chain blocks are uploaded in pieces of this size (see _run_blocked.stage)
 FUSE_STORED_SWEEP = True       # n_thin = 1: sweep + store epilogue captured as one graph, small ops fused across
 RING_BYTES = 1 << 30           # budget of the device ring of a streamed store (at least 2 slabs; the drain, not the ring, is the limit)
 
@@ -68,8 +69,8 @@ class MCMC:
     #                            the store would exceed STREAM_STORE_BYTES
     upload_blocks: int = None  # > 1: run the chains as that many contiguous chain blocks, block k+1 being uploaded and
     #                            compiled while block k sweeps (chains are independent and the RNG is keyed by the
-    #                            global chain id, so the draws are the same); None = one block per 4 GB of per-chain
-    #                            HOST input, at most 8; see _run_blocked
+    #                            global chain id, so the draws are the same); None = one block per 1.4 GB of per-chain
+    #                            HOST input, at most 16; see _run_blocked
     store: dict = field(default_factory=dict, init=False)
 
     def __post_init__(self):
@@ -507,7 +508,7 @@ class MCMC:
                     host_bytes += v.nbytes
                 elif isinstance(v, torch.Tensor) and v.dim() == 3 and v.shape[0] == C and not v.is_cuda:
                     host_bytes += v.numel() * v.element_size()
-            B = min(8, int(host_bytes // 4e9))
+            B = min(16, int(host_bytes // 1.4e9))   # ~30 ms of PCIe per block = the host's per-block plan / capture time
         B = min(int(B), self.n_chains // 2)
         if B <= 1 or self.debug_draws or self.probes or self._rj_sampler() is not None:
             return 1
@@ -537,8 +538,16 @@ class MCMC:
             with torch.cuda.stream(copy_stream):
                 for key, v in self.state.items():
                     if per_chain(v) and isinstance(v, torch.Tensor) and not v.is_cuda and v.is_pinned():
-                        out[key] = v[lo:hi].to(dev, non_blocking=True)
-                        nbytes += out[key].numel() * out[key].element_size()
+                        # in pieces of ~256 MB: the small (pageable) uploads of the block whose plan the host is
+                        # compiling meanwhile share the copy engine with this transfer and would otherwise wait behind
+                        # all of it (90 ms per block at the C2 shape)
+                        dst = torch.empty((hi - lo,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                        per = max(1, int(UPLOAD_PIECE_BYTES // max(v[0].numel() * v.element_size(), 1)))
+                        for i0 in range(lo, hi, per):
+                            i1 = min(hi, i0 + per)
+                            dst[i0 - lo:i1 - lo].copy_(v[i0:i1], non_blocking=True)
+                        out[key] = dst
+                        nbytes += dst.numel() * dst.element_size()
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             return out, ev, nbytes
