@@ -637,8 +637,15 @@ def ess_record(ctx, M, wl, n, ms, note_extra=""):
     torch.cuda.synchronize()
     ess_total = float(G.min_ess_per_chain(summ, all_ranks=True).sum().item())
     rhat_max = max(float(torch.nan_to_num(v["rhat"], nan=1.0).max().item()) for v in summ.values())
+    bulk = None
+    try:   # SURVEY §8d's estimator: bulk-ESS = ESS of the rank-normalised draws of every chain (Vehtari et al. 2021)
+        sb = G.summarize(M, elem_stride=strides, rank_normalized="chain")
+        bulk_total = float(G.min_ess_per_chain(sb, all_ranks=True).sum().item())
+        bulk = {"value": bulk_total / (ms * 1e-3), "unit": "ESS/s", "ess_total": bulk_total}
+    except Exception as exc:
+        bulk = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
     return {"value": ess_total / (ms * 1e-3), "unit": "ESS/s", "n_stored": int(M.plan.iter_counter.item()),
-            "ess_total": ess_total, "rhat_max": rhat_max, "params": sorted(summ), "diag_ms": d0.elapsed_time(d1),
+            "ess_total": ess_total, "bulk": bulk, "rhat_max": rhat_max, "params": sorted(summ), "diag_ms": d0.elapsed_time(d1),
             "gathered_chains": int(next(iter(summ.values()))["n_chains_total"]),
             "note": "sum over all chains of the minimum-over-parameters ESS of the stored draws, divided by the seconds "
                     "of the sweeps that produced them; per-chain records all-gathered over the process group; rhat_max "

@@ -493,6 +493,12 @@ typedef struct {
 } omc_chain_stats_t;
 int omc_chain_stats(const omc_chain_stats_t* args, void* stream);
 int omc_rhat_combine(const double* stats, int n_chains_total, int n_sel, double* out, void* stream);
+/* Rank normalisation (Vehtari et al. 2021): z [n_iter][n_chains][n_sel] = Phi^-1((r - 3/8) / (S + 1/4)) with r the average
+ * rank of the draw among the n_iter draws of its own series (pooled = 0) or among the draws of all n_chains chains of that
+ * element (pooled = 1); `sorted` is scratch [n_chains][n_sel][n_iter].  omc_chain_stats / omc_rhat_combine on z give
+ * bulk-ESS and rank-normalised split-R-hat.  n_iter <= 16384. */
+int omc_rank_normalize(const double* samples, long long n_iter, int n_chains, long long size, long long n_sel,
+                       long long elem_stride, int pooled, double* sorted, double* z, void* stream);
 
 /* ------------------------------------------------------------------ ReversibleJump (C5)
  * One birth / death step per chain for the Gaussian-kernel basis model of the reference's RJ tests

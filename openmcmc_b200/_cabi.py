@@ -277,6 +277,8 @@ PROTOTYPES = {
     "omc_logp_domain": (C.c_int, [C.c_int, C.c_int, Vec, Vec, C.c_int, Vec, C.c_int, C.c_void_p, C.c_void_p]),
     "omc_linear_predictor": (C.c_int, [C.POINTER(LinearPredictor), C.c_void_p]),
     "omc_combine": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.POINTER(Vec), C.POINTER(Vec), C.c_void_p, C.c_void_p]),
+    "omc_rank_normalize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "omc_sum_log": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_log_elements": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "omc_logdet_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -150,6 +150,70 @@ __global__ void rhat_combine_kernel(const double* stats, int n_chains, int n_sel
   o[3] = var_plus;
 }
 
+// ---------------------------------------------------------------------------------------------- rank normalisation
+// Vehtari, Gelman, Simpson, Carpenter, Buerkner (2021): replace every draw by the normal score of its rank,
+//   z = Phi^-1((r - 3/8) / (S + 1/4)),  r = average rank (ties share the mean of their ranks) among the S draws ranked together,
+// and run split-R-hat / ESS on z ("bulk" diagnostics: insensitive to heavy tails, invariant under monotone transforms).
+// Two kernels: every series (one selected element of one chain, n_iter draws) is sorted in shared memory (bitonic, one CTA
+// per series) and written out; then every draw finds its rank by binary search in the sorted series -- of its own chain
+// (pooled = 0: S = n_iter) or of ALL chains of the launch (pooled = 1: S = n_chains n_iter, the form split-R-hat wants
+// when the chains share a target).  Output z [n_iter][n_chains][n_sel].
+constexpr int RN_NT = 256;
+
+__global__ void __launch_bounds__(RN_NT) rank_sort_kernel(const double* __restrict__ samples, long long n_iter, int n_chains,
+                                                          long long size, long long n_sel, long long elem_stride, int npad,
+                                                          double* __restrict__ sorted) {
+  extern __shared__ double v[];                      // npad values (power of two), padded with +inf
+  const long long ser = blockIdx.x;
+  const long long chain = ser / n_sel, jsel = ser % n_sel;
+  const long long step = (long long)n_chains * size;
+  const double* x = samples + chain * size + jsel * elem_stride;
+  for (int t = threadIdx.x; t < npad; t += RN_NT) v[t] = t < n_iter ? x[(long long)t * step] : INFINITY;
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < npad; t += RN_NT) {
+        const int o = t ^ j;
+        if (o > t) {
+          const double a = v[t], b = v[o];
+          const bool up = (t & k) == 0;
+          if ((a > b) == up) { v[t] = b; v[o] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  double* out = sorted + ser * n_iter;
+  for (int t = threadIdx.x; t < n_iter; t += RN_NT) out[t] = v[t];
+}
+
+__device__ __forceinline__ void rn_counts(const double* __restrict__ s, long long n, double x, long long& less, long long& leq) {
+  long long lo = 0, hi = n;                          // first index with s[i] >= x
+  while (lo < hi) { const long long m = (lo + hi) >> 1; if (s[m] < x) lo = m + 1; else hi = m; }
+  less += lo;
+  hi = n;                                            // first index with s[i] > x
+  while (lo < hi) { const long long m = (lo + hi) >> 1; if (s[m] <= x) lo = m + 1; else hi = m; }
+  leq += lo;
+}
+
+__global__ void __launch_bounds__(RN_NT) rank_score_kernel(const double* __restrict__ samples, long long n_iter, int n_chains,
+                                                           long long size, long long n_sel, long long elem_stride, int pooled,
+                                                           const double* __restrict__ sorted, double* __restrict__ z) {
+  const long long total = n_iter * n_chains * n_sel;
+  for (long long e = (long long)blockIdx.x * RN_NT + threadIdx.x; e < total; e += (long long)gridDim.x * RN_NT) {
+    const long long jsel = e % n_sel, chain = (e / n_sel) % n_chains, t = e / (n_sel * n_chains);
+    const double x = samples[(t * n_chains + chain) * size + jsel * elem_stride];
+    long long less = 0, leq = 0;
+    if (pooled) {
+      for (int c = 0; c < n_chains; ++c) rn_counts(sorted + ((long long)c * n_sel + jsel) * n_iter, n_iter, x, less, leq);
+    } else {
+      rn_counts(sorted + (chain * n_sel + jsel) * n_iter, n_iter, x, less, leq);
+    }
+    const double S = (double)(pooled ? n_iter * n_chains : n_iter);
+    const double r = 0.5 * (double)(less + leq + 1);                 // ranks less+1 .. leq share their mean
+    z[e] = (x == x) ? normcdfinv((r - 0.375) / (S + 0.25)) : x;     // NaN draws stay NaN
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -173,6 +237,29 @@ int omc_chain_stats(const omc_chain_stats_t* a, void* stream) {
 int omc_rhat_combine(const double* stats, int n_chains_total, int n_sel, double* out, void* stream) {
   OMC_REQUIRE(stats && out && n_chains_total >= 1 && n_sel >= 1, "omc_rhat_combine: bad argument");
   rhat_combine_kernel<<<(n_sel + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n_chains_total, n_sel, out);
+  OMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int omc_rank_normalize(const double* samples, long long n_iter, int n_chains, long long size, long long n_sel,
+                       long long elem_stride, int pooled, double* sorted, double* z, void* stream) {
+  OMC_REQUIRE(samples && sorted && z, "omc_rank_normalize: null argument");
+  OMC_REQUIRE(n_iter >= 1 && n_chains >= 1 && size >= 1 && n_sel >= 1 && elem_stride >= 1 && (n_sel - 1) * elem_stride < size,
+              "omc_rank_normalize: bad shape");
+  OMC_REQUIRE(n_iter <= 16384, "omc_rank_normalize: n_iter=%lld > 16384 draws per series (shared-memory sort)", n_iter);
+  int npad = 2;
+  while (npad < n_iter) npad <<= 1;
+  const int smem = npad * 8;
+  OMC_CHECK_CUDA(cudaFuncSetAttribute(rank_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long n_series = (long long)n_chains * n_sel;
+  OMC_REQUIRE(n_series < 0x7fffffffll, "omc_rank_normalize: too many series");
+  rank_sort_kernel<<<(unsigned)n_series, RN_NT, smem, (cudaStream_t)stream>>>(samples, n_iter, n_chains, size, n_sel,
+                                                                            elem_stride, npad, sorted);
+  OMC_LAUNCH_CHECK();
+  const long long total = n_iter * n_series;
+  const long long blocks = (total + RN_NT - 1) / RN_NT;
+  rank_score_kernel<<<(unsigned)(blocks < 65535 ? blocks : 65535), RN_NT, 0, (cudaStream_t)stream>>>(
+      samples, n_iter, n_chains, size, n_sel, elem_stride, pooled, sorted, z);
   OMC_LAUNCH_CHECK();
   return 0;
 }

@@ -36,6 +36,19 @@ def chain_stats(samples: torch.Tensor, elem_stride: int = 1, n_sel: int = None, 
     return out
 
 
+def rank_normalize(samples: torch.Tensor, elem_stride: int = 1, n_sel: int = None, pooled: bool = False) -> torch.Tensor:
+    """Normal scores of the ranks (Vehtari et al. 2021) of a device store [n_iter, n_chains, size] ->
+    z [n_iter, n_chains, n_sel]; ranks within each chain's series, or (pooled) over all chains of the store."""
+    n_iter, n_chains, size = samples.shape
+    if n_sel is None:
+        n_sel = (size + elem_stride - 1) // elem_stride
+    z = torch.empty(n_iter, n_chains, n_sel, dtype=torch.float64, device=samples.device)
+    scratch = torch.empty(n_chains, n_sel, n_iter, dtype=torch.float64, device=samples.device)
+    _cabi.check(K.lib().omc_rank_normalize(samples.data_ptr(), n_iter, n_chains, size, n_sel, elem_stride, int(bool(pooled)),
+                                           scratch.data_ptr(), z.data_ptr(), K.stream_ptr()), "omc_rank_normalize")
+    return z
+
+
 def gather_records(local: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather per-chain records [n_local, n_sel, 8] over the process group -> [n_total, n_sel, 8], rank order =
     chain order.  Ranks may hold different numbers of chains (shard_chains); the counts are exchanged first."""
@@ -70,10 +83,16 @@ def rhat_combine(records: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def summarize(mcmc, params=None, elem_stride=None, max_lag: int = 127, group=None) -> dict:
+def summarize(mcmc, params=None, elem_stride=None, max_lag: int = 127, group=None, rank_normalized=None) -> dict:
     """Diagnostics of a finished (or running) `MCMC`: for every sampled parameter a dict with per-chain `records`
     [n_local, n_sel, 8], and after the all-gather `rhat`, `ess` (sum over all chains), `mean`, `var_plus` [n_sel].
-    `elem_stride[param]` thins long parameters (C3: a strided subset of the field)."""
+    `elem_stride[param]` thins long parameters (C3: a strided subset of the field).
+    rank_normalized: None = the draws themselves (Geyer ESS, plain split-R-hat); "chain" = the draws replaced by the normal
+    scores of their ranks within each chain (bulk-ESS per chain, what ESS/s sums); "pooled" = ranks over all chains of a
+    block (bulk-ESS and rank-normalised split-R-hat of Vehtari et al. 2021; for chains that share their target; the
+    ranks are pooled per device, not across ranks).  `mean` / `var_plus` then refer to the scores."""
+    if rank_normalized not in (None, "chain", "pooled"):
+        raise ValueError("rank_normalized must be None, 'chain' or 'pooled'")
     out = {}
     blocks = getattr(mcmc, "_blocks", None) or [mcmc]       # a run in chain blocks keeps its plans / stores per block
     for s in mcmc.samplers:
@@ -84,6 +103,8 @@ def summarize(mcmc, params=None, elem_stride=None, max_lag: int = 127, group=Non
         for blk in blocks:
             with torch.cuda.stream(blk.stream):
                 buf, eff_stride = blk.device_samples(s.param, stride)
+                if rank_normalized:
+                    buf, eff_stride = rank_normalize(buf, elem_stride=eff_stride, pooled=rank_normalized == "pooled"), 1
                 recs.append(chain_stats(buf, elem_stride=eff_stride, max_lag=max_lag))
             blk.stream.synchronize()
         rec = recs[0] if len(recs) == 1 else torch.cat(recs, dim=0)     # chain order = block order

@@ -60,3 +60,24 @@ def rhat_combine(stats):
         var_plus = (nh - 1) / nh * W + b_over_n
         out[j] = [np.sqrt(var_plus / W) if W > 0 else np.nan, stats[:, j, 3].sum(), stats[:, j, 1].mean(), var_plus]
     return out
+
+
+def rank_normalize(samples, elem_stride=1, n_sel=None, pooled=False):
+    """Vehtari et al. (2021), eq. (14): z = Phi^-1((r - 3/8) / (S + 1/4)), r = average rank among the S draws ranked
+    together (one chain's series, or all chains pooled).  samples [n_iter, n_chains, size] -> z [n_iter, n_chains, n_sel]."""
+    from scipy import stats
+
+    N, C, size = samples.shape
+    if n_sel is None:
+        n_sel = (size + elem_stride - 1) // elem_stride
+    z = np.empty((N, C, n_sel))
+    for j in range(n_sel):
+        x = samples[:, :, j * elem_stride]
+        if pooled:
+            r = stats.rankdata(x.ravel(), method="average").reshape(N, C)
+            z[:, :, j] = stats.norm.ppf((r - 0.375) / (N * C + 0.25))
+        else:
+            for c in range(C):
+                r = stats.rankdata(x[:, c], method="average")
+                z[:, c, j] = stats.norm.ppf((r - 0.375) / (N + 0.25))
+    return z

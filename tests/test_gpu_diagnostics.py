@@ -38,6 +38,33 @@ def test_chain_stats_and_rhat_match_oracle(N, C, size, stride, max_lag):
         np.testing.assert_allclose(comb, D.rhat_combine(ref), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("N,C,size,stride,pooled", [(7, 3, 2, 1, False), (64, 5, 3, 2, True), (500, 12, 4, 1, False),
+                                                    (1000, 6, 9, 4, True), (3000, 2, 1, 1, True), (1, 2, 1, 1, False)])
+def test_rank_normalize_matches_oracle(N, C, size, stride, pooled):
+    """omc_rank_normalize against scipy.stats.rankdata(method="average") + norm.ppf, ties and heavy tails included; the
+    bulk-ESS / rank-normalised split-R-hat records then follow from the kernels above."""
+    import torch
+
+    from openmcmc_b200 import diagnostics as G
+    from openmcmc_b200 import kernels as K
+    from oracle import diagnostics as D
+
+    K.init_device()
+    rng = np.random.default_rng(N + C + 1)
+    x = _ar1(rng, N, C, size, 0.6)
+    x[:, 0, 0] = np.round(x[:, 0, 0], 1)                       # ties
+    if C > 1:
+        x[:, 1, 0] = rng.standard_cauchy(N)                   # no variance: the case rank normalisation exists for
+    d = torch.as_tensor(x).cuda()
+    z = G.rank_normalize(d, elem_stride=stride, pooled=pooled)
+    zr = D.rank_normalize(x, elem_stride=stride, pooled=pooled)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(z.cpu().numpy(), zr, rtol=1e-12, atol=1e-13)
+    if N >= 4:
+        rec = G.chain_stats(z)
+        np.testing.assert_allclose(rec.cpu().numpy(), D.chain_stats(zr), rtol=1e-9, atol=1e-12)
+
+
 def test_summary_of_a_gibbs_run():
     """64 chains of the small Gibbs regression: R-hat near 1 for every coefficient, ESS close to the number of stored
     draws (conjugate Gibbs mixes in one sweep), and the per-chain minimum ESS feeds the ESS/s metric."""
@@ -73,6 +100,13 @@ def test_summary_of_a_gibbs_run():
     assert np.all(np.abs(rhat - 1) < 0.02), rhat
     ess = S["beta"]["ess"].cpu().numpy()
     assert np.all(ess > 0.5 * C * 400), ess
+    # rank-normalised forms (Vehtari et al. 2021): pooled ranks -> rank-normalised split-R-hat and bulk-ESS
+    Sp = G.summarize(M, rank_normalized="pooled")
+    assert np.all(np.abs(Sp["beta"]["rhat"].cpu().numpy() - 1) < 0.02)
+    assert np.all(Sp["beta"]["ess"].cpu().numpy() > 0.5 * C * 400)
+    Sc = G.summarize(M, rank_normalized="chain")
+    bulk = G.min_ess_per_chain(Sc).cpu().numpy()
+    assert bulk.shape == (C,) and np.all(bulk > 100)
     per_chain = G.min_ess_per_chain(S)
     assert per_chain.shape == (C,) and float(per_chain.min()) > 50
     # the device mean agrees with the host store
