@@ -81,7 +81,7 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="override n (debug only)")
     ap.add_argument("--upload-blocks", type=int, default=None,
                     help="chain blocks of the e2e run (upload of block k+1 under the sweeps of block k); default: "
-                         "MCMC's automatic choice, one block per 1.4 GB of per-chain host input, at most 16")
+                         "MCMC's automatic choice, one block per 2.7 GB of per-chain host input, at most 16")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the comparison legs (sweep forms, fitted values, ESS "
@@ -552,6 +552,23 @@ def e2e_leg(ctx, wl, key, C, n, p, steps, thin, upload_blocks):
     mdl, samplers2, hstate = build(wl, Ce, n, ctx.dev, ctx.rank, host=True)
     numa_interleave(False)
     n_iter = max(steps // thin, 1)
+
+    mem_before = None
+    prep = os.environ.get("OMC_BENCH_E2E_PREP", "")      # tuning aid: state of the caching allocator in front of the leg
+    if prep:
+        import gc
+
+        gc.collect()
+        st0 = torch.cuda.memory_stats()
+        mem_before = {"prep": prep, "reserved_gb": st0["reserved_bytes.all.current"] / 1e9,
+                      "allocated_gb": st0["allocated_bytes.all.current"] / 1e9,
+                      "inactive_split_gb": st0["inactive_split_bytes.all.current"] / 1e9}
+        if prep in ("empty", "warm"):
+            torch.cuda.empty_cache()
+        if prep == "warm":
+            x = torch.empty(int(per_chain_host * Ce * 1.1), dtype=torch.uint8, device=ctx.dev)
+            del x
+        sys.stderr.write(f"e2e allocator state: {mem_before}\n")
 
     def run(blocks, first=True):
         if first:

@@ -69,7 +69,7 @@ class MCMC:
     #                            the store would exceed STREAM_STORE_BYTES
     upload_blocks: int = None  # > 1: run the chains as that many contiguous chain blocks, block k+1 being uploaded and
     #                            compiled while block k sweeps (chains are independent and the RNG is keyed by the
-    #                            global chain id, so the draws are the same); None = one block per 1.4 GB of per-chain
+    #                            global chain id, so the draws are the same); None = one block per 2.7 GB of per-chain
     #                            HOST input, at most 16; see _run_blocked
     store: dict = field(default_factory=dict, init=False)
 
@@ -508,7 +508,7 @@ class MCMC:
                     host_bytes += v.nbytes
                 elif isinstance(v, torch.Tensor) and v.dim() == 3 and v.shape[0] == C and not v.is_cuda:
                     host_bytes += v.numel() * v.element_size()
-            B = min(16, int(host_bytes // 1.4e9))   # ~30 ms of PCIe per block = the host's per-block plan / capture time
+            B = min(16, int(host_bytes // 2.7e9))   # ~60 ms of PCIe per block: twice the host's per-block plan / capture time
         B = min(int(B), self.n_chains // 2)
         if B <= 1 or self.debug_draws or self.probes or self._rj_sampler() is not None:
             return 1
@@ -531,6 +531,8 @@ class MCMC:
         def per_chain(v):
             return isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim == 3 and v.shape[0] == C
 
+        arenas = {}
+
         def stage(lo, hi):
             """Queue the host->device copies of a block's pinned per-chain tensors on the copy stream.  The copies of
             block k+1 are queued BEFORE the host turns to block k's plan, so the PCIe link never waits for Python."""
@@ -541,7 +543,12 @@ class MCMC:
                         # in pieces of ~256 MB: the small (pageable) uploads of the block whose plan the host is
                         # compiling meanwhile share the copy engine with this transfer and would otherwise wait behind
                         # all of it (90 ms per block at the C2 shape)
-                        dst = torch.empty((hi - lo,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                        if key not in arenas:   # ONE device allocation per input for all blocks (they all stay resident
+                            # until the run is collected): the blocks are views, so the caching allocator is asked once
+                            # instead of once per block -- a fragmented cache answered 1.4 GB requests with a
+                            # synchronising free / malloc cycle of 0.15-0.3 s each
+                            arenas[key] = torch.empty((C,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                        dst = arenas[key][lo:hi]
                         per = max(1, int(UPLOAD_PIECE_BYTES // max(v[0].numel() * v.element_size(), 1)))
                         for i0 in range(lo, hi, per):
                             i1 = min(hi, i0 + per)

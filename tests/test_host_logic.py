@@ -83,12 +83,12 @@ def test_upload_block_policy_and_state_coercion():
     assert MCMC(state, samplers, model=mdl, n_chains=C, upload_blocks=4,
                 debug_draws={"beta": {"z": np.zeros((1, C, p))}})._n_blocks() == 1
     assert MCMC(state, samplers, model=mdl, n_chains=1, upload_blocks=4)._n_blocks() == 1
-    # automatic policy: one block per 1.4 GB of per-chain host input, at most 16 (a strided view stands in for 21 GB)
+    # automatic policy: one block per 2.7 GB of per-chain host input, at most 16 (a strided view stands in for 21 GB)
     big = np.lib.stride_tricks.as_strided(np.zeros(1), shape=(4096, 10_000, 64), strides=(0, 0, 0))
     st2 = dict(state, X=big, y=np.zeros((4096, 1, 1)))
     auto = MCMC.__new__(MCMC)
     auto.state, auto.samplers, auto.n_chains, auto.upload_blocks, auto.debug_draws, auto.probes = st2, samplers, 4096, None, None, False
-    assert auto._n_blocks() == 14
+    assert auto._n_blocks() == 7
     auto.upload_blocks = 0
     assert auto._n_blocks() == 1
 
