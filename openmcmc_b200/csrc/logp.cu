@@ -83,6 +83,53 @@ __global__ void __launch_bounds__(LP_THREADS) linear_predictor_kernel(omc_linear
       a.out[row] = a.residual_of.ptr ? a.residual_of.ptr[(long long)c * a.residual_of.chain_stride + r] - acc : acc;
   }
 }
+// Streaming form of the single-term predictor for 2 <= p <= 64, p even (the fitted values X beta of every stored
+// iteration, mcmc.py:109-111, and the explicit residual of the re-centring prologue): a warp takes 16 consecutive rows of
+// one chain, every lane one 16-byte pair of columns -- the 16 row loads go out together (8 KB in flight per warp), theta
+// sits in registers, the 16 row sums are reduced together (first across the two half-warps, then by halving: 31
+// double shuffles per 16 rows instead of 5 per row) and leave as one coalesced store.  The generic kernel above re-read
+// theta per row, reduced every row on its own and stored 8 bytes per warp and row: 2.1 TB/s on the C2 shape.
+constexpr int LPR_ROWS = 16;
+__global__ void __launch_bounds__(LP_THREADS) linear_predictor_rows_kernel(omc_linear_predictor_t a) {
+  const int lane = threadIdx.x & 31;
+  const int p = a.p[0];
+  const long long blocks_per_chain = (a.n + LPR_ROWS - 1) / LPR_ROWS;
+  const long long total = (long long)a.n_chains * blocks_per_chain;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool live = 2 * lane < p;
+  for (long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < total; blk += nwarps) {
+    const int c = (int)(blk / blocks_per_chain);
+    const long long r0 = (blk - (long long)c * blocks_per_chain) * LPR_ROWS;
+    const double* th = a.theta[0].ptr + (long long)c * a.theta[0].chain_stride;
+    double t0 = live ? th[2 * lane] : 0.0, t1 = live ? th[2 * lane + 1] : 0.0;
+    if (a.transform_exp[0]) { t0 = live ? exp(t0) : 0.0; t1 = live ? exp(t1) : 0.0; }
+    const double* x = a.X[0].ptr + (long long)c * a.X[0].chain_stride + r0 * p + 2 * lane;
+    double2 xv[LPR_ROWS];
+#pragma unroll
+    for (int i = 0; i < LPR_ROWS; ++i)
+      xv[i] = (live && r0 + i < a.n) ? __ldg(reinterpret_cast<const double2*>(x + (long long)i * p)) : make_double2(0.0, 0.0);
+    double v[LPR_ROWS];
+#pragma unroll
+    for (int i = 0; i < LPR_ROWS; ++i) v[i] = fma(xv[i].x, t0, xv[i].y * t1);
+    // lanes l and l ^ 16 first (all 16 sums), then keep half of the sums per step: lane l ends with row (l & 15)
+#pragma unroll
+    for (int i = 0; i < LPR_ROWS; ++i) v[i] += omc_shfl_xor(v[i], 16);
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+      const bool upper = (lane & h) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const double keep = upper ? v[i + h] : v[i], send = upper ? v[i] : v[i + h];
+        v[i] = keep + omc_shfl_xor(send, h);
+      }
+    }
+    const long long r = r0 + (lane & 15);
+    if (lane < 16 && r < a.n) {
+      const long long o = (long long)c * a.n + r;
+      a.out[o] = a.residual_of.ptr ? a.residual_of.ptr[(long long)c * a.residual_of.chain_stride + r] - v[0] : v[0];
+    }
+  }
+}
 __global__ void __launch_bounds__(LP_THREADS) sum_log_kernel(const double* x, long long n, double* out) {
   __shared__ double scratch[32];
   const double* xm = x + (long long)blockIdx.x * n;
@@ -224,8 +271,18 @@ int omc_combine(int n_chains, long long len, int n_terms, const omc_vec_t* x, co
 int omc_linear_predictor(const omc_linear_predictor_t* a, void* stream) {
   OMC_REQUIRE(a && a->out && a->n_terms >= 1 && a->n_terms <= 4, "omc_linear_predictor: bad argument");
   const long long total = (long long)a->n_chains * a->n;
-  long long blocks = (total * 32 + LP_THREADS - 1) / LP_THREADS;
   const long long cap = (long long)omc_sm_count() * 16;
+  const int p0 = a->p[0];
+  if (a->n_terms == 1 && p0 >= 2 && p0 <= 64 && p0 % 2 == 0 && a->X[0].ptr && a->theta[0].ptr &&
+      (reinterpret_cast<uintptr_t>(a->X[0].ptr) & 15) == 0 && a->X[0].chain_stride % 2 == 0) {
+    long long blocks = ((total + LPR_ROWS - 1) / LPR_ROWS * 32 + LP_THREADS - 1) / LP_THREADS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    linear_predictor_rows_kernel<<<(unsigned)blocks, LP_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    OMC_LAUNCH_CHECK();
+    return 0;
+  }
+  long long blocks = (total * 32 + LP_THREADS - 1) / LP_THREADS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   linear_predictor_kernel<<<(unsigned)blocks, LP_THREADS, 0, (cudaStream_t)stream>>>(*a);
