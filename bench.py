@@ -718,6 +718,7 @@ def run_b200(args, wl, key):
         op2 = next((fn for label, fn in M._ops["prologue"] if label.startswith("reg_pass")), None)
         if op2 is not None:
             syrk_ms = time_op(ctx, M, op2)
+        del op2
     clk = clocks.stop()
     ess = ess_record(ctx, M, wl, n, ms_max)
     M.collect()
@@ -763,16 +764,19 @@ def run_b200(args, wl, key):
             "hbm_gbs": C * 8.0 * n * (p + 2) * kf / (msf * 1e-3) / 1e9,
             "note": "response={'y': 'mean'}: X beta per stored iteration = one read of X (8 n p) and a write of n "
                     "values per chain; HBM-bound like the round-1 residual pass"}
-        del Mf
+        del Mf, _
         # ---- ESS over >= 1000 stored draws (the 60 draws of the timed region say little about ESS)
         k_ess = 1000
         Me, mse, _ = value_leg(ctx, wl, key, C, n, k_ess, 20, thin)
         extras["ess_long"] = ess_record(ctx, Me, wl, n, mse, note_extra=f"; separate run of {k_ess} stored sweeps after 20 burn-in sweeps")
         extras["ess_long"]["ms_per_step"] = mse / k_ess
-        del Me
+        del Me, _
     else:
         del state, mdl, samplers
     # ---- e2e: public API with HOST (pinned) inputs, upload + K sweeps + sample download inside the timed region
+    import gc
+
+    gc.collect()          # the earlier legs' device inputs (21 GB each at C2) are released before the end-to-end leg
     e2e = None if args.no_e2e else e2e_leg(ctx, wl, key, C, n, p, args.steps, thin, args.upload_blocks)
     if key == "c2" and not args.no_extras:
         try:
@@ -785,7 +789,7 @@ def run_b200(args, wl, key):
         Ms, mss, _ = value_leg(ctx, wl, key, Cs, n, args.steps, args.warmup, thin, chain_offset=rank * Cs)
         extras["strong"] = {"value": Cs * world * args.steps / (mss * 1e-3), "unit": UNIT, "chains_total": Cs * world,
                             "chains_per_gpu": Cs, "ms_per_step": mss / args.steps, "scaling": "strong"}
-        del Ms
+        del Ms, _
 
     if rank == 0:
         roof = roofline_of(wl, C, n, p, op_ms, ms_max / args.steps, peaks, fp64_peak, syrk_ms, key=key)
