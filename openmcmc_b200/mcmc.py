@@ -341,9 +341,9 @@ class MCMC:
 
         st, C = self._prepared, self.n_chains
         self._staging_warm.join()
-        self._host_store = {name: np.empty((n_iter, C, st[name].size)) for name in self._store_names}
+        self._host_store = {name: stream_store.host_array((n_iter, C, st[name].size)) for name in self._store_names}
         self._host_logpost = np.empty((n_iter, C))
-        self._host_fitted = {r: np.empty((n_iter, C, buf.shape[-1])) for r, buf in self._dev_fitted.items()}
+        self._host_fitted = {r: stream_store.host_array((n_iter, C, buf.shape[-1])) for r, buf in self._dev_fitted.items()}
         entries = [(self._dev_store[name], self._host_store[name]) for name in self._store_names]
         entries.append((self._dev_logpost, self._host_logpost))
         entries += [(self._dev_fitted[r], self._host_fitted[r]) for r in self._dev_fitted]

@@ -36,6 +36,24 @@ def staging_buffers(device_index: int):
         return _pool[device_index]
 
 
+def host_array(shape) -> np.ndarray:
+    """Destination array of a streamed store: np.empty + a transparent-huge-page hint.  The copier threads are the first
+    to touch these pages; with 4 KB pages the kernel's fault handling (zeroing, one fault per page) is what bounds them."""
+    a = np.empty(shape)
+    try:
+        import ctypes
+
+        page = 2 << 20
+        addr = a.ctypes.data
+        lo = (addr + page - 1) // page * page
+        hi = (addr + a.nbytes) // page * page
+        if hi > lo:
+            ctypes.CDLL("libc.so.6", use_errno=True).madvise(ctypes.c_void_p(lo), ctypes.c_size_t(hi - lo), 14)  # MADV_HUGEPAGE
+    except Exception:
+        pass
+    return a
+
+
 def warm(device_index: int) -> threading.Thread:
     th = threading.Thread(target=staging_buffers, args=(device_index,), daemon=True)
     th.start()
