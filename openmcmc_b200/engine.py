@@ -368,20 +368,30 @@ def unreplicate(dists, state: dict, sampled=frozenset()):
     convention, distribution.py:8-10; its introductory examples 1 and 2) into the single-column form the device path
     runs:  y (dim x n_rep) ~ N(h, Q) for every column, h an Identity mean  ==>  vec(y) ~ N(A h, I_n_rep (x) Q) with A the
     n_rep stacked identities -- the same density, now a LinearCombination mean with a diagonal precision, i.e. the
-    regression record / Normal-linear term that exist already.  Applies when the response is not sampled, the mean is
-    an Identity parameter of one column, and the precision matrix is not sampled and diagonal (always so for dim = 1).
+    regression record / Normal-linear term that exist already.  A LinearCombination mean X beta (one value per row, the
+    same for every replicate) is handled the same way with X stacked n_rep times.  Applies when the response is not
+    sampled, the mean is an Identity parameter of one column or a LinearCombination over data designs, and the
+    precision matrix is not sampled and diagonal (always so for dim = 1).
     Returns (dists', state', changed); the inputs are left untouched."""
     from openmcmc_b200.distribution.location_scale import Normal
 
     out, new_state, changed = [], state, False
     for d in dists:
         y = state.get(d.response) if type(d) is Normal else None
+        linear = y is not None and type(d.mean) is LinearCombination   # (round 2) mean X beta: the design is stacked n_rep times
         ok = (y is not None and d.response not in sampled and isinstance(y, np.ndarray) and y.ndim == 2 and y.shape[1] > 1
-              and type(d.mean) is Identity and d.domain_response_lower is None and d.domain_response_upper is None)
+              and (linear or type(d.mean) is Identity) and d.domain_response_lower is None
+              and d.domain_response_upper is None)
         if ok:
             dim, n_rep = y.shape
-            m = state.get(d.mean.form)
-            ok = m is not None and not sparse.issparse(m) and not isinstance(m, torch.Tensor) and np.size(m) == dim
+            if linear:
+                for prm, xname in d.mean.form.items():
+                    X = state.get(xname)
+                    ok = (ok and X is not None and xname not in sampled and isinstance(X, np.ndarray) and X.ndim == 2
+                          and X.shape[0] == dim)
+            else:
+                m = state.get(d.mean.form)
+                ok = m is not None and not sparse.issparse(m) and not isinstance(m, torch.Tensor) and np.size(m) == dim
         if ok:
             if isinstance(d.precision, ScaledMatrix):
                 pname, sname = d.precision.matrix, d.precision.scalar
@@ -401,9 +411,16 @@ def unreplicate(dists, state: dict, sampled=frozenset()):
             new_state, changed = dict(state), True
         tag = f"{REP_TAG}{d.response}:"
         new_state[d.response] = np.ascontiguousarray(np.asarray(y, dtype=np.float64).T).reshape(-1, 1)   # column after column
-        new_state[tag + "A"] = np.tile(np.eye(dim), (n_rep, 1))
         new_state[tag + "P"] = sparse.diags([np.tile(np.diag(Pd), n_rep)], [0], format="csc")
-        mean2 = LinearCombination(form={d.mean.form: tag + "A"})
+        if linear:
+            form2 = {}
+            for prm, xname in d.mean.form.items():
+                new_state[tag + "X:" + xname] = np.tile(np.asarray(state[xname], dtype=np.float64), (n_rep, 1))
+                form2[prm] = tag + "X:" + xname
+            mean2 = LinearCombination(form=form2)
+        else:
+            new_state[tag + "A"] = np.tile(np.eye(dim), (n_rep, 1))
+            mean2 = LinearCombination(form={d.mean.form: tag + "A"})
         prec2 = ScaledMatrix(matrix=tag + "P", scalar=sname) if sname else Identity(tag + "P")
         out.append(Normal(d.response, mean=mean2, precision=prec2))
     return out, new_state, changed

@@ -788,6 +788,36 @@ def replicated_case(dim, n_rep, seed, n_iter, scaled=False):
     return out
 
 
+def replicated_regression_case(dim, p, n_rep, seed, n_iter):
+    """Round 2: replicates in the columns of y with a LinearCombination mean -- y[:, r] ~ N(X beta, (tau W)^-1) for every
+    column r (distribution.py:8-10; the n_rep factor of location_scale.py:238-241): log_p / gradient / Hessian at the
+    start state and a ManifoldMALA chain on beta (the reference's conjugate samplers do not take this form:
+    sampler.py:192 fails to broadcast)."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((dim, p))
+    beta_true = rng.standard_normal((p, 1))
+    y = X @ beta_true + 0.4 * rng.standard_normal((dim, n_rep))
+    W = sparse.diags(rng.random(dim) + 0.5, format="csc")
+    mdl = Model([Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="W", scalar="tau")),
+                 Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam")),
+                 Gamma("tau", shape="a", rate="b")])
+    state = {"y": y, "X": X, "beta": np.zeros((p, 1)), "W": W, "tau": 1.5, "mu": np.zeros((p, 1)),
+             "P": sparse.identity(p, format="csc"), "lam": 0.3, "a": 2.0, "b": 1.0}
+    state0 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in state.items()}
+    sc = {**state0, "tau": np.array([[1.5]]), "lam": np.array([[0.3]]), "a": np.array([[2.0]]), "b": np.array([[1.0]])}
+    lik = Model([mdl["y"]])
+    g0, H0 = lik.grad_log_p(sc, "beta", hessian_required=True)
+    out = {"X": X, "y": y, "w": np.asarray(W.diagonal()), "tau": 1.5, "lam": 0.3, "a": 2.0, "b": 1.0,
+           "logp0": np.array(lik.log_p(sc)), "grad0": np.asarray(g0), "hess0": np.asarray(H0.todense() if sparse.issparse(H0) else H0)}
+    with Streams(seed + 1) as s:
+        smp = ManifoldMALA("beta", mdl, step=np.array([[0.8]]))
+        M = _run_ref(state, [smp], mdl, n_iter)
+    out.update({"z": s.stack("z"), "u": s.stack("u").ravel(), "store_beta": M.store["beta"],
+                "store_log_post": M.store["log_post"], "beta0": state0["beta"],
+                "accept": np.array([smp.accept_rate.count["accept"], smp.accept_rate.count["proposal"]])})
+    return out
+
+
 def main():
     cases = {
         "regression_n50_p3": regression_case(50, 3, 0, 6),
@@ -801,7 +831,7 @@ def main():
         "truncreg_n30_p1_lower": regression_case(30, 1, 6, 6, trunc=(np.array([[0.5]]), None)),
         "twoterm_n150_p7_q4": regression_two_term_case(150, 7, 4, 7, 5),
     }
-    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2", "round2b", "round2c"]
+    which = sys.argv[1:] or ["regression", "mh", "mh_f4", "mixture", "gmrf", "rj", "rj_moves", "replicated", "round2", "round2b", "round2c", "round2d"]
     if "regression" not in which:
         cases = {}
     if "round2" in which:
@@ -826,6 +856,9 @@ def main():
         cases.update({"mhreg_lognormal_mmala_n70_p5": mmala_regression_case(70, 5, 27, 10, 0.8, lognormal=True),
                       "mhreg_lognormal_mmala_n150_p20_eye": mmala_regression_case(150, 20, 28, 5, 0.9, weighted=False,
                                                                                   lognormal=True)})
+    if "round2d" in which:
+        cases.update({"replicated_regression_d40_p5_r6": replicated_regression_case(40, 5, 6, 61, 6),
+                      "replicated_regression_d9_p3_r25": replicated_regression_case(9, 3, 25, 62, 8)})
     if "mh" in which:
         cases.update(mh_cases())
     if "mh_f4" in which:

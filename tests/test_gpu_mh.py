@@ -343,6 +343,39 @@ def test_mmala_on_regression_coefficients(name):
     assert smp.accept_rate.count == {"accept": int(g["accept"][0]), "proposal": int(g["accept"][1])}
 
 
+@pytest.mark.parametrize("name", ["replicated_regression_d40_p5_r6", "replicated_regression_d9_p3_r25"])
+def test_mmala_on_replicated_regression(name):
+    """y of shape (dim, n_rep) with a LinearCombination mean (distribution.py:8-10, location_scale.py:238-241): compiled
+    as the single-column regression on the stacked design (engine.unreplicate); the caller's state comes back unchanged."""
+    from openmcmc_b200.distribution.distribution import Gamma
+    from openmcmc_b200.distribution.location_scale import Normal
+    from openmcmc_b200.mcmc import MCMC
+    from openmcmc_b200.model import Model
+    from openmcmc_b200.parameter import LinearCombination, ScaledMatrix
+    from openmcmc_b200.sampler.metropolis_hastings import ManifoldMALA
+
+    g = _load(name)
+    p = g["X"].shape[1]
+    mdl = Model([Normal("y", mean=LinearCombination(form={"beta": "X"}), precision=ScaledMatrix(matrix="W", scalar="tau")),
+                 Normal("beta", mean="mu", precision=ScaledMatrix(matrix="P", scalar="lam")),
+                 Gamma("tau", shape="a", rate="b")])
+    state = {"y": g["y"].copy(), "X": g["X"], "beta": g["beta0"].copy(), "W": sparse.diags(g["w"], format="csc"),
+             "tau": float(g["tau"]), "mu": np.zeros((p, 1)), "P": sparse.identity(p, format="csc"), "lam": float(g["lam"]),
+             "a": float(g["a"]), "b": float(g["b"])}
+    np.testing.assert_allclose(mdl["y"].log_p(state), g["logp0"], rtol=1e-10)
+    gr, H = mdl["y"].grad_log_p(state, "beta", hessian_required=True)
+    np.testing.assert_allclose(gr, g["grad0"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(H, g["hess0"], rtol=1e-10, atol=1e-11)
+    smp = ManifoldMALA("beta", mdl, step=np.array([[0.8]]))
+    n_iter = g["store_beta"].shape[1]
+    M = MCMC(state, [smp], model=mdl, n_burn=0, n_iter=n_iter, debug_draws={"beta": {"z": g["z"], "u": g["u"]}})
+    M.run_mcmc()
+    np.testing.assert_allclose(M.store["beta"], g["store_beta"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(M.store["log_post"], g["store_log_post"], rtol=1e-10)
+    assert smp.accept_rate.count == {"accept": int(g["accept"][0]), "proposal": int(g["accept"][1])}
+    assert M.state["y"].shape == g["y"].shape and np.array_equal(M.state["y"], g["y"])
+
+
 def test_mmala_regression_free_running_matches_conjugate_posterior():
     """Free-running mMALA on regression coefficients (fixed tau, lambda): the posterior is Gaussian in closed form, so
     per-coordinate means / variances over many chains must agree within Monte-Carlo error."""

@@ -166,6 +166,33 @@ def test_mh_lognormal_regression_chain(name):
     assert n_acc == g["accept"][0]
 
 
+@pytest.mark.parametrize("name", ["replicated_regression_d40_p5_r6", "replicated_regression_d9_p3_r25"])
+def test_mh_replicated_regression_chain(name):
+    """Replicates in the columns of y with a LinearCombination mean (distribution.py:8-10; the n_rep factor of
+    location_scale.py:238-241) == the single-column regression on the design stacked n_rep times."""
+    g = _load(name)
+    X, y, w = g["X"], g["y"], g["w"]
+    dim, n_rep = y.shape
+    Xs, ys, ws = np.tile(X, (n_rep, 1)), y.T.reshape(-1, 1), np.tile(w, n_rep)
+    p = X.shape[1]
+    terms = [mh.Term("normal_linear", data=ys, X=Xs, Q=float(g["tau"]) * np.diag(ws), transform=False),
+             mh.Term("normal_response", p1=np.zeros((p, 1)), Q=float(g["lam"]) * np.eye(p))]
+    g0, H0 = terms[0].grad_hess_analytic(g["beta0"])
+    np.testing.assert_allclose(g0, g["grad0"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(H0, g["hess0"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(terms[0].log_p(g["beta0"]), g["logp0"], rtol=1e-12)
+    theta, n_acc = g["beta0"], 0
+    from scipy import stats
+    a, b, tau = float(g["a"]), float(g["b"]), float(g["tau"])
+    lp_tau = stats.gamma.logpdf(tau, a, scale=1 / b)                    # the Gamma prior on tau is part of log_post
+    for it in range(g["store_beta"].shape[1]):
+        theta, info = mh.mmala_step(terms, theta, 0.8, g["z"][it], g["u"][it], "analytic")
+        n_acc += info["accepted"]
+        np.testing.assert_allclose(theta.ravel(), g["store_beta"][:, it], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(mh.log_p(terms, theta) + lp_tau, g["store_log_post"][it, 0], rtol=1e-10)
+    assert n_acc == g["accept"][0]
+
+
 def test_truncnorm_grid():
     g = _load("truncnorm_grid")
     x = gmrf.truncated_normal_rv(g["mean"], g["scale"], g["lower"], g["upper"], g["u"])
