@@ -317,14 +317,16 @@ class MCMC:
             return n_burn * sw + n_iter * self._stored_sweep_graph.num_kernels()
         return (n_burn + n_iter * n_thin) * sw + n_iter * store
 
-    def run_device(self, n_burn=None, n_iter=None, n_thin=None):
-        """Replay the captured sweep graph on the engine's stream (asynchronous)."""
+    def run_device(self, n_burn=None, n_iter=None, n_thin=None, restart_store=True):
+        """Replay the captured sweep graph on the engine's stream (asynchronous).  restart_store=False continues the
+        store where the previous call left it (a run split into several calls)."""
         self.prepare()
         n_burn = self.n_burn if n_burn is None else n_burn
         n_iter = self.n_iter if n_iter is None else n_iter
         n_thin = self.n_thin if n_thin is None else n_thin
         with torch.cuda.stream(self.stream):
-            self.plan.iter_counter.zero_()     # a run stores from iteration 0 again, as the reference overwrites its store
+            if restart_store:
+                self.plan.iter_counter.zero_() # a run stores from iteration 0 again, as the reference overwrites its store
             if self._streamed and n_iter > 0:
                 return self._run_streamed(n_burn, n_iter, n_thin)
             if n_thin == 1 and n_iter > 0 and getattr(self, "_stored_sweep_graph", None) is not None:
