@@ -86,3 +86,25 @@ def test_stored_sweep_graph_is_bit_identical_and_three_launches():
         assert np.array_equal(a.state[key], b.state[key]), key
     assert int(a.plan.sweep_counter.item()) == int(b.plan.sweep_counter.item()) == 15
     assert int(a.plan.iter_counter.item()) == int(b.plan.iter_counter.item()) == 12
+
+
+def test_run_split_into_calls_continues_the_store():
+    """run_device(restart_store=False): a run replayed one stored sweep per call (what bench.py does around its per-sweep
+    L2 flushes) fills the same store as one call."""
+    from openmcmc_b200 import mcmc
+    from test_gpu_stream_store import _regression
+
+    def make():
+        mdl, samplers, state = _regression(5, 120, 6, 41)
+        mdl.response = None
+        return mcmc.MCMC(state, samplers, model=mdl, n_burn=0, n_iter=7, n_thin=1, n_chains=5, seed=3)
+
+    a = make()
+    a.run_mcmc()
+    b = make()
+    b.prepare()
+    for k in range(7):
+        b.run_device(n_burn=0, n_iter=1, n_thin=1, restart_store=(k == 0))
+    b.collect()
+    for key in a.store:
+        assert np.array_equal(a.store[key], b.store[key]), key
