@@ -32,6 +32,14 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
+// -DDW_DMMA_PANEL=1: panel tiles by the tensor pipe (L(i,k) = T(i,k) L_kk^-T, the inverse transpose built by running the
+// pivot stages on an identity tile) instead of inside the pivot stages.  Correct (the parity tests pass with it) and 870
+// instructions per chain fewer, but MEASURED slower at p = 64: 0.121 against 0.114 ms -- the rank-1 updates of the panel
+// tiles are the independent work that hides the pivot chain (profiles/r02_ncu_warp64_lines.txt).
+#ifndef DW_DMMA_PANEL
+#define DW_DMMA_PANEL 0
+#endif
+constexpr bool DMMA_PANEL = DW_DMMA_PANEL != 0;
 
 __device__ __forceinline__ double wvec_at(const omc_vec_t& v, int chain, int i, double dflt) {
   return v.ptr ? v.ptr[(long long)chain * v.chain_stride + i] : dflt;
@@ -233,6 +241,11 @@ __device__ __forceinline__ void warp_chain(const omc_nn_dense_t& a, int chain, d
   bool bad = false;
 #pragma unroll
   for (int k = 0; k < PB; ++k) {
+    // DMMA_PANEL: the column operations of the 8 pivot stages run on the diagonal tile and on an identity tile E only
+    // (E becomes L_kk^-T); the tiles below follow as L(i,k) = T(i,k) E on the tensor pipe and the right-hand side as
+    // w_i -= L(i,k) w_k, instead of 8 serial rank-1 steps on every tile of the block column
+    constexpr int PANEL_END_OFF = DMMA_PANEL ? 1 : PB;
+    double E[2] = {(g == 2 * kq) ? 1.0 : 0.0, (g == 2 * kq + 1) ? 1.0 : 0.0};
 #pragma unroll 1
     for (int jq = 0; jq < 4; ++jq) {
       const bool own = kq == jq;
@@ -243,15 +256,21 @@ __device__ __forceinline__ void warp_chain(const omc_nn_dense_t& a, int chain, d
         if (!(piv > 0.0)) bad = true;
         const double rd = wrsqrt(piv);
 #pragma unroll
-        for (int i = k; i < PB; ++i) T[TI(i, k)][reg] = own ? T[TI(i, k)][reg] * rd : T[TI(i, k)][reg];
+        for (int i = k; i < (DMMA_PANEL ? k + PANEL_END_OFF : PB); ++i) T[TI(i, k)][reg] = own ? T[TI(i, k)][reg] * rd : T[TI(i, k)][reg];
+        if (DMMA_PANEL) E[reg] = own ? E[reg] * rd : E[reg];
         const double wc = shf(w[k], 4 * jj) * rd;
         if (g == jj) w[k] = wc;
         double lc0 = shf(T[TI(k, k)][reg], 8 * kq + jq);        // L[2kq][jj]
         double lc1 = shf(T[TI(k, k)][reg], 8 * kq + 4 + jq);    // L[2kq+1][jj]
         if (!(2 * kq > jj)) lc0 = 0.0;
         if (!(2 * kq + 1 > jj)) lc1 = 0.0;
+        if (DMMA_PANEL) {
+          const double le = shf(E[reg], 4 * g + jq);
+          E[0] = fma(-le, lc0, E[0]);
+          E[1] = fma(-le, lc1, E[1]);
+        }
 #pragma unroll
-        for (int i = k; i < PB; ++i) {
+        for (int i = k; i < (DMMA_PANEL ? k + PANEL_END_OFF : PB); ++i) {
           const double lg = shf(T[TI(i, k)][reg], 4 * g + jq);  // L[8i + g][8k + jj]
           T[TI(i, k)][0] = fma(-lg, lc0, T[TI(i, k)][0]);
           T[TI(i, k)][1] = fma(-lg, lc1, T[TI(i, k)][1]);
@@ -265,6 +284,33 @@ __device__ __forceinline__ void warp_chain(const omc_nn_dense_t& a, int chain, d
       }
     }
     if (k + 1 < PB) {
+      if (DMMA_PANEL) {
+        // B fragments of E: lane (g, kq), step s needs E[4s + kq][g], held by lane (4s + kq, g >> 1), register g & 1
+        double Bf[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int src = 4 * (4 * s + kq) + (g >> 1);
+          const double e0 = shf(E[0], src), e1 = shf(E[1], src);
+          Bf[s] = (g & 1) ? e1 : e0;
+        }
+        const double wk0 = shf(w[k], 4 * (2 * kq)), wk1 = shf(w[k], 4 * (2 * kq + 1));
+#pragma unroll
+        for (int i = k + 1; i < PB; ++i) {
+          double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int src = 4 * g + 2 * s + (kq >> 1);
+            const double v0 = shf(T[TI(i, k)][0], src), v1 = shf(T[TI(i, k)][1], src);
+            wdmma(c0, c1, (kq & 1) ? v1 : v0, Bf[s]);
+          }
+          T[TI(i, k)][0] = c0;
+          T[TI(i, k)][1] = c1;
+          double t = fma(c0, wk0, c1 * wk1);
+          t += shx(t, 1);
+          t += shx(t, 2);
+          w[i] -= t;
+        }
+      }
       // panel tiles as operand fragments: f_s = element [g][4s + kq] (quad-local re-layout)
       double R[PB][2];
 #pragma unroll

@@ -37,7 +37,7 @@ def dmma(c, a, b):
     return c
 
 
-def run(Q, b, z, PB):
+def run(Q, b, z, PB, dmma_panel=False):
     p = Q.shape[0]
     n = 8 * PB
     Qp, bp, zp = np.eye(n), np.zeros(n), np.zeros(n)
@@ -48,18 +48,25 @@ def run(Q, b, z, PB):
             T[i, j] = np.stack([Qp[8 * i + G, 8 * j + 2 * KQ], Qp[8 * i + G, 8 * j + 2 * KQ + 1]], axis=1)
     w = [bp[8 * i + G].copy() for i in range(PB)]
     for k in range(PB):
+        # dmma_panel: the column operations of the 8 pivot stages run on the diagonal tile and on an identity tile E only
+        # (E becomes L_kk^-T); the tiles below the diagonal are then L(i,k) = T(i,k) E on the tensor pipe, and the
+        # right-hand side follows as w_i -= L(i,k) w_k
+        E = np.stack([(G == 2 * KQ).astype(float), (G == 2 * KQ + 1).astype(float)], axis=1)
+        rows = range(k, k + 1) if dmma_panel else range(k, PB)
         for jj in range(8):
             reg, own = jj & 1, KQ == (jj >> 1)
             piv = shfl(T[k, k][:, reg], 4 * jj + (jj >> 1))
             assert np.all(piv > 0)
             rd = 1.0 / np.sqrt(piv)
-            for i in range(k, PB):
+            for i in rows:
                 T[i, k][:, reg] = np.where(own, T[i, k][:, reg] * rd, T[i, k][:, reg])
+            if dmma_panel:
+                E[:, reg] = np.where(own, E[:, reg] * rd, E[:, reg])
             wc = shfl(w[k], 4 * jj) * rd
             w[k] = np.where(G == jj, wc, w[k])
             lc0 = np.where(2 * KQ > jj, shfl(T[k, k][:, reg], 4 * (2 * KQ) + (jj >> 1)), 0.0)
             lc1 = np.where(2 * KQ + 1 > jj, shfl(T[k, k][:, reg], 4 * (2 * KQ + 1) + (jj >> 1)), 0.0)
-            for i in range(k, PB):
+            for i in rows:
                 lg = shfl(T[i, k][:, reg], 4 * G + (jj >> 1))
                 T[i, k][:, 0] -= lg * lc0
                 T[i, k][:, 1] -= lg * lc1
@@ -67,8 +74,29 @@ def run(Q, b, z, PB):
                     w[k] = np.where(G > jj, w[k] - lg * wc, w[k])
                 else:
                     w[i] = w[i] - lg * wc
+            if dmma_panel:
+                le = shfl(E[:, reg], 4 * G + (jj >> 1))
+                E[:, 0] -= le * lc0
+                E[:, 1] -= le * lc1
             # 1 / L_cc replaces L_cc on the diagonal (nothing reads L_cc again; the backward solve wants the reciprocal)
             T[k, k][:, reg] = np.where(own & (G == jj), rd, T[k, k][:, reg])
+        if dmma_panel and k + 1 < PB:
+            # B fragments of E: lane (g, kq), step s needs E[4s + kq][g], held by lane (4s + kq, g >> 1), register g & 1
+            Bf = []
+            for s in range(2):
+                src = 4 * (4 * s + KQ) + (G >> 1)
+                Bf.append(np.where(G & 1, shfl(E[:, 1], src), shfl(E[:, 0], src)))
+            wk0, wk1 = shfl(w[k], 4 * (2 * KQ)), shfl(w[k], 4 * (2 * KQ + 1))
+            for i in range(k + 1, PB):
+                A = rowfrag(T[i, k])
+                c = np.zeros((32, 2))
+                for s in range(2):
+                    c = dmma(c, A[s], Bf[s])
+                T[i, k] = c
+                t = c[:, 0] * wk0 + c[:, 1] * wk1
+                t = t + shfl(t, LANES ^ 1)
+                t = t + shfl(t, LANES ^ 2)
+                w[i] = w[i] - t
         R = {i: rowfrag(T[i, k]) for i in range(k + 1, PB)}
         for j in range(k + 1, PB):
             for i in range(j, PB):
@@ -120,4 +148,5 @@ if __name__ == "__main__":
         L = np.linalg.cholesky(Q)
         ref = np.linalg.solve(Q, b) + np.linalg.solve(L.T, z)
         got = run(Q, b, z, PB)
-        print(p, np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+        got2 = run(Q, b, z, PB, dmma_panel=True)
+        print(p, np.max(np.abs(got - ref)) / np.max(np.abs(ref)), np.max(np.abs(got2 - ref)) / np.max(np.abs(ref)))
