@@ -613,7 +613,18 @@ class MCMC:
 
         B = self._n_blocks()
         if B > 1:
-            self._run_blocked(B)
+            # the host thread is the pacemaker of the block pipeline: a generation-2 pass of Python's cycle collector in
+            # the middle of it (0.2-0.3 s in a process that has torch, scipy and a few plans loaded) stalls the uploads
+            # queued behind the block being compiled, so collection is paused for the duration of the run
+            import gc
+
+            was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                self._run_blocked(B)
+            finally:
+                if was_enabled:
+                    gc.enable()
             self._finish([sub.plan for sub in self._blocks])
             return
         t0 = time.perf_counter()
